@@ -1,0 +1,326 @@
+"""TEST INFRASTRUCTURE - CPU restatement ("port") of the reference H-bond hot path.
+
+This module is the parity oracle for the CUDA path and the `cpu_baseline` arm of `bench.py`.  It is
+NOT part of the product: only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline /
+`--impl reference` legs may import it.  The product (`cgraphs_b200.mdhbond`) never does and fails
+loudly without its CUDA library.
+
+It restates, from scratch, the algorithm of evabertalan/cgraphs `cgraphs/mdhbond`:
+
+* construction           basic.py:34-69, network.py:40-97, helpfunctions.py:30-34,44-83,107-117
+* `hbonds_in_selection`  hbond.py:96-135
+* `hbonds_in_selection_and_water_around`  hbond.py:232-289
+* angle criterion        helpfunctions.py:86-104,137-159
+* result publication     basic.py:94-98, helpfunctions.py:120-134
+
+The arithmetic of the reference lives in third-party code that is not under /root/reference:
+scipy.spatial.cKDTree (unpinned by the reference; scipy 1.18.1 in this image) for the distance
+queries and numpy (2.3.5 here) float32 ufuncs for the angle.  The reference has no tests, fixtures
+or golden vectors, so parity is pinned by executing the reference itself in the build
+container: `tests/test_oracle_vs_reference.py` runs this port against the live reference
+(`oracle/ref_harness.py`) and `tests/golden/*.json` hold outputs of the live reference generated
+by `tests/golden/make_golden.py`.
+
+Two distance back-ends are provided and tested equal: 'kdtree' issues the same cKDTree queries
+as the reference; 'brute' evaluates the predicate
+    DIST(p, q, r):  fl64(fl64(dx*dx + dy*dy) + dz*dz) <= fl64(r*r)   on float32 inputs widened to float64
+directly, which is what the CUDA kernels implement.
+
+Deliberate divergence (documented in DESIGN.md): frames with no candidate pair / no local water make
+the reference raise IndexError (hbond.py:110,254,261); the port, like the product, treats them as
+frames without bonds unless `strict=True`.
+"""
+from __future__ import annotations
+
+import itertools
+import numpy as np
+import networkx as nx
+from scipy.spatial import cKDTree
+
+DONOR_NAMES = {'OH2', 'OW', 'NE', 'NH1', 'NH2', 'ND2', 'SG', 'NE2', 'ND1', 'NZ', 'OG', 'OG1', 'NE1', 'OH',
+               'OE1', 'OE2', 'N16', 'OD1', 'OD2'}                      # helpfunctions.py:31
+ACCEPTOR_NAMES = {'OH2', 'OW', 'OD1', 'OD2', 'SG', 'OE1', 'OE2', 'ND1', 'NE2', 'SD', 'OG', 'OG1', 'OH'}  # :32
+WATER_DEFINITION = '(resname TIP3 and name OH2) or (resname HOH and name O) or (resname TIP4 and name OH2)'  # :34
+
+
+def _r_covalent(first_letter):                                          # helpfunctions.py:30
+    return {'N': 1.31, 'O': 1.31, 'P': 1.58, 'S': 1.55}.get(first_letter, 1.5)
+
+
+def _id(topo, i, detailed):                                             # helpfunctions.py:107-117
+    s = str(topo.segids[i]) + '-' + str(topo.resnames[i]) + '-' + str(int(topo.resids[i]))
+    return s + '-' + str(topo.names[i]) if detailed else s
+
+
+class PortTopology:
+    """Everything the reference constructor derives, as plain arrays/lists."""
+
+    def __init__(self, universe, selection, *, distance=3.5, cut_angle=60., start=None, stop=None, step=1,
+                 additional_donors=(), additional_acceptors=(), exclude_donors=(), exclude_acceptors=(),
+                 check_angle=True, residuewise=True, add_donors_without_hydrogen=False):
+        if selection is None:
+            raise AssertionError('No selection string.')
+        if universe is None:
+            raise AssertionError('No structure file path.')
+        topo = universe.topology
+        self.universe = universe
+        self.frame_slice = slice(start if isinstance(start, int) else None,
+                                 stop if isinstance(stop, int) else None, step)
+        self.frame_indices = list(universe.trajectory.frame_indices(self.frame_slice))
+        self.nb_frames = len(self.frame_indices)
+        sel = universe.select_atoms(selection).indices
+        if len(sel) == 0:
+            raise AssertionError('No atoms match the selection')
+        self.water_atoms = universe.select_atoms(WATER_DEFINITION).indices
+        donor_names = (DONOR_NAMES | set(additional_donors)) - set(exclude_donors)
+        acceptor_names = (ACCEPTOR_NAMES | set(additional_acceptors)) - set(exclude_acceptors)
+        # hydrogen detection uses the coordinates of frame 0 (the frame-count loop rewinds, A.1 step 5)
+        pos0 = universe.trajectory.frames.frame(0)
+
+        donors, acceptors, hydrogens, donor2h = [], [], [], []
+        for a in sel:
+            name = str(topo.names[a])
+            polar = (len(name) > 1) and name[0] in ('N', 'O')
+            if name in donor_names or polar:
+                if add_donors_without_hydrogen:
+                    donors.append(a)
+                else:
+                    rc = np.float32(_r_covalent(name[0]))
+                    found = 0
+                    for o in topo.residue_atoms(topo.resindices[a]):
+                        on = str(topo.names[o])
+                        if on[0] == 'H' or on[:2] in ('1H', '2H', '3H') or topo.types[o] == 'H':
+                            d = np.sqrt(((pos0[a] - pos0[o]) ** 2).sum())   # float32 throughout
+                            if d < rc:
+                                hydrogens.append(o)
+                                found += 1
+                    if found:
+                        donor2h.append(list(range(len(hydrogens) - found, len(hydrogens))))
+                        donors.append(a)
+            if name in acceptor_names or polar:
+                acceptors.append(a)
+        if len(donors) + len(acceptors) == 0:
+            raise AssertionError('neither donors nor acceptors in the selection')
+        self.nD, self.nA, self.nW = len(donors), len(acceptors), len(self.water_atoms)
+        self.donors = np.asarray(donors, dtype=np.int64)
+        self.acceptors = np.asarray(acceptors, dtype=np.int64)
+        self.entry_atom = np.concatenate([self.donors, self.acceptors, self.water_atoms]).astype(np.int64)
+        self.first_water = self.nD + self.nA
+        n_sel_h = len(hydrogens)
+        water_h = []
+        if not add_donors_without_hydrogen:
+            for w in self.water_atoms:
+                water_h.extend(topo.residue_atoms(topo.resindices[w])[1:])
+        if not hydrogens and not water_h and check_angle:
+            raise AssertionError('There are no possible hbond donors in the selection and no water. Since '
+                                 'check_angle is True, hydrogen is needed for the calculations!')
+        self.h_atom = np.asarray(hydrogens + water_h, dtype=np.int64)
+        self.heavy2hydrogen = (donor2h + [[] for _ in acceptors]
+                               + [[n_sel_h + i, n_sel_h + i + 1] for i in range(0, len(water_h), 2)])
+        nS = self.first_water
+        self.water_ids = [_id(topo, i, False) for i in self.water_atoms]
+        self.water_ids_atomwise = [_id(topo, i, True) for i in self.water_atoms]
+        self.all_ids = [_id(topo, i, not residuewise) for i in self.entry_atom[:nS]] + self.water_ids
+        self.all_ids_atomwise = [_id(topo, i, True) for i in self.entry_atom[:nS]] + self.water_ids_atomwise
+        self.resids = np.array([int(s.split('-')[2]) for s in self.all_ids], dtype=np.int64)
+        self.distance, self.cut_angle = distance, cut_angle
+        self.check_angle, self.residuewise = check_angle, residuewise
+
+
+def angle_deg(p1, p2, p3):
+    """helpfunctions.py:86-104 restated with explicit float32 operation order."""
+    v1 = p2 - p1
+    v2 = p3 - p2
+    d12 = (v1[:, 0] * v2[:, 0] + v1[:, 1] * v2[:, 1]) + v1[:, 2] * v2[:, 2]
+    d11 = (v1[:, 0] * v1[:, 0] + v1[:, 1] * v1[:, 1]) + v1[:, 2] * v1[:, 2]
+    d22 = (v2[:, 0] * v2[:, 0] + v2[:, 1] * v2[:, 1]) + v2[:, 2] * v2[:, 2]
+    with np.errstate(all='ignore'):
+        c = d12 / (np.sqrt(d11) * np.sqrt(d22))
+        c[c < -1.0] = -1.0
+        return np.rad2deg(np.arccos(c))
+
+
+def cos_arg(p1, p2, p3):
+    """The float32 `cos_arg` of helpfunctions.py:96-102 (before the clamp)."""
+    v1 = p2 - p1
+    v2 = p3 - p2
+    d12 = (v1[:, 0] * v2[:, 0] + v1[:, 1] * v2[:, 1]) + v1[:, 2] * v2[:, 2]
+    d11 = (v1[:, 0] * v1[:, 0] + v1[:, 1] * v1[:, 1]) + v1[:, 2] * v1[:, 2]
+    d22 = (v2[:, 0] * v2[:, 0] + v2[:, 1] * v2[:, 1]) + v2[:, 2] * v2[:, 2]
+    with np.errstate(all='ignore'):
+        return d12 / (np.sqrt(d11) * np.sqrt(d22))
+
+
+def _flatten(lists):
+    lens = np.fromiter((len(l) for l in lists), dtype=np.int64, count=len(lists))
+    i = np.repeat(np.arange(len(lists), dtype=np.int64), lens)
+    j = np.fromiter(itertools.chain.from_iterable(lists), dtype=np.int64, count=int(lens.sum()))
+    return i, j
+
+
+def _dist2_f64(a, b):
+    d = a.astype(np.float64)[:, None, :] - b.astype(np.float64)[None, :, :]
+    return (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+
+
+def ball_pairs(a, b, r, backend='kdtree'):
+    """All (i, j) with DIST(a_i, b_j, r)."""
+    if len(a) == 0 or len(b) == 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    if backend == 'kdtree':
+        return _flatten(cKDTree(a).query_ball_tree(cKDTree(b), r))
+    r2 = np.float64(r) * np.float64(r)
+    out_i, out_j = [], []
+    step = max(1, int(4e6 // max(1, len(b))))
+    for s in range(0, len(a), step):
+        i, j = np.nonzero(_dist2_f64(a[s:s + step], b) <= r2)
+        out_i.append(i + s)
+        out_j.append(j)
+    return np.concatenate(out_i), np.concatenate(out_j)
+
+
+def self_pairs(a, r, backend='kdtree'):
+    """All i < j with DIST(a_i, a_j, r)."""
+    if len(a) < 2:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    if backend == 'kdtree':
+        p = cKDTree(a).query_pairs(r, output_type='ndarray')
+        return p[:, 0].astype(np.int64), p[:, 1].astype(np.int64)
+    i, j = ball_pairs(a, a, r, 'brute')
+    keep = i < j
+    return i[keep], j[keep]
+
+
+def _angle_filter(pt, e0, e1, coords, hcoords, cut_angle, cos_threshold=None):
+    """helpfunctions.py:137-159: keep a pair if any hydrogen of either partner passes the angle test."""
+    if len(e0) == 0:
+        return e0, e1
+    h2h = pt.heavy2hydrogen
+    cnt = np.fromiter((len(h2h[a]) + len(h2h[b]) for a, b in zip(e0, e1)), dtype=np.int64, count=len(e0))
+    pair_of = np.repeat(np.arange(len(e0)), cnt)
+    hidx = np.fromiter(itertools.chain.from_iterable(
+        itertools.chain(h2h[a], h2h[b]) for a, b in zip(e0, e1)), dtype=np.int64, count=int(cnt.sum()))
+    pa = coords[e0[pair_of]]
+    pb = coords[e1[pair_of]]
+    ph = hcoords[hidx]
+    if cos_threshold is None:
+        ok = angle_deg(pb, ph, pa) <= np.float32(cut_angle)
+    else:  # the threshold form the kernels use; tested equal to the line above
+        c = cos_arg(pb, ph, pa)
+        with np.errstate(all='ignore'):
+            ok = (c >= np.float32(cos_threshold)) & (c <= np.float32(1.0))
+    keep = np.zeros(len(e0), dtype=bool)
+    keep[pair_of[ok]] = True
+    return e0[keep], e1[keep]
+
+
+def _frame_keys(pt, e0, e1, ids):
+    """hbond.py:119-127 / 271-281: orientation by resid, optional same-residue skip; returns key strings."""
+    x = np.minimum(e0, e1)
+    y = np.maximum(e0, e1)
+    check = pt.resids[x] < pt.resids[y]
+    first = np.where(check, x, y)
+    second = np.where(check, y, x)
+    keys = set()
+    for f, s in set(zip(first.tolist(), second.tolist())):
+        a, b = ids[f], ids[s]
+        if not pt.check_angle and a.split('-')[:3] == b.split('-')[:3]:
+            continue
+        keys.add(a + ':' + b)
+    return keys
+
+
+def _backbone_flags(pt):
+    return np.array([(s.split('-')[3] in ('O', 'N')) for s in pt.all_ids_atomwise], dtype=bool)
+
+
+def frame_pairs(pt, pos, method, around=None, exclude_backbone_backbone=True, backend='kdtree',
+                cos_threshold=None, strict=False):
+    """Entry pairs (col0, col1) that are H-bonds in one frame, before key building."""
+    nD, nA, fw = pt.nD, pt.nA, pt.first_water
+    coords_sel = pos[pt.entry_atom[:fw]]
+    e0 = np.zeros(0, np.int64)
+    e1 = np.zeros(0, np.int64)
+    if nD > 0 and nA > 0:
+        ia, jd = ball_pairs(pos[pt.acceptors], pos[pt.donors], pt.distance, backend)
+        if strict and len(ia) == 0:
+            raise IndexError('reference raises on frames without donor-acceptor pairs')
+        e0, e1 = ia + nD, jd
+        if exclude_backbone_backbone and len(e0):
+            bb = _backbone_flags(pt)
+            keep = ~(bb[e0] & bb[e1])
+            e0, e1 = e0[keep], e1[keep]
+    if method == 'in_selection':
+        coords = coords_sel
+    else:
+        wpos = pos[pt.water_atoms]
+        _, wj = ball_pairs(coords_sel, wpos, float(around), backend)
+        local = np.unique(wj)
+        if strict and len(local) == 0:
+            raise IndexError('reference raises on frames without local water')
+        lpos = wpos[local]
+        si, lj = ball_pairs(coords_sel, lpos, pt.distance, backend)
+        wi, wj2 = self_pairs(lpos, pt.distance, backend)
+        # candidate order of the reference: DA ++ WW ++ SW (irrelevant for the result)
+        e0 = np.concatenate([e0, local[wi] + fw, si])
+        e1 = np.concatenate([e1, local[wj2] + fw, local[lj] + fw])
+        coords = np.vstack([coords_sel, wpos])
+    if pt.check_angle:
+        e0, e1 = _angle_filter(pt, e0, e1, coords, pos[pt.h_atom], pt.cut_angle, cos_threshold)
+    return e0, e1
+
+
+class PortResult:
+    def __init__(self, pt, results):
+        self.topology = pt
+        self.initial_results = results
+        self.filtered_results = results
+        self.nb_frames = pt.nb_frames
+        self.residuewise = pt.residuewise
+        self.initial_graph = dict2graph(results, pt.residuewise)
+        self.filtered_graph = self.initial_graph
+
+
+def dict2graph(bonds, residuewise=True):
+    """helpfunctions.py:120-134."""
+    g = nx.Graph()
+    cut = 3 if residuewise else 4
+    edges = []
+    for bond in bonds:
+        a, b = bond.split(':')
+        a = '-'.join(a.split('-')[:cut])
+        b = '-'.join(b.split('-')[:cut])
+        if int(a.split('-')[2]) > int(b.split('-')[2]):
+            a, b = b, a
+        if a != b:
+            edges.append((a, b))
+    g.add_edges_from(edges)
+    return g
+
+
+def run(universe, selection, method='in_selection', around=3.5, exclude_backbone_backbone=True,
+        backend='kdtree', cos_threshold=None, strict=False, frame_range=None, **ctor):
+    """Run the port; returns a PortResult whose `initial_results` is `dict[str, bool[nb_frames]]`."""
+    pt = PortTopology(universe, selection, **ctor)
+    if method == 'in_selection':
+        if pt.nA == 0:
+            raise AssertionError('No acceptors in the selection')
+        if pt.nD == 0:
+            raise AssertionError('No donors in the selection')
+        ids = pt.all_ids                                          # hbond.py:122 (always _all_ids)
+    else:
+        ids = pt.all_ids if pt.residuewise else pt.all_ids_atomwise   # hbond.py:276-277
+    results = {}
+    frames = universe.trajectory.frames
+    todo = pt.frame_indices
+    for col, f in enumerate(todo):
+        if frame_range is not None and not (frame_range[0] <= col < frame_range[1]):
+            continue
+        pos = np.asarray(frames.frame(f), dtype=np.float32)
+        e0, e1 = frame_pairs(pt, pos, method, around, exclude_backbone_backbone, backend, cos_threshold, strict)
+        for key in _frame_keys(pt, e0, e1, ids):
+            row = results.get(key)
+            if row is None:
+                row = results[key] = np.zeros(pt.nb_frames, dtype=bool)
+            row[col] = True
+    return PortResult(pt, results)

@@ -1,0 +1,111 @@
+"""TEST INFRASTRUCTURE - live-reference harness (not part of the product path).
+
+Imports the reference's own ``mdhbond`` package, unmodified, from ``$CGRAPHS_REF`` (default
+``/root/reference/cgraphs``) so that its ``HbondAnalysis`` can be executed in this container and used
+to (a) validate the CPU restatement in ``oracle/hbond_port.py`` and (b) generate the golden vectors
+under ``tests/golden/`` (``tests/golden/make_golden.py``).
+
+The reference hard-imports ``MDAnalysis`` and ``matplotlib`` (``cgraphs/mdhbond/basic.py:24-30``,
+``hbond.py:25-35``, ``network.py:24-34``); neither is installable offline.  They are
+replaced in ``sys.modules`` by thin stubs: ``MDAnalysis.Universe(structure)`` returns the
+``cgraphs_b200.universe.Universe`` it is given, ``MDAnalysis.core.groups.AtomGroup`` is the array
+backed AtomGroup of that module, and the matplotlib names only need to exist.
+
+``/root/reference`` does not exist on the GPU box: nothing that runs there may import this module.
+Only ``tests/`` (CPU side) and ``tests/golden/make_golden.py`` do.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+REF_DEFAULT = "/root/reference/cgraphs"
+
+
+def reference_available(path=None):
+    path = path or os.environ.get("CGRAPHS_REF", REF_DEFAULT)
+    return os.path.isfile(os.path.join(path, "mdhbond", "hbond.py"))
+
+
+def _install_stubs():
+    from cgraphs_b200 import universe as uni
+
+    if "MDAnalysis" not in sys.modules or getattr(sys.modules["MDAnalysis"], "_hbgpu_stub", False):
+        mda = types.ModuleType("MDAnalysis")
+        mda._hbgpu_stub = True
+
+        def Universe(structure, trajectories=None, *a, **k):
+            if isinstance(structure, uni.Universe):
+                return structure
+            raise RuntimeError("stub MDAnalysis: pass a cgraphs_b200.universe.Universe as `structure`")
+
+        mda.Universe = Universe
+        core = types.ModuleType("MDAnalysis.core")
+        groups = types.ModuleType("MDAnalysis.core.groups")
+        groups.AtomGroup = uni.AtomGroup
+        ag_mod = types.ModuleType("MDAnalysis.core.AtomGroup")
+        ag_mod.AtomGroup = uni.AtomGroup
+        core.groups = groups
+        core.AtomGroup = ag_mod
+        mda.core = core
+        mda.AtomGroup = uni.AtomGroup
+        sys.modules["MDAnalysis"] = mda
+        sys.modules["MDAnalysis.core"] = core
+        sys.modules["MDAnalysis.core.groups"] = groups
+        sys.modules["MDAnalysis.core.AtomGroup"] = ag_mod
+    if "matplotlib" not in sys.modules:
+        mpl = types.ModuleType("matplotlib")
+        mpl._hbgpu_stub = True
+        plt = types.ModuleType("matplotlib.pyplot")
+        ticker = types.ModuleType("matplotlib.ticker")
+        ticker.MaxNLocator = type("MaxNLocator", (), {"__init__": lambda self, *a, **k: None})
+        mpl.pyplot = plt
+        mpl.ticker = ticker
+        mpl.use = lambda *a, **k: None
+        sys.modules["matplotlib"] = mpl
+        sys.modules["matplotlib.pyplot"] = plt
+        sys.modules["matplotlib.ticker"] = ticker
+
+
+_REF = None
+
+
+def load_reference(path=None):
+    """Return the reference's ``mdhbond`` package (imported once)."""
+    global _REF
+    if _REF is not None:
+        return _REF
+    path = path or os.environ.get("CGRAPHS_REF", REF_DEFAULT)
+    if not reference_available(path):
+        raise ImportError("reference mdhbond not found under %s" % path)
+    _install_stubs()
+    # import `mdhbond` as a top-level package, skipping cgraphs/__init__.py (tkinter, Bio, sklearn GUI imports)
+    spec = importlib.util.spec_from_file_location(
+        "_cgraphs_ref_mdhbond", os.path.join(path, "mdhbond", "__init__.py"),
+        submodule_search_locations=[os.path.join(path, "mdhbond")])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["_cgraphs_ref_mdhbond"] = mod
+    spec.loader.exec_module(mod)
+    _REF = mod
+    return mod
+
+
+def run_reference(universe, selection, method="in_selection", around=3.5, exclude_backbone_backbone=True,
+                  **ctor_kwargs):
+    """Run the reference HbondAnalysis on a stub Universe and return the analysis object."""
+    ref = load_reference()
+    hba = ref.HbondAnalysis(selection, universe, **ctor_kwargs)
+    if method == "in_selection":
+        hba.set_hbonds_in_selection(exclude_backbone_backbone=exclude_backbone_backbone)
+    elif method == "water_around":
+        hba.set_hbonds_in_selection_and_water_around(around, exclude_backbone_backbone=exclude_backbone_backbone)
+    else:
+        raise ValueError(method)
+    return hba
+
+
+def results_bytes(results):
+    """Canonical comparable form of a result dict (SURVEY 8c parity definition)."""
+    return {k: bytes(memoryview(v.astype(bool))) for k, v in results.items()}
