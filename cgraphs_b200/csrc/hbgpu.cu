@@ -1,0 +1,1468 @@
+// libhbgpu - hand-written sm_100a kernels + C ABI for the cgraphs / Bridge H-bond hot path.
+//
+// Replaces the per-frame body of HbondAnalysis.set_hbonds_in_selection (reference
+// cgraphs/mdhbond/hbond.py:96-135) and set_hbonds_in_selection_and_water_around (hbond.py:232-289),
+// including check_angle (helpfunctions.py:137-159) and the result[key][frame] = True bookkeeping.
+//
+// Pipeline per batch of frames (all frames of a batch are processed by every kernel launch):
+//   K0 init_frames        reset per-frame bounding boxes / counters
+//   K1 gather_sel         selection points -> float4 + per-frame bounding box
+//   K2 grid_setup         per-frame cell-grid geometry (non-periodic bounding-box grid)
+//   K3 count / K4 scan / K5 scatter   counting sort of points into cells (cell list)
+//   K6 local_water        waters within around_radius of any selection entry (hbond.py:249-252)
+//   K7 pairs              half-shell neighbour search, exact DIST and ANG predicates, key build,
+//                         insert into the bond hash table, set the bit (bond, frame)
+// Finalize: compact the table, radix-sort the keys, gather occupancy rows in key order.
+//
+// Exactness:
+//   DIST: float32 coordinates widened to double, s = fl(fl(dx*dx + dy*dy) + dz*dz) <= fl(r*r), inclusive.
+//   ANG : float32 chain with individually rounded operations in the reference's order, compared as
+//         cos_threshold <= c <= 1 (c < -1 clamps to -1), cos_threshold calibrated on the host.
+// No fast-math, no FMA contraction on these paths (explicit _rn intrinsics).
+#include "../../include/hbgpu.h"
+
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#define HB_VERSION "hbgpu 0.1 (sm_100a)"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// device-side views
+// ------------------------------------------------------------------------------------------------
+struct DevTopo {
+    int n_systems;
+    const long long* sys_atom_off;
+    const int* sys_sel_off;
+    const int* sys_wat_off;
+    const int* sel_atom;
+    const int* sel_don;
+    const int* sel_acc;
+    const int* sel_wat;
+    const unsigned char* sel_bb;
+    const int* wat_atom;
+    const int* wat_ent;
+    const int* ent_group;
+    const int* ent_resid;
+    const int* ent_residue;
+    const int* ent_h_off;
+    const int* ent_h_atom;
+};
+
+struct FrameGrid {      // geometry of one cell grid of one frame
+    float ox, oy, oz;   // origin
+    float inv;          // 1 / cell edge
+    int nx, ny, nz;
+    int ncell;
+};
+
+struct FrameState {     // per frame slot of a batch
+    int bb_min[3];      // ordered-int encoded float min / max of the selection points
+    int bb_max[3];
+    int n_local;        // local waters appended so far
+    int n_points;       // points in the pair-search set (selection + local waters)
+    FrameGrid g1;       // selection grid used by the local-water test (cell >= around_radius)
+    FrameGrid g2;       // pair-search grid (cell >= distance)
+    float lo[3], hi[3]; // decoded bounding box of the selection points
+};
+
+struct BatchView {
+    const float* xyz;        // coordinates of the batch
+    long long frame0;        // global index (occupancy column) of the first frame of the batch
+    int n_frames;            // frames in this batch
+    long long atoms_per_frame;   // trajectory mode stride (atoms)
+    long long atom_base;     // structure_batch: sys_atom_off of the first system of the batch
+    int structure_batch;
+    int max_sel, max_wat;    // per-frame capacities of the scratch arrays
+    int cell_cap;            // cells per grid per frame (capacity)
+    FrameState* fs;
+    float4* selpos;          // [n_frames][max_sel]
+    float4* sorted1;         // [n_frames][max_sel]          selection points in g1 cell order
+    float4* lw;              // [n_frames][max_wat]          local waters (unordered)
+    float4* sorted2;         // [n_frames][max_sel+max_wat]  pair-search points in g2 cell order
+    int* cells1;             // [n_frames][cell_cap+1]
+    int* cells2;             // [n_frames][cell_cap+1]
+};
+
+struct RunParams {
+    double r2;               // fl(distance*distance)
+    double around2;          // fl(around*around)
+    float r2f_hi;            // float prefilter bounds (slightly above the double thresholds)
+    float around2f_hi;
+    float cell1;             // cell edge of g1
+    float cell2;             // cell edge of g2
+    float around_f;          // around_radius rounded up a little (bounding-box dilation)
+    float cos_threshold;
+    int check_angle;
+    int excl_bb;
+    int method;
+};
+
+struct BondTable {
+    unsigned long long* keys;   // open addressing, EMPTY = ~0
+    unsigned int* bits;         // [capacity][wpr]
+    unsigned int mask;          // capacity - 1
+    int wpr;                    // 32-bit words per row
+    int* n_keys;
+    int* overflow;
+    unsigned long long* n_hits;
+};
+
+#define EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+#define WATER_TAG 0x40000000
+
+__device__ __forceinline__ int f2ord(float f) {
+    int i = __float_as_int(f);
+    return i ^ ((i >> 31) & 0x7fffffff);
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
+
+__device__ __forceinline__ const float* frame_xyz(const BatchView& bv, const DevTopo& tp, int b, int& sys) {
+    if (bv.structure_batch) {
+        sys = (int)(bv.frame0 + b);
+        return bv.xyz + 3ll * (tp.sys_atom_off[sys] - bv.atom_base);
+    }
+    sys = 0;
+    return bv.xyz + 3ll * bv.atoms_per_frame * b;
+}
+
+__device__ __forceinline__ int cell_coord(float x, float o, float inv, int n) {
+    int c = (int)floorf((x - o) * inv);
+    return min(max(c, 0), n - 1);
+}
+__device__ __forceinline__ int cell_of(const FrameGrid& g, float x, float y, float z) {
+    int cx = cell_coord(x, g.ox, g.inv, g.nx);
+    int cy = cell_coord(y, g.oy, g.inv, g.ny);
+    int cz = cell_coord(z, g.oz, g.inv, g.nz);
+    return (cz * g.ny + cy) * g.nx + cx;
+}
+
+// DIST predicate, SURVEY A.2 / F2 (scipy cKDTree semantics on float32 inputs)
+__device__ __forceinline__ bool dist_le(float ax, float ay, float az, float bx, float by, float bz, double r2) {
+    double dx = (double)ax - (double)bx;
+    double dy = (double)ay - (double)by;
+    double dz = (double)az - (double)bz;
+    double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    return s <= r2;
+}
+__device__ __forceinline__ float dist2f(float ax, float ay, float az, float bx, float by, float bz) {
+    float dx = ax - bx, dy = ay - by, dz = az - bz;
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// ANG predicate, SURVEY A.2 / F3 (helpfunctions.py:96-104,155): b = pair partner, h = hydrogen, a = other partner
+__device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
+}
+__device__ __forceinline__ bool ang_ok(float bx, float by, float bz, float hx, float hy, float hz, float ax,
+                                       float ay, float az, float cthr) {
+    float v1x = __fsub_rn(hx, bx), v1y = __fsub_rn(hy, by), v1z = __fsub_rn(hz, bz);
+    float v2x = __fsub_rn(ax, hx), v2y = __fsub_rn(ay, hy), v2z = __fsub_rn(az, hz);
+    float d12 = dot3_rn(v1x, v1y, v1z, v2x, v2y, v2z);
+    float d11 = dot3_rn(v1x, v1y, v1z, v1x, v1y, v1z);
+    float d22 = dot3_rn(v2x, v2y, v2z, v2x, v2y, v2z);
+    float den = __fmul_rn(__fsqrt_rn(d11), __fsqrt_rn(d22));
+    float c = __fdiv_rn(d12, den);
+    if (c < -1.0f) c = -1.0f;
+    return (c >= cthr) && (c <= 1.0f);   // NaN fails both
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: reset per-frame state
+// ------------------------------------------------------------------------------------------------
+__global__ void k_init_frames(BatchView bv) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= bv.n_frames) return;
+    FrameState& f = bv.fs[b];
+    for (int k = 0; k < 3; ++k) {
+        f.bb_min[k] = 0x7fffffff;
+        f.bb_max[k] = (int)0x80000000;
+    }
+    f.n_local = 0;
+    f.n_points = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: gather selection points, per-frame bounding box
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_sel(BatchView bv, DevTopo tp) {
+    int b = blockIdx.y;
+    int sys;
+    const float* xyz = frame_xyz(bv, tp, b, sys);
+    int s0 = tp.sys_sel_off[sys], s1 = tp.sys_sel_off[sys + 1];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float x = 0.f, y = 0.f, z = 0.f;
+    bool live = (s0 + i) < s1;
+    if (live) {
+        const float* p = xyz + 3ll * tp.sel_atom[s0 + i];
+        x = p[0]; y = p[1]; z = p[2];
+        bv.selpos[(size_t)b * bv.max_sel + i] = make_float4(x, y, z, __int_as_float(i));
+    }
+    float mn[3] = {live ? x : INFINITY, live ? y : INFINITY, live ? z : INFINITY};
+    float mx[3] = {live ? x : -INFINITY, live ? y : -INFINITY, live ? z : -INFINITY};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0 && mn[0] <= mx[0]) {
+        FrameState& f = bv.fs[b];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            atomicMin(&f.bb_min[k], f2ord(mn[k]));
+            atomicMax(&f.bb_max[k], f2ord(mx[k]));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: grid geometry. g1 covers the selection bounding box with one padding cell on every side so that
+// every water inside the dilated box maps to a valid cell; g2 covers the dilated box.
+// Cell edges carry a 1e-3 relative margin over the cut-off so float32 binning can never separate a
+// true neighbour pair by more than one cell; grids are capped at 1024 cells per axis and at
+// cell_cap cells in total by coarsening (coarser cells stay correct with a 27-cell neighbourhood).
+// ------------------------------------------------------------------------------------------------
+__device__ void make_grid(FrameGrid& g, const float* lo, const float* hi, float pad, float cell, int cap) {
+    float ext[3];
+    bool finite = true;
+    for (int k = 0; k < 3; ++k) {
+        ext[k] = (hi[k] - lo[k]) + 2.f * pad;
+        finite = finite && isfinite(ext[k]) && ext[k] >= 0.f;
+    }
+    g.ox = lo[0] - pad; g.oy = lo[1] - pad; g.oz = lo[2] - pad;
+    if (!finite) { g.inv = 0.f; g.nx = g.ny = g.nz = 1; g.ncell = 1; g.ox = g.oy = g.oz = 0.f; return; }
+    for (int it = 0; it < 64; ++it) {
+        int n[3];
+        double tot = 1.0;
+        bool ok = true;
+        for (int k = 0; k < 3; ++k) {
+            float q = floorf(ext[k] / cell) + 1.f;
+            if (q > 1024.f) ok = false;
+            n[k] = (int)fminf(q, 1024.f);
+            tot *= (double)n[k];
+        }
+        if (ok && tot <= (double)cap) {
+            g.nx = n[0]; g.ny = n[1]; g.nz = n[2]; g.ncell = n[0] * n[1] * n[2];
+            g.inv = 1.0f / cell;
+            return;
+        }
+        cell *= 1.2f;
+    }
+    g.inv = 0.f; g.nx = g.ny = g.nz = 1; g.ncell = 1;
+}
+
+__global__ void k_grid_setup(BatchView bv, RunParams rp) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= bv.n_frames) return;
+    FrameState& f = bv.fs[b];
+    for (int k = 0; k < 3; ++k) {
+        f.lo[k] = ord2f(f.bb_min[k]);
+        f.hi[k] = ord2f(f.bb_max[k]);
+    }
+    if (rp.method == HB_METHOD_WATER_AROUND) {
+        make_grid(f.g1, f.lo, f.hi, rp.cell1, rp.cell1, bv.cell_cap);
+        make_grid(f.g2, f.lo, f.hi, rp.around_f, rp.cell2, bv.cell_cap);
+    } else {
+        make_grid(f.g2, f.lo, f.hi, 0.f, rp.cell2, bv.cell_cap);
+        f.g1 = f.g2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3-K5: counting sort of a point list into the cells of a grid. which = 1: selection points -> g1;
+// which = 2: selection points ++ local waters -> g2.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool load_point(const BatchView& bv, const DevTopo& tp, int b, int which, int i, float4& p) {
+    int sys = bv.structure_batch ? (int)(bv.frame0 + b) : 0;
+    int nsel = tp.sys_sel_off[sys + 1] - tp.sys_sel_off[sys];
+    if (i < nsel) { p = bv.selpos[(size_t)b * bv.max_sel + i]; return true; }
+    if (which == 1) return false;
+    int j = i - nsel;
+    if (j >= bv.fs[b].n_local) return false;
+    p = bv.lw[(size_t)b * bv.max_wat + j];
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k_count(BatchView bv, DevTopo tp, int which) {
+    int b = blockIdx.y;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float4 p;
+    if (!load_point(bv, tp, b, which, i, p)) return;
+    const FrameGrid& g = which == 1 ? bv.fs[b].g1 : bv.fs[b].g2;
+    int* cells = (which == 1 ? bv.cells1 : bv.cells2) + (size_t)b * (bv.cell_cap + 1);
+    atomicAdd(&cells[cell_of(g, p.x, p.y, p.z)], 1);
+}
+
+// exclusive scan of the per-cell counts of one frame (one block per frame), in place
+__global__ void __launch_bounds__(1024) k_scan(BatchView bv, int which) {
+    int b = blockIdx.x;
+    const FrameGrid& g = which == 1 ? bv.fs[b].g1 : bv.fs[b].g2;
+    int* cells = (which == 1 ? bv.cells1 : bv.cells2) + (size_t)b * (bv.cell_cap + 1);
+    __shared__ int warp_sum[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    int n = g.ncell;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = i < n ? cells[i] : 0;
+        int s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        if (lane == 31) warp_sum[w] = s;
+        __syncthreads();
+        if (w == 0) {
+            int t = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int u = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += u;
+            }
+            warp_sum[lane] = t;
+        }
+        __syncthreads();
+        int off = carry + (w ? warp_sum[w - 1] : 0);
+        if (i < n) cells[i] = off + s - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warp_sum[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        cells[n] = carry;
+        if (which == 2) bv.fs[b].n_points = carry;
+    }
+}
+
+// after this kernel cells[c] holds the END of cell c; its start is cells[c-1] (0 for c = 0)
+__global__ void __launch_bounds__(256) k_scatter(BatchView bv, DevTopo tp, int which) {
+    int b = blockIdx.y;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float4 p;
+    if (!load_point(bv, tp, b, which, i, p)) return;
+    const FrameGrid& g = which == 1 ? bv.fs[b].g1 : bv.fs[b].g2;
+    int* cells = (which == 1 ? bv.cells1 : bv.cells2) + (size_t)b * (bv.cell_cap + 1);
+    int pos = atomicAdd(&cells[cell_of(g, p.x, p.y, p.z)], 1);
+    if (which == 1) bv.sorted1[(size_t)b * bv.max_sel + pos] = p;
+    else bv.sorted2[(size_t)b * (bv.max_sel + bv.max_wat) + pos] = p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: local waters = waters with DIST <= around_radius to any selection entry (hbond.py:249-252)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_local_water(BatchView bv, DevTopo tp, RunParams rp) {
+    int b = blockIdx.y;
+    int sys;
+    const float* xyz = frame_xyz(bv, tp, b, sys);
+    int w0 = tp.sys_wat_off[sys], w1 = tp.sys_wat_off[sys + 1];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const FrameState& f = bv.fs[b];
+    bool local = false;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (w0 + i < w1) {
+        const float* p = xyz + 3ll * tp.wat_atom[w0 + i];
+        x = p[0]; y = p[1]; z = p[2];
+        float a = rp.around_f;
+        bool inside = x >= f.lo[0] - a && x <= f.hi[0] + a && y >= f.lo[1] - a && y <= f.hi[1] + a &&
+                      z >= f.lo[2] - a && z <= f.hi[2] + a;
+        if (inside) {
+            const FrameGrid& g = f.g1;
+            const int* cells = bv.cells1 + (size_t)b * (bv.cell_cap + 1);
+            const float4* pts = bv.sorted1 + (size_t)b * bv.max_sel;
+            int cx = cell_coord(x, g.ox, g.inv, g.nx);
+            int cy = cell_coord(y, g.oy, g.inv, g.ny);
+            int cz = cell_coord(z, g.oz, g.inv, g.nz);
+            for (int zz = max(cz - 1, 0); zz <= min(cz + 1, g.nz - 1) && !local; ++zz)
+                for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.ny - 1) && !local; ++yy) {
+                    int c_lo = (zz * g.ny + yy) * g.nx + max(cx - 1, 0);
+                    int c_hi = (zz * g.ny + yy) * g.nx + min(cx + 1, g.nx - 1);
+                    int s = c_lo ? cells[c_lo - 1] : 0;
+                    int e = cells[c_hi];
+                    for (int q = s; q < e; ++q) {
+                        float4 sp = pts[q];
+                        if (dist2f(x, y, z, sp.x, sp.y, sp.z) <= rp.around2f_hi &&
+                            dist_le(x, y, z, sp.x, sp.y, sp.z, rp.around2)) { local = true; break; }
+                    }
+                }
+        }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, local);
+    if (m) {
+        int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&bv.fs[b].n_local, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (local) {
+            int pos = base + __popc(m & ((1u << lane) - 1u));
+            bv.lw[(size_t)b * bv.max_wat + pos] = make_float4(x, y, z, __int_as_float(WATER_TAG | i));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bond table: insert key, set bit
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned hash64(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return (unsigned)k;
+}
+
+__device__ __forceinline__ void record_bond(const BondTable& bt, unsigned long long key, long long frame) {
+    unsigned h = hash64(key) & bt.mask;
+    for (unsigned probe = 0; probe <= bt.mask; ++probe) {
+        unsigned long long cur = bt.keys[h];
+        if (cur == EMPTY_KEY) {
+            cur = atomicCAS(&bt.keys[h], EMPTY_KEY, key);
+            if (cur == EMPTY_KEY) { atomicAdd(bt.n_keys, 1); cur = key; }
+        }
+        if (cur == key) {
+            atomicOr(&bt.bits[(size_t)h * bt.wpr + (frame >> 5)], 1u << (frame & 31));
+            return;
+        }
+        h = (h + 1) & bt.mask;
+    }
+    atomicExch(bt.overflow, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: pair search
+// ------------------------------------------------------------------------------------------------
+struct PointInfo {
+    int don, acc, wat;   // global entry indices or -1
+    int bb;
+    float x, y, z;
+};
+
+__device__ __forceinline__ void load_info(const DevTopo& tp, const RunParams& rp, int sys, float4 p, PointInfo& o) {
+    int id = __float_as_int(p.w);
+    o.x = p.x; o.y = p.y; o.z = p.z;
+    if (id & WATER_TAG) {
+        o.don = -1; o.acc = -1; o.bb = 0;
+        o.wat = tp.wat_ent[tp.sys_wat_off[sys] + (id & ~WATER_TAG)];
+    } else {
+        int s = tp.sys_sel_off[sys] + id;
+        o.don = tp.sel_don[s];
+        o.acc = tp.sel_acc[s];
+        o.wat = rp.method == HB_METHOD_WATER_AROUND ? tp.sel_wat[s] : -1;
+        o.bb = tp.sel_bb[s];
+    }
+}
+
+// any hydrogen of entry `e` (owned by point H) with ANG(other, h, owner) satisfied
+__device__ __forceinline__ bool any_h(const DevTopo& tp, const float* xyz, int e, const PointInfo& owner,
+                                      const PointInfo& other, float cthr) {
+    int s = tp.ent_h_off[e], t = tp.ent_h_off[e + 1];
+    for (int k = s; k < t; ++k) {
+        const float* h = xyz + 3ll * tp.ent_h_atom[k];
+        if (ang_ok(other.x, other.y, other.z, h[0], h[1], h[2], owner.x, owner.y, owner.z, cthr)) return true;
+    }
+    return false;
+}
+
+__device__ __forceinline__ void emit(const DevTopo& tp, const RunParams& rp, const BondTable& bt, long long frame,
+                                     int e0, int e1, int& nhit) {
+    int x = min(e0, e1), y = max(e0, e1);
+    bool chk = tp.ent_resid[x] < tp.ent_resid[y];      // hbond.py:120-122
+    int first = chk ? x : y, second = chk ? y : x;
+    if (!rp.check_angle && tp.ent_residue[first] == tp.ent_residue[second]) return;   // hbond.py:125-127
+    unsigned long long key = ((unsigned long long)(unsigned)tp.ent_group[first] << 32) |
+                             (unsigned long long)(unsigned)tp.ent_group[second];
+    ++nhit;
+    record_bond(bt, key, frame);
+}
+
+// All entry pairs generated by the point pair (P, Q), P != Q as points
+__device__ void process_pair(const DevTopo& tp, const RunParams& rp, const BondTable& bt, const float* xyz,
+                             long long frame, const PointInfo& P, const PointInfo& Q, int& nhit) {
+    const bool ang = rp.check_angle != 0;
+    const float ct = rp.cos_threshold;
+    // lazily evaluated "some hydrogen of this entry passes" flags; -1 = not evaluated
+    int pd = -1, qd = -1, pw = -1, qw = -1;
+    auto PD = [&]() { if (pd < 0) pd = (!ang) || any_h(tp, xyz, P.don, P, Q, ct); return pd; };
+    auto QD = [&]() { if (qd < 0) qd = (!ang) || any_h(tp, xyz, Q.don, Q, P, ct); return qd; };
+    auto PW = [&]() { if (pw < 0) pw = (!ang) || any_h(tp, xyz, P.wat, P, Q, ct); return pw; };
+    auto QW = [&]() { if (qw < 0) qw = (!ang) || any_h(tp, xyz, Q.wat, Q, P, ct); return qw; };
+    const bool bb_skip = rp.excl_bb && P.bb && Q.bb;
+    if (!bb_skip) {
+        if (P.acc >= 0 && Q.don >= 0 && QD()) emit(tp, rp, bt, frame, P.acc, Q.don, nhit);
+        if (Q.acc >= 0 && P.don >= 0 && PD()) emit(tp, rp, bt, frame, Q.acc, P.don, nhit);
+    }
+    if (P.wat >= 0 && Q.wat >= 0 && (PW() || QW())) emit(tp, rp, bt, frame, P.wat, Q.wat, nhit);
+    if (Q.wat >= 0) {
+        if (P.don >= 0 && (PD() || QW())) emit(tp, rp, bt, frame, P.don, Q.wat, nhit);
+        if (P.acc >= 0 && QW()) emit(tp, rp, bt, frame, P.acc, Q.wat, nhit);
+    }
+    if (P.wat >= 0) {
+        if (Q.don >= 0 && (QD() || PW())) emit(tp, rp, bt, frame, Q.don, P.wat, nhit);
+        if (Q.acc >= 0 && PW()) emit(tp, rp, bt, frame, Q.acc, P.wat, nhit);
+    }
+}
+
+// Entry pairs of a point with itself (distance 0): acceptor-donor and selection-water entries of one atom
+__device__ void process_self(const DevTopo& tp, const RunParams& rp, const BondTable& bt, const float* xyz,
+                             long long frame, const PointInfo& P, int& nhit) {
+    const bool ang = rp.check_angle != 0;
+    const float ct = rp.cos_threshold;
+    bool need = (P.acc >= 0 && P.don >= 0) || (P.wat >= 0 && (P.don >= 0 || P.acc >= 0));
+    if (!need) return;
+    bool pd = P.don >= 0 ? ((!ang) || any_h(tp, xyz, P.don, P, P, ct)) : false;
+    bool pw = P.wat >= 0 ? ((!ang) || any_h(tp, xyz, P.wat, P, P, ct)) : false;
+    if (P.acc >= 0 && P.don >= 0 && !(rp.excl_bb && P.bb) && pd) emit(tp, rp, bt, frame, P.acc, P.don, nhit);
+    if (P.wat >= 0) {
+        if (P.don >= 0 && (pd || pw)) emit(tp, rp, bt, frame, P.don, P.wat, nhit);
+        if (P.acc >= 0 && pw) emit(tp, rp, bt, frame, P.acc, P.wat, nhit);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_pairs(BatchView bv, DevTopo tp, RunParams rp, BondTable bt) {
+    int b = blockIdx.y;
+    const FrameState& f = bv.fs[b];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (blockIdx.x * blockDim.x >= f.n_points) return;
+    int nhit = 0;
+    if (i < f.n_points) {
+    int sys;
+    const float* xyz = frame_xyz(bv, tp, b, sys);
+    const FrameGrid& g = f.g2;
+    const int* cells = bv.cells2 + (size_t)b * (bv.cell_cap + 1);
+    const float4* pts = bv.sorted2 + (size_t)b * (bv.max_sel + bv.max_wat);
+    long long frame = bv.frame0 + b;
+    float4 p4 = pts[i];
+    PointInfo P;
+    load_info(tp, rp, sys, p4, P);
+    process_self(tp, rp, bt, xyz, frame, P, nhit);
+    int cx = cell_coord(P.x, g.ox, g.inv, g.nx);
+    int cy = cell_coord(P.y, g.oy, g.inv, g.ny);
+    int cz = cell_coord(P.z, g.oz, g.inv, g.nz);
+    // half shell: the rest of the own cell and cell x+1, then rows (y+1, z) and (y-1..y+1, z+1), x-1..x+1
+    for (int run = 0; run < 5; ++run) {
+        int s, e;
+        if (run == 0) {
+            int c_hi = (cz * g.ny + cy) * g.nx + min(cx + 1, g.nx - 1);
+            s = i + 1;
+            e = cells[c_hi];
+        } else {
+            int yy = run == 1 ? cy + 1 : cy + (run - 3);
+            int zz = run == 1 ? cz : cz + 1;
+            if (yy < 0 || yy >= g.ny || zz >= g.nz) continue;
+            int c_lo = (zz * g.ny + yy) * g.nx + max(cx - 1, 0);
+            int c_hi = (zz * g.ny + yy) * g.nx + min(cx + 1, g.nx - 1);
+            s = c_lo ? cells[c_lo - 1] : 0;
+            e = cells[c_hi];
+        }
+        for (int q = s; q < e; ++q) {
+            float4 q4 = pts[q];
+            if (dist2f(P.x, P.y, P.z, q4.x, q4.y, q4.z) > rp.r2f_hi) continue;
+            if (!dist_le(P.x, P.y, P.z, q4.x, q4.y, q4.z, rp.r2)) continue;
+            PointInfo Q;
+            load_info(tp, rp, sys, q4, Q);
+            process_pair(tp, rp, bt, xyz, frame, P, Q, nhit);
+        }
+    }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nhit += __shfl_xor_sync(0xffffffffu, nhit, o);
+    if ((threadIdx.x & 31) == 0 && nhit) atomicAdd(bt.n_hits, (unsigned long long)nhit);
+}
+
+// ------------------------------------------------------------------------------------------------
+// finalize kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fill_u64(unsigned long long* p, size_t n, unsigned long long v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+__global__ void k_compact(BondTable bt, unsigned long long* out_keys, unsigned* out_slots, int* counter) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = i <= bt.mask && bt.keys[i] != EMPTY_KEY;
+    unsigned m = __ballot_sync(0xffffffffu, live);
+    if (!m) return;
+    int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (live) {
+        int pos = base + __popc(m & ((1u << lane) - 1u));
+        out_keys[pos] = bt.keys[i];
+        out_slots[pos] = i;
+    }
+}
+
+// LSD radix sort, 8 bits per pass, of (key64, slot32) pairs. One block handles a tile; stability inside
+// a tile comes from processing the tile in warp-sized strips in order.
+#define RS_TILE 2048
+__global__ void __launch_bounds__(256) k_rs_hist(const unsigned long long* keys, int n, int shift, unsigned* hist /*[256][nblk]*/) {
+    __shared__ unsigned h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    int base = blockIdx.x * RS_TILE;
+    for (int i = threadIdx.x; i < RS_TILE && base + i < n; i += 256)
+        atomicAdd(&h[(unsigned)(keys[base + i] >> shift) & 255u], 1u);
+    __syncthreads();
+    hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(1024) k_rs_scan(unsigned* hist, size_t n) {   // single block exclusive scan
+    __shared__ unsigned warp_sum[32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (size_t base = 0; base < n; base += 1024) {
+        size_t i = base + threadIdx.x;
+        unsigned v = i < n ? hist[i] : 0, s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+        if (lane == 31) warp_sum[w] = s;
+        __syncthreads();
+        if (w == 0) {
+            unsigned t = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned u = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += u; }
+            warp_sum[lane] = t;
+        }
+        __syncthreads();
+        unsigned off = carry + (w ? warp_sum[w - 1] : 0);
+        if (i < n) hist[i] = off + s - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warp_sum[31];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(32) k_rs_scatter(const unsigned long long* keys, const unsigned* vals, int n, int shift,
+                                                   const unsigned* hist, unsigned long long* okeys, unsigned* ovals) {
+    // one warp per tile: strips of 32 in order keep the sort stable
+    __shared__ unsigned off[256];
+    for (int d = threadIdx.x; d < 256; d += 32) off[d] = hist[(size_t)d * gridDim.x + blockIdx.x];
+    __syncwarp();
+    int base = blockIdx.x * RS_TILE;
+    int lane = threadIdx.x;
+    for (int s = 0; s < RS_TILE && base + s < n; s += 32) {
+        int i = base + s + lane;
+        bool live = i < n;
+        unsigned long long k = live ? keys[i] : 0;
+        unsigned d = (unsigned)(k >> shift) & 255u;
+        unsigned peers = __match_any_sync(0xffffffffu, live ? d : 0xffffffffu);
+        unsigned rank = __popc(peers & ((1u << lane) - 1u));
+        unsigned pos = 0;
+        if (live) pos = off[d] + rank;
+        __syncwarp();
+        if (live && rank == __popc(peers) - 1) off[d] = pos + 1;   // last peer advances the digit cursor
+        __syncwarp();
+        if (live) { okeys[pos] = k; ovals[pos] = vals[i]; }
+    }
+}
+
+__global__ void k_gather_rows(const unsigned* bits, const unsigned* slots, int n, int wpr, unsigned* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)n * wpr;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        size_t row = i / wpr, col = i % wpr;
+        out[i] = bits[(size_t)slots[row] * wpr + col];
+    }
+}
+
+__global__ void k_row_counts(const unsigned* rows, int n, int wpr, long long* counts) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    int lane = threadIdx.x & 31;
+    long long c = 0;
+    for (int w = lane; w < wpr; w += 32) c += __popc(rows[(size_t)row * wpr + w]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) counts[row] = c;
+}
+
+// re-insert the rows of an old table into a larger one
+__global__ void k_rehash(BondTable oldt, BondTable newt) {
+    unsigned slot = blockIdx.x;
+    if (slot > oldt.mask) return;
+    unsigned long long key = oldt.keys[slot];
+    if (key == EMPTY_KEY) return;
+    __shared__ unsigned dst;
+    if (threadIdx.x == 0) {
+        unsigned h = hash64(key) & newt.mask;
+        for (;;) {
+            unsigned long long cur = atomicCAS(&newt.keys[h], EMPTY_KEY, key);
+            if (cur == EMPTY_KEY || cur == key) break;
+            h = (h + 1) & newt.mask;
+        }
+        dst = h;
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < oldt.wpr; w += blockDim.x)
+        newt.bits[(size_t)dst * newt.wpr + w] = oldt.bits[(size_t)slot * oldt.wpr + w];
+}
+
+enum KernelClass { KC_INIT = 0, KC_GATHER, KC_GRID, KC_COUNT, KC_SCAN, KC_SCATTER, KC_LOCAL, KC_PAIRS, KC_N };
+const char* const kKernelNames[KC_N] = {"init_frames", "gather_sel", "grid_setup", "cell_count",
+                                        "cell_scan", "cell_scatter", "local_water", "pairs"};
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_create_error;
+
+struct hb_ctx {
+    int device = 0;
+    std::string err;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaDeviceProp prop{};
+
+    // topology
+    bool have_topo = false;
+    DevTopo tp{};
+    std::vector<void*> topo_allocs;
+    std::vector<long long> h_sys_atom_off;
+    std::vector<int> h_sys_sel_off, h_sys_wat_off;
+    int n_ent = 0;
+    int* d_ent_group = nullptr;
+    int max_sel = 0, max_wat = 0;
+    long long max_atoms = 0;
+
+    // params
+    bool have_params = false;
+    hb_params prm{};
+    RunParams rp{};
+
+    // options
+    long long opt_batch_bytes = 4ll << 30;
+    long long opt_table_capacity = 1ll << 20;
+    long long opt_max_batch_frames = 2048;
+    int opt_profile = 0;
+
+    // run state
+    bool running = false, finalized = false;
+    long long n_frames_total = 0, next_frame = 0;
+    BondTable bt{};
+    long long table_cap = 0;
+    int table_grows = 0;
+    int* h_status = nullptr;          // pinned: [0] n_keys, [1] overflow
+    unsigned long long* h_hits = nullptr;
+
+    // batch scratch
+    int batch_frames = 0;
+    int cell_cap = 0;
+    BatchView bv{};
+    std::vector<void*> scratch_allocs;
+    float* d_in[2] = {nullptr, nullptr};
+    float* h_stage[2] = {nullptr, nullptr};
+    size_t in_bytes = 0;
+    cudaEvent_t ev_copied[2]{}, ev_done[2]{};
+    long long batch_counter = 0;
+
+    struct Slot { bool busy; const float* d_xyz; long long f0; int nf; long long apf; };
+    Slot slots[2] = {{false, nullptr, 0, 0, 0}, {false, nullptr, 0, 0, 0}};
+
+    // results
+    long long n_bonds = 0;
+    unsigned long long* d_out_keys = nullptr;
+    unsigned* d_out_rows = nullptr;
+
+    // timers
+    hb_timers tm{};
+    struct PendingEvent { cudaEvent_t a, b; int kc; };
+    std::vector<PendingEvent> pending;
+    std::vector<cudaEvent_t> event_pool;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                         \
+            return HB_ERR_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+static int fail(hb_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) ctx->err = msg;
+    return code;
+}
+
+template <typename T>
+static int upload(hb_ctx* ctx, const T* src, size_t n, const T** dst, std::vector<void*>& owner) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    CK(cudaMalloc(&p, bytes));
+    owner.push_back(p);
+    if (n) CK(cudaMemcpy(p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = (const T*)p;
+    return HB_OK;
+}
+
+static void free_list(std::vector<void*>& v) {
+    for (void* p : v) cudaFree(p);
+    v.clear();
+}
+
+static cudaEvent_t get_event(hb_ctx* ctx) {
+    if (!ctx->event_pool.empty()) {
+        cudaEvent_t e = ctx->event_pool.back();
+        ctx->event_pool.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+static void drain_events(hb_ctx* ctx) {
+    for (auto& pe : ctx->pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(pe.b) == cudaSuccess && cudaEventElapsedTime(&ms, pe.a, pe.b) == cudaSuccess) {
+            if (pe.kc == -1) ctx->tm.ms_total += ms;
+            else if (pe.kc == -2) ctx->tm.ms_h2d += ms;
+            else ctx->tm.ms_kernel[pe.kc] += ms;
+        }
+        ctx->event_pool.push_back(pe.a);
+        ctx->event_pool.push_back(pe.b);
+    }
+    ctx->pending.clear();
+}
+
+struct KTimer {   // times one kernel class when profiling is on
+    hb_ctx* ctx; int kc; cudaEvent_t a{};
+    KTimer(hb_ctx* c, int k) : ctx(c), kc(k) {
+        ctx->tm.launches[kc]++;
+        ctx->tm.n_launches++;
+        if (ctx->opt_profile) { a = get_event(ctx); cudaEventRecord(a, ctx->s_compute); }
+    }
+    ~KTimer() {
+        if (ctx->opt_profile) {
+            cudaEvent_t b = get_event(ctx);
+            cudaEventRecord(b, ctx->s_compute);
+            ctx->pending.push_back({a, b, kc});
+        }
+    }
+};
+
+extern "C" {
+
+const char* hb_version(void) { return HB_VERSION; }
+
+const char* hb_kernel_name(int k) { return (k >= 0 && k < KC_N) ? kKernelNames[k] : nullptr; }
+
+const char* hb_last_error(hb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int hb_create(hb_ctx** out, int device) {
+    if (!out) return HB_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e);
+        return HB_ERR_NODEVICE;
+    }
+    if (device < 0 || device >= n) { g_create_error = "device ordinal out of range"; return HB_ERR_ARG; }
+    hb_ctx* ctx = new (std::nothrow) hb_ctx();
+    if (!ctx) return HB_ERR_NOMEM;
+    ctx->device = device;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        delete ctx;
+        return HB_ERR_CUDA;
+    }
+    if (ctx->prop.major != 10) {
+        g_create_error = "libhbgpu is built for sm_100a (B200) only; found sm_" + std::to_string(ctx->prop.major) +
+                         std::to_string(ctx->prop.minor);
+        delete ctx;
+        return HB_ERR_NODEVICE;
+    }
+    cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking);
+    for (int k = 0; k < 2; ++k) {
+        cudaEventCreateWithFlags(&ctx->ev_copied[k], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming);
+    }
+    cudaHostAlloc((void**)&ctx->h_status, 4 * sizeof(int), cudaHostAllocDefault);
+    cudaHostAlloc((void**)&ctx->h_hits, sizeof(unsigned long long), cudaHostAllocDefault);
+    *out = ctx;
+    return HB_OK;
+}
+
+static void free_run(hb_ctx* ctx) {
+    free_list(ctx->scratch_allocs);
+    for (int k = 0; k < 2; ++k) {
+        if (ctx->d_in[k]) cudaFree(ctx->d_in[k]);
+        if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]);
+        ctx->d_in[k] = nullptr;
+        ctx->h_stage[k] = nullptr;
+    }
+    if (ctx->bt.keys) cudaFree(ctx->bt.keys);
+    if (ctx->bt.bits) cudaFree(ctx->bt.bits);
+    if (ctx->bt.n_keys) cudaFree(ctx->bt.n_keys);
+    ctx->bt = BondTable{};
+    if (ctx->d_out_keys) cudaFree(ctx->d_out_keys);
+    if (ctx->d_out_rows) cudaFree(ctx->d_out_rows);
+    ctx->d_out_keys = nullptr;
+    ctx->d_out_rows = nullptr;
+    ctx->running = ctx->finalized = false;
+    for (auto& sl : ctx->slots) sl.busy = false;
+}
+
+int hb_destroy(hb_ctx* ctx) {
+    if (!ctx) return HB_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    drain_events(ctx);
+    free_run(ctx);
+    free_list(ctx->topo_allocs);
+    for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
+    for (int k = 0; k < 2; ++k) { cudaEventDestroy(ctx->ev_copied[k]); cudaEventDestroy(ctx->ev_done[k]); }
+    if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    if (ctx->h_hits) cudaFreeHost(ctx->h_hits);
+    cudaStreamDestroy(ctx->s_compute);
+    cudaStreamDestroy(ctx->s_copy);
+    delete ctx;
+    return HB_OK;
+}
+
+int hb_set_option(hb_ctx* ctx, const char* name, int64_t value) {
+    if (!ctx || !name) return HB_ERR_ARG;
+    std::string n(name);
+    if (n == "batch_bytes") ctx->opt_batch_bytes = std::max<long long>(value, 1 << 20);
+    else if (n == "table_capacity") ctx->opt_table_capacity = std::max<long long>(value, 1024);
+    else if (n == "profile") ctx->opt_profile = value != 0;
+    else if (n == "max_batch_frames") ctx->opt_max_batch_frames = std::max<long long>(value, 1);
+    else return fail(ctx, HB_ERR_ARG, "unknown option " + n);
+    return HB_OK;
+}
+
+int hb_set_topology(hb_ctx* ctx, const hb_topology* t) {
+    if (!ctx || !t) return HB_ERR_ARG;
+    if (ctx->running) return fail(ctx, HB_ERR_STATE, "hb_set_topology during a run");
+    if (t->n_systems < 1 || !t->sys_atom_off || !t->sys_sel_off || !t->sys_wat_off)
+        return fail(ctx, HB_ERR_ARG, "topology: system offset tables missing");
+    if (t->n_sel < 0 || t->n_wat < 0 || t->n_ent < 0 || t->n_ent_h < 0) return fail(ctx, HB_ERR_ARG, "topology: negative count");
+    if (t->n_sel >= WATER_TAG || t->n_wat >= WATER_TAG) return fail(ctx, HB_ERR_ARG, "topology: too many points");
+    CK(cudaSetDevice(ctx->device));
+    free_list(ctx->topo_allocs);
+    ctx->have_topo = false;
+    int ns = t->n_systems;
+    ctx->h_sys_atom_off.assign(t->sys_atom_off, t->sys_atom_off + ns + 1);
+    ctx->h_sys_sel_off.assign(t->sys_sel_off, t->sys_sel_off + ns + 1);
+    ctx->h_sys_wat_off.assign(t->sys_wat_off, t->sys_wat_off + ns + 1);
+    ctx->max_sel = ctx->max_wat = 0;
+    ctx->max_atoms = 0;
+    for (int s = 0; s < ns; ++s) {
+        int a = t->sys_sel_off[s + 1] - t->sys_sel_off[s], w = t->sys_wat_off[s + 1] - t->sys_wat_off[s];
+        long long at = t->sys_atom_off[s + 1] - t->sys_atom_off[s];
+        if (a < 0 || w < 0 || at < 0) return fail(ctx, HB_ERR_ARG, "topology: offsets not monotone");
+        ctx->max_sel = std::max(ctx->max_sel, a);
+        ctx->max_wat = std::max(ctx->max_wat, w);
+        ctx->max_atoms = std::max(ctx->max_atoms, at);
+    }
+    if (t->sys_sel_off[ns] != t->n_sel || t->sys_wat_off[ns] != t->n_wat) return fail(ctx, HB_ERR_ARG, "topology: offsets do not cover the point tables");
+    // validate indices on the host (cheap, once)
+    for (int s = 0; s < ns; ++s) {
+        long long at = t->sys_atom_off[s + 1] - t->sys_atom_off[s];
+        for (int i = t->sys_sel_off[s]; i < t->sys_sel_off[s + 1]; ++i) {
+            if (t->sel_atom[i] < 0 || t->sel_atom[i] >= at) return fail(ctx, HB_ERR_ARG, "topology: sel_atom out of range");
+            int d = t->sel_don[i], a = t->sel_acc[i], w = t->sel_wat[i];
+            if (d >= t->n_ent || a >= t->n_ent || w >= t->n_ent) return fail(ctx, HB_ERR_ARG, "topology: entry index out of range");
+        }
+        for (int i = t->sys_wat_off[s]; i < t->sys_wat_off[s + 1]; ++i) {
+            if (t->wat_atom[i] < 0 || t->wat_atom[i] >= at) return fail(ctx, HB_ERR_ARG, "topology: wat_atom out of range");
+            if (t->wat_ent[i] < 0 || t->wat_ent[i] >= t->n_ent) return fail(ctx, HB_ERR_ARG, "topology: wat_ent out of range");
+        }
+    }
+    if (t->n_ent) {
+        if (t->ent_h_off[0] != 0 || t->ent_h_off[t->n_ent] != t->n_ent_h) return fail(ctx, HB_ERR_ARG, "topology: hydrogen CSR inconsistent");
+        for (int e = 0; e < t->n_ent; ++e)
+            if (t->ent_h_off[e + 1] < t->ent_h_off[e]) return fail(ctx, HB_ERR_ARG, "topology: hydrogen CSR not monotone");
+    }
+    for (int k = 0; k < t->n_ent_h; ++k)
+        if (t->ent_h_atom[k] < 0 || t->ent_h_atom[k] >= ctx->max_atoms) return fail(ctx, HB_ERR_ARG, "topology: hydrogen atom out of range");
+
+    DevTopo& d = ctx->tp;
+    d.n_systems = ns;
+    int rc;
+    static const int zero_off[2] = {0, 0};
+    if ((rc = upload(ctx, (const long long*)t->sys_atom_off, ns + 1, &d.sys_atom_off, ctx->topo_allocs))) return rc;
+    if ((rc = upload(ctx, t->sys_sel_off, ns + 1, &d.sys_sel_off, ctx->topo_allocs))) return rc;
+    if ((rc = upload(ctx, t->sys_wat_off, ns + 1, &d.sys_wat_off, ctx->topo_allocs))) return rc;
+    if ((rc = upload(ctx, t->sel_atom, t->n_sel, &d.sel_atom, ctx->topo_allocs))) return rc;
+    if ((rc = upload(ctx, t->sel_don, t->n_sel, &d.sel_don, ctx->topo_allocs))) return rc;
+    if ((rc = upload(ctx, t->sel_acc, t->n_sel, &d.sel_acc, ctx->topo_allocs))) return rc;
+    if ((rc = upload(ctx, t->sel_wat, t->n_sel, &d.sel_wat, ctx->topo_allocs))) return rc;
+    if ((rc = upload(ctx, t->sel_bb, t->n_sel, &d.sel_bb, ctx->topo_allocs))) return rc;
+    if ((rc = upload(ctx, t->wat_atom, t->n_wat, &d.wat_atom, ctx->topo_allocs))) return rc;
+    if ((rc = upload(ctx, t->wat_ent, t->n_wat, &d.wat_ent, ctx->topo_allocs))) return rc;
+    if ((rc = upload(ctx, t->ent_group, t->n_ent, &d.ent_group, ctx->topo_allocs))) return rc;
+    if ((rc = upload(ctx, t->ent_resid, t->n_ent, &d.ent_resid, ctx->topo_allocs))) return rc;
+    if ((rc = upload(ctx, t->ent_residue, t->n_ent, &d.ent_residue, ctx->topo_allocs))) return rc;
+    if ((rc = upload(ctx, t->n_ent ? t->ent_h_off : zero_off, (size_t)t->n_ent + 1, &d.ent_h_off, ctx->topo_allocs))) return rc;
+    if ((rc = upload(ctx, t->ent_h_atom, t->n_ent_h, &d.ent_h_atom, ctx->topo_allocs))) return rc;
+    ctx->d_ent_group = (int*)d.ent_group;
+    ctx->n_ent = t->n_ent;
+    ctx->have_topo = true;
+    return HB_OK;
+}
+
+int hb_set_entry_groups(hb_ctx* ctx, const int32_t* g, int32_t n) {
+    if (!ctx || !g) return HB_ERR_ARG;
+    if (!ctx->have_topo || n != ctx->n_ent) return fail(ctx, HB_ERR_ARG, "hb_set_entry_groups: size mismatch");
+    if (ctx->running) return fail(ctx, HB_ERR_STATE, "hb_set_entry_groups during a run");
+    CK(cudaSetDevice(ctx->device));
+    if (n) CK(cudaMemcpy(ctx->d_ent_group, g, (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+    return HB_OK;
+}
+
+int hb_set_params(hb_ctx* ctx, const hb_params* p) {
+    if (!ctx || !p) return HB_ERR_ARG;
+    if (ctx->running) return fail(ctx, HB_ERR_STATE, "hb_set_params during a run");
+    if (!(p->distance > 0.0) || !std::isfinite(p->distance)) return fail(ctx, HB_ERR_ARG, "distance must be positive");
+    if (p->method != HB_METHOD_IN_SELECTION && p->method != HB_METHOD_WATER_AROUND) return fail(ctx, HB_ERR_ARG, "unknown method");
+    if (p->method == HB_METHOD_WATER_AROUND && (!(p->around_radius >= 0.0) || !std::isfinite(p->around_radius)))
+        return fail(ctx, HB_ERR_ARG, "around_radius must be >= 0");
+    if (p->pbc_mode != HB_PBC_NONE) return fail(ctx, HB_ERR_ARG, "pbc_mode: only HB_PBC_NONE is implemented in this build");
+    ctx->prm = *p;
+    RunParams& r = ctx->rp;
+    r.r2 = p->distance * p->distance;
+    r.around2 = p->around_radius * p->around_radius;
+    r.r2f_hi = nextafterf((float)(r.r2 * (1.0 + 1e-5)), INFINITY);
+    r.around2f_hi = nextafterf((float)(r.around2 * (1.0 + 1e-5)), INFINITY);
+    r.cell2 = (float)(p->distance * 1.001);
+    r.cell1 = (float)(std::max(p->around_radius, 1e-3) * 1.001);
+    r.around_f = (float)(p->around_radius * 1.001 + 1e-6);
+    r.cos_threshold = p->cos_threshold;
+    r.check_angle = p->check_angle;
+    r.excl_bb = p->exclude_backbone_backbone;
+    r.method = p->method;
+    ctx->have_params = true;
+    return HB_OK;
+}
+
+static int alloc_table(hb_ctx* ctx, BondTable& bt, long long cap, int wpr) {
+    bt = BondTable{};
+    bt.mask = (unsigned)(cap - 1);
+    bt.wpr = wpr;
+    CK(cudaMalloc((void**)&bt.keys, (size_t)cap * sizeof(unsigned long long)));
+    CK(cudaMalloc((void**)&bt.bits, (size_t)cap * wpr * sizeof(unsigned)));
+    k_fill_u64<<<1184, 256, 0, ctx->s_compute>>>(bt.keys, (size_t)cap, EMPTY_KEY);
+    CK(cudaMemsetAsync(bt.bits, 0, (size_t)cap * wpr * sizeof(unsigned), ctx->s_compute));
+    CK(cudaGetLastError());
+    return HB_OK;
+}
+
+int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
+    if (!ctx) return HB_ERR_ARG;
+    if (!ctx->have_topo || !ctx->have_params) return fail(ctx, HB_ERR_STATE, "hb_begin before topology/params");
+    if (n_frames_total < 1) return fail(ctx, HB_ERR_ARG, "n_frames_total must be >= 1");
+    if (ctx->prm.structure_batch && n_frames_total != ctx->tp.n_systems)
+        return fail(ctx, HB_ERR_ARG, "structure_batch: n_frames_total must equal n_systems");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaDeviceSynchronize());
+    drain_events(ctx);
+    free_run(ctx);
+    ctx->tm = hb_timers{};
+    ctx->n_frames_total = n_frames_total;
+    ctx->next_frame = 0;
+    ctx->batch_counter = 0;
+    ctx->table_grows = 0;
+    int wpr = (int)((n_frames_total + 31) / 32);
+
+    // bond table
+    long long cap = 1024;
+    while (cap < ctx->opt_table_capacity) cap <<= 1;
+    int rc = alloc_table(ctx, ctx->bt, cap, wpr);
+    if (rc) return rc;
+    ctx->table_cap = cap;
+    CK(cudaMalloc((void**)&ctx->bt.n_keys, 4 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 4 * sizeof(unsigned long long), ctx->s_compute));
+    ctx->bt.overflow = ctx->bt.n_keys + 1;
+    ctx->bt.n_hits = (unsigned long long*)(ctx->bt.n_keys + 2);
+
+    // batch sizing
+    size_t npts = (size_t)ctx->max_sel + ctx->max_wat;
+    long long cc = 4096;
+    while (cc < (long long)(2 * npts)) cc <<= 1;
+    cc = std::min<long long>(cc, 1ll << 22);
+    ctx->cell_cap = (int)cc;
+    size_t per_frame = (size_t)ctx->max_atoms * 12 * 2                      // two input buffers
+                       + sizeof(FrameState) + (size_t)ctx->max_sel * 32 + (size_t)ctx->max_wat * 16 + npts * 16 +
+                       2 * (size_t)(cc + 1) * 4;
+    long long fb = (long long)(ctx->opt_batch_bytes / std::max<size_t>(per_frame, 1));
+    fb = std::max<long long>(1, std::min<long long>(fb, ctx->opt_max_batch_frames));
+    fb = std::min<long long>(fb, n_frames_total);
+    if (fb >= 32) fb -= fb % 32;
+    ctx->batch_frames = (int)fb;
+    BatchView& bv = ctx->bv;
+    bv = BatchView{};
+    bv.max_sel = ctx->max_sel;
+    bv.max_wat = ctx->max_wat;
+    bv.cell_cap = ctx->cell_cap;
+    bv.structure_batch = ctx->prm.structure_batch;
+    auto dalloc = [&](void** p, size_t bytes) -> int {
+        CK(cudaMalloc(p, std::max<size_t>(bytes, 16)));
+        ctx->scratch_allocs.push_back(*p);
+        return HB_OK;
+    };
+    if ((rc = dalloc((void**)&bv.fs, fb * sizeof(FrameState)))) return rc;
+    if ((rc = dalloc((void**)&bv.selpos, fb * (size_t)ctx->max_sel * 16))) return rc;
+    if ((rc = dalloc((void**)&bv.sorted1, fb * (size_t)ctx->max_sel * 16))) return rc;
+    if ((rc = dalloc((void**)&bv.lw, fb * (size_t)ctx->max_wat * 16))) return rc;
+    if ((rc = dalloc((void**)&bv.sorted2, fb * npts * 16))) return rc;
+    if ((rc = dalloc((void**)&bv.cells1, fb * (size_t)(cc + 1) * 4))) return rc;
+    if ((rc = dalloc((void**)&bv.cells2, fb * (size_t)(cc + 1) * 4))) return rc;
+    ctx->in_bytes = (size_t)fb * ctx->max_atoms * 12;
+    ctx->running = true;
+    ctx->finalized = false;
+    return HB_OK;
+}
+
+static int grow_table(hb_ctx* ctx) {
+    long long ncap = ctx->table_cap * 2;
+    BondTable nt;
+    int rc = alloc_table(ctx, nt, ncap, ctx->bt.wpr);
+    if (rc) return rc;
+    nt.n_keys = ctx->bt.n_keys;
+    nt.overflow = ctx->bt.overflow;
+    nt.n_hits = ctx->bt.n_hits;
+    k_rehash<<<(unsigned)ctx->table_cap, 128, 0, ctx->s_compute>>>(ctx->bt, nt);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->s_compute));
+    cudaFree(ctx->bt.keys);
+    cudaFree(ctx->bt.bits);
+    ctx->bt = nt;
+    ctx->table_cap = ncap;
+    ctx->table_grows++;
+    return HB_OK;
+}
+
+// launch the kernel pipeline for one batch resident at d_xyz
+static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, long long atoms_per_frame) {
+    BatchView bv = ctx->bv;
+    bv.xyz = d_xyz;
+    bv.frame0 = frame0;
+    bv.n_frames = nf;
+    bv.atoms_per_frame = atoms_per_frame;
+    bv.atom_base = bv.structure_batch ? ctx->h_sys_atom_off[frame0] : 0;
+    cudaStream_t st = ctx->s_compute;
+    const RunParams& rp = ctx->rp;
+    const DevTopo& tp = ctx->tp;
+    bool wa = rp.method == HB_METHOD_WATER_AROUND;
+    cudaEvent_t t0 = get_event(ctx), t1 = get_event(ctx);
+    cudaEventRecord(t0, st);
+    { KTimer t(ctx, KC_INIT); k_init_frames<<<(nf + 127) / 128, 128, 0, st>>>(bv); }
+    size_t cells_bytes = (size_t)nf * (bv.cell_cap + 1) * 4;
+    if (wa) CK(cudaMemsetAsync(bv.cells1, 0, cells_bytes, st));
+    CK(cudaMemsetAsync(bv.cells2, 0, cells_bytes, st));
+    dim3 gsel((bv.max_sel + 255) / 256, nf), gwat((bv.max_wat + 255) / 256, nf);
+    if (bv.max_sel > 0) { KTimer t(ctx, KC_GATHER); k_gather_sel<<<gsel, 256, 0, st>>>(bv, tp); }
+    { KTimer t(ctx, KC_GRID); k_grid_setup<<<(nf + 127) / 128, 128, 0, st>>>(bv, rp); }
+    if (wa && bv.max_sel > 0 && bv.max_wat > 0) {
+        { KTimer t(ctx, KC_COUNT); k_count<<<gsel, 256, 0, st>>>(bv, tp, 1); }
+        { KTimer t(ctx, KC_SCAN); k_scan<<<nf, 1024, 0, st>>>(bv, 1); }
+        { KTimer t(ctx, KC_SCATTER); k_scatter<<<gsel, 256, 0, st>>>(bv, tp, 1); }
+        { KTimer t(ctx, KC_LOCAL); k_local_water<<<gwat, 256, 0, st>>>(bv, tp, rp); }
+    }
+    int maxp = bv.max_sel + (wa ? bv.max_wat : 0);
+    if (maxp > 0) {
+        dim3 gall((maxp + 255) / 256, nf);
+        { KTimer t(ctx, KC_COUNT); k_count<<<gall, 256, 0, st>>>(bv, tp, 2); }
+        { KTimer t(ctx, KC_SCAN); k_scan<<<nf, 1024, 0, st>>>(bv, 2); }
+        { KTimer t(ctx, KC_SCATTER); k_scatter<<<gall, 256, 0, st>>>(bv, tp, 2); }
+        dim3 gp((maxp + 127) / 128, nf);
+        { KTimer t(ctx, KC_PAIRS); k_pairs<<<gp, 128, 0, st>>>(bv, tp, rp, ctx->bt); }
+    }
+    cudaEventRecord(t1, st);
+    ctx->pending.push_back({t0, t1, -1});
+    CK(cudaGetLastError());
+    ctx->tm.frames += nf;
+    return HB_OK;
+}
+
+// ---- batch bookkeeping -------------------------------------------------------------------------------
+// A batch stays "in flight" (its coordinates must stay intact) until a status snapshot taken right
+// after it on the compute stream shows that the bond table did not overflow while it ran.  On overflow
+// the table is grown and every in-flight batch is re-run (idempotent: bits are OR-ed, keys deduplicate).
+static int full_verify(hb_ctx* ctx) {
+    for (int attempt = 0; attempt < 28; ++attempt) {
+        CK(cudaStreamSynchronize(ctx->s_compute));
+        int st[2];
+        CK(cudaMemcpy(st, ctx->bt.n_keys, sizeof(st), cudaMemcpyDeviceToHost));
+        bool overflow = st[1] != 0;
+        if (!overflow && (long long)st[0] * 2 <= ctx->table_cap) {
+            for (auto& sl : ctx->slots) sl.busy = false;
+            return HB_OK;
+        }
+        int rc = grow_table(ctx);
+        if (rc) return rc;
+        while ((long long)st[0] * 2 > ctx->table_cap)
+            if ((rc = grow_table(ctx))) return rc;
+        if (overflow) {
+            CK(cudaMemsetAsync(ctx->bt.overflow, 0, sizeof(int), ctx->s_compute));
+            for (auto& sl : ctx->slots)
+                if (sl.busy) {
+                    long long frames_before = ctx->tm.frames;
+                    if ((rc = run_batch(ctx, sl.d_xyz, sl.f0, sl.nf, sl.apf))) return rc;
+                    ctx->tm.frames = frames_before;
+                }
+        }
+    }
+    return fail(ctx, HB_ERR_NOMEM, "bond table kept overflowing");
+}
+
+// make slot k reusable: its previous batch must be complete and verified
+static int acquire_slot(hb_ctx* ctx, int k) {
+    hb_ctx::Slot& sl = ctx->slots[k];
+    if (!sl.busy) return HB_OK;
+    CK(cudaEventSynchronize(ctx->ev_done[k]));
+    int nkeys = ctx->h_status[2 * k], overflow = ctx->h_status[2 * k + 1];
+    if (overflow || (long long)nkeys * 2 > ctx->table_cap) return full_verify(ctx);
+    sl.busy = false;
+    return HB_OK;
+}
+
+static int launch_in_slot(hb_ctx* ctx, int k, const float* d_xyz, long long f0, int nf, long long apf) {
+    int rc = run_batch(ctx, d_xyz, f0, nf, apf);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ctx->h_status + 2 * k, ctx->bt.n_keys, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->s_compute));
+    CK(cudaEventRecord(ctx->ev_done[k], ctx->s_compute));
+    ctx->slots[k] = hb_ctx::Slot{true, d_xyz, f0, nf, apf};
+    return HB_OK;
+}
+
+static int check_submit(hb_ctx* ctx, int64_t n_atoms, int64_t n_frames) {
+    if (!ctx->running) return fail(ctx, HB_ERR_STATE, "hb_submit_frames before hb_begin");
+    if (n_frames < 0 || ctx->next_frame + n_frames > ctx->n_frames_total) return fail(ctx, HB_ERR_ARG, "more frames submitted than announced in hb_begin");
+    if (!ctx->prm.structure_batch && n_atoms != ctx->h_sys_atom_off[1] - ctx->h_sys_atom_off[0])
+        return fail(ctx, HB_ERR_ARG, "n_atoms does not match the topology");
+    return HB_OK;
+}
+
+static long long batch_atoms(hb_ctx* ctx, long long f0, int nf, long long n_atoms) {
+    if (ctx->prm.structure_batch) return ctx->h_sys_atom_off[f0 + nf] - ctx->h_sys_atom_off[f0];
+    return n_atoms * nf;
+}
+
+static int next_batch_frames(hb_ctx* ctx, long long f0, long long remaining) {
+    int nf = (int)std::min<long long>(remaining, ctx->batch_frames);
+    if (ctx->prm.structure_batch) {   // ragged: stay within the input buffer
+        long long budget = (long long)(ctx->in_bytes / 12);
+        while (nf > 1 && ctx->h_sys_atom_off[f0 + nf] - ctx->h_sys_atom_off[f0] > budget) --nf;
+    }
+    return nf;
+}
+
+int hb_submit_frames(hb_ctx* ctx, const float* xyz, int64_t n_atoms, int64_t n_frames, const float* box) {
+    if (!ctx || (!xyz && n_frames > 0)) return HB_ERR_ARG;
+    (void)box;
+    int rc = check_submit(ctx, n_atoms, n_frames);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    cudaPointerAttributes attr{};
+    bool pinned = cudaPointerGetAttributes(&attr, xyz) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    for (int k = 0; k < 2; ++k) {
+        if (!ctx->d_in[k]) CK(cudaMalloc((void**)&ctx->d_in[k], std::max<size_t>(ctx->in_bytes, 16)));
+        if (!pinned && !ctx->h_stage[k]) CK(cudaHostAlloc((void**)&ctx->h_stage[k], std::max<size_t>(ctx->in_bytes, 16), cudaHostAllocDefault));
+    }
+    const float* src = xyz;
+    long long done = 0;
+    while (done < n_frames) {
+        long long f0 = ctx->next_frame;
+        int nf = next_batch_frames(ctx, f0, n_frames - done);
+        long long atoms = batch_atoms(ctx, f0, nf, n_atoms);
+        size_t bytes = (size_t)atoms * 12;
+        int k = (int)(ctx->batch_counter & 1);
+        if ((rc = acquire_slot(ctx, k))) return rc;       // buffer k (device + staging) is free again
+        const float* h = src;
+        if (!pinned) { memcpy(ctx->h_stage[k], src, bytes); h = ctx->h_stage[k]; }
+        cudaEvent_t c0 = get_event(ctx), c1 = get_event(ctx);
+        cudaEventRecord(c0, ctx->s_copy);
+        CK(cudaMemcpyAsync(ctx->d_in[k], h, bytes, cudaMemcpyHostToDevice, ctx->s_copy));
+        cudaEventRecord(c1, ctx->s_copy);
+        ctx->pending.push_back({c0, c1, -2});
+        CK(cudaEventRecord(ctx->ev_copied[k], ctx->s_copy));
+        CK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_copied[k], 0));
+        if ((rc = launch_in_slot(ctx, k, ctx->d_in[k], f0, nf, n_atoms))) return rc;
+        ctx->batch_counter++;
+        ctx->next_frame += nf;
+        done += nf;
+        src += (size_t)atoms * 3;
+        if (ctx->pending.size() > 8192) drain_events(ctx);
+    }
+    if (pinned) CK(cudaStreamSynchronize(ctx->s_copy));   // caller may reuse its pinned buffer on return
+    return HB_OK;
+}
+
+int hb_submit_frames_device(hb_ctx* ctx, const float* d_xyz, int64_t n_atoms, int64_t n_frames, const float* d_box) {
+    if (!ctx || (!d_xyz && n_frames > 0)) return HB_ERR_ARG;
+    (void)d_box;
+    int rc = check_submit(ctx, n_atoms, n_frames);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const float* src = d_xyz;
+    long long done = 0;
+    while (done < n_frames) {
+        long long f0 = ctx->next_frame;
+        int nf = next_batch_frames(ctx, f0, n_frames - done);
+        long long atoms = batch_atoms(ctx, f0, nf, n_atoms);
+        int k = (int)(ctx->batch_counter & 1);
+        if ((rc = acquire_slot(ctx, k))) return rc;
+        if ((rc = launch_in_slot(ctx, k, src, f0, nf, n_atoms))) return rc;
+        ctx->batch_counter++;
+        ctx->next_frame += nf;
+        done += nf;
+        src += (size_t)atoms * 3;
+        if (ctx->pending.size() > 8192) drain_events(ctx);
+    }
+    // the caller's buffer must stay valid until verified: settle before returning
+    return full_verify(ctx);
+}
+
+int hb_sync(hb_ctx* ctx) {
+    if (!ctx) return HB_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->s_copy));
+    if (ctx->running) {
+        int rc = full_verify(ctx);
+        if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(ctx->s_compute));
+    drain_events(ctx);
+    return HB_OK;
+}
+
+int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
+    if (!ctx) return HB_ERR_ARG;
+    if (!ctx->running) return fail(ctx, HB_ERR_STATE, "hb_finalize before hb_begin");
+    int rc = hb_sync(ctx);
+    if (rc) return rc;
+    cudaStream_t st = ctx->s_compute;
+    CK(cudaMemcpyAsync(ctx->h_status, ctx->bt.n_keys, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ctx->h_hits, ctx->bt.n_hits, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int n = ctx->h_status[0];
+    ctx->tm.pairs_emitted = (long long)*ctx->h_hits;
+    int wpr = ctx->bt.wpr;
+    if (ctx->d_out_keys) { cudaFree(ctx->d_out_keys); ctx->d_out_keys = nullptr; }
+    if (ctx->d_out_rows) { cudaFree(ctx->d_out_rows); ctx->d_out_rows = nullptr; }
+    unsigned long long *k0 = nullptr, *k1 = nullptr;
+    unsigned *v0 = nullptr, *v1 = nullptr, *hist = nullptr;
+    int* counter = nullptr;
+    size_t nn = std::max(n, 1);
+    CK(cudaMalloc((void**)&k0, nn * 8));
+    CK(cudaMalloc((void**)&k1, nn * 8));
+    CK(cudaMalloc((void**)&v0, nn * 4));
+    CK(cudaMalloc((void**)&v1, nn * 4));
+    CK(cudaMalloc((void**)&counter, 4));
+    CK(cudaMemsetAsync(counter, 0, 4, st));
+    unsigned cap = ctx->bt.mask + 1u;
+    k_compact<<<(cap + 255) / 256, 256, 0, st>>>(ctx->bt, k0, v0, counter);
+    int nblk = (n + RS_TILE - 1) / RS_TILE;
+    if (n > 1) {
+        CK(cudaMalloc((void**)&hist, (size_t)256 * nblk * 4));
+        for (int pass = 0; pass < 8; ++pass) {
+            int shift = pass * 8;
+            k_rs_hist<<<nblk, 256, 0, st>>>(k0, n, shift, hist);
+            k_rs_scan<<<1, 1024, 0, st>>>(hist, (size_t)256 * nblk);
+            k_rs_scatter<<<nblk, 32, 0, st>>>(k0, v0, n, shift, hist, k1, v1);
+            std::swap(k0, k1);
+            std::swap(v0, v1);
+        }
+    }
+    CK(cudaMalloc((void**)&ctx->d_out_rows, nn * (size_t)wpr * 4));
+    if (n > 0) k_gather_rows<<<1184, 256, 0, st>>>(ctx->bt.bits, v0, n, wpr, ctx->d_out_rows);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+    ctx->d_out_keys = k0;
+    cudaFree(k1);
+    cudaFree(v0);
+    cudaFree(v1);
+    cudaFree(counter);
+    if (hist) cudaFree(hist);
+    ctx->n_bonds = n;
+    ctx->finalized = true;
+    if (n_bonds) *n_bonds = n;
+    if (words_per_bond) *words_per_bond = wpr;
+    return HB_OK;
+}
+
+int hb_get_keys(hb_ctx* ctx, uint64_t* keys) {
+    if (!ctx || !keys) return HB_ERR_ARG;
+    if (!ctx->finalized) return fail(ctx, HB_ERR_STATE, "hb_get_keys before hb_finalize");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n_bonds) CK(cudaMemcpy(keys, ctx->d_out_keys, (size_t)ctx->n_bonds * 8, cudaMemcpyDeviceToHost));
+    return HB_OK;
+}
+
+int hb_get_bits(hb_ctx* ctx, uint32_t* words) {
+    if (!ctx || !words) return HB_ERR_ARG;
+    if (!ctx->finalized) return fail(ctx, HB_ERR_STATE, "hb_get_bits before hb_finalize");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n_bonds) CK(cudaMemcpy(words, ctx->d_out_rows, (size_t)ctx->n_bonds * ctx->bt.wpr * 4, cudaMemcpyDeviceToHost));
+    return HB_OK;
+}
+
+int hb_get_keys_device(hb_ctx* ctx, uint64_t* d_keys) {
+    if (!ctx || !d_keys) return HB_ERR_ARG;
+    if (!ctx->finalized) return fail(ctx, HB_ERR_STATE, "hb_get_keys_device before hb_finalize");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n_bonds) CK(cudaMemcpy(d_keys, ctx->d_out_keys, (size_t)ctx->n_bonds * 8, cudaMemcpyDeviceToDevice));
+    return HB_OK;
+}
+
+int hb_get_bits_device(hb_ctx* ctx, uint32_t* d_words) {
+    if (!ctx || !d_words) return HB_ERR_ARG;
+    if (!ctx->finalized) return fail(ctx, HB_ERR_STATE, "hb_get_bits_device before hb_finalize");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n_bonds) CK(cudaMemcpy(d_words, ctx->d_out_rows, (size_t)ctx->n_bonds * ctx->bt.wpr * 4, cudaMemcpyDeviceToDevice));
+    return HB_OK;
+}
+
+int hb_get_counts(hb_ctx* ctx, int64_t* counts) {
+    if (!ctx || !counts) return HB_ERR_ARG;
+    if (!ctx->finalized) return fail(ctx, HB_ERR_STATE, "hb_get_counts before hb_finalize");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->n_bonds) return HB_OK;
+    long long* d = nullptr;
+    CK(cudaMalloc((void**)&d, (size_t)ctx->n_bonds * 8));
+    int n = (int)ctx->n_bonds;
+    k_row_counts<<<(n + 7) / 8, 256, 0, ctx->s_compute>>>(ctx->d_out_rows, n, ctx->bt.wpr, d);
+    cudaError_t e = cudaMemcpyAsync(counts, d, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->s_compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_compute);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, HB_ERR_CUDA, cudaGetErrorString(e));
+    return HB_OK;
+}
+
+int hb_get_timers(hb_ctx* ctx, hb_timers* out) {
+    if (!ctx || !out) return HB_ERR_ARG;
+    drain_events(ctx);
+    ctx->tm.table_capacity = ctx->table_cap;
+    ctx->tm.table_grows = ctx->table_grows;
+    *out = ctx->tm;
+    return HB_OK;
+}
+
+int hb_host_alloc(void** ptr, uint64_t bytes) {
+    if (!ptr) return HB_ERR_ARG;
+    return cudaHostAlloc(ptr, bytes ? bytes : 16, cudaHostAllocDefault) == cudaSuccess ? HB_OK : HB_ERR_NOMEM;
+}
+
+int hb_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? HB_OK : HB_ERR_CUDA; }
+
+}  // extern "C"

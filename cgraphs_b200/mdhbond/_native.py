@@ -1,0 +1,272 @@
+"""ctypes binding of libhbgpu.so (include/hbgpu.h).  There is no CPU fallback: if the library or a
+B200 is missing, the calls raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import numpy as np
+
+_LIB = None
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc", "libhbgpu.so")
+
+METHOD_IN_SELECTION = 0
+METHOD_WATER_AROUND = 1
+
+
+class HbTopology(C.Structure):
+    _fields_ = [
+        ("n_systems", C.c_int32),
+        ("sys_atom_off", C.POINTER(C.c_int64)),
+        ("sys_sel_off", C.POINTER(C.c_int32)),
+        ("sys_wat_off", C.POINTER(C.c_int32)),
+        ("n_sel", C.c_int32),
+        ("sel_atom", C.POINTER(C.c_int32)),
+        ("sel_don", C.POINTER(C.c_int32)),
+        ("sel_acc", C.POINTER(C.c_int32)),
+        ("sel_wat", C.POINTER(C.c_int32)),
+        ("sel_bb", C.POINTER(C.c_uint8)),
+        ("n_wat", C.c_int32),
+        ("wat_atom", C.POINTER(C.c_int32)),
+        ("wat_ent", C.POINTER(C.c_int32)),
+        ("n_ent", C.c_int32),
+        ("ent_group", C.POINTER(C.c_int32)),
+        ("ent_resid", C.POINTER(C.c_int32)),
+        ("ent_residue", C.POINTER(C.c_int32)),
+        ("ent_h_off", C.POINTER(C.c_int32)),
+        ("n_ent_h", C.c_int32),
+        ("ent_h_atom", C.POINTER(C.c_int32)),
+    ]
+
+
+class HbParams(C.Structure):
+    _fields_ = [
+        ("distance", C.c_double),
+        ("around_radius", C.c_double),
+        ("cos_threshold", C.c_float),
+        ("check_angle", C.c_int32),
+        ("exclude_backbone_backbone", C.c_int32),
+        ("method", C.c_int32),
+        ("pbc_mode", C.c_int32),
+        ("structure_batch", C.c_int32),
+    ]
+
+
+class HbTimers(C.Structure):
+    _fields_ = [
+        ("ms_total", C.c_double),
+        ("ms_h2d", C.c_double),
+        ("ms_kernel", C.c_double * 16),
+        ("launches", C.c_int64 * 16),
+        ("n_launches", C.c_int64),
+        ("frames", C.c_int64),
+        ("pairs_emitted", C.c_int64),
+        ("table_capacity", C.c_int64),
+        ("table_grows", C.c_int64),
+    ]
+
+
+# every symbol include/hbgpu.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = [
+    ("hb_create", C.c_int, [C.POINTER(_P), C.c_int]),
+    ("hb_destroy", C.c_int, [_P]),
+    ("hb_last_error", C.c_char_p, [_P]),
+    ("hb_version", C.c_char_p, []),
+    ("hb_kernel_name", C.c_char_p, [C.c_int]),
+    ("hb_set_topology", C.c_int, [_P, C.POINTER(HbTopology)]),
+    ("hb_set_entry_groups", C.c_int, [_P, C.POINTER(C.c_int32), C.c_int32]),
+    ("hb_set_params", C.c_int, [_P, C.POINTER(HbParams)]),
+    ("hb_set_option", C.c_int, [_P, C.c_char_p, C.c_int64]),
+    ("hb_begin", C.c_int, [_P, C.c_int64]),
+    ("hb_submit_frames", C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
+    ("hb_submit_frames_device", C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
+    ("hb_finalize", C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("hb_get_keys", C.c_int, [_P, _P]),
+    ("hb_get_bits", C.c_int, [_P, _P]),
+    ("hb_get_keys_device", C.c_int, [_P, _P]),
+    ("hb_get_bits_device", C.c_int, [_P, _P]),
+    ("hb_get_counts", C.c_int, [_P, _P]),
+    ("hb_get_timers", C.c_int, [_P, C.POINTER(HbTimers)]),
+    ("hb_sync", C.c_int, [_P]),
+    ("hb_host_alloc", C.c_int, [C.POINTER(_P), C.c_uint64]),
+    ("hb_host_free", C.c_int, [_P]),
+]
+
+
+class HbError(RuntimeError):
+    pass
+
+
+def load_library(path=None):
+    """dlopen libhbgpu.so and declare the prototypes.  Raises if the library was not built."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    p = os.path.abspath(path or LIB_PATH)
+    if not os.path.exists(p):
+        raise HbError("libhbgpu.so not found at %s - build it with `python -m cgraphs_b200.build` "
+                      "(there is no CPU fallback)" % p)
+    lib = C.CDLL(p)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Context:
+    """One hb_ctx. Keeps the numpy arrays of the topology alive for the duration of the upload only."""
+
+    def __init__(self, device=0):
+        self.lib = load_library()
+        h = _P()
+        rc = self.lib.hb_create(C.byref(h), int(device))
+        if rc != 0:
+            raise HbError("hb_create failed (%d): %s" % (rc, (self.lib.hb_last_error(None) or b"").decode()))
+        self.h = h
+        self.device = int(device)
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise HbError("%s failed (%d): %s" % (what, rc, (self.lib.hb_last_error(self.h) or b"").decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name, value):
+        self._ck(self.lib.hb_set_option(self.h, name.encode(), int(value)), "hb_set_option")
+
+    def set_topology(self, t):
+        """t: dict of numpy arrays named like the hb_topology fields."""
+        keep = {}
+        st = HbTopology()
+        st.n_systems = int(t["n_systems"])
+        keep["sys_atom_off"] = np.ascontiguousarray(t["sys_atom_off"], dtype=np.int64)
+        st.sys_atom_off = _ptr(keep["sys_atom_off"], C.c_int64)
+        for k in ("sys_sel_off", "sys_wat_off", "sel_atom", "sel_don", "sel_acc", "sel_wat", "wat_atom", "wat_ent",
+                  "ent_group", "ent_resid", "ent_residue", "ent_h_off", "ent_h_atom"):
+            keep[k] = _i32(t[k])
+            setattr(st, k, _ptr(keep[k], C.c_int32))
+        keep["sel_bb"] = np.ascontiguousarray(t["sel_bb"], dtype=np.uint8)
+        st.sel_bb = _ptr(keep["sel_bb"], C.c_uint8)
+        st.n_sel = len(keep["sel_atom"])
+        st.n_wat = len(keep["wat_atom"])
+        st.n_ent = len(keep["ent_group"])
+        st.n_ent_h = len(keep["ent_h_atom"])
+        assert len(keep["ent_h_off"]) == st.n_ent + 1
+        self._ck(self.lib.hb_set_topology(self.h, C.byref(st)), "hb_set_topology")
+
+    def set_entry_groups(self, groups):
+        g = _i32(groups)
+        self._ck(self.lib.hb_set_entry_groups(self.h, _ptr(g, C.c_int32), len(g)), "hb_set_entry_groups")
+
+    def set_params(self, distance, around_radius, cos_threshold, check_angle, exclude_backbone_backbone, method,
+                   pbc_mode=0, structure_batch=False):
+        p = HbParams(float(distance), float(around_radius), float(cos_threshold), int(bool(check_angle)),
+                     int(bool(exclude_backbone_backbone)), int(method), int(pbc_mode), int(bool(structure_batch)))
+        self._ck(self.lib.hb_set_params(self.h, C.byref(p)), "hb_set_params")
+
+    def begin(self, n_frames_total):
+        self._ck(self.lib.hb_begin(self.h, int(n_frames_total)), "hb_begin")
+
+    def submit(self, xyz, n_atoms=None):
+        """xyz: float32 host array [F, N, 3] (or ragged flat [sum N, 3] with structure_batch)."""
+        a = np.ascontiguousarray(xyz, dtype=np.float32)
+        if a.ndim == 3:
+            nf, na = a.shape[0], a.shape[1]
+        else:
+            raise ValueError("submit expects [F, N, 3]; use submit_raw for ragged batches")
+        self._ck(self.lib.hb_submit_frames(self.h, a.ctypes.data, na, nf, None), "hb_submit_frames")
+
+    def submit_raw(self, ptr, n_atoms, n_frames):
+        self._ck(self.lib.hb_submit_frames(self.h, int(ptr), int(n_atoms), int(n_frames), None), "hb_submit_frames")
+
+    def submit_device(self, dev_ptr, n_atoms, n_frames):
+        self._ck(self.lib.hb_submit_frames_device(self.h, int(dev_ptr), int(n_atoms), int(n_frames), None),
+                 "hb_submit_frames_device")
+
+    def sync(self):
+        self._ck(self.lib.hb_sync(self.h), "hb_sync")
+
+    def finalize(self):
+        nb, wpr = C.c_int64(), C.c_int64()
+        self._ck(self.lib.hb_finalize(self.h, C.byref(nb), C.byref(wpr)), "hb_finalize")
+        return nb.value, wpr.value
+
+    def results(self):
+        """(keys uint64 [B] ascending, words uint32 [B, wpr])."""
+        nb, wpr = self.finalize()
+        keys = np.empty(nb, dtype=np.uint64)
+        words = np.empty((nb, wpr), dtype=np.uint32)
+        if nb:
+            self._ck(self.lib.hb_get_keys(self.h, keys.ctypes.data), "hb_get_keys")
+            self._ck(self.lib.hb_get_bits(self.h, words.ctypes.data), "hb_get_bits")
+        return keys, words
+
+    def keys_to_device(self, dev_ptr):
+        self._ck(self.lib.hb_get_keys_device(self.h, int(dev_ptr)), "hb_get_keys_device")
+
+    def bits_to_device(self, dev_ptr):
+        self._ck(self.lib.hb_get_bits_device(self.h, int(dev_ptr)), "hb_get_bits_device")
+
+    def counts(self, n_bonds):
+        c = np.zeros(n_bonds, dtype=np.int64)
+        if n_bonds:
+            self._ck(self.lib.hb_get_counts(self.h, c.ctypes.data), "hb_get_counts")
+        return c
+
+    def timers(self):
+        t = HbTimers()
+        self._ck(self.lib.hb_get_timers(self.h, C.byref(t)), "hb_get_timers")
+        names = []
+        k = 0
+        while True:
+            n = self.lib.hb_kernel_name(k)
+            if not n:
+                break
+            names.append(n.decode())
+            k += 1
+        return dict(ms_total=t.ms_total, ms_h2d=t.ms_h2d, n_launches=t.n_launches, frames=t.frames,
+                    pairs_emitted=t.pairs_emitted, table_capacity=t.table_capacity, table_grows=t.table_grows,
+                    ms_kernel={n: t.ms_kernel[i] for i, n in enumerate(names)},
+                    launches={n: t.launches[i] for i, n in enumerate(names)})
+
+
+class PinnedBuffer:
+    """float32 numpy array over cudaHostAlloc memory."""
+
+    def __init__(self, shape):
+        lib = load_library()
+        self.lib = lib
+        n = int(np.prod(shape))
+        p = _P()
+        rc = lib.hb_host_alloc(C.byref(p), n * 4)
+        if rc != 0:
+            raise HbError("hb_host_alloc(%d bytes) failed" % (n * 4))
+        self.ptr = p.value
+        buf = (C.c_float * n).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=np.float32).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.lib.hb_host_free(self.ptr)
+            self.ptr = None

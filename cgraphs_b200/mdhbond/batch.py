@@ -1,0 +1,89 @@
+"""Batched static structures: many independent structures searched in one launch (BASELINE config C5).
+
+cgraphs' conserved-graph workflow builds one ``HbondAnalysis`` per PDB structure and runs it on a
+single frame (reference ``cgraphs/proteingraphanalyser.py:370-450``).  ``HbondBatch`` does the same
+work for a list of structures at once: the topologies are concatenated into one ragged ``hb_topology``
+(one system per structure), the coordinates into one ragged buffer, and "frame" f of the occupancy
+matrix is structure f.  Bond keys share one id space over the batch, so the matrix is directly the
+bond x structure table the conserved-graph reduction needs (``conservedgraph.py:114-170``).
+"""
+from __future__ import annotations
+
+import numpy as _np
+
+from . import _native
+from .calib import cos_threshold as _cos_threshold
+from .hbond import HbondAnalysis, dict2graph
+from .topology import pack_systems
+
+
+class StructureResult(object):
+    """What a per-structure ``HbondAnalysis`` exposes after a ``set_hbonds_*`` call."""
+
+    def __init__(self, results, residuewise):
+        self.initial_results = results
+        self.filtered_results = results
+        self.nb_frames = 1
+        self.residuewise = residuewise
+        self.initial_graph = dict2graph(results, residuewise)
+        self.filtered_graph = self.initial_graph
+
+
+class HbondBatch(object):
+    def __init__(self, structures, selection, device=None, **ctor_kwargs):
+        """structures: Universe-like objects (single frame each); other kwargs as HbondAnalysis."""
+        if not structures:
+            raise AssertionError('No structure file path.')
+        self._device = device
+        self.analyses = [HbondAnalysis(selection, s, device=device, **ctor_kwargs) for s in structures]
+        a0 = self.analyses[0]
+        self.check_angle, self.residuewise = a0.check_angle, a0.residuewise
+        self.distance, self.cut_angle = a0.distance, a0.cut_angle
+        self._ctx = None
+        self.results = None
+        self.bond_keys = None
+        self.occupancy_words = None
+        self.last_run_stats = None
+
+    def set_hbonds_in_selection(self, exclude_backbone_backbone=True):
+        for a in self.analyses:
+            if a._nb_acceptors == 0: raise AssertionError('No acceptors in the selection')
+            if a._nb_donors == 0: raise AssertionError('No donors in the selection')
+        return self._run("in_selection", 0.0, exclude_backbone_backbone)
+
+    def set_hbonds_in_selection_and_water_around(self, around_radius, exclude_backbone_backbone=True):
+        return self._run("water_around", float(around_radius), exclude_backbone_backbone)
+
+    def _run(self, method, around, excl_bb):
+        tops = [a._topology for a in self.analyses]
+        for a in self.analyses:
+            a._check_hydrogen_tables(method)
+        n_atoms = [a._n_atoms for a in self.analyses]
+        tables, group_names = pack_systems(tops, [t.key_ids(method) for t in tops], n_atoms)
+        if self._ctx is None:
+            self._ctx = _native.Context(self._device if self._device is not None else 0)
+        ctx = self._ctx
+        ctx.set_topology(tables)
+        cthr = _cos_threshold(float(self.cut_angle)) if self.check_angle else -1.0
+        ctx.set_params(self.distance, around, cthr, self.check_angle, excl_bb,
+                       _native.METHOD_WATER_AROUND if method == "water_around" else _native.METHOD_IN_SELECTION,
+                       structure_batch=True)
+        n = len(self.analyses)
+        xyz = _np.concatenate([a._first_frame_positions() for a in self.analyses]).astype(_np.float32)
+        ctx.begin(n)
+        ctx.submit_raw(xyz.ctypes.data, 0, n)
+        keys, words = ctx.results()
+        self.last_run_stats = ctx.timers()
+        self.bond_keys = [group_names[int(k >> _np.uint64(32))] + ':' + group_names[int(k & _np.uint64(0xFFFFFFFF))]
+                          for k in keys]
+        self.occupancy_words = words
+        bits = _np.unpackbits(words.view(_np.uint8), axis=1, bitorder="little")[:, :n].astype(bool) \
+            if len(keys) else _np.zeros((0, n), bool)
+        self.occupancy = bits
+        self.results = []
+        for i, a in enumerate(self.analyses):
+            rows = _np.nonzero(bits[:, i])[0]
+            res = {self.bond_keys[r]: _np.ones(1, dtype=bool) for r in rows}
+            a._set_results(res)
+            self.results.append(StructureResult(res, self.residuewise))
+        return self.results

@@ -1,0 +1,320 @@
+"""Drop-in ``HbondAnalysis`` whose per-frame search runs in libhbgpu's sm_100a kernels.
+
+Mirrors the public surface of the reference class chain ``HbondAnalysis -> NetworkAnalysis ->
+BasicFunctionality`` (``cgraphs/mdhbond/hbond.py:40-55,96-135,232-289``; ``network.py:40-107,1216-1220``;
+``basic.py:34-117``) for the H-bond path: same constructor keywords, same two ``set_hbonds_*`` methods,
+same result objects (``initial_results`` / ``filtered_results`` = ``dict[str, bool[nb_frames]]``,
+``initial_graph`` / ``filtered_graph`` = ``networkx.Graph``), ``filter_occupancy``, ``dump_to_file`` /
+``load_from_file`` / ``duplicate``.  Install as a drop-in with
+``cgraphs.mdhbond.HbondAnalysis = cgraphs_b200.mdhbond.HbondAnalysis``.
+
+``structure`` may be a path (needs MDAnalysis), a real ``MDAnalysis.Universe`` or a
+``cgraphs_b200.universe.Universe``.
+
+Extra keyword arguments (all optional, parity-preserving defaults): ``device`` (CUDA ordinal),
+``shard=(rank, world)`` to process only a contiguous frame block per rank and merge bond keys with one
+all-gather, ``cos_threshold`` to pin the calibrated angle threshold, ``batch_bytes``.
+
+Documented divergences from the reference: frames without any candidate pair / local water
+are frames without bonds here, while the reference raises IndexError (hbond.py:110,254,261).
+"""
+from __future__ import annotations
+
+import copy as _cp
+import pickle as _pickle
+
+import networkx as _nx
+import numpy as _np
+
+from . import _native
+from .calib import cos_threshold as _cos_threshold
+from .topology import AtomColumns, CompiledTopology, WATER_DEFINITION, pack_systems
+
+
+def dict2graph(bonds, residuewise=True):
+    """Same graph as the reference builds from a result dict (helpfunctions.py:120-134)."""
+    g = _nx.Graph()
+    cut = 3 if residuewise else 4
+    edges = []
+    for bond in bonds:
+        a, b = bond.split(':')
+        a = '-'.join(a.split('-')[:cut])
+        b = '-'.join(b.split('-')[:cut])
+        if int(a.split('-')[2]) > int(b.split('-')[2]):
+            a, b = b, a
+        if a != b:
+            edges.append((a, b))
+    g.add_edges_from(edges)
+    return g
+
+
+def _as_universe(structure, trajectories):
+    if isinstance(structure, (str, bytes)) or hasattr(structure, "__fspath__"):
+        try:
+            import MDAnalysis as _MDAnalysis
+        except ImportError as e:  # pragma: no cover - MDAnalysis is absent in the build image
+            raise ImportError("a structure path needs MDAnalysis; pass a Universe object instead") from e
+        return _MDAnalysis.Universe(structure, trajectories) if trajectories is not None else _MDAnalysis.Universe(structure)
+    if hasattr(structure, "select_atoms") and hasattr(structure, "trajectory"):
+        return structure
+    raise TypeError("structure must be a path or a Universe-like object")
+
+
+def _frame_blocks(universe, frame_indices, block):
+    """Yield float32 arrays [k, N, 3] covering `frame_indices` in order."""
+    traj = universe.trajectory
+    frames = getattr(traj, "frames", None)
+    i = 0
+    n = len(frame_indices)
+    contiguous = isinstance(frame_indices, range) and frame_indices.step == 1
+    while i < n:
+        j = min(n, i + block)
+        if frames is not None and contiguous and hasattr(frames, "block"):
+            yield _np.ascontiguousarray(frames.block(frame_indices[i], frame_indices[j - 1] + 1), dtype=_np.float32)
+        elif frames is not None and hasattr(frames, "frame"):
+            yield _np.stack([_np.asarray(frames.frame(f), dtype=_np.float32) for f in frame_indices[i:j]])
+        else:  # real MDAnalysis reader
+            out = _np.empty((j - i, len(universe.atoms), 3), dtype=_np.float32)
+            for k, f in enumerate(frame_indices[i:j]):
+                traj[f]
+                out[k] = universe.atoms.positions
+            yield out
+        i = j
+
+
+class HbondAnalysis(object):
+
+    def __init__(self, selection=None, structure=None, trajectories=None, distance=3.5, cut_angle=60.,
+                 start=None, stop=None, step=1, additional_donors=[],
+                 additional_acceptors=[], exclude_donors=[], exclude_acceptors=[],
+                 ions=[], check_angle=True, residuewise=True, add_donors_without_hydrogen=False,
+                 restore_filename=None, device=None, shard=None, cos_threshold=None, batch_bytes=None):
+        self._device = device
+        self._shard = shard
+        self._cos_threshold_override = cos_threshold
+        self._batch_bytes = batch_bytes
+        self._ctx = None
+        if restore_filename is not None:
+            self.load_from_file(restore_filename)
+            return
+        # basic.py:41-48
+        if selection is None: raise AssertionError('No selection string.')
+        if structure is None: raise AssertionError('No structure file path.')
+        self._selection = selection
+        self._structure = structure if isinstance(structure, (str, bytes)) else None
+        self._trajectories = trajectories
+        self._universe = _as_universe(structure, trajectories)
+        self._trajectory_slice = slice(start if isinstance(start, int) else None,
+                                       stop if isinstance(stop, int) else None, step)
+        self._mda_selection = self._universe.select_atoms(selection)
+        if not len(self._mda_selection): raise AssertionError('No atoms match the selection')
+        if ions:
+            raise NotImplementedError('ion interactions (hbond.py:57-94) are outside the accelerated path')
+        self._ions_list = ions
+        self._water = self._universe.select_atoms(WATER_DEFINITION)
+        self.initial_results = {}
+        self.filtered_results = {}
+        n_traj = len(self._universe.trajectory)
+        self._frame_indices = range(*self._trajectory_slice.indices(n_traj))
+        self.nb_frames = len(self._frame_indices)
+        self.applied_filters = {'resnames': None, 'segnames': None, 'shortest_paths': None, 'single_path': None,
+                                'occupancy': None, 'connected_component': None, 'shells': None,
+                                'avg_least_bonds': None, 'backbone': None}
+        # network.py:48-97
+        self.check_angle = check_angle
+        self.distance = distance
+        self.cut_angle = cut_angle
+        self._add_donors_without_hydrogen = add_donors_without_hydrogen
+        self.residuewise = residuewise
+        cols = AtomColumns(self._universe)
+        self._n_atoms = cols.n_atoms
+        pos0 = self._first_frame_positions()
+        top = CompiledTopology(cols, _np.asarray(self._mda_selection.indices), _np.asarray(self._water.indices), pos0,
+                               additional_donors=additional_donors, additional_acceptors=additional_acceptors,
+                               exclude_donors=exclude_donors, exclude_acceptors=exclude_acceptors,
+                               check_angle=check_angle, residuewise=residuewise,
+                               add_donors_without_hydrogen=add_donors_without_hydrogen)
+        self._topology = top
+        self.donor_names = top.donor_names
+        self.acceptor_names = top.acceptor_names
+        self._nb_donors = top.nD
+        self._nb_acceptors = top.nA
+        self._first_water_id = top.first_water
+        self._first_water_hydrogen_id = top.first_water_h
+        self._water_ids = top.water_ids
+        self._water_ids_atomwise = top.water_ids_atomwise
+        self._all_ids = top.all_ids
+        self._all_ids_atomwise = top.all_ids_atomwise
+        self._resids = top.resids
+        self.initial_graph = _nx.Graph()
+        self.filtered_graph = self.initial_graph
+        self.joint_occupancy_series = None
+        self.joint_occupancy_frames = None
+        self._exclude_backbone_backbone = True
+        self.add_missing_residues = 0
+        self._connection_position = None
+        self._i4_distribution = None
+        self.last_run_stats = None
+
+    # the reference measures donor-hydrogen distances after the frame-count loop has rewound the reader
+    # to frame 0 (basic.py:68, network.py:54)
+    def _first_frame_positions(self):
+        traj = self._universe.trajectory
+        frames = getattr(traj, "frames", None)
+        if frames is not None and hasattr(frames, "frame"):
+            return _np.asarray(frames.frame(0), dtype=_np.float32)
+        traj[0]
+        return _np.asarray(self._universe.atoms.positions, dtype=_np.float32)
+
+    @property
+    def heavy2hydrogen(self):
+        return self._topology.heavy2hydrogen()
+
+    # ---------------------------------------------------------------------------------------------
+    # the two accelerated methods
+    # ---------------------------------------------------------------------------------------------
+    def set_hbonds_in_selection(self, exclude_backbone_backbone=True):
+        """hbond.py:96-135."""
+        if self._nb_acceptors == 0: raise AssertionError('No acceptors in the selection')
+        if self._nb_donors == 0: raise AssertionError('No donors in the selection')
+        result = self._run("in_selection", 0.0, exclude_backbone_backbone)
+        self._set_results(result)
+
+    def set_hbonds_in_selection_and_water_around(self, around_radius, exclude_backbone_backbone=True):
+        """hbond.py:232-289."""
+        result = self._run("water_around", float(around_radius), exclude_backbone_backbone)
+        self._set_results(result)
+
+    def _context(self):
+        if self._ctx is None:
+            dev = self._device
+            if dev is None:
+                dev = 0
+                try:
+                    import torch
+                    if torch.cuda.is_available() and torch.cuda.is_initialized():
+                        dev = torch.cuda.current_device()
+                except Exception:
+                    pass
+            self._ctx = _native.Context(dev)
+            if self._batch_bytes:
+                self._ctx.set_option("batch_bytes", self._batch_bytes)
+        return self._ctx
+
+    def _check_hydrogen_tables(self, method):
+        top = self._topology
+        if self.check_angle and method == "water_around" and top.nW > 0:
+            if top.water_h_lists < top.nW or top.water_h_ragged:
+                raise IndexError('water hydrogens do not pair up as two per water; the reference indexes past '
+                                 'heavy2hydrogen here (network.py:86, helpfunctions.py:144)')
+
+    def _run(self, method, around_radius, exclude_backbone_backbone):
+        top = self._topology
+        self._check_hydrogen_tables(method)
+        ctx = self._context()
+        ids = top.key_ids(method)
+        tables, group_names = pack_systems([top], [ids], [self._n_atoms])
+        ctx.set_topology(tables)
+        cthr = self._cos_threshold_override
+        if cthr is None:
+            cthr = _cos_threshold(float(self.cut_angle)) if self.check_angle else -1.0
+        ctx.set_params(self.distance, around_radius, cthr, self.check_angle, exclude_backbone_backbone,
+                       _native.METHOD_WATER_AROUND if method == "water_around" else _native.METHOD_IN_SELECTION)
+        # frame block of this rank (block boundaries are multiples of 32 frames)
+        fi = self._frame_indices
+        lo, hi = 0, self.nb_frames
+        if self._shard is not None:
+            from .sharding import shard_range
+            lo, hi = shard_range(self.nb_frames, *self._shard)
+        n_local = hi - lo
+        keys = _np.zeros(0, _np.uint64)
+        words = _np.zeros((0, (max(n_local, 1) + 31) // 32), _np.uint32)
+        if n_local > 0:
+            ctx.begin(n_local)
+            block = max(1, min(n_local, int((256 << 20) // max(1, self._n_atoms * 12))))
+            for xyz in _frame_blocks(self._universe, fi[lo:hi], block):
+                ctx.submit(xyz)
+            keys, words = ctx.results()
+            self.last_run_stats = ctx.timers()
+        if self._shard is not None and self._shard[1] > 1:
+            from .sharding import merge_shards
+            keys, words = merge_shards(keys, words, lo, hi, self.nb_frames, self._shard, ctx)
+        return self._results_dict(keys, words, group_names, self.nb_frames)
+
+    @staticmethod
+    def _results_dict(keys, words, group_names, nb_frames):
+        """keys (group_first << 32 | group_second) + packed rows -> the reference's result dict."""
+        if len(keys) == 0:
+            return {}
+        bits = _np.unpackbits(words.view(_np.uint8), axis=1, bitorder="little")[:, :nb_frames].astype(bool)
+        first = (keys >> _np.uint64(32)).astype(_np.int64)
+        second = (keys & _np.uint64(0xFFFFFFFF)).astype(_np.int64)
+        return {group_names[a] + ':' + group_names[b]: bits[i] for i, (a, b) in enumerate(zip(first, second))}
+
+    # ---------------------------------------------------------------------------------------------
+    # result plumbing shared with the reference API
+    # ---------------------------------------------------------------------------------------------
+    def _set_results(self, result):                                   # basic.py:94-98
+        self.initial_results = result
+        self.filtered_results = result
+        self._generate_graph_from_current_results()
+        self._generate_filtered_graph_from_filtered_results()
+
+    def _add_overwrite_results(self, result):                         # basic.py:100-105
+        for bond in result:
+            self.initial_results[bond] = result[bond]
+        self.filtered_results = self.initial_results
+        self._generate_graph_from_current_results()
+        self._generate_filtered_graph_from_filtered_results()
+
+    def _generate_graph_from_current_results(self):                   # network.py:1216-1217
+        self.initial_graph = dict2graph(self.initial_results, self.residuewise)
+
+    def _generate_filtered_graph_from_filtered_results(self):         # network.py:1219-1220
+        self.filtered_graph = dict2graph(self.filtered_results, self.residuewise)
+
+    def filter_occupancy(self, min_occupancy, use_filtered=True):     # network.py:99-107
+        results = self.filtered_results if use_filtered else self.initial_results
+        if len(results) == 0: raise AssertionError('nothing to filter!')
+        filtered_result = {key: results[key] for key in results if _np.mean(results[key]) > min_occupancy}
+        if self.applied_filters['occupancy'] != None:
+            self.applied_filters['occupancy'] = max(self.applied_filters['occupancy'], min_occupancy)
+        else:
+            self.applied_filters['occupancy'] = min_occupancy
+        self.filtered_results = filtered_result
+        self._generate_filtered_graph_from_filtered_results()
+
+    def dump_to_file(self, fname):                                    # basic.py:71-81
+        tmp = _cp.copy(self)
+        for name in ('_universe', '_water', '_mda_selection', '_ctx', '_topology'):
+            tmp.__dict__[name] = None
+        with open(fname, 'wb') as af:
+            af.write(_pickle.dumps(tmp.__dict__))
+
+    def load_from_file(self, fname, reload_universe=False):           # basic.py:83-86
+        with open(fname, 'rb') as af:
+            state = _pickle.loads(af.read())
+        self.__dict__.update(state)
+        self._ctx = None
+        if reload_universe: self._reload_universe()
+
+    def _reload_universe(self):                                       # basic.py:88-92
+        if self._structure is None:
+            raise AssertionError('the analysis was created from a Universe object; pass it again to reload')
+        self._universe = _as_universe(self._structure, self._trajectories)
+        self._mda_selection = self._universe.select_atoms(self._selection)
+        self._water = self._universe.select_atoms(WATER_DEFINITION)
+
+    def duplicate(self):                                              # basic.py:116-117
+        return _cp.copy(self)
+
+    def __copy__(self):
+        new = self.__class__.__new__(self.__class__)
+        new.__dict__.update(self.__dict__)
+        new._ctx = None
+        return new
+
+    def close(self):
+        if self._ctx is not None:
+            self._ctx.close()
+            self._ctx = None

@@ -1,0 +1,82 @@
+"""Frame sharding across ranks and the bond-key merge.
+
+Frames are independent (reference hbond.py:103,238 keep no cross-frame state except OR-ing into the
+per-key vectors), so rank g processes one contiguous block of frames whose boundaries are multiples of
+32 frames - packed occupancy words are never shared between ranks.  The only exchange is at the end:
+one all-gather of each rank's sorted distinct bond keys (NCCL over NVLink when the process group is
+NCCL, gloo in the CPU tests) makes bond ids global, then the frame-sharded word columns are gathered so
+every rank holds the complete matrix, exactly as a single-GPU run would.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_range(n_frames, rank, world):
+    """Frame block [lo, hi) of `rank`; boundaries are multiples of 32."""
+    n_words = (n_frames + 31) // 32
+    lo = 32 * ((rank * n_words) // world)
+    hi = 32 * (((rank + 1) * n_words) // world)
+    return min(lo, n_frames), min(hi, n_frames)
+
+
+def _dist():
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized():
+        raise RuntimeError("shard=(rank, world) with world > 1 needs an initialised torch.distributed group")
+    return dist
+
+
+def merge_keys(local_keys, device=None, group=None):
+    """All-gather sorted distinct uint64 keys; returns the global sorted distinct key list (numpy uint64).
+
+    With an NCCL group the gather runs on `device` (keys travel GPU to GPU); with gloo on the CPU.
+    """
+    import torch
+    dist = _dist()
+    world = dist.get_world_size(group)
+    on_gpu = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", device if device is not None else torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    mine = torch.from_numpy(np.ascontiguousarray(local_keys).view(np.int64)).to(dev)
+    count = torch.tensor([mine.numel()], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(count) for _ in range(world)]
+    dist.all_gather(counts, count, group=group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    padded = torch.full((cap,), -1, dtype=torch.int64, device=dev)
+    padded[:mine.numel()] = mine
+    gathered = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(gathered, padded, group=group)            # the one key exchange
+    allk = torch.cat([g[:c] for g, c in zip(gathered, counts)])
+    allk = allk.cpu().numpy().view(np.uint64)
+    return np.unique(allk)
+
+
+def merge_shards(keys, words, lo, hi, n_frames, shard, ctx=None, group=None):
+    """Combine per-rank results into the global (keys, words) every rank returns.
+
+    keys: this rank's sorted distinct keys; words: uint32 [len(keys), ceil((hi-lo)/32)].
+    """
+    import torch
+    dist = _dist()
+    rank, world = shard
+    device = getattr(ctx, "device", None)
+    gkeys = merge_keys(keys, device=device, group=group)
+    n_words_total = (n_frames + 31) // 32
+    spans = [shard_range(n_frames, r, world) for r in range(world)]
+    widths = [((b - a) + 31) // 32 for a, b in spans]
+    wmax = max(max(widths), 1)
+    # my word columns, rows aligned to the global key list, padded to the widest shard
+    local = np.zeros((len(gkeys), wmax), dtype=np.uint32)
+    if len(keys):
+        local[np.searchsorted(gkeys, keys), :words.shape[1]] = words
+    on_gpu = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", device if device is not None else torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    t = torch.from_numpy(local.view(np.int32)).to(dev)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t, group=group)
+    out = np.zeros((len(gkeys), n_words_total), dtype=np.uint32)
+    for (a, b), w, part in zip(spans, widths, parts):
+        if w:
+            out[:, a // 32:a // 32 + w] = part[:, :w].cpu().numpy().view(np.uint32)
+    return gkeys, out

@@ -420,3 +420,109 @@ def c5_structures(n_structures=500, seed0=5000):
         n_res = int(rng.integers(120, 181))
         out.append(make_system(n_atoms, n_res, seed0 + i, hydrogens=False, water="HOH"))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Known-answer / adversarial micro-systems (SURVEY 4, 8d "adversarial add-ons")
+# ------------------------------------------------------------------------------------------------
+def _step_f32(x, k):
+    """x moved by k float32 ulps."""
+    x = np.float32(x)
+    for _ in range(abs(int(k))):
+        x = np.nextafter(x, np.float32(np.inf if k > 0 else -np.inf))
+    return x
+
+
+def _dist2_f64(p, q):
+    d = p.astype(np.float64) - q.astype(np.float64)
+    return (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]
+
+
+def kat_distance_system(n_pairs=1000, seed=0, r=3.5):
+    """Pairs of bare water oxygens (TIP3/OH2, no hydrogens) whose separation sits within a few
+    float32 ulps of the cut-off r, on both sides, plus axis-aligned pairs at exactly r.
+    Use with check_angle=False, add_donors_without_hydrogen=True, selection 'resname TIP3'."""
+    rng = np.random.default_rng([seed, 41])
+    side = int(np.ceil(n_pairs ** (1.0 / 3.0)))
+    xyz = np.zeros((2 * n_pairs, 3), dtype=np.float32)
+    r2 = np.float64(r) * np.float64(r)
+    for i in range(n_pairs):
+        cell = np.array([i % side, (i // side) % side, i // (side * side)], dtype=np.float64)
+        p1 = (cell * 12.0 + 6.0 + rng.uniform(-1, 1, 3)).astype(np.float32)
+        if i % 8 == 0:   # exactly representable separation along one axis
+            p1 = np.round(p1 * 2) / np.float32(2)
+            p2 = p1.copy()
+            ax = (i // 8) % 3
+            p2[ax] = p1[ax] + np.float32(r)
+            p2[ax] = _step_f32(p2[ax], (i // 24) % 3 - 1)
+        else:
+            u = _random_unit(rng, 1)[0]
+            p2 = (p1.astype(np.float64) + r * u).astype(np.float32)
+            ax = int(np.argmax(np.abs(u)))
+            sgn = 1 if p2[ax] > p1[ax] else -1
+            # walk outwards until just outside, then inwards to the last inside position
+            for _ in range(64):
+                if _dist2_f64(p1, p2) > r2:
+                    break
+                p2[ax] = _step_f32(p2[ax], sgn)
+            for _ in range(64):
+                if _dist2_f64(p1, p2) <= r2:
+                    break
+                p2[ax] = _step_f32(p2[ax], -sgn)
+            p2[ax] = _step_f32(p2[ax], sgn * ((i % 4) - 1))     # -1, 0 (last inside), +1 (first outside), +2
+        xyz[2 * i], xyz[2 * i + 1] = p1, p2
+    n = 2 * n_pairs
+    topo = Topology(["OH2"] * n, ["TIP3"] * n, np.arange(1, n + 1), ["W"] * n)
+    return SynthSystem(topo, xyz, np.arange(n), None, seed, dict(kind="kat_distance", n_pairs=n_pairs))
+
+
+def _cos_arg32(b, h, a):
+    """float32 cos_arg of ANG(b, h, a) in the reference's operation order (helpfunctions.py:96-102)."""
+    b, h, a = (np.asarray(t, dtype=np.float32) for t in (b, h, a))
+    v1 = h - b
+    v2 = a - h
+    d12 = (v1[0] * v2[0] + v1[1] * v2[1]) + v1[2] * v2[2]
+    d11 = (v1[0] * v1[0] + v1[1] * v1[1]) + v1[2] * v1[2]
+    d22 = (v2[0] * v2[0] + v2[1] * v2[1]) + v2[2] * v2[2]
+    return d12 / (np.sqrt(d11) * np.sqrt(d22))
+
+
+def kat_angle_system(n_pairs=1000, seed=0, cos_threshold=0.49999994, r_oo=2.9):
+    """TIP3 water pairs whose donor hydrogen makes cos_arg land within a few float32 ulps of the
+    angle threshold, on both sides.  Use with check_angle=True, selection 'resname TIP3'."""
+    rng = np.random.default_rng([seed, 43])
+    side = int(np.ceil(n_pairs ** (1.0 / 3.0)))
+    cthr = np.float32(cos_threshold)
+    xyz = np.zeros((n_pairs, 2, 3, 3), dtype=np.float32)
+    for i in range(n_pairs):
+        cell = np.array([i % side, (i // side) % side, i // (side * side)], dtype=np.float64)
+        o1 = cell * 12.0 + 6.0 + rng.uniform(-1, 1, 3)
+        u = _random_unit(rng, 1)[0]
+        v = np.cross(u, _random_unit(rng, 1)[0])
+        v /= np.linalg.norm(v)
+        o2 = o1 + r_oo * u
+        o1f, o2f = o1.astype(np.float32), o2.astype(np.float32)
+        # bisect the off-axis angle of the donor hydrogen so that cos_arg crosses the threshold
+        lo, hi = 0.0, np.pi / 2
+        for _ in range(60):
+            mid = 0.5 * (lo + hi)
+            h = (o1 + 0.96 * (np.cos(mid) * u + np.sin(mid) * v)).astype(np.float32)
+            if _cos_arg32(o2f, h, o1f) >= cthr:
+                lo = mid
+            else:
+                hi = mid
+        h = (o1 + 0.96 * (np.cos(lo) * u + np.sin(lo) * v)).astype(np.float32)
+        ax = int(np.argmax(np.abs(v)))
+        h[ax] = _step_f32(h[ax], (i % 7) - 3)
+        h2 = (o1 - 0.96 * u).astype(np.float32)                      # points away from the partner
+        w = np.cross(u, v)
+        h3 = (o2 + 0.96 * (np.cos(0.9) * u + np.sin(0.9) * w)).astype(np.float32)
+        h4 = (o2 + 0.96 * (np.cos(0.9) * u - np.sin(0.9) * w)).astype(np.float32)
+        xyz[i, 0] = [o1f, h, h2]
+        xyz[i, 1] = [o2f, h3, h4]
+    n_w = 2 * n_pairs
+    names = ["OH2", "H1", "H2"] * n_w
+    resids = np.repeat(np.arange(1, n_w + 1), 3)
+    topo = Topology(names, ["TIP3"] * (3 * n_w), resids, ["W"] * (3 * n_w))
+    parent = np.repeat(np.arange(0, 3 * n_w, 3), 3)
+    return SynthSystem(topo, xyz.reshape(-1, 3), parent, None, seed, dict(kind="kat_angle", n_pairs=n_pairs))

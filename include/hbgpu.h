@@ -1,0 +1,163 @@
+/* hbgpu.h - C ABI of libhbgpu.so: B200 (sm_100a) H-bond detection for cgraphs / Bridge HbondAnalysis.
+ *
+ * This is the drop-in boundary of the hot path.  The reference has no FFI of its own (it is
+ * pure Python); each entry point below names the reference code whose work it takes over
+ * (paths relative to the reference checkout, evabertalan/cgraphs):
+ *
+ *   hb_set_topology   <- tables built once per object by NetworkAnalysis.__init__
+ *                        cgraphs/mdhbond/network.py:40-97 (+ helpfunctions.py:44-83,107-117)
+ *   hb_set_params     <- distance / cut_angle / check_angle / residuewise kwargs, hbond.py:42-52, and the
+ *                        method arguments exclude_backbone_backbone / around_radius, hbond.py:96,232
+ *   hb_begin          <- `result = {}` + `frames = self.nb_frames`, hbond.py:98-100 / 234-236
+ *   hb_submit_frames  <- the per-frame loop body, hbond.py:103-132 (set_hbonds_in_selection) and
+ *                        hbond.py:238-286 (set_hbonds_in_selection_and_water_around): position fetch,
+ *                        cKDTree builds and ball queries, check_angle (helpfunctions.py:137-159),
+ *                        key building and result[key][frame] = True
+ *   hb_finalize / hb_get_keys / hb_get_bits
+ *                     <- the `result` dict handed to _set_results, hbond.py:134 / 288 (basic.py:94-98)
+ *
+ * Conventions: every function returns 0 on success or a negative hb_status; no C++ exception crosses the
+ * ABI; the message of the last failure is available from hb_last_error().  The caller owns every host
+ * buffer it passes in or out; the library owns all device memory, pinned staging buffers and streams.
+ * A context serves one submitting host thread; contexts are independent.  The library is compiled for
+ * sm_100a only and has no CPU fallback: without a usable GPU hb_create fails.
+ */
+#ifndef HBGPU_H
+#define HBGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hb_ctx hb_ctx;
+
+typedef enum {
+    HB_OK = 0,
+    HB_ERR_CUDA = -1,       /* a CUDA runtime call failed (message has the CUDA error string) */
+    HB_ERR_ARG = -2,        /* invalid argument / call order */
+    HB_ERR_NOMEM = -3,      /* host or device allocation failed */
+    HB_ERR_NODEVICE = -4,   /* no CUDA device / not sm_100 */
+    HB_ERR_STATE = -5       /* e.g. results requested before hb_finalize */
+} hb_status;
+
+#define HB_METHOD_IN_SELECTION 0   /* HbondAnalysis.set_hbonds_in_selection, hbond.py:96 */
+#define HB_METHOD_WATER_AROUND 1   /* HbondAnalysis.set_hbonds_in_selection_and_water_around, hbond.py:232 */
+
+#define HB_PBC_NONE 0              /* reference semantics: no periodic images */
+#define HB_PBC_ORTHO 1             /* opt-in minimum image, orthorhombic cell */
+#define HB_PBC_TRICLINIC 2         /* opt-in minimum image, triclinic cell */
+
+/* Topology tables.  "Entries" are the reference's index space donors ++ acceptors ++ waters
+ * (network.py:55-67): entry e < nD is a donor, nD <= e < nD+nA an acceptor, the rest waters.
+ * "Points" are the distinct heavy atoms behind those entries: selection points (atoms that are donor
+ * and/or acceptor; they may additionally be a water of the water group) and water points (waters of
+ * the water group that are not selection points).
+ *
+ * A topology holds n_systems >= 1 independent systems.  A trajectory uses one system for all frames.
+ * A batch of static structures (BASELINE config C5) uses one system per "frame"; entries of all systems
+ * share one global numbering, points and atoms are numbered per system through the offset arrays.
+ */
+typedef struct {
+    int32_t n_systems;
+    const int64_t* sys_atom_off;  /* [n_systems+1] atoms before each system in a ragged coordinate batch */
+    const int32_t* sys_sel_off;   /* [n_systems+1] ranges of selection points */
+    const int32_t* sys_wat_off;   /* [n_systems+1] ranges of water points */
+
+    int32_t n_sel;                /* selection points, all systems */
+    const int32_t* sel_atom;      /* atom index inside its system */
+    const int32_t* sel_don;       /* donor entry (global) or -1 */
+    const int32_t* sel_acc;       /* acceptor entry (global) or -1 */
+    const int32_t* sel_wat;       /* water entry (global) if the atom is also in the water group, else -1 */
+    const uint8_t* sel_bb;        /* 1 if the atom name is 'O' or 'N' (backbone filter, hbond.py:97,111) */
+
+    int32_t n_wat;                /* water points, all systems */
+    const int32_t* wat_atom;
+    const int32_t* wat_ent;       /* water entry (global) */
+
+    int32_t n_ent;                /* entries, all systems */
+    const int32_t* ent_group;     /* key group id: index of the entry's id string among the distinct ids */
+    const int32_t* ent_resid;     /* _resids, network.py:89 (orientation rule hbond.py:120-122) */
+    const int32_t* ent_residue;   /* id of 'segid-resname-resid' (same-residue skip, hbond.py:125-127) */
+    const int32_t* ent_h_off;     /* [n_ent+1] CSR into ent_h_atom = heavy2hydrogen, network.py:86 */
+    int32_t n_ent_h;
+    const int32_t* ent_h_atom;    /* hydrogen atom index inside its system */
+} hb_topology;
+
+typedef struct {
+    double distance;              /* heavy-atom cut-off, A (hbond.py:42, default 3.5) */
+    double around_radius;         /* water_around only: local-water radius (hbond.py:232,251) */
+    float cos_threshold;          /* smallest float32 cos_arg that still satisfies
+                                     rad2deg(arccos(c)) <= float32(cut_angle) on the host's numpy
+                                     (helpfunctions.py:102-104,155) */
+    int32_t check_angle;          /* hbond.py:113,265 */
+    int32_t exclude_backbone_backbone; /* hbond.py:96,232 */
+    int32_t method;               /* HB_METHOD_* */
+    int32_t pbc_mode;             /* HB_PBC_*; HB_PBC_NONE reproduces the reference */
+    int32_t structure_batch;      /* 0: trajectory of system 0; 1: frame f is system f (ragged batch) */
+} hb_params;
+
+typedef struct {
+    double ms_total;              /* device time of all search kernels since hb_begin (CUDA events) */
+    double ms_h2d;                /* device time of the host->device frame copies */
+    double ms_kernel[16];         /* per kernel class, filled when profiling is on (see hb_kernel_name) */
+    int64_t launches[16];
+    int64_t n_launches;           /* kernels launched since hb_begin */
+    int64_t frames;               /* frames processed since hb_begin */
+    int64_t pairs_emitted;        /* H-bond hits (entry pairs passing all criteria), all frames */
+    int64_t table_capacity;       /* bond hash-table slots */
+    int64_t table_grows;
+} hb_timers;
+
+int hb_create(hb_ctx** out, int device_ordinal);
+int hb_destroy(hb_ctx* ctx);
+const char* hb_last_error(hb_ctx* ctx);            /* ctx may be NULL: message of the last failed hb_create */
+const char* hb_version(void);
+const char* hb_kernel_name(int kernel_class);      /* names for hb_timers.ms_kernel[]; NULL past the end */
+
+int hb_set_topology(hb_ctx* ctx, const hb_topology* topo);
+int hb_set_entry_groups(hb_ctx* ctx, const int32_t* ent_group, int32_t n_ent); /* swap key ids only */
+int hb_set_params(hb_ctx* ctx, const hb_params* params);
+int hb_set_option(hb_ctx* ctx, const char* name, int64_t value);
+        /* "batch_bytes": device budget per frame batch; "table_capacity": initial bond-table slots;
+           "profile": 1 = time every kernel class with CUDA events; "max_batch_frames" */
+
+/* Start an analysis over n_frames_total frames (the width of the occupancy matrix). */
+int hb_begin(hb_ctx* ctx, int64_t n_frames_total);
+
+/* Feed the next n_frames frames.  xyz is float32 [n_frames][n_atoms][3] in host memory (pinned memory is
+ * copied directly, pageable memory goes through the library's two pinned staging buffers).  With
+ * structure_batch the frames are systems [next, next + n_frames) concatenated raggedly.
+ * box: NULL, or 9 floats per frame (lattice vectors as rows) when pbc_mode != HB_PBC_NONE.
+ * Asynchronous: returns once the last batch is queued; buffers passed in may be reused after return. */
+int hb_submit_frames(hb_ctx* ctx, const float* xyz, int64_t n_atoms, int64_t n_frames, const float* box);
+
+/* Same, for coordinates already resident in device memory (the caller guarantees they are complete). */
+int hb_submit_frames_device(hb_ctx* ctx, const float* d_xyz, int64_t n_atoms, int64_t n_frames,
+                            const float* d_box);
+
+/* Wait for all queued work, sort the distinct bond keys, gather the occupancy rows in key order. */
+int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond);
+
+/* keys[i] = (group_first << 32) | group_second, ascending; bits = [n_bonds][words_per_bond] uint32, bit
+ * (f & 31) of word (f >> 5) of row i is set iff bond i exists in frame f. */
+int hb_get_keys(hb_ctx* ctx, uint64_t* keys);
+int hb_get_bits(hb_ctx* ctx, uint32_t* words);
+/* Device-side access for collectives: copy keys / rows into caller-provided DEVICE buffers. */
+int hb_get_keys_device(hb_ctx* ctx, uint64_t* d_keys);
+int hb_get_bits_device(hb_ctx* ctx, uint32_t* d_words);
+/* Per-bond popcount over frames (occupancy numerator; network.py:99-107 filter_occupancy). */
+int hb_get_counts(hb_ctx* ctx, int64_t* counts);
+
+int hb_get_timers(hb_ctx* ctx, hb_timers* out);
+int hb_sync(hb_ctx* ctx);
+
+/* Pinned host memory helpers for callers that want zero-staging H2D. */
+int hb_host_alloc(void** ptr, uint64_t bytes);
+int hb_host_free(void* ptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HBGPU_H */

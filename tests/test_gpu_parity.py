@@ -1,0 +1,251 @@
+"""Parity of the CUDA path (through the C ABI / drop-in class) against the golden vectors of the live
+reference and against the CPU oracle on seeded systems.  Bit-exact: same key set, identical bool vectors."""
+import itertools
+
+import numpy as np
+import pytest
+
+from cgraphs_b200 import synth
+from cgraphs_b200.universe import Universe
+from tests.helpers import assert_same_results, golden_cases, graph_edges, lists_to_results, load_golden
+
+pytestmark = pytest.mark.gpu
+
+_CACHE = {}
+
+
+def _fixture(name):
+    if name not in _CACHE:
+        _CACHE[name] = load_golden(name)
+    return _CACHE[name]
+
+
+def _run_gpu(u, selection, method, around=3.5, excl_bb=True, cos_threshold=None, **kw):
+    from cgraphs_b200.mdhbond import HbondAnalysis
+    hba = HbondAnalysis(selection, u, cos_threshold=cos_threshold, **kw)
+    if method == "in_selection":
+        hba.set_hbonds_in_selection(exclude_backbone_backbone=excl_bb)
+    else:
+        hba.set_hbonds_in_selection_and_water_around(around, exclude_backbone_backbone=excl_bb)
+    return hba
+
+
+def _run_port(u, selection, method, around=3.5, excl_bb=True, **kw):
+    from oracle import hbond_port
+    return hbond_port.run(u, selection, method, around=around, exclude_backbone_backbone=excl_bb, **kw)
+
+
+@pytest.mark.parametrize("name,idx", golden_cases())
+def test_gpu_matches_golden(name, idx):
+    u, runs = _fixture(name)
+    run = runs[idx]
+    expect = lists_to_results(run["results"], run["nb_frames"])
+    hba = _run_gpu(u, run["selection"], run["method"], run["around"], run["excl_bb"],
+                   cos_threshold=run["cos_threshold"] if run["kwargs"].get("check_angle", True) else None,
+                   **run["kwargs"])
+    assert hba.nb_frames == run["nb_frames"]
+    assert_same_results(hba.initial_results, expect, "%s[%d]" % (name, idx))
+    assert hba.initial_results is hba.filtered_results
+    assert graph_edges(hba.filtered_graph) == {frozenset(e) for e in run["graph_edges"]}
+    assert all(v.dtype == bool and v.shape == (run["nb_frames"],) for v in hba.initial_results.values())
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_gpu_matches_port_random(seed):
+    s = synth.make_system(4000, 40, 300 + seed, hydrogens=True, water="TIP3", n_chains=2)
+    u = s.universe(5)
+    for sel, method, ca, rw in itertools.product(["protein", "protein or resname TIP3"],
+                                                 ["in_selection", "water_around"], [True, False], [True, False]):
+        kw = dict(check_angle=ca, residuewise=rw, additional_donors=['N'], additional_acceptors=['O'])
+        a = _run_gpu(u, sel, method, **kw)
+        b = _run_port(u, sel, method, **kw)
+        assert_same_results(a.initial_results, b.initial_results, "%s %s %s %s" % (sel, method, ca, rw))
+        assert graph_edges(a.filtered_graph) == graph_edges(b.filtered_graph)
+
+
+@pytest.mark.parametrize("cfg_name,scale,frames", [("C1", 1.0, 1), ("C2", 1.0, 8), ("C3", 0.5, 4), ("C3", 1.0, 2)])
+def test_gpu_matches_port_baseline_configs(cfg_name, scale, frames):
+    s, cfg = synth.config(cfg_name, scale=scale)
+    u = s.universe(frames, static=cfg["static"])
+    kw = dict(check_angle=cfg["check_angle"], add_donors_without_hydrogen=cfg["add_donors_without_hydrogen"])
+    for method in ("in_selection", "water_around"):
+        a = _run_gpu(u, cfg["selection"], method, cfg["around"], **kw)
+        b = _run_port(u, cfg["selection"], method, cfg["around"], **kw)
+        assert len(b.initial_results) > 0
+        assert_same_results(a.initial_results, b.initial_results, "%s %s" % (cfg_name, method))
+
+
+def test_gpu_all_waters_in_selection_c2():
+    s, cfg = synth.config("C2", scale=0.4)
+    u = s.universe(3)
+    a = _run_gpu(u, "protein or resname TIP3", "in_selection")
+    b = _run_port(u, "protein or resname TIP3", "in_selection")
+    assert len(b.initial_results) > 1000
+    assert_same_results(a.initial_results, b.initial_results)
+
+
+@pytest.mark.parametrize("seed", [5, 6])
+def test_gpu_kat_other_seeds(seed):
+    """Fresh adversarial systems (not the committed ones) against the oracle on this host."""
+    from cgraphs_b200.mdhbond.calib import cos_threshold
+    s = synth.kat_distance_system(1200, seed)
+    u = s.universe(1, static=True)
+    kw = dict(check_angle=False, add_donors_without_hydrogen=True)
+    a, b = _run_gpu(u, "resname TIP3", "in_selection", **kw), _run_port(u, "resname TIP3", "in_selection", **kw)
+    assert 300 < len(b.initial_results) < 900
+    assert_same_results(a.initial_results, b.initial_results, "kat_distance")
+    for cut in (60., 45., 30.):
+        s = synth.kat_angle_system(700, seed, cos_threshold=cos_threshold(cut))
+        u = s.universe(1, static=True)
+        a = _run_gpu(u, "resname TIP3", "water_around", cut_angle=cut)
+        b = _run_port(u, "resname TIP3", "water_around", cut_angle=cut)
+        assert 200 < len(b.initial_results) < 600
+        assert_same_results(a.initial_results, b.initial_results, "kat_angle %s" % cut)
+
+
+def test_gpu_invariances():
+    """Translation by a float32-exact offset, atom-order-preserving frame permutation, frame slicing."""
+    s = synth.make_system(3000, 30, 77)
+    xyz = s.frames(0, 6)
+    u = Universe(s.topology, xyz)
+    base = _run_gpu(u, "protein", "water_around").initial_results
+    # permuting frames permutes result columns
+    perm = np.array([3, 0, 5, 1, 4, 2])
+    up = Universe(s.topology, xyz[perm])
+    rp = _run_gpu(up, "protein", "water_around").initial_results
+    assert set(rp) == set(base)
+    for k in base:
+        assert np.array_equal(rp[k], base[k][perm])
+    # start/stop/step
+    sl = _run_gpu(u, "protein", "water_around", start=1, stop=6, step=2).initial_results
+    for k, v in sl.items():
+        assert np.array_equal(v, base[k][1:6:2])
+    assert {k for k, v in base.items() if v[1:6:2].any()} == set(sl)
+
+
+def test_gpu_empty_and_degenerate_frames():
+    """Frames without any candidate pair are all-False columns (documented divergence)."""
+    s = synth.make_system(2000, 20, 9)
+    xyz = s.frames(0, 3)
+    # frame 1: blow the system up so nothing is within 3.5 A (hydrogens stay bonded in frame 0)
+    centre = xyz[1].mean(axis=0)
+    xyz[1] = (xyz[1] - centre) * 40.0 + centre
+    u = Universe(s.topology, xyz)
+    a = _run_gpu(u, "protein", "water_around").initial_results
+    b = _run_port(u, "protein", "water_around").initial_results
+    assert_same_results(a, b)
+    assert not any(v[1] for v in a.values())
+    # identical coordinates for everything: all pairs at distance 0
+    xyz0 = np.zeros_like(xyz[:1])
+    u0 = Universe(s.topology, np.concatenate([xyz[:1], xyz0]))
+    a = _run_gpu(u0, "protein", "in_selection", check_angle=False).initial_results
+    b = _run_port(u0, "protein", "in_selection", check_angle=False).initial_results
+    assert_same_results(a, b)
+
+
+def test_gpu_error_behaviour():
+    from cgraphs_b200.mdhbond import HbondAnalysis
+    s = synth.make_system(1500, 10, 3)
+    u = s.universe(1)
+    with pytest.raises(AssertionError, match="No selection string"):
+        HbondAnalysis(None, u)
+    with pytest.raises(AssertionError, match="No structure file path"):
+        HbondAnalysis("protein", None)
+    with pytest.raises(AssertionError, match="No atoms match the selection"):
+        HbondAnalysis("resname XXX", u)
+    with pytest.raises(AssertionError, match="neither donors nor acceptors"):
+        HbondAnalysis("name CA", u)
+    h = HbondAnalysis("name NZ", u)     # donors (and acceptors by the N-rule) only of one kind is fine
+    h = HbondAnalysis("name OD1", u)
+    with pytest.raises(AssertionError, match="No donors in the selection"):
+        h.set_hbonds_in_selection()
+
+
+def test_gpu_table_growth_and_batches():
+    """Tiny initial bond table and tiny batches: the table must grow and batches re-run without loss."""
+    from cgraphs_b200.mdhbond import HbondAnalysis
+    s, cfg = synth.config("C2", scale=0.3)
+    u = s.universe(70)
+    ref = _run_port(u, "protein or resname TIP3", "water_around").initial_results
+    hba = HbondAnalysis("protein or resname TIP3", u, batch_bytes=8 << 20)
+    ctx = hba._context()
+    ctx.set_option("table_capacity", 1024)
+    ctx.set_option("max_batch_frames", 7)
+    hba.set_hbonds_in_selection_and_water_around(3.5)
+    assert_same_results(hba.initial_results, ref)
+    assert hba.last_run_stats["table_grows"] >= 1
+    assert hba.last_run_stats["frames"] == 70
+
+
+def test_gpu_device_resident_and_pinned_paths():
+    """hb_submit_frames from pinned memory and hb_submit_frames_device give the same matrix as pageable."""
+    import torch
+    from cgraphs_b200.mdhbond import HbondAnalysis, _native
+    from cgraphs_b200.mdhbond.topology import pack_systems
+    s = synth.make_system(6000, 50, 31)
+    nf = 40
+    xyz = s.frames(0, nf)
+    u = Universe(s.topology, xyz)
+    hba = HbondAnalysis("protein", u)
+    hba.set_hbonds_in_selection_and_water_around(3.5)
+    ctx = hba._context()
+    # same context, same topology/params: re-run from other sources
+    outs = []
+    ctx.begin(nf)
+    ctx.submit(xyz)
+    outs.append(ctx.results())
+    pin = _native.PinnedBuffer(xyz.shape)
+    pin.array[...] = xyz
+    ctx.begin(nf)
+    ctx.submit_raw(pin.ptr, xyz.shape[1], nf)
+    outs.append(ctx.results())
+    d = torch.from_numpy(xyz).cuda()
+    torch.cuda.synchronize()
+    ctx.begin(nf)
+    ctx.submit_device(d.data_ptr(), xyz.shape[1], nf // 2)
+    ctx.submit_device(d.data_ptr() + (nf // 2) * xyz.shape[1] * 12, xyz.shape[1], nf - nf // 2)
+    outs.append(ctx.results())
+    pin.free()
+    for k, w in outs[1:]:
+        assert np.array_equal(k, outs[0][0]) and np.array_equal(w, outs[0][1])
+    assert len(outs[0][0]) == len(hba.initial_results)
+    counts = ctx.counts(len(outs[0][0]))
+    bits = np.unpackbits(outs[0][1].view(np.uint8), axis=1, bitorder="little")[:, :nf]
+    assert np.array_equal(counts, bits.sum(axis=1))
+
+
+def test_gpu_structure_batch_c5():
+    """Config C5 in miniature: independent static structures searched in one batched launch."""
+    from cgraphs_b200.mdhbond import HbondBatch
+    systems = synth.c5_structures(12, seed0=5000)
+    unis = [s.universe(1, static=True) for s in systems]
+    kw = dict(check_angle=False, add_donors_without_hydrogen=True)
+    batch = HbondBatch(unis, "protein", **kw)
+    for method in ("in_selection", "water_around"):
+        if method == "in_selection":
+            res = batch.set_hbonds_in_selection()
+        else:
+            res = batch.set_hbonds_in_selection_and_water_around(3.5)
+        for u, r in zip(unis, res):
+            b = _run_port(u, "protein", method, **kw)
+            assert_same_results(r.initial_results, b.initial_results, "batch %s" % method)
+            assert graph_edges(r.filtered_graph) == graph_edges(b.filtered_graph)
+    assert batch.occupancy.shape[1] == 12
+
+
+def test_gpu_dump_and_restore(tmp_path):
+    from cgraphs_b200.mdhbond import HbondAnalysis
+    s = synth.make_system(2000, 20, 13)
+    u = s.universe(3)
+    hba = HbondAnalysis("protein", u)
+    hba.set_hbonds_in_selection_and_water_around(3.5)
+    f = str(tmp_path / "hba.pkl")
+    hba.dump_to_file(f)
+    back = HbondAnalysis(restore_filename=f)
+    assert_same_results(back.initial_results, hba.initial_results)
+    assert graph_edges(back.filtered_graph) == graph_edges(hba.filtered_graph)
+    hba.filter_occupancy(0.5)
+    assert all(v.mean() > 0.5 for v in hba.filtered_results.values())
+    assert hba.applied_filters['occupancy'] == 0.5
+    dup = hba.duplicate()
+    assert dup.filtered_results is hba.filtered_results
