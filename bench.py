@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Benchmark of the H-bond hot path on BASELINE.json's headline workload.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config C3): 100,000-atom membrane-protein-like synthetic system x 10,000 frames, triclinic
+box, `set_hbonds_in_selection_and_water_around(3.5)`, 3.5 A + 60 deg angle criterion, selection `protein`.
+One "step" = one full pass of the hot path over all 10,000 frames.
+
+* `value`  : frames/s with the frames already resident in HBM (hb_submit_frames_device), device-timed.
+* `e2e`    : frames/s through the C ABI with HOST (pinned) frames: H2D streaming of all frames and the D2H
+             read of bond keys + occupancy matrix inside the timed region.
+* `roofline`: algorithmic bytes of the dominant kernel / its CUDA-event time, against the measured HBM peak.
+* `cpu_baseline`: the CPU oracle port (1 core) on a bounded sample of the same frames.
+* `--impl reference`: the CPU path with all host cores on a bounded sample per step.
+
+Multi-GPU (torchrun, one rank per GPU): weak scaling - every rank processes its own 10,000-frame block of
+one long trajectory; the only exchange is the all-gather of distinct bond keys at the end of each pass.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "C3"
+SELECTION = "protein"
+AROUND = 3.5
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_case(scale, n_frames):
+    from cgraphs_b200 import synth
+    system, cfg = synth.config(WORKLOAD, scale=scale)
+    cfg["n_frames"] = n_frames
+    return system, cfg
+
+
+def algorithmic_bytes(top, n_bonds):
+    """12 B x distinct atoms whose coordinates the method reads + one output bit per bond."""
+    n_part = len(top.sel_atom) + len(top.wat_atom) + len(np.unique(top.h_atom))
+    return 12 * n_part + (n_bonds + 7) // 8, n_part
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arms
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    pt, xyz, method, around = args
+    from oracle import hbond_port
+    t = time.perf_counter()
+    res = hbond_port.run_block(pt, xyz, method, around, nb_frames=len(xyz))
+    return time.perf_counter() - t, len(res)
+
+
+def cpu_port_rate(system, cfg, frames_xyz, n_procs):
+    """frames/s of the oracle port over frames_xyz using n_procs processes (frame sharded)."""
+    from oracle import hbond_port
+    from cgraphs_b200.universe import Universe
+    u = Universe(system.topology, frames_xyz[:1])
+    pt = hbond_port.PortTopology(u, SELECTION, check_angle=cfg["check_angle"],
+                                 add_donors_without_hydrogen=cfg["add_donors_without_hydrogen"])
+    method = "water_around"
+    if n_procs <= 1:
+        t = time.perf_counter()
+        hbond_port.run_block(pt, frames_xyz, method, AROUND, nb_frames=len(frames_xyz))
+        dt = time.perf_counter() - t
+        return len(frames_xyz) / dt, dt
+    import multiprocessing as mp
+    chunks = np.array_split(np.arange(len(frames_xyz)), n_procs)
+    jobs = [(pt, frames_xyz[c[0]:c[-1] + 1], method, AROUND) for c in chunks if len(c)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(len(jobs)) as pool:
+        pool.map(_cpu_worker, [(pt, frames_xyz[:1], method, AROUND)] * len(jobs))   # spin-up, untimed
+        t = time.perf_counter()
+        pool.map(_cpu_worker, jobs)
+        dt = time.perf_counter() - t
+    return len(frames_xyz) / dt, dt
+
+
+def run_reference_arm(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    scale = args.scale
+    system, cfg = build_case(scale, args.frames)
+    cores = os.cpu_count() or 1
+    per_step = max(cores * 4, 32)
+    xyz = system.frames(0, per_step)
+    times = []
+    for i in range(args.warmup + args.steps):
+        rate, dt = cpu_port_rate(system, cfg, xyz, cores)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1000.0 * float(np.mean(times))
+    value = per_step / (ms / 1000.0)
+    sample = "%d frames of the %d-atom workload per step, frame-sharded over %d processes" % (per_step, system.n_atoms, cores)
+    line = {"impl": "reference", "metric": "hbond_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 distance / f32 angle", "data": "synthetic",
+            "config": workload_config(system, cfg, args),
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(system, cfg, args):
+    return {"workload": "C3: %d-atom membrane-protein-like system x %d frames per GPU, triclinic box, "
+                        "set_hbonds_in_selection_and_water_around(3.5), 3.5 A + 60 deg, selection 'protein'"
+                        % (system.n_atoms, args.frames),
+            "n_atoms": system.n_atoms, "n_frames_per_gpu": args.frames, "selection": SELECTION, "method": "water_around",
+            "check_angle": True, "pbc": "none (reference semantics; skin system)",
+            "cache": "inputs (%.1f GB of frames per GPU) are far larger than the 126 MB L2" % (system.n_atoms * 12 * args.frames / 1e9)}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from cgraphs_b200 import build as hb_build
+    hb_build.build()
+    from cgraphs_b200.mdhbond import HbondAnalysis, _native
+    from cgraphs_b200.mdhbond.calib import cos_threshold
+    from cgraphs_b200.mdhbond.topology import pack_systems
+    from cgraphs_b200.mdhbond.sharding import merge_keys
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local_rank = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: no CUDA device is visible (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    system, cfg = build_case(args.scale, args.frames)
+    nf, na = args.frames, system.n_atoms
+    f0 = rank * nf                                      # weak scaling: each rank owns its own frame block
+    # frames generated on the device (synthetic data), then one copy to pinned host memory for the e2e arm
+    d_xyz = torch.empty((nf, na, 3), dtype=torch.float32, device=dev)
+    system.frames_torch(f0, f0 + nf, dev, out=d_xyz)
+    torch.cuda.synchronize()
+
+    u = system.universe(1)
+    hba = HbondAnalysis(SELECTION, u, check_angle=cfg["check_angle"], device=local_rank,
+                        add_donors_without_hydrogen=cfg["add_donors_without_hydrogen"])
+    top = hba._topology
+    tables, group_names = pack_systems([top], [top.key_ids("water_around")], [na])
+    ctx = hba._context()
+    ctx.set_topology(tables)
+    ctx.set_params(3.5, AROUND, cos_threshold(60.0), True, True, _native.METHOD_WATER_AROUND)
+    ctx.set_option("profile", 1)
+    if args.batch_bytes:
+        ctx.set_option("batch_bytes", args.batch_bytes)
+
+    def one_pass_device():
+        ctx.begin(nf)
+        ctx.submit_device(d_xyz.data_ptr(), na, nf)
+        nb, wpr = ctx.finalize()
+        if world > 1:                                   # the one exchange: distinct bond keys
+            k = torch.empty(max(nb, 1), dtype=torch.int64, device=dev)
+            ctx.keys_to_device(k.data_ptr())
+            merge_keys(k[:nb].cpu().numpy().view(np.uint64), device=local_rank)
+        return nb, wpr
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_pass_device()
+    sampler = ClockSampler(local_rank)
+    sync_all()
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms = 0.0
+    launches = 0
+    kernel_ms = {}
+    kernel_launches = {}
+    for _ in range(args.steps):
+        nb, wpr = one_pass_device()
+        tm = ctx.timers()
+        dev_ms += tm["ms_run"]
+        launches += tm["n_launches"]
+        for k, v in tm["ms_kernel"].items():
+            kernel_ms[k] = kernel_ms.get(k, 0.0) + v
+            kernel_launches[k] = kernel_launches.get(k, 0) + tm["launches"][k]
+    sync_all()
+    wall_ms = 1000.0 * (time.perf_counter() - t0)
+    clocks = sampler.stop()
+    # max over ranks of the device-timed pass (CUDA events begin -> finalize), cross-checked by wall clock
+    t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max = float(t[0]), float(t[1])
+    ms_per_step = dev_ms_max / args.steps
+    value = world * nf / (ms_per_step / 1000.0)
+
+    # ---- e2e: host frames through the C ABI (H2D inside the timed region, results read back) ----
+    e2e = None
+    if not args.no_e2e:
+        try:
+            pin = _native.PinnedBuffer((nf, na, 3))
+            host = pin.array
+            pinned = True
+        except Exception:
+            pin, host, pinned = None, np.empty((nf, na, 3), dtype=np.float32), False
+        chunk = max(1, (1 << 30) // (na * 12))
+        for s in range(0, nf, chunk):
+            host[s:s + chunk] = d_xyz[s:s + chunk].cpu().numpy()
+
+        def one_pass_host():
+            ctx.begin(nf)
+            ctx.submit_raw(host.ctypes.data, na, nf)
+            keys, words = ctx.results()
+            if world > 1:
+                merge_keys(keys, device=local_rank)
+            return keys, words
+
+        one_pass_host()
+        sync_all()
+        t0 = time.perf_counter()
+        e2e_steps = max(1, min(args.steps, 3))
+        for _ in range(e2e_steps):
+            keys, words = one_pass_host()
+        sync_all()
+        e2e_ms = 1000.0 * (time.perf_counter() - t0)
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t[0]) / e2e_steps
+        e2e = {"value": world * nf / (e2e_ms / 1000.0), "unit": "frames/s", "h2d_bytes_per_step": int(nf) * na * 12,
+               "d2h_bytes_per_step": int(keys.nbytes + words.nbytes), "ms_per_step": e2e_ms,
+               "host_memory": "pinned" if pinned else "pageable", "timer": "wall clock between device synchronisations"}
+        if pin is not None:
+            pin.free()
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    peak, peak_kind = measured_peaks()
+    bytes_frame, n_part = algorithmic_bytes(top, nb)
+    dom = max(kernel_ms, key=lambda k: kernel_ms[k]) if kernel_ms else None
+    roofline = None
+    if dom and kernel_ms[dom] > 0:
+        n_l = kernel_launches[dom]
+        frames_per_launch = args.steps * nf / n_l
+        avg_ms = kernel_ms[dom] / n_l
+        achieved = bytes_frame * frames_per_launch / (avg_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                    "algorithmic_bytes_per_frame": bytes_frame, "frames_per_launch": frames_per_launch,
+                    "avg_launch_ms": avg_ms, "kernel_share_of_step": kernel_ms[dom] / sum(kernel_ms.values()),
+                    "whole_path_frac": bytes_frame * (nf / (ms_per_step / 1e3)) / 1e9 / peak,
+                    "kernel_ms_per_step": {k: v / args.steps for k, v in kernel_ms.items()}}
+
+    # ---- CPU baseline: oracle port, 1 core, bounded sample of the same frames -----------------------
+    cpu = None
+    if not args.no_cpu:
+        sample_n = args.cpu_frames
+        sample = d_xyz[:sample_n].cpu().numpy()
+        rate, dt = cpu_port_rate(system, cfg, sample, 1)
+        cpu = {"value": rate, "unit": "frames/s", "cores": 1, "kind": "port",
+               "sample": "first %d frames of the same %d-atom trajectory (%.1f s of CPU work), oracle/hbond_port.py"
+                         % (sample_n, na, dt)}
+
+    line = {"metric": "hbond_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64 distance / f32 angle", "data": "synthetic",
+            "config": workload_config(system, cfg, args),
+            "atom_frames_per_s": value * na, "wall_ms_per_step": wall_ms_max / args.steps,
+            "n_bonds": int(nb), "n_part_atoms": int(n_part),
+            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=10000, help="frames per GPU (BASELINE config: 10000)")
+    ap.add_argument("--scale", type=float, default=1.0, help="atom-count scale of the workload (1.0 = BASELINE config)")
+    ap.add_argument("--cpu-frames", type=int, default=1024)
+    ap.add_argument("--batch-bytes", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours" and not os.environ.get("HB_BENCH_ALLOW_SHORT_WARMUP"):
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

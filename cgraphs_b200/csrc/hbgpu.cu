@@ -755,6 +755,7 @@ struct hb_ctx {
     long long n_frames_total = 0, next_frame = 0;
     BondTable bt{};
     long long table_cap = 0;
+    long long alloc_sig[7] = {0, 0, 0, 0, 0, 0, 0};
     int table_grows = 0;
     int* h_status = nullptr;          // pinned: [0] n_keys, [1] overflow
     unsigned long long* h_hits = nullptr;
@@ -768,6 +769,7 @@ struct hb_ctx {
     float* h_stage[2] = {nullptr, nullptr};
     size_t in_bytes = 0;
     cudaEvent_t ev_copied[2]{}, ev_done[2]{};
+    cudaEvent_t ev_run0{}, ev_run1{};
     long long batch_counter = 0;
 
     struct Slot { bool busy; const float* d_xyz; long long f0; int nf; long long apf; };
@@ -894,6 +896,8 @@ int hb_create(hb_ctx** out, int device) {
         cudaEventCreateWithFlags(&ctx->ev_copied[k], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming);
     }
+    cudaEventCreate(&ctx->ev_run0);
+    cudaEventCreate(&ctx->ev_run1);
     cudaHostAlloc((void**)&ctx->h_status, 4 * sizeof(int), cudaHostAllocDefault);
     cudaHostAlloc((void**)&ctx->h_hits, sizeof(unsigned long long), cudaHostAllocDefault);
     *out = ctx;
@@ -929,6 +933,8 @@ int hb_destroy(hb_ctx* ctx) {
     free_list(ctx->topo_allocs);
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     for (int k = 0; k < 2; ++k) { cudaEventDestroy(ctx->ev_copied[k]); cudaEventDestroy(ctx->ev_done[k]); }
+    cudaEventDestroy(ctx->ev_run0);
+    cudaEventDestroy(ctx->ev_run1);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->h_hits) cudaFreeHost(ctx->h_hits);
     cudaStreamDestroy(ctx->s_compute);
@@ -958,6 +964,7 @@ int hb_set_topology(hb_ctx* ctx, const hb_topology* t) {
     CK(cudaSetDevice(ctx->device));
     free_list(ctx->topo_allocs);
     ctx->have_topo = false;
+    memset(ctx->alloc_sig, 0, sizeof(ctx->alloc_sig));
     int ns = t->n_systems;
     ctx->h_sys_atom_off.assign(t->sys_atom_off, t->sys_atom_off + ns + 1);
     ctx->h_sys_sel_off.assign(t->sys_sel_off, t->sys_sel_off + ns + 1);
@@ -1074,31 +1081,13 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaDeviceSynchronize());
     drain_events(ctx);
-    free_run(ctx);
-    ctx->tm = hb_timers{};
-    ctx->n_frames_total = n_frames_total;
-    ctx->next_frame = 0;
-    ctx->batch_counter = 0;
-    ctx->table_grows = 0;
     int wpr = (int)((n_frames_total + 31) / 32);
-
-    // bond table
     long long cap = 1024;
     while (cap < ctx->opt_table_capacity) cap <<= 1;
-    int rc = alloc_table(ctx, ctx->bt, cap, wpr);
-    if (rc) return rc;
-    ctx->table_cap = cap;
-    CK(cudaMalloc((void**)&ctx->bt.n_keys, 4 * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 4 * sizeof(unsigned long long), ctx->s_compute));
-    ctx->bt.overflow = ctx->bt.n_keys + 1;
-    ctx->bt.n_hits = (unsigned long long*)(ctx->bt.n_keys + 2);
-
-    // batch sizing
     size_t npts = (size_t)ctx->max_sel + ctx->max_wat;
     long long cc = 4096;
     while (cc < (long long)(2 * npts)) cc <<= 1;
     cc = std::min<long long>(cc, 1ll << 22);
-    ctx->cell_cap = (int)cc;
     size_t per_frame = (size_t)ctx->max_atoms * 12 * 2                      // two input buffers
                        + sizeof(FrameState) + (size_t)ctx->max_sel * 32 + (size_t)ctx->max_wat * 16 + npts * 16 +
                        2 * (size_t)(cc + 1) * 4;
@@ -1106,6 +1095,38 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     fb = std::max<long long>(1, std::min<long long>(fb, ctx->opt_max_batch_frames));
     fb = std::min<long long>(fb, n_frames_total);
     if (fb >= 32) fb -= fb % 32;
+    // allocations of the previous run are reused when nothing that sizes them changed
+    long long sig[7] = {wpr, ctx->max_sel, ctx->max_wat, ctx->max_atoms, fb, cc, ctx->prm.structure_batch};
+    bool reuse = ctx->bt.keys && ctx->table_cap >= cap && memcmp(sig, ctx->alloc_sig, sizeof(sig)) == 0;
+    if (!reuse) free_run(ctx);
+    ctx->tm = hb_timers{};
+    CK(cudaEventRecord(ctx->ev_run0, ctx->s_compute));
+    ctx->n_frames_total = n_frames_total;
+    ctx->next_frame = 0;
+    ctx->batch_counter = 0;
+    ctx->table_grows = 0;
+    for (auto& sl : ctx->slots) sl.busy = false;
+    int rc;
+    if (reuse) {
+        size_t tc = (size_t)ctx->table_cap;
+        k_fill_u64<<<1184, 256, 0, ctx->s_compute>>>(ctx->bt.keys, tc, EMPTY_KEY);
+        CK(cudaMemsetAsync(ctx->bt.bits, 0, tc * wpr * sizeof(unsigned), ctx->s_compute));
+        CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 4 * sizeof(unsigned long long), ctx->s_compute));
+        if (ctx->d_out_keys) { cudaFree(ctx->d_out_keys); ctx->d_out_keys = nullptr; }
+        if (ctx->d_out_rows) { cudaFree(ctx->d_out_rows); ctx->d_out_rows = nullptr; }
+        ctx->running = true;
+        ctx->finalized = false;
+        return HB_OK;
+    }
+    // bond table
+    if ((rc = alloc_table(ctx, ctx->bt, cap, wpr))) return rc;
+    ctx->table_cap = cap;
+    CK(cudaMalloc((void**)&ctx->bt.n_keys, 4 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 4 * sizeof(unsigned long long), ctx->s_compute));
+    ctx->bt.overflow = ctx->bt.n_keys + 1;
+    ctx->bt.n_hits = (unsigned long long*)(ctx->bt.n_keys + 2);
+
+    ctx->cell_cap = (int)cc;
     ctx->batch_frames = (int)fb;
     BatchView& bv = ctx->bv;
     bv = BatchView{};
@@ -1126,6 +1147,7 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     if ((rc = dalloc((void**)&bv.cells1, fb * (size_t)(cc + 1) * 4))) return rc;
     if ((rc = dalloc((void**)&bv.cells2, fb * (size_t)(cc + 1) * 4))) return rc;
     ctx->in_bytes = (size_t)fb * ctx->max_atoms * 12;
+    memcpy(ctx->alloc_sig, sig, sizeof(sig));
     ctx->running = true;
     ctx->finalized = false;
     return HB_OK;
@@ -1348,6 +1370,11 @@ int hb_sync(hb_ctx* ctx) {
 
 int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
     if (!ctx) return HB_ERR_ARG;
+    if (ctx->finalized && !ctx->running) {   // idempotent
+        if (n_bonds) *n_bonds = ctx->n_bonds;
+        if (words_per_bond) *words_per_bond = ctx->bt.wpr;
+        return HB_OK;
+    }
     if (!ctx->running) return fail(ctx, HB_ERR_STATE, "hb_finalize before hb_begin");
     int rc = hb_sync(ctx);
     if (rc) return rc;
@@ -1387,7 +1414,12 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
     CK(cudaMalloc((void**)&ctx->d_out_rows, nn * (size_t)wpr * 4));
     if (n > 0) k_gather_rows<<<1184, 256, 0, st>>>(ctx->bt.bits, v0, n, wpr, ctx->d_out_rows);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_run1, st));
     CK(cudaStreamSynchronize(st));
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev_run0, ctx->ev_run1) == cudaSuccess) ctx->tm.ms_run = ms;
+    }
     ctx->d_out_keys = k0;
     cudaFree(k1);
     cudaFree(v0);
@@ -1396,6 +1428,7 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
     if (hist) cudaFree(hist);
     ctx->n_bonds = n;
     ctx->finalized = true;
+    ctx->running = false;
     if (n_bonds) *n_bonds = n;
     if (words_per_bond) *words_per_bond = wpr;
     return HB_OK;

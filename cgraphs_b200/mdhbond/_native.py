@@ -62,6 +62,7 @@ class HbTimers(C.Structure):
         ("pairs_emitted", C.c_int64),
         ("table_capacity", C.c_int64),
         ("table_grows", C.c_int64),
+        ("ms_run", C.c_double),
     ]
 
 
@@ -244,7 +245,7 @@ class Context:
                 break
             names.append(n.decode())
             k += 1
-        return dict(ms_total=t.ms_total, ms_h2d=t.ms_h2d, n_launches=t.n_launches, frames=t.frames,
+        return dict(ms_total=t.ms_total, ms_h2d=t.ms_h2d, ms_run=t.ms_run, n_launches=t.n_launches, frames=t.frames,
                     pairs_emitted=t.pairs_emitted, table_capacity=t.table_capacity, table_grows=t.table_grows,
                     ms_kernel={n: t.ms_kernel[i] for i, n in enumerate(names)},
                     launches={n: t.launches[i] for i, n in enumerate(names)})

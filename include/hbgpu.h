@@ -108,6 +108,7 @@ typedef struct {
     int64_t pairs_emitted;        /* H-bond hits (entry pairs passing all criteria), all frames */
     int64_t table_capacity;       /* bond hash-table slots */
     int64_t table_grows;
+    double ms_run;                /* device time from hb_begin to the end of hb_finalize (CUDA events) */
 } hb_timers;
 
 int hb_create(hb_ctx** out, int device_ordinal);

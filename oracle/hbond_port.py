@@ -298,6 +298,32 @@ def dict2graph(bonds, residuewise=True):
     return g
 
 
+def key_ids(pt, method):
+    """hbond.py:122 (always _all_ids) / hbond.py:276-277 (_all_ids or _all_ids_atomwise)."""
+    if method == 'in_selection' or pt.residuewise:
+        return pt.all_ids
+    return pt.all_ids_atomwise
+
+
+def run_block(pt, xyz, method, around=3.5, exclude_backbone_backbone=True, backend='kdtree',
+              cos_threshold=None, strict=False, results=None, col0=0, nb_frames=None):
+    """Process the frames xyz[k] (float32 [K, N, 3]) into `results` columns col0 + k; returns results."""
+    ids = key_ids(pt, method)
+    if results is None:
+        results = {}
+    if nb_frames is None:
+        nb_frames = pt.nb_frames
+    for k in range(len(xyz)):
+        pos = np.asarray(xyz[k], dtype=np.float32)
+        e0, e1 = frame_pairs(pt, pos, method, around, exclude_backbone_backbone, backend, cos_threshold, strict)
+        for key in _frame_keys(pt, e0, e1, ids):
+            row = results.get(key)
+            if row is None:
+                row = results[key] = np.zeros(nb_frames, dtype=bool)
+            row[col0 + k] = True
+    return results
+
+
 def run(universe, selection, method='in_selection', around=3.5, exclude_backbone_backbone=True,
         backend='kdtree', cos_threshold=None, strict=False, frame_range=None, **ctor):
     """Run the port; returns a PortResult whose `initial_results` is `dict[str, bool[nb_frames]]`."""
@@ -307,20 +333,11 @@ def run(universe, selection, method='in_selection', around=3.5, exclude_backbone
             raise AssertionError('No acceptors in the selection')
         if pt.nD == 0:
             raise AssertionError('No donors in the selection')
-        ids = pt.all_ids                                          # hbond.py:122 (always _all_ids)
-    else:
-        ids = pt.all_ids if pt.residuewise else pt.all_ids_atomwise   # hbond.py:276-277
     results = {}
     frames = universe.trajectory.frames
-    todo = pt.frame_indices
-    for col, f in enumerate(todo):
+    for col, f in enumerate(pt.frame_indices):
         if frame_range is not None and not (frame_range[0] <= col < frame_range[1]):
             continue
-        pos = np.asarray(frames.frame(f), dtype=np.float32)
-        e0, e1 = frame_pairs(pt, pos, method, around, exclude_backbone_backbone, backend, cos_threshold, strict)
-        for key in _frame_keys(pt, e0, e1, ids):
-            row = results.get(key)
-            if row is None:
-                row = results[key] = np.zeros(pt.nb_frames, dtype=bool)
-            row[col] = True
+        run_block(pt, [frames.frame(f)], method, around, exclude_backbone_backbone, backend, cos_threshold,
+                  strict, results, col)
     return PortResult(pt, results)

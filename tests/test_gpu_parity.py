@@ -145,7 +145,7 @@ def test_gpu_empty_and_degenerate_frames():
 
 def test_gpu_error_behaviour():
     from cgraphs_b200.mdhbond import HbondAnalysis
-    s = synth.make_system(1500, 10, 3)
+    s = synth.make_system(2500, 40, 3)
     u = s.universe(1)
     with pytest.raises(AssertionError, match="No selection string"):
         HbondAnalysis(None, u)
@@ -155,8 +155,11 @@ def test_gpu_error_behaviour():
         HbondAnalysis("resname XXX", u)
     with pytest.raises(AssertionError, match="neither donors nor acceptors"):
         HbondAnalysis("name CA", u)
-    h = HbondAnalysis("name NZ", u)     # donors (and acceptors by the N-rule) only of one kind is fine
-    h = HbondAnalysis("name OD1", u)
+    # carboxylate / carbonyl oxygens carry no hydrogen: acceptors only
+    names = set(s.topology.names)
+    acc_only = [n for n in ("OD1", "OE1", "OD2", "OE2") if n in names]
+    h = HbondAnalysis("name " + " ".join(acc_only), u)
+    assert h._nb_donors == 0 and h._nb_acceptors > 0
     with pytest.raises(AssertionError, match="No donors in the selection"):
         h.set_hbonds_in_selection()
 
