@@ -1,0 +1,142 @@
+// hb_finalize.cuh - table maintenance and finalisation: compaction, LSD radix sort of the bond keys,
+// row gather, per-bond popcounts, rehash on growth.
+#pragma once
+#include "hb_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// finalize kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void k_fill_u64(unsigned long long* p, size_t n, unsigned long long v) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) p[i] = v;
+}
+
+__global__ void k_compact(BondTable bt, unsigned long long* out_keys, unsigned* out_slots, int* counter) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool live = i <= bt.mask && bt.keys[i] != EMPTY_KEY;
+    unsigned m = __ballot_sync(0xffffffffu, live);
+    if (!m) return;
+    int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (live) {
+        int pos = base + __popc(m & ((1u << lane) - 1u));
+        out_keys[pos] = bt.keys[i];
+        out_slots[pos] = i;
+    }
+}
+
+// LSD radix sort, 8 bits per pass, of (key64, slot32) pairs. One block handles a tile; stability inside
+// a tile comes from processing the tile in warp-sized strips in order.
+#define RS_TILE 2048
+__global__ void __launch_bounds__(256) k_rs_hist(const unsigned long long* keys, int n, int shift, unsigned* hist /*[256][nblk]*/) {
+    __shared__ unsigned h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    int base = blockIdx.x * RS_TILE;
+    for (int i = threadIdx.x; i < RS_TILE && base + i < n; i += 256)
+        atomicAdd(&h[(unsigned)(keys[base + i] >> shift) & 255u], 1u);
+    __syncthreads();
+    hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(1024) k_rs_scan(unsigned* hist, size_t n) {   // single block exclusive scan
+    __shared__ unsigned warp_sum[32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (size_t base = 0; base < n; base += 1024) {
+        size_t i = base + threadIdx.x;
+        unsigned v = i < n ? hist[i] : 0, s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+        if (lane == 31) warp_sum[w] = s;
+        __syncthreads();
+        if (w == 0) {
+            unsigned t = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned u = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += u; }
+            warp_sum[lane] = t;
+        }
+        __syncthreads();
+        unsigned off = carry + (w ? warp_sum[w - 1] : 0);
+        if (i < n) hist[i] = off + s - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warp_sum[31];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(32) k_rs_scatter(const unsigned long long* keys, const unsigned* vals, int n, int shift,
+                                                   const unsigned* hist, unsigned long long* okeys, unsigned* ovals) {
+    // one warp per tile: strips of 32 in order keep the sort stable
+    __shared__ unsigned off[256];
+    for (int d = threadIdx.x; d < 256; d += 32) off[d] = hist[(size_t)d * gridDim.x + blockIdx.x];
+    __syncwarp();
+    int base = blockIdx.x * RS_TILE;
+    int lane = threadIdx.x;
+    for (int s = 0; s < RS_TILE && base + s < n; s += 32) {
+        int i = base + s + lane;
+        bool live = i < n;
+        unsigned long long k = live ? keys[i] : 0;
+        unsigned d = (unsigned)(k >> shift) & 255u;
+        unsigned peers = __match_any_sync(0xffffffffu, live ? d : 0xffffffffu);
+        unsigned rank = __popc(peers & ((1u << lane) - 1u));
+        unsigned pos = 0;
+        if (live) pos = off[d] + rank;
+        __syncwarp();
+        if (live && rank == __popc(peers) - 1) off[d] = pos + 1;   // last peer advances the digit cursor
+        __syncwarp();
+        if (live) { okeys[pos] = k; ovals[pos] = vals[i]; }
+    }
+}
+
+__global__ void k_gather_rows(const unsigned* bits, const unsigned* slots, int n, int wpr, unsigned* out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)n * wpr;
+    size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        size_t row = i / wpr, col = i % wpr;
+        out[i] = bits[(size_t)slots[row] * wpr + col];
+    }
+}
+
+__global__ void k_row_counts(const unsigned* rows, int n, int wpr, long long* counts) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n) return;
+    int lane = threadIdx.x & 31;
+    long long c = 0;
+    for (int w = lane; w < wpr; w += 32) c += __popc(rows[(size_t)row * wpr + w]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) counts[row] = c;
+}
+
+// re-insert the rows of an old table into a larger one
+__global__ void k_rehash(BondTable oldt, BondTable newt) {
+    unsigned slot = blockIdx.x;
+    if (slot > oldt.mask) return;
+    unsigned long long key = oldt.keys[slot];
+    if (key == EMPTY_KEY) return;
+    __shared__ unsigned dst;
+    if (threadIdx.x == 0) {
+        unsigned h = hash64(key) & newt.mask;
+        for (;;) {
+            unsigned long long cur = atomicCAS(&newt.keys[h], EMPTY_KEY, key);
+            if (cur == EMPTY_KEY || cur == key) break;
+            h = (h + 1) & newt.mask;
+        }
+        dst = h;
+    }
+    __syncthreads();
+    for (int w = threadIdx.x; w < oldt.wpr; w += blockDim.x)
+        newt.bits[(size_t)dst * newt.wpr + w] = oldt.bits[(size_t)slot * oldt.wpr + w];
+}
+
+
+}  // namespace

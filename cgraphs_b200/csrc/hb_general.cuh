@@ -1,0 +1,223 @@
+// hb_general.cuh - general path: global-memory cell lists, any system size (one launch per stage per batch).
+#pragma once
+#include "hb_common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// K0: reset per-frame state
+// ------------------------------------------------------------------------------------------------
+__global__ void k_init_frames(BatchView bv) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= bv.n_frames) return;
+    FrameState& f = bv.fs[b];
+    for (int k = 0; k < 3; ++k) {
+        f.bb_min[k] = 0x7fffffff;
+        f.bb_max[k] = (int)0x80000000;
+    }
+    f.n_local = 0;
+    f.n_points = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: gather selection points, per-frame bounding box
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_sel(BatchView bv, DevTopo tp) {
+    int b = blockIdx.y;
+    int sys;
+    const float* xyz = frame_xyz(bv, tp, b, sys);
+    int s0 = tp.sys_sel_off[sys], s1 = tp.sys_sel_off[sys + 1];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float x = 0.f, y = 0.f, z = 0.f;
+    bool live = (s0 + i) < s1;
+    if (live) {
+        const float* p = xyz + 3ll * tp.sel_atom[s0 + i];
+        x = p[0]; y = p[1]; z = p[2];
+        bv.selpos[(size_t)b * bv.max_sel + i] = make_float4(x, y, z, __int_as_float(i));
+    }
+    float mn[3] = {live ? x : INFINITY, live ? y : INFINITY, live ? z : INFINITY};
+    float mx[3] = {live ? x : -INFINITY, live ? y : -INFINITY, live ? z : -INFINITY};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0 && mn[0] <= mx[0]) {
+        FrameState& f = bv.fs[b];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            atomicMin(&f.bb_min[k], f2ord(mn[k]));
+            atomicMax(&f.bb_max[k], f2ord(mx[k]));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: grid geometry. g1 covers the selection bounding box with one padding cell on every side so that
+// every water inside the dilated box maps to a valid cell; g2 covers the dilated box.
+// Cell edges carry a 1e-3 relative margin over the cut-off so float32 binning can never separate a
+// true neighbour pair by more than one cell; grids are capped at 1024 cells per axis and at
+// cell_cap cells in total by coarsening (coarser cells stay correct with a 27-cell neighbourhood).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_grid_setup(BatchView bv, RunParams rp) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= bv.n_frames) return;
+    FrameState& f = bv.fs[b];
+    for (int k = 0; k < 3; ++k) {
+        f.lo[k] = ord2f(f.bb_min[k]);
+        f.hi[k] = ord2f(f.bb_max[k]);
+    }
+    if (rp.method == HB_METHOD_WATER_AROUND) {
+        make_grid(f.g1, f.lo, f.hi, rp.cell1, rp.cell1, bv.cell_cap);
+        make_grid(f.g2, f.lo, f.hi, rp.around_f, rp.cell2, bv.cell_cap);
+    } else {
+        make_grid(f.g2, f.lo, f.hi, 0.f, rp.cell2, bv.cell_cap);
+        f.g1 = f.g2;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3-K5: counting sort of a point list into the cells of a grid. which = 1: selection points -> g1;
+// which = 2: selection points ++ local waters -> g2.  Grids are (X, frames): X blocks stride over the
+// points of their frame, so frames with few points cost few idle blocks.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int n_points_of(const BatchView& bv, const DevTopo& tp, int b, int which) {
+    int sys = bv.structure_batch ? (int)(bv.frame0 + b) : 0;
+    int nsel = tp.sys_sel_off[sys + 1] - tp.sys_sel_off[sys];
+    return which == 1 ? nsel : nsel + bv.fs[b].n_local;
+}
+__device__ __forceinline__ float4 load_point(const BatchView& bv, const DevTopo& tp, int b, int i) {
+    int sys = bv.structure_batch ? (int)(bv.frame0 + b) : 0;
+    int nsel = tp.sys_sel_off[sys + 1] - tp.sys_sel_off[sys];
+    if (i < nsel) return bv.selpos[(size_t)b * bv.max_sel + i];
+    return bv.lw[(size_t)b * bv.max_wat + (i - nsel)];
+}
+
+__global__ void __launch_bounds__(256) k_zero_cells(BatchView bv, int which) {
+    int b = blockIdx.y;
+    const FrameGrid& g = which == 1 ? bv.fs[b].g1 : bv.fs[b].g2;
+    int* cells = (which == 1 ? bv.cells1 : bv.cells2) + (size_t)b * (bv.cell_cap + 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= g.ncell; i += gridDim.x * blockDim.x) cells[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) k_count(BatchView bv, DevTopo tp, int which) {
+    int b = blockIdx.y;
+    int n = n_points_of(bv, tp, b, which);
+    const FrameGrid& g = which == 1 ? bv.fs[b].g1 : bv.fs[b].g2;
+    int* cells = (which == 1 ? bv.cells1 : bv.cells2) + (size_t)b * (bv.cell_cap + 1);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 p = load_point(bv, tp, b, i);
+        atomicAdd(&cells[cell_of(g, p.x, p.y, p.z)], 1);
+    }
+}
+
+// exclusive scan of the per-cell counts of one frame (one block per frame), in place
+__global__ void __launch_bounds__(1024) k_scan(BatchView bv, int which) {
+    int b = blockIdx.x;
+    const FrameGrid& g = which == 1 ? bv.fs[b].g1 : bv.fs[b].g2;
+    int* cells = (which == 1 ? bv.cells1 : bv.cells2) + (size_t)b * (bv.cell_cap + 1);
+    __shared__ int warp_sum[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    int n = g.ncell;
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int base = 0; base < n; base += 1024) {
+        int i = base + threadIdx.x;
+        int v = i < n ? cells[i] : 0;
+        int s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, s, o);
+            if (lane >= o) s += t;
+        }
+        if (lane == 31) warp_sum[w] = s;
+        __syncthreads();
+        if (w == 0) {
+            int t = warp_sum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int u = __shfl_up_sync(0xffffffffu, t, o);
+                if (lane >= o) t += u;
+            }
+            warp_sum[lane] = t;
+        }
+        __syncthreads();
+        int off = carry + (w ? warp_sum[w - 1] : 0);
+        if (i < n) cells[i] = off + s - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += warp_sum[31];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        cells[n] = carry;
+        if (which == 2) bv.fs[b].n_points = carry;
+    }
+}
+
+// after this kernel cells[c] holds the END of cell c; its start is cells[c-1] (0 for c = 0)
+__global__ void __launch_bounds__(256) k_scatter(BatchView bv, DevTopo tp, int which) {
+    int b = blockIdx.y;
+    int n = n_points_of(bv, tp, b, which);
+    const FrameGrid& g = which == 1 ? bv.fs[b].g1 : bv.fs[b].g2;
+    int* cells = (which == 1 ? bv.cells1 : bv.cells2) + (size_t)b * (bv.cell_cap + 1);
+    float4* dst = which == 1 ? bv.sorted1 + (size_t)b * bv.max_sel : bv.sorted2 + (size_t)b * (bv.max_sel + bv.max_wat);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 p = load_point(bv, tp, b, i);
+        dst[atomicAdd(&cells[cell_of(g, p.x, p.y, p.z)], 1)] = p;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: local waters = waters with DIST <= around_radius to any selection entry (hbond.py:249-252)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_local_water(BatchView bv, DevTopo tp, RunParams rp) {
+    int b = blockIdx.y;
+    int sys;
+    const float* xyz = frame_xyz(bv, tp, b, sys);
+    int w0 = tp.sys_wat_off[sys], w1 = tp.sys_wat_off[sys + 1];
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const FrameState& f = bv.fs[b];
+    bool local = false;
+    float x = 0.f, y = 0.f, z = 0.f;
+    if (w0 + i < w1) {
+        const float* p = xyz + 3ll * tp.wat_atom[w0 + i];
+        x = p[0]; y = p[1]; z = p[2];
+        float a = rp.around_f;
+        bool inside = x >= f.lo[0] - a && x <= f.hi[0] + a && y >= f.lo[1] - a && y <= f.hi[1] + a &&
+                      z >= f.lo[2] - a && z <= f.hi[2] + a;
+        if (inside)
+            local = water_is_local(f.g1, bv.cells1 + (size_t)b * (bv.cell_cap + 1),
+                                   bv.sorted1 + (size_t)b * bv.max_sel, x, y, z, rp);
+    }
+    unsigned m = __ballot_sync(0xffffffffu, local);
+    if (m) {
+        int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&bv.fs[b].n_local, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (local) {
+            int pos = base + __popc(m & ((1u << lane) - 1u));
+            bv.lw[(size_t)b * bv.max_wat + pos] = make_float4(x, y, z, __int_as_float(WATER_TAG | i));
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_pairs(BatchView bv, DevTopo tp, RunParams rp, BondTable bt) {
+    int b = blockIdx.y;
+    const FrameState& f = bv.fs[b];
+    int sys;
+    const float* xyz = frame_xyz(bv, tp, b, sys);
+    const int* cells = bv.cells2 + (size_t)b * (bv.cell_cap + 1);
+    const float4* pts = bv.sorted2 + (size_t)b * (bv.max_sel + bv.max_wat);
+    long long frame = bv.frame0 + b;
+    int nhit = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < f.n_points; i += gridDim.x * blockDim.x)
+        search_point(tp, rp, bt, xyz, frame, sys, f.g2, cells, pts, i, nhit);
+    flush_hits(bt, nhit);
+}
+
+}  // namespace

@@ -32,684 +32,11 @@
 
 #define HB_VERSION "hbgpu 0.1 (sm_100a)"
 
+#include "hb_general.cuh"
+#include "hb_fused.cuh"
+#include "hb_finalize.cuh"
+
 namespace {
-
-// ------------------------------------------------------------------------------------------------
-// device-side views
-// ------------------------------------------------------------------------------------------------
-struct DevTopo {
-    int n_systems;
-    const long long* sys_atom_off;
-    const int* sys_sel_off;
-    const int* sys_wat_off;
-    const int* sel_atom;
-    const int* sel_don;
-    const int* sel_acc;
-    const int* sel_wat;
-    const unsigned char* sel_bb;
-    const int* wat_atom;
-    const int* wat_ent;
-    const int* ent_group;
-    const int* ent_resid;
-    const int* ent_residue;
-    const int* ent_h_off;
-    const int* ent_h_atom;
-};
-
-struct FrameGrid {      // geometry of one cell grid of one frame
-    float ox, oy, oz;   // origin
-    float inv;          // 1 / cell edge
-    int nx, ny, nz;
-    int ncell;
-};
-
-struct FrameState {     // per frame slot of a batch
-    int bb_min[3];      // ordered-int encoded float min / max of the selection points
-    int bb_max[3];
-    int n_local;        // local waters appended so far
-    int n_points;       // points in the pair-search set (selection + local waters)
-    FrameGrid g1;       // selection grid used by the local-water test (cell >= around_radius)
-    FrameGrid g2;       // pair-search grid (cell >= distance)
-    float lo[3], hi[3]; // decoded bounding box of the selection points
-};
-
-struct BatchView {
-    const float* xyz;        // coordinates of the batch
-    long long frame0;        // global index (occupancy column) of the first frame of the batch
-    int n_frames;            // frames in this batch
-    long long atoms_per_frame;   // trajectory mode stride (atoms)
-    long long atom_base;     // structure_batch: sys_atom_off of the first system of the batch
-    int structure_batch;
-    int max_sel, max_wat;    // per-frame capacities of the scratch arrays
-    int cell_cap;            // cells per grid per frame (capacity)
-    FrameState* fs;
-    float4* selpos;          // [n_frames][max_sel]
-    float4* sorted1;         // [n_frames][max_sel]          selection points in g1 cell order
-    float4* lw;              // [n_frames][max_wat]          local waters (unordered)
-    float4* sorted2;         // [n_frames][max_sel+max_wat]  pair-search points in g2 cell order
-    int* cells1;             // [n_frames][cell_cap+1]
-    int* cells2;             // [n_frames][cell_cap+1]
-};
-
-struct RunParams {
-    double r2;               // fl(distance*distance)
-    double around2;          // fl(around*around)
-    float r2f_hi;            // float prefilter bounds (slightly above the double thresholds)
-    float around2f_hi;
-    float cell1;             // cell edge of g1
-    float cell2;             // cell edge of g2
-    float around_f;          // around_radius rounded up a little (bounding-box dilation)
-    float cos_threshold;
-    int check_angle;
-    int excl_bb;
-    int method;
-};
-
-struct BondTable {
-    unsigned long long* keys;   // open addressing, EMPTY = ~0
-    unsigned int* bits;         // [capacity][wpr]
-    unsigned int mask;          // capacity - 1
-    int wpr;                    // 32-bit words per row
-    int* n_keys;
-    int* overflow;
-    unsigned long long* n_hits;
-};
-
-#define EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
-#define WATER_TAG 0x40000000
-
-__device__ __forceinline__ int f2ord(float f) {
-    int i = __float_as_int(f);
-    return i ^ ((i >> 31) & 0x7fffffff);
-}
-__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i ^ ((i >> 31) & 0x7fffffff)); }
-
-__device__ __forceinline__ const float* frame_xyz(const BatchView& bv, const DevTopo& tp, int b, int& sys) {
-    if (bv.structure_batch) {
-        sys = (int)(bv.frame0 + b);
-        return bv.xyz + 3ll * (tp.sys_atom_off[sys] - bv.atom_base);
-    }
-    sys = 0;
-    return bv.xyz + 3ll * bv.atoms_per_frame * b;
-}
-
-__device__ __forceinline__ int cell_coord(float x, float o, float inv, int n) {
-    int c = (int)floorf((x - o) * inv);
-    return min(max(c, 0), n - 1);
-}
-__device__ __forceinline__ int cell_of(const FrameGrid& g, float x, float y, float z) {
-    int cx = cell_coord(x, g.ox, g.inv, g.nx);
-    int cy = cell_coord(y, g.oy, g.inv, g.ny);
-    int cz = cell_coord(z, g.oz, g.inv, g.nz);
-    return (cz * g.ny + cy) * g.nx + cx;
-}
-
-// DIST predicate, SURVEY A.2 / F2 (scipy cKDTree semantics on float32 inputs)
-__device__ __forceinline__ bool dist_le(float ax, float ay, float az, float bx, float by, float bz, double r2) {
-    double dx = (double)ax - (double)bx;
-    double dy = (double)ay - (double)by;
-    double dz = (double)az - (double)bz;
-    double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-    return s <= r2;
-}
-__device__ __forceinline__ float dist2f(float ax, float ay, float az, float bx, float by, float bz) {
-    float dx = ax - bx, dy = ay - by, dz = az - bz;
-    return dx * dx + dy * dy + dz * dz;
-}
-
-// ANG predicate, SURVEY A.2 / F3 (helpfunctions.py:96-104,155): b = pair partner, h = hydrogen, a = other partner
-__device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz) {
-    return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
-}
-__device__ __forceinline__ bool ang_ok(float bx, float by, float bz, float hx, float hy, float hz, float ax,
-                                       float ay, float az, float cthr) {
-    float v1x = __fsub_rn(hx, bx), v1y = __fsub_rn(hy, by), v1z = __fsub_rn(hz, bz);
-    float v2x = __fsub_rn(ax, hx), v2y = __fsub_rn(ay, hy), v2z = __fsub_rn(az, hz);
-    float d12 = dot3_rn(v1x, v1y, v1z, v2x, v2y, v2z);
-    float d11 = dot3_rn(v1x, v1y, v1z, v1x, v1y, v1z);
-    float d22 = dot3_rn(v2x, v2y, v2z, v2x, v2y, v2z);
-    float den = __fmul_rn(__fsqrt_rn(d11), __fsqrt_rn(d22));
-    float c = __fdiv_rn(d12, den);
-    if (c < -1.0f) c = -1.0f;
-    return (c >= cthr) && (c <= 1.0f);   // NaN fails both
-}
-
-// ------------------------------------------------------------------------------------------------
-// K0: reset per-frame state
-// ------------------------------------------------------------------------------------------------
-__global__ void k_init_frames(BatchView bv) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= bv.n_frames) return;
-    FrameState& f = bv.fs[b];
-    for (int k = 0; k < 3; ++k) {
-        f.bb_min[k] = 0x7fffffff;
-        f.bb_max[k] = (int)0x80000000;
-    }
-    f.n_local = 0;
-    f.n_points = 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K1: gather selection points, per-frame bounding box
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_gather_sel(BatchView bv, DevTopo tp) {
-    int b = blockIdx.y;
-    int sys;
-    const float* xyz = frame_xyz(bv, tp, b, sys);
-    int s0 = tp.sys_sel_off[sys], s1 = tp.sys_sel_off[sys + 1];
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float x = 0.f, y = 0.f, z = 0.f;
-    bool live = (s0 + i) < s1;
-    if (live) {
-        const float* p = xyz + 3ll * tp.sel_atom[s0 + i];
-        x = p[0]; y = p[1]; z = p[2];
-        bv.selpos[(size_t)b * bv.max_sel + i] = make_float4(x, y, z, __int_as_float(i));
-    }
-    float mn[3] = {live ? x : INFINITY, live ? y : INFINITY, live ? z : INFINITY};
-    float mx[3] = {live ? x : -INFINITY, live ? y : -INFINITY, live ? z : -INFINITY};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
-            mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
-        }
-    }
-    if ((threadIdx.x & 31) == 0 && mn[0] <= mx[0]) {
-        FrameState& f = bv.fs[b];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            atomicMin(&f.bb_min[k], f2ord(mn[k]));
-            atomicMax(&f.bb_max[k], f2ord(mx[k]));
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K2: grid geometry. g1 covers the selection bounding box with one padding cell on every side so that
-// every water inside the dilated box maps to a valid cell; g2 covers the dilated box.
-// Cell edges carry a 1e-3 relative margin over the cut-off so float32 binning can never separate a
-// true neighbour pair by more than one cell; grids are capped at 1024 cells per axis and at
-// cell_cap cells in total by coarsening (coarser cells stay correct with a 27-cell neighbourhood).
-// ------------------------------------------------------------------------------------------------
-__device__ void make_grid(FrameGrid& g, const float* lo, const float* hi, float pad, float cell, int cap) {
-    float ext[3];
-    bool finite = true;
-    for (int k = 0; k < 3; ++k) {
-        ext[k] = (hi[k] - lo[k]) + 2.f * pad;
-        finite = finite && isfinite(ext[k]) && ext[k] >= 0.f;
-    }
-    g.ox = lo[0] - pad; g.oy = lo[1] - pad; g.oz = lo[2] - pad;
-    if (!finite) { g.inv = 0.f; g.nx = g.ny = g.nz = 1; g.ncell = 1; g.ox = g.oy = g.oz = 0.f; return; }
-    for (int it = 0; it < 64; ++it) {
-        int n[3];
-        double tot = 1.0;
-        bool ok = true;
-        for (int k = 0; k < 3; ++k) {
-            float q = floorf(ext[k] / cell) + 1.f;
-            if (q > 1024.f) ok = false;
-            n[k] = (int)fminf(q, 1024.f);
-            tot *= (double)n[k];
-        }
-        if (ok && tot <= (double)cap) {
-            g.nx = n[0]; g.ny = n[1]; g.nz = n[2]; g.ncell = n[0] * n[1] * n[2];
-            g.inv = 1.0f / cell;
-            return;
-        }
-        cell *= 1.2f;
-    }
-    g.inv = 0.f; g.nx = g.ny = g.nz = 1; g.ncell = 1;
-}
-
-__global__ void k_grid_setup(BatchView bv, RunParams rp) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= bv.n_frames) return;
-    FrameState& f = bv.fs[b];
-    for (int k = 0; k < 3; ++k) {
-        f.lo[k] = ord2f(f.bb_min[k]);
-        f.hi[k] = ord2f(f.bb_max[k]);
-    }
-    if (rp.method == HB_METHOD_WATER_AROUND) {
-        make_grid(f.g1, f.lo, f.hi, rp.cell1, rp.cell1, bv.cell_cap);
-        make_grid(f.g2, f.lo, f.hi, rp.around_f, rp.cell2, bv.cell_cap);
-    } else {
-        make_grid(f.g2, f.lo, f.hi, 0.f, rp.cell2, bv.cell_cap);
-        f.g1 = f.g2;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K3-K5: counting sort of a point list into the cells of a grid. which = 1: selection points -> g1;
-// which = 2: selection points ++ local waters -> g2.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool load_point(const BatchView& bv, const DevTopo& tp, int b, int which, int i, float4& p) {
-    int sys = bv.structure_batch ? (int)(bv.frame0 + b) : 0;
-    int nsel = tp.sys_sel_off[sys + 1] - tp.sys_sel_off[sys];
-    if (i < nsel) { p = bv.selpos[(size_t)b * bv.max_sel + i]; return true; }
-    if (which == 1) return false;
-    int j = i - nsel;
-    if (j >= bv.fs[b].n_local) return false;
-    p = bv.lw[(size_t)b * bv.max_wat + j];
-    return true;
-}
-
-__global__ void __launch_bounds__(256) k_count(BatchView bv, DevTopo tp, int which) {
-    int b = blockIdx.y;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float4 p;
-    if (!load_point(bv, tp, b, which, i, p)) return;
-    const FrameGrid& g = which == 1 ? bv.fs[b].g1 : bv.fs[b].g2;
-    int* cells = (which == 1 ? bv.cells1 : bv.cells2) + (size_t)b * (bv.cell_cap + 1);
-    atomicAdd(&cells[cell_of(g, p.x, p.y, p.z)], 1);
-}
-
-// exclusive scan of the per-cell counts of one frame (one block per frame), in place
-__global__ void __launch_bounds__(1024) k_scan(BatchView bv, int which) {
-    int b = blockIdx.x;
-    const FrameGrid& g = which == 1 ? bv.fs[b].g1 : bv.fs[b].g2;
-    int* cells = (which == 1 ? bv.cells1 : bv.cells2) + (size_t)b * (bv.cell_cap + 1);
-    __shared__ int warp_sum[32];
-    __shared__ int carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    int n = g.ncell;
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int base = 0; base < n; base += 1024) {
-        int i = base + threadIdx.x;
-        int v = i < n ? cells[i] : 0;
-        int s = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, s, o);
-            if (lane >= o) s += t;
-        }
-        if (lane == 31) warp_sum[w] = s;
-        __syncthreads();
-        if (w == 0) {
-            int t = warp_sum[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int u = __shfl_up_sync(0xffffffffu, t, o);
-                if (lane >= o) t += u;
-            }
-            warp_sum[lane] = t;
-        }
-        __syncthreads();
-        int off = carry + (w ? warp_sum[w - 1] : 0);
-        if (i < n) cells[i] = off + s - v;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += warp_sum[31];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        cells[n] = carry;
-        if (which == 2) bv.fs[b].n_points = carry;
-    }
-}
-
-// after this kernel cells[c] holds the END of cell c; its start is cells[c-1] (0 for c = 0)
-__global__ void __launch_bounds__(256) k_scatter(BatchView bv, DevTopo tp, int which) {
-    int b = blockIdx.y;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    float4 p;
-    if (!load_point(bv, tp, b, which, i, p)) return;
-    const FrameGrid& g = which == 1 ? bv.fs[b].g1 : bv.fs[b].g2;
-    int* cells = (which == 1 ? bv.cells1 : bv.cells2) + (size_t)b * (bv.cell_cap + 1);
-    int pos = atomicAdd(&cells[cell_of(g, p.x, p.y, p.z)], 1);
-    if (which == 1) bv.sorted1[(size_t)b * bv.max_sel + pos] = p;
-    else bv.sorted2[(size_t)b * (bv.max_sel + bv.max_wat) + pos] = p;
-}
-
-// ------------------------------------------------------------------------------------------------
-// K6: local waters = waters with DIST <= around_radius to any selection entry (hbond.py:249-252)
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_local_water(BatchView bv, DevTopo tp, RunParams rp) {
-    int b = blockIdx.y;
-    int sys;
-    const float* xyz = frame_xyz(bv, tp, b, sys);
-    int w0 = tp.sys_wat_off[sys], w1 = tp.sys_wat_off[sys + 1];
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const FrameState& f = bv.fs[b];
-    bool local = false;
-    float x = 0.f, y = 0.f, z = 0.f;
-    if (w0 + i < w1) {
-        const float* p = xyz + 3ll * tp.wat_atom[w0 + i];
-        x = p[0]; y = p[1]; z = p[2];
-        float a = rp.around_f;
-        bool inside = x >= f.lo[0] - a && x <= f.hi[0] + a && y >= f.lo[1] - a && y <= f.hi[1] + a &&
-                      z >= f.lo[2] - a && z <= f.hi[2] + a;
-        if (inside) {
-            const FrameGrid& g = f.g1;
-            const int* cells = bv.cells1 + (size_t)b * (bv.cell_cap + 1);
-            const float4* pts = bv.sorted1 + (size_t)b * bv.max_sel;
-            int cx = cell_coord(x, g.ox, g.inv, g.nx);
-            int cy = cell_coord(y, g.oy, g.inv, g.ny);
-            int cz = cell_coord(z, g.oz, g.inv, g.nz);
-            for (int zz = max(cz - 1, 0); zz <= min(cz + 1, g.nz - 1) && !local; ++zz)
-                for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.ny - 1) && !local; ++yy) {
-                    int c_lo = (zz * g.ny + yy) * g.nx + max(cx - 1, 0);
-                    int c_hi = (zz * g.ny + yy) * g.nx + min(cx + 1, g.nx - 1);
-                    int s = c_lo ? cells[c_lo - 1] : 0;
-                    int e = cells[c_hi];
-                    for (int q = s; q < e; ++q) {
-                        float4 sp = pts[q];
-                        if (dist2f(x, y, z, sp.x, sp.y, sp.z) <= rp.around2f_hi &&
-                            dist_le(x, y, z, sp.x, sp.y, sp.z, rp.around2)) { local = true; break; }
-                    }
-                }
-        }
-    }
-    unsigned m = __ballot_sync(0xffffffffu, local);
-    if (m) {
-        int lane = threadIdx.x & 31;
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&bv.fs[b].n_local, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (local) {
-            int pos = base + __popc(m & ((1u << lane) - 1u));
-            bv.lw[(size_t)b * bv.max_wat + pos] = make_float4(x, y, z, __int_as_float(WATER_TAG | i));
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// bond table: insert key, set bit
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned hash64(unsigned long long k) {
-    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
-    return (unsigned)k;
-}
-
-__device__ __forceinline__ void record_bond(const BondTable& bt, unsigned long long key, long long frame) {
-    unsigned h = hash64(key) & bt.mask;
-    for (unsigned probe = 0; probe <= bt.mask; ++probe) {
-        unsigned long long cur = bt.keys[h];
-        if (cur == EMPTY_KEY) {
-            cur = atomicCAS(&bt.keys[h], EMPTY_KEY, key);
-            if (cur == EMPTY_KEY) { atomicAdd(bt.n_keys, 1); cur = key; }
-        }
-        if (cur == key) {
-            atomicOr(&bt.bits[(size_t)h * bt.wpr + (frame >> 5)], 1u << (frame & 31));
-            return;
-        }
-        h = (h + 1) & bt.mask;
-    }
-    atomicExch(bt.overflow, 1);
-}
-
-// ------------------------------------------------------------------------------------------------
-// K7: pair search
-// ------------------------------------------------------------------------------------------------
-struct PointInfo {
-    int don, acc, wat;   // global entry indices or -1
-    int bb;
-    float x, y, z;
-};
-
-__device__ __forceinline__ void load_info(const DevTopo& tp, const RunParams& rp, int sys, float4 p, PointInfo& o) {
-    int id = __float_as_int(p.w);
-    o.x = p.x; o.y = p.y; o.z = p.z;
-    if (id & WATER_TAG) {
-        o.don = -1; o.acc = -1; o.bb = 0;
-        o.wat = tp.wat_ent[tp.sys_wat_off[sys] + (id & ~WATER_TAG)];
-    } else {
-        int s = tp.sys_sel_off[sys] + id;
-        o.don = tp.sel_don[s];
-        o.acc = tp.sel_acc[s];
-        o.wat = rp.method == HB_METHOD_WATER_AROUND ? tp.sel_wat[s] : -1;
-        o.bb = tp.sel_bb[s];
-    }
-}
-
-// any hydrogen of entry `e` (owned by point H) with ANG(other, h, owner) satisfied
-__device__ __forceinline__ bool any_h(const DevTopo& tp, const float* xyz, int e, const PointInfo& owner,
-                                      const PointInfo& other, float cthr) {
-    int s = tp.ent_h_off[e], t = tp.ent_h_off[e + 1];
-    for (int k = s; k < t; ++k) {
-        const float* h = xyz + 3ll * tp.ent_h_atom[k];
-        if (ang_ok(other.x, other.y, other.z, h[0], h[1], h[2], owner.x, owner.y, owner.z, cthr)) return true;
-    }
-    return false;
-}
-
-__device__ __forceinline__ void emit(const DevTopo& tp, const RunParams& rp, const BondTable& bt, long long frame,
-                                     int e0, int e1, int& nhit) {
-    int x = min(e0, e1), y = max(e0, e1);
-    bool chk = tp.ent_resid[x] < tp.ent_resid[y];      // hbond.py:120-122
-    int first = chk ? x : y, second = chk ? y : x;
-    if (!rp.check_angle && tp.ent_residue[first] == tp.ent_residue[second]) return;   // hbond.py:125-127
-    unsigned long long key = ((unsigned long long)(unsigned)tp.ent_group[first] << 32) |
-                             (unsigned long long)(unsigned)tp.ent_group[second];
-    ++nhit;
-    record_bond(bt, key, frame);
-}
-
-// All entry pairs generated by the point pair (P, Q), P != Q as points
-__device__ void process_pair(const DevTopo& tp, const RunParams& rp, const BondTable& bt, const float* xyz,
-                             long long frame, const PointInfo& P, const PointInfo& Q, int& nhit) {
-    const bool ang = rp.check_angle != 0;
-    const float ct = rp.cos_threshold;
-    // lazily evaluated "some hydrogen of this entry passes" flags; -1 = not evaluated
-    int pd = -1, qd = -1, pw = -1, qw = -1;
-    auto PD = [&]() { if (pd < 0) pd = (!ang) || any_h(tp, xyz, P.don, P, Q, ct); return pd; };
-    auto QD = [&]() { if (qd < 0) qd = (!ang) || any_h(tp, xyz, Q.don, Q, P, ct); return qd; };
-    auto PW = [&]() { if (pw < 0) pw = (!ang) || any_h(tp, xyz, P.wat, P, Q, ct); return pw; };
-    auto QW = [&]() { if (qw < 0) qw = (!ang) || any_h(tp, xyz, Q.wat, Q, P, ct); return qw; };
-    const bool bb_skip = rp.excl_bb && P.bb && Q.bb;
-    if (!bb_skip) {
-        if (P.acc >= 0 && Q.don >= 0 && QD()) emit(tp, rp, bt, frame, P.acc, Q.don, nhit);
-        if (Q.acc >= 0 && P.don >= 0 && PD()) emit(tp, rp, bt, frame, Q.acc, P.don, nhit);
-    }
-    if (P.wat >= 0 && Q.wat >= 0 && (PW() || QW())) emit(tp, rp, bt, frame, P.wat, Q.wat, nhit);
-    if (Q.wat >= 0) {
-        if (P.don >= 0 && (PD() || QW())) emit(tp, rp, bt, frame, P.don, Q.wat, nhit);
-        if (P.acc >= 0 && QW()) emit(tp, rp, bt, frame, P.acc, Q.wat, nhit);
-    }
-    if (P.wat >= 0) {
-        if (Q.don >= 0 && (QD() || PW())) emit(tp, rp, bt, frame, Q.don, P.wat, nhit);
-        if (Q.acc >= 0 && PW()) emit(tp, rp, bt, frame, Q.acc, P.wat, nhit);
-    }
-}
-
-// Entry pairs of a point with itself (distance 0): acceptor-donor and selection-water entries of one atom
-__device__ void process_self(const DevTopo& tp, const RunParams& rp, const BondTable& bt, const float* xyz,
-                             long long frame, const PointInfo& P, int& nhit) {
-    const bool ang = rp.check_angle != 0;
-    const float ct = rp.cos_threshold;
-    bool need = (P.acc >= 0 && P.don >= 0) || (P.wat >= 0 && (P.don >= 0 || P.acc >= 0));
-    if (!need) return;
-    bool pd = P.don >= 0 ? ((!ang) || any_h(tp, xyz, P.don, P, P, ct)) : false;
-    bool pw = P.wat >= 0 ? ((!ang) || any_h(tp, xyz, P.wat, P, P, ct)) : false;
-    if (P.acc >= 0 && P.don >= 0 && !(rp.excl_bb && P.bb) && pd) emit(tp, rp, bt, frame, P.acc, P.don, nhit);
-    if (P.wat >= 0) {
-        if (P.don >= 0 && (pd || pw)) emit(tp, rp, bt, frame, P.don, P.wat, nhit);
-        if (P.acc >= 0 && pw) emit(tp, rp, bt, frame, P.acc, P.wat, nhit);
-    }
-}
-
-__global__ void __launch_bounds__(128) k_pairs(BatchView bv, DevTopo tp, RunParams rp, BondTable bt) {
-    int b = blockIdx.y;
-    const FrameState& f = bv.fs[b];
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x * blockDim.x >= f.n_points) return;
-    int nhit = 0;
-    if (i < f.n_points) {
-    int sys;
-    const float* xyz = frame_xyz(bv, tp, b, sys);
-    const FrameGrid& g = f.g2;
-    const int* cells = bv.cells2 + (size_t)b * (bv.cell_cap + 1);
-    const float4* pts = bv.sorted2 + (size_t)b * (bv.max_sel + bv.max_wat);
-    long long frame = bv.frame0 + b;
-    float4 p4 = pts[i];
-    PointInfo P;
-    load_info(tp, rp, sys, p4, P);
-    process_self(tp, rp, bt, xyz, frame, P, nhit);
-    int cx = cell_coord(P.x, g.ox, g.inv, g.nx);
-    int cy = cell_coord(P.y, g.oy, g.inv, g.ny);
-    int cz = cell_coord(P.z, g.oz, g.inv, g.nz);
-    // half shell: the rest of the own cell and cell x+1, then rows (y+1, z) and (y-1..y+1, z+1), x-1..x+1
-    for (int run = 0; run < 5; ++run) {
-        int s, e;
-        if (run == 0) {
-            int c_hi = (cz * g.ny + cy) * g.nx + min(cx + 1, g.nx - 1);
-            s = i + 1;
-            e = cells[c_hi];
-        } else {
-            int yy = run == 1 ? cy + 1 : cy + (run - 3);
-            int zz = run == 1 ? cz : cz + 1;
-            if (yy < 0 || yy >= g.ny || zz >= g.nz) continue;
-            int c_lo = (zz * g.ny + yy) * g.nx + max(cx - 1, 0);
-            int c_hi = (zz * g.ny + yy) * g.nx + min(cx + 1, g.nx - 1);
-            s = c_lo ? cells[c_lo - 1] : 0;
-            e = cells[c_hi];
-        }
-        for (int q = s; q < e; ++q) {
-            float4 q4 = pts[q];
-            if (dist2f(P.x, P.y, P.z, q4.x, q4.y, q4.z) > rp.r2f_hi) continue;
-            if (!dist_le(P.x, P.y, P.z, q4.x, q4.y, q4.z, rp.r2)) continue;
-            PointInfo Q;
-            load_info(tp, rp, sys, q4, Q);
-            process_pair(tp, rp, bt, xyz, frame, P, Q, nhit);
-        }
-    }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nhit += __shfl_xor_sync(0xffffffffu, nhit, o);
-    if ((threadIdx.x & 31) == 0 && nhit) atomicAdd(bt.n_hits, (unsigned long long)nhit);
-}
-
-// ------------------------------------------------------------------------------------------------
-// finalize kernels
-// ------------------------------------------------------------------------------------------------
-__global__ void k_fill_u64(unsigned long long* p, size_t n, unsigned long long v) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < n; i += stride) p[i] = v;
-}
-
-__global__ void k_compact(BondTable bt, unsigned long long* out_keys, unsigned* out_slots, int* counter) {
-    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool live = i <= bt.mask && bt.keys[i] != EMPTY_KEY;
-    unsigned m = __ballot_sync(0xffffffffu, live);
-    if (!m) return;
-    int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(counter, __popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (live) {
-        int pos = base + __popc(m & ((1u << lane) - 1u));
-        out_keys[pos] = bt.keys[i];
-        out_slots[pos] = i;
-    }
-}
-
-// LSD radix sort, 8 bits per pass, of (key64, slot32) pairs. One block handles a tile; stability inside
-// a tile comes from processing the tile in warp-sized strips in order.
-#define RS_TILE 2048
-__global__ void __launch_bounds__(256) k_rs_hist(const unsigned long long* keys, int n, int shift, unsigned* hist /*[256][nblk]*/) {
-    __shared__ unsigned h[256];
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    int base = blockIdx.x * RS_TILE;
-    for (int i = threadIdx.x; i < RS_TILE && base + i < n; i += 256)
-        atomicAdd(&h[(unsigned)(keys[base + i] >> shift) & 255u], 1u);
-    __syncthreads();
-    hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = h[threadIdx.x];
-}
-
-__global__ void __launch_bounds__(1024) k_rs_scan(unsigned* hist, size_t n) {   // single block exclusive scan
-    __shared__ unsigned warp_sum[32];
-    __shared__ unsigned carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (size_t base = 0; base < n; base += 1024) {
-        size_t i = base + threadIdx.x;
-        unsigned v = i < n ? hist[i] : 0, s = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
-        if (lane == 31) warp_sum[w] = s;
-        __syncthreads();
-        if (w == 0) {
-            unsigned t = warp_sum[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { unsigned u = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += u; }
-            warp_sum[lane] = t;
-        }
-        __syncthreads();
-        unsigned off = carry + (w ? warp_sum[w - 1] : 0);
-        if (i < n) hist[i] = off + s - v;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += warp_sum[31];
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(32) k_rs_scatter(const unsigned long long* keys, const unsigned* vals, int n, int shift,
-                                                   const unsigned* hist, unsigned long long* okeys, unsigned* ovals) {
-    // one warp per tile: strips of 32 in order keep the sort stable
-    __shared__ unsigned off[256];
-    for (int d = threadIdx.x; d < 256; d += 32) off[d] = hist[(size_t)d * gridDim.x + blockIdx.x];
-    __syncwarp();
-    int base = blockIdx.x * RS_TILE;
-    int lane = threadIdx.x;
-    for (int s = 0; s < RS_TILE && base + s < n; s += 32) {
-        int i = base + s + lane;
-        bool live = i < n;
-        unsigned long long k = live ? keys[i] : 0;
-        unsigned d = (unsigned)(k >> shift) & 255u;
-        unsigned peers = __match_any_sync(0xffffffffu, live ? d : 0xffffffffu);
-        unsigned rank = __popc(peers & ((1u << lane) - 1u));
-        unsigned pos = 0;
-        if (live) pos = off[d] + rank;
-        __syncwarp();
-        if (live && rank == __popc(peers) - 1) off[d] = pos + 1;   // last peer advances the digit cursor
-        __syncwarp();
-        if (live) { okeys[pos] = k; ovals[pos] = vals[i]; }
-    }
-}
-
-__global__ void k_gather_rows(const unsigned* bits, const unsigned* slots, int n, int wpr, unsigned* out) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t total = (size_t)n * wpr;
-    size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (; i < total; i += stride) {
-        size_t row = i / wpr, col = i % wpr;
-        out[i] = bits[(size_t)slots[row] * wpr + col];
-    }
-}
-
-__global__ void k_row_counts(const unsigned* rows, int n, int wpr, long long* counts) {
-    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= n) return;
-    int lane = threadIdx.x & 31;
-    long long c = 0;
-    for (int w = lane; w < wpr; w += 32) c += __popc(rows[(size_t)row * wpr + w]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if (lane == 0) counts[row] = c;
-}
-
-// re-insert the rows of an old table into a larger one
-__global__ void k_rehash(BondTable oldt, BondTable newt) {
-    unsigned slot = blockIdx.x;
-    if (slot > oldt.mask) return;
-    unsigned long long key = oldt.keys[slot];
-    if (key == EMPTY_KEY) return;
-    __shared__ unsigned dst;
-    if (threadIdx.x == 0) {
-        unsigned h = hash64(key) & newt.mask;
-        for (;;) {
-            unsigned long long cur = atomicCAS(&newt.keys[h], EMPTY_KEY, key);
-            if (cur == EMPTY_KEY || cur == key) break;
-            h = (h + 1) & newt.mask;
-        }
-        dst = h;
-    }
-    __syncthreads();
-    for (int w = threadIdx.x; w < oldt.wpr; w += blockDim.x)
-        newt.bits[(size_t)dst * newt.wpr + w] = oldt.bits[(size_t)slot * oldt.wpr + w];
-}
 
 enum KernelClass { KC_INIT = 0, KC_GATHER, KC_GRID, KC_COUNT, KC_SCAN, KC_SCATTER, KC_LOCAL, KC_PAIRS, KC_N };
 const char* const kKernelNames[KC_N] = {"init_frames", "gather_sel", "grid_setup", "cell_count",
@@ -1499,3 +826,4 @@ int hb_host_alloc(void** ptr, uint64_t bytes) {
 int hb_host_free(void* ptr) { return cudaFreeHost(ptr) == cudaSuccess ? HB_OK : HB_ERR_CUDA; }
 
 }  // extern "C"
+
