@@ -28,6 +28,9 @@ struct DevTopo {
     const int* ent_residue;
     const int* ent_h_off;
     const int* ent_h_atom;
+    // packed copies built by hb_set_topology (one 16-byte load instead of four 4-byte loads)
+    const int4* sel_pack;    // {sel_don, sel_acc, sel_wat, sel_bb}
+    const int4* ent_pack;    // {ent_resid, ent_residue, ent_h_off, hydrogen count}
 };
 
 struct FrameGrid {      // geometry of one cell grid of one frame
@@ -91,7 +94,10 @@ struct BondTable {
 };
 
 #define EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
-#define WATER_TAG 0x40000000
+// tag bits in the id a point carries in the w component of its float4
+#define WATER_TAG 0x40000000      // water point (id = index into the system's water points)
+#define SELF_TAG 0x20000000       // selection point with more than one entry: has distance-0 entry pairs
+#define POINT_ID_MASK 0x1fffffff
 
 __device__ __forceinline__ int f2ord(float f) {
     int i = __float_as_int(f);
@@ -217,20 +223,21 @@ __device__ __forceinline__ void load_info(const DevTopo& tp, const RunParams& rp
     o.x = p.x; o.y = p.y; o.z = p.z;
     if (id & WATER_TAG) {
         o.don = -1; o.acc = -1; o.bb = 0;
-        o.wat = tp.wat_ent[tp.sys_wat_off[sys] + (id & ~WATER_TAG)];
+        o.wat = tp.wat_ent[tp.sys_wat_off[sys] + (id & POINT_ID_MASK)];
     } else {
-        int s = tp.sys_sel_off[sys] + id;
-        o.don = tp.sel_don[s];
-        o.acc = tp.sel_acc[s];
-        o.wat = rp.method == HB_METHOD_WATER_AROUND ? tp.sel_wat[s] : -1;
-        o.bb = tp.sel_bb[s];
+        int4 k = tp.sel_pack[tp.sys_sel_off[sys] + (id & POINT_ID_MASK)];
+        o.don = k.x;
+        o.acc = k.y;
+        o.wat = rp.method == HB_METHOD_WATER_AROUND ? k.z : -1;
+        o.bb = k.w;
     }
 }
 
 // any hydrogen of entry `e` (owned by point H) with ANG(other, h, owner) satisfied
 __device__ __forceinline__ bool any_h(const DevTopo& tp, const float* xyz, int e, const PointInfo& owner,
                                       const PointInfo& other, float cthr) {
-    int s = tp.ent_h_off[e], t = tp.ent_h_off[e + 1];
+    int4 ep = tp.ent_pack[e];
+    int s = ep.z, t = ep.z + ep.w;
     for (int k = s; k < t; ++k) {
         const float* h = xyz + 3ll * tp.ent_h_atom[k];
         if (ang_ok(other.x, other.y, other.z, h[0], h[1], h[2], owner.x, owner.y, owner.z, cthr)) return true;
@@ -241,9 +248,10 @@ __device__ __forceinline__ bool any_h(const DevTopo& tp, const float* xyz, int e
 __device__ __forceinline__ void emit(const DevTopo& tp, const RunParams& rp, const BondTable& bt, long long frame,
                                      int e0, int e1, int& nhit) {
     int x = min(e0, e1), y = max(e0, e1);
-    bool chk = tp.ent_resid[x] < tp.ent_resid[y];      // hbond.py:120-122
+    int4 px = tp.ent_pack[x], py = tp.ent_pack[y];
+    bool chk = px.x < py.x;                            // hbond.py:120-122
     int first = chk ? x : y, second = chk ? y : x;
-    if (!rp.check_angle && tp.ent_residue[first] == tp.ent_residue[second]) return;   // hbond.py:125-127
+    if (!rp.check_angle && px.y == py.y) return;       // hbond.py:125-127
     unsigned long long key = ((unsigned long long)(unsigned)tp.ent_group[first] << 32) |
                              (unsigned long long)(unsigned)tp.ent_group[second];
     ++nhit;

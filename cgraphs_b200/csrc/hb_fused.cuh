@@ -1,35 +1,48 @@
-// hb_fused.cuh - fused fast path: ONE CTA processes ONE frame end to end, everything but the frame's
+// hb_fused.cuh - fused fast path: ONE CTA processes ONE frame end to end; everything but the frame's
 // coordinates and the bond table stays in shared memory.
 //
-//   phase A  gather the selection points (<= sel_cap), bounding box, cell grid g1, counting sort in smem
-//   phase B  stream every water oxygen of the frame once: each warp pulls 32-water slabs of the
-//            coordinate array into its own shared-memory ring with 1-D bulk async copies (TMA,
-//            cp.async.bulk + mbarrier), tests them against the dilated bounding box and the g1 cells
-//            (exact DIST predicate) and appends the local waters (hbond.py:249-252) to a shared list
-//   phase C  cell grid g2 over selection + local waters, half-shell pair search with the exact DIST /
-//            ANG predicates, key build, bond-table insert, occupancy bit
+// The CTA has 8 consumer warps and 1 producer warp.
 //
-// HBM traffic per frame is the water slab read once plus a few gathers; several CTAs are resident per
-// SM so the compute of one frame overlaps the streaming of others.  Frames that exceed the shared
-// capacities (sel_cap / lw_cap) raise `fused_overflow`; the host then re-runs the batch on the general path.
+//   phase A  (consumers) gather the selection points (<= sel_cap) into smem, bounding box, cell grid g1
+//            (edge >= around_radius), counting sort, "near" bitmap: bit c is set iff some selection point
+//            lies in the 27-cell neighbourhood of cell c.
+//   phase B  the producer warp streams the frame's water block through a ring of shared-memory stages
+//            with 1-D bulk async copies (TMA engine: cp.async.bulk + mbarrier complete_tx); a tile is
+//            256 consecutive waters (O,H,H,O,H,H ... as they lie in the coordinate array), so HBM is read
+//            in large aligned bursts exactly once.  Consumer thread j takes water j of the tile:
+//            dilated-bounding-box test, near-bitmap test, then the survivors ("candidates") go to a
+//            per-warp buffer and are tested 32 at a time, densely, against the 27 neighbouring g1 cells
+//            with the exact DIST predicate; local waters (hbond.py:249-252) are appended to a shared list.
+//   phase C  (consumers) cell grid g2 (edge >= distance) over selection + local waters; per block of 256
+//            points: half-shell walk collecting the point pairs that pass the exact DIST test into a pair
+//            list, then one thread per pair expands it into the reference's entry pairs, applies the
+//            exact ANG test over the hydrogen lists and records the bond (hash-table insert + frame bit).
+//
+// Several CTAs are resident per SM, so the gathers of phases A / C of one frame overlap the streaming
+// of others.  Frames that exceed the shared capacities (sel_cap / lw_cap / pair_cap) raise
+// `fused_overflow`; the host then re-runs the batch on the general path (hb_general.cuh).
 #pragma once
 #include "hb_common.cuh"
 
 namespace {
 
-#define FUSED_THREADS 256
-#define FUSED_WARPS (FUSED_THREADS / 32)
-#define FUSED_STAGES 2
-#define FUSED_CHUNK 32   // waters per slab (one per lane)
+#define FUSED_CWARPS 8
+#define FUSED_CONSUMERS (FUSED_CWARPS * 32)
+#define FUSED_THREADS (FUSED_CONSUMERS + 32)
+#define FUSED_TILE 256          // waters per tile: one per consumer thread
+#define FUSED_MAX_STAGES 8
+#define FUSED_CAND 64           // per-warp candidate buffer entries
 
 struct FusedCfg {
     int sel_cap;              // selection points per frame that fit
     int lw_cap;               // local waters per frame that fit
     int cell_cap;             // cells per grid (packed 16-bit counters)
-    int regular;              // 1: water point i is atom w_first + i * w_stride in every system -> TMA slabs
+    int pair_cap;             // point pairs per block of 256 points
+    int regular;              // 1: water point i is atom w_first + i * w_stride in every system -> TMA tiles
     int w_stride;             // atoms between consecutive water oxygens
-    unsigned stage_bytes;     // bytes of one slab buffer (multiple of 16)
-    unsigned off_spos, off_bc, off_lw, off_cells, off_bar;   // byte offsets in dynamic shared memory
+    int stages;               // ring depth
+    unsigned stage_bytes;     // bytes of one stage (multiple of 16)
+    unsigned off_spos, off_union, off_lw, off_cells, off_near, off_cand, off_bar;   // byte offsets in dynamic smem
     unsigned smem_bytes;
     unsigned long long buf_begin, buf_end;   // address range of the coordinate batch (bounds for bulk copies)
 };
@@ -37,12 +50,14 @@ struct FusedCfg {
 struct FusedShared {          // small fixed part at the start of dynamic shared memory
     FrameGrid g1, g2;
     float lo[3], hi[3];
-    float red[FUSED_WARPS][6];
+    float red[FUSED_CWARPS][6];
     int n_lw;
-    int n_points;
+    int n_pairs[2];
     int overflow;
-    int scan_carry;
-    int warp_sum[FUSED_WARPS];
+    int warp_sum[FUSED_CWARPS];
+    unsigned stage_head[FUSED_MAX_STAGES];   // byte offset of the tile's first water inside the stage
+    unsigned stage_lo[FUSED_MAX_STAGES];     // [lo, hi): bytes of the stage the bulk copy filled
+    unsigned stage_hi[FUSED_MAX_STAGES];
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -51,6 +66,9 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -67,6 +85,17 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
         : "memory");
     return ok != 0;
 }
+// bounded wait (about a second): a lost copy must never hang the GPU; the caller flags the frame instead
+__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned parity) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    for (;;) {
+        for (int k = 0; k < 256; ++k)
+            if (mbar_try_wait(bar, parity)) return true;
+        if (clock64() - t0 > 2000000000ll) return false;
+    }
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(FUSED_CONSUMERS) : "memory"); }
 
 // counting-sort helpers on packed 16-bit cell counters ---------------------------------------------
 __device__ __forceinline__ unsigned cell_add(unsigned* words, int c) {   // returns the old 16-bit value
@@ -74,10 +103,10 @@ __device__ __forceinline__ unsigned cell_add(unsigned* words, int c) {   // retu
     return (c & 1) ? (old >> 16) : (old & 0xffffu);
 }
 
-// exclusive scan of n 16-bit counters in place (whole CTA); returns the total
-__device__ int block_scan_cells(unsigned short* cells, int n, FusedShared* sh) {
+// exclusive scan of n 16-bit counters in place (all consumers)
+__device__ void block_scan_cells(unsigned short* cells, int n, FusedShared* sh) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int per = (n + FUSED_THREADS - 1) / FUSED_THREADS;
+    const int per = (n + FUSED_CONSUMERS - 1) / FUSED_CONSUMERS;
     const int s = min(tid * per, n), e = min(s + per, n);
     int sum = 0;
     for (int i = s; i < e; ++i) sum += cells[i];
@@ -88,7 +117,7 @@ __device__ int block_scan_cells(unsigned short* cells, int n, FusedShared* sh) {
         if (lane >= o) incl += t;
     }
     if (lane == 31) sh->warp_sum[w] = incl;
-    __syncthreads();
+    consumer_sync();
     int base = 0;
     for (int k = 0; k < w; ++k) base += sh->warp_sum[k];
     int run = base + incl - sum;
@@ -97,10 +126,7 @@ __device__ int block_scan_cells(unsigned short* cells, int n, FusedShared* sh) {
         cells[i] = (unsigned short)run;
         run += v;
     }
-    int total = 0;
-    for (int k = 0; k < FUSED_WARPS; ++k) total += sh->warp_sum[k];
-    __syncthreads();
-    return total;
+    consumer_sync();
 }
 
 // sort `n` points (src(i)) into the cells of g: zero, count, scan, scatter. After return cells[c] is the END of cell c.
@@ -108,31 +134,67 @@ template <typename Src>
 __device__ void block_cell_sort(const FrameGrid& g, unsigned short* cells, float4* dst, int n, Src src, FusedShared* sh) {
     unsigned* words = reinterpret_cast<unsigned*>(cells);
     const int nwords = (g.ncell + 2) >> 1;
-    for (int i = threadIdx.x; i < nwords; i += FUSED_THREADS) words[i] = 0u;
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += FUSED_THREADS) {
+    for (int i = threadIdx.x; i < nwords; i += FUSED_CONSUMERS) words[i] = 0u;
+    consumer_sync();
+    for (int i = threadIdx.x; i < n; i += FUSED_CONSUMERS) {
         float4 p = src(i);
         cell_add(words, cell_of(g, p.x, p.y, p.z));
     }
-    __syncthreads();
+    consumer_sync();
     block_scan_cells(cells, g.ncell, sh);
-    for (int i = threadIdx.x; i < n; i += FUSED_THREADS) {
+    for (int i = threadIdx.x; i < n; i += FUSED_CONSUMERS) {
         float4 p = src(i);
         dst[cell_add(words, cell_of(g, p.x, p.y, p.z))] = p;
     }
-    __syncthreads();
+    consumer_sync();
+}
+
+// point pairs (i, q), i < q in cell order, that pass the exact DIST test: half shell of point i
+__device__ __forceinline__ void collect_pairs(const RunParams& rp, const FrameGrid& g, const unsigned short* cells,
+                                              const float4* pts, int i, unsigned* pairs, int pair_cap, int* n_pairs) {
+    const float4 p = pts[i];
+    const int cx = cell_coord(p.x, g.ox, g.inv, g.nx);
+    const int cy = cell_coord(p.y, g.oy, g.inv, g.ny);
+    const int cz = cell_coord(p.z, g.oz, g.inv, g.nz);
+    const int xl = max(cx - 1, 0), xh = min(cx + 1, g.nx - 1);
+#pragma unroll 1
+    for (int run = 0; run < 5; ++run) {
+        int s, e;
+        if (run == 0) {
+            s = i + 1;
+            e = (int)cells[(cz * g.ny + cy) * g.nx + xh];
+        } else {
+            const int yy = run == 1 ? cy + 1 : cy + (run - 3);
+            const int zz = run == 1 ? cz : cz + 1;
+            if (yy < 0 || yy >= g.ny || zz >= g.nz) continue;
+            const int row = (zz * g.ny + yy) * g.nx;
+            s = (row + xl) ? (int)cells[row + xl - 1] : 0;
+            e = (int)cells[row + xh];
+        }
+        for (int q = s; q < e; ++q) {
+            const float4 q4 = pts[q];
+            if (dist2f(p.x, p.y, p.z, q4.x, q4.y, q4.z) > rp.r2f_hi) continue;
+            if (!dist_le(p.x, p.y, p.z, q4.x, q4.y, q4.z, rp.r2)) continue;
+            const int k = atomicAdd(n_pairs, 1);
+            if (k < pair_cap) pairs[k] = (unsigned)i | ((unsigned)q << 16);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(FUSED_THREADS) k_frame_fused(BatchView bv, DevTopo tp, RunParams rp, BondTable bt, FusedCfg fc) {
     extern __shared__ __align__(16) unsigned char smem[];
     FusedShared* sh = reinterpret_cast<FusedShared*>(smem);
-    float4* spos = reinterpret_cast<float4*>(smem + fc.off_spos);        // selection points, gather order
-    float4* sorted1 = reinterpret_cast<float4*>(smem + fc.off_bc);       // selection points in g1 cell order
-    unsigned char* stages = smem + fc.off_bc + (size_t)fc.sel_cap * 16;  // per-warp slab rings (phase B)
-    float4* psorted = reinterpret_cast<float4*>(smem + fc.off_bc);       // phase C: aliases sorted1 + rings
+    float4* spos = reinterpret_cast<float4*>(smem + fc.off_spos);          // selection points, gather order
+    float4* sorted1 = reinterpret_cast<float4*>(smem + fc.off_union);      // phase B: selection points in g1 cell order
+    unsigned char* ring = smem + fc.off_union + (size_t)fc.sel_cap * 16;   // phase B: tile stages
+    float4* psorted = reinterpret_cast<float4*>(smem + fc.off_union);      // phase C: aliases sorted1 + ring
+    unsigned* pairs = reinterpret_cast<unsigned*>(smem + fc.off_union + ((size_t)fc.sel_cap + fc.lw_cap) * 16);
     float4* lw = reinterpret_cast<float4*>(smem + fc.off_lw);
     unsigned short* cells = reinterpret_cast<unsigned short*>(smem + fc.off_cells);
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + fc.off_bar);
+    unsigned* near = reinterpret_cast<unsigned*>(smem + fc.off_near);
+    float4* cand = reinterpret_cast<float4*>(smem + fc.off_cand);
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + fc.off_bar);
+    unsigned long long* empty = full + FUSED_MAX_STAGES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x;
@@ -142,24 +204,64 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_frame_fused(BatchView bv, Dev
     const int s0 = tp.sys_sel_off[sys], nsel = tp.sys_sel_off[sys + 1] - s0;
     const int w0 = tp.sys_wat_off[sys], nwp = tp.sys_wat_off[sys + 1] - w0;
     const bool wa = rp.method == HB_METHOD_WATER_AROUND;
+    const bool scan_waters = wa && nwp > 0 && nsel > 0;
+    const bool stream = scan_waters && fc.regular;
+    const int ntiles = (nwp + FUSED_TILE - 1) / FUSED_TILE;
+    const int stride12 = fc.w_stride * 12;
 
+    if (nsel > fc.sel_cap) {           // uniform over the CTA: this frame does not fit
+        if (tid == 0) atomicExch(bt.fused_overflow, 1);
+        return;
+    }
     if (tid == 0) {
         sh->n_lw = 0;
         sh->overflow = 0;
-        for (int k = 0; k < FUSED_WARPS * FUSED_STAGES; ++k) mbar_init(&bars[k], 1);
+        for (int k = 0; k < fc.stages; ++k) { mbar_init(&full[k], 1); mbar_init(&empty[k], FUSED_CWARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (nsel > fc.sel_cap) {           // uniform over the CTA: this frame does not fit
-        if (tid == 0) atomicExch(bt.fused_overflow, 1);
+    __syncthreads();
+
+    // ---- producer warp: stream the water block of this frame ------------------------------------------
+    if (warp == FUSED_CWARPS) {
+        if (stream && lane == 0) {
+            const unsigned long long gbase = (unsigned long long)(uintptr_t)(xyz + 3ll * tp.wat_atom[w0]);
+            const unsigned long long lim_lo = (fc.buf_begin + 15ull) & ~15ull, lim_hi = fc.buf_end & ~15ull;
+            for (int t = 0; t < ntiles; ++t) {
+                const int st = t % fc.stages, round = t / fc.stages;
+                if (round > 0 && !mbar_wait(&empty[st], (unsigned)((round - 1) & 1))) { sh->overflow = 2; break; }
+                const int nw = min(FUSED_TILE, nwp - t * FUSED_TILE);
+                const unsigned long long ga = gbase + (unsigned long long)t * (unsigned long long)(FUSED_TILE * stride12);
+                const unsigned long long start = ga & ~15ull;
+                const unsigned head = (unsigned)(ga - start);
+                const unsigned long long end = (ga + (unsigned long long)((nw - 1) * stride12 + 12) + 15ull) & ~15ull;
+                const unsigned long long c0 = start > lim_lo ? start : lim_lo, c1 = end < lim_hi ? end : lim_hi;
+                sh->stage_head[st] = head;
+                unsigned char* dst = ring + (size_t)st * fc.stage_bytes;
+                if (c1 > c0) {
+                    const unsigned lo = (unsigned)(c0 - start), bytes = (unsigned)(c1 - c0);
+                    sh->stage_lo[st] = lo;
+                    sh->stage_hi[st] = lo + bytes;
+                    mbar_expect_tx(&full[st], bytes);
+                    bulk_g2s(dst + lo, reinterpret_cast<const void*>(c0), bytes, &full[st]);
+                } else {
+                    sh->stage_lo[st] = 0;
+                    sh->stage_hi[st] = 0;
+                    mbar_arrive(&full[st]);
+                }
+            }
+        }
         return;
     }
 
     // ---- phase A: selection points, bounding box, grids ------------------------------------------
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int i = tid; i < nsel; i += FUSED_THREADS) {
+    for (int i = tid; i < nsel; i += FUSED_CONSUMERS) {
         const float* p = xyz + 3ll * tp.sel_atom[s0 + i];
+        const int4 k = tp.sel_pack[s0 + i];
         float x = p[0], y = p[1], z = p[2];
-        spos[i] = make_float4(x, y, z, __int_as_float(i));
+        const int multi = (k.x >= 0) + (k.y >= 0) + ((wa && k.z >= 0) ? 1 : 0);
+        spos[i] = make_float4(x, y, z, __int_as_float(i | (multi > 1 ? SELF_TAG : 0)));
         mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
         mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
     }
@@ -172,12 +274,12 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_frame_fused(BatchView bv, Dev
         }
     if (lane == 0)
         for (int k = 0; k < 3; ++k) { sh->red[warp][k] = mn[k]; sh->red[warp][3 + k] = mx[k]; }
-    __syncthreads();
+    consumer_sync();
     if (tid == 0) {
         // same values the general path obtains through its ordered-int atomics: min / max over the points
         for (int k = 0; k < 3; ++k) {
             float a = sh->red[0][k], c = sh->red[0][3 + k];
-            for (int w = 1; w < FUSED_WARPS; ++w) { a = fminf(a, sh->red[w][k]); c = fmaxf(c, sh->red[w][3 + k]); }
+            for (int w = 1; w < FUSED_CWARPS; ++w) { a = fminf(a, sh->red[w][k]); c = fmaxf(c, sh->red[w][3 + k]); }
             sh->lo[k] = a; sh->hi[k] = c;
         }
         if (wa) {
@@ -188,111 +290,96 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_frame_fused(BatchView bv, Dev
             sh->g1 = sh->g2;
         }
     }
-    __syncthreads();
+    consumer_sync();
 
     // ---- phase B: local waters ---------------------------------------------------------------------
-    if (wa && nwp > 0 && nsel > 0) {
-        block_cell_sort(sh->g1, cells, sorted1, nsel, [&](int i) { return spos[i]; }, sh);
+    if (scan_waters) {
         const FrameGrid g1 = sh->g1;
+        for (int i = tid; i < (g1.ncell + 31) / 32; i += FUSED_CONSUMERS) near[i] = 0u;
+        block_cell_sort(g1, cells, sorted1, nsel, [&](int i) { return spos[i]; }, sh);   // (syncs cover the zeroing)
+        for (int i = tid; i < nsel; i += FUSED_CONSUMERS) {
+            const float4 p = spos[i];
+            const int cx = cell_coord(p.x, g1.ox, g1.inv, g1.nx);
+            const int cy = cell_coord(p.y, g1.oy, g1.inv, g1.ny);
+            const int cz = cell_coord(p.z, g1.oz, g1.inv, g1.nz);
+            for (int zz = max(cz - 1, 0); zz <= min(cz + 1, g1.nz - 1); ++zz)
+                for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g1.ny - 1); ++yy)
+                    for (int xx = max(cx - 1, 0); xx <= min(cx + 1, g1.nx - 1); ++xx) {
+                        const int c = (zz * g1.ny + yy) * g1.nx + xx;
+                        atomicOr(&near[c >> 5], 1u << (c & 31));
+                    }
+        }
+        consumer_sync();
+
         const float a = rp.around_f;
         const float lox = sh->lo[0] - a, loy = sh->lo[1] - a, loz = sh->lo[2] - a;
         const float hix = sh->hi[0] + a, hiy = sh->hi[1] + a, hiz = sh->hi[2] + a;
-        auto test_and_append = [&](bool live, float x, float y, float z, int i) {
+        float4* wc = cand + warp * FUSED_CAND;
+        int ncand = 0;                                  // warp-uniform
+        // exact local-water test of (up to) 32 buffered candidates, one per lane
+        auto test_candidates = [&](int first, int count) {
             bool local = false;
-            if (live && x >= lox && x <= hix && y >= loy && y <= hiy && z >= loz && z <= hiz)
-                local = water_is_local(g1, cells, sorted1, x, y, z, rp);
-            unsigned m = __ballot_sync(0xffffffffu, local);
+            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < count) {
+                c = wc[first + lane];
+                local = water_is_local(g1, cells, sorted1, c.x, c.y, c.z, rp);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, local);
             if (m) {
                 int base = 0;
                 if (lane == 0) base = atomicAdd(&sh->n_lw, __popc(m));
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (local) {
-                    int pos = base + __popc(m & ((1u << lane) - 1u));
-                    if (pos < fc.lw_cap) lw[pos] = make_float4(x, y, z, __int_as_float(WATER_TAG | i));
+                    const int pos = base + __popc(m & ((1u << lane) - 1u));
+                    if (pos < fc.lw_cap) lw[pos] = c;
                     else sh->overflow = 1;
                 }
             }
         };
-        const int nchunk = (nwp + FUSED_CHUNK - 1) / FUSED_CHUNK;
-        if (fc.regular) {
-            // slab k of this warp = waters [32 c, 32 c + 32), c = warp + 8 k; bytes from the first to the last oxygen
-            const unsigned char* gbase = reinterpret_cast<const unsigned char*>(xyz + 3ll * tp.wat_atom[w0]);
-            const long long slab_stride = (long long)FUSED_CHUNK * fc.w_stride * 12;
-            unsigned char* ring = stages + (size_t)warp * FUSED_STAGES * fc.stage_bytes;
-            unsigned long long* wbar = bars + warp * FUSED_STAGES;
-            const int nk = warp < nchunk ? (nchunk - warp + FUSED_WARPS - 1) / FUSED_WARPS : 0;
-            auto slab = [&](int k, unsigned long long& start, unsigned& size, unsigned& head, int& nw) {
-                int c = warp + k * FUSED_WARPS;
-                nw = min(FUSED_CHUNK, nwp - c * FUSED_CHUNK);
-                unsigned long long ga = (unsigned long long)(gbase + (long long)c * slab_stride);
-                unsigned nbytes = (unsigned)(((nw - 1) * fc.w_stride * 3 + 3) * 4);
-                start = ga & ~15ull;
-                head = (unsigned)(ga - start);
-                size = (head + nbytes + 15u) & ~15u;
-                return start >= fc.buf_begin && start + size <= fc.buf_end && size <= fc.stage_bytes;
-            };
-            int issued = 0;      // TMA slabs issued so far (ring position), consumed likewise
-            int k_issue = 0;
-            auto issue_next = [&]() {    // lane 0: queue the next TMA-able slab, if any
-                while (k_issue < nk) {
-                    unsigned long long start; unsigned size, head; int nw;
-                    bool ok = slab(k_issue, start, size, head, nw);
-                    ++k_issue;
-                    if (ok) {
-                        int st = issued % FUSED_STAGES;
-                        mbar_expect_tx(&wbar[st], size);
-                        bulk_g2s(ring + (size_t)st * fc.stage_bytes, reinterpret_cast<const void*>(start), size, &wbar[st]);
-                        ++issued;
-                        return;
-                    }
-                }
-            };
-            __syncthreads();     // barrier init visible to every warp before the first wait
-            if (lane == 0)
-                for (int s = 0; s < FUSED_STAGES; ++s) issue_next();
-            int consumed = 0;
-            for (int k = 0; k < nk; ++k) {
-                unsigned long long start; unsigned size, head; int nw;
-                bool ok = slab(k, start, size, head, nw);
-                const int c = warp + k * FUSED_WARPS;
-                const int i = c * FUSED_CHUNK + lane;
-                const bool live = lane < nw;
-                float x = 0.f, y = 0.f, z = 0.f;
-                if (ok) {
-                    int st = consumed % FUSED_STAGES;
-                    unsigned parity = (unsigned)((consumed / FUSED_STAGES) & 1);
-                    unsigned spins = 0;
-                    while (!mbar_try_wait(&wbar[st], parity)) {
-                        if (++spins > (1u << 26)) { sh->overflow = 2; break; }     // never hang the GPU
-                    }
-                    if (live) {
-                        const float* f = reinterpret_cast<const float*>(ring + (size_t)st * fc.stage_bytes + head) +
-                                         lane * fc.w_stride * 3;
+        for (int t = 0; t < ntiles; ++t) {
+            const int i = t * FUSED_TILE + tid;
+            const bool live = i < nwp;
+            float x = 0.f, y = 0.f, z = 0.f;
+            if (stream) {
+                const int st = t % fc.stages;
+                if (*(volatile int*)&sh->overflow == 2) break;          // the pipeline broke down: give the frame up
+                if (!mbar_wait(&full[st], (unsigned)((t / fc.stages) & 1))) { sh->overflow = 2; break; }
+                const unsigned off = sh->stage_head[st] + (unsigned)(tid * stride12);
+                if (live) {
+                    if (off >= sh->stage_lo[st] && off + 12u <= sh->stage_hi[st]) {
+                        const float* f = reinterpret_cast<const float*>(ring + (size_t)st * fc.stage_bytes + off);
+                        x = f[0]; y = f[1]; z = f[2];
+                    } else {                            // tile touches the edge of the batch buffer: plain loads
+                        const float* f = xyz + 3ll * tp.wat_atom[w0 + i];
                         x = f[0]; y = f[1]; z = f[2];
                     }
-                    ++consumed;
-                    __syncwarp();                     // every lane has read its water before the slot is refilled
-                    if (lane == 0) issue_next();
-                } else if (live) {                    // slab touches the edge of the batch buffer: plain loads
-                    const float* f = xyz + 3ll * tp.wat_atom[w0 + i];
-                    x = f[0]; y = f[1]; z = f[2];
                 }
-                test_and_append(live, x, y, z, i);
+                __syncwarp();                           // every lane has read its water before the stage is released
+                if (lane == 0) mbar_arrive(&empty[st]);
+            } else if (live) {
+                const float* f = xyz + 3ll * tp.wat_atom[w0 + i];
+                x = f[0]; y = f[1]; z = f[2];
             }
-        } else {
-            for (int c = warp; c < nchunk; c += FUSED_WARPS) {
-                const int i = c * FUSED_CHUNK + lane;
-                const bool live = i < nwp;
-                float x = 0.f, y = 0.f, z = 0.f;
-                if (live) {
-                    const float* f = xyz + 3ll * tp.wat_atom[w0 + i];
-                    x = f[0]; y = f[1]; z = f[2];
+            bool is_cand = live && x >= lox && x <= hix && y >= loy && y <= hiy && z >= loz && z <= hiz;
+            if (is_cand) {
+                const int c = cell_of(g1, x, y, z);
+                is_cand = (near[c >> 5] >> (c & 31)) & 1u;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, is_cand);
+            if (m) {
+                if (is_cand) wc[ncand + __popc(m & ((1u << lane) - 1u))] = make_float4(x, y, z, __int_as_float(WATER_TAG | i));
+                ncand += __popc(m);
+                __syncwarp();
+                if (ncand >= 32) {
+                    ncand -= 32;
+                    test_candidates(ncand, 32);
+                    __syncwarp();
                 }
-                test_and_append(live, x, y, z, i);
             }
         }
+        if (ncand) test_candidates(0, ncand);
     }
-    __syncthreads();
+    consumer_sync();
     if (sh->overflow || sh->n_lw > fc.lw_cap) {
         if (tid == 0) atomicExch(bt.fused_overflow, 1);
         return;
@@ -304,8 +391,36 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_frame_fused(BatchView bv, Dev
     block_cell_sort(sh->g2, cells, psorted, np, [&](int i) { return i < nsel ? spos[i] : lw[i - nsel]; }, sh);
     int nhit = 0;
     const FrameGrid g2 = sh->g2;
-    for (int i = tid; i < np; i += FUSED_THREADS)
-        search_point(tp, rp, bt, xyz, frame, sys, g2, cells, psorted, i, nhit);
+    if (tid == 0) sh->n_pairs[0] = sh->n_pairs[1] = 0;
+    consumer_sync();
+    for (int base = 0, it = 0; base < np; base += FUSED_CONSUMERS, ++it) {
+        int* cnt = &sh->n_pairs[it & 1];
+        const int i = base + tid;
+        if (i < np) {
+            collect_pairs(rp, g2, cells, psorted, i, pairs, fc.pair_cap, cnt);
+            const float4 p4 = psorted[i];
+            if (__float_as_int(p4.w) & SELF_TAG) {
+                PointInfo P;
+                load_info(tp, rp, sys, p4, P);
+                process_self(tp, rp, bt, xyz, frame, P, nhit);
+            }
+        }
+        consumer_sync();
+        const int npairs = *cnt;
+        if (tid == 0) sh->n_pairs[(it & 1) ^ 1] = 0;    // nobody uses the other counter between these two barriers
+        if (npairs > fc.pair_cap) {                     // uniform
+            if (tid == 0) atomicExch(bt.fused_overflow, 1);
+            break;
+        }
+        for (int k = tid; k < npairs; k += FUSED_CONSUMERS) {
+            const unsigned pq = pairs[k];
+            PointInfo P, Q;
+            load_info(tp, rp, sys, psorted[pq & 0xffffu], P);
+            load_info(tp, rp, sys, psorted[pq >> 16], Q);
+            process_pair(tp, rp, bt, xyz, frame, P, Q, nhit);
+        }
+        consumer_sync();                                // the pair list may be overwritten by the next block
+    }
     flush_hits(bt, nhit);
 }
 

@@ -27,6 +27,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -38,9 +39,9 @@
 
 namespace {
 
-enum KernelClass { KC_INIT = 0, KC_GATHER, KC_GRID, KC_COUNT, KC_SCAN, KC_SCATTER, KC_LOCAL, KC_PAIRS, KC_N };
+enum KernelClass { KC_INIT = 0, KC_GATHER, KC_GRID, KC_COUNT, KC_SCAN, KC_SCATTER, KC_LOCAL, KC_PAIRS, KC_FUSED, KC_N };
 const char* const kKernelNames[KC_N] = {"init_frames", "gather_sel", "grid_setup", "cell_count",
-                                        "cell_scan", "cell_scatter", "local_water", "pairs"};
+                                        "cell_scan", "cell_scatter", "local_water", "pairs", "frame_fused"};
 
 }  // namespace
 
@@ -73,9 +74,22 @@ struct hb_ctx {
 
     // options
     long long opt_batch_bytes = 4ll << 30;
-    long long opt_table_capacity = 1ll << 20;
+    long long opt_table_capacity = 0;   // 0: sized from the selection
     long long opt_max_batch_frames = 2048;
     int opt_profile = 0;
+    int opt_fused = 1;                // 1: use the one-CTA-per-frame kernel when a frame fits in shared memory
+    long long opt_fused_lw_cap = 0;   // 0: automatic
+    long long opt_fused_cell_cap = 0; // 0: automatic
+    long long opt_fused_pair_cap = 0; // 0: automatic
+    long long opt_fused_stages = 3;   // depth of the water-tile ring
+    int fused_grow = 0;
+
+    // fused-path plan (valid for the current run)
+    bool water_regular = false;       // water point i of every system is atom first + i * stride
+    int water_stride = 0;
+    bool fused_active = false;
+    FusedCfg fc{};
+    long long fused_fallbacks = 0;
 
     // run state
     bool running = false, finalized = false;
@@ -84,7 +98,7 @@ struct hb_ctx {
     long long table_cap = 0;
     long long alloc_sig[7] = {0, 0, 0, 0, 0, 0, 0};
     int table_grows = 0;
-    int* h_status = nullptr;          // pinned: [0] n_keys, [1] overflow
+    int* h_status = nullptr;          // pinned, 4 ints per slot: n_keys, overflow, fused_overflow, pad
     unsigned long long* h_hits = nullptr;
 
     // batch scratch
@@ -99,13 +113,22 @@ struct hb_ctx {
     cudaEvent_t ev_run0{}, ev_run1{};
     long long batch_counter = 0;
 
-    struct Slot { bool busy; const float* d_xyz; long long f0; int nf; long long apf; };
-    Slot slots[2] = {{false, nullptr, 0, 0, 0}, {false, nullptr, 0, 0, 0}};
+    struct Slot { bool busy; const float* d_xyz; long long f0; int nf; long long apf; size_t bytes; };
+    Slot slots[2] = {{false, nullptr, 0, 0, 0, 0}, {false, nullptr, 0, 0, 0, 0}};
 
     // results
     long long n_bonds = 0;
-    unsigned long long* d_out_keys = nullptr;
+    unsigned long long* d_out_keys = nullptr;     // == fin_k[fin_cur] after hb_finalize
     unsigned* d_out_rows = nullptr;
+    size_t out_rows_cap = 0;                      // bytes
+    // finalize scratch, kept across runs
+    unsigned long long* fin_k[2] = {nullptr, nullptr};
+    unsigned* fin_v[2] = {nullptr, nullptr};
+    unsigned* fin_hist = nullptr;
+    int* fin_counter = nullptr;
+    size_t fin_cap = 0, fin_hist_cap = 0;
+    long long n_sel_total = 0, n_wat_total = 0;
+    int trace = 0;
 
     // timers
     hb_timers tm{};
@@ -122,6 +145,18 @@ struct hb_ctx {
             return HB_ERR_CUDA;                                                                    \
         }                                                                                          \
     } while (0)
+
+// HBGPU_TRACE=1: wall-clock trace of the host-side phases on stderr
+struct Trace {
+    hb_ctx* ctx; const char* what; std::chrono::steady_clock::time_point t0;
+    Trace(hb_ctx* c, const char* w) : ctx(c), what(w), t0(std::chrono::steady_clock::now()) {}
+    void mark(const char* step) {
+        if (!ctx->trace) return;
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[hbgpu] %s/%s %.3f ms\n", what, step, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 static int fail(hb_ctx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
@@ -206,6 +241,7 @@ int hb_create(hb_ctx** out, int device) {
     hb_ctx* ctx = new (std::nothrow) hb_ctx();
     if (!ctx) return HB_ERR_NOMEM;
     ctx->device = device;
+    ctx->trace = getenv("HBGPU_TRACE") != nullptr;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e);
         delete ctx;
@@ -225,7 +261,7 @@ int hb_create(hb_ctx** out, int device) {
     }
     cudaEventCreate(&ctx->ev_run0);
     cudaEventCreate(&ctx->ev_run1);
-    cudaHostAlloc((void**)&ctx->h_status, 4 * sizeof(int), cudaHostAllocDefault);
+    cudaHostAlloc((void**)&ctx->h_status, 8 * sizeof(int), cudaHostAllocDefault);
     cudaHostAlloc((void**)&ctx->h_hits, sizeof(unsigned long long), cudaHostAllocDefault);
     *out = ctx;
     return HB_OK;
@@ -243,8 +279,18 @@ static void free_run(hb_ctx* ctx) {
     if (ctx->bt.bits) cudaFree(ctx->bt.bits);
     if (ctx->bt.n_keys) cudaFree(ctx->bt.n_keys);
     ctx->bt = BondTable{};
-    if (ctx->d_out_keys) cudaFree(ctx->d_out_keys);
     if (ctx->d_out_rows) cudaFree(ctx->d_out_rows);
+    for (int k = 0; k < 2; ++k) {
+        if (ctx->fin_k[k]) cudaFree(ctx->fin_k[k]);
+        if (ctx->fin_v[k]) cudaFree(ctx->fin_v[k]);
+        ctx->fin_k[k] = nullptr;
+        ctx->fin_v[k] = nullptr;
+    }
+    if (ctx->fin_hist) cudaFree(ctx->fin_hist);
+    if (ctx->fin_counter) cudaFree(ctx->fin_counter);
+    ctx->fin_hist = nullptr;
+    ctx->fin_counter = nullptr;
+    ctx->fin_cap = ctx->fin_hist_cap = ctx->out_rows_cap = 0;
     ctx->d_out_keys = nullptr;
     ctx->d_out_rows = nullptr;
     ctx->running = ctx->finalized = false;
@@ -277,6 +323,11 @@ int hb_set_option(hb_ctx* ctx, const char* name, int64_t value) {
     else if (n == "table_capacity") ctx->opt_table_capacity = std::max<long long>(value, 1024);
     else if (n == "profile") ctx->opt_profile = value != 0;
     else if (n == "max_batch_frames") ctx->opt_max_batch_frames = std::max<long long>(value, 1);
+    else if (n == "fused") ctx->opt_fused = value != 0;
+    else if (n == "fused_lw_cap") ctx->opt_fused_lw_cap = std::max<long long>(value, 0);
+    else if (n == "fused_cell_cap") ctx->opt_fused_cell_cap = std::max<long long>(value, 0);
+    else if (n == "fused_pair_cap") ctx->opt_fused_pair_cap = std::max<long long>(value, 0);
+    else if (n == "fused_stages") ctx->opt_fused_stages = std::max<long long>(value, 2);
     else return fail(ctx, HB_ERR_ARG, "unknown option " + n);
     return HB_OK;
 }
@@ -298,6 +349,8 @@ int hb_set_topology(hb_ctx* ctx, const hb_topology* t) {
     ctx->h_sys_wat_off.assign(t->sys_wat_off, t->sys_wat_off + ns + 1);
     ctx->max_sel = ctx->max_wat = 0;
     ctx->max_atoms = 0;
+    ctx->n_sel_total = t->n_sel;
+    ctx->n_wat_total = t->n_wat;
     for (int s = 0; s < ns; ++s) {
         int a = t->sys_sel_off[s + 1] - t->sys_sel_off[s], w = t->sys_wat_off[s + 1] - t->sys_wat_off[s];
         long long at = t->sys_atom_off[s + 1] - t->sys_atom_off[s];
@@ -327,6 +380,18 @@ int hb_set_topology(hb_ctx* ctx, const hb_topology* t) {
     }
     for (int k = 0; k < t->n_ent_h; ++k)
         if (t->ent_h_atom[k] < 0 || t->ent_h_atom[k] >= ctx->max_atoms) return fail(ctx, HB_ERR_ARG, "topology: hydrogen atom out of range");
+    // water points at a constant atom stride (O, H, H, O, H, H ...) can be streamed as contiguous slabs
+    ctx->water_regular = t->n_wat > 0;
+    ctx->water_stride = 0;
+    for (int s = 0; s < ns && ctx->water_regular; ++s) {
+        int w0 = t->sys_wat_off[s], w1 = t->sys_wat_off[s + 1];
+        for (int i = w0 + 1; i < w1; ++i) {
+            int d = t->wat_atom[i] - t->wat_atom[i - 1];
+            if (ctx->water_stride == 0) ctx->water_stride = d;
+            if (d != ctx->water_stride || d < 1) { ctx->water_regular = false; break; }
+        }
+    }
+    if (ctx->water_stride == 0) ctx->water_stride = 1;
 
     DevTopo& d = ctx->tp;
     d.n_systems = ns;
@@ -347,6 +412,14 @@ int hb_set_topology(hb_ctx* ctx, const hb_topology* t) {
     if ((rc = upload(ctx, t->ent_residue, t->n_ent, &d.ent_residue, ctx->topo_allocs))) return rc;
     if ((rc = upload(ctx, t->n_ent ? t->ent_h_off : zero_off, (size_t)t->n_ent + 1, &d.ent_h_off, ctx->topo_allocs))) return rc;
     if ((rc = upload(ctx, t->ent_h_atom, t->n_ent_h, &d.ent_h_atom, ctx->topo_allocs))) return rc;
+    {   // packed copies for the kernels
+        std::vector<int4> sp((size_t)std::max(t->n_sel, 1)), ep((size_t)std::max(t->n_ent, 1));
+        for (int i = 0; i < t->n_sel; ++i) sp[i] = make_int4(t->sel_don[i], t->sel_acc[i], t->sel_wat[i], t->sel_bb[i] ? 1 : 0);
+        for (int e = 0; e < t->n_ent; ++e)
+            ep[e] = make_int4(t->ent_resid[e], t->ent_residue[e], t->ent_h_off[e], t->ent_h_off[e + 1] - t->ent_h_off[e]);
+        if ((rc = upload(ctx, sp.data(), sp.size(), &d.sel_pack, ctx->topo_allocs))) return rc;
+        if ((rc = upload(ctx, ep.data(), ep.size(), &d.ent_pack, ctx->topo_allocs))) return rc;
+    }
     ctx->d_ent_group = (int*)d.ent_group;
     ctx->n_ent = t->n_ent;
     ctx->have_topo = true;
@@ -387,6 +460,58 @@ int hb_set_params(hb_ctx* ctx, const hb_params* p) {
     return HB_OK;
 }
 
+// Decide whether the one-CTA-per-frame kernel can serve this run and lay out its shared memory.
+// `grow` > 0 doubles the local-water / pair capacities that many times (used after a fused overflow).
+static bool plan_fused(hb_ctx* ctx, int grow = 0) {
+    ctx->fused_active = false;
+    if (!ctx->opt_fused) return false;
+    const bool wa = ctx->rp.method == HB_METHOD_WATER_AROUND;
+    FusedCfg fc{};
+    fc.sel_cap = std::max(ctx->max_sel, 1);
+    long long lw = 0;
+    if (wa && ctx->max_wat > 0) {
+        lw = ctx->opt_fused_lw_cap ? ctx->opt_fused_lw_cap : std::max<long long>(256, fc.sel_cap);
+        lw <<= grow;
+        lw = std::min<long long>(lw, ctx->max_wat);
+    }
+    fc.lw_cap = (int)lw;
+    if ((long long)fc.sel_cap + fc.lw_cap > 65535) return false;      // 16-bit cell cursors / pair indices
+    long long cc = ctx->opt_fused_cell_cap ? ctx->opt_fused_cell_cap : 4096;
+    fc.cell_cap = (int)std::min<long long>(cc, 32768);
+    fc.pair_cap = (int)((ctx->opt_fused_pair_cap ? ctx->opt_fused_pair_cap : 2048) << grow);
+    fc.regular = (wa && ctx->water_regular && ctx->water_stride <= 8) ? 1 : 0;
+    fc.w_stride = ctx->water_stride;
+    fc.stages = fc.regular ? (int)std::min<long long>(std::max<long long>(ctx->opt_fused_stages, 2), FUSED_MAX_STAGES) : 0;
+    fc.stage_bytes = fc.regular ? (unsigned)(((FUSED_TILE - 1) * fc.w_stride * 12 + 12 + 15 + 15 + 16) & ~15) : 0u;
+    size_t off = (sizeof(FusedShared) + 15) & ~(size_t)15;
+    fc.off_spos = (unsigned)off;
+    off += (size_t)fc.sel_cap * 16;
+    fc.off_union = (unsigned)off;
+    size_t un_b = (size_t)fc.sel_cap * 16 + (size_t)fc.stages * fc.stage_bytes;
+    size_t un_c = ((size_t)fc.sel_cap + fc.lw_cap) * 16 + (size_t)fc.pair_cap * 4;
+    off += (std::max(un_b, un_c) + 15) & ~(size_t)15;
+    fc.off_lw = (unsigned)off;
+    off += (size_t)fc.lw_cap * 16;
+    fc.off_cells = (unsigned)off;
+    off += (((size_t)fc.cell_cap + 2) * 2 + 15) & ~(size_t)15;
+    fc.off_near = (unsigned)off;
+    off += (((size_t)fc.cell_cap + 31) / 32 * 4 + 15) & ~(size_t)15;
+    fc.off_cand = (unsigned)off;
+    off += wa ? (size_t)FUSED_CWARPS * FUSED_CAND * 16 : 0;
+    fc.off_bar = (unsigned)off;
+    off += (size_t)2 * FUSED_MAX_STAGES * 8;
+    fc.smem_bytes = (unsigned)off;
+    if (fc.smem_bytes > 112 * 1024) return false;                     // keep at least two frames resident per SM
+    if (cudaFuncSetAttribute(k_frame_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fc.smem_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    ctx->fc = fc;
+    ctx->fused_grow = grow;
+    ctx->fused_active = true;
+    return true;
+}
+
 static int alloc_table(hb_ctx* ctx, BondTable& bt, long long cap, int wpr) {
     bt = BondTable{};
     bt.mask = (unsigned)(cap - 1);
@@ -406,11 +531,19 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     if (ctx->prm.structure_batch && n_frames_total != ctx->tp.n_systems)
         return fail(ctx, HB_ERR_ARG, "structure_batch: n_frames_total must equal n_systems");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaDeviceSynchronize());
+    Trace tr(ctx, "begin");
+    CK(cudaStreamSynchronize(ctx->s_copy));
+    CK(cudaStreamSynchronize(ctx->s_compute));
     drain_events(ctx);
+    tr.mark("sync");
     int wpr = (int)((n_frames_total + 31) / 32);
+    long long want = ctx->opt_table_capacity;
+    if (!want) {   // a few slots per selection point (+ as many local waters); the table doubles on demand
+        want = 8 * (ctx->n_sel_total + (ctx->rp.method == HB_METHOD_WATER_AROUND ? std::min(ctx->n_sel_total, ctx->n_wat_total) : 0));
+        want = std::min<long long>(std::max<long long>(want, 4096), 1ll << 22);
+    }
     long long cap = 1024;
-    while (cap < ctx->opt_table_capacity) cap <<= 1;
+    while (cap < want) cap <<= 1;
     size_t npts = (size_t)ctx->max_sel + ctx->max_wat;
     long long cc = 4096;
     while (cc < (long long)(2 * npts)) cc <<= 1;
@@ -422,6 +555,8 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     fb = std::max<long long>(1, std::min<long long>(fb, ctx->opt_max_batch_frames));
     fb = std::min<long long>(fb, n_frames_total);
     if (fb >= 32) fb -= fb % 32;
+    plan_fused(ctx);
+    tr.mark("plan");
     // allocations of the previous run are reused when nothing that sizes them changed
     long long sig[7] = {wpr, ctx->max_sel, ctx->max_wat, ctx->max_atoms, fb, cc, ctx->prm.structure_batch};
     bool reuse = ctx->bt.keys && ctx->table_cap >= cap && memcmp(sig, ctx->alloc_sig, sizeof(sig)) == 0;
@@ -432,6 +567,7 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     ctx->next_frame = 0;
     ctx->batch_counter = 0;
     ctx->table_grows = 0;
+    ctx->fused_fallbacks = 0;
     for (auto& sl : ctx->slots) sl.busy = false;
     int rc;
     if (reuse) {
@@ -439,8 +575,7 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
         k_fill_u64<<<1184, 256, 0, ctx->s_compute>>>(ctx->bt.keys, tc, EMPTY_KEY);
         CK(cudaMemsetAsync(ctx->bt.bits, 0, tc * wpr * sizeof(unsigned), ctx->s_compute));
         CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 4 * sizeof(unsigned long long), ctx->s_compute));
-        if (ctx->d_out_keys) { cudaFree(ctx->d_out_keys); ctx->d_out_keys = nullptr; }
-        if (ctx->d_out_rows) { cudaFree(ctx->d_out_rows); ctx->d_out_rows = nullptr; }
+        if (ctx->trace) { cudaStreamSynchronize(ctx->s_compute); tr.mark("clear(reuse)"); }
         ctx->running = true;
         ctx->finalized = false;
         return HB_OK;
@@ -451,7 +586,8 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     CK(cudaMalloc((void**)&ctx->bt.n_keys, 4 * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 4 * sizeof(unsigned long long), ctx->s_compute));
     ctx->bt.overflow = ctx->bt.n_keys + 1;
-    ctx->bt.n_hits = (unsigned long long*)(ctx->bt.n_keys + 2);
+    ctx->bt.fused_overflow = ctx->bt.n_keys + 2;
+    ctx->bt.n_hits = (unsigned long long*)(ctx->bt.n_keys + 4);
 
     ctx->cell_cap = (int)cc;
     ctx->batch_frames = (int)fb;
@@ -487,6 +623,7 @@ static int grow_table(hb_ctx* ctx) {
     if (rc) return rc;
     nt.n_keys = ctx->bt.n_keys;
     nt.overflow = ctx->bt.overflow;
+    nt.fused_overflow = ctx->bt.fused_overflow;
     nt.n_hits = ctx->bt.n_hits;
     k_rehash<<<(unsigned)ctx->table_cap, 128, 0, ctx->s_compute>>>(ctx->bt, nt);
     CK(cudaGetLastError());
@@ -500,7 +637,8 @@ static int grow_table(hb_ctx* ctx) {
 }
 
 // launch the kernel pipeline for one batch resident at d_xyz
-static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, long long atoms_per_frame) {
+static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, long long atoms_per_frame,
+                     size_t xyz_bytes, bool allow_fused = true) {
     BatchView bv = ctx->bv;
     bv.xyz = d_xyz;
     bv.frame0 = frame0;
@@ -513,6 +651,18 @@ static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, 
     bool wa = rp.method == HB_METHOD_WATER_AROUND;
     cudaEvent_t t0 = get_event(ctx), t1 = get_event(ctx);
     cudaEventRecord(t0, st);
+    if (ctx->fused_active && allow_fused) {
+        FusedCfg fc = ctx->fc;
+        fc.buf_begin = (unsigned long long)(uintptr_t)d_xyz;
+        fc.buf_end = fc.buf_begin + xyz_bytes;
+        { KTimer t(ctx, KC_FUSED); k_frame_fused<<<nf, FUSED_THREADS, fc.smem_bytes, st>>>(bv, tp, rp, ctx->bt, fc); }
+        cudaEventRecord(t1, st);
+        ctx->pending.push_back({t0, t1, -1});
+        CK(cudaGetLastError());
+        ctx->tm.frames += nf;
+        ctx->tm.fused_frames += nf;
+        return HB_OK;
+    }
     { KTimer t(ctx, KC_INIT); k_init_frames<<<(nf + 127) / 128, 128, 0, st>>>(bv); }
     size_t cells_bytes = (size_t)nf * (bv.cell_cap + 1) * 4;
     if (wa) CK(cudaMemsetAsync(bv.cells1, 0, cells_bytes, st));
@@ -549,23 +699,30 @@ static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, 
 static int full_verify(hb_ctx* ctx) {
     for (int attempt = 0; attempt < 28; ++attempt) {
         CK(cudaStreamSynchronize(ctx->s_compute));
-        int st[2];
+        int st[3];
         CK(cudaMemcpy(st, ctx->bt.n_keys, sizeof(st), cudaMemcpyDeviceToHost));
-        bool overflow = st[1] != 0;
-        if (!overflow && (long long)st[0] * 2 <= ctx->table_cap) {
+        bool overflow = st[1] != 0, fused_overflow = st[2] != 0;
+        if (!overflow && !fused_overflow && (long long)st[0] * 2 <= ctx->table_cap) {
             for (auto& sl : ctx->slots) sl.busy = false;
             return HB_OK;
         }
-        int rc = grow_table(ctx);
-        if (rc) return rc;
-        while ((long long)st[0] * 2 > ctx->table_cap)
+        int rc;
+        if (overflow || (long long)st[0] * 2 > ctx->table_cap) {
             if ((rc = grow_table(ctx))) return rc;
-        if (overflow) {
-            CK(cudaMemsetAsync(ctx->bt.overflow, 0, sizeof(int), ctx->s_compute));
+            while ((long long)st[0] * 2 > ctx->table_cap)
+                if ((rc = grow_table(ctx))) return rc;
+        }
+        if (fused_overflow) {      // some frame did not fit in shared memory: retry with doubled capacities
+            ctx->fused_fallbacks++;   // while they fit, else this run continues on the general path
+            if (ctx->opt_fused_lw_cap || ctx->opt_fused_pair_cap || ctx->fused_grow >= 6 || !plan_fused(ctx, ctx->fused_grow + 1))
+                ctx->fused_active = false;
+        }
+        if (overflow || fused_overflow) {
+            CK(cudaMemsetAsync(ctx->bt.overflow, 0, 2 * sizeof(int), ctx->s_compute));
             for (auto& sl : ctx->slots)
                 if (sl.busy) {
                     long long frames_before = ctx->tm.frames;
-                    if ((rc = run_batch(ctx, sl.d_xyz, sl.f0, sl.nf, sl.apf))) return rc;
+                    if ((rc = run_batch(ctx, sl.d_xyz, sl.f0, sl.nf, sl.apf, sl.bytes))) return rc;
                     ctx->tm.frames = frames_before;
                 }
         }
@@ -578,18 +735,18 @@ static int acquire_slot(hb_ctx* ctx, int k) {
     hb_ctx::Slot& sl = ctx->slots[k];
     if (!sl.busy) return HB_OK;
     CK(cudaEventSynchronize(ctx->ev_done[k]));
-    int nkeys = ctx->h_status[2 * k], overflow = ctx->h_status[2 * k + 1];
+    int nkeys = ctx->h_status[4 * k], overflow = ctx->h_status[4 * k + 1] | ctx->h_status[4 * k + 2];
     if (overflow || (long long)nkeys * 2 > ctx->table_cap) return full_verify(ctx);
     sl.busy = false;
     return HB_OK;
 }
 
-static int launch_in_slot(hb_ctx* ctx, int k, const float* d_xyz, long long f0, int nf, long long apf) {
-    int rc = run_batch(ctx, d_xyz, f0, nf, apf);
+static int launch_in_slot(hb_ctx* ctx, int k, const float* d_xyz, long long f0, int nf, long long apf, size_t bytes) {
+    int rc = run_batch(ctx, d_xyz, f0, nf, apf, bytes);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(ctx->h_status + 2 * k, ctx->bt.n_keys, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->s_compute));
+    CK(cudaMemcpyAsync(ctx->h_status + 4 * k, ctx->bt.n_keys, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->s_compute));
     CK(cudaEventRecord(ctx->ev_done[k], ctx->s_compute));
-    ctx->slots[k] = hb_ctx::Slot{true, d_xyz, f0, nf, apf};
+    ctx->slots[k] = hb_ctx::Slot{true, d_xyz, f0, nf, apf, bytes};
     return HB_OK;
 }
 
@@ -646,7 +803,7 @@ int hb_submit_frames(hb_ctx* ctx, const float* xyz, int64_t n_atoms, int64_t n_f
         ctx->pending.push_back({c0, c1, -2});
         CK(cudaEventRecord(ctx->ev_copied[k], ctx->s_copy));
         CK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_copied[k], 0));
-        if ((rc = launch_in_slot(ctx, k, ctx->d_in[k], f0, nf, n_atoms))) return rc;
+        if ((rc = launch_in_slot(ctx, k, ctx->d_in[k], f0, nf, n_atoms, bytes))) return rc;
         ctx->batch_counter++;
         ctx->next_frame += nf;
         done += nf;
@@ -671,7 +828,7 @@ int hb_submit_frames_device(hb_ctx* ctx, const float* d_xyz, int64_t n_atoms, in
         long long atoms = batch_atoms(ctx, f0, nf, n_atoms);
         int k = (int)(ctx->batch_counter & 1);
         if ((rc = acquire_slot(ctx, k))) return rc;
-        if ((rc = launch_in_slot(ctx, k, src, f0, nf, n_atoms))) return rc;
+        if ((rc = launch_in_slot(ctx, k, src, f0, nf, n_atoms, (size_t)atoms * 12))) return rc;
         ctx->batch_counter++;
         ctx->next_frame += nf;
         done += nf;
@@ -703,8 +860,10 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
         return HB_OK;
     }
     if (!ctx->running) return fail(ctx, HB_ERR_STATE, "hb_finalize before hb_begin");
+    Trace tr(ctx, "finalize");
     int rc = hb_sync(ctx);
     if (rc) return rc;
+    tr.mark("sync");
     cudaStream_t st = ctx->s_compute;
     CK(cudaMemcpyAsync(ctx->h_status, ctx->bt.n_keys, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(ctx->h_hits, ctx->bt.n_hits, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -712,23 +871,45 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
     int n = ctx->h_status[0];
     ctx->tm.pairs_emitted = (long long)*ctx->h_hits;
     int wpr = ctx->bt.wpr;
-    if (ctx->d_out_keys) { cudaFree(ctx->d_out_keys); ctx->d_out_keys = nullptr; }
-    if (ctx->d_out_rows) { cudaFree(ctx->d_out_rows); ctx->d_out_rows = nullptr; }
-    unsigned long long *k0 = nullptr, *k1 = nullptr;
-    unsigned *v0 = nullptr, *v1 = nullptr, *hist = nullptr;
-    int* counter = nullptr;
     size_t nn = std::max(n, 1);
-    CK(cudaMalloc((void**)&k0, nn * 8));
-    CK(cudaMalloc((void**)&k1, nn * 8));
-    CK(cudaMalloc((void**)&v0, nn * 4));
-    CK(cudaMalloc((void**)&v1, nn * 4));
-    CK(cudaMalloc((void**)&counter, 4));
+    int nblk = (n + RS_TILE - 1) / RS_TILE;
+    if (nn > ctx->fin_cap) {                      // (re)allocate the sort buffers with headroom
+        size_t cap2 = std::max<size_t>(nn * 2, 4096);
+        for (int k = 0; k < 2; ++k) {
+            if (ctx->fin_k[k]) cudaFree(ctx->fin_k[k]);
+            if (ctx->fin_v[k]) cudaFree(ctx->fin_v[k]);
+            ctx->fin_k[k] = nullptr; ctx->fin_v[k] = nullptr;
+        }
+        ctx->fin_cap = 0;
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaMalloc((void**)&ctx->fin_k[k], cap2 * 8));
+            CK(cudaMalloc((void**)&ctx->fin_v[k], cap2 * 4));
+        }
+        ctx->fin_cap = cap2;
+    }
+    size_t hist_need = (size_t)256 * std::max(nblk, 1) * 4;
+    if (hist_need > ctx->fin_hist_cap) {
+        if (ctx->fin_hist) cudaFree(ctx->fin_hist);
+        ctx->fin_hist = nullptr; ctx->fin_hist_cap = 0;
+        CK(cudaMalloc((void**)&ctx->fin_hist, hist_need * 2));
+        ctx->fin_hist_cap = hist_need * 2;
+    }
+    if (!ctx->fin_counter) CK(cudaMalloc((void**)&ctx->fin_counter, 4));
+    size_t rows_need = nn * (size_t)wpr * 4;
+    if (rows_need > ctx->out_rows_cap) {
+        if (ctx->d_out_rows) cudaFree(ctx->d_out_rows);
+        ctx->d_out_rows = nullptr; ctx->out_rows_cap = 0;
+        CK(cudaMalloc((void**)&ctx->d_out_rows, rows_need * 2));
+        ctx->out_rows_cap = rows_need * 2;
+    }
+    tr.mark("alloc");
+    unsigned long long *k0 = ctx->fin_k[0], *k1 = ctx->fin_k[1];
+    unsigned *v0 = ctx->fin_v[0], *v1 = ctx->fin_v[1], *hist = ctx->fin_hist;
+    int* counter = ctx->fin_counter;
     CK(cudaMemsetAsync(counter, 0, 4, st));
     unsigned cap = ctx->bt.mask + 1u;
     k_compact<<<(cap + 255) / 256, 256, 0, st>>>(ctx->bt, k0, v0, counter);
-    int nblk = (n + RS_TILE - 1) / RS_TILE;
     if (n > 1) {
-        CK(cudaMalloc((void**)&hist, (size_t)256 * nblk * 4));
         for (int pass = 0; pass < 8; ++pass) {
             int shift = pass * 8;
             k_rs_hist<<<nblk, 256, 0, st>>>(k0, n, shift, hist);
@@ -738,7 +919,6 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
             std::swap(v0, v1);
         }
     }
-    CK(cudaMalloc((void**)&ctx->d_out_rows, nn * (size_t)wpr * 4));
     if (n > 0) k_gather_rows<<<1184, 256, 0, st>>>(ctx->bt.bits, v0, n, wpr, ctx->d_out_rows);
     CK(cudaGetLastError());
     CK(cudaEventRecord(ctx->ev_run1, st));
@@ -748,11 +928,7 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
         if (cudaEventElapsedTime(&ms, ctx->ev_run0, ctx->ev_run1) == cudaSuccess) ctx->tm.ms_run = ms;
     }
     ctx->d_out_keys = k0;
-    cudaFree(k1);
-    cudaFree(v0);
-    cudaFree(v1);
-    cudaFree(counter);
-    if (hist) cudaFree(hist);
+    tr.mark("sort+gather");
     ctx->n_bonds = n;
     ctx->finalized = true;
     ctx->running = false;
@@ -814,6 +990,7 @@ int hb_get_timers(hb_ctx* ctx, hb_timers* out) {
     drain_events(ctx);
     ctx->tm.table_capacity = ctx->table_cap;
     ctx->tm.table_grows = ctx->table_grows;
+    ctx->tm.fused_fallbacks = ctx->fused_fallbacks;
     *out = ctx->tm;
     return HB_OK;
 }

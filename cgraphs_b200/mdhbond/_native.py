@@ -63,6 +63,8 @@ class HbTimers(C.Structure):
         ("table_capacity", C.c_int64),
         ("table_grows", C.c_int64),
         ("ms_run", C.c_double),
+        ("fused_frames", C.c_int64),
+        ("fused_fallbacks", C.c_int64),
     ]
 
 
@@ -247,6 +249,7 @@ class Context:
             k += 1
         return dict(ms_total=t.ms_total, ms_h2d=t.ms_h2d, ms_run=t.ms_run, n_launches=t.n_launches, frames=t.frames,
                     pairs_emitted=t.pairs_emitted, table_capacity=t.table_capacity, table_grows=t.table_grows,
+                    fused_frames=t.fused_frames, fused_fallbacks=t.fused_fallbacks,
                     ms_kernel={n: t.ms_kernel[i] for i, n in enumerate(names)},
                     launches={n: t.launches[i] for i, n in enumerate(names)})
 

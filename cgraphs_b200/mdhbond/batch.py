@@ -30,11 +30,12 @@ class StructureResult(object):
 
 
 class HbondBatch(object):
-    def __init__(self, structures, selection, device=None, **ctor_kwargs):
+    def __init__(self, structures, selection, device=None, native_options=None, **ctor_kwargs):
         """structures: Universe-like objects (single frame each); other kwargs as HbondAnalysis."""
         if not structures:
             raise AssertionError('No structure file path.')
         self._device = device
+        self._native_options = dict(native_options or {})
         self.analyses = [HbondAnalysis(selection, s, device=device, **ctor_kwargs) for s in structures]
         a0 = self.analyses[0]
         self.check_angle, self.residuewise = a0.check_angle, a0.residuewise
@@ -62,6 +63,8 @@ class HbondBatch(object):
         tables, group_names = pack_systems(tops, [t.key_ids(method) for t in tops], n_atoms)
         if self._ctx is None:
             self._ctx = _native.Context(self._device if self._device is not None else 0)
+            for name, value in self._native_options.items():
+                self._ctx.set_option(name, value)
         ctx = self._ctx
         ctx.set_topology(tables)
         cthr = _cos_threshold(float(self.cut_angle)) if self.check_angle else -1.0

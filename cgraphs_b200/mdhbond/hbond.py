@@ -13,7 +13,8 @@ same result objects (``initial_results`` / ``filtered_results`` = ``dict[str, bo
 
 Extra keyword arguments (all optional, parity-preserving defaults): ``device`` (CUDA ordinal),
 ``shard=(rank, world)`` to process only a contiguous frame block per rank and merge bond keys with one
-all-gather, ``cos_threshold`` to pin the calibrated angle threshold, ``batch_bytes``.
+all-gather, ``cos_threshold`` to pin the calibrated angle threshold, ``batch_bytes``, ``native_options``
+(dict passed to ``hb_set_option``, e.g. ``{"fused": 0}`` to force the general kernels).
 
 Documented divergences from the reference: frames without any candidate pair / local water
 are frames without bonds here, while the reference raises IndexError (hbond.py:110,254,261).
@@ -88,8 +89,10 @@ class HbondAnalysis(object):
                  start=None, stop=None, step=1, additional_donors=[],
                  additional_acceptors=[], exclude_donors=[], exclude_acceptors=[],
                  ions=[], check_angle=True, residuewise=True, add_donors_without_hydrogen=False,
-                 restore_filename=None, device=None, shard=None, cos_threshold=None, batch_bytes=None):
+                 restore_filename=None, device=None, shard=None, cos_threshold=None, batch_bytes=None,
+                 native_options=None):
         self._device = device
+        self._native_options = dict(native_options or {})
         self._shard = shard
         self._cos_threshold_override = cos_threshold
         self._batch_bytes = batch_bytes
@@ -199,6 +202,8 @@ class HbondAnalysis(object):
             self._ctx = _native.Context(dev)
             if self._batch_bytes:
                 self._ctx.set_option("batch_bytes", self._batch_bytes)
+            for name, value in self._native_options.items():
+                self._ctx.set_option(name, value)
         return self._ctx
 
     def _check_hydrogen_tables(self, method):

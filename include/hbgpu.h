@@ -109,6 +109,9 @@ typedef struct {
     int64_t table_capacity;       /* bond hash-table slots */
     int64_t table_grows;
     double ms_run;                /* device time from hb_begin to the end of hb_finalize (CUDA events) */
+    int64_t fused_frames;         /* frames processed by the one-CTA-per-frame kernel */
+    int64_t fused_fallbacks;      /* times a frame did not fit in shared memory and the run moved to the
+                                     general (global-memory cell list) kernels */
 } hb_timers;
 
 int hb_create(hb_ctx** out, int device_ordinal);
@@ -122,7 +125,9 @@ int hb_set_entry_groups(hb_ctx* ctx, const int32_t* ent_group, int32_t n_ent); /
 int hb_set_params(hb_ctx* ctx, const hb_params* params);
 int hb_set_option(hb_ctx* ctx, const char* name, int64_t value);
         /* "batch_bytes": device budget per frame batch; "table_capacity": initial bond-table slots;
-           "profile": 1 = time every kernel class with CUDA events; "max_batch_frames" */
+           "profile": 1 = time every kernel class with CUDA events; "max_batch_frames";
+           "fused": 0 = never use the one-CTA-per-frame kernel; "fused_lw_cap" / "fused_cell_cap": its
+           shared-memory capacities (0 = automatic) */
 
 /* Start an analysis over n_frames_total frames (the width of the occupancy matrix). */
 int hb_begin(hb_ctx* ctx, int64_t n_frames_total);

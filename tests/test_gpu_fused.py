@@ -1,0 +1,142 @@
+"""The one-CTA-per-frame kernel (hb_fused.cuh) and the general multi-kernel path (hb_general.cuh) must
+give the same bits as the CPU oracle; frames that do not fit in shared memory must fall back without
+losing or duplicating anything."""
+import itertools
+
+import numpy as np
+import pytest
+
+from cgraphs_b200 import synth
+from cgraphs_b200.universe import Universe
+from tests.helpers import assert_same_results
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(u, selection, method, options, around=3.5, **kw):
+    from cgraphs_b200.mdhbond import HbondAnalysis
+    hba = HbondAnalysis(selection, u, native_options=options, **kw)
+    if method == "in_selection":
+        hba.set_hbonds_in_selection()
+    else:
+        hba.set_hbonds_in_selection_and_water_around(around)
+    return hba
+
+
+def _port(u, selection, method, around=3.5, **kw):
+    from oracle import hbond_port
+    return hbond_port.run(u, selection, method, around=around, **kw)
+
+
+@pytest.mark.parametrize("seed", [0, 1])
+def test_fused_and_general_match_oracle(seed):
+    s = synth.make_system(5000, 40, 900 + seed, hydrogens=True, water="TIP3", n_chains=2)
+    u = s.universe(9)
+    for sel, method, ca in itertools.product(["protein", "protein or resname TIP3"],
+                                             ["in_selection", "water_around"], [True, False]):
+        kw = dict(check_angle=ca, additional_donors=['N'], additional_acceptors=['O'])
+        ref = _port(u, sel, method, **kw).initial_results
+        f = _run(u, sel, method, {"fused": 1}, **kw)
+        g = _run(u, sel, method, {"fused": 0}, **kw)
+        assert_same_results(f.initial_results, ref, "fused %s %s %s" % (sel, method, ca))
+        assert_same_results(g.initial_results, ref, "general %s %s %s" % (sel, method, ca))
+        assert g.last_run_stats["fused_frames"] == 0
+        assert f.last_run_stats["fused_frames"] == 9, f.last_run_stats
+        assert f.last_run_stats["n_launches"] < g.last_run_stats["n_launches"]
+
+
+def test_fused_c3_half_scale():
+    s, cfg = synth.config("C3", scale=0.5)
+    u = s.universe(6)
+    kw = dict(check_angle=True)
+    ref = _port(u, "protein", "water_around", **kw).initial_results
+    f = _run(u, "protein", "water_around", {"fused": 1}, **kw)
+    assert_same_results(f.initial_results, ref)
+    assert f.last_run_stats["fused_frames"] == 6 and f.last_run_stats["fused_fallbacks"] == 0
+    assert f.last_run_stats["launches"]["frame_fused"] >= 1
+
+
+def test_fused_falls_back_when_local_waters_do_not_fit():
+    s = synth.make_system(6000, 50, 77)
+    u = s.universe(5)
+    ref = _port(u, "protein", "water_around").initial_results
+    f = _run(u, "protein", "water_around", {"fused": 1, "fused_lw_cap": 8})
+    assert_same_results(f.initial_results, ref)
+    assert f.last_run_stats["fused_fallbacks"] >= 1
+
+
+def test_fused_small_cell_budget_coarsens_grid():
+    s = synth.make_system(6000, 50, 78)
+    u = s.universe(3)
+    ref = _port(u, "protein", "water_around").initial_results
+    f = _run(u, "protein", "water_around", {"fused": 1, "fused_cell_cap": 64})
+    assert_same_results(f.initial_results, ref)
+    assert f.last_run_stats["fused_frames"] == 3
+
+
+def test_fused_waters_without_regular_stride():
+    """HOH oxygens only (stride 1) and a system whose waters are interleaved irregularly."""
+    s = synth.make_system(3000, 60, 5, hydrogens=False, water="HOH")
+    u = s.universe(1, static=True)
+    kw = dict(check_angle=False, add_donors_without_hydrogen=True)
+    ref = _port(u, "protein", "water_around", **kw).initial_results
+    f = _run(u, "protein", "water_around", {"fused": 1}, **kw)
+    assert_same_results(f.initial_results, ref)
+    # irregular: drop every 7th water oxygen from the water group by renaming it
+    topo = s.topology
+    names = list(topo.names)
+    wat = [i for i, (n, r) in enumerate(zip(topo.names, topo.resnames)) if r == "HOH"]
+    for i in wat[::7]:
+        names[i] = "OX"
+    from cgraphs_b200.universe import Topology
+    t2 = Topology(names, list(topo.resnames), list(topo.resids), list(topo.segids))
+    u2 = Universe(t2, s.frames(0, 1, static=True))
+    ref2 = _port(u2, "protein", "water_around", **kw).initial_results
+    f2 = _run(u2, "protein", "water_around", {"fused": 1}, **kw)
+    assert_same_results(f2.initial_results, ref2)
+    assert f2.last_run_stats["fused_frames"] == 1
+
+
+def test_fused_structure_batch():
+    from cgraphs_b200.mdhbond import HbondBatch
+    systems = synth.c5_structures(10, seed0=5100)
+    unis = [s.universe(1, static=True) for s in systems]
+    kw = dict(check_angle=False, add_donors_without_hydrogen=True)
+    out = {}
+    for fused in (1, 0):
+        batch = HbondBatch(unis, "protein", native_options={"fused": fused}, **kw)
+        batch.set_hbonds_in_selection_and_water_around(3.5)
+        out[fused] = (batch.bond_keys, batch.occupancy.copy(), batch.last_run_stats)
+    assert out[1][0] == out[0][0]
+    assert np.array_equal(out[1][1], out[0][1])
+    assert out[1][2]["fused_frames"] == 10 and out[0][2]["fused_frames"] == 0
+    for u, col in zip(unis, range(10)):
+        ref = _port(u, "protein", "water_around", **kw).initial_results
+        got = {k for k, row in zip(out[1][0], out[1][1]) if row[col]}
+        assert got == set(ref)
+
+
+def test_fused_device_resident_unaligned_frames():
+    """Frames at 12-byte granularity in device memory: slabs that cannot be 16-byte aligned inside the
+    buffer use plain loads; results must not change with the buffer offset."""
+    import torch
+    from cgraphs_b200.mdhbond import HbondAnalysis
+    s = synth.make_system(4001, 30, 41)          # odd atom count: frame starts rotate through all alignments
+    nf = 12
+    xyz = s.frames(0, nf)
+    u = Universe(s.topology, xyz)
+    hba = HbondAnalysis("protein", u, native_options={"fused": 1})
+    hba.set_hbonds_in_selection_and_water_around(3.5)
+    ctx = hba._context()
+    ctx.begin(nf)
+    ctx.submit(xyz)
+    k0, w0 = ctx.results()
+    for pad in (0, 1, 2, 3):
+        buf = torch.zeros(xyz.size + pad, dtype=torch.float32, device="cuda")
+        buf[pad:] = torch.from_numpy(xyz.reshape(-1)).cuda()
+        torch.cuda.synchronize()
+        ctx.begin(nf)
+        ctx.submit_device(buf.data_ptr() + 4 * pad, xyz.shape[1], nf)
+        k, w = ctx.results()
+        assert np.array_equal(k, k0) and np.array_equal(w, w0), pad
+    assert ctx.timers()["fused_frames"] == nf
