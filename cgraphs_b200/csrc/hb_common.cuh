@@ -142,8 +142,8 @@ __device__ __forceinline__ float dist2f(float ax, float ay, float az, float bx, 
 __device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz) {
     return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
 }
-__device__ __forceinline__ bool ang_ok(float bx, float by, float bz, float hx, float hy, float hz, float ax,
-                                       float ay, float az, float cthr) {
+__device__ __forceinline__ bool ang_ok_exact(float bx, float by, float bz, float hx, float hy, float hz, float ax,
+                                             float ay, float az, float cthr) {
     float v1x = __fsub_rn(hx, bx), v1y = __fsub_rn(hy, by), v1z = __fsub_rn(hz, bz);
     float v2x = __fsub_rn(ax, hx), v2y = __fsub_rn(ay, hy), v2z = __fsub_rn(az, hz);
     float d12 = dot3_rn(v1x, v1y, v1z, v2x, v2y, v2z);
@@ -153,6 +153,21 @@ __device__ __forceinline__ bool ang_ok(float bx, float by, float bz, float hx, f
     float c = __fdiv_rn(d12, den);
     if (c < -1.0f) c = -1.0f;
     return (c >= cthr) && (c <= 1.0f);   // NaN fails both
+}
+// Same decision, cheaper on average: an approximate cosine (rsqrt, FMA allowed; relative error < 1e-6)
+// settles every case that is further than 1e-5 from both ends of the accepted interval [cthr, 1];
+// only the rest (and NaN / degenerate vectors) runs the exact, individually rounded chain above.
+__device__ __forceinline__ bool ang_ok(float bx, float by, float bz, float hx, float hy, float hz, float ax,
+                                       float ay, float az, float cthr) {
+    const float v1x = hx - bx, v1y = hy - by, v1z = hz - bz;
+    const float v2x = ax - hx, v2y = ay - hy, v2z = az - hz;
+    const float d12 = v1x * v2x + v1y * v2y + v1z * v2z;
+    const float d11 = v1x * v1x + v1y * v1y + v1z * v1z;
+    const float d22 = v2x * v2x + v2y * v2y + v2z * v2z;
+    const float ca = d12 * rsqrtf(d11 * d22);
+    if (ca < cthr - 1e-5f) return false;
+    if (ca > cthr + 1e-5f && ca < 1.0f - 1e-5f) return true;
+    return ang_ok_exact(bx, by, bz, hx, hy, hz, ax, ay, az, cthr);
 }
 
 __device__ void make_grid(FrameGrid& g, const float* lo, const float* hi, float pad, float cell, int cap) {

@@ -41,6 +41,7 @@ struct FusedCfg {
     int regular;              // 1: water point i is atom w_first + i * w_stride in every system -> TMA tiles
     int w_stride;             // atoms between consecutive water oxygens
     int stages;               // ring depth
+    int prefetch;             // tiles pulled into L2 ahead of the ring
     unsigned stage_bytes;     // bytes of one stage (multiple of 16)
     unsigned off_spos, off_union, off_lw, off_cells, off_near, off_cand, off_bar;   // byte offsets in dynamic smem
     unsigned smem_bytes;
@@ -90,8 +91,10 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned pari
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
     for (;;) {
-        for (int k = 0; k < 256; ++k)
+        for (int k = 0; k < 256; ++k) {
+            __nanosleep(32);
             if (mbar_try_wait(bar, parity)) return true;
+        }
         if (clock64() - t0 > 2000000000ll) return false;
     }
 }
@@ -227,16 +230,32 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_frame_fused(BatchView bv, Dev
         if (stream && lane == 0) {
             const unsigned long long gbase = (unsigned long long)(uintptr_t)(xyz + 3ll * tp.wat_atom[w0]);
             const unsigned long long lim_lo = (fc.buf_begin + 15ull) & ~15ull, lim_hi = fc.buf_end & ~15ull;
+            // tiles further ahead are pulled into L2 while the ring holds the next few: the ring then only
+            // has to cover the L2 -> shared-memory latency
+            const unsigned long long wat_end = gbase + (unsigned long long)(nwp - 1) * (unsigned long long)stride12 + 12ull;
+            auto prefetch_tile = [&](int t) {
+                unsigned long long a = (gbase + (unsigned long long)t * (unsigned long long)(FUSED_TILE * stride12)) & ~15ull;
+                unsigned long long e = a + (unsigned long long)(FUSED_TILE * stride12);
+                if (e > wat_end) e = wat_end & ~15ull;
+                if (a < lim_lo) a = lim_lo;
+                if (e > lim_hi) e = lim_hi;
+                if (e > a)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((unsigned)(e - a)) : "memory");
+            };
+            for (int t = 0; t < min(fc.prefetch, ntiles); ++t) prefetch_tile(t);
+            int st = 0;
+            unsigned parity = 1;                        // parity of the "previous round" of the empty barriers
             for (int t = 0; t < ntiles; ++t) {
-                const int st = t % fc.stages, round = t / fc.stages;
-                if (round > 0 && !mbar_wait(&empty[st], (unsigned)((round - 1) & 1))) { sh->overflow = 2; break; }
+                if (t + fc.prefetch < ntiles) prefetch_tile(t + fc.prefetch);
+                if (t >= fc.stages && !mbar_wait(&empty[st], parity)) { sh->overflow = 2; break; }
                 const int nw = min(FUSED_TILE, nwp - t * FUSED_TILE);
                 const unsigned long long ga = gbase + (unsigned long long)t * (unsigned long long)(FUSED_TILE * stride12);
                 const unsigned long long start = ga & ~15ull;
                 const unsigned head = (unsigned)(ga - start);
                 const unsigned long long end = (ga + (unsigned long long)((nw - 1) * stride12 + 12) + 15ull) & ~15ull;
                 const unsigned long long c0 = start > lim_lo ? start : lim_lo, c1 = end < lim_hi ? end : lim_hi;
-                sh->stage_head[st] = head;
+                const bool partial = c0 != start || c1 != end;     // tile touches the edge of the batch buffer
+                sh->stage_head[st] = head | (partial ? 0x80000000u : 0u);
                 unsigned char* dst = ring + (size_t)st * fc.stage_bytes;
                 if (c1 > c0) {
                     const unsigned lo = (unsigned)(c0 - start), bytes = (unsigned)(c1 - c0);
@@ -249,6 +268,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_frame_fused(BatchView bv, Dev
                     sh->stage_hi[st] = 0;
                     mbar_arrive(&full[st]);
                 }
+                if (++st == fc.stages) { st = 0; parity ^= 1u; }
             }
         }
         return;
@@ -336,26 +356,29 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_frame_fused(BatchView bv, Dev
                 }
             }
         };
+        int st = 0;
+        unsigned parity = 0;
+        const unsigned my_off = (unsigned)(tid * stride12);
         for (int t = 0; t < ntiles; ++t) {
             const int i = t * FUSED_TILE + tid;
             const bool live = i < nwp;
             float x = 0.f, y = 0.f, z = 0.f;
             if (stream) {
-                const int st = t % fc.stages;
-                if (*(volatile int*)&sh->overflow == 2) break;          // the pipeline broke down: give the frame up
-                if (!mbar_wait(&full[st], (unsigned)((t / fc.stages) & 1))) { sh->overflow = 2; break; }
-                const unsigned off = sh->stage_head[st] + (unsigned)(tid * stride12);
+                if (!mbar_wait(&full[st], parity)) { sh->overflow = 2; break; }
+                const unsigned head = sh->stage_head[st];
                 if (live) {
-                    if (off >= sh->stage_lo[st] && off + 12u <= sh->stage_hi[st]) {
+                    const unsigned off = (head & 0x7fffffffu) + my_off;
+                    if (!(head & 0x80000000u) || (off >= sh->stage_lo[st] && off + 12u <= sh->stage_hi[st])) {
                         const float* f = reinterpret_cast<const float*>(ring + (size_t)st * fc.stage_bytes + off);
                         x = f[0]; y = f[1]; z = f[2];
-                    } else {                            // tile touches the edge of the batch buffer: plain loads
+                    } else {                            // bytes outside the batch buffer were not copied: plain loads
                         const float* f = xyz + 3ll * tp.wat_atom[w0 + i];
                         x = f[0]; y = f[1]; z = f[2];
                     }
                 }
                 __syncwarp();                           // every lane has read its water before the stage is released
                 if (lane == 0) mbar_arrive(&empty[st]);
+                if (++st == fc.stages) { st = 0; parity ^= 1u; }
             } else if (live) {
                 const float* f = xyz + 3ll * tp.wat_atom[w0 + i];
                 x = f[0]; y = f[1]; z = f[2];

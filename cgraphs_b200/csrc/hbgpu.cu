@@ -81,7 +81,8 @@ struct hb_ctx {
     long long opt_fused_lw_cap = 0;   // 0: automatic
     long long opt_fused_cell_cap = 0; // 0: automatic
     long long opt_fused_pair_cap = 0; // 0: automatic
-    long long opt_fused_stages = 3;   // depth of the water-tile ring
+    long long opt_fused_stages = 4;   // depth of the water-tile ring
+    long long opt_fused_prefetch = 8; // tiles prefetched into L2 ahead of the ring
     int fused_grow = 0;
 
     // fused-path plan (valid for the current run)
@@ -96,13 +97,15 @@ struct hb_ctx {
     long long n_frames_total = 0, next_frame = 0;
     BondTable bt{};
     long long table_cap = 0;
-    long long alloc_sig[7] = {0, 0, 0, 0, 0, 0, 0};
+    long long alloc_sig[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int table_grows = 0;
     int* h_status = nullptr;          // pinned, 4 ints per slot: n_keys, overflow, fused_overflow, pad
     unsigned long long* h_hits = nullptr;
 
     // batch scratch
-    int batch_frames = 0;
+    int batch_frames = 0;             // frames the general-path scratch holds
+    int host_batch_frames = 0;        // frames one input buffer of hb_submit_frames holds
+    long long opt_fused_batch_frames = 1 << 15;   // frames per launch of the fused kernel (device-resident input)
     int cell_cap = 0;
     BatchView bv{};
     std::vector<void*> scratch_allocs;
@@ -328,6 +331,8 @@ int hb_set_option(hb_ctx* ctx, const char* name, int64_t value) {
     else if (n == "fused_cell_cap") ctx->opt_fused_cell_cap = std::max<long long>(value, 0);
     else if (n == "fused_pair_cap") ctx->opt_fused_pair_cap = std::max<long long>(value, 0);
     else if (n == "fused_stages") ctx->opt_fused_stages = std::max<long long>(value, 2);
+    else if (n == "fused_batch_frames") ctx->opt_fused_batch_frames = std::max<long long>(value, 1);
+    else if (n == "fused_prefetch") ctx->opt_fused_prefetch = std::max<long long>(value, 0);
     else return fail(ctx, HB_ERR_ARG, "unknown option " + n);
     return HB_OK;
 }
@@ -470,7 +475,7 @@ static bool plan_fused(hb_ctx* ctx, int grow = 0) {
     fc.sel_cap = std::max(ctx->max_sel, 1);
     long long lw = 0;
     if (wa && ctx->max_wat > 0) {
-        lw = ctx->opt_fused_lw_cap ? ctx->opt_fused_lw_cap : std::max<long long>(256, fc.sel_cap);
+        lw = ctx->opt_fused_lw_cap ? ctx->opt_fused_lw_cap : std::max<long long>(256, fc.sel_cap / 2);
         lw <<= grow;
         lw = std::min<long long>(lw, ctx->max_wat);
     }
@@ -482,6 +487,7 @@ static bool plan_fused(hb_ctx* ctx, int grow = 0) {
     fc.regular = (wa && ctx->water_regular && ctx->water_stride <= 8) ? 1 : 0;
     fc.w_stride = ctx->water_stride;
     fc.stages = fc.regular ? (int)std::min<long long>(std::max<long long>(ctx->opt_fused_stages, 2), FUSED_MAX_STAGES) : 0;
+    fc.prefetch = (int)ctx->opt_fused_prefetch;
     fc.stage_bytes = fc.regular ? (unsigned)(((FUSED_TILE - 1) * fc.w_stride * 12 + 12 + 15 + 15 + 16) & ~15) : 0u;
     size_t off = (sizeof(FusedShared) + 15) & ~(size_t)15;
     fc.off_spos = (unsigned)off;
@@ -548,17 +554,18 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     long long cc = 4096;
     while (cc < (long long)(2 * npts)) cc <<= 1;
     cc = std::min<long long>(cc, 1ll << 22);
-    size_t per_frame = (size_t)ctx->max_atoms * 12 * 2                      // two input buffers
-                       + sizeof(FrameState) + (size_t)ctx->max_sel * 32 + (size_t)ctx->max_wat * 16 + npts * 16 +
-                       2 * (size_t)(cc + 1) * 4;
-    long long fb = (long long)(ctx->opt_batch_bytes / std::max<size_t>(per_frame, 1));
-    fb = std::max<long long>(1, std::min<long long>(fb, ctx->opt_max_batch_frames));
-    fb = std::min<long long>(fb, n_frames_total);
-    if (fb >= 32) fb -= fb % 32;
+    // device budget: half for the two input buffers of hb_submit_frames, half for the general-path scratch
+    auto round32 = [](long long f) { return f >= 32 ? f - f % 32 : f; };
+    size_t per_frame_scratch = sizeof(FrameState) + (size_t)ctx->max_sel * 32 + (size_t)ctx->max_wat * 16 + npts * 16 +
+                               2 * (size_t)(cc + 1) * 4;
+    long long fb = (long long)(ctx->opt_batch_bytes / 2 / std::max<size_t>(per_frame_scratch, 1));
+    fb = round32(std::min<long long>(std::max<long long>(1, std::min<long long>(fb, ctx->opt_max_batch_frames)), n_frames_total));
+    long long hb = (long long)(ctx->opt_batch_bytes / 2 / std::max<size_t>((size_t)ctx->max_atoms * 24, 1));
+    hb = round32(std::min<long long>(std::max<long long>(1, std::min<long long>(hb, ctx->opt_max_batch_frames)), n_frames_total));
     plan_fused(ctx);
     tr.mark("plan");
     // allocations of the previous run are reused when nothing that sizes them changed
-    long long sig[7] = {wpr, ctx->max_sel, ctx->max_wat, ctx->max_atoms, fb, cc, ctx->prm.structure_batch};
+    long long sig[8] = {wpr, ctx->max_sel, ctx->max_wat, ctx->max_atoms, fb, cc, ctx->prm.structure_batch, hb};
     bool reuse = ctx->bt.keys && ctx->table_cap >= cap && memcmp(sig, ctx->alloc_sig, sizeof(sig)) == 0;
     if (!reuse) free_run(ctx);
     ctx->tm = hb_timers{};
@@ -591,25 +598,14 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
 
     ctx->cell_cap = (int)cc;
     ctx->batch_frames = (int)fb;
+    ctx->host_batch_frames = (int)hb;
     BatchView& bv = ctx->bv;
     bv = BatchView{};
     bv.max_sel = ctx->max_sel;
     bv.max_wat = ctx->max_wat;
     bv.cell_cap = ctx->cell_cap;
     bv.structure_batch = ctx->prm.structure_batch;
-    auto dalloc = [&](void** p, size_t bytes) -> int {
-        CK(cudaMalloc(p, std::max<size_t>(bytes, 16)));
-        ctx->scratch_allocs.push_back(*p);
-        return HB_OK;
-    };
-    if ((rc = dalloc((void**)&bv.fs, fb * sizeof(FrameState)))) return rc;
-    if ((rc = dalloc((void**)&bv.selpos, fb * (size_t)ctx->max_sel * 16))) return rc;
-    if ((rc = dalloc((void**)&bv.sorted1, fb * (size_t)ctx->max_sel * 16))) return rc;
-    if ((rc = dalloc((void**)&bv.lw, fb * (size_t)ctx->max_wat * 16))) return rc;
-    if ((rc = dalloc((void**)&bv.sorted2, fb * npts * 16))) return rc;
-    if ((rc = dalloc((void**)&bv.cells1, fb * (size_t)(cc + 1) * 4))) return rc;
-    if ((rc = dalloc((void**)&bv.cells2, fb * (size_t)(cc + 1) * 4))) return rc;
-    ctx->in_bytes = (size_t)fb * ctx->max_atoms * 12;
+    ctx->in_bytes = (size_t)hb * ctx->max_atoms * 12;
     memcpy(ctx->alloc_sig, sig, sizeof(sig));
     ctx->running = true;
     ctx->finalized = false;
@@ -636,33 +632,34 @@ static int grow_table(hb_ctx* ctx) {
     return HB_OK;
 }
 
+// the general path's per-batch scratch is allocated the first time that path runs
+static int ensure_scratch(hb_ctx* ctx) {
+    if (!ctx->scratch_allocs.empty()) return HB_OK;
+    BatchView& bv = ctx->bv;
+    size_t fb = (size_t)ctx->batch_frames, cc = (size_t)ctx->cell_cap, npts = (size_t)ctx->max_sel + ctx->max_wat;
+    auto dalloc = [&](void** p, size_t bytes) -> int {
+        CK(cudaMalloc(p, std::max<size_t>(bytes, 16)));
+        ctx->scratch_allocs.push_back(*p);
+        return HB_OK;
+    };
+    int rc;
+    if ((rc = dalloc((void**)&bv.fs, fb * sizeof(FrameState)))) return rc;
+    if ((rc = dalloc((void**)&bv.selpos, fb * (size_t)ctx->max_sel * 16))) return rc;
+    if ((rc = dalloc((void**)&bv.sorted1, fb * (size_t)ctx->max_sel * 16))) return rc;
+    if ((rc = dalloc((void**)&bv.lw, fb * (size_t)ctx->max_wat * 16))) return rc;
+    if ((rc = dalloc((void**)&bv.sorted2, fb * npts * 16))) return rc;
+    if ((rc = dalloc((void**)&bv.cells1, fb * (cc + 1) * 4))) return rc;
+    if ((rc = dalloc((void**)&bv.cells2, fb * (cc + 1) * 4))) return rc;
+    return HB_OK;
+}
+
 // launch the kernel pipeline for one batch resident at d_xyz
-static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, long long atoms_per_frame,
-                     size_t xyz_bytes, bool allow_fused = true) {
-    BatchView bv = ctx->bv;
-    bv.xyz = d_xyz;
-    bv.frame0 = frame0;
-    bv.n_frames = nf;
-    bv.atoms_per_frame = atoms_per_frame;
-    bv.atom_base = bv.structure_batch ? ctx->h_sys_atom_off[frame0] : 0;
+static int run_general(hb_ctx* ctx, BatchView bv) {
     cudaStream_t st = ctx->s_compute;
     const RunParams& rp = ctx->rp;
     const DevTopo& tp = ctx->tp;
+    const int nf = bv.n_frames;
     bool wa = rp.method == HB_METHOD_WATER_AROUND;
-    cudaEvent_t t0 = get_event(ctx), t1 = get_event(ctx);
-    cudaEventRecord(t0, st);
-    if (ctx->fused_active && allow_fused) {
-        FusedCfg fc = ctx->fc;
-        fc.buf_begin = (unsigned long long)(uintptr_t)d_xyz;
-        fc.buf_end = fc.buf_begin + xyz_bytes;
-        { KTimer t(ctx, KC_FUSED); k_frame_fused<<<nf, FUSED_THREADS, fc.smem_bytes, st>>>(bv, tp, rp, ctx->bt, fc); }
-        cudaEventRecord(t1, st);
-        ctx->pending.push_back({t0, t1, -1});
-        CK(cudaGetLastError());
-        ctx->tm.frames += nf;
-        ctx->tm.fused_frames += nf;
-        return HB_OK;
-    }
     { KTimer t(ctx, KC_INIT); k_init_frames<<<(nf + 127) / 128, 128, 0, st>>>(bv); }
     size_t cells_bytes = (size_t)nf * (bv.cell_cap + 1) * 4;
     if (wa) CK(cudaMemsetAsync(bv.cells1, 0, cells_bytes, st));
@@ -685,9 +682,45 @@ static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, 
         dim3 gp((maxp + 127) / 128, nf);
         { KTimer t(ctx, KC_PAIRS); k_pairs<<<gp, 128, 0, st>>>(bv, tp, rp, ctx->bt); }
     }
+    CK(cudaGetLastError());
+    return HB_OK;
+}
+
+// launch the kernels for one batch resident at d_xyz: one fused launch, or the general pipeline over
+// sub-batches of at most `batch_frames` frames (the capacity of its scratch)
+static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, long long atoms_per_frame,
+                     size_t xyz_bytes, bool allow_fused = true) {
+    BatchView bv = ctx->bv;
+    bv.xyz = d_xyz;
+    bv.frame0 = frame0;
+    bv.n_frames = nf;
+    bv.atoms_per_frame = atoms_per_frame;
+    bv.atom_base = bv.structure_batch ? ctx->h_sys_atom_off[frame0] : 0;
+    cudaStream_t st = ctx->s_compute;
+    cudaEvent_t t0 = get_event(ctx), t1 = get_event(ctx);
+    cudaEventRecord(t0, st);
+    if (ctx->fused_active && allow_fused) {
+        FusedCfg fc = ctx->fc;
+        fc.buf_begin = (unsigned long long)(uintptr_t)d_xyz;
+        fc.buf_end = fc.buf_begin + xyz_bytes;
+        { KTimer t(ctx, KC_FUSED); k_frame_fused<<<nf, FUSED_THREADS, fc.smem_bytes, st>>>(bv, ctx->tp, ctx->rp, ctx->bt, fc); }
+        CK(cudaGetLastError());
+        ctx->tm.fused_frames += nf;
+    } else {
+        int rc = ensure_scratch(ctx);
+        if (rc) return rc;
+        bv = ctx->bv;                     // scratch pointers
+        bv.atoms_per_frame = atoms_per_frame;
+        bv.atom_base = bv.structure_batch ? ctx->h_sys_atom_off[frame0] : 0;
+        for (int done = 0; done < nf; done += ctx->batch_frames) {
+            bv.n_frames = std::min(nf - done, ctx->batch_frames);
+            bv.frame0 = frame0 + done;
+            bv.xyz = bv.structure_batch ? d_xyz : d_xyz + (size_t)done * atoms_per_frame * 3;
+            if ((rc = run_general(ctx, bv))) return rc;
+        }
+    }
     cudaEventRecord(t1, st);
     ctx->pending.push_back({t0, t1, -1});
-    CK(cudaGetLastError());
     ctx->tm.frames += nf;
     return HB_OK;
 }
@@ -763,9 +796,10 @@ static long long batch_atoms(hb_ctx* ctx, long long f0, int nf, long long n_atom
     return n_atoms * nf;
 }
 
-static int next_batch_frames(hb_ctx* ctx, long long f0, long long remaining) {
-    int nf = (int)std::min<long long>(remaining, ctx->batch_frames);
-    if (ctx->prm.structure_batch) {   // ragged: stay within the input buffer
+static int next_batch_frames(hb_ctx* ctx, long long f0, long long remaining, bool host) {
+    long long lim = host ? ctx->host_batch_frames : (ctx->fused_active ? ctx->opt_fused_batch_frames : ctx->batch_frames);
+    int nf = (int)std::min<long long>(remaining, std::max<long long>(lim, 1));
+    if (host && ctx->prm.structure_batch) {   // ragged: stay within the input buffer
         long long budget = (long long)(ctx->in_bytes / 12);
         while (nf > 1 && ctx->h_sys_atom_off[f0 + nf] - ctx->h_sys_atom_off[f0] > budget) --nf;
     }
@@ -789,7 +823,7 @@ int hb_submit_frames(hb_ctx* ctx, const float* xyz, int64_t n_atoms, int64_t n_f
     long long done = 0;
     while (done < n_frames) {
         long long f0 = ctx->next_frame;
-        int nf = next_batch_frames(ctx, f0, n_frames - done);
+        int nf = next_batch_frames(ctx, f0, n_frames - done, true);
         long long atoms = batch_atoms(ctx, f0, nf, n_atoms);
         size_t bytes = (size_t)atoms * 12;
         int k = (int)(ctx->batch_counter & 1);
@@ -824,7 +858,7 @@ int hb_submit_frames_device(hb_ctx* ctx, const float* d_xyz, int64_t n_atoms, in
     long long done = 0;
     while (done < n_frames) {
         long long f0 = ctx->next_frame;
-        int nf = next_batch_frames(ctx, f0, n_frames - done);
+        int nf = next_batch_frames(ctx, f0, n_frames - done, false);
         long long atoms = batch_atoms(ctx, f0, nf, n_atoms);
         int k = (int)(ctx->batch_counter & 1);
         if ((rc = acquire_slot(ctx, k))) return rc;
