@@ -31,6 +31,10 @@ struct DevTopo {
     // packed copies built by hb_set_topology (one 16-byte load instead of four 4-byte loads)
     const int4* sel_pack;    // {sel_don, sel_acc, sel_wat, sel_bb}
     const int4* ent_pack;    // {ent_resid, ent_residue, ent_h_off, hydrogen count}
+    // inline hydrogen lists: four signed bytes, hydrogen atom = heavy atom + byte (-128 = none)
+    const int2* sel_h;       // {donor entry's hydrogens, water entry's hydrogens} of a selection point
+    const int* wat_h;        // hydrogens of a water point's entry
+    int h_wide;              // some entry has more than 4 hydrogens or one further than 127 atoms away: use the CSR
 };
 
 struct FrameGrid {      // geometry of one cell grid of one frame
@@ -80,6 +84,7 @@ struct RunParams {
     int check_angle;
     int excl_bb;
     int method;
+    int self_pairs;          // 1: distance-0 entry pairs of one atom can pass (only with cut_angle >= 180 deg)
 };
 
 struct BondTable {
@@ -91,6 +96,7 @@ struct BondTable {
     int* overflow;
     int* fused_overflow;        // a frame exceeded the shared-memory capacities of the fused kernel
     unsigned long long* n_hits;
+    unsigned long long* phase_cycles;   // optional (HBGPU_TRACE): SM cycles thread 0 of each fused CTA spent per phase
 };
 
 #define EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
@@ -231,24 +237,38 @@ struct PointInfo {
     int don, acc, wat;   // global entry indices or -1
     int bb;
     float x, y, z;
+    int atom;            // atom index inside the frame
+    int hd, hw;          // packed hydrogen offsets of the donor / water entry (complete unless tp.h_wide)
 };
+#define H_NONE4 ((int)0x80808080)
 
+// everything the pair expansion needs to know about a point: independent loads, one round trip
 __device__ __forceinline__ void load_info(const DevTopo& tp, const RunParams& rp, int sys, float4 p, PointInfo& o) {
     int id = __float_as_int(p.w);
     o.x = p.x; o.y = p.y; o.z = p.z;
     if (id & WATER_TAG) {
+        const int w = tp.sys_wat_off[sys] + (id & POINT_ID_MASK);
         o.don = -1; o.acc = -1; o.bb = 0;
-        o.wat = tp.wat_ent[tp.sys_wat_off[sys] + (id & POINT_ID_MASK)];
+        o.wat = tp.wat_ent[w];
+        o.atom = tp.wat_atom[w];
+        o.hd = H_NONE4;
+        o.hw = tp.wat_h[w];
     } else {
-        int4 k = tp.sel_pack[tp.sys_sel_off[sys] + (id & POINT_ID_MASK)];
+        const int s = tp.sys_sel_off[sys] + (id & POINT_ID_MASK);
+        const int4 k = tp.sel_pack[s];
+        const bool wa = rp.method == HB_METHOD_WATER_AROUND;
         o.don = k.x;
         o.acc = k.y;
-        o.wat = rp.method == HB_METHOD_WATER_AROUND ? k.z : -1;
+        o.wat = wa ? k.z : -1;
         o.bb = k.w;
+        o.atom = tp.sel_atom[s];
+        const int2 h = tp.sel_h[s];
+        o.hd = h.x;
+        o.hw = h.y;
     }
 }
 
-// any hydrogen of entry `e` (owned by point H) with ANG(other, h, owner) satisfied
+// any hydrogen of entry `e` (owned by point `owner`) with ANG(other, h, owner) satisfied: CSR walk
 __device__ __forceinline__ bool any_h(const DevTopo& tp, const float* xyz, int e, const PointInfo& owner,
                                       const PointInfo& other, float cthr) {
     int4 ep = tp.ent_pack[e];
@@ -259,45 +279,128 @@ __device__ __forceinline__ bool any_h(const DevTopo& tp, const float* xyz, int e
     }
     return false;
 }
-
-__device__ __forceinline__ void emit(const DevTopo& tp, const RunParams& rp, const BondTable& bt, long long frame,
-                                     int e0, int e1, int& nhit) {
-    int x = min(e0, e1), y = max(e0, e1);
-    int4 px = tp.ent_pack[x], py = tp.ent_pack[y];
-    bool chk = px.x < py.x;                            // hbond.py:120-122
-    int first = chk ? x : y, second = chk ? y : x;
-    if (!rp.check_angle && px.y == py.y) return;       // hbond.py:125-127
-    unsigned long long key = ((unsigned long long)(unsigned)tp.ent_group[first] << 32) |
-                             (unsigned long long)(unsigned)tp.ent_group[second];
-    ++nhit;
-    record_bond(bt, key, frame);
+// same over an inline list of up to four hydrogens of the atom `atom` at (ox, oy, oz); (tx, ty, tz) is the
+// partner. The coordinate loads are issued together. Not inlined: it is called from up to four places per
+// pair and would otherwise multiply the register footprint of the calling kernels.
+__device__ __noinline__ bool any_h4(const float* xyz, int hl, int atom, float ox, float oy, float oz, float tx, float ty,
+                                    float tz, float cthr) {
+    float h[4][3];
+    int d[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        d[k] = (int)(signed char)((unsigned)hl >> (8 * k));
+        if (d[k] != -128) {
+            const float* p = xyz + 3ll * (atom + d[k]);
+            h[k][0] = p[0]; h[k][1] = p[1]; h[k][2] = p[2];
+        }
+    }
+    bool ok = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (d[k] != -128 && !ok) ok = ang_ok(tx, ty, tz, h[k][0], h[k][1], h[k][2], ox, oy, oz, cthr);
+    return ok;
 }
 
-// All entry pairs generated by the point pair (P, Q), P != Q as points
-__device__ void process_pair(const DevTopo& tp, const RunParams& rp, const BondTable& bt, const float* xyz,
-                             long long frame, const PointInfo& P, const PointInfo& Q, int& nhit) {
+__device__ __noinline__ void emit_bond(const int4* ent_pack, const int* ent_group, int check_angle, BondTable bt,
+                                       long long frame, int e0, int e1, int* nhit) {
+    int x = min(e0, e1), y = max(e0, e1);
+    int4 px = ent_pack[x], py = ent_pack[y];
+    int gx = ent_group[x], gy = ent_group[y];
+    bool chk = px.x < py.x;                            // hbond.py:120-122
+    if (!check_angle && px.y == py.y) return;          // hbond.py:125-127
+    unsigned long long key = ((unsigned long long)(unsigned)(chk ? gx : gy) << 32) | (unsigned long long)(unsigned)(chk ? gy : gx);
+    ++*nhit;
+    record_bond(bt, key, frame);
+}
+__device__ __forceinline__ void emit(const DevTopo& tp, const RunParams& rp, const BondTable& bt, long long frame,
+                                     int e0, int e1, int& nhit) {
+    emit_bond(tp.ent_pack, tp.ent_group, rp.check_angle, bt, frame, e0, e1, &nhit);
+}
+// All entry pairs generated by the point pair (P, Q), P != Q as points.
+// "Some hydrogen of this entry passes the angle test" is evaluated once per entry that takes part in a pair.
+__device__ __forceinline__ void process_pair(const DevTopo& tp, const RunParams& rp, const BondTable& bt, const float* xyz,
+                                             long long frame, const PointInfo& P, const PointInfo& Q, int& nhit) {
     const bool ang = rp.check_angle != 0;
     const float ct = rp.cos_threshold;
-    // lazily evaluated "some hydrogen of this entry passes" flags; -1 = not evaluated
-    int pd = -1, qd = -1, pw = -1, qw = -1;
-    auto PD = [&]() { if (pd < 0) pd = (!ang) || any_h(tp, xyz, P.don, P, Q, ct); return pd; };
-    auto QD = [&]() { if (qd < 0) qd = (!ang) || any_h(tp, xyz, Q.don, Q, P, ct); return qd; };
-    auto PW = [&]() { if (pw < 0) pw = (!ang) || any_h(tp, xyz, P.wat, P, Q, ct); return pw; };
-    auto QW = [&]() { if (qw < 0) qw = (!ang) || any_h(tp, xyz, Q.wat, Q, P, ct); return qw; };
     const bool bb_skip = rp.excl_bb && P.bb && Q.bb;
-    if (!bb_skip) {
-        if (P.acc >= 0 && Q.don >= 0 && QD()) emit(tp, rp, bt, frame, P.acc, Q.don, nhit);
-        if (Q.acc >= 0 && P.don >= 0 && PD()) emit(tp, rp, bt, frame, Q.acc, P.don, nhit);
+    const bool need_pd = P.don >= 0 && ((!bb_skip && Q.acc >= 0) || Q.wat >= 0);
+    const bool need_qd = Q.don >= 0 && ((!bb_skip && P.acc >= 0) || P.wat >= 0);
+    const bool need_pw = P.wat >= 0;
+    const bool need_qw = Q.wat >= 0;
+    bool pd = need_pd, qd = need_qd, pw = need_pw, qw = need_qw;
+    if (ang) {
+        if (tp.h_wide) {
+            if (need_pd) pd = any_h(tp, xyz, P.don, P, Q, ct);
+            if (need_qd) qd = any_h(tp, xyz, Q.don, Q, P, ct);
+            if (need_pw) pw = any_h(tp, xyz, P.wat, P, Q, ct);
+            if (need_qw) qw = any_h(tp, xyz, Q.wat, Q, P, ct);
+        } else {
+            if (need_pd) pd = any_h4(xyz, P.hd, P.atom, P.x, P.y, P.z, Q.x, Q.y, Q.z, ct);
+            if (need_qd) qd = any_h4(xyz, Q.hd, Q.atom, Q.x, Q.y, Q.z, P.x, P.y, P.z, ct);
+            if (need_pw) pw = any_h4(xyz, P.hw, P.atom, P.x, P.y, P.z, Q.x, Q.y, Q.z, ct);
+            if (need_qw) qw = any_h4(xyz, Q.hw, Q.atom, Q.x, Q.y, Q.z, P.x, P.y, P.z, ct);
+        }
     }
-    if (P.wat >= 0 && Q.wat >= 0 && (PW() || QW())) emit(tp, rp, bt, frame, P.wat, Q.wat, nhit);
+    if (!bb_skip) {
+        if (P.acc >= 0 && Q.don >= 0 && qd) emit(tp, rp, bt, frame, P.acc, Q.don, nhit);
+        if (Q.acc >= 0 && P.don >= 0 && pd) emit(tp, rp, bt, frame, Q.acc, P.don, nhit);
+    }
+    if (P.wat >= 0 && Q.wat >= 0 && (pw || qw)) emit(tp, rp, bt, frame, P.wat, Q.wat, nhit);
     if (Q.wat >= 0) {
-        if (P.don >= 0 && (PD() || QW())) emit(tp, rp, bt, frame, P.don, Q.wat, nhit);
-        if (P.acc >= 0 && QW()) emit(tp, rp, bt, frame, P.acc, Q.wat, nhit);
+        if (P.don >= 0 && (pd || qw)) emit(tp, rp, bt, frame, P.don, Q.wat, nhit);
+        if (P.acc >= 0 && qw) emit(tp, rp, bt, frame, P.acc, Q.wat, nhit);
     }
     if (P.wat >= 0) {
-        if (Q.don >= 0 && (QD() || PW())) emit(tp, rp, bt, frame, Q.don, P.wat, nhit);
-        if (Q.acc >= 0 && PW()) emit(tp, rp, bt, frame, Q.acc, P.wat, nhit);
+        if (Q.don >= 0 && (qd || pw)) emit(tp, rp, bt, frame, Q.don, P.wat, nhit);
+        if (Q.acc >= 0 && pw) emit(tp, rp, bt, frame, Q.acc, P.wat, nhit);
     }
+}
+
+// The same expansion in three separable steps (used by the fused kernel, which runs the angle tests as
+// one dense task list between steps one and three).
+//   rules bit r: entry pair r exists.       r0 (P.acc,Q.don)  r1 (Q.acc,P.don)  r2 (P.wat,Q.wat)  r3 (P.don,Q.wat)
+//                                            r4 (P.acc,Q.wat)  r5 (Q.don,P.wat)  r6 (Q.acc,P.wat)
+//   flags bit f: some hydrogen of entry f passes the angle test.   f0 P.don  f1 Q.don  f2 P.wat  f3 Q.wat
+__device__ __forceinline__ unsigned pair_rules(const PointInfo& P, const PointInfo& Q, bool excl_bb) {
+    const bool bb_skip = excl_bb && P.bb && Q.bb;
+    unsigned r = 0;
+    if (!bb_skip && P.acc >= 0 && Q.don >= 0) r |= 1u;
+    if (!bb_skip && Q.acc >= 0 && P.don >= 0) r |= 2u;
+    if (P.wat >= 0 && Q.wat >= 0) r |= 4u;
+    if (Q.wat >= 0 && P.don >= 0) r |= 8u;
+    if (Q.wat >= 0 && P.acc >= 0) r |= 16u;
+    if (P.wat >= 0 && Q.don >= 0) r |= 32u;
+    if (P.wat >= 0 && Q.acc >= 0) r |= 64u;
+    return r;
+}
+__device__ __forceinline__ unsigned rules_need(unsigned r) {      // flags that decide some existing rule
+    unsigned n = 0;
+    if (r & (2u | 8u)) n |= 1u;
+    if (r & (1u | 32u)) n |= 2u;
+    if (r & (4u | 32u | 64u)) n |= 4u;
+    if (r & (4u | 8u | 16u)) n |= 8u;
+    return n;
+}
+__device__ __forceinline__ unsigned rules_pass(unsigned f) {      // rules satisfied by the flags
+    const bool pd = f & 1u, qd = f & 2u, pw = f & 4u, qw = f & 8u;
+    return (qd ? 1u : 0u) | (pd ? 2u : 0u) | ((pw || qw) ? 4u : 0u) | ((pd || qw) ? 8u : 0u) | (qw ? 16u : 0u) |
+           ((qd || pw) ? 32u : 0u) | (pw ? 64u : 0u);
+}
+__device__ __forceinline__ void rule_entries(const PointInfo& P, const PointInfo& Q, int r, int& e0, int& e1) {
+    switch (r) {
+        case 0: e0 = P.acc; e1 = Q.don; break;
+        case 1: e0 = Q.acc; e1 = P.don; break;
+        case 2: e0 = P.wat; e1 = Q.wat; break;
+        case 3: e0 = P.don; e1 = Q.wat; break;
+        case 4: e0 = P.acc; e1 = Q.wat; break;
+        case 5: e0 = Q.don; e1 = P.wat; break;
+        default: e0 = Q.acc; e1 = P.wat; break;
+    }
+}
+__device__ __forceinline__ int h_count(int hl) {                  // bytes of the packed list that are not -128
+    const unsigned x = (unsigned)hl ^ 0x80808080u;                // zero byte <=> none
+    const unsigned nz = (x | ((x & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;   // high bit set <=> byte non-zero
+    return __popc(nz);
 }
 
 // Entry pairs of a point with itself (distance 0): acceptor-donor and selection-water entries of one atom
@@ -352,7 +455,7 @@ __device__ __forceinline__ void search_point(const DevTopo& tp, const RunParams&
     float4 p4 = pts[i];
     PointInfo P;
     load_info(tp, rp, sys, p4, P);
-    process_self(tp, rp, bt, xyz, frame, P, nhit);
+    if (rp.self_pairs) process_self(tp, rp, bt, xyz, frame, P, nhit);
     int cx = cell_coord(P.x, g.ox, g.inv, g.nx);
     int cy = cell_coord(P.y, g.oy, g.inv, g.ny);
     int cz = cell_coord(P.z, g.oz, g.inv, g.nz);

@@ -37,7 +37,8 @@ struct FusedCfg {
     int sel_cap;              // selection points per frame that fit
     int lw_cap;               // local waters per frame that fit
     int cell_cap;             // cells per grid (packed 16-bit counters)
-    int pair_cap;             // point pairs per block of 256 points
+    int pair_cap;             // point pairs per frame
+    int task_cap;             // hydrogens to test per chunk of 256 pairs
     int regular;              // 1: water point i is atom w_first + i * w_stride in every system -> TMA tiles
     int w_stride;             // atoms between consecutive water oxygens
     int stages;               // ring depth
@@ -53,7 +54,8 @@ struct FusedShared {          // small fixed part at the start of dynamic shared
     float lo[3], hi[3];
     float red[FUSED_CWARPS][6];
     int n_lw;
-    int n_pairs[2];
+    int n_pairs;
+    int n_tasks;
     int overflow;
     int warp_sum[FUSED_CWARPS];
     unsigned stage_head[FUSED_MAX_STAGES];   // byte offset of the tile's first water inside the stage
@@ -184,7 +186,7 @@ __device__ __forceinline__ void collect_pairs(const RunParams& rp, const FrameGr
     }
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS) k_frame_fused(BatchView bv, DevTopo tp, RunParams rp, BondTable bt, FusedCfg fc) {
+__global__ void __launch_bounds__(FUSED_THREADS, 4) k_frame_fused(BatchView bv, DevTopo tp, RunParams rp, BondTable bt, FusedCfg fc) {
     extern __shared__ __align__(16) unsigned char smem[];
     FusedShared* sh = reinterpret_cast<FusedShared*>(smem);
     float4* spos = reinterpret_cast<float4*>(smem + fc.off_spos);          // selection points, gather order
@@ -192,6 +194,8 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_frame_fused(BatchView bv, Dev
     unsigned char* ring = smem + fc.off_union + (size_t)fc.sel_cap * 16;   // phase B: tile stages
     float4* psorted = reinterpret_cast<float4*>(smem + fc.off_union);      // phase C: aliases sorted1 + ring
     unsigned* pairs = reinterpret_cast<unsigned*>(smem + fc.off_union + ((size_t)fc.sel_cap + fc.lw_cap) * 16);
+    uint2* tasks = reinterpret_cast<uint2*>(pairs + fc.pair_cap);          // phase C: (pair | flag, hydrogen atom)
+    unsigned* pflags = reinterpret_cast<unsigned*>(tasks + fc.task_cap);   // phase C: angle flags of the chunk's pairs
     float4* lw = reinterpret_cast<float4*>(smem + fc.off_lw);
     unsigned short* cells = reinterpret_cast<unsigned short*>(smem + fc.off_cells);
     unsigned* near = reinterpret_cast<unsigned*>(smem + fc.off_near);
@@ -212,12 +216,21 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_frame_fused(BatchView bv, Dev
     const int ntiles = (nwp + FUSED_TILE - 1) / FUSED_TILE;
     const int stride12 = fc.w_stride * 12;
 
+    long long tick = bt.phase_cycles ? clock64() : 0;
+    auto phase_done = [&](int k) {     // trace only: cycles thread 0 spent in phase k
+        if (bt.phase_cycles && tid == 0) {
+            const long long now = clock64();
+            atomicAdd(&bt.phase_cycles[k], (unsigned long long)(now - tick));
+            tick = now;
+        }
+    };
     if (nsel > fc.sel_cap) {           // uniform over the CTA: this frame does not fit
         if (tid == 0) atomicExch(bt.fused_overflow, 1);
         return;
     }
     if (tid == 0) {
         sh->n_lw = 0;
+        sh->n_pairs = 0;
         sh->overflow = 0;
         for (int k = 0; k < fc.stages; ++k) { mbar_init(&full[k], 1); mbar_init(&empty[k], FUSED_CWARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -312,6 +325,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_frame_fused(BatchView bv, Dev
     }
     consumer_sync();
 
+    phase_done(0);
     // ---- phase B: local waters ---------------------------------------------------------------------
     if (scan_waters) {
         const FrameGrid g1 = sh->g1;
@@ -330,6 +344,7 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_frame_fused(BatchView bv, Dev
                     }
         }
         consumer_sync();
+        phase_done(1);
 
         const float a = rp.around_f;
         const float lox = sh->lo[0] - a, loy = sh->lo[1] - a, loz = sh->lo[2] - a;
@@ -401,8 +416,10 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_frame_fused(BatchView bv, Dev
             }
         }
         if (ncand) test_candidates(0, ncand);
+        phase_done(2);
     }
     consumer_sync();
+    phase_done(3);
     if (sh->overflow || sh->n_lw > fc.lw_cap) {
         if (tid == 0) atomicExch(bt.fused_overflow, 1);
         return;
@@ -414,13 +431,13 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_frame_fused(BatchView bv, Dev
     block_cell_sort(sh->g2, cells, psorted, np, [&](int i) { return i < nsel ? spos[i] : lw[i - nsel]; }, sh);
     int nhit = 0;
     const FrameGrid g2 = sh->g2;
-    if (tid == 0) sh->n_pairs[0] = sh->n_pairs[1] = 0;
-    consumer_sync();
-    for (int base = 0, it = 0; base < np; base += FUSED_CONSUMERS, ++it) {
-        int* cnt = &sh->n_pairs[it & 1];
-        const int i = base + tid;
-        if (i < np) {
-            collect_pairs(rp, g2, cells, psorted, i, pairs, fc.pair_cap, cnt);
+    phase_done(4);
+    const bool ang = rp.check_angle != 0;
+    const float ct = rp.cos_threshold;
+    // C1: every point walks its half shell and appends the point pairs within `distance` to one list
+    for (int i = tid; i < np; i += FUSED_CONSUMERS) {
+        collect_pairs(rp, g2, cells, psorted, i, pairs, fc.pair_cap, &sh->n_pairs);
+        if (rp.self_pairs) {
             const float4 p4 = psorted[i];
             if (__float_as_int(p4.w) & SELF_TAG) {
                 PointInfo P;
@@ -428,23 +445,96 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_frame_fused(BatchView bv, Dev
                 process_self(tp, rp, bt, xyz, frame, P, nhit);
             }
         }
+    }
+    phase_done(5);
+    consumer_sync();
+    const int npairs = sh->n_pairs;
+    if (npairs > fc.pair_cap) {                         // uniform
+        if (tid == 0) atomicExch(bt.fused_overflow, 1);
+        return;
+    }
+    phase_done(6);
+    // C2: pairs in chunks of 256, three dense steps per chunk
+    for (int base = 0; base < npairs; base += FUSED_CONSUMERS) {
+        const int k = base + tid;
+        const bool have = k < npairs;
+        PointInfo P, Q;
+        unsigned rules = 0;
+        if (tid == 0) sh->n_tasks = 0;
+        pflags[tid] = 0u;
         consumer_sync();
-        const int npairs = *cnt;
-        if (tid == 0) sh->n_pairs[(it & 1) ^ 1] = 0;    // nobody uses the other counter between these two barriers
-        if (npairs > fc.pair_cap) {                     // uniform
-            if (tid == 0) atomicExch(bt.fused_overflow, 1);
-            break;
-        }
-        for (int k = tid; k < npairs; k += FUSED_CONSUMERS) {
+        // (a) topology of the two points, entry pairs that exist, one task per hydrogen to test
+        if (have) {
             const unsigned pq = pairs[k];
-            PointInfo P, Q;
             load_info(tp, rp, sys, psorted[pq & 0xffffu], P);
             load_info(tp, rp, sys, psorted[pq >> 16], Q);
-            process_pair(tp, rp, bt, xyz, frame, P, Q, nhit);
+            rules = pair_rules(P, Q, rp.excl_bb != 0);
+            if (ang) {
+                const unsigned need = rules_need(rules);
+                if (tp.h_wide) {                        // hydrogen lists too long for the inline tables: CSR walk here
+                    unsigned f = 0;
+                    if ((need & 1u) && any_h(tp, xyz, P.don, P, Q, ct)) f |= 1u;
+                    if ((need & 2u) && any_h(tp, xyz, Q.don, Q, P, ct)) f |= 2u;
+                    if ((need & 4u) && any_h(tp, xyz, P.wat, P, Q, ct)) f |= 4u;
+                    if ((need & 8u) && any_h(tp, xyz, Q.wat, Q, P, ct)) f |= 8u;
+                    pflags[tid] = f;
+                } else {
+                    const int lists[4] = {P.hd, Q.hd, P.hw, Q.hw};
+                    const int atoms[4] = {P.atom, Q.atom, P.atom, Q.atom};
+                    int nt = 0;
+#pragma unroll
+                    for (int f = 0; f < 4; ++f)
+                        if (need & (1u << f)) nt += h_count(lists[f]);
+                    int slot = nt ? atomicAdd(&sh->n_tasks, nt) : 0;
+                    if (slot + nt <= fc.task_cap) {
+#pragma unroll
+                        for (int f = 0; f < 4; ++f)
+                            if (need & (1u << f)) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const int d = (int)(signed char)((unsigned)lists[f] >> (8 * j));
+                                    if (d != -128) tasks[slot++] = make_uint2((unsigned)tid | ((unsigned)f << 16), (unsigned)(atoms[f] + d));
+                                }
+                            }
+                    }
+                }
+            } else {
+                pflags[tid] = 0xfu;
+            }
         }
-        consumer_sync();                                // the pair list may be overwritten by the next block
+        consumer_sync();
+        // (b) one thread per hydrogen: ANG(other, h, owner)
+        const int ntasks = sh->n_tasks;
+        if (ntasks > fc.task_cap) {                     // uniform
+            if (tid == 0) atomicExch(bt.fused_overflow, 1);
+            return;
+        }
+        for (int t = tid; t < ntasks; t += FUSED_CONSUMERS) {
+            const uint2 tk = tasks[t];
+            const unsigned kk = tk.x & 0xffffu, f = tk.x >> 16;
+            const unsigned pq = pairs[base + kk];
+            const float4 a4 = psorted[pq & 0xffffu], b4 = psorted[pq >> 16];
+            const float4 own = (f & 1u) ? b4 : a4, oth = (f & 1u) ? a4 : b4;
+            const float* h = xyz + 3ll * (long long)tk.y;
+            if (ang_ok(oth.x, oth.y, oth.z, h[0], h[1], h[2], own.x, own.y, own.z, ct)) atomicOr(&pflags[kk], 1u << f);
+        }
+        consumer_sync();
+        // (c) entry pairs whose hydrogens passed
+        if (have) {
+            unsigned m = rules & rules_pass(pflags[tid]);
+            while (m) {
+                const int r = __ffs(m) - 1;
+                m &= m - 1;
+                int e0, e1;
+                rule_entries(P, Q, r, e0, e1);
+                emit(tp, rp, bt, frame, e0, e1, nhit);
+            }
+        }
+        consumer_sync();                                // pflags / tasks are rewritten by the next chunk
     }
+    phase_done(7);
     flush_hits(bt, nhit);
+    phase_done(8);
 }
 
 }  // namespace

@@ -81,7 +81,7 @@ struct hb_ctx {
     long long opt_fused_lw_cap = 0;   // 0: automatic
     long long opt_fused_cell_cap = 0; // 0: automatic
     long long opt_fused_pair_cap = 0; // 0: automatic
-    long long opt_fused_stages = 4;   // depth of the water-tile ring
+    long long opt_fused_stages = 2;   // depth of the water-tile ring
     long long opt_fused_prefetch = 8; // tiles prefetched into L2 ahead of the ring
     int fused_grow = 0;
 
@@ -424,6 +424,27 @@ int hb_set_topology(hb_ctx* ctx, const hb_topology* t) {
             ep[e] = make_int4(t->ent_resid[e], t->ent_residue[e], t->ent_h_off[e], t->ent_h_off[e + 1] - t->ent_h_off[e]);
         if ((rc = upload(ctx, sp.data(), sp.size(), &d.sel_pack, ctx->topo_allocs))) return rc;
         if ((rc = upload(ctx, ep.data(), ep.size(), &d.ent_pack, ctx->topo_allocs))) return rc;
+        // inline hydrogen lists: offsets of the first four hydrogens from the heavy atom, one signed byte each
+        d.h_wide = 0;
+        auto hlist = [&](int e, int heavy_atom) {
+            unsigned v = 0x80808080u;
+            if (e >= 0) {
+                int s0 = t->ent_h_off[e], n = t->ent_h_off[e + 1] - s0;
+                if (n > 4) d.h_wide = 1;
+                for (int k = 0; k < std::min(n, 4); ++k) {
+                    int delta = t->ent_h_atom[s0 + k] - heavy_atom;
+                    if (delta < -127 || delta > 127) { d.h_wide = 1; delta = 0; }
+                    v = (v & ~(0xffu << (8 * k))) | ((unsigned)(delta & 0xff) << (8 * k));
+                }
+            }
+            return (int)v;
+        };
+        std::vector<int2> sh((size_t)std::max(t->n_sel, 1));
+        std::vector<int> wh((size_t)std::max(t->n_wat, 1));
+        for (int i = 0; i < t->n_sel; ++i) sh[i] = make_int2(hlist(t->sel_don[i], t->sel_atom[i]), hlist(t->sel_wat[i], t->sel_atom[i]));
+        for (int i = 0; i < t->n_wat; ++i) wh[i] = hlist(t->wat_ent[i], t->wat_atom[i]);
+        if ((rc = upload(ctx, sh.data(), sh.size(), &d.sel_h, ctx->topo_allocs))) return rc;
+        if ((rc = upload(ctx, wh.data(), wh.size(), &d.wat_h, ctx->topo_allocs))) return rc;
     }
     ctx->d_ent_group = (int*)d.ent_group;
     ctx->n_ent = t->n_ent;
@@ -461,6 +482,9 @@ int hb_set_params(hb_ctx* ctx, const hb_params* p) {
     r.check_angle = p->check_angle;
     r.excl_bb = p->exclude_backbone_backbone;
     r.method = p->method;
+    // a point paired with itself: with the angle criterion ANG(P, h, P) is 180 degrees (cos_arg = -1) and fails
+    // unless the threshold admits -1; without it both entries share one residue and are skipped (hbond.py:125-127)
+    r.self_pairs = (p->check_angle && !(p->cos_threshold > -1.0f)) ? 1 : 0;
     ctx->have_params = true;
     return HB_OK;
 }
@@ -494,7 +518,10 @@ static bool plan_fused(hb_ctx* ctx, int grow = 0) {
     off += (size_t)fc.sel_cap * 16;
     fc.off_union = (unsigned)off;
     size_t un_b = (size_t)fc.sel_cap * 16 + (size_t)fc.stages * fc.stage_bytes;
-    size_t un_c = ((size_t)fc.sel_cap + fc.lw_cap) * 16 + (size_t)fc.pair_cap * 4;
+    fc.off_cand = (unsigned)(off + un_b);                             // candidate buffers live only in phase B
+    un_b += wa ? (size_t)FUSED_CWARPS * FUSED_CAND * 16 : 0;
+    fc.task_cap = 1536 << grow;
+    size_t un_c = ((size_t)fc.sel_cap + fc.lw_cap) * 16 + (size_t)fc.pair_cap * 4 + (size_t)fc.task_cap * 8 + FUSED_CONSUMERS * 4;
     off += (std::max(un_b, un_c) + 15) & ~(size_t)15;
     fc.off_lw = (unsigned)off;
     off += (size_t)fc.lw_cap * 16;
@@ -502,8 +529,6 @@ static bool plan_fused(hb_ctx* ctx, int grow = 0) {
     off += (((size_t)fc.cell_cap + 2) * 2 + 15) & ~(size_t)15;
     fc.off_near = (unsigned)off;
     off += (((size_t)fc.cell_cap + 31) / 32 * 4 + 15) & ~(size_t)15;
-    fc.off_cand = (unsigned)off;
-    off += wa ? (size_t)FUSED_CWARPS * FUSED_CAND * 16 : 0;
     fc.off_bar = (unsigned)off;
     off += (size_t)2 * FUSED_MAX_STAGES * 8;
     fc.smem_bytes = (unsigned)off;
@@ -581,7 +606,7 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
         size_t tc = (size_t)ctx->table_cap;
         k_fill_u64<<<1184, 256, 0, ctx->s_compute>>>(ctx->bt.keys, tc, EMPTY_KEY);
         CK(cudaMemsetAsync(ctx->bt.bits, 0, tc * wpr * sizeof(unsigned), ctx->s_compute));
-        CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 4 * sizeof(unsigned long long), ctx->s_compute));
+        CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 16 * sizeof(unsigned long long), ctx->s_compute));
         if (ctx->trace) { cudaStreamSynchronize(ctx->s_compute); tr.mark("clear(reuse)"); }
         ctx->running = true;
         ctx->finalized = false;
@@ -590,11 +615,12 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     // bond table
     if ((rc = alloc_table(ctx, ctx->bt, cap, wpr))) return rc;
     ctx->table_cap = cap;
-    CK(cudaMalloc((void**)&ctx->bt.n_keys, 4 * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 4 * sizeof(unsigned long long), ctx->s_compute));
+    CK(cudaMalloc((void**)&ctx->bt.n_keys, 16 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 16 * sizeof(unsigned long long), ctx->s_compute));
     ctx->bt.overflow = ctx->bt.n_keys + 1;
     ctx->bt.fused_overflow = ctx->bt.n_keys + 2;
     ctx->bt.n_hits = (unsigned long long*)(ctx->bt.n_keys + 4);
+    ctx->bt.phase_cycles = ctx->trace ? (unsigned long long*)(ctx->bt.n_keys + 8) : nullptr;
 
     ctx->cell_cap = (int)cc;
     ctx->batch_frames = (int)fb;
@@ -621,6 +647,7 @@ static int grow_table(hb_ctx* ctx) {
     nt.overflow = ctx->bt.overflow;
     nt.fused_overflow = ctx->bt.fused_overflow;
     nt.n_hits = ctx->bt.n_hits;
+    nt.phase_cycles = ctx->bt.phase_cycles;
     k_rehash<<<(unsigned)ctx->table_cap, 128, 0, ctx->s_compute>>>(ctx->bt, nt);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->s_compute));
@@ -754,9 +781,10 @@ static int full_verify(hb_ctx* ctx) {
             CK(cudaMemsetAsync(ctx->bt.overflow, 0, 2 * sizeof(int), ctx->s_compute));
             for (auto& sl : ctx->slots)
                 if (sl.busy) {
-                    long long frames_before = ctx->tm.frames;
+                    long long frames_before = ctx->tm.frames, fused_before = ctx->tm.fused_frames;
                     if ((rc = run_batch(ctx, sl.d_xyz, sl.f0, sl.nf, sl.apf, sl.bytes))) return rc;
-                    ctx->tm.frames = frames_before;
+                    ctx->tm.frames = frames_before;                 // a re-run is not new work
+                    ctx->tm.fused_frames = ctx->fused_active ? fused_before : fused_before - sl.nf;
                 }
         }
     }
@@ -963,6 +991,15 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
     }
     ctx->d_out_keys = k0;
     tr.mark("sort+gather");
+    if (ctx->trace && ctx->bt.phase_cycles && ctx->tm.fused_frames) {
+        unsigned long long pc[10];
+        if (cudaMemcpy(pc, ctx->bt.phase_cycles, sizeof(pc), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            double f = (double)ctx->tm.fused_frames;
+            fprintf(stderr, "[hbgpu] fused phases, cycles per frame (thread 0): A gather+grid %.0f | g1 sort+near %.0f | B stream %.0f | "
+                            "B tail sync %.0f | C sort %.0f | C collect %.0f | C sync %.0f | C expand %.0f | flush %.0f\n",
+                    pc[0] / f, pc[1] / f, pc[2] / f, pc[3] / f, pc[4] / f, pc[5] / f, pc[6] / f, pc[7] / f, pc[8] / f);
+        }
+    }
     ctx->n_bonds = n;
     ctx->finalized = true;
     ctx->running = false;

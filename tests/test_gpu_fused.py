@@ -45,6 +45,19 @@ def test_fused_and_general_match_oracle(seed):
         assert f.last_run_stats["n_launches"] < g.last_run_stats["n_launches"]
 
 
+@pytest.mark.parametrize("cut", [180.0, 179.0, 120.0])
+def test_wide_angle_cutoffs_and_self_pairs(cut):
+    """cut_angle = 180 admits cos_arg = -1: entries of one atom then pair with themselves (distance 0)."""
+    s = synth.make_system(3000, 30, 55, hydrogens=True, water="TIP3")
+    u = s.universe(3)
+    for sel, method in [("protein", "in_selection"), ("protein or resname TIP3", "water_around")]:
+        kw = dict(cut_angle=cut, additional_donors=['N'], additional_acceptors=['O'])
+        ref = _port(u, sel, method, **kw).initial_results
+        for fused in (1, 0):
+            got = _run(u, sel, method, {"fused": fused}, **kw).initial_results
+            assert_same_results(got, ref, "cut %s %s %s fused=%d" % (cut, sel, method, fused))
+
+
 def test_fused_c3_half_scale():
     s, cfg = synth.config("C3", scale=0.5)
     u = s.universe(6)
