@@ -106,6 +106,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per frame of `kernel` from the committed ncu capture (profiles/ncu_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        d = json.load(open(p))
+        return d[kernel]
+    except Exception:
+        return None
+
+
 def build_case(scale, n_frames):
     from cgraphs_b200 import synth
     system, cfg = synth.config(WORKLOAD, scale=scale)
@@ -313,7 +323,8 @@ def run_ours(args):
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t[0]) / e2e_steps
-        e2e = {"value": world * nf / (e2e_ms / 1000.0), "unit": "frames/s", "h2d_bytes_per_step": int(nf) * na * 12,
+        e2e = {"value": world * nf / (e2e_ms / 1000.0), "unit": "frames/s", "h2d_bytes_per_step": int(ctx.timers()["h2d_bytes"]),
+               "frame_bytes_per_step": int(nf) * na * 12,
                "d2h_bytes_per_step": int(keys.nbytes + words.nbytes), "ms_per_step": e2e_ms,
                "host_memory": "pinned" if pinned else "pageable", "timer": "wall clock between device synchronisations"}
         if pin is not None:
@@ -334,8 +345,12 @@ def run_ours(args):
         frames_per_launch = args.steps * nf / n_l
         avg_ms = kernel_ms[dom] / n_l
         achieved = bytes_frame * frames_per_launch / (avg_ms * 1e-3) / 1e9
+        tr = ncu_traffic(dom)
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                    "frac": achieved / peak,
+                    "traffic": tr["dram_bytes_per_frame"] * frames_per_launch if tr else None,
+                    "traffic_source": tr["source"] if tr else None, "peak_source": peak_kind,
+                    "algorithmic_bytes_per_launch": bytes_frame * frames_per_launch,
                     "algorithmic_bytes_per_frame": bytes_frame, "frames_per_launch": frames_per_launch,
                     "avg_launch_ms": avg_ms, "kernel_share_of_step": kernel_ms[dom] / sum(kernel_ms.values()),
                     "whole_path_frac": bytes_frame * (nf / (ms_per_step / 1e3)) / 1e9 / peak,

@@ -96,6 +96,37 @@ __global__ void __launch_bounds__(32) k_rs_scatter(const unsigned long long* key
     }
 }
 
+// Small results (the common case: a few thousand distinct bonds): one CTA sorts (key, slot) pairs in shared
+// memory with a bitonic network; n <= SORT_SMALL_MAX, padded with the largest key to a power of two.
+#define SORT_SMALL_MAX 4096
+__global__ void __launch_bounds__(1024) k_sort_small(const unsigned long long* keys_in, const unsigned* vals_in, int n,
+                                                     unsigned long long* keys_out, unsigned* vals_out) {
+    __shared__ unsigned long long k[SORT_SMALL_MAX];
+    __shared__ unsigned v[SORT_SMALL_MAX];
+    int m = 1;
+    while (m < n) m <<= 1;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        k[i] = i < n ? keys_in[i] : 0xFFFFFFFFFFFFFFFFull;
+        v[i] = i < n ? vals_in[i] : 0u;
+    }
+    __syncthreads();
+    for (int size = 2; size <= m; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < (m >> 1); i += blockDim.x) {
+                int lo = 2 * i - (i & (stride - 1));          // index of the lower element of pair i
+                int hi = lo + stride;
+                bool up = (lo & size) == 0;
+                unsigned long long a = k[lo], b = k[hi];
+                if ((a > b) == up) {
+                    k[lo] = b; k[hi] = a;
+                    unsigned t = v[lo]; v[lo] = v[hi]; v[hi] = t;
+                }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { keys_out[i] = k[i]; vals_out[i] = v[i]; }
+}
+
 __global__ void k_gather_rows(const unsigned* bits, const unsigned* slots, int n, int wpr, unsigned* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)n * wpr;

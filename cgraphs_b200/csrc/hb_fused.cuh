@@ -79,12 +79,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes or ~1 us passed,
+// instead of burning issue slots in a polling loop
 __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
     unsigned ok;
     asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(1000u)
         : "memory");
     return ok != 0;
 }
@@ -93,10 +95,8 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned pari
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
     for (;;) {
-        for (int k = 0; k < 256; ++k) {
-            __nanosleep(32);
+        for (int k = 0; k < 64; ++k)
             if (mbar_try_wait(bar, parity)) return true;
-        }
         if (clock64() - t0 > 2000000000ll) return false;
     }
 }

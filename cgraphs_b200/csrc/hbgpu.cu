@@ -77,6 +77,7 @@ struct hb_ctx {
     long long opt_table_capacity = 0;   // 0: sized from the selection
     long long opt_max_batch_frames = 2048;
     int opt_profile = 0;
+    int opt_force_radix = 0;          // 1: always use the multi-pass radix sort in hb_finalize (test hook)
     int opt_fused = 1;                // 1: use the one-CTA-per-frame kernel when a frame fits in shared memory
     long long opt_fused_lw_cap = 0;   // 0: automatic
     long long opt_fused_cell_cap = 0; // 0: automatic
@@ -131,6 +132,10 @@ struct hb_ctx {
     int* fin_counter = nullptr;
     size_t fin_cap = 0, fin_hist_cap = 0;
     long long n_sel_total = 0, n_wat_total = 0;
+    // trajectory mode: atom ranges [begin, end) that hold every atom the kernels read; the rest of a frame
+    // (inert atoms) is never copied to the device. Empty = copy whole frames.
+    std::vector<std::pair<long long, long long>> copy_ranges;
+    int opt_copy_ranges = 1;
     int trace = 0;
 
     // timers
@@ -327,6 +332,8 @@ int hb_set_option(hb_ctx* ctx, const char* name, int64_t value) {
     else if (n == "profile") ctx->opt_profile = value != 0;
     else if (n == "max_batch_frames") ctx->opt_max_batch_frames = std::max<long long>(value, 1);
     else if (n == "fused") ctx->opt_fused = value != 0;
+    else if (n == "force_radix_sort") ctx->opt_force_radix = value != 0;
+    else if (n == "copy_ranges") ctx->opt_copy_ranges = value != 0;
     else if (n == "fused_lw_cap") ctx->opt_fused_lw_cap = std::max<long long>(value, 0);
     else if (n == "fused_cell_cap") ctx->opt_fused_cell_cap = std::max<long long>(value, 0);
     else if (n == "fused_pair_cap") ctx->opt_fused_pair_cap = std::max<long long>(value, 0);
@@ -385,6 +392,26 @@ int hb_set_topology(hb_ctx* ctx, const hb_topology* t) {
     }
     for (int k = 0; k < t->n_ent_h; ++k)
         if (t->ent_h_atom[k] < 0 || t->ent_h_atom[k] >= ctx->max_atoms) return fail(ctx, HB_ERR_ARG, "topology: hydrogen atom out of range");
+    // atoms the kernels can touch (single system): selection points, water points, every listed hydrogen
+    ctx->copy_ranges.clear();
+    if (ns == 1 && ctx->max_atoms > 0) {
+        std::vector<unsigned char> used((size_t)ctx->max_atoms, 0);
+        for (int i = 0; i < t->n_sel; ++i) used[t->sel_atom[i]] = 1;
+        for (int i = 0; i < t->n_wat; ++i) used[t->wat_atom[i]] = 1;
+        for (int i = 0; i < t->n_ent_h; ++i) used[t->ent_h_atom[i]] = 1;
+        const long long gap = 4096;                    // holes shorter than this (48 kB) are copied along
+        long long covered = 0, a = 0, n = ctx->max_atoms;
+        while (a < n) {
+            while (a < n && !used[a]) ++a;
+            if (a >= n) break;
+            long long b = a, last = a;
+            while (b < n && b - last <= gap) { if (used[b]) last = b; ++b; }
+            ctx->copy_ranges.push_back({a, last + 1});
+            covered += last + 1 - a;
+            a = last + 1;
+        }
+        if (ctx->copy_ranges.size() > 8 || covered * 10 > n * 9) ctx->copy_ranges.clear();   // not worth it
+    }
     // water points at a constant atom stride (O, H, H, O, H, H ...) can be streamed as contiguous slabs
     ctx->water_regular = t->n_wat > 0;
     ctx->water_stride = 0;
@@ -605,6 +632,7 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     if (reuse) {
         size_t tc = (size_t)ctx->table_cap;
         k_fill_u64<<<1184, 256, 0, ctx->s_compute>>>(ctx->bt.keys, tc, EMPTY_KEY);
+        ctx->tm.n_launches += 1;
         CK(cudaMemsetAsync(ctx->bt.bits, 0, tc * wpr * sizeof(unsigned), ctx->s_compute));
         CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 16 * sizeof(unsigned long long), ctx->s_compute));
         if (ctx->trace) { cudaStreamSynchronize(ctx->s_compute); tr.mark("clear(reuse)"); }
@@ -857,10 +885,31 @@ int hb_submit_frames(hb_ctx* ctx, const float* xyz, int64_t n_atoms, int64_t n_f
         int k = (int)(ctx->batch_counter & 1);
         if ((rc = acquire_slot(ctx, k))) return rc;       // buffer k (device + staging) is free again
         const float* h = src;
-        if (!pinned) { memcpy(ctx->h_stage[k], src, bytes); h = ctx->h_stage[k]; }
+        const bool ranged = ctx->opt_copy_ranges && !ctx->prm.structure_batch && !ctx->copy_ranges.empty();
+        if (!pinned) {
+            if (ranged) {
+                for (int f = 0; f < nf; ++f)
+                    for (auto& r : ctx->copy_ranges)
+                        memcpy(ctx->h_stage[k] + ((size_t)f * n_atoms + r.first) * 3, src + ((size_t)f * n_atoms + r.first) * 3,
+                               (size_t)(r.second - r.first) * 12);
+            } else {
+                memcpy(ctx->h_stage[k], src, bytes);
+            }
+            h = ctx->h_stage[k];
+        }
         cudaEvent_t c0 = get_event(ctx), c1 = get_event(ctx);
         cudaEventRecord(c0, ctx->s_copy);
-        CK(cudaMemcpyAsync(ctx->d_in[k], h, bytes, cudaMemcpyHostToDevice, ctx->s_copy));
+        if (ranged) {      // strided copies: only the atom ranges the search reads, same layout on the device
+            const size_t pitch = (size_t)n_atoms * 12;
+            for (auto& r : ctx->copy_ranges) {
+                CK(cudaMemcpy2DAsync((char*)ctx->d_in[k] + (size_t)r.first * 12, pitch, (const char*)h + (size_t)r.first * 12, pitch,
+                                     (size_t)(r.second - r.first) * 12, (size_t)nf, cudaMemcpyHostToDevice, ctx->s_copy));
+                ctx->tm.h2d_bytes += (long long)(r.second - r.first) * 12 * nf;
+            }
+        } else {
+            CK(cudaMemcpyAsync(ctx->d_in[k], h, bytes, cudaMemcpyHostToDevice, ctx->s_copy));
+            ctx->tm.h2d_bytes += (long long)bytes;
+        }
         cudaEventRecord(c1, ctx->s_copy);
         ctx->pending.push_back({c0, c1, -2});
         CK(cudaEventRecord(ctx->ev_copied[k], ctx->s_copy));
@@ -971,7 +1020,12 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
     CK(cudaMemsetAsync(counter, 0, 4, st));
     unsigned cap = ctx->bt.mask + 1u;
     k_compact<<<(cap + 255) / 256, 256, 0, st>>>(ctx->bt, k0, v0, counter);
-    if (n > 1) {
+    ctx->tm.n_launches += 1 + (n > 0 ? 1 : 0) + (n > 1 ? ((n <= SORT_SMALL_MAX && !ctx->opt_force_radix) ? 1 : 24) : 0);
+    if (n > 1 && n <= SORT_SMALL_MAX && !ctx->opt_force_radix) {
+        k_sort_small<<<1, 1024, 0, st>>>(k0, v0, n, k1, v1);
+        std::swap(k0, k1);
+        std::swap(v0, v1);
+    } else if (n > 1) {
         for (int pass = 0; pass < 8; ++pass) {
             int shift = pass * 8;
             k_rs_hist<<<nblk, 256, 0, st>>>(k0, n, shift, hist);

@@ -65,6 +65,7 @@ class HbTimers(C.Structure):
         ("ms_run", C.c_double),
         ("fused_frames", C.c_int64),
         ("fused_fallbacks", C.c_int64),
+        ("h2d_bytes", C.c_int64),
     ]
 
 
@@ -249,7 +250,7 @@ class Context:
             k += 1
         return dict(ms_total=t.ms_total, ms_h2d=t.ms_h2d, ms_run=t.ms_run, n_launches=t.n_launches, frames=t.frames,
                     pairs_emitted=t.pairs_emitted, table_capacity=t.table_capacity, table_grows=t.table_grows,
-                    fused_frames=t.fused_frames, fused_fallbacks=t.fused_fallbacks,
+                    fused_frames=t.fused_frames, fused_fallbacks=t.fused_fallbacks, h2d_bytes=t.h2d_bytes,
                     ms_kernel={n: t.ms_kernel[i] for i, n in enumerate(names)},
                     launches={n: t.launches[i] for i, n in enumerate(names)})
 

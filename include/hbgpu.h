@@ -112,6 +112,7 @@ typedef struct {
     int64_t fused_frames;         /* frames processed by the one-CTA-per-frame kernel */
     int64_t fused_fallbacks;      /* times a frame did not fit in shared memory and the run moved to the
                                      general (global-memory cell list) kernels */
+    int64_t h2d_bytes;            /* bytes hb_submit_frames copied host -> device (inert atom ranges are skipped) */
 } hb_timers;
 
 int hb_create(hb_ctx** out, int device_ordinal);
@@ -127,7 +128,8 @@ int hb_set_option(hb_ctx* ctx, const char* name, int64_t value);
         /* "batch_bytes": device budget per frame batch; "table_capacity": initial bond-table slots;
            "profile": 1 = time every kernel class with CUDA events; "max_batch_frames";
            "fused": 0 = never use the one-CTA-per-frame kernel; "fused_lw_cap" / "fused_cell_cap": its
-           shared-memory capacities (0 = automatic) */
+           shared-memory capacities (0 = automatic); "fused_stages", "fused_prefetch", "fused_batch_frames";
+           "copy_ranges": 0 = always copy whole frames; "force_radix_sort" (test hook) */
 
 /* Start an analysis over n_frames_total frames (the width of the occupancy matrix). */
 int hb_begin(hb_ctx* ctx, int64_t n_frames_total);

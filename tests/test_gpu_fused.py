@@ -153,3 +153,44 @@ def test_fused_device_resident_unaligned_frames():
         k, w = ctx.results()
         assert np.array_equal(k, k0) and np.array_equal(w, w0), pad
     assert ctx.timers()["fused_frames"] == nf
+
+
+def test_finalize_sort_paths_agree():
+    """hb_finalize sorts small key sets in one CTA (bitonic) and large ones with the radix passes."""
+    s, cfg = synth.config("C2", scale=0.6)
+    u = s.universe(4)
+    small = _run(u, "protein", "water_around", {})
+    small_r = _run(u, "protein", "water_around", {"force_radix_sort": 1})
+    assert 0 < len(small.initial_results) < 4096
+    assert_same_results(small.initial_results, small_r.initial_results)
+    big = _run(u, "protein or resname TIP3", "water_around", {})
+    assert len(big.initial_results) > 4096
+    assert_same_results(big.initial_results, _port(u, "protein or resname TIP3", "water_around").initial_results)
+
+
+def test_h2d_skips_inert_atom_ranges():
+    """Trajectory frames are copied to the device without the atom ranges no kernel reads (membrane filler)."""
+    from cgraphs_b200.mdhbond import HbondAnalysis, _native
+    s, cfg = synth.config("C3", scale=0.5)
+    nf = 10
+    xyz = s.frames(0, nf)
+    u = Universe(s.topology, xyz)
+    ref = _port(u, "protein", "water_around").initial_results
+    full = _run(u, "protein", "water_around", {"copy_ranges": 0})
+    part = _run(u, "protein", "water_around", {"copy_ranges": 1})
+    assert_same_results(full.initial_results, ref)
+    assert_same_results(part.initial_results, ref)
+    assert full.last_run_stats["h2d_bytes"] == xyz.nbytes
+    assert part.last_run_stats["h2d_bytes"] < 0.9 * xyz.nbytes
+    # pinned source memory takes the direct (unstaged) copy path
+    ctx = part._context()
+    pin = _native.PinnedBuffer(xyz.shape)
+    pin.array[...] = xyz
+    ctx.begin(nf)
+    ctx.submit_raw(pin.ptr, xyz.shape[1], nf)
+    k1, w1 = ctx.results()
+    ctx.begin(nf)
+    ctx.submit(xyz)
+    k2, w2 = ctx.results()
+    pin.free()
+    assert np.array_equal(k1, k2) and np.array_equal(w1, w2) and len(k1) == len(ref)
