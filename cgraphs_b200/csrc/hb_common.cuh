@@ -37,11 +37,25 @@ struct DevTopo {
     int h_wide;              // some entry has more than 4 hydrogens or one further than 127 atoms away: use the CSR
 };
 
+struct Box6 {           // lower-triangular lattice: a = (ax, 0, 0), b = (bx, by, 0), c = (cx, cy, cz)
+    float ax, bx, by, cx, cy, cz;
+};
+
+struct PbcGrid {        // minimum-image modes: grid in fractional coordinates. Per lattice axis either a window
+    Box6 box;           // around the selection (non-periodic, `per` = 0) or the whole period (wraps, `per` = 1)
+    float ia, ib, ic;   // 1 / ax, 1 / by, 1 / cz
+    float c[3];         // window centre (absolute fractional coordinate)
+    float half[3];      // window half width (0.5 for a periodic axis)
+    float scale[3];     // cells per fractional unit
+    int per[3];
+};
+
 struct FrameGrid {      // geometry of one cell grid of one frame
-    float ox, oy, oz;   // origin
-    float inv;          // 1 / cell edge
+    float ox, oy, oz;   // origin                       (non-periodic mode)
+    float inv;          // 1 / cell edge                (non-periodic mode)
     int nx, ny, nz;
     int ncell;
+    PbcGrid p;          // minimum-image modes only
 };
 
 struct FrameState {     // per frame slot of a batch
@@ -51,11 +65,13 @@ struct FrameState {     // per frame slot of a batch
     int n_points;       // points in the pair-search set (selection + local waters)
     FrameGrid g1;       // selection grid used by the local-water test (cell >= around_radius)
     FrameGrid g2;       // pair-search grid (cell >= distance)
-    float lo[3], hi[3]; // decoded bounding box of the selection points
+    float lo[3], hi[3]; // decoded bounding box of the selection points (minimum-image modes: fractional,
+                        // relative to the first selection point and wrapped into [-0.5, 0.5])
 };
 
 struct BatchView {
     const float* xyz;        // coordinates of the batch
+    const float* box;        // minimum-image modes: 9 floats per frame of the batch (lattice vectors as rows)
     long long frame0;        // global index (occupancy column) of the first frame of the batch
     int n_frames;            // frames in this batch
     long long atoms_per_frame;   // trajectory mode stride (atoms)
@@ -85,6 +101,7 @@ struct RunParams {
     int excl_bb;
     int method;
     int self_pairs;          // 1: distance-0 entry pairs of one atom can pass (only with cut_angle >= 180 deg)
+    int pbc;                 // HB_PBC_*
 };
 
 struct BondTable {
@@ -124,11 +141,81 @@ __device__ __forceinline__ int cell_coord(float x, float o, float inv, int n) {
     int c = (int)floorf((x - o) * inv);
     return min(max(c, 0), n - 1);
 }
+
+__device__ __forceinline__ Box6 load_box(const float* b9) {
+    Box6 B;
+    B.ax = b9[0]; B.bx = b9[3]; B.by = b9[4]; B.cx = b9[6]; B.cy = b9[7]; B.cz = b9[8];
+    return B;
+}
+// fractional coordinates (not wrapped) in the lower-triangular lattice
+__device__ __forceinline__ void frac_coords(const PbcGrid& p, float x, float y, float z, float& sa, float& sb, float& sc) {
+    sc = z * p.ic;
+    sb = (y - sc * p.box.cy) * p.ib;
+    sa = (x - sb * p.box.bx - sc * p.box.cx) * p.ia;
+}
+// cell coordinates in a minimum-image grid; false when the point lies outside a windowed axis
+__device__ __forceinline__ bool cell3_pbc(const FrameGrid& g, float x, float y, float z, int& cx, int& cy, int& cz) {
+    float s[3];
+    frac_coords(g.p, x, y, z, s[0], s[1], s[2]);
+    const int n[3] = {g.nx, g.ny, g.nz};
+    int c[3];
+    bool inside = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float u = s[k] - g.p.c[k];
+        u -= rintf(u);
+        const float v = u + g.p.half[k];
+        inside = inside && (g.p.per[k] || (v >= 0.f && v <= 2.f * g.p.half[k]));
+        c[k] = min(max((int)floorf(v * g.p.scale[k]), 0), n[k] - 1);
+    }
+    cx = c[0]; cy = c[1]; cz = c[2];
+    return inside;
+}
+template <bool PBC>
+__device__ __forceinline__ void cell3(const FrameGrid& g, float x, float y, float z, int& cx, int& cy, int& cz) {
+    if constexpr (PBC) {
+        cell3_pbc(g, x, y, z, cx, cy, cz);
+    } else {
+        cx = cell_coord(x, g.ox, g.inv, g.nx);
+        cy = cell_coord(y, g.oy, g.inv, g.ny);
+        cz = cell_coord(z, g.oz, g.inv, g.nz);
+    }
+}
+template <bool PBC>
 __device__ __forceinline__ int cell_of(const FrameGrid& g, float x, float y, float z) {
-    int cx = cell_coord(x, g.ox, g.inv, g.nx);
-    int cy = cell_coord(y, g.oy, g.inv, g.ny);
-    int cz = cell_coord(z, g.oz, g.inv, g.nz);
+    int cx, cy, cz;
+    cell3<PBC>(g, x, y, z, cx, cy, cz);
     return (cz * g.ny + cy) * g.nx + cx;
+}
+// neighbour cells along one axis of a minimum-image grid, each listed once
+struct AxisList { int v[3]; int n; };
+__device__ __forceinline__ AxisList axis_neighbors(int c, int n, int per) {
+    AxisList a;
+    if (!per) {
+        const int lo = max(c - 1, 0), hi = min(c + 1, n - 1);
+        a.n = hi - lo + 1;
+        a.v[0] = lo; a.v[1] = lo + 1; a.v[2] = lo + 2;
+    } else if (n >= 3) {
+        a.n = 3;
+        a.v[0] = c ? c - 1 : n - 1; a.v[1] = c; a.v[2] = c + 1 < n ? c + 1 : 0;
+    } else {
+        a.n = n;
+        a.v[0] = 0; a.v[1] = 1; a.v[2] = 0;
+    }
+    return a;
+}
+// the x-neighbours of a row as one or two runs of contiguous cells [lo, hi]
+struct XSegs { int lo[2], hi[2]; int n; };
+__device__ __forceinline__ XSegs x_segments(int c, int n, int per) {
+    XSegs x;
+    x.n = 1;
+    x.lo[1] = 0; x.hi[1] = -1;
+    if (!per) { x.lo[0] = max(c - 1, 0); x.hi[0] = min(c + 1, n - 1); }
+    else if (n < 3) { x.lo[0] = 0; x.hi[0] = n - 1; }
+    else if (c == 0) { x.lo[0] = 0; x.hi[0] = 1; x.lo[1] = n - 1; x.hi[1] = n - 1; x.n = 2; }
+    else if (c == n - 1) { x.lo[0] = n - 2; x.hi[0] = n - 1; x.lo[1] = 0; x.hi[1] = 0; x.n = 2; }
+    else { x.lo[0] = c - 1; x.hi[0] = c + 1; }
+    return x;
 }
 
 // DIST predicate, SURVEY A.2 / F2 (scipy cKDTree semantics on float32 inputs)
@@ -143,15 +230,73 @@ __device__ __forceinline__ float dist2f(float ax, float ay, float az, float bx, 
     float dx = ax - bx, dy = ay - by, dz = az - bz;
     return dx * dx + dy * dy + dz * dz;
 }
+// Minimum-image DIST (opt-in extension): the float64 difference vector is reduced along c, b, a in
+// turn (n = rint(d_k / L_k), individually rounded multiply and subtract), then tested like DIST. When no
+// reduction applies (n = 0 three times) the arithmetic is exactly that of dist_le.
+__device__ __forceinline__ bool dist_le_pbc(float ax, float ay, float az, float bx, float by, float bz, double r2, const Box6& B) {
+    double dx = (double)ax - (double)bx;
+    double dy = (double)ay - (double)by;
+    double dz = (double)az - (double)bz;
+    double n = rint(__ddiv_rn(dz, (double)B.cz));
+    dz = __dsub_rn(dz, __dmul_rn(n, (double)B.cz));
+    dy = __dsub_rn(dy, __dmul_rn(n, (double)B.cy));
+    dx = __dsub_rn(dx, __dmul_rn(n, (double)B.cx));
+    n = rint(__ddiv_rn(dy, (double)B.by));
+    dy = __dsub_rn(dy, __dmul_rn(n, (double)B.by));
+    dx = __dsub_rn(dx, __dmul_rn(n, (double)B.bx));
+    n = rint(__ddiv_rn(dx, (double)B.ax));
+    dx = __dsub_rn(dx, __dmul_rn(n, (double)B.ax));
+    double s = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+    return s <= r2;
+}
+// float32 minimum image of a difference vector, individually rounded (ANG under PBC; also the pre-filter)
+__device__ __forceinline__ void min_image_f32(float& vx, float& vy, float& vz, const Box6& B) {
+    float n = rintf(__fdiv_rn(vz, B.cz));
+    vz = __fsub_rn(vz, __fmul_rn(n, B.cz));
+    vy = __fsub_rn(vy, __fmul_rn(n, B.cy));
+    vx = __fsub_rn(vx, __fmul_rn(n, B.cx));
+    n = rintf(__fdiv_rn(vy, B.by));
+    vy = __fsub_rn(vy, __fmul_rn(n, B.by));
+    vx = __fsub_rn(vx, __fmul_rn(n, B.bx));
+    n = rintf(__fdiv_rn(vx, B.ax));
+    vx = __fsub_rn(vx, __fmul_rn(n, B.ax));
+}
+__device__ __forceinline__ float dist2f_pbc(float ax, float ay, float az, float bx, float by, float bz, const Box6& B,
+                                            float ia, float ib, float ic) {
+    float dx = ax - bx, dy = ay - by, dz = az - bz;
+    float n = rintf(dz * ic);
+    dz -= n * B.cz; dy -= n * B.cy; dx -= n * B.cx;
+    n = rintf(dy * ib);
+    dy -= n * B.by; dx -= n * B.bx;
+    n = rintf(dx * ia);
+    dx -= n * B.ax;
+    return dx * dx + dy * dy + dz * dz;
+}
+template <bool PBC>
+__device__ __forceinline__ bool within(float ax, float ay, float az, float bx, float by, float bz, float r2f_hi, double r2,
+                                       const PbcGrid& p) {
+    if constexpr (PBC) {
+        if (dist2f_pbc(ax, ay, az, bx, by, bz, p.box, p.ia, p.ib, p.ic) > r2f_hi) return false;
+        return dist_le_pbc(ax, ay, az, bx, by, bz, r2, p.box);
+    } else {
+        if (dist2f(ax, ay, az, bx, by, bz) > r2f_hi) return false;
+        return dist_le(ax, ay, az, bx, by, bz, r2);
+    }
+}
 
 // ANG predicate, SURVEY A.2 / F3 (helpfunctions.py:96-104,155): b = pair partner, h = hydrogen, a = other partner
 __device__ __forceinline__ float dot3_rn(float ax, float ay, float az, float bx, float by, float bz) {
     return __fadd_rn(__fadd_rn(__fmul_rn(ax, bx), __fmul_rn(ay, by)), __fmul_rn(az, bz));
 }
+template <bool PBC>
 __device__ __forceinline__ bool ang_ok_exact(float bx, float by, float bz, float hx, float hy, float hz, float ax,
-                                             float ay, float az, float cthr) {
+                                             float ay, float az, float cthr, const Box6& B) {
     float v1x = __fsub_rn(hx, bx), v1y = __fsub_rn(hy, by), v1z = __fsub_rn(hz, bz);
     float v2x = __fsub_rn(ax, hx), v2y = __fsub_rn(ay, hy), v2z = __fsub_rn(az, hz);
+    if constexpr (PBC) {
+        min_image_f32(v1x, v1y, v1z, B);
+        min_image_f32(v2x, v2y, v2z, B);
+    }
     float d12 = dot3_rn(v1x, v1y, v1z, v2x, v2y, v2z);
     float d11 = dot3_rn(v1x, v1y, v1z, v1x, v1y, v1z);
     float d22 = dot3_rn(v2x, v2y, v2z, v2x, v2y, v2z);
@@ -163,17 +308,22 @@ __device__ __forceinline__ bool ang_ok_exact(float bx, float by, float bz, float
 // Same decision, cheaper on average: an approximate cosine (rsqrt, FMA allowed; relative error < 1e-6)
 // settles every case that is further than 1e-5 from both ends of the accepted interval [cthr, 1];
 // only the rest (and NaN / degenerate vectors) runs the exact, individually rounded chain above.
+template <bool PBC>
 __device__ __forceinline__ bool ang_ok(float bx, float by, float bz, float hx, float hy, float hz, float ax,
-                                       float ay, float az, float cthr) {
-    const float v1x = hx - bx, v1y = hy - by, v1z = hz - bz;
-    const float v2x = ax - hx, v2y = ay - hy, v2z = az - hz;
+                                       float ay, float az, float cthr, const Box6& B) {
+    float v1x = hx - bx, v1y = hy - by, v1z = hz - bz;
+    float v2x = ax - hx, v2y = ay - hy, v2z = az - hz;
+    if constexpr (PBC) {
+        min_image_f32(v1x, v1y, v1z, B);
+        min_image_f32(v2x, v2y, v2z, B);
+    }
     const float d12 = v1x * v2x + v1y * v2y + v1z * v2z;
     const float d11 = v1x * v1x + v1y * v1y + v1z * v1z;
     const float d22 = v2x * v2x + v2y * v2y + v2z * v2z;
     const float ca = d12 * rsqrtf(d11 * d22);
     if (ca < cthr - 1e-5f) return false;
     if (ca > cthr + 1e-5f && ca < 1.0f - 1e-5f) return true;
-    return ang_ok_exact(bx, by, bz, hx, hy, hz, ax, ay, az, cthr);
+    return ang_ok_exact<PBC>(bx, by, bz, hx, hy, hz, ax, ay, az, cthr, B);
 }
 
 __device__ void make_grid(FrameGrid& g, const float* lo, const float* hi, float pad, float cell, int cap) {
@@ -203,6 +353,54 @@ __device__ void make_grid(FrameGrid& g, const float* lo, const float* hi, float 
         cell *= 1.2f;
     }
     g.inv = 0.f; g.nx = g.ny = g.nz = 1; g.ncell = 1;
+}
+
+// Minimum-image grid. sR = fractional coordinates of the reference point (first selection point), [umin, umax] =
+// fractional bounding box of the selection relative to it (each coordinate wrapped into [-0.5, 0.5]), pad = real
+// distance every point of interest may lie outside that box. An axis whose padded box stays below 0.9 periods
+// gets a window (no wrap, points outside are of no interest), otherwise the whole period with wrap-around.
+// Cell thickness (distance between opposite cell faces) is >= `cell` on every axis.
+__device__ void make_grid_pbc(FrameGrid& g, const Box6& B, const float* sR, const float* umin, const float* umax,
+                              float pad, float cell, int cap) {
+    PbcGrid& p = g.p;
+    p.box = B;
+    p.ia = 1.0f / B.ax; p.ib = 1.0f / B.by; p.ic = 1.0f / B.cz;
+    const float bcx = B.by * B.cz, bcy = -B.bx * B.cz, bcz = B.bx * B.cy - B.by * B.cx;
+    float w[3];                                    // perpendicular widths of the cell
+    w[0] = B.ax * B.by * B.cz / sqrtf(bcx * bcx + bcy * bcy + bcz * bcz);
+    w[1] = B.by * B.cz / sqrtf(B.cz * B.cz + B.cy * B.cy);
+    w[2] = B.cz;
+    for (int k = 0; k < 3; ++k) {
+        const float padf = pad / w[k] * 1.001f + 1e-6f;
+        const float width = (umax[k] - umin[k]) + 2.f * padf;
+        if (width < 0.9f && isfinite(sR[k])) {
+            p.per[k] = 0;
+            p.c[k] = sR[k] + 0.5f * (umin[k] + umax[k]);
+            p.half[k] = 0.5f * width;
+        } else {
+            p.per[k] = 1;
+            p.c[k] = 0.5f;
+            p.half[k] = 0.5f;
+        }
+    }
+    int n[3] = {1, 1, 1};
+    for (int it = 0; it < 64; ++it) {
+        double tot = 1.0;
+        bool ok = true;
+        for (int k = 0; k < 3; ++k) {
+            float q = floorf(2.f * p.half[k] * w[k] / cell);
+            if (!(q >= 1.f)) q = 1.f;
+            if (q > 1024.f) { ok = false; q = 1024.f; }
+            n[k] = (int)q;
+            tot *= (double)n[k];
+        }
+        if (ok && tot <= (double)cap) break;
+        cell *= 1.2f;
+        if (it == 63) n[0] = n[1] = n[2] = 1;
+    }
+    for (int k = 0; k < 3; ++k) p.scale[k] = (float)n[k] / (2.f * p.half[k]);
+    g.nx = n[0]; g.ny = n[1]; g.nz = n[2]; g.ncell = n[0] * n[1] * n[2];
+    g.ox = g.oy = g.oz = 0.f; g.inv = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -269,21 +467,23 @@ __device__ __forceinline__ void load_info(const DevTopo& tp, const RunParams& rp
 }
 
 // any hydrogen of entry `e` (owned by point `owner`) with ANG(other, h, owner) satisfied: CSR walk
+template <bool PBC>
 __device__ __forceinline__ bool any_h(const DevTopo& tp, const float* xyz, int e, const PointInfo& owner,
-                                      const PointInfo& other, float cthr) {
+                                      const PointInfo& other, float cthr, const Box6& B) {
     int4 ep = tp.ent_pack[e];
     int s = ep.z, t = ep.z + ep.w;
     for (int k = s; k < t; ++k) {
         const float* h = xyz + 3ll * tp.ent_h_atom[k];
-        if (ang_ok(other.x, other.y, other.z, h[0], h[1], h[2], owner.x, owner.y, owner.z, cthr)) return true;
+        if (ang_ok<PBC>(other.x, other.y, other.z, h[0], h[1], h[2], owner.x, owner.y, owner.z, cthr, B)) return true;
     }
     return false;
 }
 // same over an inline list of up to four hydrogens of the atom `atom` at (ox, oy, oz); (tx, ty, tz) is the
 // partner. The coordinate loads are issued together. Not inlined: it is called from up to four places per
 // pair and would otherwise multiply the register footprint of the calling kernels.
+template <bool PBC>
 __device__ __noinline__ bool any_h4(const float* xyz, int hl, int atom, float ox, float oy, float oz, float tx, float ty,
-                                    float tz, float cthr) {
+                                    float tz, float cthr, const Box6* B) {
     float h[4][3];
     int d[4];
 #pragma unroll
@@ -297,7 +497,7 @@ __device__ __noinline__ bool any_h4(const float* xyz, int hl, int atom, float ox
     bool ok = false;
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-        if (d[k] != -128 && !ok) ok = ang_ok(tx, ty, tz, h[k][0], h[k][1], h[k][2], ox, oy, oz, cthr);
+        if (d[k] != -128 && !ok) ok = ang_ok<PBC>(tx, ty, tz, h[k][0], h[k][1], h[k][2], ox, oy, oz, cthr, *B);
     return ok;
 }
 
@@ -318,8 +518,9 @@ __device__ __forceinline__ void emit(const DevTopo& tp, const RunParams& rp, con
 }
 // All entry pairs generated by the point pair (P, Q), P != Q as points.
 // "Some hydrogen of this entry passes the angle test" is evaluated once per entry that takes part in a pair.
+template <bool PBC>
 __device__ __forceinline__ void process_pair(const DevTopo& tp, const RunParams& rp, const BondTable& bt, const float* xyz,
-                                             long long frame, const PointInfo& P, const PointInfo& Q, int& nhit) {
+                                             long long frame, const PointInfo& P, const PointInfo& Q, int& nhit, const Box6& B) {
     const bool ang = rp.check_angle != 0;
     const float ct = rp.cos_threshold;
     const bool bb_skip = rp.excl_bb && P.bb && Q.bb;
@@ -330,15 +531,15 @@ __device__ __forceinline__ void process_pair(const DevTopo& tp, const RunParams&
     bool pd = need_pd, qd = need_qd, pw = need_pw, qw = need_qw;
     if (ang) {
         if (tp.h_wide) {
-            if (need_pd) pd = any_h(tp, xyz, P.don, P, Q, ct);
-            if (need_qd) qd = any_h(tp, xyz, Q.don, Q, P, ct);
-            if (need_pw) pw = any_h(tp, xyz, P.wat, P, Q, ct);
-            if (need_qw) qw = any_h(tp, xyz, Q.wat, Q, P, ct);
+            if (need_pd) pd = any_h<PBC>(tp, xyz, P.don, P, Q, ct, B);
+            if (need_qd) qd = any_h<PBC>(tp, xyz, Q.don, Q, P, ct, B);
+            if (need_pw) pw = any_h<PBC>(tp, xyz, P.wat, P, Q, ct, B);
+            if (need_qw) qw = any_h<PBC>(tp, xyz, Q.wat, Q, P, ct, B);
         } else {
-            if (need_pd) pd = any_h4(xyz, P.hd, P.atom, P.x, P.y, P.z, Q.x, Q.y, Q.z, ct);
-            if (need_qd) qd = any_h4(xyz, Q.hd, Q.atom, Q.x, Q.y, Q.z, P.x, P.y, P.z, ct);
-            if (need_pw) pw = any_h4(xyz, P.hw, P.atom, P.x, P.y, P.z, Q.x, Q.y, Q.z, ct);
-            if (need_qw) qw = any_h4(xyz, Q.hw, Q.atom, Q.x, Q.y, Q.z, P.x, P.y, P.z, ct);
+            if (need_pd) pd = any_h4<PBC>(xyz, P.hd, P.atom, P.x, P.y, P.z, Q.x, Q.y, Q.z, ct, &B);
+            if (need_qd) qd = any_h4<PBC>(xyz, Q.hd, Q.atom, Q.x, Q.y, Q.z, P.x, P.y, P.z, ct, &B);
+            if (need_pw) pw = any_h4<PBC>(xyz, P.hw, P.atom, P.x, P.y, P.z, Q.x, Q.y, Q.z, ct, &B);
+            if (need_qw) qw = any_h4<PBC>(xyz, Q.hw, Q.atom, Q.x, Q.y, Q.z, P.x, P.y, P.z, ct, &B);
         }
     }
     if (!bb_skip) {
@@ -404,14 +605,15 @@ __device__ __forceinline__ int h_count(int hl) {                  // bytes of th
 }
 
 // Entry pairs of a point with itself (distance 0): acceptor-donor and selection-water entries of one atom
+template <bool PBC>
 __device__ void process_self(const DevTopo& tp, const RunParams& rp, const BondTable& bt, const float* xyz,
-                             long long frame, const PointInfo& P, int& nhit) {
+                             long long frame, const PointInfo& P, int& nhit, const Box6& B) {
     const bool ang = rp.check_angle != 0;
     const float ct = rp.cos_threshold;
     bool need = (P.acc >= 0 && P.don >= 0) || (P.wat >= 0 && (P.don >= 0 || P.acc >= 0));
     if (!need) return;
-    bool pd = P.don >= 0 ? ((!ang) || any_h(tp, xyz, P.don, P, P, ct)) : false;
-    bool pw = P.wat >= 0 ? ((!ang) || any_h(tp, xyz, P.wat, P, P, ct)) : false;
+    bool pd = P.don >= 0 ? ((!ang) || any_h<PBC>(tp, xyz, P.don, P, P, ct, B)) : false;
+    bool pw = P.wat >= 0 ? ((!ang) || any_h<PBC>(tp, xyz, P.wat, P, P, ct, B)) : false;
     if (P.acc >= 0 && P.don >= 0 && !(rp.excl_bb && P.bb) && pd) emit(tp, rp, bt, frame, P.acc, P.don, nhit);
     if (P.wat >= 0) {
         if (P.don >= 0 && (pd || pw)) emit(tp, rp, bt, frame, P.don, P.wat, nhit);
@@ -425,65 +627,101 @@ __device__ void process_self(const DevTopo& tp, const RunParams& rp, const BondT
 // point array (start = cells[c-1], 0 for c = 0); cells are ordered x-fastest, so the three x-neighbours
 // of a (y, z) row are one contiguous run of points.
 // ------------------------------------------------------------------------------------------------
-template <typename CellT>
+template <bool PBC, typename CellT>
 __device__ __forceinline__ bool water_is_local(const FrameGrid& g, const CellT* cells, const float4* pts, float x,
                                                float y, float z, const RunParams& rp) {
-    int cx = cell_coord(x, g.ox, g.inv, g.nx);
-    int cy = cell_coord(y, g.oy, g.inv, g.ny);
-    int cz = cell_coord(z, g.oz, g.inv, g.nz);
-    for (int zz = max(cz - 1, 0); zz <= min(cz + 1, g.nz - 1); ++zz)
-        for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.ny - 1); ++yy) {
-            int c_lo = (zz * g.ny + yy) * g.nx + max(cx - 1, 0);
-            int c_hi = (zz * g.ny + yy) * g.nx + min(cx + 1, g.nx - 1);
-            int s = c_lo ? (int)cells[c_lo - 1] : 0;
-            int e = (int)cells[c_hi];
-            for (int q = s; q < e; ++q) {
-                float4 sp = pts[q];
-                if (dist2f(x, y, z, sp.x, sp.y, sp.z) <= rp.around2f_hi &&
-                    dist_le(x, y, z, sp.x, sp.y, sp.z, rp.around2))
-                    return true;
+    int cx, cy, cz;
+    cell3<PBC>(g, x, y, z, cx, cy, cz);
+    if constexpr (PBC) {
+        const AxisList zl = axis_neighbors(cz, g.nz, g.p.per[2]), yl = axis_neighbors(cy, g.ny, g.p.per[1]);
+        const XSegs xs = x_segments(cx, g.nx, g.p.per[0]);
+        for (int a = 0; a < zl.n; ++a)
+            for (int b = 0; b < yl.n; ++b) {
+                const int row = (zl.v[a] * g.ny + yl.v[b]) * g.nx;
+                for (int k = 0; k < xs.n; ++k) {
+                    const int c_lo = row + xs.lo[k], c_hi = row + xs.hi[k];
+                    const int s = c_lo ? (int)cells[c_lo - 1] : 0, e = (int)cells[c_hi];
+                    for (int q = s; q < e; ++q) {
+                        const float4 sp = pts[q];
+                        if (within<true>(x, y, z, sp.x, sp.y, sp.z, rp.around2f_hi, rp.around2, g.p)) return true;
+                    }
+                }
             }
-        }
-    return false;
+        return false;
+    } else {
+        for (int zz = max(cz - 1, 0); zz <= min(cz + 1, g.nz - 1); ++zz)
+            for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.ny - 1); ++yy) {
+                int c_lo = (zz * g.ny + yy) * g.nx + max(cx - 1, 0);
+                int c_hi = (zz * g.ny + yy) * g.nx + min(cx + 1, g.nx - 1);
+                int s = c_lo ? (int)cells[c_lo - 1] : 0;
+                int e = (int)cells[c_hi];
+                for (int q = s; q < e; ++q) {
+                    float4 sp = pts[q];
+                    if (dist2f(x, y, z, sp.x, sp.y, sp.z) <= rp.around2f_hi &&
+                        dist_le(x, y, z, sp.x, sp.y, sp.z, rp.around2))
+                        return true;
+                }
+            }
+        return false;
+    }
 }
 
-// all H-bond entry pairs of cell-sorted point i with itself and with the points of its half shell
-template <typename CellT>
+// Calls f(q) for every cell-sorted point q > i that shares a neighbourhood with point i: half shell (own cell
+// + 13 forward cells as 5 contiguous runs) in the non-periodic grid, the full de-duplicated shell filtered
+// by q > i in a minimum-image grid (wrap-around breaks the forward ordering of cells).
+template <bool PBC, typename CellT, typename F>
+__device__ __forceinline__ void for_each_partner(const FrameGrid& g, const CellT* cells, int i, float x, float y, float z, F f) {
+    int cx, cy, cz;
+    cell3<PBC>(g, x, y, z, cx, cy, cz);
+    if constexpr (PBC) {
+        const AxisList zl = axis_neighbors(cz, g.nz, g.p.per[2]), yl = axis_neighbors(cy, g.ny, g.p.per[1]);
+        const XSegs xs = x_segments(cx, g.nx, g.p.per[0]);
+        for (int a = 0; a < zl.n; ++a)
+            for (int b = 0; b < yl.n; ++b) {
+                const int row = (zl.v[a] * g.ny + yl.v[b]) * g.nx;
+                for (int k = 0; k < xs.n; ++k) {
+                    const int c_lo = row + xs.lo[k], c_hi = row + xs.hi[k];
+                    const int s = max(c_lo ? (int)cells[c_lo - 1] : 0, i + 1), e = (int)cells[c_hi];
+                    for (int q = s; q < e; ++q) f(q);
+                }
+            }
+    } else {
+        const int xl = max(cx - 1, 0), xh = min(cx + 1, g.nx - 1);
+#pragma unroll 1
+        for (int run = 0; run < 5; ++run) {
+            int s, e;
+            if (run == 0) {
+                s = i + 1;
+                e = (int)cells[(cz * g.ny + cy) * g.nx + xh];
+            } else {
+                const int yy = run == 1 ? cy + 1 : cy + (run - 3);
+                const int zz = run == 1 ? cz : cz + 1;
+                if (yy < 0 || yy >= g.ny || zz >= g.nz) continue;
+                const int row = (zz * g.ny + yy) * g.nx;
+                s = (row + xl) ? (int)cells[row + xl - 1] : 0;
+                e = (int)cells[row + xh];
+            }
+            for (int q = s; q < e; ++q) f(q);
+        }
+    }
+}
+
+// all H-bond entry pairs of cell-sorted point i with itself and with its partners (general path)
+template <bool PBC, typename CellT>
 __device__ __forceinline__ void search_point(const DevTopo& tp, const RunParams& rp, const BondTable& bt,
                                              const float* xyz, long long frame, int sys, const FrameGrid& g,
                                              const CellT* cells, const float4* pts, int i, int& nhit) {
     float4 p4 = pts[i];
     PointInfo P;
     load_info(tp, rp, sys, p4, P);
-    if (rp.self_pairs) process_self(tp, rp, bt, xyz, frame, P, nhit);
-    int cx = cell_coord(P.x, g.ox, g.inv, g.nx);
-    int cy = cell_coord(P.y, g.oy, g.inv, g.ny);
-    int cz = cell_coord(P.z, g.oz, g.inv, g.nz);
-    // half shell: the rest of the own cell and cell x+1, then rows (y+1, z) and (y-1..y+1, z+1), x-1..x+1
-    for (int run = 0; run < 5; ++run) {
-        int s, e;
-        if (run == 0) {
-            int c_hi = (cz * g.ny + cy) * g.nx + min(cx + 1, g.nx - 1);
-            s = i + 1;
-            e = (int)cells[c_hi];
-        } else {
-            int yy = run == 1 ? cy + 1 : cy + (run - 3);
-            int zz = run == 1 ? cz : cz + 1;
-            if (yy < 0 || yy >= g.ny || zz >= g.nz) continue;
-            int c_lo = (zz * g.ny + yy) * g.nx + max(cx - 1, 0);
-            int c_hi = (zz * g.ny + yy) * g.nx + min(cx + 1, g.nx - 1);
-            s = c_lo ? (int)cells[c_lo - 1] : 0;
-            e = (int)cells[c_hi];
-        }
-        for (int q = s; q < e; ++q) {
-            float4 q4 = pts[q];
-            if (dist2f(P.x, P.y, P.z, q4.x, q4.y, q4.z) > rp.r2f_hi) continue;
-            if (!dist_le(P.x, P.y, P.z, q4.x, q4.y, q4.z, rp.r2)) continue;
-            PointInfo Q;
-            load_info(tp, rp, sys, q4, Q);
-            process_pair(tp, rp, bt, xyz, frame, P, Q, nhit);
-        }
-    }
+    if (rp.self_pairs) process_self<PBC>(tp, rp, bt, xyz, frame, P, nhit, g.p.box);
+    for_each_partner<PBC>(g, cells, i, P.x, P.y, P.z, [&](int q) {
+        const float4 q4 = pts[q];
+        if (!within<PBC>(P.x, P.y, P.z, q4.x, q4.y, q4.z, rp.r2f_hi, rp.r2, g.p)) return;
+        PointInfo Q;
+        load_info(tp, rp, sys, q4, Q);
+        process_pair<PBC>(tp, rp, bt, xyz, frame, P, Q, nhit, g.p.box);
+    });
 }
 
 __device__ __forceinline__ void flush_hits(const BondTable& bt, int nhit) {

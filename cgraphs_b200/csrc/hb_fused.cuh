@@ -135,7 +135,7 @@ __device__ void block_scan_cells(unsigned short* cells, int n, FusedShared* sh) 
 }
 
 // sort `n` points (src(i)) into the cells of g: zero, count, scan, scatter. After return cells[c] is the END of cell c.
-template <typename Src>
+template <bool PBC, typename Src>
 __device__ void block_cell_sort(const FrameGrid& g, unsigned short* cells, float4* dst, int n, Src src, FusedShared* sh) {
     unsigned* words = reinterpret_cast<unsigned*>(cells);
     const int nwords = (g.ncell + 2) >> 1;
@@ -143,49 +143,31 @@ __device__ void block_cell_sort(const FrameGrid& g, unsigned short* cells, float
     consumer_sync();
     for (int i = threadIdx.x; i < n; i += FUSED_CONSUMERS) {
         float4 p = src(i);
-        cell_add(words, cell_of(g, p.x, p.y, p.z));
+        cell_add(words, cell_of<PBC>(g, p.x, p.y, p.z));
     }
     consumer_sync();
     block_scan_cells(cells, g.ncell, sh);
     for (int i = threadIdx.x; i < n; i += FUSED_CONSUMERS) {
         float4 p = src(i);
-        dst[cell_add(words, cell_of(g, p.x, p.y, p.z))] = p;
+        dst[cell_add(words, cell_of<PBC>(g, p.x, p.y, p.z))] = p;
     }
     consumer_sync();
 }
 
-// point pairs (i, q), i < q in cell order, that pass the exact DIST test: half shell of point i
+// point pairs (i, q), i < q in cell order, that pass the exact DIST test
+template <bool PBC>
 __device__ __forceinline__ void collect_pairs(const RunParams& rp, const FrameGrid& g, const unsigned short* cells,
                                               const float4* pts, int i, unsigned* pairs, int pair_cap, int* n_pairs) {
     const float4 p = pts[i];
-    const int cx = cell_coord(p.x, g.ox, g.inv, g.nx);
-    const int cy = cell_coord(p.y, g.oy, g.inv, g.ny);
-    const int cz = cell_coord(p.z, g.oz, g.inv, g.nz);
-    const int xl = max(cx - 1, 0), xh = min(cx + 1, g.nx - 1);
-#pragma unroll 1
-    for (int run = 0; run < 5; ++run) {
-        int s, e;
-        if (run == 0) {
-            s = i + 1;
-            e = (int)cells[(cz * g.ny + cy) * g.nx + xh];
-        } else {
-            const int yy = run == 1 ? cy + 1 : cy + (run - 3);
-            const int zz = run == 1 ? cz : cz + 1;
-            if (yy < 0 || yy >= g.ny || zz >= g.nz) continue;
-            const int row = (zz * g.ny + yy) * g.nx;
-            s = (row + xl) ? (int)cells[row + xl - 1] : 0;
-            e = (int)cells[row + xh];
-        }
-        for (int q = s; q < e; ++q) {
-            const float4 q4 = pts[q];
-            if (dist2f(p.x, p.y, p.z, q4.x, q4.y, q4.z) > rp.r2f_hi) continue;
-            if (!dist_le(p.x, p.y, p.z, q4.x, q4.y, q4.z, rp.r2)) continue;
-            const int k = atomicAdd(n_pairs, 1);
-            if (k < pair_cap) pairs[k] = (unsigned)i | ((unsigned)q << 16);
-        }
-    }
+    for_each_partner<PBC>(g, cells, i, p.x, p.y, p.z, [&](int q) {
+        const float4 q4 = pts[q];
+        if (!within<PBC>(p.x, p.y, p.z, q4.x, q4.y, q4.z, rp.r2f_hi, rp.r2, g.p)) return;
+        const int k = atomicAdd(n_pairs, 1);
+        if (k < pair_cap) pairs[k] = (unsigned)i | ((unsigned)q << 16);
+    });
 }
 
+template <bool PBC>
 __global__ void __launch_bounds__(FUSED_THREADS, 4) k_frame_fused(BatchView bv, DevTopo tp, RunParams rp, BondTable bt, FusedCfg fc) {
     extern __shared__ __align__(16) unsigned char smem[];
     FusedShared* sh = reinterpret_cast<FusedShared*>(smem);
@@ -295,6 +277,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_frame_fused(BatchView bv, 
         float x = p[0], y = p[1], z = p[2];
         const int multi = (k.x >= 0) + (k.y >= 0) + ((wa && k.z >= 0) ? 1 : 0);
         spos[i] = make_float4(x, y, z, __int_as_float(i | (multi > 1 ? SELF_TAG : 0)));
+        if constexpr (PBC) {   // fractional coordinates relative to the first selection point, wrapped
+            PbcGrid pg;
+            pg.box = load_box(bv.box + 9ll * b);
+            pg.ia = 1.0f / pg.box.ax; pg.ib = 1.0f / pg.box.by; pg.ic = 1.0f / pg.box.cz;
+            const float* r = xyz + 3ll * tp.sel_atom[s0];
+            float ra, rb, rc, sa, sb, sc;
+            frac_coords(pg, r[0], r[1], r[2], ra, rb, rc);
+            frac_coords(pg, x, y, z, sa, sb, sc);
+            x = sa - ra; y = sb - rb; z = sc - rc;
+            x -= rintf(x); y -= rintf(y); z -= rintf(z);
+        }
         mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
         mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
     }
@@ -315,7 +308,23 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_frame_fused(BatchView bv, 
             for (int w = 1; w < FUSED_CWARPS; ++w) { a = fminf(a, sh->red[w][k]); c = fmaxf(c, sh->red[w][3 + k]); }
             sh->lo[k] = a; sh->hi[k] = c;
         }
-        if (wa) {
+        if constexpr (PBC) {
+            PbcGrid pg;
+            pg.box = load_box(bv.box + 9ll * b);
+            pg.ia = 1.0f / pg.box.ax; pg.ib = 1.0f / pg.box.by; pg.ic = 1.0f / pg.box.cz;
+            float sR[3] = {NAN, NAN, NAN};
+            if (nsel > 0) {
+                const float* r = xyz + 3ll * tp.sel_atom[s0];
+                frac_coords(pg, r[0], r[1], r[2], sR[0], sR[1], sR[2]);
+            }
+            if (wa) {
+                make_grid_pbc(sh->g1, pg.box, sR, sh->lo, sh->hi, rp.cell1, rp.cell1, fc.cell_cap);
+                make_grid_pbc(sh->g2, pg.box, sR, sh->lo, sh->hi, rp.around_f, rp.cell2, fc.cell_cap);
+            } else {
+                make_grid_pbc(sh->g2, pg.box, sR, sh->lo, sh->hi, 0.f, rp.cell2, fc.cell_cap);
+                sh->g1 = sh->g2;
+            }
+        } else if (wa) {
             make_grid(sh->g1, sh->lo, sh->hi, rp.cell1, rp.cell1, fc.cell_cap);
             make_grid(sh->g2, sh->lo, sh->hi, rp.around_f, rp.cell2, fc.cell_cap);
         } else {
@@ -330,18 +339,28 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_frame_fused(BatchView bv, 
     if (scan_waters) {
         const FrameGrid g1 = sh->g1;
         for (int i = tid; i < (g1.ncell + 31) / 32; i += FUSED_CONSUMERS) near[i] = 0u;
-        block_cell_sort(g1, cells, sorted1, nsel, [&](int i) { return spos[i]; }, sh);   // (syncs cover the zeroing)
+        block_cell_sort<PBC>(g1, cells, sorted1, nsel, [&](int i) { return spos[i]; }, sh);   // (syncs cover the zeroing)
         for (int i = tid; i < nsel; i += FUSED_CONSUMERS) {
             const float4 p = spos[i];
-            const int cx = cell_coord(p.x, g1.ox, g1.inv, g1.nx);
-            const int cy = cell_coord(p.y, g1.oy, g1.inv, g1.ny);
-            const int cz = cell_coord(p.z, g1.oz, g1.inv, g1.nz);
-            for (int zz = max(cz - 1, 0); zz <= min(cz + 1, g1.nz - 1); ++zz)
-                for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g1.ny - 1); ++yy)
-                    for (int xx = max(cx - 1, 0); xx <= min(cx + 1, g1.nx - 1); ++xx) {
-                        const int c = (zz * g1.ny + yy) * g1.nx + xx;
-                        atomicOr(&near[c >> 5], 1u << (c & 31));
-                    }
+            int cx, cy, cz;
+            cell3<PBC>(g1, p.x, p.y, p.z, cx, cy, cz);
+            if constexpr (PBC) {
+                const AxisList zl = axis_neighbors(cz, g1.nz, g1.p.per[2]), yl = axis_neighbors(cy, g1.ny, g1.p.per[1]),
+                               xl = axis_neighbors(cx, g1.nx, g1.p.per[0]);
+                for (int a = 0; a < zl.n; ++a)
+                    for (int bb = 0; bb < yl.n; ++bb)
+                        for (int k = 0; k < xl.n; ++k) {
+                            const int c = (zl.v[a] * g1.ny + yl.v[bb]) * g1.nx + xl.v[k];
+                            atomicOr(&near[c >> 5], 1u << (c & 31));
+                        }
+            } else {
+                for (int zz = max(cz - 1, 0); zz <= min(cz + 1, g1.nz - 1); ++zz)
+                    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g1.ny - 1); ++yy)
+                        for (int xx = max(cx - 1, 0); xx <= min(cx + 1, g1.nx - 1); ++xx) {
+                            const int c = (zz * g1.ny + yy) * g1.nx + xx;
+                            atomicOr(&near[c >> 5], 1u << (c & 31));
+                        }
+            }
         }
         consumer_sync();
         phase_done(1);
@@ -357,7 +376,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_frame_fused(BatchView bv, 
             float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
             if (lane < count) {
                 c = wc[first + lane];
-                local = water_is_local(g1, cells, sorted1, c.x, c.y, c.z, rp);
+                local = water_is_local<PBC>(g1, cells, sorted1, c.x, c.y, c.z, rp);
             }
             const unsigned m = __ballot_sync(0xffffffffu, local);
             if (m) {
@@ -398,10 +417,20 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_frame_fused(BatchView bv, 
                 const float* f = xyz + 3ll * tp.wat_atom[w0 + i];
                 x = f[0]; y = f[1]; z = f[2];
             }
-            bool is_cand = live && x >= lox && x <= hix && y >= loy && y <= hiy && z >= loz && z <= hiz;
-            if (is_cand) {
-                const int c = cell_of(g1, x, y, z);
-                is_cand = (near[c >> 5] >> (c & 31)) & 1u;
+            bool is_cand;
+            if constexpr (PBC) {
+                int cx, cy, cz;
+                is_cand = cell3_pbc(g1, x, y, z, cx, cy, cz) && live;
+                if (is_cand) {
+                    const int c = (cz * g1.ny + cy) * g1.nx + cx;
+                    is_cand = (near[c >> 5] >> (c & 31)) & 1u;
+                }
+            } else {
+                is_cand = live && x >= lox && x <= hix && y >= loy && y <= hiy && z >= loz && z <= hiz;
+                if (is_cand) {
+                    const int c = cell_of<false>(g1, x, y, z);
+                    is_cand = (near[c >> 5] >> (c & 31)) & 1u;
+                }
             }
             const unsigned m = __ballot_sync(0xffffffffu, is_cand);
             if (m) {
@@ -428,7 +457,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_frame_fused(BatchView bv, 
     // ---- phase C: pair search over selection + local waters --------------------------------------------
     const int nlw = sh->n_lw;
     const int np = nsel + nlw;
-    block_cell_sort(sh->g2, cells, psorted, np, [&](int i) { return i < nsel ? spos[i] : lw[i - nsel]; }, sh);
+    block_cell_sort<PBC>(sh->g2, cells, psorted, np, [&](int i) { return i < nsel ? spos[i] : lw[i - nsel]; }, sh);
     int nhit = 0;
     const FrameGrid g2 = sh->g2;
     phase_done(4);
@@ -436,13 +465,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_frame_fused(BatchView bv, 
     const float ct = rp.cos_threshold;
     // C1: every point walks its half shell and appends the point pairs within `distance` to one list
     for (int i = tid; i < np; i += FUSED_CONSUMERS) {
-        collect_pairs(rp, g2, cells, psorted, i, pairs, fc.pair_cap, &sh->n_pairs);
+        collect_pairs<PBC>(rp, g2, cells, psorted, i, pairs, fc.pair_cap, &sh->n_pairs);
         if (rp.self_pairs) {
             const float4 p4 = psorted[i];
             if (__float_as_int(p4.w) & SELF_TAG) {
                 PointInfo P;
                 load_info(tp, rp, sys, p4, P);
-                process_self(tp, rp, bt, xyz, frame, P, nhit);
+                process_self<PBC>(tp, rp, bt, xyz, frame, P, nhit, g2.p.box);
             }
         }
     }
@@ -473,10 +502,10 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_frame_fused(BatchView bv, 
                 const unsigned need = rules_need(rules);
                 if (tp.h_wide) {                        // hydrogen lists too long for the inline tables: CSR walk here
                     unsigned f = 0;
-                    if ((need & 1u) && any_h(tp, xyz, P.don, P, Q, ct)) f |= 1u;
-                    if ((need & 2u) && any_h(tp, xyz, Q.don, Q, P, ct)) f |= 2u;
-                    if ((need & 4u) && any_h(tp, xyz, P.wat, P, Q, ct)) f |= 4u;
-                    if ((need & 8u) && any_h(tp, xyz, Q.wat, Q, P, ct)) f |= 8u;
+                    if ((need & 1u) && any_h<PBC>(tp, xyz, P.don, P, Q, ct, g2.p.box)) f |= 1u;
+                    if ((need & 2u) && any_h<PBC>(tp, xyz, Q.don, Q, P, ct, g2.p.box)) f |= 2u;
+                    if ((need & 4u) && any_h<PBC>(tp, xyz, P.wat, P, Q, ct, g2.p.box)) f |= 4u;
+                    if ((need & 8u) && any_h<PBC>(tp, xyz, Q.wat, Q, P, ct, g2.p.box)) f |= 8u;
                     pflags[tid] = f;
                 } else {
                     const int lists[4] = {P.hd, Q.hd, P.hw, Q.hw};
@@ -516,7 +545,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_frame_fused(BatchView bv, 
             const float4 a4 = psorted[pq & 0xffffu], b4 = psorted[pq >> 16];
             const float4 own = (f & 1u) ? b4 : a4, oth = (f & 1u) ? a4 : b4;
             const float* h = xyz + 3ll * (long long)tk.y;
-            if (ang_ok(oth.x, oth.y, oth.z, h[0], h[1], h[2], own.x, own.y, own.z, ct)) atomicOr(&pflags[kk], 1u << f);
+            if (ang_ok<PBC>(oth.x, oth.y, oth.z, h[0], h[1], h[2], own.x, own.y, own.z, ct, g2.p.box)) atomicOr(&pflags[kk], 1u << f);
         }
         consumer_sync();
         // (c) entry pairs whose hydrogens passed

@@ -22,6 +22,13 @@ __global__ void k_init_frames(BatchView bv) {
 // ------------------------------------------------------------------------------------------------
 // K1: gather selection points, per-frame bounding box
 // ------------------------------------------------------------------------------------------------
+// fractional coordinates of the selection's reference point (its first point) and the lattice of frame b
+__device__ __forceinline__ void frame_lattice(const BatchView& bv, int b, PbcGrid& p) {
+    p.box = load_box(bv.box + 9ll * b);
+    p.ia = 1.0f / p.box.ax; p.ib = 1.0f / p.box.by; p.ic = 1.0f / p.box.cz;
+}
+
+template <bool PBC>
 __global__ void __launch_bounds__(256) k_gather_sel(BatchView bv, DevTopo tp) {
     int b = blockIdx.y;
     int sys;
@@ -34,6 +41,18 @@ __global__ void __launch_bounds__(256) k_gather_sel(BatchView bv, DevTopo tp) {
         const float* p = xyz + 3ll * tp.sel_atom[s0 + i];
         x = p[0]; y = p[1]; z = p[2];
         bv.selpos[(size_t)b * bv.max_sel + i] = make_float4(x, y, z, __int_as_float(i));
+    }
+    if constexpr (PBC) {       // bounding box in fractional coordinates relative to the first selection point
+        if (live) {
+            PbcGrid pg;
+            frame_lattice(bv, b, pg);
+            const float* r = xyz + 3ll * tp.sel_atom[s0];
+            float ra, rb, rc, sa, sb, sc;
+            frac_coords(pg, r[0], r[1], r[2], ra, rb, rc);
+            frac_coords(pg, x, y, z, sa, sb, sc);
+            x = sa - ra; y = sb - rb; z = sc - rc;
+            x -= rintf(x); y -= rintf(y); z -= rintf(z);
+        }
     }
     float mn[3] = {live ? x : INFINITY, live ? y : INFINITY, live ? z : INFINITY};
     float mx[3] = {live ? x : -INFINITY, live ? y : -INFINITY, live ? z : -INFINITY};
@@ -62,7 +81,8 @@ __global__ void __launch_bounds__(256) k_gather_sel(BatchView bv, DevTopo tp) {
 // true neighbour pair by more than one cell; grids are capped at 1024 cells per axis and at
 // cell_cap cells in total by coarsening (coarser cells stay correct with a 27-cell neighbourhood).
 // ------------------------------------------------------------------------------------------------
-__global__ void k_grid_setup(BatchView bv, RunParams rp) {
+template <bool PBC>
+__global__ void k_grid_setup(BatchView bv, DevTopo tp, RunParams rp) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= bv.n_frames) return;
     FrameState& f = bv.fs[b];
@@ -70,12 +90,31 @@ __global__ void k_grid_setup(BatchView bv, RunParams rp) {
         f.lo[k] = ord2f(f.bb_min[k]);
         f.hi[k] = ord2f(f.bb_max[k]);
     }
-    if (rp.method == HB_METHOD_WATER_AROUND) {
-        make_grid(f.g1, f.lo, f.hi, rp.cell1, rp.cell1, bv.cell_cap);
-        make_grid(f.g2, f.lo, f.hi, rp.around_f, rp.cell2, bv.cell_cap);
+    if constexpr (PBC) {
+        int sys;
+        const float* xyz = frame_xyz(bv, tp, b, sys);
+        PbcGrid pg;
+        frame_lattice(bv, b, pg);
+        float sR[3] = {NAN, NAN, NAN};
+        if (tp.sys_sel_off[sys + 1] > tp.sys_sel_off[sys]) {
+            const float* r = xyz + 3ll * tp.sel_atom[tp.sys_sel_off[sys]];
+            frac_coords(pg, r[0], r[1], r[2], sR[0], sR[1], sR[2]);
+        }
+        if (rp.method == HB_METHOD_WATER_AROUND) {
+            make_grid_pbc(f.g1, pg.box, sR, f.lo, f.hi, rp.cell1, rp.cell1, bv.cell_cap);
+            make_grid_pbc(f.g2, pg.box, sR, f.lo, f.hi, rp.around_f, rp.cell2, bv.cell_cap);
+        } else {
+            make_grid_pbc(f.g2, pg.box, sR, f.lo, f.hi, 0.f, rp.cell2, bv.cell_cap);
+            f.g1 = f.g2;
+        }
     } else {
-        make_grid(f.g2, f.lo, f.hi, 0.f, rp.cell2, bv.cell_cap);
-        f.g1 = f.g2;
+        if (rp.method == HB_METHOD_WATER_AROUND) {
+            make_grid(f.g1, f.lo, f.hi, rp.cell1, rp.cell1, bv.cell_cap);
+            make_grid(f.g2, f.lo, f.hi, rp.around_f, rp.cell2, bv.cell_cap);
+        } else {
+            make_grid(f.g2, f.lo, f.hi, 0.f, rp.cell2, bv.cell_cap);
+            f.g1 = f.g2;
+        }
     }
 }
 
@@ -103,6 +142,7 @@ __global__ void __launch_bounds__(256) k_zero_cells(BatchView bv, int which) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= g.ncell; i += gridDim.x * blockDim.x) cells[i] = 0;
 }
 
+template <bool PBC>
 __global__ void __launch_bounds__(256) k_count(BatchView bv, DevTopo tp, int which) {
     int b = blockIdx.y;
     int n = n_points_of(bv, tp, b, which);
@@ -110,7 +150,7 @@ __global__ void __launch_bounds__(256) k_count(BatchView bv, DevTopo tp, int whi
     int* cells = (which == 1 ? bv.cells1 : bv.cells2) + (size_t)b * (bv.cell_cap + 1);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 p = load_point(bv, tp, b, i);
-        atomicAdd(&cells[cell_of(g, p.x, p.y, p.z)], 1);
+        atomicAdd(&cells[cell_of<PBC>(g, p.x, p.y, p.z)], 1);
     }
 }
 
@@ -159,6 +199,7 @@ __global__ void __launch_bounds__(1024) k_scan(BatchView bv, int which) {
 }
 
 // after this kernel cells[c] holds the END of cell c; its start is cells[c-1] (0 for c = 0)
+template <bool PBC>
 __global__ void __launch_bounds__(256) k_scatter(BatchView bv, DevTopo tp, int which) {
     int b = blockIdx.y;
     int n = n_points_of(bv, tp, b, which);
@@ -167,13 +208,14 @@ __global__ void __launch_bounds__(256) k_scatter(BatchView bv, DevTopo tp, int w
     float4* dst = which == 1 ? bv.sorted1 + (size_t)b * bv.max_sel : bv.sorted2 + (size_t)b * (bv.max_sel + bv.max_wat);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 p = load_point(bv, tp, b, i);
-        dst[atomicAdd(&cells[cell_of(g, p.x, p.y, p.z)], 1)] = p;
+        dst[atomicAdd(&cells[cell_of<PBC>(g, p.x, p.y, p.z)], 1)] = p;
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K6: local waters = waters with DIST <= around_radius to any selection entry (hbond.py:249-252)
 // ------------------------------------------------------------------------------------------------
+template <bool PBC>
 __global__ void __launch_bounds__(256) k_local_water(BatchView bv, DevTopo tp, RunParams rp) {
     int b = blockIdx.y;
     int sys;
@@ -186,12 +228,18 @@ __global__ void __launch_bounds__(256) k_local_water(BatchView bv, DevTopo tp, R
     if (w0 + i < w1) {
         const float* p = xyz + 3ll * tp.wat_atom[w0 + i];
         x = p[0]; y = p[1]; z = p[2];
-        float a = rp.around_f;
-        bool inside = x >= f.lo[0] - a && x <= f.hi[0] + a && y >= f.lo[1] - a && y <= f.hi[1] + a &&
-                      z >= f.lo[2] - a && z <= f.hi[2] + a;
+        bool inside;
+        if constexpr (PBC) {
+            int cx, cy, cz;
+            inside = cell3_pbc(f.g1, x, y, z, cx, cy, cz);
+        } else {
+            float a = rp.around_f;
+            inside = x >= f.lo[0] - a && x <= f.hi[0] + a && y >= f.lo[1] - a && y <= f.hi[1] + a &&
+                     z >= f.lo[2] - a && z <= f.hi[2] + a;
+        }
         if (inside)
-            local = water_is_local(f.g1, bv.cells1 + (size_t)b * (bv.cell_cap + 1),
-                                   bv.sorted1 + (size_t)b * bv.max_sel, x, y, z, rp);
+            local = water_is_local<PBC>(f.g1, bv.cells1 + (size_t)b * (bv.cell_cap + 1),
+                                        bv.sorted1 + (size_t)b * bv.max_sel, x, y, z, rp);
     }
     unsigned m = __ballot_sync(0xffffffffu, local);
     if (m) {
@@ -206,6 +254,7 @@ __global__ void __launch_bounds__(256) k_local_water(BatchView bv, DevTopo tp, R
     }
 }
 
+template <bool PBC>
 __global__ void __launch_bounds__(128) k_pairs(BatchView bv, DevTopo tp, RunParams rp, BondTable bt) {
     int b = blockIdx.y;
     const FrameState& f = bv.fs[b];
@@ -216,7 +265,7 @@ __global__ void __launch_bounds__(128) k_pairs(BatchView bv, DevTopo tp, RunPara
     long long frame = bv.frame0 + b;
     int nhit = 0;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < f.n_points; i += gridDim.x * blockDim.x)
-        search_point(tp, rp, bt, xyz, frame, sys, f.g2, cells, pts, i, nhit);
+        search_point<PBC>(tp, rp, bt, xyz, frame, sys, f.g2, cells, pts, i, nhit);
     flush_hits(bt, nhit);
 }
 

@@ -117,8 +117,11 @@ struct hb_ctx {
     cudaEvent_t ev_run0{}, ev_run1{};
     long long batch_counter = 0;
 
-    struct Slot { bool busy; const float* d_xyz; long long f0; int nf; long long apf; size_t bytes; };
-    Slot slots[2] = {{false, nullptr, 0, 0, 0, 0}, {false, nullptr, 0, 0, 0, 0}};
+    struct Slot { bool busy; const float* d_xyz; long long f0; int nf; long long apf; size_t bytes; const float* d_box; };
+    Slot slots[2] = {{false, nullptr, 0, 0, 0, 0, nullptr}, {false, nullptr, 0, 0, 0, 0, nullptr}};
+    float* d_box[2] = {nullptr, nullptr};      // lattice vectors of the frames in each input buffer
+    float* h_box[2] = {nullptr, nullptr};      // pinned staging for them
+    size_t box_cap = 0;                        // frames
 
     // results
     long long n_bonds = 0;
@@ -283,6 +286,13 @@ static void free_run(hb_ctx* ctx) {
         ctx->d_in[k] = nullptr;
         ctx->h_stage[k] = nullptr;
     }
+    for (int k = 0; k < 2; ++k) {
+        if (ctx->d_box[k]) cudaFree(ctx->d_box[k]);
+        if (ctx->h_box[k]) cudaFreeHost(ctx->h_box[k]);
+        ctx->d_box[k] = nullptr;
+        ctx->h_box[k] = nullptr;
+    }
+    ctx->box_cap = 0;
     if (ctx->bt.keys) cudaFree(ctx->bt.keys);
     if (ctx->bt.bits) cudaFree(ctx->bt.bits);
     if (ctx->bt.n_keys) cudaFree(ctx->bt.n_keys);
@@ -495,13 +505,18 @@ int hb_set_params(hb_ctx* ctx, const hb_params* p) {
     if (p->method != HB_METHOD_IN_SELECTION && p->method != HB_METHOD_WATER_AROUND) return fail(ctx, HB_ERR_ARG, "unknown method");
     if (p->method == HB_METHOD_WATER_AROUND && (!(p->around_radius >= 0.0) || !std::isfinite(p->around_radius)))
         return fail(ctx, HB_ERR_ARG, "around_radius must be >= 0");
-    if (p->pbc_mode != HB_PBC_NONE) return fail(ctx, HB_ERR_ARG, "pbc_mode: only HB_PBC_NONE is implemented in this build");
+    if (p->pbc_mode != HB_PBC_NONE && p->pbc_mode != HB_PBC_ORTHO && p->pbc_mode != HB_PBC_TRICLINIC)
+        return fail(ctx, HB_ERR_ARG, "unknown pbc_mode");
     ctx->prm = *p;
     RunParams& r = ctx->rp;
     r.r2 = p->distance * p->distance;
     r.around2 = p->around_radius * p->around_radius;
-    r.r2f_hi = nextafterf((float)(r.r2 * (1.0 + 1e-5)), INFINITY);
-    r.around2f_hi = nextafterf((float)(r.around2 * (1.0 + 1e-5)), INFINITY);
+    // float32 pre-filter bounds: a little above the float64 thresholds (more under minimum image, where the
+    // float32 reduction of the difference vector adds rounding of its own)
+    const double slack = p->pbc_mode != HB_PBC_NONE ? 1e-4 : 1e-5;
+    r.r2f_hi = nextafterf((float)(r.r2 * (1.0 + slack)), INFINITY);
+    r.around2f_hi = nextafterf((float)(r.around2 * (1.0 + slack)), INFINITY);
+    r.pbc = p->pbc_mode;
     r.cell2 = (float)(p->distance * 1.001);
     r.cell1 = (float)(std::max(p->around_radius, 1e-3) * 1.001);
     r.around_f = (float)(p->around_radius * 1.001 + 1e-6);
@@ -560,7 +575,8 @@ static bool plan_fused(hb_ctx* ctx, int grow = 0) {
     off += (size_t)2 * FUSED_MAX_STAGES * 8;
     fc.smem_bytes = (unsigned)off;
     if (fc.smem_bytes > 112 * 1024) return false;                     // keep at least two frames resident per SM
-    if (cudaFuncSetAttribute(k_frame_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fc.smem_bytes) != cudaSuccess) {
+    if (cudaFuncSetAttribute(k_frame_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fc.smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(k_frame_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fc.smem_bytes) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
@@ -709,7 +725,9 @@ static int ensure_scratch(hb_ctx* ctx) {
 }
 
 // launch the kernel pipeline for one batch resident at d_xyz
-static int run_general(hb_ctx* ctx, BatchView bv) {
+}  // extern "C" (templates need C++ linkage)
+template <bool PBC>
+static int run_general_t(hb_ctx* ctx, BatchView bv) {
     cudaStream_t st = ctx->s_compute;
     const RunParams& rp = ctx->rp;
     const DevTopo& tp = ctx->tp;
@@ -720,33 +738,38 @@ static int run_general(hb_ctx* ctx, BatchView bv) {
     if (wa) CK(cudaMemsetAsync(bv.cells1, 0, cells_bytes, st));
     CK(cudaMemsetAsync(bv.cells2, 0, cells_bytes, st));
     dim3 gsel((bv.max_sel + 255) / 256, nf), gwat((bv.max_wat + 255) / 256, nf);
-    if (bv.max_sel > 0) { KTimer t(ctx, KC_GATHER); k_gather_sel<<<gsel, 256, 0, st>>>(bv, tp); }
-    { KTimer t(ctx, KC_GRID); k_grid_setup<<<(nf + 127) / 128, 128, 0, st>>>(bv, rp); }
+    if (bv.max_sel > 0) { KTimer t(ctx, KC_GATHER); k_gather_sel<PBC><<<gsel, 256, 0, st>>>(bv, tp); }
+    { KTimer t(ctx, KC_GRID); k_grid_setup<PBC><<<(nf + 127) / 128, 128, 0, st>>>(bv, tp, rp); }
     if (wa && bv.max_sel > 0 && bv.max_wat > 0) {
-        { KTimer t(ctx, KC_COUNT); k_count<<<gsel, 256, 0, st>>>(bv, tp, 1); }
+        { KTimer t(ctx, KC_COUNT); k_count<PBC><<<gsel, 256, 0, st>>>(bv, tp, 1); }
         { KTimer t(ctx, KC_SCAN); k_scan<<<nf, 1024, 0, st>>>(bv, 1); }
-        { KTimer t(ctx, KC_SCATTER); k_scatter<<<gsel, 256, 0, st>>>(bv, tp, 1); }
-        { KTimer t(ctx, KC_LOCAL); k_local_water<<<gwat, 256, 0, st>>>(bv, tp, rp); }
+        { KTimer t(ctx, KC_SCATTER); k_scatter<PBC><<<gsel, 256, 0, st>>>(bv, tp, 1); }
+        { KTimer t(ctx, KC_LOCAL); k_local_water<PBC><<<gwat, 256, 0, st>>>(bv, tp, rp); }
     }
     int maxp = bv.max_sel + (wa ? bv.max_wat : 0);
     if (maxp > 0) {
         dim3 gall((maxp + 255) / 256, nf);
-        { KTimer t(ctx, KC_COUNT); k_count<<<gall, 256, 0, st>>>(bv, tp, 2); }
+        { KTimer t(ctx, KC_COUNT); k_count<PBC><<<gall, 256, 0, st>>>(bv, tp, 2); }
         { KTimer t(ctx, KC_SCAN); k_scan<<<nf, 1024, 0, st>>>(bv, 2); }
-        { KTimer t(ctx, KC_SCATTER); k_scatter<<<gall, 256, 0, st>>>(bv, tp, 2); }
+        { KTimer t(ctx, KC_SCATTER); k_scatter<PBC><<<gall, 256, 0, st>>>(bv, tp, 2); }
         dim3 gp((maxp + 127) / 128, nf);
-        { KTimer t(ctx, KC_PAIRS); k_pairs<<<gp, 128, 0, st>>>(bv, tp, rp, ctx->bt); }
+        { KTimer t(ctx, KC_PAIRS); k_pairs<PBC><<<gp, 128, 0, st>>>(bv, tp, rp, ctx->bt); }
     }
     CK(cudaGetLastError());
     return HB_OK;
+}
+extern "C" {
+static int run_general(hb_ctx* ctx, const BatchView& bv) {
+    return ctx->rp.pbc != HB_PBC_NONE ? run_general_t<true>(ctx, bv) : run_general_t<false>(ctx, bv);
 }
 
 // launch the kernels for one batch resident at d_xyz: one fused launch, or the general pipeline over
 // sub-batches of at most `batch_frames` frames (the capacity of its scratch)
 static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, long long atoms_per_frame,
-                     size_t xyz_bytes, bool allow_fused = true) {
+                     size_t xyz_bytes, const float* d_box, bool allow_fused = true) {
     BatchView bv = ctx->bv;
     bv.xyz = d_xyz;
+    bv.box = d_box;
     bv.frame0 = frame0;
     bv.n_frames = nf;
     bv.atoms_per_frame = atoms_per_frame;
@@ -758,19 +781,25 @@ static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, 
         FusedCfg fc = ctx->fc;
         fc.buf_begin = (unsigned long long)(uintptr_t)d_xyz;
         fc.buf_end = fc.buf_begin + xyz_bytes;
-        { KTimer t(ctx, KC_FUSED); k_frame_fused<<<nf, FUSED_THREADS, fc.smem_bytes, st>>>(bv, ctx->tp, ctx->rp, ctx->bt, fc); }
+        {
+            KTimer t(ctx, KC_FUSED);
+            if (ctx->rp.pbc != HB_PBC_NONE) k_frame_fused<true><<<nf, FUSED_THREADS, fc.smem_bytes, st>>>(bv, ctx->tp, ctx->rp, ctx->bt, fc);
+            else k_frame_fused<false><<<nf, FUSED_THREADS, fc.smem_bytes, st>>>(bv, ctx->tp, ctx->rp, ctx->bt, fc);
+        }
         CK(cudaGetLastError());
         ctx->tm.fused_frames += nf;
     } else {
         int rc = ensure_scratch(ctx);
         if (rc) return rc;
         bv = ctx->bv;                     // scratch pointers
+        bv.box = d_box;
         bv.atoms_per_frame = atoms_per_frame;
         bv.atom_base = bv.structure_batch ? ctx->h_sys_atom_off[frame0] : 0;
         for (int done = 0; done < nf; done += ctx->batch_frames) {
             bv.n_frames = std::min(nf - done, ctx->batch_frames);
             bv.frame0 = frame0 + done;
             bv.xyz = bv.structure_batch ? d_xyz : d_xyz + (size_t)done * atoms_per_frame * 3;
+            bv.box = d_box ? d_box + (size_t)done * 9 : nullptr;
             if ((rc = run_general(ctx, bv))) return rc;
         }
     }
@@ -810,7 +839,7 @@ static int full_verify(hb_ctx* ctx) {
             for (auto& sl : ctx->slots)
                 if (sl.busy) {
                     long long frames_before = ctx->tm.frames, fused_before = ctx->tm.fused_frames;
-                    if ((rc = run_batch(ctx, sl.d_xyz, sl.f0, sl.nf, sl.apf, sl.bytes))) return rc;
+                    if ((rc = run_batch(ctx, sl.d_xyz, sl.f0, sl.nf, sl.apf, sl.bytes, sl.d_box))) return rc;
                     ctx->tm.frames = frames_before;                 // a re-run is not new work
                     ctx->tm.fused_frames = ctx->fused_active ? fused_before : fused_before - sl.nf;
                 }
@@ -830,12 +859,13 @@ static int acquire_slot(hb_ctx* ctx, int k) {
     return HB_OK;
 }
 
-static int launch_in_slot(hb_ctx* ctx, int k, const float* d_xyz, long long f0, int nf, long long apf, size_t bytes) {
-    int rc = run_batch(ctx, d_xyz, f0, nf, apf, bytes);
+static int launch_in_slot(hb_ctx* ctx, int k, const float* d_xyz, long long f0, int nf, long long apf, size_t bytes,
+                          const float* d_box) {
+    int rc = run_batch(ctx, d_xyz, f0, nf, apf, bytes, d_box);
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->h_status + 4 * k, ctx->bt.n_keys, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->s_compute));
     CK(cudaEventRecord(ctx->ev_done[k], ctx->s_compute));
-    ctx->slots[k] = hb_ctx::Slot{true, d_xyz, f0, nf, apf, bytes};
+    ctx->slots[k] = hb_ctx::Slot{true, d_xyz, f0, nf, apf, bytes, d_box};
     return HB_OK;
 }
 
@@ -844,6 +874,24 @@ static int check_submit(hb_ctx* ctx, int64_t n_atoms, int64_t n_frames) {
     if (n_frames < 0 || ctx->next_frame + n_frames > ctx->n_frames_total) return fail(ctx, HB_ERR_ARG, "more frames submitted than announced in hb_begin");
     if (!ctx->prm.structure_batch && n_atoms != ctx->h_sys_atom_off[1] - ctx->h_sys_atom_off[0])
         return fail(ctx, HB_ERR_ARG, "n_atoms does not match the topology");
+    return HB_OK;
+}
+
+// lattice vectors of host-supplied frames: lower-triangular rows a, b, c with a positive diagonal, and cut-offs
+// below half of every brick edge so that the sequential minimum-image reduction finds every pair
+static int check_boxes(hb_ctx* ctx, const float* box, long long n_frames) {
+    const double rmax = std::max(ctx->prm.distance, ctx->prm.method == HB_METHOD_WATER_AROUND ? ctx->prm.around_radius : 0.0);
+    for (long long f = 0; f < n_frames; ++f) {
+        const float* b = box + 9 * f;
+        if (b[1] != 0.f || b[2] != 0.f || b[5] != 0.f)
+            return fail(ctx, HB_ERR_ARG, "box: lattice vectors must be lower-triangular rows (a = (ax,0,0), b = (bx,by,0), c = (cx,cy,cz))");
+        if (!(b[0] > 0.f) || !(b[4] > 0.f) || !(b[8] > 0.f) || !std::isfinite(b[0] + b[3] + b[4] + b[6] + b[7] + b[8]))
+            return fail(ctx, HB_ERR_ARG, "box: non-positive or non-finite cell edge");
+        if (ctx->prm.pbc_mode == HB_PBC_ORTHO && (b[3] != 0.f || b[6] != 0.f || b[7] != 0.f))
+            return fail(ctx, HB_ERR_ARG, "box: HB_PBC_ORTHO needs an orthorhombic cell");
+        if (!(2.0 * rmax < std::min(b[0], std::min(b[4], b[8]))))
+            return fail(ctx, HB_ERR_ARG, "box: cut-off radius must stay below half of the smallest cell edge");
+    }
     return HB_OK;
 }
 
@@ -864,10 +912,28 @@ static int next_batch_frames(hb_ctx* ctx, long long f0, long long remaining, boo
 
 int hb_submit_frames(hb_ctx* ctx, const float* xyz, int64_t n_atoms, int64_t n_frames, const float* box) {
     if (!ctx || (!xyz && n_frames > 0)) return HB_ERR_ARG;
-    (void)box;
     int rc = check_submit(ctx, n_atoms, n_frames);
     if (rc) return rc;
+    const bool pbc = ctx->prm.pbc_mode != HB_PBC_NONE;
+    if (pbc) {
+        if (!box) return fail(ctx, HB_ERR_ARG, "hb_submit_frames: pbc_mode needs the lattice vectors of every frame");
+        if ((rc = check_boxes(ctx, box, n_frames))) return rc;
+    }
     CK(cudaSetDevice(ctx->device));
+    if (pbc && ctx->box_cap < (size_t)std::max(ctx->host_batch_frames, 1)) {
+        size_t cap = (size_t)std::max(ctx->host_batch_frames, 1);
+        for (int k = 0; k < 2; ++k) {
+            if (ctx->d_box[k]) cudaFree(ctx->d_box[k]);
+            if (ctx->h_box[k]) cudaFreeHost(ctx->h_box[k]);
+            ctx->d_box[k] = nullptr; ctx->h_box[k] = nullptr;
+        }
+        ctx->box_cap = 0;
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaMalloc((void**)&ctx->d_box[k], cap * 36));
+            CK(cudaHostAlloc((void**)&ctx->h_box[k], cap * 36, cudaHostAllocDefault));
+        }
+        ctx->box_cap = cap;
+    }
     cudaPointerAttributes attr{};
     bool pinned = cudaPointerGetAttributes(&attr, xyz) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
@@ -897,6 +963,10 @@ int hb_submit_frames(hb_ctx* ctx, const float* xyz, int64_t n_atoms, int64_t n_f
             }
             h = ctx->h_stage[k];
         }
+        if (pbc) {
+            memcpy(ctx->h_box[k], box + 9 * done, (size_t)nf * 36);
+            CK(cudaMemcpyAsync(ctx->d_box[k], ctx->h_box[k], (size_t)nf * 36, cudaMemcpyHostToDevice, ctx->s_copy));
+        }
         cudaEvent_t c0 = get_event(ctx), c1 = get_event(ctx);
         cudaEventRecord(c0, ctx->s_copy);
         if (ranged) {      // strided copies: only the atom ranges the search reads, same layout on the device
@@ -914,7 +984,7 @@ int hb_submit_frames(hb_ctx* ctx, const float* xyz, int64_t n_atoms, int64_t n_f
         ctx->pending.push_back({c0, c1, -2});
         CK(cudaEventRecord(ctx->ev_copied[k], ctx->s_copy));
         CK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_copied[k], 0));
-        if ((rc = launch_in_slot(ctx, k, ctx->d_in[k], f0, nf, n_atoms, bytes))) return rc;
+        if ((rc = launch_in_slot(ctx, k, ctx->d_in[k], f0, nf, n_atoms, bytes, pbc ? ctx->d_box[k] : nullptr))) return rc;
         ctx->batch_counter++;
         ctx->next_frame += nf;
         done += nf;
@@ -927,9 +997,10 @@ int hb_submit_frames(hb_ctx* ctx, const float* xyz, int64_t n_atoms, int64_t n_f
 
 int hb_submit_frames_device(hb_ctx* ctx, const float* d_xyz, int64_t n_atoms, int64_t n_frames, const float* d_box) {
     if (!ctx || (!d_xyz && n_frames > 0)) return HB_ERR_ARG;
-    (void)d_box;
     int rc = check_submit(ctx, n_atoms, n_frames);
     if (rc) return rc;
+    const bool pbc = ctx->prm.pbc_mode != HB_PBC_NONE;
+    if (pbc && !d_box) return fail(ctx, HB_ERR_ARG, "hb_submit_frames_device: pbc_mode needs the lattice vectors of every frame");
     CK(cudaSetDevice(ctx->device));
     const float* src = d_xyz;
     long long done = 0;
@@ -939,7 +1010,7 @@ int hb_submit_frames_device(hb_ctx* ctx, const float* d_xyz, int64_t n_atoms, in
         long long atoms = batch_atoms(ctx, f0, nf, n_atoms);
         int k = (int)(ctx->batch_counter & 1);
         if ((rc = acquire_slot(ctx, k))) return rc;
-        if ((rc = launch_in_slot(ctx, k, src, f0, nf, n_atoms, (size_t)atoms * 12))) return rc;
+        if ((rc = launch_in_slot(ctx, k, src, f0, nf, n_atoms, (size_t)atoms * 12, pbc ? d_box + 9 * done : nullptr))) return rc;
         ctx->batch_counter++;
         ctx->next_frame += nf;
         done += nf;

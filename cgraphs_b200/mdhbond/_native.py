@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc"
 
 METHOD_IN_SELECTION = 0
 METHOD_WATER_AROUND = 1
+PBC_NONE, PBC_ORTHO, PBC_TRICLINIC = 0, 1, 2
 
 
 class HbTopology(C.Structure):
@@ -191,20 +192,29 @@ class Context:
     def begin(self, n_frames_total):
         self._ck(self.lib.hb_begin(self.h, int(n_frames_total)), "hb_begin")
 
-    def submit(self, xyz, n_atoms=None):
-        """xyz: float32 host array [F, N, 3] (or ragged flat [sum N, 3] with structure_batch)."""
+    def submit(self, xyz, n_atoms=None, box=None):
+        """xyz: float32 host array [F, N, 3]; box: None or float32 [F, 3, 3] lattice rows (pbc modes)."""
         a = np.ascontiguousarray(xyz, dtype=np.float32)
         if a.ndim == 3:
             nf, na = a.shape[0], a.shape[1]
         else:
             raise ValueError("submit expects [F, N, 3]; use submit_raw for ragged batches")
-        self._ck(self.lib.hb_submit_frames(self.h, a.ctypes.data, na, nf, None), "hb_submit_frames")
+        b = None
+        if box is not None:
+            b = np.ascontiguousarray(box, dtype=np.float32).reshape(nf, 9)
+        self._ck(self.lib.hb_submit_frames(self.h, a.ctypes.data, na, nf, b.ctypes.data if b is not None else None),
+                 "hb_submit_frames")
 
-    def submit_raw(self, ptr, n_atoms, n_frames):
-        self._ck(self.lib.hb_submit_frames(self.h, int(ptr), int(n_atoms), int(n_frames), None), "hb_submit_frames")
+    def submit_raw(self, ptr, n_atoms, n_frames, box=None):
+        b = None
+        if box is not None:
+            b = np.ascontiguousarray(box, dtype=np.float32).reshape(int(n_frames), 9)
+        self._ck(self.lib.hb_submit_frames(self.h, int(ptr), int(n_atoms), int(n_frames),
+                                           b.ctypes.data if b is not None else None), "hb_submit_frames")
 
-    def submit_device(self, dev_ptr, n_atoms, n_frames):
-        self._ck(self.lib.hb_submit_frames_device(self.h, int(dev_ptr), int(n_atoms), int(n_frames), None),
+    def submit_device(self, dev_ptr, n_atoms, n_frames, box_dev_ptr=None):
+        self._ck(self.lib.hb_submit_frames_device(self.h, int(dev_ptr), int(n_atoms), int(n_frames),
+                                                  int(box_dev_ptr) if box_dev_ptr else None),
                  "hb_submit_frames_device")
 
     def sync(self):

@@ -13,7 +13,9 @@ same result objects (``initial_results`` / ``filtered_results`` = ``dict[str, bo
 
 Extra keyword arguments (all optional, parity-preserving defaults): ``device`` (CUDA ordinal),
 ``shard=(rank, world)`` to process only a contiguous frame block per rank and merge bond keys with one
-all-gather, ``cos_threshold`` to pin the calibrated angle threshold, ``batch_bytes``, ``native_options``
+all-gather, ``pbc`` (False = the reference's behaviour: no periodic images; True / "ortho" / "triclinic" =
+minimum-image search with the cell of every frame, an extension the reference does not have - DESIGN.md 2),
+``cos_threshold`` to pin the calibrated angle threshold, ``batch_bytes``, ``native_options``
 (dict passed to ``hb_set_option``, e.g. ``{"fused": 0}`` to force the general kernels).
 
 Documented divergences from the reference: frames without any candidate pair / local water
@@ -61,6 +63,38 @@ def _as_universe(structure, trajectories):
     raise TypeError("structure must be a path or a Universe-like object")
 
 
+def box_rows(dimensions):
+    """[a, b, c, alpha, beta, gamma] -> float32 3x3 lattice rows (the layout of MDAnalysis' triclinic_vectors)."""
+    a, b, c, al, be, ga = [float(x) for x in dimensions]
+    al, be, ga = _np.deg2rad([al, be, ga])
+    m = _np.zeros((3, 3), dtype=_np.float64)
+    m[0, 0] = a
+    m[1, 0] = b * _np.cos(ga)
+    m[1, 1] = b * _np.sin(ga)
+    m[2, 0] = c * _np.cos(be)
+    m[2, 1] = c * (_np.cos(al) - _np.cos(be) * _np.cos(ga)) / _np.sin(ga)
+    m[2, 2] = _np.sqrt(max(c * c - m[2, 0] ** 2 - m[2, 1] ** 2, 0.0))
+    m[_np.abs(m) < 1e-12] = 0.0
+    return m.astype(_np.float32)
+
+
+def _frame_boxes(universe, frame_indices):
+    """float32 [k, 3, 3] lattice rows of the given frames."""
+    traj = universe.trajectory
+    if getattr(traj, "frames", None) is not None:          # array-backed Universe: one cell for all frames
+        dims = getattr(traj, "dimensions", None)
+        if dims is None:
+            raise ValueError("pbc needs unit-cell dimensions; the Universe has none")
+        return _np.broadcast_to(box_rows(dims), (len(frame_indices), 3, 3)).copy()
+    out = _np.empty((len(frame_indices), 3, 3), dtype=_np.float32)
+    for k, f in enumerate(frame_indices):                   # real MDAnalysis reader
+        ts = traj[f]
+        if ts.dimensions is None:
+            raise ValueError("pbc needs unit-cell dimensions; frame %d has none" % f)
+        out[k] = box_rows(ts.dimensions)
+    return out
+
+
 def _frame_blocks(universe, frame_indices, block):
     """Yield float32 arrays [k, N, 3] covering `frame_indices` in order."""
     traj = universe.trajectory
@@ -90,8 +124,9 @@ class HbondAnalysis(object):
                  additional_acceptors=[], exclude_donors=[], exclude_acceptors=[],
                  ions=[], check_angle=True, residuewise=True, add_donors_without_hydrogen=False,
                  restore_filename=None, device=None, shard=None, cos_threshold=None, batch_bytes=None,
-                 native_options=None):
+                 native_options=None, pbc=False):
         self._device = device
+        self._pbc = pbc
         self._native_options = dict(native_options or {})
         self._shard = shard
         self._cos_threshold_override = cos_threshold
@@ -223,8 +258,18 @@ class HbondAnalysis(object):
         cthr = self._cos_threshold_override
         if cthr is None:
             cthr = _cos_threshold(float(self.cut_angle)) if self.check_angle else -1.0
+        pbc_mode = _native.PBC_NONE
+        if self._pbc:
+            if self._pbc in ("ortho", "orthorhombic"):
+                pbc_mode = _native.PBC_ORTHO
+            elif self._pbc in ("triclinic",):
+                pbc_mode = _native.PBC_TRICLINIC
+            else:   # True: decide from the first frame's cell
+                b0 = _frame_boxes(self._universe, self._frame_indices[:1])[0]
+                pbc_mode = _native.PBC_ORTHO if not (b0[1, 0] or b0[2, 0] or b0[2, 1]) else _native.PBC_TRICLINIC
         ctx.set_params(self.distance, around_radius, cthr, self.check_angle, exclude_backbone_backbone,
-                       _native.METHOD_WATER_AROUND if method == "water_around" else _native.METHOD_IN_SELECTION)
+                       _native.METHOD_WATER_AROUND if method == "water_around" else _native.METHOD_IN_SELECTION,
+                       pbc_mode=pbc_mode)
         # frame block of this rank (block boundaries are multiples of 32 frames)
         fi = self._frame_indices
         lo, hi = 0, self.nb_frames
@@ -237,8 +282,11 @@ class HbondAnalysis(object):
         if n_local > 0:
             ctx.begin(n_local)
             block = max(1, min(n_local, int((256 << 20) // max(1, self._n_atoms * 12))))
+            done = lo
             for xyz in _frame_blocks(self._universe, fi[lo:hi], block):
-                ctx.submit(xyz)
+                box = _frame_boxes(self._universe, fi[done:done + len(xyz)]) if pbc_mode else None
+                ctx.submit(xyz, box=box)
+                done += len(xyz)
             keys, words = ctx.results()
             self.last_run_stats = ctx.timers()
         if self._shard is not None and self._shard[1] > 1:

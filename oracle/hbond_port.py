@@ -191,7 +191,84 @@ def self_pairs(a, r, backend='kdtree'):
     return i[keep], j[keep]
 
 
-def _angle_filter(pt, e0, e1, coords, hcoords, cut_angle, cos_threshold=None):
+# ------------------------------------------------------------------------------------------------
+# Minimum-image extension (NOT in the reference, which applies no periodic boundary conditions - SURVEY F1).
+# Definition shared with the kernels (DESIGN.md 2): lattice vectors are lower-triangular rows a, b, c (float32);
+# a difference vector is reduced along c, then b, then a with n = rint(d_k / L_k) and individually rounded
+# multiply / subtract - in float64 on the float64 differences for DIST, in float32 for the angle vectors. When
+# nothing wraps (n = 0) the arithmetic is exactly the reference's.
+# ------------------------------------------------------------------------------------------------
+def box_rows(dimensions):
+    """[a, b, c, alpha, beta, gamma] -> float32 3x3, rows = lattice vectors (MDAnalysis triclinic_vectors layout)."""
+    a, b, c, al, be, ga = [float(x) for x in dimensions]
+    al, be, ga = np.deg2rad([al, be, ga])
+    m = np.zeros((3, 3), dtype=np.float64)
+    m[0, 0] = a
+    m[1, 0] = b * np.cos(ga)
+    m[1, 1] = b * np.sin(ga)
+    m[2, 0] = c * np.cos(be)
+    m[2, 1] = c * (np.cos(al) - np.cos(be) * np.cos(ga)) / np.sin(ga)
+    m[2, 2] = np.sqrt(max(c * c - m[2, 0] ** 2 - m[2, 1] ** 2, 0.0))
+    m[np.abs(m) < 1e-12] = 0.0
+    return m.astype(np.float32)
+
+
+def _reduce(dx, dy, dz, box, dtype):
+    ax, bx, by, cx, cy, cz = [dtype(box[i, j]) for i, j in ((0, 0), (1, 0), (1, 1), (2, 0), (2, 1), (2, 2))]
+    n = np.rint(dz / cz)
+    dz = dz - n * cz
+    dy = dy - n * cy
+    dx = dx - n * cx
+    n = np.rint(dy / by)
+    dy = dy - n * by
+    dx = dx - n * bx
+    n = np.rint(dx / ax)
+    dx = dx - n * ax
+    return dx, dy, dz
+
+
+def dist2_pbc(pa, pb, box):
+    """float64 squared minimum-image distance of float32 points pa[k], pb[k] (same operation order as dist_le_pbc)."""
+    d = pa.astype(np.float64) - pb.astype(np.float64)
+    dx, dy, dz = _reduce(d[:, 0].copy(), d[:, 1].copy(), d[:, 2].copy(), box, np.float64)
+    return (dx * dx + dy * dy) + dz * dz
+
+
+def min_image32(v, box):
+    vx, vy, vz = _reduce(v[:, 0].copy(), v[:, 1].copy(), v[:, 2].copy(), box, np.float32)
+    return np.stack([vx, vy, vz], axis=1)
+
+
+def ball_pairs_pbc(a, b, r, box):
+    """All (i, j) with minimum-image DIST(a_i, b_j, r): candidates from a KD-tree over the 27 images of b."""
+    if len(a) == 0 or len(b) == 0:
+        return np.zeros(0, np.int64), np.zeros(0, np.int64)
+    h = box.astype(np.float64)
+    shifts = np.array([[i, j, k] for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1)], dtype=np.float64) @ h
+    # bring everything into one cell first so that +-1 images suffice for the candidate search
+    def wrap(p):
+        f = p.astype(np.float64) @ np.linalg.inv(h)
+        return (f - np.floor(f)) @ h
+    aw, bw = wrap(a), wrap(b)
+    images = (bw[None, :, :] + shifts[:, None, :]).reshape(-1, 3)
+    lists = cKDTree(aw).query_ball_tree(cKDTree(images), float(r) * 1.001 + 1e-3)
+    i, j = _flatten(lists)
+    j = j % len(b)
+    if len(i):
+        ij = np.unique(np.stack([i, j], axis=1), axis=0)
+        i, j = ij[:, 0], ij[:, 1]
+        keep = dist2_pbc(a[i], b[j], box) <= np.float64(r) * np.float64(r)
+        i, j = i[keep], j[keep]
+    return i, j
+
+
+def self_pairs_pbc(a, r, box):
+    i, j = ball_pairs_pbc(a, a, r, box)
+    keep = i < j
+    return i[keep], j[keep]
+
+
+def _angle_filter(pt, e0, e1, coords, hcoords, cut_angle, cos_threshold=None, box=None):
     """helpfunctions.py:137-159: keep a pair if any hydrogen of either partner passes the angle test."""
     if len(e0) == 0:
         return e0, e1
@@ -203,7 +280,21 @@ def _angle_filter(pt, e0, e1, coords, hcoords, cut_angle, cos_threshold=None):
     pa = coords[e0[pair_of]]
     pb = coords[e1[pair_of]]
     ph = hcoords[hidx]
-    if cos_threshold is None:
+    if box is not None:       # minimum-image vectors: v1 = h - b, v2 = a - h, each reduced in float32
+        v1 = min_image32(ph - pb, box)
+        v2 = min_image32(pa - ph, box)
+        d12 = (v1[:, 0] * v2[:, 0] + v1[:, 1] * v2[:, 1]) + v1[:, 2] * v2[:, 2]
+        d11 = (v1[:, 0] * v1[:, 0] + v1[:, 1] * v1[:, 1]) + v1[:, 2] * v1[:, 2]
+        d22 = (v2[:, 0] * v2[:, 0] + v2[:, 1] * v2[:, 1]) + v2[:, 2] * v2[:, 2]
+        with np.errstate(all='ignore'):
+            c = d12 / (np.sqrt(d11) * np.sqrt(d22))
+            if cos_threshold is None:
+                cc = c.copy()
+                cc[cc < -1.0] = -1.0
+                ok = np.rad2deg(np.arccos(cc)) <= np.float32(cut_angle)
+            else:
+                ok = (np.where(c < -1.0, np.float32(-1.0), c) >= np.float32(cos_threshold)) & (c <= np.float32(1.0))
+    elif cos_threshold is None:
         ok = angle_deg(pb, ph, pa) <= np.float32(cut_angle)
     else:  # the threshold form the kernels use; tested equal to the line above
         c = cos_arg(pb, ph, pa)
@@ -235,14 +326,21 @@ def _backbone_flags(pt):
 
 
 def frame_pairs(pt, pos, method, around=None, exclude_backbone_backbone=True, backend='kdtree',
-                cos_threshold=None, strict=False):
-    """Entry pairs (col0, col1) that are H-bonds in one frame, before key building."""
+                cos_threshold=None, strict=False, box=None):
+    """Entry pairs (col0, col1) that are H-bonds in one frame, before key building.
+    box (float32 3x3 lattice rows) switches to the minimum-image extension."""
     nD, nA, fw = pt.nD, pt.nA, pt.first_water
+    if box is not None:
+        box = np.asarray(box, dtype=np.float32)
+        _bp = lambda a, b, r, backend: ball_pairs_pbc(a, b, r, box)
+        _sp = lambda a, r, backend: self_pairs_pbc(a, r, box)
+    else:
+        _bp, _sp = ball_pairs, self_pairs
     coords_sel = pos[pt.entry_atom[:fw]]
     e0 = np.zeros(0, np.int64)
     e1 = np.zeros(0, np.int64)
     if nD > 0 and nA > 0:
-        ia, jd = ball_pairs(pos[pt.acceptors], pos[pt.donors], pt.distance, backend)
+        ia, jd = _bp(pos[pt.acceptors], pos[pt.donors], pt.distance, backend)
         if strict and len(ia) == 0:
             raise IndexError('reference raises on frames without donor-acceptor pairs')
         e0, e1 = ia + nD, jd
@@ -254,19 +352,19 @@ def frame_pairs(pt, pos, method, around=None, exclude_backbone_backbone=True, ba
         coords = coords_sel
     else:
         wpos = pos[pt.water_atoms]
-        _, wj = ball_pairs(coords_sel, wpos, float(around), backend)
+        _, wj = _bp(coords_sel, wpos, float(around), backend)
         local = np.unique(wj)
         if strict and len(local) == 0:
             raise IndexError('reference raises on frames without local water')
         lpos = wpos[local]
-        si, lj = ball_pairs(coords_sel, lpos, pt.distance, backend)
-        wi, wj2 = self_pairs(lpos, pt.distance, backend)
+        si, lj = _bp(coords_sel, lpos, pt.distance, backend)
+        wi, wj2 = _sp(lpos, pt.distance, backend)
         # candidate order of the reference: DA ++ WW ++ SW (irrelevant for the result)
         e0 = np.concatenate([e0, local[wi] + fw, si])
         e1 = np.concatenate([e1, local[wj2] + fw, local[lj] + fw])
         coords = np.vstack([coords_sel, wpos])
     if pt.check_angle:
-        e0, e1 = _angle_filter(pt, e0, e1, coords, pos[pt.h_atom], pt.cut_angle, cos_threshold)
+        e0, e1 = _angle_filter(pt, e0, e1, coords, pos[pt.h_atom], pt.cut_angle, cos_threshold, box)
     return e0, e1
 
 
@@ -306,8 +404,9 @@ def key_ids(pt, method):
 
 
 def run_block(pt, xyz, method, around=3.5, exclude_backbone_backbone=True, backend='kdtree',
-              cos_threshold=None, strict=False, results=None, col0=0, nb_frames=None):
-    """Process the frames xyz[k] (float32 [K, N, 3]) into `results` columns col0 + k; returns results."""
+              cos_threshold=None, strict=False, results=None, col0=0, nb_frames=None, box=None):
+    """Process the frames xyz[k] (float32 [K, N, 3]) into `results` columns col0 + k; returns results.
+    box: None, one 3x3 lattice for all frames or an array [K, 3, 3] (minimum-image extension)."""
     ids = key_ids(pt, method)
     if results is None:
         results = {}
@@ -315,7 +414,8 @@ def run_block(pt, xyz, method, around=3.5, exclude_backbone_backbone=True, backe
         nb_frames = pt.nb_frames
     for k in range(len(xyz)):
         pos = np.asarray(xyz[k], dtype=np.float32)
-        e0, e1 = frame_pairs(pt, pos, method, around, exclude_backbone_backbone, backend, cos_threshold, strict)
+        bk = None if box is None else (np.asarray(box)[k] if np.asarray(box).ndim == 3 else np.asarray(box))
+        e0, e1 = frame_pairs(pt, pos, method, around, exclude_backbone_backbone, backend, cos_threshold, strict, bk)
         for key in _frame_keys(pt, e0, e1, ids):
             row = results.get(key)
             if row is None:
@@ -325,7 +425,7 @@ def run_block(pt, xyz, method, around=3.5, exclude_backbone_backbone=True, backe
 
 
 def run(universe, selection, method='in_selection', around=3.5, exclude_backbone_backbone=True,
-        backend='kdtree', cos_threshold=None, strict=False, frame_range=None, **ctor):
+        backend='kdtree', cos_threshold=None, strict=False, frame_range=None, box=None, **ctor):
     """Run the port; returns a PortResult whose `initial_results` is `dict[str, bool[nb_frames]]`."""
     pt = PortTopology(universe, selection, **ctor)
     if method == 'in_selection':
@@ -339,5 +439,5 @@ def run(universe, selection, method='in_selection', around=3.5, exclude_backbone
         if frame_range is not None and not (frame_range[0] <= col < frame_range[1]):
             continue
         run_block(pt, [frames.frame(f)], method, around, exclude_backbone_backbone, backend, cos_threshold,
-                  strict, results, col)
+                  strict, results, col, box=box)
     return PortResult(pt, results)
