@@ -171,6 +171,31 @@ __device__ __forceinline__ bool cell3_pbc(const FrameGrid& g, float x, float y, 
     cx = c[0]; cy = c[1]; cz = c[2];
     return inside;
 }
+// same result as cell3_pbc + linear cell index, but leaves as soon as one windowed axis excludes the point
+// (the c axis depends on z only, b on y and z: most waters of a frame fall out after the first few operations)
+__device__ __forceinline__ bool cell_in_window_pbc(const FrameGrid& g, float x, float y, float z, int& cell) {
+    const PbcGrid& p = g.p;
+    const float sc = z * p.ic;
+    float u = sc - p.c[2];
+    u -= rintf(u);
+    const float vc = u + p.half[2];
+    if (!p.per[2] && !(vc >= 0.f && vc <= 2.f * p.half[2])) return false;
+    const float sb = (y - sc * p.box.cy) * p.ib;
+    u = sb - p.c[1];
+    u -= rintf(u);
+    const float vb = u + p.half[1];
+    if (!p.per[1] && !(vb >= 0.f && vb <= 2.f * p.half[1])) return false;
+    const float sa = (x - sb * p.box.bx - sc * p.box.cx) * p.ia;
+    u = sa - p.c[0];
+    u -= rintf(u);
+    const float va = u + p.half[0];
+    if (!p.per[0] && !(va >= 0.f && va <= 2.f * p.half[0])) return false;
+    const int cx = min(max((int)floorf(va * p.scale[0]), 0), g.nx - 1);
+    const int cy = min(max((int)floorf(vb * p.scale[1]), 0), g.ny - 1);
+    const int cz = min(max((int)floorf(vc * p.scale[2]), 0), g.nz - 1);
+    cell = (cz * g.ny + cy) * g.nx + cx;
+    return true;
+}
 template <bool PBC>
 __device__ __forceinline__ void cell3(const FrameGrid& g, float x, float y, float z, int& cx, int& cy, int& cz) {
     if constexpr (PBC) {
@@ -673,31 +698,36 @@ template <bool PBC, typename CellT, typename F>
 __device__ __forceinline__ void for_each_partner(const FrameGrid& g, const CellT* cells, int i, float x, float y, float z, F f) {
     int cx, cy, cz;
     cell3<PBC>(g, x, y, z, cx, cy, cz);
-    if constexpr (PBC) {
-        const AxisList zl = axis_neighbors(cz, g.nz, g.p.per[2]), yl = axis_neighbors(cy, g.ny, g.p.per[1]);
-        const XSegs xs = x_segments(cx, g.nx, g.p.per[0]);
-        for (int a = 0; a < zl.n; ++a)
-            for (int b = 0; b < yl.n; ++b) {
-                const int row = (zl.v[a] * g.ny + yl.v[b]) * g.nx;
-                for (int k = 0; k < xs.n; ++k) {
-                    const int c_lo = row + xs.lo[k], c_hi = row + xs.hi[k];
-                    const int s = max(c_lo ? (int)cells[c_lo - 1] : 0, i + 1), e = (int)cells[c_hi];
-                    for (int q = s; q < e; ++q) f(q);
+    bool wraps = false;
+    if constexpr (PBC) wraps = g.p.per[0] | g.p.per[1] | g.p.per[2];
+    if (wraps) {
+        if constexpr (PBC) {
+            const AxisList zl = axis_neighbors(cz, g.nz, g.p.per[2]), yl = axis_neighbors(cy, g.ny, g.p.per[1]);
+            const XSegs xs = x_segments(cx, g.nx, g.p.per[0]);
+            for (int a = 0; a < zl.n; ++a)
+                for (int b = 0; b < yl.n; ++b) {
+                    const int row = (zl.v[a] * g.ny + yl.v[b]) * g.nx;
+                    for (int k = 0; k < xs.n; ++k) {
+                        const int c_lo = row + xs.lo[k], c_hi = row + xs.hi[k];
+                        const int s = max(c_lo ? (int)cells[c_lo - 1] : 0, i + 1), e = (int)cells[c_hi];
+                        for (int q = s; q < e; ++q) f(q);
+                    }
                 }
-            }
-    } else {
-        const int xl = max(cx - 1, 0), xh = min(cx + 1, g.nx - 1);
+        }
+    } else {      // no wrap-around on any axis (always so without PBC; windowed selection with PBC): forward half shell
+        const int nx = g.nx, ny = g.ny, nz = g.nz;
+        const int xl = max(cx - 1, 0), xh = min(cx + 1, nx - 1);
 #pragma unroll 1
         for (int run = 0; run < 5; ++run) {
             int s, e;
             if (run == 0) {
                 s = i + 1;
-                e = (int)cells[(cz * g.ny + cy) * g.nx + xh];
+                e = (int)cells[(cz * ny + cy) * nx + xh];
             } else {
                 const int yy = run == 1 ? cy + 1 : cy + (run - 3);
                 const int zz = run == 1 ? cz : cz + 1;
-                if (yy < 0 || yy >= g.ny || zz >= g.nz) continue;
-                const int row = (zz * g.ny + yy) * g.nx;
+                if (yy < 0 || yy >= ny || zz >= nz) continue;
+                const int row = (zz * ny + yy) * nx;
                 s = (row + xl) ? (int)cells[row + xl - 1] : 0;
                 e = (int)cells[row + xh];
             }

@@ -168,7 +168,7 @@ __device__ __forceinline__ void collect_pairs(const RunParams& rp, const FrameGr
 }
 
 template <bool PBC>
-__global__ void __launch_bounds__(FUSED_THREADS, 4) k_frame_fused(BatchView bv, DevTopo tp, RunParams rp, BondTable bt, FusedCfg fc) {
+__global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(BatchView bv, DevTopo tp, RunParams rp, BondTable bt, FusedCfg fc) {
     extern __shared__ __align__(16) unsigned char smem[];
     FusedShared* sh = reinterpret_cast<FusedShared*>(smem);
     float4* spos = reinterpret_cast<float4*>(smem + fc.off_spos);          // selection points, gather order
@@ -337,6 +337,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 4) k_frame_fused(BatchView bv, 
     phase_done(0);
     // ---- phase B: local waters ---------------------------------------------------------------------
     if (scan_waters) {
+        // non-periodic grid geometry lives in registers; the larger minimum-image geometry stays in shared memory
         const FrameGrid g1 = sh->g1;
         for (int i = tid; i < (g1.ncell + 31) / 32; i += FUSED_CONSUMERS) near[i] = 0u;
         block_cell_sort<PBC>(g1, cells, sorted1, nsel, [&](int i) { return spos[i]; }, sh);   // (syncs cover the zeroing)

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--options", default="", help="comma separated name=value pairs for hb_set_option")
     ap.add_argument("--modes", default="1,0")
+    ap.add_argument("--pbc", type=int, default=0, help="0 none, 1 ortho, 2 triclinic")
     args = ap.parse_args()
     import torch
     from cgraphs_b200 import build as hb_build, synth
@@ -42,7 +43,11 @@ def main():
     ctx = hba._context()
     ctx.set_topology(tables)
     ctx.set_params(3.5, 3.5, cos_threshold(60.0) if cfg["check_angle"] else -1.0, cfg["check_angle"], True,
-                   _native.METHOD_WATER_AROUND)
+                   _native.METHOD_WATER_AROUND, pbc_mode=args.pbc)
+    d_box = None
+    if args.pbc:
+        from cgraphs_b200.mdhbond.hbond import box_rows
+        d_box = torch.from_numpy(np.broadcast_to(box_rows(system.dimensions).reshape(1, 9), (nf, 9)).copy()).to(dev)
     ctx.set_option("profile", 1)
     for kv in filter(None, args.options.split(",")):
         k, v = kv.split("=")
@@ -55,7 +60,7 @@ def main():
             ctx.begin(nf)
             torch.cuda.synchronize()
             t1 = time.perf_counter()
-            ctx.submit_device(d_xyz.data_ptr(), na, nf)
+            ctx.submit_device(d_xyz.data_ptr(), na, nf, d_box.data_ptr() if d_box is not None else None)
             torch.cuda.synchronize()
             t2 = time.perf_counter()
             nb, wpr = ctx.finalize()
