@@ -132,53 +132,65 @@ def algorithmic_bytes(top, n_bonds):
 # ------------------------------------------------------------------------------------------------
 # CPU arms
 # ------------------------------------------------------------------------------------------------
-def _cpu_worker(args):
-    pt, xyz, method, around = args
+_CPU_SHARED = {}     # inherited by forked workers: no pickling of topology or frames
+
+
+def _cpu_worker(span):
     from oracle import hbond_port
+    pt, xyz, method, around = _CPU_SHARED["pt"], _CPU_SHARED["xyz"], _CPU_SHARED["method"], _CPU_SHARED["around"]
+    lo, hi = span
     t = time.perf_counter()
-    res = hbond_port.run_block(pt, xyz, method, around, nb_frames=len(xyz))
+    res = hbond_port.run_block(pt, xyz[lo:hi], method, around, nb_frames=hi - lo)
     return time.perf_counter() - t, len(res)
 
 
-def cpu_port_rate(system, cfg, frames_xyz, n_procs):
-    """frames/s of the oracle port over frames_xyz using n_procs processes (frame sharded)."""
+def cpu_port_topology(system, cfg, frames_xyz):
     from oracle import hbond_port
     from cgraphs_b200.universe import Universe
     u = Universe(system.topology, frames_xyz[:1])
-    pt = hbond_port.PortTopology(u, SELECTION, check_angle=cfg["check_angle"],
-                                 add_donors_without_hydrogen=cfg["add_donors_without_hydrogen"])
+    return hbond_port.PortTopology(u, SELECTION, check_angle=cfg["check_angle"],
+                                   add_donors_without_hydrogen=cfg["add_donors_without_hydrogen"])
+
+
+def cpu_port_rate(system, cfg, frames_xyz, n_procs, pool=None):
+    """frames/s of the oracle port over frames_xyz using n_procs processes (frame sharded)."""
+    from oracle import hbond_port
     method = "water_around"
     if n_procs <= 1:
+        pt = cpu_port_topology(system, cfg, frames_xyz)
         t = time.perf_counter()
         hbond_port.run_block(pt, frames_xyz, method, AROUND, nb_frames=len(frames_xyz))
         dt = time.perf_counter() - t
         return len(frames_xyz) / dt, dt
-    import multiprocessing as mp
-    chunks = np.array_split(np.arange(len(frames_xyz)), n_procs)
-    jobs = [(pt, frames_xyz[c[0]:c[-1] + 1], method, AROUND) for c in chunks if len(c)]
-    ctx = mp.get_context("fork")
-    with ctx.Pool(len(jobs)) as pool:
-        pool.map(_cpu_worker, [(pt, frames_xyz[:1], method, AROUND)] * len(jobs))   # spin-up, untimed
-        t = time.perf_counter()
-        pool.map(_cpu_worker, jobs)
-        dt = time.perf_counter() - t
+    bounds = np.linspace(0, len(frames_xyz), n_procs + 1).astype(int)
+    spans = [(int(a), int(b)) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+    t = time.perf_counter()
+    pool.map(_cpu_worker, spans, chunksize=1)
+    dt = time.perf_counter() - t
     return len(frames_xyz) / dt, dt
 
 
 def run_reference_arm(args):
+    """The CPU path on all host cores: the validated port (the reference itself needs /root/reference and
+    MDAnalysis stubs, which do not travel to the GPU box), frame-sharded over one process per core."""
     rank = env_int("RANK", 0)
     if rank != 0:
         return 0
+    import multiprocessing as mp
     scale = args.scale
     system, cfg = build_case(scale, args.frames)
     cores = os.cpu_count() or 1
-    per_step = max(cores * 4, 32)
+    per_step = int(min(512, max(cores * 16, 64)))
     xyz = system.frames(0, per_step)
+    _CPU_SHARED.update(pt=cpu_port_topology(system, cfg, xyz), xyz=xyz, method="water_around", around=AROUND)
+    ctx = mp.get_context("fork")
     times = []
-    for i in range(args.warmup + args.steps):
-        rate, dt = cpu_port_rate(system, cfg, xyz, cores)
-        if i >= args.warmup:
-            times.append(dt)
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(0, 1)] * cores, chunksize=1)          # spin-up, untimed
+        for i in range(args.warmup + args.steps):
+            rate, dt = cpu_port_rate(system, cfg, xyz, cores, pool)
+            if i >= args.warmup:
+                times.append(dt)
     ms = 1000.0 * float(np.mean(times))
     value = per_step / (ms / 1000.0)
     sample = "%d frames of the %d-atom workload per step, frame-sharded over %d processes" % (per_step, system.n_atoms, cores)

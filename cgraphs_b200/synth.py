@@ -316,7 +316,12 @@ def make_system(n_atoms, n_residues, seed, *, n_filler=0, hydrogens=True, water=
             cand = cand[ptree.query(cand)[0] > 2.4]
         if n_filler > 0 and len(cand) and len(filler_xyz):
             cand = cand[cKDTree(filler_xyz).query(cand)[0] > 2.6]
-        if fits and len(cand) >= n_wat:
+        prot_ok = True
+        if n_prot:      # the protein itself must keep the skin too (small cells around large proteins)
+            pf = (prot + centre) @ hinv * perpendicular_widths(h)
+            pw = (1.0 - (prot + centre) @ hinv) * perpendicular_widths(h)
+            prot_ok = bool(pf.min() > SKIN + MAX_DISP and pw.min() > SKIN + MAX_DISP)
+        if fits and prot_ok and len(cand) >= n_wat:
             break
         inner *= 1.015
     else:
