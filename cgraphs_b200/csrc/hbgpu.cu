@@ -112,7 +112,8 @@ struct hb_ctx {
     std::vector<void*> scratch_allocs;
     float* d_in[2] = {nullptr, nullptr};
     float* h_stage[2] = {nullptr, nullptr};
-    size_t in_bytes = 0;
+    size_t in_bytes = 0;              // planned capacity of one input buffer
+    size_t in_alloc = 0;              // bytes actually allocated per input buffer
     cudaEvent_t ev_copied[2]{}, ev_done[2]{};
     cudaEvent_t ev_run0{}, ev_run1{};
     long long batch_counter = 0;
@@ -286,6 +287,7 @@ static void free_run(hb_ctx* ctx) {
         ctx->d_in[k] = nullptr;
         ctx->h_stage[k] = nullptr;
     }
+    ctx->in_alloc = 0;
     for (int k = 0; k < 2; ++k) {
         if (ctx->d_box[k]) cudaFree(ctx->d_box[k]);
         if (ctx->h_box[k]) cudaFreeHost(ctx->h_box[k]);
@@ -363,8 +365,7 @@ int hb_set_topology(hb_ctx* ctx, const hb_topology* t) {
     if (t->n_sel >= WATER_TAG || t->n_wat >= WATER_TAG) return fail(ctx, HB_ERR_ARG, "topology: too many points");
     CK(cudaSetDevice(ctx->device));
     free_list(ctx->topo_allocs);
-    ctx->have_topo = false;
-    memset(ctx->alloc_sig, 0, sizeof(ctx->alloc_sig));
+    ctx->have_topo = false;       // (run allocations are kept: hb_begin compares everything that sizes them)
     int ns = t->n_systems;
     ctx->h_sys_atom_off.assign(t->sys_atom_off, t->sys_atom_off + ns + 1);
     ctx->h_sys_sel_off.assign(t->sys_sel_off, t->sys_sel_off + ns + 1);
@@ -613,7 +614,7 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     int wpr = (int)((n_frames_total + 31) / 32);
     long long want = ctx->opt_table_capacity;
     if (!want) {   // a few slots per selection point (+ as many local waters); the table doubles on demand
-        want = 8 * (ctx->n_sel_total + (ctx->rp.method == HB_METHOD_WATER_AROUND ? std::min(ctx->n_sel_total, ctx->n_wat_total) : 0));
+        want = 4 * (ctx->n_sel_total + (ctx->rp.method == HB_METHOD_WATER_AROUND ? std::min(ctx->n_sel_total, ctx->n_wat_total) : 0));
         want = std::min<long long>(std::max<long long>(want, 4096), 1ll << 22);
     }
     long long cap = 1024;
@@ -903,8 +904,12 @@ static long long batch_atoms(hb_ctx* ctx, long long f0, int nf, long long n_atom
 static int next_batch_frames(hb_ctx* ctx, long long f0, long long remaining, bool host) {
     long long lim = host ? ctx->host_batch_frames : (ctx->fused_active ? ctx->opt_fused_batch_frames : ctx->batch_frames);
     int nf = (int)std::min<long long>(remaining, std::max<long long>(lim, 1));
+    if (host && !ctx->prm.structure_batch) {
+        long long fit = (long long)(ctx->in_alloc / std::max<size_t>((size_t)ctx->max_atoms * 12, 1));
+        nf = (int)std::max<long long>(1, std::min<long long>(nf, fit));
+    }
     if (host && ctx->prm.structure_batch) {   // ragged: stay within the input buffer
-        long long budget = (long long)(ctx->in_bytes / 12);
+        long long budget = (long long)(ctx->in_alloc / 12);
         while (nf > 1 && ctx->h_sys_atom_off[f0 + nf] - ctx->h_sys_atom_off[f0] > budget) --nf;
     }
     return nf;
@@ -937,9 +942,31 @@ int hb_submit_frames(hb_ctx* ctx, const float* xyz, int64_t n_atoms, int64_t n_f
     cudaPointerAttributes attr{};
     bool pinned = cudaPointerGetAttributes(&attr, xyz) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    for (int k = 0; k < 2; ++k) {
-        if (!ctx->d_in[k]) CK(cudaMalloc((void**)&ctx->d_in[k], std::max<size_t>(ctx->in_bytes, 16)));
-        if (!pinned && !ctx->h_stage[k]) CK(cudaHostAlloc((void**)&ctx->h_stage[k], std::max<size_t>(ctx->in_bytes, 16), cudaHostAllocDefault));
+    {   // input buffers: as large as one batch of this call needs, at most the planned capacity
+        size_t call_bytes = (size_t)batch_atoms(ctx, ctx->next_frame, (int)std::min<long long>(n_frames, 1 << 30), n_atoms) * 12;
+        size_t need = std::max<size_t>(std::min(ctx->in_bytes, call_bytes), 16);
+        if (need > ctx->in_alloc || (!pinned && !ctx->h_stage[0])) {
+            CK(cudaStreamSynchronize(ctx->s_copy));
+            int rcv = full_verify(ctx);           // nothing may still read the old buffers
+            if (rcv) return rcv;
+            need = std::max(need, ctx->in_alloc);
+            for (int k = 0; k < 2; ++k) {
+                if (need > ctx->in_alloc) {
+                    if (ctx->d_in[k]) cudaFree(ctx->d_in[k]);
+                    ctx->d_in[k] = nullptr;
+                    CK(cudaMalloc((void**)&ctx->d_in[k], need));
+                }
+                if (!pinned && (need > ctx->in_alloc || !ctx->h_stage[k])) {
+                    if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]);
+                    ctx->h_stage[k] = nullptr;
+                    CK(cudaHostAlloc((void**)&ctx->h_stage[k], need, cudaHostAllocDefault));
+                } else if (pinned && need > ctx->in_alloc && ctx->h_stage[k]) {
+                    cudaFreeHost(ctx->h_stage[k]);       // too small now; re-created on demand
+                    ctx->h_stage[k] = nullptr;
+                }
+            }
+            ctx->in_alloc = need;
+        }
     }
     const float* src = xyz;
     long long done = 0;

@@ -161,6 +161,7 @@ class Context:
 
     def set_topology(self, t):
         """t: dict of numpy arrays named like the hb_topology fields."""
+        self._uploaded = None          # callers that cache packed tables set this marker afterwards
         keep = {}
         st = HbTopology()
         st.n_systems = int(t["n_systems"])

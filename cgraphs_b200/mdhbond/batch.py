@@ -60,13 +60,18 @@ class HbondBatch(object):
         for a in self.analyses:
             a._check_hydrogen_tables(method)
         n_atoms = [a._n_atoms for a in self.analyses]
-        tables, group_names = pack_systems(tops, [t.key_ids(method) for t in tops], n_atoms)
+        cache = self.__dict__.setdefault("_packed", {})
+        if method not in cache:
+            cache[method] = pack_systems(tops, [t.key_ids(method) for t in tops], n_atoms)
+        tables, group_names = cache[method]
         if self._ctx is None:
             self._ctx = _native.Context(self._device if self._device is not None else 0)
             for name, value in self._native_options.items():
                 self._ctx.set_option(name, value)
         ctx = self._ctx
-        ctx.set_topology(tables)
+        if getattr(ctx, "_uploaded", None) is not tables:
+            ctx.set_topology(tables)
+            ctx._uploaded = tables
         cthr = _cos_threshold(float(self.cut_angle)) if self.check_angle else -1.0
         ctx.set_params(self.distance, around, cthr, self.check_angle, excl_bb,
                        _native.METHOD_WATER_AROUND if method == "water_around" else _native.METHOD_IN_SELECTION,

@@ -252,9 +252,13 @@ class HbondAnalysis(object):
         top = self._topology
         self._check_hydrogen_tables(method)
         ctx = self._context()
-        ids = top.key_ids(method)
-        tables, group_names = pack_systems([top], [ids], [self._n_atoms])
-        ctx.set_topology(tables)
+        cache = self.__dict__.setdefault("_packed", {})
+        if method not in cache:          # packed device tables per method (the key id strings differ)
+            cache[method] = pack_systems([top], [top.key_ids(method)], [self._n_atoms])
+        tables, group_names = cache[method]
+        if getattr(ctx, "_uploaded", None) is not tables:
+            ctx.set_topology(tables)
+            ctx._uploaded = tables
         cthr = self._cos_threshold_override
         if cthr is None:
             cthr = _cos_threshold(float(self.cut_angle)) if self.check_angle else -1.0
@@ -339,7 +343,7 @@ class HbondAnalysis(object):
 
     def dump_to_file(self, fname):                                    # basic.py:71-81
         tmp = _cp.copy(self)
-        for name in ('_universe', '_water', '_mda_selection', '_ctx', '_topology'):
+        for name in ('_universe', '_water', '_mda_selection', '_ctx', '_topology', '_packed'):
             tmp.__dict__[name] = None
         with open(fname, 'wb') as af:
             af.write(_pickle.dumps(tmp.__dict__))
