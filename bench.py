@@ -223,7 +223,7 @@ def run_ours(args):
     from cgraphs_b200.mdhbond import HbondAnalysis, _native
     from cgraphs_b200.mdhbond.calib import cos_threshold
     from cgraphs_b200.mdhbond.topology import pack_systems
-    from cgraphs_b200.mdhbond.sharding import merge_keys
+    from cgraphs_b200.mdhbond.sharding import merge_keys, merge_keys_device
 
     world = env_int("WORLD_SIZE", 1)
     rank = env_int("RANK", 0)
@@ -256,15 +256,24 @@ def run_ours(args):
     ctx.set_option("profile", 1)
     if args.batch_bytes:
         ctx.set_option("batch_bytes", args.batch_bytes)
+    # every kernel of the library and the NCCL exchange run on one torch stream, so a pair of CUDA events on that
+    # stream brackets whole passes (search + finalize + key merge)
+    stream = torch.cuda.Stream(device=dev)
+    ctx.set_option("compute_stream", stream.cuda_stream)
+    torch.cuda.set_stream(stream)
 
-    def one_pass_device():
+    merged = []
+
+    def one_pass_device(sync_merge=True):
         ctx.begin(nf)
         ctx.submit_device(d_xyz.data_ptr(), na, nf)
         nb, wpr = ctx.finalize()
-        if world > 1:                                   # the one exchange: distinct bond keys
+        if world > 1:                                   # the one exchange: distinct bond keys, GPU to GPU
             k = torch.empty(max(nb, 1), dtype=torch.int64, device=dev)
-            ctx.keys_to_device(k.data_ptr())
-            merge_keys(k[:nb].cpu().numpy().view(np.uint64), device=local_rank)
+            ctx.keys_to_device(k.data_ptr(), sync=False)
+            r = merge_keys_device(k[:nb], ctx=ctx, sync=sync_merge)
+            if not sync_merge:
+                merged.append(r[1])                     # [n_keys, overflow] on the device, checked after the loop
         return nb, wpr
 
     def sync_all():
@@ -278,27 +287,41 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     sync_all()
     sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    dev_ms = 0.0
     launches = 0
     kernel_ms = {}
     kernel_launches = {}
+    ev0.record(stream)
     for _ in range(args.steps):
-        nb, wpr = one_pass_device()
+        nb, wpr = one_pass_device(sync_merge=False)     # gather capacity learnt during warm-up; no host wait here
         tm = ctx.timers()
-        dev_ms += tm["ms_run"]
         launches += tm["n_launches"]
         for k, v in tm["ms_kernel"].items():
             kernel_ms[k] = kernel_ms.get(k, 0.0) + v
             kernel_launches[k] = kernel_launches.get(k, 0) + tm["launches"][k]
+    ev1.record(stream)
     sync_all()
     wall_ms = 1000.0 * (time.perf_counter() - t0)
+    dev_ms = ev0.elapsed_time(ev1)      # CUDA events on the launching stream around exactly `steps` passes
+    n_global_keys = None
+    for info in merged:
+        n_out, over = info.tolist()
+        if over:
+            raise SystemExit("bench: the key gather overflowed its learnt capacity inside the timed loop")
+        n_global_keys = n_out
     clocks = sampler.stop()
     # max over ranks of the device-timed pass (CUDA events begin -> finalize), cross-checked by wall clock
     t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max, wall_ms_max = float(t[0]), float(t[1])
+    per_rank = None
+    if dist is not None:      # per-rank view: device ms per step and the fused kernel's ms per step
+        mine = torch.tensor([dev_ms / args.steps, kernel_ms.get("frame_fused", 0.0) / args.steps], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[round(float(x[0]), 4), round(float(x[1]), 4)] for x in allr]
     ms_per_step = dev_ms_max / args.steps
     value = world * nf / (ms_per_step / 1000.0)
 
@@ -383,8 +406,10 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f64 distance / f32 angle", "data": "synthetic",
             "config": workload_config(system, cfg, args),
             "atom_frames_per_s": value * na, "wall_ms_per_step": wall_ms_max / args.steps,
-            "n_bonds": int(nb), "n_part_atoms": int(n_part),
+            "n_bonds": int(nb), "n_global_bonds": n_global_keys, "n_part_atoms": int(n_part),
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
+    if per_rank is not None:
+        line["per_rank_ms_per_step"] = {"columns": ["pass", "frame_fused kernel"], "ranks": per_rank}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -127,6 +127,57 @@ __global__ void __launch_bounds__(1024) k_sort_small(const unsigned long long* k
     for (int i = threadIdx.x; i < n; i += blockDim.x) { keys_out[i] = k[i]; vals_out[i] = v[i]; }
 }
 
+// Merge step of the multi-GPU key exchange: `gathered` holds, per rank, [count, key_0 .. key_{cap-1}] as the
+// all-gather delivered it (keys sorted, padding arbitrary). One CTA loads the valid keys into shared memory,
+// sorts them (bitonic), drops duplicates and writes the global sorted distinct list; info[0] = its length,
+// info[1] = 1 if some rank had more than `cap` keys (the caller then repeats with a larger capacity).
+__global__ void __launch_bounds__(1024) k_merge_keys(const unsigned long long* gathered, int world, int cap, int m,
+                                                     unsigned long long* out, long long* info) {
+    extern __shared__ __align__(16) unsigned long long mk[];
+    __shared__ int part[1024];
+    __shared__ int over;
+    if (threadIdx.x == 0) over = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const int w = i / cap, j = i - w * cap;
+        unsigned long long key = EMPTY_KEY;
+        if (w < world) {
+            const long long cnt = (long long)gathered[(size_t)w * (cap + 1)];
+            if (j == 0 && cnt > cap) over = 1;
+            if (j < cnt) key = gathered[(size_t)w * (cap + 1) + 1 + j];
+        }
+        mk[i] = key;
+    }
+    __syncthreads();
+    for (int size = 2; size <= m; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < (m >> 1); i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long a = mk[lo], b = mk[hi];
+                if ((a > b) == up) { mk[lo] = b; mk[hi] = a; }
+            }
+            __syncthreads();
+        }
+    // distinct keys: each thread owns a contiguous slice
+    const int per = (m + blockDim.x - 1) / blockDim.x;
+    const int s0 = min((int)threadIdx.x * per, m), s1 = min(s0 + per, m);
+    int cnt = 0;
+    for (int i = s0; i < s1; ++i) cnt += (mk[i] != EMPTY_KEY && (i == 0 || mk[i] != mk[i - 1])) ? 1 : 0;
+    part[threadIdx.x] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int t = 0; t < (int)blockDim.x; ++t) { int c = part[t]; part[t] = run; run += c; }
+        info[0] = run;
+        info[1] = over;
+    }
+    __syncthreads();
+    int pos = part[threadIdx.x];
+    for (int i = s0; i < s1; ++i)
+        if (mk[i] != EMPTY_KEY && (i == 0 || mk[i] != mk[i - 1])) out[pos++] = mk[i];
+}
+
 __global__ void k_gather_rows(const unsigned* bits, const unsigned* slots, int n, int wpr, unsigned* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)n * wpr;

@@ -54,6 +54,7 @@ struct hb_ctx {
     int device = 0;
     std::string err;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaStream_t s_own = nullptr;     // the library's own compute stream (s_compute may be a caller's stream)
     cudaDeviceProp prop{};
 
     // topology
@@ -101,6 +102,8 @@ struct hb_ctx {
     long long alloc_sig[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int table_grows = 0;
     int* h_status = nullptr;          // pinned, 4 ints per slot: n_keys, overflow, fused_overflow, pad
+    int last_status[6] = {0, 0, 0, 0, 0, 0};   // status block as of the last full_verify
+    int* h_verify = nullptr;          // pinned landing zone of that read back
     unsigned long long* h_hits = nullptr;
 
     // batch scratch
@@ -265,7 +268,8 @@ int hb_create(hb_ctx** out, int device) {
         delete ctx;
         return HB_ERR_NODEVICE;
     }
-    cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&ctx->s_own, cudaStreamNonBlocking);
+    ctx->s_compute = ctx->s_own;
     cudaStreamCreateWithFlags(&ctx->s_copy, cudaStreamNonBlocking);
     for (int k = 0; k < 2; ++k) {
         cudaEventCreateWithFlags(&ctx->ev_copied[k], cudaEventDisableTiming);
@@ -274,6 +278,7 @@ int hb_create(hb_ctx** out, int device) {
     cudaEventCreate(&ctx->ev_run0);
     cudaEventCreate(&ctx->ev_run1);
     cudaHostAlloc((void**)&ctx->h_status, 8 * sizeof(int), cudaHostAllocDefault);
+    cudaHostAlloc((void**)&ctx->h_verify, 8 * sizeof(int), cudaHostAllocDefault);
     cudaHostAlloc((void**)&ctx->h_hits, sizeof(unsigned long long), cudaHostAllocDefault);
     *out = ctx;
     return HB_OK;
@@ -329,8 +334,9 @@ int hb_destroy(hb_ctx* ctx) {
     cudaEventDestroy(ctx->ev_run0);
     cudaEventDestroy(ctx->ev_run1);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    if (ctx->h_verify) cudaFreeHost(ctx->h_verify);
     if (ctx->h_hits) cudaFreeHost(ctx->h_hits);
-    cudaStreamDestroy(ctx->s_compute);
+    cudaStreamDestroy(ctx->s_own);
     cudaStreamDestroy(ctx->s_copy);
     delete ctx;
     return HB_OK;
@@ -345,6 +351,11 @@ int hb_set_option(hb_ctx* ctx, const char* name, int64_t value) {
     else if (n == "max_batch_frames") ctx->opt_max_batch_frames = std::max<long long>(value, 1);
     else if (n == "fused") ctx->opt_fused = value != 0;
     else if (n == "force_radix_sort") ctx->opt_force_radix = value != 0;
+    else if (n == "compute_stream") {   // run all kernels on the caller's CUDA stream (0 = back to the library's own)
+        if (ctx->running) return fail(ctx, HB_ERR_STATE, "compute_stream cannot change during a run");
+        cudaStreamSynchronize(ctx->s_compute);
+        ctx->s_compute = value ? (cudaStream_t)(uintptr_t)value : ctx->s_own;
+    }
     else if (n == "copy_ranges") ctx->opt_copy_ranges = value != 0;
     else if (n == "fused_lw_cap") ctx->opt_fused_lw_cap = std::max<long long>(value, 0);
     else if (n == "fused_cell_cap") ctx->opt_fused_cell_cap = std::max<long long>(value, 0);
@@ -816,9 +827,11 @@ static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, 
 // the table is grown and every in-flight batch is re-run (idempotent: bits are OR-ed, keys deduplicate).
 static int full_verify(hb_ctx* ctx) {
     for (int attempt = 0; attempt < 28; ++attempt) {
+        int st[6];        // n_keys, overflow, fused_overflow, pad, n_hits (64 bit): one stream-ordered read back
+        CK(cudaMemcpyAsync(ctx->h_verify, ctx->bt.n_keys, sizeof(st), cudaMemcpyDeviceToHost, ctx->s_compute));
         CK(cudaStreamSynchronize(ctx->s_compute));
-        int st[3];
-        CK(cudaMemcpy(st, ctx->bt.n_keys, sizeof(st), cudaMemcpyDeviceToHost));
+        memcpy(st, ctx->h_verify, sizeof(st));
+        memcpy(ctx->last_status, st, sizeof(st));
         bool overflow = st[1] != 0, fused_overflow = st[2] != 0;
         if (!overflow && !fused_overflow && (long long)st[0] * 2 <= ctx->table_cap) {
             for (auto& sl : ctx->slots) sl.busy = false;
@@ -1044,8 +1057,8 @@ int hb_submit_frames_device(hb_ctx* ctx, const float* d_xyz, int64_t n_atoms, in
         src += (size_t)atoms * 3;
         if (ctx->pending.size() > 8192) drain_events(ctx);
     }
-    // the caller's buffer must stay valid until verified: settle before returning
-    return full_verify(ctx);
+    // the caller's buffers must stay valid until the batches are verified, which hb_sync / hb_finalize do
+    return HB_OK;
 }
 
 int hb_sync(hb_ctx* ctx) {
@@ -1074,11 +1087,12 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
     if (rc) return rc;
     tr.mark("sync");
     cudaStream_t st = ctx->s_compute;
-    CK(cudaMemcpyAsync(ctx->h_status, ctx->bt.n_keys, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(ctx->h_hits, ctx->bt.n_hits, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    int n = ctx->h_status[0];
-    ctx->tm.pairs_emitted = (long long)*ctx->h_hits;
+    int n = ctx->last_status[0];      // hb_sync just verified and read the status block; nothing ran since
+    {
+        unsigned long long hits;
+        memcpy(&hits, ctx->last_status + 4, sizeof(hits));
+        ctx->tm.pairs_emitted = (long long)hits;
+    }
     int wpr = ctx->bt.wpr;
     size_t nn = std::max(n, 1);
     int nblk = (n + RS_TILE - 1) / RS_TILE;
@@ -1180,7 +1194,8 @@ int hb_get_keys_device(hb_ctx* ctx, uint64_t* d_keys) {
     if (!ctx || !d_keys) return HB_ERR_ARG;
     if (!ctx->finalized) return fail(ctx, HB_ERR_STATE, "hb_get_keys_device before hb_finalize");
     CK(cudaSetDevice(ctx->device));
-    if (ctx->n_bonds) CK(cudaMemcpy(d_keys, ctx->d_out_keys, (size_t)ctx->n_bonds * 8, cudaMemcpyDeviceToDevice));
+    // device to device on the compute stream: ordered with the caller's work on that stream, no host round trip
+    if (ctx->n_bonds) CK(cudaMemcpyAsync(d_keys, ctx->d_out_keys, (size_t)ctx->n_bonds * 8, cudaMemcpyDeviceToDevice, ctx->s_compute));
     return HB_OK;
 }
 
@@ -1188,7 +1203,23 @@ int hb_get_bits_device(hb_ctx* ctx, uint32_t* d_words) {
     if (!ctx || !d_words) return HB_ERR_ARG;
     if (!ctx->finalized) return fail(ctx, HB_ERR_STATE, "hb_get_bits_device before hb_finalize");
     CK(cudaSetDevice(ctx->device));
-    if (ctx->n_bonds) CK(cudaMemcpy(d_words, ctx->d_out_rows, (size_t)ctx->n_bonds * ctx->bt.wpr * 4, cudaMemcpyDeviceToDevice));
+    if (ctx->n_bonds) CK(cudaMemcpyAsync(d_words, ctx->d_out_rows, (size_t)ctx->n_bonds * ctx->bt.wpr * 4, cudaMemcpyDeviceToDevice, ctx->s_compute));
+    return HB_OK;
+}
+
+int hb_merge_keys_device(hb_ctx* ctx, const uint64_t* d_gathered, int32_t world, int32_t cap, uint64_t* d_out, int64_t* d_info) {
+    if (!ctx || !d_gathered || !d_out || !d_info || world < 1 || cap < 1) return HB_ERR_ARG;
+    long long total = (long long)world * cap;
+    int m = 2;
+    while (m < total) m <<= 1;
+    if (total > 16384) return fail(ctx, HB_ERR_ARG, "hb_merge_keys_device: more than 16384 gathered keys; merge on the host");
+    CK(cudaSetDevice(ctx->device));
+    size_t smem = (size_t)m * 8;
+    CK(cudaFuncSetAttribute(k_merge_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_merge_keys<<<1, 1024, smem, ctx->s_compute>>>((const unsigned long long*)d_gathered, world, cap, m,
+                                                     (unsigned long long*)d_out, (long long*)d_info);
+    CK(cudaGetLastError());
+    ctx->tm.n_launches += 1;
     return HB_OK;
 }
 

@@ -90,6 +90,7 @@ SYMBOLS = [
     ("hb_get_bits", C.c_int, [_P, _P]),
     ("hb_get_keys_device", C.c_int, [_P, _P]),
     ("hb_get_bits_device", C.c_int, [_P, _P]),
+    ("hb_merge_keys_device", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     ("hb_get_counts", C.c_int, [_P, _P]),
     ("hb_get_timers", C.c_int, [_P, C.POINTER(HbTimers)]),
     ("hb_sync", C.c_int, [_P]),
@@ -236,11 +237,20 @@ class Context:
             self._ck(self.lib.hb_get_bits(self.h, words.ctypes.data), "hb_get_bits")
         return keys, words
 
-    def keys_to_device(self, dev_ptr):
+    def keys_to_device(self, dev_ptr, sync=True):
+        """Queue the copy on the context's compute stream; sync=False when the caller works on that stream."""
         self._ck(self.lib.hb_get_keys_device(self.h, int(dev_ptr)), "hb_get_keys_device")
+        if sync:
+            self.sync()
 
-    def bits_to_device(self, dev_ptr):
+    def bits_to_device(self, dev_ptr, sync=True):
         self._ck(self.lib.hb_get_bits_device(self.h, int(dev_ptr)), "hb_get_bits_device")
+        if sync:
+            self.sync()
+
+    def merge_keys_device(self, gathered_ptr, world, cap, out_ptr, info_ptr):
+        self._ck(self.lib.hb_merge_keys_device(self.h, int(gathered_ptr), int(world), int(cap), int(out_ptr), int(info_ptr)),
+                 "hb_merge_keys_device")
 
     def counts(self, n_bonds):
         c = np.zeros(n_bonds, dtype=np.int64)

@@ -27,6 +27,54 @@ def _dist():
     return dist
 
 
+_GATHER_CAP = {}      # per process group: keys per rank the gather buffer holds (grows, identical on all ranks)
+
+
+def merge_keys_device(local_keys, group=None, ctx=None, sync=True):
+    """All-gather sorted distinct keys held in a device tensor (int64 view of the uint64 keys); returns the global
+    sorted distinct key list as a device tensor.
+
+    One all-gather of a fixed-capacity block per rank: slot 0 carries the rank's key count, the rest its keys
+    (real keys are non-negative as int64: group ids < 2^31). Every rank sees every count, so if some rank did not
+    fit, all ranks agree to repeat with a larger capacity - no separate size exchange.
+
+    With `ctx` (a _native.Context on the same device) the merge runs in libhbgpu's k_merge_keys on the context's
+    compute stream; with sync=False nothing waits on the host: the result is (padded keys, info) where info is a
+    device tensor [n_keys, overflow] - the caller checks it later (used inside timed loops once the capacity has
+    been learnt by a synchronous call)."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size(group)
+    dev = local_keys.device
+    n = int(local_keys.numel())
+    cap = _GATHER_CAP.get(group, 2048)
+    while True:
+        buf = torch.empty((cap + 1,), dtype=torch.int64, device=dev)
+        buf[0].fill_(n)
+        m = min(n, cap)
+        if m:
+            buf[1:1 + m] = local_keys[:m]
+        gathered = torch.empty((world, cap + 1), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered, buf, group=group)      # the one key exchange
+        if ctx is not None and world * cap <= 16384:
+            out = torch.empty((world * cap,), dtype=torch.int64, device=dev)
+            info = torch.empty((2,), dtype=torch.int64, device=dev)
+            ctx.merge_keys_device(gathered.data_ptr(), world, cap, out.data_ptr(), info.data_ptr())
+            if not sync:
+                return out, info
+            n_out, over = info.tolist()
+            if not over:
+                return out[:n_out]
+            counts = gathered[:, 0].tolist()
+        else:
+            counts = gathered[:, 0].tolist()
+            if max(counts) <= cap:
+                valid = torch.arange(cap, device=dev)[None, :] < gathered[:, :1]
+                return torch.unique(gathered[:, 1:][valid])
+        cap = 1 << (int(max(counts)) - 1).bit_length()
+        _GATHER_CAP[group] = cap
+
+
 def merge_keys(local_keys, device=None, group=None):
     """All-gather sorted distinct uint64 keys; returns the global sorted distinct key list (numpy uint64).
 
@@ -38,6 +86,8 @@ def merge_keys(local_keys, device=None, group=None):
     on_gpu = dist.get_backend(group) == "nccl"
     dev = torch.device("cuda", device if device is not None else torch.cuda.current_device()) if on_gpu else torch.device("cpu")
     mine = torch.from_numpy(np.ascontiguousarray(local_keys).view(np.int64)).to(dev)
+    if on_gpu:
+        return merge_keys_device(mine, group).cpu().numpy().view(np.uint64)
     count = torch.tensor([mine.numel()], dtype=torch.int64, device=dev)
     counts = [torch.zeros_like(count) for _ in range(world)]
     dist.all_gather(counts, count, group=group)

@@ -129,7 +129,9 @@ int hb_set_option(hb_ctx* ctx, const char* name, int64_t value);
            "profile": 1 = time every kernel class with CUDA events; "max_batch_frames";
            "fused": 0 = never use the one-CTA-per-frame kernel; "fused_lw_cap" / "fused_cell_cap": its
            shared-memory capacities (0 = automatic); "fused_stages", "fused_prefetch", "fused_batch_frames";
-           "copy_ranges": 0 = always copy whole frames; "force_radix_sort" (test hook) */
+           "copy_ranges": 0 = always copy whole frames; "force_radix_sort" (test hook);
+           "compute_stream": a cudaStream_t of the caller on which every kernel of the context is launched, so
+           that the caller's own stream-ordered work (events, collectives) brackets the search (0 = library stream) */
 
 /* Start an analysis over n_frames_total frames (the width of the occupancy matrix). */
 int hb_begin(hb_ctx* ctx, int64_t n_frames_total);
@@ -141,7 +143,8 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total);
  * Asynchronous: returns once the last batch is queued; buffers passed in may be reused after return. */
 int hb_submit_frames(hb_ctx* ctx, const float* xyz, int64_t n_atoms, int64_t n_frames, const float* box);
 
-/* Same, for coordinates already resident in device memory (the caller guarantees they are complete). */
+/* Same, for coordinates already resident in device memory (the caller guarantees they are complete, and keeps
+ * d_xyz / d_box valid and unchanged until hb_sync or hb_finalize returns: a batch may be re-run on overflow). */
 int hb_submit_frames_device(hb_ctx* ctx, const float* d_xyz, int64_t n_atoms, int64_t n_frames,
                             const float* d_box);
 
@@ -152,9 +155,15 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond);
  * (f & 31) of word (f >> 5) of row i is set iff bond i exists in frame f. */
 int hb_get_keys(hb_ctx* ctx, uint64_t* keys);
 int hb_get_bits(hb_ctx* ctx, uint32_t* words);
-/* Device-side access for collectives: copy keys / rows into caller-provided DEVICE buffers. */
+/* Device-side access for collectives: copy keys / rows into caller-provided DEVICE buffers. The copies are
+ * queued on the context's compute stream (see "compute_stream"); use hb_sync or that stream to wait for them. */
 int hb_get_keys_device(hb_ctx* ctx, uint64_t* d_keys);
 int hb_get_bits_device(hb_ctx* ctx, uint32_t* d_words);
+/* Multi-GPU exchange, merge step: d_gathered = all-gather of one [count, key_0 .. key_{cap-1}] block
+ * per rank (uint64, keys sorted ascending); writes the global sorted distinct keys to d_out (room for world*cap)
+ * and {n_out, overflow flag} to d_info. world*cap <= 16384. Queued on the compute stream, no host round trip. */
+int hb_merge_keys_device(hb_ctx* ctx, const uint64_t* d_gathered, int32_t world, int32_t cap, uint64_t* d_out,
+                         int64_t* d_info);
 /* Per-bond popcount over frames (occupancy numerator; network.py:99-107 filter_occupancy). */
 int hb_get_counts(hb_ctx* ctx, int64_t* counts);
 

@@ -194,3 +194,31 @@ def test_h2d_skips_inert_atom_ranges():
     k2, w2 = ctx.results()
     pin.free()
     assert np.array_equal(k1, k2) and np.array_equal(w1, w2) and len(k1) == len(ref)
+
+
+def test_merge_keys_kernel():
+    """hb_merge_keys_device: merge step of the multi-GPU key exchange (emulated gather buffers on one GPU)."""
+    import torch
+    from cgraphs_b200.mdhbond import _native
+    ctx = _native.Context(0)
+    rng = np.random.default_rng(3)
+    for world, cap, counts in [(3, 8, [5, 8, 0]), (8, 2048, [1507, 1490, 2048, 0, 1, 777, 1507, 1200]), (2, 4, [9, 2])]:
+        gathered = rng.integers(0, 1 << 62, size=(world, cap + 1), dtype=np.int64)     # padding = garbage
+        expect = []
+        for w, c in enumerate(counts):
+            keys = np.sort(rng.choice(5000, size=min(c, cap), replace=False).astype(np.int64) * 977)
+            gathered[w, 0] = c
+            gathered[w, 1:1 + len(keys)] = keys
+            expect.append(keys)
+        expect = np.unique(np.concatenate(expect))
+        g = torch.from_numpy(gathered).cuda()
+        out = torch.empty(world * cap, dtype=torch.int64, device="cuda")
+        info = torch.empty(2, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        ctx.merge_keys_device(g.data_ptr(), world, cap, out.data_ptr(), info.data_ptr())
+        ctx.sync()
+        n_out, over = info.tolist()
+        assert over == int(max(counts) > cap)
+        assert n_out == len(expect)
+        assert np.array_equal(out[:n_out].cpu().numpy(), expect)
+    ctx.close()
