@@ -99,10 +99,11 @@ __global__ void __launch_bounds__(32) k_rs_scatter(const unsigned long long* key
 // Small results (the common case: a few thousand distinct bonds): one CTA sorts (key, slot) pairs in shared
 // memory with a bitonic network; n <= SORT_SMALL_MAX, padded with the largest key to a power of two.
 #define SORT_SMALL_MAX 4096
-__global__ void __launch_bounds__(1024) k_sort_small(const unsigned long long* keys_in, const unsigned* vals_in, int n,
-                                                     unsigned long long* keys_out, unsigned* vals_out) {
+__global__ void __launch_bounds__(1024) k_sort_small(const unsigned long long* keys_in, const unsigned* vals_in,
+                                                     const int* n_ptr, unsigned long long* keys_out, unsigned* vals_out) {
     __shared__ unsigned long long k[SORT_SMALL_MAX];
     __shared__ unsigned v[SORT_SMALL_MAX];
+    const int n = min(*n_ptr, SORT_SMALL_MAX);     // (a larger count is caught by the host and redone with radix passes)
     int m = 1;
     while (m < n) m <<= 1;
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
@@ -132,12 +133,14 @@ __global__ void __launch_bounds__(1024) k_sort_small(const unsigned long long* k
 // sorts them (bitonic), drops duplicates and writes the global sorted distinct list; info[0] = its length,
 // info[1] = 1 if some rank had more than `cap` keys (the caller then repeats with a larger capacity).
 __global__ void __launch_bounds__(1024) k_merge_keys(const unsigned long long* gathered, int world, int cap, int m,
-                                                     unsigned long long* out, long long* info) {
+                                                     int sorted_runs, unsigned long long* out, long long* info) {
     extern __shared__ __align__(16) unsigned long long mk[];
     __shared__ int part[1024];
     __shared__ int over;
     if (threadIdx.x == 0) over = 0;
     __syncthreads();
+    // every rank's list is sorted: store odd lists reversed, so that the runs of length `cap` alternate
+    // ascending / descending and only the merge phases (size > cap) of the bitonic network are left to do
     for (int i = threadIdx.x; i < m; i += blockDim.x) {
         const int w = i / cap, j = i - w * cap;
         unsigned long long key = EMPTY_KEY;
@@ -146,10 +149,10 @@ __global__ void __launch_bounds__(1024) k_merge_keys(const unsigned long long* g
             if (j == 0 && cnt > cap) over = 1;
             if (j < cnt) key = gathered[(size_t)w * (cap + 1) + 1 + j];
         }
-        mk[i] = key;
+        mk[(w & 1) ? (w * cap + (cap - 1 - j)) : i] = key;
     }
     __syncthreads();
-    for (int size = 2; size <= m; size <<= 1)
+    for (int size = sorted_runs ? 2 * cap : 2; size <= m; size <<= 1)
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             for (int i = threadIdx.x; i < (m >> 1); i += blockDim.x) {
                 const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
@@ -178,9 +181,9 @@ __global__ void __launch_bounds__(1024) k_merge_keys(const unsigned long long* g
         if (mk[i] != EMPTY_KEY && (i == 0 || mk[i] != mk[i - 1])) out[pos++] = mk[i];
 }
 
-__global__ void k_gather_rows(const unsigned* bits, const unsigned* slots, int n, int wpr, unsigned* out) {
+__global__ void k_gather_rows(const unsigned* bits, const unsigned* slots, const int* n_ptr, int n_max, int wpr, unsigned* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t total = (size_t)n * wpr;
+    size_t total = (size_t)min(*n_ptr, n_max) * wpr;
     size_t stride = (size_t)gridDim.x * blockDim.x;
     for (; i < total; i += stride) {
         size_t row = i / wpr, col = i % wpr;

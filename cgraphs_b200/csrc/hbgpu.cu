@@ -1083,74 +1083,110 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
     }
     if (!ctx->running) return fail(ctx, HB_ERR_STATE, "hb_finalize before hb_begin");
     Trace tr(ctx, "finalize");
-    int rc = hb_sync(ctx);
-    if (rc) return rc;
-    tr.mark("sync");
     cudaStream_t st = ctx->s_compute;
-    int n = ctx->last_status[0];      // hb_sync just verified and read the status block; nothing ran since
+    const int wpr = ctx->bt.wpr;
+    int rc;
+    int n = 0;
+    bool settled = false;             // ev_run1 recorded and the stream drained
+    unsigned long long *k0 = nullptr, *k1 = nullptr;
+    unsigned *v0 = nullptr, *v1 = nullptr;
+    CK(cudaStreamSynchronize(ctx->s_copy));
+    for (int attempt = 0;; ++attempt) {
+        if (attempt > 40) return fail(ctx, HB_ERR_NOMEM, "hb_finalize: the bond table kept overflowing");
+        // Small tables (the common case): compaction, sort and row gather are queued behind the search without
+        // knowing the bond count on the host; ONE read back at the end both verifies the run and delivers the
+        // count. Large tables first settle (hb_sync) to size the radix passes.
+        const bool speculative = ctx->table_cap <= 2ll * SORT_SMALL_MAX && !ctx->opt_force_radix;
+        long long n_max = speculative ? ctx->table_cap / 2 : 0;
+        if (!speculative) {
+            if ((rc = hb_sync(ctx))) return rc;
+            n = ctx->last_status[0];
+            n_max = std::max(n, 1);
+        }
+        tr.mark("sync");
+        const int nblk = (int)((n_max + RS_TILE - 1) / RS_TILE);
+        if ((size_t)n_max > ctx->fin_cap) {           // (re)allocate the sort buffers with headroom
+            size_t cap2 = std::max<size_t>((size_t)n_max * 2, 4096);
+            for (int k = 0; k < 2; ++k) {
+                if (ctx->fin_k[k]) cudaFree(ctx->fin_k[k]);
+                if (ctx->fin_v[k]) cudaFree(ctx->fin_v[k]);
+                ctx->fin_k[k] = nullptr; ctx->fin_v[k] = nullptr;
+            }
+            ctx->fin_cap = 0;
+            for (int k = 0; k < 2; ++k) {
+                CK(cudaMalloc((void**)&ctx->fin_k[k], cap2 * 8));
+                CK(cudaMalloc((void**)&ctx->fin_v[k], cap2 * 4));
+            }
+            ctx->fin_cap = cap2;
+        }
+        size_t hist_need = (size_t)256 * std::max(nblk, 1) * 4;
+        if (hist_need > ctx->fin_hist_cap) {
+            if (ctx->fin_hist) cudaFree(ctx->fin_hist);
+            ctx->fin_hist = nullptr; ctx->fin_hist_cap = 0;
+            CK(cudaMalloc((void**)&ctx->fin_hist, hist_need * 2));
+            ctx->fin_hist_cap = hist_need * 2;
+        }
+        if (!ctx->fin_counter) CK(cudaMalloc((void**)&ctx->fin_counter, 4));
+        size_t rows_need = (size_t)n_max * (size_t)wpr * 4;
+        if (rows_need > ctx->out_rows_cap) {
+            if (ctx->d_out_rows) cudaFree(ctx->d_out_rows);
+            ctx->d_out_rows = nullptr; ctx->out_rows_cap = 0;
+            CK(cudaMalloc((void**)&ctx->d_out_rows, rows_need * 2));
+            ctx->out_rows_cap = rows_need * 2;
+        }
+        tr.mark("alloc");
+        k0 = ctx->fin_k[0]; k1 = ctx->fin_k[1];
+        v0 = ctx->fin_v[0]; v1 = ctx->fin_v[1];
+        unsigned* hist = ctx->fin_hist;
+        int* counter = ctx->fin_counter;
+        CK(cudaMemsetAsync(counter, 0, 4, st));
+        unsigned cap = ctx->bt.mask + 1u;
+        k_compact<<<(cap + 255) / 256, 256, 0, st>>>(ctx->bt, k0, v0, counter);
+        if (speculative || (n > 1 && n <= SORT_SMALL_MAX && !ctx->opt_force_radix)) {
+            k_sort_small<<<1, 1024, 0, st>>>(k0, v0, counter, k1, v1);
+            std::swap(k0, k1);
+            std::swap(v0, v1);
+            ctx->tm.n_launches += 3;
+        } else if (n > 1) {
+            for (int pass = 0; pass < 8; ++pass) {
+                int shift = pass * 8;
+                k_rs_hist<<<nblk, 256, 0, st>>>(k0, n, shift, hist);
+                k_rs_scan<<<1, 1024, 0, st>>>(hist, (size_t)256 * nblk);
+                k_rs_scatter<<<nblk, 32, 0, st>>>(k0, v0, n, shift, hist, k1, v1);
+                std::swap(k0, k1);
+                std::swap(v0, v1);
+            }
+            ctx->tm.n_launches += 26;
+        } else {
+            ctx->tm.n_launches += 2;
+        }
+        k_gather_rows<<<1184, 256, 0, st>>>(ctx->bt.bits, v0, counter, (int)n_max, wpr, ctx->d_out_rows);
+        CK(cudaGetLastError());
+        if (!speculative) break;
+        // the one round trip of a speculative finalize
+        CK(cudaMemcpyAsync(ctx->h_verify, ctx->bt.n_keys, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ctx->ev_run1, st));
+        CK(cudaStreamSynchronize(st));
+        memcpy(ctx->last_status, ctx->h_verify, 6 * sizeof(int));
+        n = ctx->last_status[0];
+        const bool bad = ctx->last_status[1] || ctx->last_status[2] || (long long)n * 2 > ctx->table_cap;
+        if (!bad) {
+            for (auto& sl : ctx->slots) sl.busy = false;
+            drain_events(ctx);
+            settled = true;
+            break;
+        }
+        if ((rc = full_verify(ctx))) return rc;       // grows the table / re-runs the in-flight batches, then retry
+    }
     {
         unsigned long long hits;
         memcpy(&hits, ctx->last_status + 4, sizeof(hits));
         ctx->tm.pairs_emitted = (long long)hits;
     }
-    int wpr = ctx->bt.wpr;
-    size_t nn = std::max(n, 1);
-    int nblk = (n + RS_TILE - 1) / RS_TILE;
-    if (nn > ctx->fin_cap) {                      // (re)allocate the sort buffers with headroom
-        size_t cap2 = std::max<size_t>(nn * 2, 4096);
-        for (int k = 0; k < 2; ++k) {
-            if (ctx->fin_k[k]) cudaFree(ctx->fin_k[k]);
-            if (ctx->fin_v[k]) cudaFree(ctx->fin_v[k]);
-            ctx->fin_k[k] = nullptr; ctx->fin_v[k] = nullptr;
-        }
-        ctx->fin_cap = 0;
-        for (int k = 0; k < 2; ++k) {
-            CK(cudaMalloc((void**)&ctx->fin_k[k], cap2 * 8));
-            CK(cudaMalloc((void**)&ctx->fin_v[k], cap2 * 4));
-        }
-        ctx->fin_cap = cap2;
+    if (!settled) {
+        CK(cudaEventRecord(ctx->ev_run1, st));
+        CK(cudaStreamSynchronize(st));
     }
-    size_t hist_need = (size_t)256 * std::max(nblk, 1) * 4;
-    if (hist_need > ctx->fin_hist_cap) {
-        if (ctx->fin_hist) cudaFree(ctx->fin_hist);
-        ctx->fin_hist = nullptr; ctx->fin_hist_cap = 0;
-        CK(cudaMalloc((void**)&ctx->fin_hist, hist_need * 2));
-        ctx->fin_hist_cap = hist_need * 2;
-    }
-    if (!ctx->fin_counter) CK(cudaMalloc((void**)&ctx->fin_counter, 4));
-    size_t rows_need = nn * (size_t)wpr * 4;
-    if (rows_need > ctx->out_rows_cap) {
-        if (ctx->d_out_rows) cudaFree(ctx->d_out_rows);
-        ctx->d_out_rows = nullptr; ctx->out_rows_cap = 0;
-        CK(cudaMalloc((void**)&ctx->d_out_rows, rows_need * 2));
-        ctx->out_rows_cap = rows_need * 2;
-    }
-    tr.mark("alloc");
-    unsigned long long *k0 = ctx->fin_k[0], *k1 = ctx->fin_k[1];
-    unsigned *v0 = ctx->fin_v[0], *v1 = ctx->fin_v[1], *hist = ctx->fin_hist;
-    int* counter = ctx->fin_counter;
-    CK(cudaMemsetAsync(counter, 0, 4, st));
-    unsigned cap = ctx->bt.mask + 1u;
-    k_compact<<<(cap + 255) / 256, 256, 0, st>>>(ctx->bt, k0, v0, counter);
-    ctx->tm.n_launches += 1 + (n > 0 ? 1 : 0) + (n > 1 ? ((n <= SORT_SMALL_MAX && !ctx->opt_force_radix) ? 1 : 24) : 0);
-    if (n > 1 && n <= SORT_SMALL_MAX && !ctx->opt_force_radix) {
-        k_sort_small<<<1, 1024, 0, st>>>(k0, v0, n, k1, v1);
-        std::swap(k0, k1);
-        std::swap(v0, v1);
-    } else if (n > 1) {
-        for (int pass = 0; pass < 8; ++pass) {
-            int shift = pass * 8;
-            k_rs_hist<<<nblk, 256, 0, st>>>(k0, n, shift, hist);
-            k_rs_scan<<<1, 1024, 0, st>>>(hist, (size_t)256 * nblk);
-            k_rs_scatter<<<nblk, 32, 0, st>>>(k0, v0, n, shift, hist, k1, v1);
-            std::swap(k0, k1);
-            std::swap(v0, v1);
-        }
-    }
-    if (n > 0) k_gather_rows<<<1184, 256, 0, st>>>(ctx->bt.bits, v0, n, wpr, ctx->d_out_rows);
-    CK(cudaGetLastError());
-    CK(cudaEventRecord(ctx->ev_run1, st));
-    CK(cudaStreamSynchronize(st));
     {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->ev_run0, ctx->ev_run1) == cudaSuccess) ctx->tm.ms_run = ms;
@@ -1212,11 +1248,12 @@ int hb_merge_keys_device(hb_ctx* ctx, const uint64_t* d_gathered, int32_t world,
     long long total = (long long)world * cap;
     int m = 2;
     while (m < total) m <<= 1;
+    const int pow2_cap = (cap & (cap - 1)) == 0 && cap >= 2;     // merge-only network needs power-of-two runs
     if (total > 16384) return fail(ctx, HB_ERR_ARG, "hb_merge_keys_device: more than 16384 gathered keys; merge on the host");
     CK(cudaSetDevice(ctx->device));
     size_t smem = (size_t)m * 8;
     CK(cudaFuncSetAttribute(k_merge_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_merge_keys<<<1, 1024, smem, ctx->s_compute>>>((const unsigned long long*)d_gathered, world, cap, m,
+    k_merge_keys<<<1, 1024, smem, ctx->s_compute>>>((const unsigned long long*)d_gathered, world, cap, m, pow2_cap,
                                                      (unsigned long long*)d_out, (long long*)d_info);
     CK(cudaGetLastError());
     ctx->tm.n_launches += 1;
