@@ -44,7 +44,7 @@ struct FusedCfg {
     int stages;               // ring depth
     int prefetch;             // tiles pulled into L2 ahead of the ring
     unsigned stage_bytes;     // bytes of one stage (multiple of 16)
-    unsigned off_spos, off_union, off_lw, off_cells, off_near, off_cand, off_bar;   // byte offsets in dynamic smem
+    unsigned off_union, off_lw, off_cells, off_near, off_cand, off_bar;   // byte offsets in dynamic smem
     unsigned smem_bytes;
     unsigned long long buf_begin, buf_end;   // address range of the coordinate batch (bounds for bulk copies)
 };
@@ -58,7 +58,7 @@ struct FusedShared {          // small fixed part at the start of dynamic shared
     int n_tasks;
     int overflow;
     int warp_sum[FUSED_CWARPS];
-    unsigned stage_head[FUSED_MAX_STAGES];   // byte offset of the tile's first water inside the stage
+    unsigned stage_head[FUSED_MAX_STAGES];   // 1: the tile touches the edge of the batch buffer (only [lo, hi) was copied)
     unsigned stage_lo[FUSED_MAX_STAGES];     // [lo, hi): bytes of the stage the bulk copy filled
     unsigned stage_hi[FUSED_MAX_STAGES];
 };
@@ -171,11 +171,11 @@ template <bool PBC>
 __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(BatchView bv, DevTopo tp, RunParams rp, BondTable bt, FusedCfg fc) {
     extern __shared__ __align__(16) unsigned char smem[];
     FusedShared* sh = reinterpret_cast<FusedShared*>(smem);
-    float4* spos = reinterpret_cast<float4*>(smem + fc.off_spos);          // selection points, gather order
-    float4* sorted1 = reinterpret_cast<float4*>(smem + fc.off_union);      // phase B: selection points in g1 cell order
+    // union region, phases A/B: [sorted1][tile ring][candidate buffers];  phase C: [sorted1][psorted][pairs][tasks][flags]
+    float4* sorted1 = reinterpret_cast<float4*>(smem + fc.off_union);      // selection points (g1 cell order with waters)
     unsigned char* ring = smem + fc.off_union + (size_t)fc.sel_cap * 16;   // phase B: tile stages
-    float4* psorted = reinterpret_cast<float4*>(smem + fc.off_union);      // phase C: aliases sorted1 + ring
-    unsigned* pairs = reinterpret_cast<unsigned*>(smem + fc.off_union + ((size_t)fc.sel_cap + fc.lw_cap) * 16);
+    float4* psorted = reinterpret_cast<float4*>(ring);                     // phase C: selection + local waters, g2 order
+    unsigned* pairs = reinterpret_cast<unsigned*>(psorted + fc.sel_cap + fc.lw_cap);
     uint2* tasks = reinterpret_cast<uint2*>(pairs + fc.pair_cap);          // phase C: (pair | flag, hydrogen atom)
     unsigned* pflags = reinterpret_cast<unsigned*>(tasks + fc.task_cap);   // phase C: angle flags of the chunk's pairs
     float4* lw = reinterpret_cast<float4*>(smem + fc.off_lw);
@@ -195,6 +195,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
     const bool wa = rp.method == HB_METHOD_WATER_AROUND;
     const bool scan_waters = wa && nwp > 0 && nsel > 0;
     const bool stream = scan_waters && fc.regular;
+    // selection points in gather order are only needed until the g1 sort, so they borrow the candidate buffers;
+    // without a water scan there is no g1 sort and they go straight to sorted1
+    float4* spos = scan_waters ? cand : sorted1;
     const int ntiles = (nwp + FUSED_TILE - 1) / FUSED_TILE;
     const int stride12 = fc.w_stride * 12;
 
@@ -250,7 +253,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
                 const unsigned long long end = (ga + (unsigned long long)((nw - 1) * stride12 + 12) + 15ull) & ~15ull;
                 const unsigned long long c0 = start > lim_lo ? start : lim_lo, c1 = end < lim_hi ? end : lim_hi;
                 const bool partial = c0 != start || c1 != end;     // tile touches the edge of the batch buffer
-                sh->stage_head[st] = head | (partial ? 0x80000000u : 0u);
+                sh->stage_head[st] = partial ? 1u : 0u;
                 unsigned char* dst = ring + (size_t)st * fc.stage_bytes;
                 if (c1 > c0) {
                     const unsigned lo = (unsigned)(c0 - start), bytes = (unsigned)(c1 - c0);
@@ -342,7 +345,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
         for (int i = tid; i < (g1.ncell + 31) / 32; i += FUSED_CONSUMERS) near[i] = 0u;
         block_cell_sort<PBC>(g1, cells, sorted1, nsel, [&](int i) { return spos[i]; }, sh);   // (syncs cover the zeroing)
         for (int i = tid; i < nsel; i += FUSED_CONSUMERS) {
-            const float4 p = spos[i];
+            const float4 p = sorted1[i];
             int cx, cy, cz;
             cell3<PBC>(g1, p.x, p.y, p.z, cx, cy, cz);
             if constexpr (PBC) {
@@ -393,23 +396,22 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
         };
         int st = 0;
         unsigned parity = 0;
-        const unsigned my_off = (unsigned)(tid * stride12);
+        // a tile advances by 256 * stride * 12 bytes, a multiple of 16: the offset of its first water inside the
+        // 16-byte aligned stage is the same for every tile of the frame
+        const unsigned my_off = stream ? (unsigned)(((unsigned long long)(uintptr_t)(xyz + 3ll * tp.wat_atom[w0]) & 15ull) +
+                                                    (unsigned long long)(tid * stride12)) : 0u;
         for (int t = 0; t < ntiles; ++t) {
             const int i = t * FUSED_TILE + tid;
             const bool live = i < nwp;
             float x = 0.f, y = 0.f, z = 0.f;
             if (stream) {
                 if (!mbar_wait(&full[st], parity)) { sh->overflow = 2; break; }
-                const unsigned head = sh->stage_head[st];
-                if (live) {
-                    const unsigned off = (head & 0x7fffffffu) + my_off;
-                    if (!(head & 0x80000000u) || (off >= sh->stage_lo[st] && off + 12u <= sh->stage_hi[st])) {
-                        const float* f = reinterpret_cast<const float*>(ring + (size_t)st * fc.stage_bytes + off);
-                        x = f[0]; y = f[1]; z = f[2];
-                    } else {                            // bytes outside the batch buffer were not copied: plain loads
-                        const float* f = xyz + 3ll * tp.wat_atom[w0 + i];
-                        x = f[0]; y = f[1]; z = f[2];
-                    }
+                const float* f = reinterpret_cast<const float*>(ring + (size_t)st * fc.stage_bytes + my_off);
+                x = f[0]; y = f[1]; z = f[2];             // (always inside the stage; meaningful if the bytes were copied)
+                const unsigned partial = sh->stage_head[st];
+                if (partial && live && !(my_off >= sh->stage_lo[st] && my_off + 12u <= sh->stage_hi[st])) {
+                    const float* g = xyz + 3ll * tp.wat_atom[w0 + i];   // bytes outside the batch buffer were not copied
+                    x = g[0]; y = g[1]; z = g[2];
                 }
                 __syncwarp();                           // every lane has read its water before the stage is released
                 if (lane == 0) mbar_arrive(&empty[st]);
@@ -458,7 +460,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
     // ---- phase C: pair search over selection + local waters --------------------------------------------
     const int nlw = sh->n_lw;
     const int np = nsel + nlw;
-    block_cell_sort<PBC>(sh->g2, cells, psorted, np, [&](int i) { return i < nsel ? spos[i] : lw[i - nsel]; }, sh);
+    block_cell_sort<PBC>(sh->g2, cells, psorted, np, [&](int i) { return i < nsel ? sorted1[i] : lw[i - nsel]; }, sh);
     int nhit = 0;
     const FrameGrid g2 = sh->g2;
     phase_done(4);

@@ -83,8 +83,8 @@ struct hb_ctx {
     long long opt_fused_lw_cap = 0;   // 0: automatic
     long long opt_fused_cell_cap = 0; // 0: automatic
     long long opt_fused_pair_cap = 0; // 0: automatic
-    long long opt_fused_stages = 2;   // depth of the water-tile ring
-    long long opt_fused_prefetch = 8; // tiles prefetched into L2 ahead of the ring
+    long long opt_fused_stages = 3;   // depth of the water-tile ring
+    long long opt_fused_prefetch = 2; // tiles prefetched into L2 ahead of the ring (more evicts lines before use)
     int fused_grow = 0;
 
     // fused-path plan (valid for the current run)
@@ -559,23 +559,24 @@ static bool plan_fused(hb_ctx* ctx, int grow = 0) {
     }
     fc.lw_cap = (int)lw;
     if ((long long)fc.sel_cap + fc.lw_cap > 65535) return false;      // 16-bit cell cursors / pair indices
-    long long cc = ctx->opt_fused_cell_cap ? ctx->opt_fused_cell_cap : 4096;
+    long long cc = ctx->opt_fused_cell_cap ? ctx->opt_fused_cell_cap : 3712;   // 16-bit counters: 7.3 kB
     fc.cell_cap = (int)std::min<long long>(cc, 32768);
     fc.pair_cap = (int)((ctx->opt_fused_pair_cap ? ctx->opt_fused_pair_cap : 2048) << grow);
     fc.regular = (wa && ctx->water_regular && ctx->water_stride <= 8) ? 1 : 0;
     fc.w_stride = ctx->water_stride;
     fc.stages = fc.regular ? (int)std::min<long long>(std::max<long long>(ctx->opt_fused_stages, 2), FUSED_MAX_STAGES) : 0;
     fc.prefetch = (int)ctx->opt_fused_prefetch;
-    fc.stage_bytes = fc.regular ? (unsigned)(((FUSED_TILE - 1) * fc.w_stride * 12 + 12 + 15 + 15 + 16) & ~15) : 0u;
+    fc.stage_bytes = fc.regular ? (unsigned)(((FUSED_TILE - 1) * fc.w_stride * 12 + 12 + 15 + 15) & ~15) : 0u;
     size_t off = (sizeof(FusedShared) + 15) & ~(size_t)15;
-    fc.off_spos = (unsigned)off;
-    off += (size_t)fc.sel_cap * 16;
     fc.off_union = (unsigned)off;
+    // phases A/B: [sorted1][tile ring][candidate buffers (before the g1 sort: selection points in gather order)]
     size_t un_b = (size_t)fc.sel_cap * 16 + (size_t)fc.stages * fc.stage_bytes;
-    fc.off_cand = (unsigned)(off + un_b);                             // candidate buffers live only in phase B
-    un_b += wa ? (size_t)FUSED_CWARPS * FUSED_CAND * 16 : 0;
+    fc.off_cand = (unsigned)(off + un_b);
+    un_b += wa ? std::max((size_t)FUSED_CWARPS * FUSED_CAND * 16, (size_t)fc.sel_cap * 16) : 0;
+    // phase C: [sorted1][psorted][pairs][tasks][flags]
     fc.task_cap = 1536 << grow;
-    size_t un_c = ((size_t)fc.sel_cap + fc.lw_cap) * 16 + (size_t)fc.pair_cap * 4 + (size_t)fc.task_cap * 8 + FUSED_CONSUMERS * 4;
+    size_t un_c = (size_t)fc.sel_cap * 16 + ((size_t)fc.sel_cap + fc.lw_cap) * 16 + (size_t)fc.pair_cap * 4 +
+                  (size_t)fc.task_cap * 8 + FUSED_CONSUMERS * 4;
     off += (std::max(un_b, un_c) + 15) & ~(size_t)15;
     fc.off_lw = (unsigned)off;
     off += (size_t)fc.lw_cap * 16;
