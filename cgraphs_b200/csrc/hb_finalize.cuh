@@ -128,6 +128,14 @@ __global__ void __launch_bounds__(1024) k_sort_small(const unsigned long long* k
     for (int i = threadIdx.x; i < n; i += blockDim.x) { keys_out[i] = k[i]; vals_out[i] = v[i]; }
 }
 
+// Multi-GPU key exchange, send side: this rank's block of the all-gather = [count, key_0 .. key_{cap-1}].
+__global__ void k_pack_block(const unsigned long long* keys, const int* n_ptr, int n_max, unsigned long long* block, int cap) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = min(*n_ptr, n_max);
+    if (i == 0) block[0] = (unsigned long long)n;
+    else if (i <= cap) block[i] = (i - 1 < n) ? keys[i - 1] : EMPTY_KEY;
+}
+
 // Merge step of the multi-GPU key exchange: `gathered` holds, per rank, [count, key_0 .. key_{cap-1}] as the
 // all-gather delivered it (keys sorted, padding arbitrary). One CTA loads the valid keys into shared memory,
 // sorts them (bitonic), drops duplicates and writes the global sorted distinct list; info[0] = its length,

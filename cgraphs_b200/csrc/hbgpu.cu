@@ -138,6 +138,9 @@ struct hb_ctx {
     unsigned* fin_hist = nullptr;
     int* fin_counter = nullptr;
     size_t fin_cap = 0, fin_hist_cap = 0;
+    unsigned long long* fin_sorted_k = nullptr;   // sorted keys of the queued / last finalize
+    long long fin_n_max = 0;
+    bool fin_queued = false, fin_speculative = false;
     long long n_sel_total = 0, n_wat_total = 0;
     // trajectory mode: atom ranges [begin, end) that hold every atom the kernels read; the rest of a frame
     // (inert atoms) is never copied to the device. Empty = copy whole frames.
@@ -656,6 +659,7 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     ctx->batch_counter = 0;
     ctx->table_grows = 0;
     ctx->fused_fallbacks = 0;
+    ctx->fin_queued = false;
     for (auto& sl : ctx->slots) sl.busy = false;
     int rc;
     if (reuse) {
@@ -1075,6 +1079,112 @@ int hb_sync(hb_ctx* ctx) {
     return HB_OK;
 }
 
+// Queue compaction, key sort and row gather behind the search. Small tables (the common case) are handled
+// speculatively: nothing is known about the bond count on the host, the kernels read it from the device
+// counter, and one status read back at the end verifies the run and delivers the count. Large tables first
+// settle (hb_sync) to size the radix passes. Leaves the sorted keys / slots in ctx->fin_sorted_*.
+static int queue_finalize(hb_ctx* ctx, bool speculative, int* n_known) {
+    cudaStream_t st = ctx->s_compute;
+    const int wpr = ctx->bt.wpr;
+    int rc, n = 0;
+    long long n_max = speculative ? ctx->table_cap / 2 : 0;
+    if (!speculative) {
+        if ((rc = hb_sync(ctx))) return rc;
+        n = ctx->last_status[0];
+        n_max = std::max(n, 1);
+    }
+    const int nblk = (int)((n_max + RS_TILE - 1) / RS_TILE);
+    if ((size_t)n_max > ctx->fin_cap) {           // (re)allocate the sort buffers with headroom
+        size_t cap2 = std::max<size_t>((size_t)n_max * 2, 4096);
+        for (int k = 0; k < 2; ++k) {
+            if (ctx->fin_k[k]) cudaFree(ctx->fin_k[k]);
+            if (ctx->fin_v[k]) cudaFree(ctx->fin_v[k]);
+            ctx->fin_k[k] = nullptr; ctx->fin_v[k] = nullptr;
+        }
+        ctx->fin_cap = 0;
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaMalloc((void**)&ctx->fin_k[k], cap2 * 8));
+            CK(cudaMalloc((void**)&ctx->fin_v[k], cap2 * 4));
+        }
+        ctx->fin_cap = cap2;
+    }
+    size_t hist_need = (size_t)256 * std::max(nblk, 1) * 4;
+    if (hist_need > ctx->fin_hist_cap) {
+        if (ctx->fin_hist) cudaFree(ctx->fin_hist);
+        ctx->fin_hist = nullptr; ctx->fin_hist_cap = 0;
+        CK(cudaMalloc((void**)&ctx->fin_hist, hist_need * 2));
+        ctx->fin_hist_cap = hist_need * 2;
+    }
+    if (!ctx->fin_counter) CK(cudaMalloc((void**)&ctx->fin_counter, 4));
+    size_t rows_need = (size_t)n_max * (size_t)wpr * 4;
+    if (rows_need > ctx->out_rows_cap) {
+        if (ctx->d_out_rows) cudaFree(ctx->d_out_rows);
+        ctx->d_out_rows = nullptr; ctx->out_rows_cap = 0;
+        CK(cudaMalloc((void**)&ctx->d_out_rows, rows_need * 2));
+        ctx->out_rows_cap = rows_need * 2;
+    }
+    unsigned long long *k0 = ctx->fin_k[0], *k1 = ctx->fin_k[1];
+    unsigned *v0 = ctx->fin_v[0], *v1 = ctx->fin_v[1];
+    unsigned* hist = ctx->fin_hist;
+    int* counter = ctx->fin_counter;
+    CK(cudaMemsetAsync(counter, 0, 4, st));
+    unsigned cap = ctx->bt.mask + 1u;
+    k_compact<<<(cap + 255) / 256, 256, 0, st>>>(ctx->bt, k0, v0, counter);
+    if (speculative || (n > 1 && n <= SORT_SMALL_MAX && !ctx->opt_force_radix)) {
+        k_sort_small<<<1, 1024, 0, st>>>(k0, v0, counter, k1, v1);
+        std::swap(k0, k1);
+        std::swap(v0, v1);
+        ctx->tm.n_launches += 3;
+    } else if (n > 1) {
+        for (int pass = 0; pass < 8; ++pass) {
+            int shift = pass * 8;
+            k_rs_hist<<<nblk, 256, 0, st>>>(k0, n, shift, hist);
+            k_rs_scan<<<1, 1024, 0, st>>>(hist, (size_t)256 * nblk);
+            k_rs_scatter<<<nblk, 32, 0, st>>>(k0, v0, n, shift, hist, k1, v1);
+            std::swap(k0, k1);
+            std::swap(v0, v1);
+        }
+        ctx->tm.n_launches += 26;
+    } else {
+        ctx->tm.n_launches += 2;
+    }
+    k_gather_rows<<<1184, 256, 0, st>>>(ctx->bt.bits, v0, counter, (int)n_max, wpr, ctx->d_out_rows);
+    CK(cudaGetLastError());
+    ctx->fin_sorted_k = k0;
+    ctx->fin_n_max = n_max;
+    if (speculative) {   // the read back that verifies the run, and the end-of-run time stamp
+        CK(cudaMemcpyAsync(ctx->h_verify, ctx->bt.n_keys, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ctx->ev_run1, st));
+    }
+    ctx->fin_queued = true;
+    ctx->fin_speculative = speculative;
+    *n_known = n;
+    return HB_OK;
+}
+
+static bool finalize_can_speculate(hb_ctx* ctx) { return ctx->table_cap <= 2ll * SORT_SMALL_MAX && !ctx->opt_force_radix; }
+
+int hb_finalize_async(hb_ctx* ctx) {
+    if (!ctx) return HB_ERR_ARG;
+    if (!ctx->running) return fail(ctx, HB_ERR_STATE, "hb_finalize_async before hb_begin");
+    if (ctx->fin_queued || !finalize_can_speculate(ctx)) return HB_OK;    // large tables: hb_finalize does it all
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->s_copy));
+    int n;
+    return queue_finalize(ctx, true, &n);
+}
+
+int hb_pack_keys_device(hb_ctx* ctx, uint64_t* d_block, int32_t cap) {
+    if (!ctx || !d_block || cap < 1) return HB_ERR_ARG;
+    if (!ctx->fin_queued && !ctx->finalized) return fail(ctx, HB_ERR_STATE, "hb_pack_keys_device before hb_finalize_async / hb_finalize");
+    CK(cudaSetDevice(ctx->device));
+    k_pack_block<<<(cap + 1 + 255) / 256, 256, 0, ctx->s_compute>>>(ctx->fin_sorted_k, ctx->fin_counter, (int)ctx->fin_n_max,
+                                                                     (unsigned long long*)d_block, cap);
+    CK(cudaGetLastError());
+    ctx->tm.n_launches += 1;
+    return HB_OK;
+}
+
 int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
     if (!ctx) return HB_ERR_ARG;
     if (ctx->finalized && !ctx->running) {   // idempotent
@@ -1089,84 +1199,13 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
     int rc;
     int n = 0;
     bool settled = false;             // ev_run1 recorded and the stream drained
-    unsigned long long *k0 = nullptr, *k1 = nullptr;
-    unsigned *v0 = nullptr, *v1 = nullptr;
     CK(cudaStreamSynchronize(ctx->s_copy));
     for (int attempt = 0;; ++attempt) {
         if (attempt > 40) return fail(ctx, HB_ERR_NOMEM, "hb_finalize: the bond table kept overflowing");
-        // Small tables (the common case): compaction, sort and row gather are queued behind the search without
-        // knowing the bond count on the host; ONE read back at the end both verifies the run and delivers the
-        // count. Large tables first settle (hb_sync) to size the radix passes.
-        const bool speculative = ctx->table_cap <= 2ll * SORT_SMALL_MAX && !ctx->opt_force_radix;
-        long long n_max = speculative ? ctx->table_cap / 2 : 0;
-        if (!speculative) {
-            if ((rc = hb_sync(ctx))) return rc;
-            n = ctx->last_status[0];
-            n_max = std::max(n, 1);
-        }
-        tr.mark("sync");
-        const int nblk = (int)((n_max + RS_TILE - 1) / RS_TILE);
-        if ((size_t)n_max > ctx->fin_cap) {           // (re)allocate the sort buffers with headroom
-            size_t cap2 = std::max<size_t>((size_t)n_max * 2, 4096);
-            for (int k = 0; k < 2; ++k) {
-                if (ctx->fin_k[k]) cudaFree(ctx->fin_k[k]);
-                if (ctx->fin_v[k]) cudaFree(ctx->fin_v[k]);
-                ctx->fin_k[k] = nullptr; ctx->fin_v[k] = nullptr;
-            }
-            ctx->fin_cap = 0;
-            for (int k = 0; k < 2; ++k) {
-                CK(cudaMalloc((void**)&ctx->fin_k[k], cap2 * 8));
-                CK(cudaMalloc((void**)&ctx->fin_v[k], cap2 * 4));
-            }
-            ctx->fin_cap = cap2;
-        }
-        size_t hist_need = (size_t)256 * std::max(nblk, 1) * 4;
-        if (hist_need > ctx->fin_hist_cap) {
-            if (ctx->fin_hist) cudaFree(ctx->fin_hist);
-            ctx->fin_hist = nullptr; ctx->fin_hist_cap = 0;
-            CK(cudaMalloc((void**)&ctx->fin_hist, hist_need * 2));
-            ctx->fin_hist_cap = hist_need * 2;
-        }
-        if (!ctx->fin_counter) CK(cudaMalloc((void**)&ctx->fin_counter, 4));
-        size_t rows_need = (size_t)n_max * (size_t)wpr * 4;
-        if (rows_need > ctx->out_rows_cap) {
-            if (ctx->d_out_rows) cudaFree(ctx->d_out_rows);
-            ctx->d_out_rows = nullptr; ctx->out_rows_cap = 0;
-            CK(cudaMalloc((void**)&ctx->d_out_rows, rows_need * 2));
-            ctx->out_rows_cap = rows_need * 2;
-        }
-        tr.mark("alloc");
-        k0 = ctx->fin_k[0]; k1 = ctx->fin_k[1];
-        v0 = ctx->fin_v[0]; v1 = ctx->fin_v[1];
-        unsigned* hist = ctx->fin_hist;
-        int* counter = ctx->fin_counter;
-        CK(cudaMemsetAsync(counter, 0, 4, st));
-        unsigned cap = ctx->bt.mask + 1u;
-        k_compact<<<(cap + 255) / 256, 256, 0, st>>>(ctx->bt, k0, v0, counter);
-        if (speculative || (n > 1 && n <= SORT_SMALL_MAX && !ctx->opt_force_radix)) {
-            k_sort_small<<<1, 1024, 0, st>>>(k0, v0, counter, k1, v1);
-            std::swap(k0, k1);
-            std::swap(v0, v1);
-            ctx->tm.n_launches += 3;
-        } else if (n > 1) {
-            for (int pass = 0; pass < 8; ++pass) {
-                int shift = pass * 8;
-                k_rs_hist<<<nblk, 256, 0, st>>>(k0, n, shift, hist);
-                k_rs_scan<<<1, 1024, 0, st>>>(hist, (size_t)256 * nblk);
-                k_rs_scatter<<<nblk, 32, 0, st>>>(k0, v0, n, shift, hist, k1, v1);
-                std::swap(k0, k1);
-                std::swap(v0, v1);
-            }
-            ctx->tm.n_launches += 26;
-        } else {
-            ctx->tm.n_launches += 2;
-        }
-        k_gather_rows<<<1184, 256, 0, st>>>(ctx->bt.bits, v0, counter, (int)n_max, wpr, ctx->d_out_rows);
-        CK(cudaGetLastError());
-        if (!speculative) break;
+        if (!ctx->fin_queued && (rc = queue_finalize(ctx, finalize_can_speculate(ctx), &n))) return rc;
+        tr.mark("queued");
+        if (!ctx->fin_speculative) break;
         // the one round trip of a speculative finalize
-        CK(cudaMemcpyAsync(ctx->h_verify, ctx->bt.n_keys, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CK(cudaEventRecord(ctx->ev_run1, st));
         CK(cudaStreamSynchronize(st));
         memcpy(ctx->last_status, ctx->h_verify, 6 * sizeof(int));
         n = ctx->last_status[0];
@@ -1177,6 +1216,8 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
             settled = true;
             break;
         }
+        ctx->fin_queued = false;                      // what was queued (and anything built on it) is void
+        ctx->tm.finalize_retries++;
         if ((rc = full_verify(ctx))) return rc;       // grows the table / re-runs the in-flight batches, then retry
     }
     {
@@ -1192,6 +1233,8 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->ev_run0, ctx->ev_run1) == cudaSuccess) ctx->tm.ms_run = ms;
     }
+    unsigned long long* k0 = ctx->fin_sorted_k;
+    ctx->fin_queued = false;
     ctx->d_out_keys = k0;
     tr.mark("sort+gather");
     if (ctx->trace && ctx->bt.phase_cycles && ctx->tm.fused_frames) {

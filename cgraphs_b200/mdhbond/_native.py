@@ -67,6 +67,7 @@ class HbTimers(C.Structure):
         ("fused_frames", C.c_int64),
         ("fused_fallbacks", C.c_int64),
         ("h2d_bytes", C.c_int64),
+        ("finalize_retries", C.c_int64),
     ]
 
 
@@ -85,6 +86,8 @@ SYMBOLS = [
     ("hb_begin", C.c_int, [_P, C.c_int64]),
     ("hb_submit_frames", C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
     ("hb_submit_frames_device", C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
+    ("hb_finalize_async", C.c_int, [_P]),
+    ("hb_pack_keys_device", C.c_int, [_P, _P, C.c_int32]),
     ("hb_finalize", C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     ("hb_get_keys", C.c_int, [_P, _P]),
     ("hb_get_bits", C.c_int, [_P, _P]),
@@ -222,6 +225,12 @@ class Context:
     def sync(self):
         self._ck(self.lib.hb_sync(self.h), "hb_sync")
 
+    def finalize_async(self):
+        self._ck(self.lib.hb_finalize_async(self.h), "hb_finalize_async")
+
+    def pack_keys_device(self, block_ptr, cap):
+        self._ck(self.lib.hb_pack_keys_device(self.h, int(block_ptr), int(cap)), "hb_pack_keys_device")
+
     def finalize(self):
         nb, wpr = C.c_int64(), C.c_int64()
         self._ck(self.lib.hb_finalize(self.h, C.byref(nb), C.byref(wpr)), "hb_finalize")
@@ -272,6 +281,7 @@ class Context:
         return dict(ms_total=t.ms_total, ms_h2d=t.ms_h2d, ms_run=t.ms_run, n_launches=t.n_launches, frames=t.frames,
                     pairs_emitted=t.pairs_emitted, table_capacity=t.table_capacity, table_grows=t.table_grows,
                     fused_frames=t.fused_frames, fused_fallbacks=t.fused_fallbacks, h2d_bytes=t.h2d_bytes,
+                    finalize_retries=t.finalize_retries,
                     ms_kernel={n: t.ms_kernel[i] for i, n in enumerate(names)},
                     launches={n: t.launches[i] for i, n in enumerate(names)})
 

@@ -75,6 +75,30 @@ def merge_keys_device(local_keys, group=None, ctx=None, sync=True):
         _GATHER_CAP[group] = cap
 
 
+def exchange_keys_queued(ctx, group=None):
+    """The whole key exchange queued on the context's compute stream, nothing waits on the host:
+    hb_pack_keys_device (this rank's [count, keys...] block straight from the queued finalisation) -> one
+    ncclAllGather -> hb_merge_keys_device. Call between ctx.finalize_async() and ctx.finalize(); torch's current
+    stream must be the context's compute stream. Returns (keys, info): padded global sorted distinct keys and the
+    device tensor [n_keys, overflow] to be checked after the next synchronisation (overflow: repeat with the
+    synchronous merge_keys_device, which learns a larger capacity)."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size(group)
+    dev = torch.device("cuda", ctx.device)
+    cap = _GATHER_CAP.get(group, 2048)
+    if world * cap > 16384:
+        raise RuntimeError("exchange_keys_queued: more than 16384 gathered keys; use merge_keys_device")
+    block = torch.empty((cap + 1,), dtype=torch.int64, device=dev)
+    ctx.pack_keys_device(block.data_ptr(), cap)
+    gathered = torch.empty((world, cap + 1), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gathered, block, group=group)        # the one key exchange
+    out = torch.empty((world * cap,), dtype=torch.int64, device=dev)
+    info = torch.empty((2,), dtype=torch.int64, device=dev)
+    ctx.merge_keys_device(gathered.data_ptr(), world, cap, out.data_ptr(), info.data_ptr())
+    return out, info
+
+
 def merge_keys(local_keys, device=None, group=None):
     """All-gather sorted distinct uint64 keys; returns the global sorted distinct key list (numpy uint64).
 

@@ -113,6 +113,8 @@ typedef struct {
     int64_t fused_fallbacks;      /* times a frame did not fit in shared memory and the run moved to the
                                      general (global-memory cell list) kernels */
     int64_t h2d_bytes;            /* bytes hb_submit_frames copied host -> device (inert atom ranges are skipped) */
+    int64_t finalize_retries;     /* times a speculative finalize found an overflow and was redone (anything a caller
+                                     queued on top of hb_finalize_async is void then and must be repeated) */
 } hb_timers;
 
 int hb_create(hb_ctx** out, int device_ordinal);
@@ -148,6 +150,10 @@ int hb_submit_frames(hb_ctx* ctx, const float* xyz, int64_t n_atoms, int64_t n_f
 int hb_submit_frames_device(hb_ctx* ctx, const float* d_xyz, int64_t n_atoms, int64_t n_frames,
                             const float* d_box);
 
+/* Optional: queue the finalisation (compaction, key sort, row gather) behind the search WITHOUT waiting, so that
+ * the caller can queue more stream-ordered work on the compute stream (hb_pack_keys_device, a collective,
+ * hb_merge_keys_device) before the single host wait in hb_finalize. A no-op for large bond tables. */
+int hb_finalize_async(hb_ctx* ctx);
 /* Wait for all queued work, sort the distinct bond keys, gather the occupancy rows in key order. */
 int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond);
 
@@ -159,6 +165,9 @@ int hb_get_bits(hb_ctx* ctx, uint32_t* words);
  * queued on the context's compute stream (see "compute_stream"); use hb_sync or that stream to wait for them. */
 int hb_get_keys_device(hb_ctx* ctx, uint64_t* d_keys);
 int hb_get_bits_device(hb_ctx* ctx, uint32_t* d_words);
+/* Multi-GPU exchange, send side: write this rank's block [count, key_0 .. key_{cap-1}] (uint64, keys ascending,
+ * padding after them) to d_block (cap + 1 words). After hb_finalize_async or hb_finalize; stream-ordered. */
+int hb_pack_keys_device(hb_ctx* ctx, uint64_t* d_block, int32_t cap);
 /* Multi-GPU exchange, merge step: d_gathered = all-gather of one [count, key_0 .. key_{cap-1}] block
  * per rank (uint64, keys sorted ascending); writes the global sorted distinct keys to d_out (room for world*cap)
  * and {n_out, overflow flag} to d_info. world*cap <= 16384. Queued on the compute stream, no host round trip. */

@@ -38,7 +38,7 @@ def test_struct_sizes_match_header(lib):
     # layout sanity for the by-pointer structs (pointers 8 bytes, natural alignment)
     assert ctypes.sizeof(_native.HbParams) == 40
     assert ctypes.sizeof(_native.HbTopology) == 8 + 3 * 8 + 8 + 5 * 8 + 8 + 2 * 8 + 8 + 4 * 8 + 8 + 8
-    assert ctypes.sizeof(_native.HbTimers) == 16 + 16 * 8 + 16 * 8 + 5 * 8 + 8 + 24
+    assert ctypes.sizeof(_native.HbTimers) == 16 + 16 * 8 + 16 * 8 + 5 * 8 + 8 + 32
 
 
 def test_version_and_kernel_names(lib):

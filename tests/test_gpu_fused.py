@@ -222,3 +222,38 @@ def test_merge_keys_kernel():
         assert n_out == len(expect)
         assert np.array_equal(out[:n_out].cpu().numpy(), expect)
     ctx.close()
+
+
+def test_finalize_async_and_pack_block():
+    """hb_finalize_async queues the finalisation; hb_pack_keys_device writes [count, keys...] from it; a bond table
+    that overflows under a queued finalisation is redone (finalize_retries) with the same final result."""
+    import torch
+    from cgraphs_b200.mdhbond import HbondAnalysis
+    s, cfg = synth.config("C2", scale=0.4)
+    nf = 6
+    xyz = s.frames(0, nf)
+    u = Universe(s.topology, xyz)
+    hba = HbondAnalysis("protein", u)
+    hba.set_hbonds_in_selection_and_water_around(3.5)
+    ctx = hba._context()
+    ctx.begin(nf)
+    ctx.submit(xyz)
+    k0, w0 = ctx.results()
+    cap = 256
+    block = torch.full((cap + 1,), 7, dtype=torch.int64, device="cuda")
+    torch.cuda.synchronize()
+    ctx.begin(nf)
+    ctx.submit(xyz)
+    ctx.finalize_async()
+    ctx.pack_keys_device(block.data_ptr(), cap)
+    k1, w1 = ctx.results()
+    assert np.array_equal(k0, k1) and np.array_equal(w0, w1)
+    b = block.cpu().numpy()
+    assert b[0] == len(k0) and np.array_equal(b[1:1 + len(k0)].view(np.uint64), k0) and (b[1 + len(k0):] == -1).all()
+    # tiny table: the queued finalisation sees an overflow and is redone
+    big = HbondAnalysis("protein or resname TIP3", u, native_options={"table_capacity": 1024})
+    ref = _port(u, "protein or resname TIP3", "water_around").initial_results
+    c2 = big._context()
+    big.set_hbonds_in_selection_and_water_around(3.5)
+    assert_same_results(big.initial_results, ref)
+    assert big.last_run_stats["table_grows"] >= 1
