@@ -210,6 +210,31 @@ __global__ void k_row_counts(const unsigned* rows, int n, int wpr, long long* co
     if (lane == 0) counts[row] = c;
 }
 
+// AND of the selected occupancy rows, word by word (NetworkAnalysis.compute_joint_occupancy, network.py:369-376);
+// one thread per 32-frame word, rows walked in order. select == nullptr: all rows.
+__global__ void k_joint_rows(const unsigned* rows, const unsigned char* select, int n, int wpr, unsigned tail_mask,
+                             unsigned* out, unsigned long long* n_set) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned acc = 0u;
+    if (w < wpr) {
+        acc = 0xffffffffu;
+        for (int r = 0; r < n; ++r)
+            if (!select || select[r]) acc &= rows[(size_t)r * wpr + w];
+        if (w == wpr - 1) acc &= tail_mask;
+        out[w] = acc;
+    }
+    unsigned c = __popc(acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(n_set, (unsigned long long)c);
+}
+
+// which bonds exist in one frame (NetworkAnalysis._compute_graph_in_frame, network.py:1186-1198)
+__global__ void k_frame_column(const unsigned* rows, int n, int wpr, long long frame, unsigned char* present) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) present[r] = (rows[(size_t)r * wpr + (frame >> 5)] >> (frame & 31)) & 1u;
+}
+
 // re-insert the rows of an old table into a larger one
 __global__ void k_rehash(BondTable oldt, BondTable newt) {
     unsigned slot = blockIdx.x;

@@ -1320,6 +1320,55 @@ int hb_get_counts(hb_ctx* ctx, int64_t* counts) {
     return HB_OK;
 }
 
+int hb_joint_occupancy(hb_ctx* ctx, const uint8_t* select, uint32_t* words, int64_t* n_frames_set) {
+    if (!ctx || !words) return HB_ERR_ARG;
+    if (!ctx->finalized) return fail(ctx, HB_ERR_STATE, "hb_joint_occupancy before hb_finalize");
+    CK(cudaSetDevice(ctx->device));
+    const int n = (int)ctx->n_bonds, wpr = ctx->bt.wpr;
+    const long long nf = ctx->n_frames_total;
+    const unsigned tail = (nf & 31) ? ((1u << (nf & 31)) - 1u) : 0xffffffffu;
+    unsigned char* d_sel = nullptr;
+    unsigned* d_out = nullptr;
+    unsigned long long* d_cnt = nullptr;
+    cudaStream_t st = ctx->s_compute;
+    cudaError_t e = cudaMalloc((void**)&d_out, (size_t)wpr * 4 + 8);
+    if (e == cudaSuccess && select && n) e = cudaMalloc((void**)&d_sel, (size_t)n);
+    if (e == cudaSuccess && d_sel) e = cudaMemcpyAsync(d_sel, select, (size_t)n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        d_cnt = (unsigned long long*)(d_out + wpr + (wpr & 1));
+        e = cudaMemsetAsync(d_cnt, 0, 8, st);
+    }
+    unsigned long long cnt = 0;
+    if (e == cudaSuccess) {
+        k_joint_rows<<<(wpr + 255) / 256, 256, 0, st>>>(ctx->d_out_rows, d_sel, n, wpr, tail, d_out, d_cnt);
+        e = cudaMemcpyAsync(words, d_out, (size_t)wpr * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (d_out) cudaFree(d_out);
+    if (d_sel) cudaFree(d_sel);
+    if (e != cudaSuccess) return fail(ctx, HB_ERR_CUDA, cudaGetErrorString(e));
+    if (n_frames_set) *n_frames_set = (int64_t)cnt;
+    return HB_OK;
+}
+
+int hb_get_frame_column(hb_ctx* ctx, int64_t frame, uint8_t* present) {
+    if (!ctx || !present) return HB_ERR_ARG;
+    if (!ctx->finalized) return fail(ctx, HB_ERR_STATE, "hb_get_frame_column before hb_finalize");
+    if (frame < 0 || frame >= ctx->n_frames_total) return fail(ctx, HB_ERR_ARG, "hb_get_frame_column: frame out of range");
+    CK(cudaSetDevice(ctx->device));
+    const int n = (int)ctx->n_bonds;
+    if (!n) return HB_OK;
+    unsigned char* d = nullptr;
+    CK(cudaMalloc((void**)&d, (size_t)n));
+    k_frame_column<<<(n + 255) / 256, 256, 0, ctx->s_compute>>>(ctx->d_out_rows, n, ctx->bt.wpr, frame, d);
+    cudaError_t e = cudaMemcpyAsync(present, d, (size_t)n, cudaMemcpyDeviceToHost, ctx->s_compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_compute);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(ctx, HB_ERR_CUDA, cudaGetErrorString(e));
+    return HB_OK;
+}
+
 int hb_get_timers(hb_ctx* ctx, hb_timers* out) {
     if (!ctx || !out) return HB_ERR_ARG;
     drain_events(ctx);

@@ -95,6 +95,8 @@ SYMBOLS = [
     ("hb_get_bits_device", C.c_int, [_P, _P]),
     ("hb_merge_keys_device", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
     ("hb_get_counts", C.c_int, [_P, _P]),
+    ("hb_joint_occupancy", C.c_int, [_P, _P, _P, C.POINTER(C.c_int64)]),
+    ("hb_get_frame_column", C.c_int, [_P, C.c_int64, _P]),
     ("hb_get_timers", C.c_int, [_P, C.POINTER(HbTimers)]),
     ("hb_sync", C.c_int, [_P]),
     ("hb_host_alloc", C.c_int, [C.POINTER(_P), C.c_uint64]),
@@ -195,6 +197,7 @@ class Context:
         self._ck(self.lib.hb_set_params(self.h, C.byref(p)), "hb_set_params")
 
     def begin(self, n_frames_total):
+        self._run_id = getattr(self, "_run_id", 0) + 1     # device-side results of earlier runs are gone
         self._ck(self.lib.hb_begin(self.h, int(n_frames_total)), "hb_begin")
 
     def submit(self, xyz, n_atoms=None, box=None):
@@ -266,6 +269,23 @@ class Context:
         if n_bonds:
             self._ck(self.lib.hb_get_counts(self.h, c.ctypes.data), "hb_get_counts")
         return c
+
+    def joint_occupancy(self, wpr, select=None):
+        """(uint32 words [wpr], number of frames in which every selected bond exists)."""
+        words = np.zeros(wpr, dtype=np.uint32)
+        cnt = C.c_int64()
+        sel = None
+        if select is not None:
+            sel = np.ascontiguousarray(select, dtype=np.uint8)
+        self._ck(self.lib.hb_joint_occupancy(self.h, sel.ctypes.data if sel is not None else None, words.ctypes.data,
+                                             C.byref(cnt)), "hb_joint_occupancy")
+        return words, cnt.value
+
+    def frame_column(self, frame, n_bonds):
+        present = np.zeros(n_bonds, dtype=np.uint8)
+        if n_bonds:
+            self._ck(self.lib.hb_get_frame_column(self.h, int(frame), present.ctypes.data), "hb_get_frame_column")
+        return present.astype(bool)
 
     def timers(self):
         t = HbTimers()

@@ -293,6 +293,10 @@ class HbondAnalysis(object):
                 done += len(xyz)
             keys, words = ctx.results()
             self.last_run_stats = ctx.timers()
+            if self._shard is None:      # the packed rows stay on the device for the occupancy post-processing below
+                self._rows = dict(run_id=ctx._run_id, wpr=words.shape[1], n=len(keys),
+                                  row_of={group_names[int(k >> _np.uint64(32))] + ':' + group_names[int(k & _np.uint64(0xFFFFFFFF))]: i
+                                          for i, k in enumerate(keys)})
         if self._shard is not None and self._shard[1] > 1:
             from .sharding import merge_shards
             keys, words = merge_shards(keys, words, lo, hi, self.nb_frames, self._shard, ctx)
@@ -333,7 +337,8 @@ class HbondAnalysis(object):
     def filter_occupancy(self, min_occupancy, use_filtered=True):     # network.py:99-107
         results = self.filtered_results if use_filtered else self.initial_results
         if len(results) == 0: raise AssertionError('nothing to filter!')
-        filtered_result = {key: results[key] for key in results if _np.mean(results[key]) > min_occupancy}
+        occ = self.occupancies(use_filtered)       # count / nb_frames == numpy's mean of the bool vector
+        filtered_result = {key: results[key] for key in results if occ[key] > min_occupancy}
         if self.applied_filters['occupancy'] != None:
             self.applied_filters['occupancy'] = max(self.applied_filters['occupancy'], min_occupancy)
         else:
@@ -341,9 +346,67 @@ class HbondAnalysis(object):
         self.filtered_results = filtered_result
         self._generate_filtered_graph_from_filtered_results()
 
+    # ---------------------------------------------------------------------------------------------
+    # occupancy post-processing on the bit-packed bond x frame matrix that is still on the device
+    # (SURVEY 8f "next" #2; same results as the reference's numpy code on the bool vectors)
+    # ---------------------------------------------------------------------------------------------
+    def _device_rows(self, results):
+        """(ctx, rows-info, uint8 row mask of `results`) if every key of `results` is a row of the last run's
+        matrix on the device, else None."""
+        rows = self.__dict__.get("_rows")
+        if rows is None or self._ctx is None or getattr(self._ctx, "_run_id", None) != rows["run_id"]:
+            return None
+        mask = _np.zeros(rows["n"], dtype=_np.uint8)
+        for key in results:
+            i = rows["row_of"].get(key)
+            if i is None or results[key] is not self.initial_results.get(key):
+                return None
+            mask[i] = 1
+        return self._ctx, rows, mask
+
+    def compute_joint_occupancy(self, use_filtered=True):             # network.py:369-376
+        results = self.filtered_results if use_filtered else self.initial_results
+        dev = self._device_rows(results)
+        if dev is not None:
+            ctx, rows, mask = dev
+            words, _ = ctx.joint_occupancy(rows["wpr"], mask)
+            combined = _np.unpackbits(words.view(_np.uint8), bitorder="little")[:self.nb_frames].astype(bool)
+        else:
+            combined = _np.ones(self.nb_frames, dtype=bool)
+            for res in results: combined &= results[res]
+        self.joint_occupancy_series = combined
+        self.joint_occupancy_frames = _np.nonzero(combined)[0]
+        return combined.mean()
+
+    def _compute_graph_in_frame(self, frame, set_as_filtered_results=False, use_filtered=True):   # network.py:1186-1198
+        results = self.filtered_results if use_filtered else self.initial_results
+        if set_as_filtered_results:
+            raise NotImplementedError('set_as_filtered_results rebuilds results from a graph (network.py:1200-1214); '
+                                      'outside the accelerated path')
+        dev = self._device_rows(results)
+        if dev is not None:
+            ctx, rows, mask = dev
+            present = ctx.frame_column(int(frame) % self.nb_frames if frame < 0 else int(frame), rows["n"])
+            keep = [key for key in results if present[rows["row_of"][key]]]
+        else:
+            keep = [key for key in results if results[key][frame]]
+        graph = _nx.Graph()
+        graph.add_edges_from((key.split(':')[0], key.split(':')[1]) for key in keep)
+        return graph
+
+    def occupancies(self, use_filtered=True):
+        """{key: fraction of frames} from per-row popcounts on the device (numerator of filter_occupancy)."""
+        results = self.filtered_results if use_filtered else self.initial_results
+        dev = self._device_rows(results)
+        if dev is not None:
+            ctx, rows, mask = dev
+            counts = ctx.counts(rows["n"])
+            return {key: counts[rows["row_of"][key]] / self.nb_frames for key in results}
+        return {key: float(_np.mean(results[key])) for key in results}
+
     def dump_to_file(self, fname):                                    # basic.py:71-81
         tmp = _cp.copy(self)
-        for name in ('_universe', '_water', '_mda_selection', '_ctx', '_topology', '_packed'):
+        for name in ('_universe', '_water', '_mda_selection', '_ctx', '_topology', '_packed', '_rows'):
             tmp.__dict__[name] = None
         with open(fname, 'wb') as af:
             af.write(_pickle.dumps(tmp.__dict__))

@@ -175,6 +175,11 @@ int hb_merge_keys_device(hb_ctx* ctx, const uint64_t* d_gathered, int32_t world,
                          int64_t* d_info);
 /* Per-bond popcount over frames (occupancy numerator; network.py:99-107 filter_occupancy). */
 int hb_get_counts(hb_ctx* ctx, int64_t* counts);
+/* AND of the occupancy rows with select[i] != 0 (NULL: all rows): words = uint32 [words_per_bond] (host),
+ * n_frames_set = frames in which every selected bond exists (network.py:369-376 compute_joint_occupancy). */
+int hb_joint_occupancy(hb_ctx* ctx, const uint8_t* select, uint32_t* words, int64_t* n_frames_set);
+/* present[i] = 1 iff bond i exists in `frame` (network.py:1186-1198 _compute_graph_in_frame). */
+int hb_get_frame_column(hb_ctx* ctx, int64_t frame, uint8_t* present);
 
 int hb_get_timers(hb_ctx* ctx, hb_timers* out);
 int hb_sync(hb_ctx* ctx);

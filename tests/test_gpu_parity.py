@@ -252,3 +252,47 @@ def test_gpu_dump_and_restore(tmp_path):
     assert hba.applied_filters['occupancy'] == 0.5
     dup = hba.duplicate()
     assert dup.filtered_results is hba.filtered_results
+
+
+def test_gpu_occupancy_postprocessing_matches_numpy():
+    """filter_occupancy / compute_joint_occupancy / _compute_graph_in_frame on the packed device matrix give what
+    the reference's numpy code gives on the bool vectors (network.py:99-107, 369-376, 1186-1198)."""
+    import networkx as nx
+    from cgraphs_b200.mdhbond import HbondAnalysis
+    s = synth.make_system(4000, 40, 71)
+    u = s.universe(45)                      # not a multiple of 32: the tail word is partial
+    hba = HbondAnalysis("protein", u)
+    hba.set_hbonds_in_selection_and_water_around(3.5)
+    res = hba.initial_results
+    assert hba._device_rows(res) is not None
+    # reference formulas on the bool vectors
+    occ = {k: float(np.mean(v)) for k, v in res.items()}
+    got = hba.occupancies()
+    assert got.keys() == occ.keys() and all(got[k] == occ[k] for k in occ)
+    thr = float(np.median(list(occ.values())))
+    hba.filter_occupancy(thr)
+    assert set(hba.filtered_results) == {k for k, o in occ.items() if o > thr}
+    assert hba.applied_filters['occupancy'] == thr
+    # joint occupancy of the filtered subset (row mask) and of everything
+    combined = np.ones(hba.nb_frames, dtype=bool)
+    for k in hba.filtered_results:
+        combined &= res[k]
+    assert hba.compute_joint_occupancy() == combined.mean()
+    assert np.array_equal(hba.joint_occupancy_series, combined)
+    assert np.array_equal(hba.joint_occupancy_frames, np.nonzero(combined)[0])
+    allc = np.ones(hba.nb_frames, dtype=bool)
+    for k in res:
+        allc &= res[k]
+    assert hba.compute_joint_occupancy(use_filtered=False) == allc.mean()
+    # per-frame graphs
+    for frame in (0, 17, 44):
+        g = hba._compute_graph_in_frame(frame, use_filtered=False)
+        ref = nx.Graph()
+        ref.add_edges_from((k.split(':')[0], k.split(':')[1]) for k, v in res.items() if v[frame])
+        assert graph_edges(g) == graph_edges(ref)
+    # a new run invalidates the device rows of the old one: host fallback, same answers
+    other = HbondAnalysis("protein", u)
+    other._ctx = hba._ctx
+    other.set_hbonds_in_selection()
+    assert hba._device_rows(res) is None
+    assert hba.compute_joint_occupancy(use_filtered=False) == allc.mean()
