@@ -63,7 +63,8 @@ def test_gpu_matches_port_random(seed):
         assert graph_edges(a.filtered_graph) == graph_edges(b.filtered_graph)
 
 
-@pytest.mark.parametrize("cfg_name,scale,frames", [("C1", 1.0, 1), ("C2", 1.0, 8), ("C3", 0.5, 4), ("C3", 1.0, 2)])
+@pytest.mark.parametrize("cfg_name,scale,frames", [("C1", 1.0, 1), ("C2", 1.0, 8), ("C3", 0.5, 4), ("C3", 1.0, 2),
+                                                   ("C4", 1.0, 2)])
 def test_gpu_matches_port_baseline_configs(cfg_name, scale, frames):
     s, cfg = synth.config(cfg_name, scale=scale)
     u = s.universe(frames, static=cfg["static"])
