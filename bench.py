@@ -334,19 +334,22 @@ def run_ours(args):
     # ---- e2e: host frames through the C ABI (H2D inside the timed region, results read back) ----
     e2e = None
     if not args.no_e2e:
+        # host memory: all frames of the pass at N=1; with several ranks on one host the pinned budget is shared,
+        # so each rank streams a bounded number of distinct frames per pass (same metric, shorter pass)
+        ef = nf if world == 1 else int(min(nf, max(2048, nf // world)))
         try:
-            pin = _native.PinnedBuffer((nf, na, 3))
+            pin = _native.PinnedBuffer((ef, na, 3))
             host = pin.array
             pinned = True
         except Exception:
-            pin, host, pinned = None, np.empty((nf, na, 3), dtype=np.float32), False
+            pin, host, pinned = None, np.empty((ef, na, 3), dtype=np.float32), False
         chunk = max(1, (1 << 30) // (na * 12))
-        for s in range(0, nf, chunk):
-            host[s:s + chunk] = d_xyz[s:s + chunk].cpu().numpy()
+        for s in range(0, ef, chunk):
+            host[s:s + chunk] = d_xyz[s:min(s + chunk, ef)].cpu().numpy()
 
         def one_pass_host():
-            ctx.begin(nf)
-            ctx.submit_raw(host.ctypes.data, na, nf)
+            ctx.begin(ef)
+            ctx.submit_raw(host.ctypes.data, na, ef)
             keys, words = ctx.results()
             if world > 1:
                 merge_keys(keys, device=local_rank)
@@ -364,8 +367,8 @@ def run_ours(args):
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t[0]) / e2e_steps
-        e2e = {"value": world * nf / (e2e_ms / 1000.0), "unit": "frames/s", "h2d_bytes_per_step": int(ctx.timers()["h2d_bytes"]),
-               "frame_bytes_per_step": int(nf) * na * 12,
+        e2e = {"value": world * ef / (e2e_ms / 1000.0), "unit": "frames/s", "h2d_bytes_per_step": int(ctx.timers()["h2d_bytes"]),
+               "frames_per_step_per_gpu": ef, "frame_bytes_per_step": int(ef) * na * 12,
                "d2h_bytes_per_step": int(keys.nbytes + words.nbytes), "ms_per_step": e2e_ms,
                "host_memory": "pinned" if pinned else "pageable", "timer": "wall clock between device synchronisations"}
         if pin is not None:

@@ -43,6 +43,7 @@ struct FusedCfg {
     int w_stride;             // atoms between consecutive water oxygens
     int stages;               // ring depth
     int prefetch;             // tiles pulled into L2 ahead of the ring
+    unsigned wait_ns;         // sleep between two polls of a barrier
     unsigned stage_bytes;     // bytes of one stage (multiple of 16)
     unsigned off_union, off_lw, off_cells, off_near, off_cand, off_bar;   // byte offsets in dynamic smem
     unsigned smem_bytes;
@@ -90,13 +91,17 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
         : "memory");
     return ok != 0;
 }
-// bounded wait (about a second): a lost copy must never hang the GPU; the caller flags the frame instead
-__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned parity) {
+// bounded wait (about a second): a lost copy must never hang the GPU; the caller flags the frame instead.
+// Between polls the warp sleeps `ns` nanoseconds: a polling warp would otherwise take issue slots from the
+// warps of the other resident frames that have work to do.
+__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned parity, unsigned ns) {
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
     for (;;) {
-        for (int k = 0; k < 64; ++k)
+        for (int k = 0; k < 64; ++k) {
+            if (ns) __nanosleep(ns);
             if (mbar_try_wait(bar, parity)) return true;
+        }
         if (clock64() - t0 > 2000000000ll) return false;
     }
 }
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
             unsigned parity = 1;                        // parity of the "previous round" of the empty barriers
             for (int t = 0; t < ntiles; ++t) {
                 if (t + fc.prefetch < ntiles) prefetch_tile(t + fc.prefetch);
-                if (t >= fc.stages && !mbar_wait(&empty[st], parity)) { sh->overflow = 2; break; }
+                if (t >= fc.stages && !mbar_wait(&empty[st], parity, fc.wait_ns)) { sh->overflow = 2; break; }
                 const int nw = min(FUSED_TILE, nwp - t * FUSED_TILE);
                 const unsigned long long ga = gbase + (unsigned long long)t * (unsigned long long)(FUSED_TILE * stride12);
                 const unsigned long long start = ga & ~15ull;
@@ -405,7 +410,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
             const bool live = i < nwp;
             float x = 0.f, y = 0.f, z = 0.f;
             if (stream) {
-                if (!mbar_wait(&full[st], parity)) { sh->overflow = 2; break; }
+                if (!mbar_wait(&full[st], parity, fc.wait_ns)) { sh->overflow = 2; break; }
                 const float* f = reinterpret_cast<const float*>(ring + (size_t)st * fc.stage_bytes + my_off);
                 x = f[0]; y = f[1]; z = f[2];             // (always inside the stage; meaningful if the bytes were copied)
                 const unsigned partial = sh->stage_head[st];

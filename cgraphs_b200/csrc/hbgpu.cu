@@ -84,6 +84,7 @@ struct hb_ctx {
     long long opt_fused_cell_cap = 0; // 0: automatic
     long long opt_fused_pair_cap = 0; // 0: automatic
     long long opt_fused_stages = 3;   // depth of the water-tile ring
+    long long opt_fused_wait_ns = 100;
     long long opt_fused_prefetch = 2; // tiles prefetched into L2 ahead of the ring (more evicts lines before use)
     int fused_grow = 0;
 
@@ -366,6 +367,7 @@ int hb_set_option(hb_ctx* ctx, const char* name, int64_t value) {
     else if (n == "fused_stages") ctx->opt_fused_stages = std::max<long long>(value, 2);
     else if (n == "fused_batch_frames") ctx->opt_fused_batch_frames = std::max<long long>(value, 1);
     else if (n == "fused_prefetch") ctx->opt_fused_prefetch = std::max<long long>(value, 0);
+    else if (n == "fused_wait_ns") ctx->opt_fused_wait_ns = std::max<long long>(value, 0);
     else return fail(ctx, HB_ERR_ARG, "unknown option " + n);
     return HB_OK;
 }
@@ -569,6 +571,7 @@ static bool plan_fused(hb_ctx* ctx, int grow = 0) {
     fc.w_stride = ctx->water_stride;
     fc.stages = fc.regular ? (int)std::min<long long>(std::max<long long>(ctx->opt_fused_stages, 2), FUSED_MAX_STAGES) : 0;
     fc.prefetch = (int)ctx->opt_fused_prefetch;
+    fc.wait_ns = (unsigned)ctx->opt_fused_wait_ns;
     fc.stage_bytes = fc.regular ? (unsigned)(((FUSED_TILE - 1) * fc.w_stride * 12 + 12 + 15 + 15) & ~15) : 0u;
     size_t off = (sizeof(FusedShared) + 15) & ~(size_t)15;
     fc.off_union = (unsigned)off;
