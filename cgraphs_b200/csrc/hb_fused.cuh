@@ -539,7 +539,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
                 pflags[tid] = 0xfu;
             }
         }
+        phase_done(10);
         consumer_sync();
+        phase_done(11);
         // (b) one thread per hydrogen: ANG(other, h, owner)
         const int ntasks = sh->n_tasks;
         if (ntasks > fc.task_cap) {                     // uniform
@@ -555,7 +557,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
             const float* h = xyz + 3ll * (long long)tk.y;
             if (ang_ok<PBC>(oth.x, oth.y, oth.z, h[0], h[1], h[2], own.x, own.y, own.z, ct, g2.p.box)) atomicOr(&pflags[kk], 1u << f);
         }
+        phase_done(12);
         consumer_sync();
+        phase_done(13);
         // (c) entry pairs whose hydrogens passed
         if (have) {
             unsigned m = rules & rules_pass(pflags[tid]);
@@ -567,7 +571,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
                 emit(tp, rp, bt, frame, e0, e1, nhit);
             }
         }
+        phase_done(14);
         consumer_sync();                                // pflags / tasks are rewritten by the next chunk
+        phase_done(15);
     }
     phase_done(7);
     flush_hits(bt, nhit);

@@ -670,7 +670,7 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
         k_fill_u64<<<1184, 256, 0, ctx->s_compute>>>(ctx->bt.keys, tc, EMPTY_KEY);
         ctx->tm.n_launches += 1;
         CK(cudaMemsetAsync(ctx->bt.bits, 0, tc * wpr * sizeof(unsigned), ctx->s_compute));
-        CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 16 * sizeof(unsigned long long), ctx->s_compute));
+        CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 32 * sizeof(unsigned long long), ctx->s_compute));
         if (ctx->trace) { cudaStreamSynchronize(ctx->s_compute); tr.mark("clear(reuse)"); }
         ctx->running = true;
         ctx->finalized = false;
@@ -679,8 +679,8 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     // bond table
     if ((rc = alloc_table(ctx, ctx->bt, cap, wpr))) return rc;
     ctx->table_cap = cap;
-    CK(cudaMalloc((void**)&ctx->bt.n_keys, 16 * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 16 * sizeof(unsigned long long), ctx->s_compute));
+    CK(cudaMalloc((void**)&ctx->bt.n_keys, 32 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 32 * sizeof(unsigned long long), ctx->s_compute));
     ctx->bt.overflow = ctx->bt.n_keys + 1;
     ctx->bt.fused_overflow = ctx->bt.n_keys + 2;
     ctx->bt.n_hits = (unsigned long long*)(ctx->bt.n_keys + 4);
@@ -1241,12 +1241,14 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
     ctx->d_out_keys = k0;
     tr.mark("sort+gather");
     if (ctx->trace && ctx->bt.phase_cycles && ctx->tm.fused_frames) {
-        unsigned long long pc[10];
+        unsigned long long pc[16];
         if (cudaMemcpy(pc, ctx->bt.phase_cycles, sizeof(pc), cudaMemcpyDeviceToHost) == cudaSuccess) {
             double f = (double)ctx->tm.fused_frames;
             fprintf(stderr, "[hbgpu] fused phases, cycles per frame (thread 0): A gather+grid %.0f | g1 sort+near %.0f | B stream %.0f | "
                             "B tail sync %.0f | C sort %.0f | C collect %.0f | C sync %.0f | C expand %.0f | flush %.0f\n",
                     pc[0] / f, pc[1] / f, pc[2] / f, pc[3] / f, pc[4] / f, pc[5] / f, pc[6] / f, pc[7] / f, pc[8] / f);
+            fprintf(stderr, "[hbgpu]   C expand split: (a) setup %.0f | sync %.0f | (b) angle tasks %.0f | sync %.0f | (c) emit %.0f | sync %.0f\n",
+                    pc[10] / f, pc[11] / f, pc[12] / f, pc[13] / f, pc[14] / f, pc[15] / f);
         }
     }
     ctx->n_bonds = n;
