@@ -29,6 +29,9 @@ class StructureResult(object):
         self.filtered_graph = self.initial_graph
 
 
+WATER_TYPES = ("HOH", "TIP3", "TIP4")        # cgraphs/helperfunctions.py:47
+
+
 class HbondBatch(object):
     def __init__(self, structures, selection, device=None, native_options=None, **ctor_kwargs):
         """structures: Universe-like objects (single frame each); other kwargs as HbondAnalysis."""
@@ -95,3 +98,60 @@ class HbondBatch(object):
             a._set_results(res)
             self.results.append(StructureResult(res, self.residuewise))
         return self.results
+
+    # ---------------------------------------------------------------------------------------------
+    # conserved network over the batch (SURVEY 8f "next" #3): the counting rule of
+    # ConservedGraph.get_conserved_graph for graph_type "hbond" (cgraphs/conservedgraph.py:114-170, without the
+    # water-cluster relabelling of :139-149, which needs the workflow's superimposed reference coordinates),
+    # evaluated on the bond x structure occupancy matrix instead of one networkx graph per structure
+    # ---------------------------------------------------------------------------------------------
+    def get_conserved_graph(self, conservation_threshold=0.9):
+        """Returns (conserved_nodes, conserved_edges): nodes / edges present in at least
+        round(n_structures * conservation_threshold) of the per-structure graphs. Edges are (node, node) tuples with
+        the smaller resid first (the orientation dict2graph gives them, helpfunctions.py:120-134); water nodes are
+        kept only when they take part in a conserved edge (conservedgraph.py:160-168)."""
+        if self.results is None:
+            raise AssertionError('run set_hbonds_in_selection / set_hbonds_in_selection_and_water_around first')
+        n = len(self.analyses)
+        th = _np.round(n * conservation_threshold)
+        cut = 3 if self.residuewise else 4
+        edge_of_row = _np.full(len(self.bond_keys), -1, dtype=_np.int64)
+        edges, index = [], {}
+        for r, key in enumerate(self.bond_keys):                 # graph edge of every bond key (once per key)
+            a, b = key.split(':')
+            a = '-'.join(a.split('-')[:cut])
+            b = '-'.join(b.split('-')[:cut])
+            if int(a.split('-')[2]) > int(b.split('-')[2]):
+                a, b = b, a
+            if a == b:
+                continue
+            e = frozenset((a, b))
+            if e not in index:
+                index[e] = len(edges)
+                edges.append((a, b))
+            edge_of_row[r] = index[e]
+        occ = self.occupancy                                     # bool [n_bonds, n_structures]
+        keep = edge_of_row >= 0
+        edge_present = _np.zeros((len(edges), n), dtype=bool)
+        _np.logical_or.at(edge_present, edge_of_row[keep], occ[keep])
+        edge_counts = edge_present.sum(axis=1)
+        node_index, node_names = {}, []
+        ends = _np.empty((len(edges), 2), dtype=_np.int64)
+        for i, (a, b) in enumerate(edges):
+            for j, name in enumerate((a, b)):
+                if name not in node_index:
+                    node_index[name] = len(node_names)
+                    node_names.append(name)
+                ends[i, j] = node_index[name]
+        node_present = _np.zeros((len(node_names), n), dtype=bool)
+        if len(edges):
+            _np.logical_or.at(node_present, ends[:, 0], edge_present)
+            _np.logical_or.at(node_present, ends[:, 1], edge_present)
+        node_counts = node_present.sum(axis=1)
+        conserved_edges = [edges[i] for i in _np.nonzero(edge_counts >= th)[0]]
+        in_edge = {x for e in conserved_edges for x in e}
+        conserved_nodes = [node_names[i] for i in _np.nonzero(node_counts >= th)[0]
+                           if node_names[i].split('-')[1] not in WATER_TYPES or node_names[i] in in_edge]
+        self.conserved_edges = sorted(conserved_edges)
+        self.conserved_nodes = sorted(conserved_nodes)
+        return self.conserved_nodes, self.conserved_edges

@@ -297,3 +297,31 @@ def test_gpu_occupancy_postprocessing_matches_numpy():
     other.set_hbonds_in_selection()
     assert hba._device_rows(res) is None
     assert hba.compute_joint_occupancy(use_filtered=False) == allc.mean()
+
+
+def test_gpu_batch_conserved_graph():
+    """HbondBatch.get_conserved_graph == the counting rule of ConservedGraph.get_conserved_graph
+    (conservedgraph.py:114-170, hbond branch without water relabelling) applied to per-structure oracle graphs."""
+    from cgraphs_b200.mdhbond import HbondBatch
+    # the same protein in several conformations: static structure + frames of its trajectory as separate structures
+    s = synth.make_system(3000, 60, 901, hydrogens=False, water="HOH")
+    xyz = s.frames(0, 9)
+    unis = [Universe(s.topology, xyz[i:i + 1]) for i in range(9)]
+    kw = dict(check_angle=False, add_donors_without_hydrogen=True)
+    batch = HbondBatch(unis, "protein", **kw)
+    batch.set_hbonds_in_selection_and_water_around(3.5)
+    for cth in (0.9, 0.5, 0.2):
+        nodes, edges = batch.get_conserved_graph(cth)
+        # reference rule on per-structure graphs
+        all_nodes, all_edges = [], []
+        for u in unis:
+            g = _run_port(u, "protein", "water_around", **kw).filtered_graph
+            all_nodes += list(g.nodes)
+            all_edges += [frozenset(e) for e in g.edges]
+        th = np.round(len(unis) * cth)
+        un, cn = np.unique(all_nodes, return_counts=True)
+        ce = {e for e in set(all_edges) if all_edges.count(e) >= th}
+        cnodes = {x for x, c in zip(un, cn) if c >= th and (x.split('-')[1] not in ("HOH", "TIP3", "TIP4") or any(x in e for e in ce))}
+        assert {frozenset(e) for e in edges} == ce
+        assert set(nodes) == cnodes
+        assert len(ce) > 0
