@@ -171,31 +171,6 @@ __device__ __forceinline__ bool cell3_pbc(const FrameGrid& g, float x, float y, 
     cx = c[0]; cy = c[1]; cz = c[2];
     return inside;
 }
-// same result as cell3_pbc + linear cell index, but leaves as soon as one windowed axis excludes the point
-// (the c axis depends on z only, b on y and z: most waters of a frame fall out after the first few operations)
-__device__ __forceinline__ bool cell_in_window_pbc(const FrameGrid& g, float x, float y, float z, int& cell) {
-    const PbcGrid& p = g.p;
-    const float sc = z * p.ic;
-    float u = sc - p.c[2];
-    u -= rintf(u);
-    const float vc = u + p.half[2];
-    if (!p.per[2] && !(vc >= 0.f && vc <= 2.f * p.half[2])) return false;
-    const float sb = (y - sc * p.box.cy) * p.ib;
-    u = sb - p.c[1];
-    u -= rintf(u);
-    const float vb = u + p.half[1];
-    if (!p.per[1] && !(vb >= 0.f && vb <= 2.f * p.half[1])) return false;
-    const float sa = (x - sb * p.box.bx - sc * p.box.cx) * p.ia;
-    u = sa - p.c[0];
-    u -= rintf(u);
-    const float va = u + p.half[0];
-    if (!p.per[0] && !(va >= 0.f && va <= 2.f * p.half[0])) return false;
-    const int cx = min(max((int)floorf(va * p.scale[0]), 0), g.nx - 1);
-    const int cy = min(max((int)floorf(vb * p.scale[1]), 0), g.ny - 1);
-    const int cz = min(max((int)floorf(vc * p.scale[2]), 0), g.nz - 1);
-    cell = (cz * g.ny + cy) * g.nx + cx;
-    return true;
-}
 template <bool PBC>
 __device__ __forceinline__ void cell3(const FrameGrid& g, float x, float y, float z, int& cx, int& cy, int& cz) {
     if constexpr (PBC) {
