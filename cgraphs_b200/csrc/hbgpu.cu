@@ -754,12 +754,13 @@ static int run_general_t(hb_ctx* ctx, BatchView bv) {
     const int nf = bv.n_frames;
     bool wa = rp.method == HB_METHOD_WATER_AROUND;
     { KTimer t(ctx, KC_INIT); k_init_frames<<<(nf + 127) / 128, 128, 0, st>>>(bv); }
-    size_t cells_bytes = (size_t)nf * (bv.cell_cap + 1) * 4;
-    if (wa) CK(cudaMemsetAsync(bv.cells1, 0, cells_bytes, st));
-    CK(cudaMemsetAsync(bv.cells2, 0, cells_bytes, st));
     dim3 gsel((bv.max_sel + 255) / 256, nf), gwat((bv.max_wat + 255) / 256, nf);
     if (bv.max_sel > 0) { KTimer t(ctx, KC_GATHER); k_gather_sel<PBC><<<gsel, 256, 0, st>>>(bv, tp); }
     { KTimer t(ctx, KC_GRID); k_grid_setup<PBC><<<(nf + 127) / 128, 128, 0, st>>>(bv, tp, rp); }
+    // only the cells each frame's grid really has are cleared (the capacity is sized for the worst case)
+    dim3 gzero(16, nf);
+    if (wa) { KTimer t(ctx, KC_INIT); k_zero_cells<<<gzero, 256, 0, st>>>(bv, 1); }
+    { KTimer t(ctx, KC_INIT); k_zero_cells<<<gzero, 256, 0, st>>>(bv, 2); }
     if (wa && bv.max_sel > 0 && bv.max_wat > 0) {
         { KTimer t(ctx, KC_COUNT); k_count<PBC><<<gsel, 256, 0, st>>>(bv, tp, 1); }
         { KTimer t(ctx, KC_SCAN); k_scan<<<nf, 1024, 0, st>>>(bv, 1); }
@@ -768,11 +769,12 @@ static int run_general_t(hb_ctx* ctx, BatchView bv) {
     }
     int maxp = bv.max_sel + (wa ? bv.max_wat : 0);
     if (maxp > 0) {
-        dim3 gall((maxp + 255) / 256, nf);
+        // selection + local waters: the kernels stride over the points a frame really has (far fewer than all waters)
+        dim3 gall(std::min((maxp + 255) / 256, 48), nf);
         { KTimer t(ctx, KC_COUNT); k_count<PBC><<<gall, 256, 0, st>>>(bv, tp, 2); }
         { KTimer t(ctx, KC_SCAN); k_scan<<<nf, 1024, 0, st>>>(bv, 2); }
         { KTimer t(ctx, KC_SCATTER); k_scatter<PBC><<<gall, 256, 0, st>>>(bv, tp, 2); }
-        dim3 gp((maxp + 127) / 128, nf);
+        dim3 gp(std::min((maxp + 127) / 128, 96), nf);
         { KTimer t(ctx, KC_PAIRS); k_pairs<PBC><<<gp, 128, 0, st>>>(bv, tp, rp, ctx->bt); }
     }
     CK(cudaGetLastError());
