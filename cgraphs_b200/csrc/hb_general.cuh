@@ -269,4 +269,92 @@ __global__ void __launch_bounds__(128) k_pairs(BatchView bv, DevTopo tp, RunPara
     flush_hits(bt, nhit);
 }
 
+// ------------------------------------------------------------------------------------------------
+// K7 in two dense steps (used when the batch-wide pair buffer is available):
+//   K7a  every point walks its neighbourhood and appends the point pairs within `distance` to one pair buffer
+//        for the whole sub-batch (records staged in shared memory, one global atomic per block and trip)
+//   K7b  one thread per pair: topology of both points, angle tests, entry pairs, bond table
+// A thread then carries one short chain of dependent global loads instead of one per partner of its point.
+// Pair record: frame slot of the sub-batch << 48 | i << 24 | q  (cell-sorted point indices, < 2^24).
+// ------------------------------------------------------------------------------------------------
+#define PAIR_STAGE 2048
+
+struct PairBuf {
+    unsigned long long* rec;
+    unsigned long long cap;
+    unsigned long long* count;     // records appended (may exceed cap: the excess is dropped and flagged)
+    int* overflow;
+};
+
+template <bool PBC>
+__global__ void __launch_bounds__(128) k_collect_pairs(BatchView bv, DevTopo tp, RunParams rp, BondTable bt, PairBuf pb) {
+    __shared__ unsigned long long stage[PAIR_STAGE];
+    __shared__ unsigned n_stage;
+    __shared__ unsigned long long g_base;
+    const int b = blockIdx.y;
+    const FrameState& f = bv.fs[b];
+    int sys;
+    const float* xyz = frame_xyz(bv, tp, b, sys);
+    const int* cells = bv.cells2 + (size_t)b * (bv.cell_cap + 1);
+    const float4* pts = bv.sorted2 + (size_t)b * (bv.max_sel + bv.max_wat);
+    const long long frame = bv.frame0 + b;
+    const int n = f.n_points;
+    int nhit = 0;
+    if (threadIdx.x == 0) n_stage = 0;
+    __syncthreads();
+    for (int base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {
+        const int i = base + threadIdx.x;
+        if (i < n) {
+            const float4 p = pts[i];
+            if (rp.self_pairs) {
+                PointInfo P;
+                load_info(tp, rp, sys, p, P);
+                process_self<PBC>(tp, rp, bt, xyz, frame, P, nhit, f.g2.p.box);
+            }
+            for_each_partner<PBC>(f.g2, cells, i, p.x, p.y, p.z, [&](int q) {
+                const float4 q4 = pts[q];
+                if (!within<PBC>(p.x, p.y, p.z, q4.x, q4.y, q4.z, rp.r2f_hi, rp.r2, f.g2.p)) return;
+                const unsigned long long r = ((unsigned long long)b << 48) | ((unsigned long long)i << 24) | (unsigned long long)q;
+                const unsigned k = atomicAdd(&n_stage, 1u);
+                if (k < PAIR_STAGE) stage[k] = r;
+                else {                                          // staging full: straight to the buffer
+                    const unsigned long long g = atomicAdd(pb.count, 1ull);
+                    if (g < pb.cap) pb.rec[g] = r; else *pb.overflow = 1;
+                }
+            });
+        }
+        __syncthreads();
+        const unsigned m = min(n_stage, (unsigned)PAIR_STAGE);
+        if (threadIdx.x == 0 && m) g_base = atomicAdd(pb.count, (unsigned long long)m);
+        __syncthreads();
+        for (unsigned k = threadIdx.x; k < m; k += blockDim.x) {
+            const unsigned long long g = g_base + k;
+            if (g < pb.cap) pb.rec[g] = stage[k]; else *pb.overflow = 1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) n_stage = 0;
+        __syncthreads();
+    }
+    flush_hits(bt, nhit);
+}
+
+template <bool PBC>
+__global__ void __launch_bounds__(128) k_expand_pairs(BatchView bv, DevTopo tp, RunParams rp, BondTable bt, PairBuf pb) {
+    const unsigned long long n = min(*pb.count, pb.cap);
+    int nhit = 0;
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
+         k += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long r = pb.rec[k];
+        const int b = (int)(r >> 48), i = (int)((r >> 24) & 0xffffffull), q = (int)(r & 0xffffffull);
+        int sys;
+        const float* xyz = frame_xyz(bv, tp, b, sys);
+        const float4* pts = bv.sorted2 + (size_t)b * (bv.max_sel + bv.max_wat);
+        PointInfo P, Q;
+        load_info(tp, rp, sys, pts[i], P);
+        load_info(tp, rp, sys, pts[q], Q);
+        process_pair<PBC>(tp, rp, bt, xyz, bv.frame0 + b, P, Q, nhit, bv.fs[b].g2.p.box);
+    }
+    flush_hits(bt, nhit);
+}
+
 }  // namespace

@@ -114,6 +114,9 @@ struct hb_ctx {
     int cell_cap = 0;
     BatchView bv{};
     std::vector<void*> scratch_allocs;
+    PairBuf pairbuf{};                // batch-wide pair buffer of the general path (lazy)
+    long long opt_pair_buf_bytes = 512ll << 20;
+    bool use_pairbuf = true;
     float* d_in[2] = {nullptr, nullptr};
     float* h_stage[2] = {nullptr, nullptr};
     size_t in_bytes = 0;              // planned capacity of one input buffer
@@ -122,8 +125,9 @@ struct hb_ctx {
     cudaEvent_t ev_run0{}, ev_run1{};
     long long batch_counter = 0;
 
-    struct Slot { bool busy; const float* d_xyz; long long f0; int nf; long long apf; size_t bytes; const float* d_box; };
-    Slot slots[2] = {{false, nullptr, 0, 0, 0, 0, nullptr}, {false, nullptr, 0, 0, 0, 0, nullptr}};
+    struct Slot { bool busy; const float* d_xyz; long long f0; int nf; long long apf; size_t bytes; const float* d_box; bool fused; };
+    Slot slots[2] = {{false, nullptr, 0, 0, 0, 0, nullptr, false}, {false, nullptr, 0, 0, 0, 0, nullptr, false}};
+    bool last_batch_fused = false;
     float* d_box[2] = {nullptr, nullptr};      // lattice vectors of the frames in each input buffer
     float* h_box[2] = {nullptr, nullptr};      // pinned staging for them
     size_t box_cap = 0;                        // frames
@@ -355,6 +359,7 @@ int hb_set_option(hb_ctx* ctx, const char* name, int64_t value) {
     else if (n == "max_batch_frames") ctx->opt_max_batch_frames = std::max<long long>(value, 1);
     else if (n == "fused") ctx->opt_fused = value != 0;
     else if (n == "force_radix_sort") ctx->opt_force_radix = value != 0;
+    else if (n == "pair_buf_bytes") { ctx->opt_pair_buf_bytes = std::max<long long>(value, 0); ctx->use_pairbuf = value > 0; }
     else if (n == "compute_stream") {   // run all kernels on the caller's CUDA stream (0 = back to the library's own)
         if (ctx->running) return fail(ctx, HB_ERR_STATE, "compute_stream cannot change during a run");
         cudaStreamSynchronize(ctx->s_compute);
@@ -741,6 +746,13 @@ static int ensure_scratch(hb_ctx* ctx) {
     if ((rc = dalloc((void**)&bv.sorted2, fb * npts * 16))) return rc;
     if ((rc = dalloc((void**)&bv.cells1, fb * (cc + 1) * 4))) return rc;
     if ((rc = dalloc((void**)&bv.cells2, fb * (cc + 1) * 4))) return rc;
+    ctx->pairbuf = PairBuf{};
+    if (ctx->use_pairbuf && ctx->opt_pair_buf_bytes >= 4096 && npts < (1u << 24) && fb < 65536) {
+        ctx->pairbuf.cap = (unsigned long long)ctx->opt_pair_buf_bytes / 8;
+        if ((rc = dalloc((void**)&ctx->pairbuf.rec, ctx->pairbuf.cap * 8))) return rc;
+        if ((rc = dalloc((void**)&ctx->pairbuf.count, 8))) return rc;
+        ctx->pairbuf.overflow = ctx->bt.n_keys + 3;          // fourth word of the status block
+    }
     return HB_OK;
 }
 
@@ -775,7 +787,16 @@ static int run_general_t(hb_ctx* ctx, BatchView bv) {
         { KTimer t(ctx, KC_SCAN); k_scan<<<nf, 1024, 0, st>>>(bv, 2); }
         { KTimer t(ctx, KC_SCATTER); k_scatter<PBC><<<gall, 256, 0, st>>>(bv, tp, 2); }
         dim3 gp(std::min((maxp + 127) / 128, 96), nf);
-        { KTimer t(ctx, KC_PAIRS); k_pairs<PBC><<<gp, 128, 0, st>>>(bv, tp, rp, ctx->bt); }
+        if (ctx->pairbuf.rec && ctx->use_pairbuf) {
+            PairBuf pb = ctx->pairbuf;
+            pb.overflow = ctx->bt.n_keys + 3;
+            CK(cudaMemsetAsync(pb.count, 0, 8, st));
+            { KTimer t(ctx, KC_PAIRS); k_collect_pairs<PBC><<<gp, 128, 0, st>>>(bv, tp, rp, ctx->bt, pb); }
+            { KTimer t(ctx, KC_PAIRS); k_expand_pairs<PBC><<<148 * 8, 128, 0, st>>>(bv, tp, rp, ctx->bt, pb); }
+        } else {
+            KTimer t(ctx, KC_PAIRS);
+            k_pairs<PBC><<<gp, 128, 0, st>>>(bv, tp, rp, ctx->bt);
+        }
     }
     CK(cudaGetLastError());
     return HB_OK;
@@ -810,7 +831,9 @@ static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, 
         }
         CK(cudaGetLastError());
         ctx->tm.fused_frames += nf;
+        ctx->last_batch_fused = true;
     } else {
+        ctx->last_batch_fused = false;
         int rc = ensure_scratch(ctx);
         if (rc) return rc;
         bv = ctx->bv;                     // scratch pointers
@@ -842,8 +865,8 @@ static int full_verify(hb_ctx* ctx) {
         CK(cudaStreamSynchronize(ctx->s_compute));
         memcpy(st, ctx->h_verify, sizeof(st));
         memcpy(ctx->last_status, st, sizeof(st));
-        bool overflow = st[1] != 0, fused_overflow = st[2] != 0;
-        if (!overflow && !fused_overflow && (long long)st[0] * 2 <= ctx->table_cap) {
+        bool overflow = st[1] != 0, fused_overflow = st[2] != 0, pair_overflow = st[3] != 0;
+        if (!overflow && !fused_overflow && !pair_overflow && (long long)st[0] * 2 <= ctx->table_cap) {
             for (auto& sl : ctx->slots) sl.busy = false;
             return HB_OK;
         }
@@ -858,14 +881,19 @@ static int full_verify(hb_ctx* ctx) {
             if (ctx->opt_fused_lw_cap || ctx->opt_fused_pair_cap || ctx->fused_grow >= 6 || !plan_fused(ctx, ctx->fused_grow + 1))
                 ctx->fused_active = false;
         }
-        if (overflow || fused_overflow) {
-            CK(cudaMemsetAsync(ctx->bt.overflow, 0, 2 * sizeof(int), ctx->s_compute));
+        if (pair_overflow) {       // the sub-batch found more pairs than the pair buffer holds: halve it
+            if (ctx->batch_frames > 1) ctx->batch_frames = std::max(1, ctx->batch_frames / 2);
+            else ctx->use_pairbuf = false;
+        }
+        if (overflow || fused_overflow || pair_overflow) {
+            CK(cudaMemsetAsync(ctx->bt.overflow, 0, 3 * sizeof(int), ctx->s_compute));
             for (auto& sl : ctx->slots)
                 if (sl.busy) {
-                    long long frames_before = ctx->tm.frames, fused_before = ctx->tm.fused_frames;
+                    long long frames_before = ctx->tm.frames;
+                    if (sl.fused) ctx->tm.fused_frames -= sl.nf;    // a re-run is not new work
                     if ((rc = run_batch(ctx, sl.d_xyz, sl.f0, sl.nf, sl.apf, sl.bytes, sl.d_box))) return rc;
-                    ctx->tm.frames = frames_before;                 // a re-run is not new work
-                    ctx->tm.fused_frames = ctx->fused_active ? fused_before : fused_before - sl.nf;
+                    sl.fused = ctx->last_batch_fused;
+                    ctx->tm.frames = frames_before;
                 }
         }
     }
@@ -877,7 +905,7 @@ static int acquire_slot(hb_ctx* ctx, int k) {
     hb_ctx::Slot& sl = ctx->slots[k];
     if (!sl.busy) return HB_OK;
     CK(cudaEventSynchronize(ctx->ev_done[k]));
-    int nkeys = ctx->h_status[4 * k], overflow = ctx->h_status[4 * k + 1] | ctx->h_status[4 * k + 2];
+    int nkeys = ctx->h_status[4 * k], overflow = ctx->h_status[4 * k + 1] | ctx->h_status[4 * k + 2] | ctx->h_status[4 * k + 3];
     if (overflow || (long long)nkeys * 2 > ctx->table_cap) return full_verify(ctx);
     sl.busy = false;
     return HB_OK;
@@ -889,7 +917,7 @@ static int launch_in_slot(hb_ctx* ctx, int k, const float* d_xyz, long long f0, 
     if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->h_status + 4 * k, ctx->bt.n_keys, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->s_compute));
     CK(cudaEventRecord(ctx->ev_done[k], ctx->s_compute));
-    ctx->slots[k] = hb_ctx::Slot{true, d_xyz, f0, nf, apf, bytes, d_box};
+    ctx->slots[k] = hb_ctx::Slot{true, d_xyz, f0, nf, apf, bytes, d_box, ctx->last_batch_fused};
     return HB_OK;
 }
 
@@ -1214,7 +1242,7 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
         CK(cudaStreamSynchronize(st));
         memcpy(ctx->last_status, ctx->h_verify, 6 * sizeof(int));
         n = ctx->last_status[0];
-        const bool bad = ctx->last_status[1] || ctx->last_status[2] || (long long)n * 2 > ctx->table_cap;
+        const bool bad = ctx->last_status[1] || ctx->last_status[2] || ctx->last_status[3] || (long long)n * 2 > ctx->table_cap;
         if (!bad) {
             for (auto& sl : ctx->slots) sl.busy = false;
             drain_events(ctx);

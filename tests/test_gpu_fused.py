@@ -257,3 +257,17 @@ def test_finalize_async_and_pack_block():
     big.set_hbonds_in_selection_and_water_around(3.5)
     assert_same_results(big.initial_results, ref)
     assert big.last_run_stats["table_grows"] >= 1
+
+
+def test_general_path_pair_buffer_overflow_and_fallback():
+    """The general path stages point pairs in a batch-wide buffer; a buffer that is too small halves the sub-batch
+    and finally falls back to the per-point pair kernel - same bits every way."""
+    s, cfg = synth.config("C2", scale=0.3)
+    u = s.universe(24)
+    sel = "protein or resname TIP3"
+    ref = _port(u, sel, "water_around").initial_results
+    for opts in ({"fused": 0}, {"fused": 0, "pair_buf_bytes": 0}, {"fused": 0, "pair_buf_bytes": 1 << 16},
+                 {"fused": 0, "pair_buf_bytes": 4096}):
+        got = _run(u, sel, "water_around", opts)
+        assert_same_results(got.initial_results, ref, str(opts))
+        assert got.last_run_stats["fused_frames"] == 0
