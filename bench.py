@@ -286,14 +286,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                  # nvidia-smi every 200 ms from the warm-up on: the timed region itself is ~12 ms
+    t_sampler = time.perf_counter()
     for _ in range(args.warmup):
         one_pass_device()
-    sampler = ClockSampler(local_rank)
     sync_all()
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     launches = 0
+    retries = 0
     kernel_ms = {}
     kernel_launches = {}
     ev0.record(stream)
@@ -301,6 +303,7 @@ def run_ours(args):
         nb, wpr = one_pass_device(sync_merge=False)     # gather capacity learnt during warm-up; no host wait here
         tm = ctx.timers()
         launches += tm["n_launches"]
+        retries += tm["finalize_retries"]
         for k, v in tm["ms_kernel"].items():
             kernel_ms[k] = kernel_ms.get(k, 0.0) + v
             kernel_launches[k] = kernel_launches.get(k, 0) + tm["launches"][k]
@@ -308,8 +311,13 @@ def run_ours(args):
     sync_all()
     wall_ms = 1000.0 * (time.perf_counter() - t0)
     dev_ms = ev0.elapsed_time(ev1)      # CUDA events on the launching stream around exactly `steps` passes
+    while time.perf_counter() - t_sampler < 1.2:     # keep the same load up (untimed, rank-local: no collective)
+        ctx.begin(nf)                                # until the clock sampler has a few readings
+        ctx.submit_device(d_xyz.data_ptr(), na, nf)
+        ctx.finalize()
+    torch.cuda.synchronize()
     n_global_keys = None
-    if ctx.timers()["finalize_retries"]:
+    if retries:
         raise SystemExit("bench: a finalisation was redone inside the timed loop (bond table overflow)")
     for info in merged:
         n_out, over = info.tolist()
