@@ -294,6 +294,7 @@ int hb_create(hb_ctx** out, int device) {
 
 static void free_run(hb_ctx* ctx) {
     free_list(ctx->scratch_allocs);
+    ctx->pairbuf = PairBuf{};         // lived in scratch_allocs
     for (int k = 0; k < 2; ++k) {
         if (ctx->d_in[k]) cudaFree(ctx->d_in[k]);
         if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]);
@@ -1366,7 +1367,7 @@ int hb_joint_occupancy(hb_ctx* ctx, const uint8_t* select, uint32_t* words, int6
     unsigned* d_out = nullptr;
     unsigned long long* d_cnt = nullptr;
     cudaStream_t st = ctx->s_compute;
-    cudaError_t e = cudaMalloc((void**)&d_out, (size_t)wpr * 4 + 8);
+    cudaError_t e = cudaMalloc((void**)&d_out, ((size_t)wpr + 4) * 4);     // words, padding, one 8-byte counter
     if (e == cudaSuccess && select && n) e = cudaMalloc((void**)&d_sel, (size_t)n);
     if (e == cudaSuccess && d_sel) e = cudaMemcpyAsync(d_sel, select, (size_t)n, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {

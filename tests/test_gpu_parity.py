@@ -260,8 +260,16 @@ def test_gpu_occupancy_postprocessing_matches_numpy():
     the reference's numpy code gives on the bool vectors (network.py:99-107, 369-376, 1186-1198)."""
     import networkx as nx
     from cgraphs_b200.mdhbond import HbondAnalysis
+    # odd and even numbers of 32-frame words, a partial tail word
+    for n_frames in (5, 45):
+        _check_occupancy_postprocessing(n_frames)
+
+
+def _check_occupancy_postprocessing(n_frames):
+    import networkx as nx
+    from cgraphs_b200.mdhbond import HbondAnalysis
     s = synth.make_system(4000, 40, 71)
-    u = s.universe(45)                      # not a multiple of 32: the tail word is partial
+    u = s.universe(n_frames)
     hba = HbondAnalysis("protein", u)
     hba.set_hbonds_in_selection_and_water_around(3.5)
     res = hba.initial_results
@@ -286,7 +294,7 @@ def test_gpu_occupancy_postprocessing_matches_numpy():
         allc &= res[k]
     assert hba.compute_joint_occupancy(use_filtered=False) == allc.mean()
     # per-frame graphs
-    for frame in (0, 17, 44):
+    for frame in (0, n_frames // 2, n_frames - 1):
         g = hba._compute_graph_in_frame(frame, use_filtered=False)
         ref = nx.Graph()
         ref.add_edges_from((k.split(':')[0], k.split(':')[1]) for k, v in res.items() if v[frame])
