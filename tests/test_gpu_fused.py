@@ -271,3 +271,18 @@ def test_general_path_pair_buffer_overflow_and_fallback():
         got = _run(u, sel, "water_around", opts)
         assert_same_results(got.initial_results, ref, str(opts))
         assert got.last_run_stats["fused_frames"] == 0
+
+
+@pytest.mark.parametrize("distance,around,cut", [(2.8, 2.0, 20.0), (3.0, 2.8, 30.0), (3.5, 6.0, 45.0), (4.2, 3.5, 90.0),
+                                                 (3.0, 9.0, 60.0)])
+def test_other_cutoffs_and_angles(distance, around, cut):
+    """Cut-offs other than cgraphs' defaults: around_radius above and below distance, narrow and wide angles."""
+    s = synth.make_system(4500, 35, 400 + int(distance * 10))
+    u = s.universe(4)
+    for sel in ("protein", "protein or resname TIP3"):
+        kw = dict(distance=distance, cut_angle=cut)
+        ref = _port(u, sel, "water_around", around=around, **kw).initial_results
+        assert len(ref) > 0 or sel == "protein"         # (the narrowest case leaves the protein without bonds)
+        for fused in (1, 0):
+            got = _run(u, sel, "water_around", {"fused": fused}, around=around, **kw)
+            assert_same_results(got.initial_results, ref, "d=%s a=%s cut=%s %s fused=%d" % (distance, around, cut, sel, fused))
