@@ -5,6 +5,23 @@
 namespace {
 
 // ------------------------------------------------------------------------------------------------
+// Frame decode for planar sources (DCD trajectory records hold X[N], Y[N], Z[N] per frame): interleave the
+// atoms [first, first + len) of every frame of the batch into the [atom][3] layout the search kernels read
+// (replaces the reader's decode, reference basic.py:46-47 / MDAnalysis' DCD reader)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_interleave(const unsigned char* raw, long long frame_stride, long long x_off, long long y_off,
+                                                    long long z_off, long long first, long long len, long long n_atoms, float* xyz) {
+    const long long a = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= len) return;
+    const unsigned char* fr = raw + (size_t)blockIdx.y * frame_stride;
+    const float x = reinterpret_cast<const float*>(fr + x_off)[first + a];
+    const float y = reinterpret_cast<const float*>(fr + y_off)[first + a];
+    const float z = reinterpret_cast<const float*>(fr + z_off)[first + a];
+    float* o = xyz + ((size_t)blockIdx.y * n_atoms + first + a) * 3;
+    o[0] = x; o[1] = y; o[2] = z;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K0: reset per-frame state
 // ------------------------------------------------------------------------------------------------
 __global__ void k_init_frames(BatchView bv) {

@@ -121,6 +121,9 @@ struct hb_ctx {
     float* h_stage[2] = {nullptr, nullptr};
     size_t in_bytes = 0;              // planned capacity of one input buffer
     size_t in_alloc = 0;              // bytes actually allocated per input buffer
+    size_t stage_alloc = 0;           // bytes per pinned staging buffer
+    unsigned char* d_raw[2] = {nullptr, nullptr};   // planar sources (DCD): raw frame records before the interleave
+    size_t raw_alloc = 0;
     cudaEvent_t ev_copied[2]{}, ev_done[2]{};
     cudaEvent_t ev_run0{}, ev_run1{};
     long long batch_counter = 0;
@@ -298,10 +301,12 @@ static void free_run(hb_ctx* ctx) {
     for (int k = 0; k < 2; ++k) {
         if (ctx->d_in[k]) cudaFree(ctx->d_in[k]);
         if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]);
+        if (ctx->d_raw[k]) cudaFree(ctx->d_raw[k]);
         ctx->d_in[k] = nullptr;
         ctx->h_stage[k] = nullptr;
+        ctx->d_raw[k] = nullptr;
     }
-    ctx->in_alloc = 0;
+    ctx->in_alloc = ctx->stage_alloc = ctx->raw_alloc = 0;
     for (int k = 0; k < 2; ++k) {
         if (ctx->d_box[k]) cudaFree(ctx->d_box[k]);
         if (ctx->h_box[k]) cudaFreeHost(ctx->h_box[k]);
@@ -967,6 +972,60 @@ static int next_batch_frames(hb_ctx* ctx, long long f0, long long remaining, boo
     return nf;
 }
 
+static int ensure_box_buffers(hb_ctx* ctx) {
+    if (ctx->box_cap >= (size_t)std::max(ctx->host_batch_frames, 1)) return HB_OK;
+    size_t cap = (size_t)std::max(ctx->host_batch_frames, 1);
+    for (int k = 0; k < 2; ++k) {
+        if (ctx->d_box[k]) cudaFree(ctx->d_box[k]);
+        if (ctx->h_box[k]) cudaFreeHost(ctx->h_box[k]);
+        ctx->d_box[k] = nullptr; ctx->h_box[k] = nullptr;
+    }
+    ctx->box_cap = 0;
+    for (int k = 0; k < 2; ++k) {
+        CK(cudaMalloc((void**)&ctx->d_box[k], cap * 36));
+        CK(cudaHostAlloc((void**)&ctx->h_box[k], cap * 36, cudaHostAllocDefault));
+    }
+    ctx->box_cap = cap;
+    return HB_OK;
+}
+
+// the two device input buffers (frames as [atom][3]), the two pinned staging buffers for pageable sources and,
+// for planar sources, the two raw device buffers: as large as one batch of this call needs, at most the plan
+static int ensure_input_buffers(hb_ctx* ctx, size_t call_bytes, bool pinned, size_t raw_bytes_per_aos_byte_num,
+                                size_t raw_bytes_per_aos_byte_den) {
+    size_t need = std::max<size_t>(std::min(ctx->in_bytes, call_bytes), 16);
+    const bool planar = raw_bytes_per_aos_byte_num != 0;
+    auto raw_of = [&](size_t aos) { return planar ? aos / raw_bytes_per_aos_byte_den * raw_bytes_per_aos_byte_num + 256 : (size_t)0; };
+    const bool stage_small = !pinned && (!ctx->h_stage[0] || ctx->stage_alloc < (planar ? raw_of(std::max(need, ctx->in_alloc)) : std::max(need, ctx->in_alloc)));
+    const bool raw_small = planar && (!ctx->d_raw[0] || ctx->raw_alloc < raw_of(std::max(need, ctx->in_alloc)));
+    if (need <= ctx->in_alloc && !stage_small && !raw_small) return HB_OK;
+    CK(cudaStreamSynchronize(ctx->s_copy));
+    int rcv = full_verify(ctx);               // nothing may still read the old buffers
+    if (rcv) return rcv;
+    need = std::max(need, ctx->in_alloc);
+    for (int k = 0; k < 2; ++k) {
+        if (need > ctx->in_alloc || !ctx->d_in[k]) {
+            if (ctx->d_in[k]) cudaFree(ctx->d_in[k]);
+            ctx->d_in[k] = nullptr;
+            CK(cudaMalloc((void**)&ctx->d_in[k], need));
+        }
+        if (raw_small) {
+            if (ctx->d_raw[k]) cudaFree(ctx->d_raw[k]);
+            ctx->d_raw[k] = nullptr;
+            CK(cudaMalloc((void**)&ctx->d_raw[k], raw_of(need)));
+        }
+        if (stage_small) {
+            if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]);
+            ctx->h_stage[k] = nullptr;
+            CK(cudaHostAlloc((void**)&ctx->h_stage[k], planar ? raw_of(need) : need, cudaHostAllocDefault));
+        }
+    }
+    if (raw_small) ctx->raw_alloc = raw_of(need);
+    if (stage_small) ctx->stage_alloc = planar ? raw_of(need) : need;
+    ctx->in_alloc = need;
+    return HB_OK;
+}
+
 int hb_submit_frames(hb_ctx* ctx, const float* xyz, int64_t n_atoms, int64_t n_frames, const float* box) {
     if (!ctx || (!xyz && n_frames > 0)) return HB_ERR_ARG;
     int rc = check_submit(ctx, n_atoms, n_frames);
@@ -977,48 +1036,13 @@ int hb_submit_frames(hb_ctx* ctx, const float* xyz, int64_t n_atoms, int64_t n_f
         if ((rc = check_boxes(ctx, box, n_frames))) return rc;
     }
     CK(cudaSetDevice(ctx->device));
-    if (pbc && ctx->box_cap < (size_t)std::max(ctx->host_batch_frames, 1)) {
-        size_t cap = (size_t)std::max(ctx->host_batch_frames, 1);
-        for (int k = 0; k < 2; ++k) {
-            if (ctx->d_box[k]) cudaFree(ctx->d_box[k]);
-            if (ctx->h_box[k]) cudaFreeHost(ctx->h_box[k]);
-            ctx->d_box[k] = nullptr; ctx->h_box[k] = nullptr;
-        }
-        ctx->box_cap = 0;
-        for (int k = 0; k < 2; ++k) {
-            CK(cudaMalloc((void**)&ctx->d_box[k], cap * 36));
-            CK(cudaHostAlloc((void**)&ctx->h_box[k], cap * 36, cudaHostAllocDefault));
-        }
-        ctx->box_cap = cap;
-    }
+    if (pbc && (rc = ensure_box_buffers(ctx))) return rc;
     cudaPointerAttributes attr{};
     bool pinned = cudaPointerGetAttributes(&attr, xyz) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    {   // input buffers: as large as one batch of this call needs, at most the planned capacity
+    {
         size_t call_bytes = (size_t)batch_atoms(ctx, ctx->next_frame, (int)std::min<long long>(n_frames, 1 << 30), n_atoms) * 12;
-        size_t need = std::max<size_t>(std::min(ctx->in_bytes, call_bytes), 16);
-        if (need > ctx->in_alloc || (!pinned && !ctx->h_stage[0])) {
-            CK(cudaStreamSynchronize(ctx->s_copy));
-            int rcv = full_verify(ctx);           // nothing may still read the old buffers
-            if (rcv) return rcv;
-            need = std::max(need, ctx->in_alloc);
-            for (int k = 0; k < 2; ++k) {
-                if (need > ctx->in_alloc) {
-                    if (ctx->d_in[k]) cudaFree(ctx->d_in[k]);
-                    ctx->d_in[k] = nullptr;
-                    CK(cudaMalloc((void**)&ctx->d_in[k], need));
-                }
-                if (!pinned && (need > ctx->in_alloc || !ctx->h_stage[k])) {
-                    if (ctx->h_stage[k]) cudaFreeHost(ctx->h_stage[k]);
-                    ctx->h_stage[k] = nullptr;
-                    CK(cudaHostAlloc((void**)&ctx->h_stage[k], need, cudaHostAllocDefault));
-                } else if (pinned && need > ctx->in_alloc && ctx->h_stage[k]) {
-                    cudaFreeHost(ctx->h_stage[k]);       // too small now; re-created on demand
-                    ctx->h_stage[k] = nullptr;
-                }
-            }
-            ctx->in_alloc = need;
-        }
+        if ((rc = ensure_input_buffers(ctx, call_bytes, pinned, 0, 1))) return rc;
     }
     const float* src = xyz;
     long long done = 0;
@@ -1071,6 +1095,82 @@ int hb_submit_frames(hb_ctx* ctx, const float* xyz, int64_t n_atoms, int64_t n_f
         if (ctx->pending.size() > 8192) drain_events(ctx);
     }
     if (pinned) CK(cudaStreamSynchronize(ctx->s_copy));   // caller may reuse its pinned buffer on return
+    return HB_OK;
+}
+
+int hb_submit_frames_planar(hb_ctx* ctx, const void* raw, int64_t frame_stride, int64_t x_off, int64_t y_off, int64_t z_off,
+                            int64_t n_atoms, int64_t n_frames, const float* box) {
+    if (!ctx || (!raw && n_frames > 0)) return HB_ERR_ARG;
+    int rc = check_submit(ctx, n_atoms, n_frames);
+    if (rc) return rc;
+    if (ctx->prm.structure_batch) return fail(ctx, HB_ERR_ARG, "hb_submit_frames_planar: trajectories only");
+    const int64_t plane = n_atoms * 4;
+    if ((x_off | y_off | z_off | frame_stride) & 3 || x_off < 0 || y_off < 0 || z_off < 0 || x_off + plane > frame_stride ||
+        y_off + plane > frame_stride || z_off + plane > frame_stride)
+        return fail(ctx, HB_ERR_ARG, "hb_submit_frames_planar: plane offsets must be 4-byte aligned and inside the frame record");
+    const bool pbc = ctx->prm.pbc_mode != HB_PBC_NONE;
+    if (pbc) {
+        if (!box) return fail(ctx, HB_ERR_ARG, "hb_submit_frames_planar: pbc_mode needs the lattice vectors of every frame");
+        if ((rc = check_boxes(ctx, box, n_frames))) return rc;
+    }
+    CK(cudaSetDevice(ctx->device));
+    if (pbc && (rc = ensure_box_buffers(ctx))) return rc;
+    cudaPointerAttributes attr{};
+    bool pinned = cudaPointerGetAttributes(&attr, raw) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if ((rc = ensure_input_buffers(ctx, (size_t)n_atoms * 12 * (size_t)n_frames, pinned, (size_t)frame_stride, (size_t)n_atoms * 12))) return rc;
+    const unsigned char* src = (const unsigned char*)raw;
+    const int64_t offs[3] = {x_off, y_off, z_off};
+    std::vector<std::pair<long long, long long>> whole{{0, n_atoms}};
+    const auto& ranges = (ctx->opt_copy_ranges && !ctx->copy_ranges.empty()) ? ctx->copy_ranges : whole;
+    long long done = 0;
+    while (done < n_frames) {
+        long long f0 = ctx->next_frame;
+        int nf = next_batch_frames(ctx, f0, n_frames - done, true);
+        nf = (int)std::min<long long>(nf, (long long)(ctx->raw_alloc / (size_t)frame_stride));
+        int k = (int)(ctx->batch_counter & 1);
+        if ((rc = acquire_slot(ctx, k))) return rc;
+        const unsigned char* h = src;
+        if (!pinned) {                                   // only the plane pieces that are copied on are staged
+            unsigned char* st = (unsigned char*)ctx->h_stage[k];
+            for (int f = 0; f < nf; ++f)
+                for (int p = 0; p < 3; ++p)
+                    for (auto& r : ranges)
+                        memcpy(st + (size_t)f * frame_stride + offs[p] + r.first * 4, src + (size_t)f * frame_stride + offs[p] + r.first * 4,
+                               (size_t)(r.second - r.first) * 4);
+            h = st;
+        }
+        if (pbc) {
+            memcpy(ctx->h_box[k], box + 9 * done, (size_t)nf * 36);
+            CK(cudaMemcpyAsync(ctx->d_box[k], ctx->h_box[k], (size_t)nf * 36, cudaMemcpyHostToDevice, ctx->s_copy));
+        }
+        cudaEvent_t c0 = get_event(ctx), c1 = get_event(ctx);
+        cudaEventRecord(c0, ctx->s_copy);
+        for (int p = 0; p < 3; ++p)
+            for (auto& r : ranges) {
+                CK(cudaMemcpy2DAsync(ctx->d_raw[k] + offs[p] + r.first * 4, (size_t)frame_stride, h + offs[p] + r.first * 4, (size_t)frame_stride,
+                                     (size_t)(r.second - r.first) * 4, (size_t)nf, cudaMemcpyHostToDevice, ctx->s_copy));
+                ctx->tm.h2d_bytes += (long long)(r.second - r.first) * 4 * nf;
+            }
+        for (auto& r : ranges) {
+            const long long len = r.second - r.first;
+            dim3 grid((unsigned)((len + 255) / 256), (unsigned)nf);
+            k_interleave<<<grid, 256, 0, ctx->s_copy>>>(ctx->d_raw[k], frame_stride, x_off, y_off, z_off, r.first, len, n_atoms, ctx->d_in[k]);
+            ctx->tm.n_launches += 1;
+        }
+        CK(cudaGetLastError());
+        cudaEventRecord(c1, ctx->s_copy);
+        ctx->pending.push_back({c0, c1, -2});
+        CK(cudaEventRecord(ctx->ev_copied[k], ctx->s_copy));
+        CK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_copied[k], 0));
+        if ((rc = launch_in_slot(ctx, k, ctx->d_in[k], f0, nf, n_atoms, (size_t)nf * n_atoms * 12, pbc ? ctx->d_box[k] : nullptr))) return rc;
+        ctx->batch_counter++;
+        ctx->next_frame += nf;
+        done += nf;
+        src += (size_t)nf * frame_stride;
+        if (ctx->pending.size() > 8192) drain_events(ctx);
+    }
+    if (pinned) CK(cudaStreamSynchronize(ctx->s_copy));
     return HB_OK;
 }
 

@@ -1,0 +1,183 @@
+"""Structure / trajectory files without MDAnalysis: PDB topologies and CHARMM/NAMD DCD trajectories.
+
+The reference gets its coordinates from ``MDAnalysis.Universe(structure, trajectories)``
+(``cgraphs/mdhbond/basic.py:46-47``); MDAnalysis is not installable in this image, and its DCD reader decodes
+every frame on the CPU (de-interleaving the X / Y / Z records). Here the frame records of a DCD file are handed
+to ``libhbgpu`` as they lie in the file (``hb_submit_frames_planar``): they cross PCIe untouched and are
+interleaved on the device.
+
+* :func:`read_pdb` / :func:`write_pdb`  - topology columns (names, resnames, resids, segids), one coordinate set,
+  ``CRYST1`` cell
+* :class:`DCDFrames` / :func:`write_dcd` - frame source over a DCD file (memory mapped), with the planar view
+  ``planar_block`` the native path uses, and the unit cell of every frame
+* :func:`universe_from_files` - ``Universe`` (cgraphs_b200.universe) from a PDB and an optional DCD
+"""
+from __future__ import annotations
+
+import struct
+
+import numpy as np
+
+from .universe import Topology, Universe
+
+
+# ------------------------------------------------------------------------------------------------
+# PDB
+# ------------------------------------------------------------------------------------------------
+def write_pdb(path, topology, xyz, dimensions=None):
+    """Fixed-column PDB with 4-character residue names (CHARMM style: TIP3) and the segid in columns 73-76."""
+    with open(path, "w") as f:
+        if dimensions is not None:
+            a, b, c, al, be, ga = [float(x) for x in dimensions]
+            f.write("CRYST1%9.3f%9.3f%9.3f%7.2f%7.2f%7.2f P 1           1\n" % (a, b, c, al, be, ga))
+        for i in range(topology.n_atoms):
+            name = str(topology.names[i])
+            name_field = (" %-3s" % name) if len(name) < 4 else name[:4]
+            f.write("ATOM  %5d %4s %-4s%1s%4d    %8.3f%8.3f%8.3f%6.2f%6.2f      %-4s\n" % (
+                (i + 1) % 100000, name_field, str(topology.resnames[i])[:4], " ", int(topology.resids[i]) % 10000,
+                xyz[i, 0], xyz[i, 1], xyz[i, 2], 1.0, 0.0, str(topology.segids[i])[:4]))
+        f.write("END\n")
+
+
+def read_pdb(path):
+    """Returns (Topology, float32 [N, 3], dimensions or None). ATOM / HETATM records, first model only.
+
+    Residue numbers above 9999 wrap in the file; a new residue starts whenever (segid, resid, resname) changes,
+    and wrapped numbers are unwrapped per segment so that residues stay distinct."""
+    names, resnames, resids, segids, xyz = [], [], [], [], []
+    dims = None
+    with open(path) as f:
+        for line in f:
+            rec = line[:6]
+            if rec == "CRYST1":
+                dims = [float(line[6:15]), float(line[15:24]), float(line[24:33]), float(line[33:40]), float(line[40:47]),
+                        float(line[47:54])]
+            elif rec in ("ATOM  ", "HETATM"):
+                names.append(line[12:16].strip())
+                resnames.append(line[17:21].strip())
+                resids.append(int(line[22:26]))
+                seg = line[72:76].strip() if len(line) >= 76 else ""
+                segids.append(seg if seg else (line[21].strip() or "SYSTEM"))
+                xyz.append((float(line[30:38]), float(line[38:46]), float(line[46:54])))
+            elif rec.startswith("ENDMDL"):
+                break
+    resids = np.asarray(resids, dtype=np.int64)
+    # unwrap residue numbers that restarted after 9999 inside one segment
+    out = resids.copy()
+    offset, prev_seg, prev_raw = 0, None, None
+    for i, (seg, r) in enumerate(zip(segids, resids)):
+        if seg != prev_seg:
+            offset = 0
+        elif r < prev_raw and prev_raw - r > 5000:
+            offset += 10000
+        out[i] = r + offset
+        prev_seg, prev_raw = seg, r
+    return Topology(names, resnames, out, segids), np.asarray(xyz, dtype=np.float32), dims
+
+
+# ------------------------------------------------------------------------------------------------
+# DCD (CHARMM / NAMD, little endian, 32-bit record markers)
+# ------------------------------------------------------------------------------------------------
+def write_dcd(path, frames, dimensions=None):
+    """frames: float32 array [F, N, 3] (or an iterable of [N, 3]); dimensions: [a, b, c, alpha, beta, gamma] or None."""
+    frames = [np.asarray(fr, dtype=np.float32) for fr in frames]
+    n_frames, n_atoms = len(frames), frames[0].shape[0]
+    with open(path, "wb") as f:
+        icntrl = [0] * 20
+        icntrl[0], icntrl[1], icntrl[2] = n_frames, 0, 1
+        icntrl[10] = 1 if dimensions is not None else 0
+        icntrl[19] = 24                                   # CHARMM version: unit cell block holds six doubles
+        hdr = b"CORD" + struct.pack("<9i", *icntrl[:9]) + struct.pack("<f", 1.0) + struct.pack("<10i", *icntrl[10:])
+        f.write(struct.pack("<i", 84) + hdr + struct.pack("<i", 84))
+        title = b"written by cgraphs_b200.io".ljust(80)
+        f.write(struct.pack("<i", 84) + struct.pack("<i", 1) + title + struct.pack("<i", 84))
+        f.write(struct.pack("<3i", 4, n_atoms, 4))
+        for fr in frames:
+            if dimensions is not None:
+                a, b, c, al, be, ga = [float(x) for x in dimensions]
+                cell = struct.pack("<6d", a, np.cos(np.deg2rad(ga)), b, np.cos(np.deg2rad(be)), np.cos(np.deg2rad(al)), c)
+                f.write(struct.pack("<i", 48) + cell + struct.pack("<i", 48))
+            for k in range(3):
+                f.write(struct.pack("<i", 4 * n_atoms))
+                f.write(np.ascontiguousarray(fr[:, k], dtype="<f4").tobytes())
+                f.write(struct.pack("<i", 4 * n_atoms))
+
+
+class DCDFrames:
+    """Frame source over a DCD file: ``len``, ``frame(i)``, ``block(a, b)`` like the array sources of
+    cgraphs_b200.universe, plus ``planar_block(a, b)`` (the raw frame records and where the X / Y / Z planes lie in
+    them) for ``hb_submit_frames_planar`` and ``dimensions_of(i)``."""
+
+    def __init__(self, path):
+        self.path = path
+        with open(path, "rb") as f:
+            head = f.read(92)
+            if len(head) < 92 or struct.unpack("<i", head[:4])[0] != 84 or head[4:8] != b"CORD":
+                raise ValueError("%s: not a little-endian CHARMM/NAMD DCD file" % path)
+            icntrl = struct.unpack("<9i", head[8:44]) + (0,) + struct.unpack("<10i", head[48:88])
+            self.n_frames_header = icntrl[0]
+            if icntrl[8] != 0:
+                raise ValueError("%s: DCD files with fixed atoms are not supported" % path)
+            self.has_cell = icntrl[10] != 0
+            if icntrl[11] != 0:
+                raise ValueError("%s: 4-dimensional DCD files are not supported" % path)
+            self.charmm_version = icntrl[19]
+            n = struct.unpack("<i", f.read(4))[0]
+            f.seek(n, 1)
+            if struct.unpack("<i", f.read(4))[0] != n:
+                raise ValueError("%s: corrupt title block" % path)
+            a, self.n_atoms, b = struct.unpack("<3i", f.read(12))
+            if a != 4 or b != 4:
+                raise ValueError("%s: corrupt atom-count block" % path)
+            self.data_offset = f.tell()
+        plane = 4 * self.n_atoms + 8
+        self.cell_bytes = 56 if self.has_cell else 0
+        self.frame_stride = self.cell_bytes + 3 * plane
+        self.x_off = self.cell_bytes + 4
+        self.y_off = self.x_off + plane
+        self.z_off = self.y_off + plane
+        self._map = np.memmap(path, dtype=np.uint8, mode="r", offset=self.data_offset)
+        self.n_frames = len(self._map) // self.frame_stride
+        if self.n_frames_header and self.n_frames_header < self.n_frames:
+            self.n_frames = self.n_frames_header
+
+    def __len__(self):
+        return self.n_frames
+
+    def planar_block(self, start, stop):
+        """(uint8 view of the frame records [start, stop), frame_stride, x_off, y_off, z_off)."""
+        raw = self._map[start * self.frame_stride:stop * self.frame_stride]
+        return raw, self.frame_stride, self.x_off, self.y_off, self.z_off
+
+    def block(self, start, stop):
+        raw = np.asarray(self._map[start * self.frame_stride:stop * self.frame_stride]).reshape(stop - start, self.frame_stride)
+        out = np.empty((stop - start, self.n_atoms, 3), dtype=np.float32)
+        for k, off in enumerate((self.x_off, self.y_off, self.z_off)):
+            out[:, :, k] = raw[:, off:off + 4 * self.n_atoms].copy().view("<f4")
+        return out
+
+    def frame(self, i):
+        return self.block(int(i), int(i) + 1)[0]
+
+    def dimensions_of(self, i):
+        """[a, b, c, alpha, beta, gamma] of frame i, or None."""
+        if not self.has_cell:
+            return None
+        o = i * self.frame_stride + 4
+        a, g, b, be, al, c = np.asarray(self._map[o:o + 48]).view("<f8")
+        ang = []
+        for v in (al, be, g):      # CHARMM >= 25 stores cosines, older files and NAMD may store degrees
+            ang.append(float(np.rad2deg(np.arccos(v))) if -1.0 <= v <= 1.0 else float(v))
+        return [float(a), float(b), float(c), ang[0], ang[1], ang[2]]
+
+
+def universe_from_files(structure, trajectory=None):
+    """``Universe`` from a PDB file and an optional DCD trajectory (without one, the PDB coordinates are the only frame)."""
+    topo, xyz, dims = read_pdb(structure)
+    if trajectory is None:
+        return Universe(topo, xyz[None], dims)
+    frames = DCDFrames(trajectory)
+    if frames.n_atoms != topo.n_atoms:
+        raise ValueError("%s has %d atoms, %s has %d" % (trajectory, frames.n_atoms, structure, topo.n_atoms))
+    d0 = frames.dimensions_of(0) if frames.n_frames else None
+    return Universe(topo, frames, d0 if d0 is not None else dims)

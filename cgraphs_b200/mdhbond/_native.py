@@ -85,6 +85,7 @@ SYMBOLS = [
     ("hb_set_option", C.c_int, [_P, C.c_char_p, C.c_int64]),
     ("hb_begin", C.c_int, [_P, C.c_int64]),
     ("hb_submit_frames", C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
+    ("hb_submit_frames_planar", C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),
     ("hb_submit_frames_device", C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
     ("hb_finalize_async", C.c_int, [_P]),
     ("hb_pack_keys_device", C.c_int, [_P, _P, C.c_int32]),
@@ -219,6 +220,16 @@ class Context:
             b = np.ascontiguousarray(box, dtype=np.float32).reshape(int(n_frames), 9)
         self._ck(self.lib.hb_submit_frames(self.h, int(ptr), int(n_atoms), int(n_frames),
                                            b.ctypes.data if b is not None else None), "hb_submit_frames")
+
+    def submit_planar(self, raw, frame_stride, x_off, y_off, z_off, n_atoms, n_frames, box=None):
+        """raw: contiguous uint8 array (or address) of n_frames frame records with X / Y / Z planes (DCD layout)."""
+        b = None
+        if box is not None:
+            b = np.ascontiguousarray(box, dtype=np.float32).reshape(int(n_frames), 9)
+        ptr = raw if isinstance(raw, int) else raw.ctypes.data
+        self._ck(self.lib.hb_submit_frames_planar(self.h, ptr, int(frame_stride), int(x_off), int(y_off), int(z_off),
+                                                  int(n_atoms), int(n_frames), b.ctypes.data if b is not None else None),
+                 "hb_submit_frames_planar")
 
     def submit_device(self, dev_ptr, n_atoms, n_frames, box_dev_ptr=None):
         self._ck(self.lib.hb_submit_frames_device(self.h, int(dev_ptr), int(n_atoms), int(n_frames),

@@ -55,8 +55,17 @@ def _as_universe(structure, trajectories):
     if isinstance(structure, (str, bytes)) or hasattr(structure, "__fspath__"):
         try:
             import MDAnalysis as _MDAnalysis
-        except ImportError as e:  # pragma: no cover - MDAnalysis is absent in the build image
-            raise ImportError("a structure path needs MDAnalysis; pass a Universe object instead") from e
+        except ImportError:
+            # no MDAnalysis: the built-in readers cover PDB structures and DCD trajectories (cgraphs_b200/io.py)
+            import os as _os
+            from ..io import universe_from_files
+            traj = trajectories[0] if isinstance(trajectories, (list, tuple)) and len(trajectories) == 1 else trajectories
+            ext = _os.path.splitext(str(structure))[1].lower()
+            if ext != ".pdb" or (traj is not None and (isinstance(traj, (list, tuple)) or
+                                                       _os.path.splitext(str(traj))[1].lower() != ".dcd")):
+                raise ImportError("without MDAnalysis only a .pdb structure with at most one .dcd trajectory can be "
+                                  "read; pass a Universe object instead")
+            return universe_from_files(structure, traj)
         return _MDAnalysis.Universe(structure, trajectories) if trajectories is not None else _MDAnalysis.Universe(structure)
     if hasattr(structure, "select_atoms") and hasattr(structure, "trajectory"):
         return structure
@@ -81,6 +90,14 @@ def box_rows(dimensions):
 def _frame_boxes(universe, frame_indices):
     """float32 [k, 3, 3] lattice rows of the given frames."""
     traj = universe.trajectory
+    if hasattr(getattr(traj, "frames", None), "dimensions_of"):      # DCD file: the cell of every frame
+        out = _np.empty((len(frame_indices), 3, 3), dtype=_np.float32)
+        for k, f in enumerate(frame_indices):
+            dims = traj.frames.dimensions_of(int(f))
+            if dims is None:
+                raise ValueError("pbc needs unit-cell dimensions; the trajectory has none")
+            out[k] = box_rows(dims)
+        return out
     if getattr(traj, "frames", None) is not None:          # array-backed Universe: one cell for all frames
         dims = getattr(traj, "dimensions", None)
         if dims is None:
@@ -287,10 +304,20 @@ class HbondAnalysis(object):
             ctx.begin(n_local)
             block = max(1, min(n_local, int((256 << 20) // max(1, self._n_atoms * 12))))
             done = lo
-            for xyz in _frame_blocks(self._universe, fi[lo:hi], block):
-                box = _frame_boxes(self._universe, fi[done:done + len(xyz)]) if pbc_mode else None
-                ctx.submit(xyz, box=box)
-                done += len(xyz)
+            frames = getattr(self._universe.trajectory, "frames", None)
+            sub = fi[lo:hi]
+            if hasattr(frames, "planar_block") and isinstance(sub, range) and sub.step == 1:
+                # trajectory file records go to the device as they are and are decoded (interleaved) there
+                for i in range(sub.start, sub.stop, block):
+                    j = min(sub.stop, i + block)
+                    raw, stride, xo, yo, zo = frames.planar_block(i, j)
+                    box = _frame_boxes(self._universe, range(i, j)) if pbc_mode else None
+                    ctx.submit_planar(raw, stride, xo, yo, zo, self._n_atoms, j - i, box=box)
+            else:
+                for xyz in _frame_blocks(self._universe, sub, block):
+                    box = _frame_boxes(self._universe, fi[done:done + len(xyz)]) if pbc_mode else None
+                    ctx.submit(xyz, box=box)
+                    done += len(xyz)
             keys, words = ctx.results()
             self.last_run_stats = ctx.timers()
             if self._shard is None:      # the packed rows stay on the device for the occupancy post-processing below

@@ -145,6 +145,13 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total);
  * Asynchronous: returns once the last batch is queued; buffers passed in may be reused after return. */
 int hb_submit_frames(hb_ctx* ctx, const float* xyz, int64_t n_atoms, int64_t n_frames, const float* box);
 
+/* Same, for planar frame records as trajectory files store them (DCD: per frame X[n_atoms], Y[n_atoms], Z[n_atoms]
+ * as float32 inside a record of frame_stride bytes; x_off / y_off / z_off = byte offsets of the three planes
+ * inside a frame record, all multiples of 4). The records are copied to the device as they are (inert atom ranges
+ * skipped) and interleaved there - the decode MDAnalysis' reader does for the reference (basic.py:46-47). */
+int hb_submit_frames_planar(hb_ctx* ctx, const void* raw, int64_t frame_stride, int64_t x_off, int64_t y_off,
+                            int64_t z_off, int64_t n_atoms, int64_t n_frames, const float* box);
+
 /* Same, for coordinates already resident in device memory (the caller guarantees they are complete, and keeps
  * d_xyz / d_box valid and unchanged until hb_sync or hb_finalize returns: a batch may be re-run on overflow). */
 int hb_submit_frames_device(hb_ctx* ctx, const float* d_xyz, int64_t n_atoms, int64_t n_frames,

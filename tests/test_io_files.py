@@ -1,0 +1,53 @@
+"""PDB / DCD readers (cgraphs_b200/io.py): round trips on CPU; the planar DCD path through the kernels on the GPU."""
+import numpy as np
+import pytest
+
+from cgraphs_b200 import synth
+from cgraphs_b200.io import DCDFrames, read_pdb, universe_from_files, write_dcd, write_pdb
+from tests.helpers import assert_same_results
+
+
+def _files(tmp_path, n_frames=7, kind="tric"):
+    s = synth.make_system(3200, 25, 61, dimensions_kind=kind)
+    xyz = s.frames(0, n_frames)
+    pdb, dcd = str(tmp_path / "sys.pdb"), str(tmp_path / "traj.dcd")
+    write_pdb(pdb, s.topology, xyz[0], s.dimensions)
+    write_dcd(dcd, xyz, s.dimensions)
+    return s, xyz, pdb, dcd
+
+
+def test_pdb_dcd_round_trip(tmp_path):
+    s, xyz, pdb, dcd = _files(tmp_path)
+    topo, x0, dims = read_pdb(pdb)
+    t = s.topology
+    assert list(topo.names) == list(t.names) and list(topo.resnames) == list(t.resnames)
+    assert list(topo.segids) == list(t.segids) and np.array_equal(topo.resids, t.resids)
+    assert np.allclose(x0, xyz[0], atol=6e-4)                     # PDB keeps three decimals
+    assert np.allclose(dims, s.dimensions, atol=1e-2)
+    fr = DCDFrames(dcd)
+    assert len(fr) == len(xyz) and fr.n_atoms == xyz.shape[1]
+    assert np.array_equal(fr.block(0, len(xyz)), xyz)             # DCD keeps float32 exactly
+    assert np.array_equal(fr.frame(3), xyz[3])
+    assert np.allclose(fr.dimensions_of(2), s.dimensions, atol=1e-4)
+    raw, stride, xo, yo, zo = fr.planar_block(2, 5)
+    assert len(raw) == 3 * stride and xo % 4 == 0 and yo % 4 == 0 and zo % 4 == 0 and stride % 4 == 0
+    assert np.array_equal(np.asarray(raw[stride + yo:stride + yo + 4 * fr.n_atoms]).view("<f4"), xyz[3][:, 1])
+    u = universe_from_files(pdb, dcd)
+    assert len(u.trajectory) == len(xyz) and len(u.select_atoms("protein")) == len(s.universe(1).select_atoms("protein"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pbc", [False, True])
+def test_gpu_reads_dcd_records_directly(tmp_path, pbc):
+    from cgraphs_b200.mdhbond import HbondAnalysis
+    from oracle import hbond_port
+    s, xyz, pdb, dcd = _files(tmp_path, n_frames=9)
+    ref = hbond_port.run(s.universe(9), "protein", "water_around", around=3.5).initial_results
+    for opts in ({"fused": 1}, {"fused": 0}, {"copy_ranges": 0}):
+        hba = HbondAnalysis("protein", pdb, dcd, pbc=pbc, native_options=opts)       # file paths, no MDAnalysis
+        hba.set_hbonds_in_selection_and_water_around(3.5)
+        assert_same_results(hba.initial_results, ref, "dcd %s pbc=%s" % (opts, pbc))
+        assert hba.nb_frames == 9
+    sl = HbondAnalysis("protein", pdb, dcd, start=2, stop=8, step=1)
+    sl.set_hbonds_in_selection_and_water_around(3.5)
+    assert {k: v.tobytes() for k, v in sl.initial_results.items()} == {k: v[2:8].tobytes() for k, v in ref.items() if v[2:8].any()}
