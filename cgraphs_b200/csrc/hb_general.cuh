@@ -287,6 +287,72 @@ __global__ void __launch_bounds__(128) k_pairs(BatchView bv, DevTopo tp, RunPara
 }
 
 // ------------------------------------------------------------------------------------------------
+// Ion contacts (HbondAnalysis.set_add_ion_interactions, reference hbond.py:57-94): every selection entry and,
+// with include_water, every water of the water group within `distance` of an ion; key = id of the atom ':' id of
+// the ion, no angle criterion, no orientation rule. Ions are few: their coordinates sit in shared memory and
+// every point (one thread each) tests all of them with the exact DIST predicate.
+// ------------------------------------------------------------------------------------------------
+struct IonTable {
+    const int* atom;      // atom index inside the frame
+    const int* group;     // key group id of the ion's id string
+    int n;
+};
+
+template <bool PBC>
+__global__ void __launch_bounds__(256) k_ion_contacts(BatchView bv, DevTopo tp, RunParams rp, BondTable bt, IonTable ions, int include_water) {
+    __shared__ float4 ion_s[1024];
+    const int b = blockIdx.y;
+    int sys;
+    const float* xyz = frame_xyz(bv, tp, b, sys);
+    const long long frame = bv.frame0 + b;
+    const int s0 = tp.sys_sel_off[sys], nsel = tp.sys_sel_off[sys + 1] - s0;
+    const int w0 = tp.sys_wat_off[sys], nwp = include_water ? tp.sys_wat_off[sys + 1] - w0 : 0;
+    PbcGrid pg;
+    if constexpr (PBC) {
+        pg.box = load_box(bv.box + 9ll * b);
+        pg.ia = 1.0f / pg.box.ax; pg.ib = 1.0f / pg.box.by; pg.ic = 1.0f / pg.box.cz;
+    }
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < nsel + nwp;
+    float x = 0.f, y = 0.f, z = 0.f;
+    int g0 = -1, g1 = -1;                       // key groups of the point (a selection atom of the water group has two)
+    if (live) {
+        int atom;
+        if (i < nsel) {
+            const int4 k = tp.sel_pack[s0 + i];
+            atom = tp.sel_atom[s0 + i];
+            g0 = tp.ent_group[k.x >= 0 ? k.x : k.y];
+            if (include_water && k.z >= 0) g1 = tp.ent_group[k.z];
+        } else {
+            atom = tp.wat_atom[w0 + i - nsel];
+            g0 = tp.ent_group[tp.wat_ent[w0 + i - nsel]];
+        }
+        const float* p = xyz + 3ll * atom;
+        x = p[0]; y = p[1]; z = p[2];
+    }
+    int nhit = 0;
+    for (int base = 0; base < ions.n; base += 1024) {
+        const int m = min(1024, ions.n - base);
+        __syncthreads();
+        for (int k = threadIdx.x; k < m; k += blockDim.x) {
+            const float* q = xyz + 3ll * ions.atom[base + k];
+            ion_s[k] = make_float4(q[0], q[1], q[2], __int_as_float(ions.group[base + k]));
+        }
+        __syncthreads();
+        if (!live) continue;
+        for (int k = 0; k < m; ++k) {
+            const float4 q = ion_s[k];
+            if (!within<PBC>(x, y, z, q.x, q.y, q.z, rp.r2f_hi, rp.r2, pg)) continue;
+            const unsigned long long gi = (unsigned long long)(unsigned)__float_as_int(q.w);
+            record_bond(bt, ((unsigned long long)(unsigned)g0 << 32) | gi, frame);
+            ++nhit;
+            if (g1 >= 0 && g1 != g0) { record_bond(bt, ((unsigned long long)(unsigned)g1 << 32) | gi, frame); ++nhit; }
+        }
+    }
+    flush_hits(bt, nhit);
+}
+
+// ------------------------------------------------------------------------------------------------
 // K7 in two dense steps (used when the batch-wide pair buffer is available):
 //   K7a  every point walks its neighbourhood and appends the point pairs within `distance` to one pair buffer
 //        for the whole sub-batch (records staged in shared memory, one global atomic per block and trip)

@@ -150,6 +150,8 @@ struct hb_ctx {
     long long fin_n_max = 0;
     bool fin_queued = false, fin_speculative = false;
     long long n_sel_total = 0, n_wat_total = 0;
+    IonTable ions{nullptr, nullptr, 0};
+    int ion_include_water = 1;
     // trajectory mode: atom ranges [begin, end) that hold every atom the kernels read; the rest of a frame
     // (inert atoms) is never copied to the device. Empty = copy whole frames.
     std::vector<std::pair<long long, long long>> copy_ranges;
@@ -392,6 +394,7 @@ int hb_set_topology(hb_ctx* ctx, const hb_topology* t) {
     if (t->n_sel >= WATER_TAG || t->n_wat >= WATER_TAG) return fail(ctx, HB_ERR_ARG, "topology: too many points");
     CK(cudaSetDevice(ctx->device));
     free_list(ctx->topo_allocs);
+    ctx->ions = IonTable{nullptr, nullptr, 0};
     ctx->have_topo = false;       // (run allocations are kept: hb_begin compares everything that sizes them)
     int ns = t->n_systems;
     ctx->h_sys_atom_off.assign(t->sys_atom_off, t->sys_atom_off + ns + 1);
@@ -517,6 +520,22 @@ int hb_set_topology(hb_ctx* ctx, const hb_topology* t) {
     return HB_OK;
 }
 
+int hb_set_ions(hb_ctx* ctx, const int32_t* ion_atom, const int32_t* ion_group, int32_t n_ions, int32_t include_water) {
+    if (!ctx || n_ions < 0 || (n_ions > 0 && (!ion_atom || !ion_group))) return HB_ERR_ARG;
+    if (!ctx->have_topo) return fail(ctx, HB_ERR_STATE, "hb_set_ions before hb_set_topology");
+    if (ctx->running) return fail(ctx, HB_ERR_STATE, "hb_set_ions during a run");
+    for (int i = 0; i < n_ions; ++i)
+        if (ion_atom[i] < 0 || ion_atom[i] >= ctx->max_atoms || ion_group[i] < 0) return fail(ctx, HB_ERR_ARG, "hb_set_ions: index out of range");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    ctx->ions = IonTable{nullptr, nullptr, 0};
+    if ((rc = upload(ctx, ion_atom, (size_t)n_ions, &ctx->ions.atom, ctx->topo_allocs))) return rc;
+    if ((rc = upload(ctx, ion_group, (size_t)n_ions, &ctx->ions.group, ctx->topo_allocs))) return rc;
+    ctx->ions.n = n_ions;
+    ctx->ion_include_water = include_water != 0;
+    return HB_OK;
+}
+
 int hb_set_entry_groups(hb_ctx* ctx, const int32_t* g, int32_t n) {
     if (!ctx || !g) return HB_ERR_ARG;
     if (!ctx->have_topo || n != ctx->n_ent) return fail(ctx, HB_ERR_ARG, "hb_set_entry_groups: size mismatch");
@@ -530,7 +549,9 @@ int hb_set_params(hb_ctx* ctx, const hb_params* p) {
     if (!ctx || !p) return HB_ERR_ARG;
     if (ctx->running) return fail(ctx, HB_ERR_STATE, "hb_set_params during a run");
     if (!(p->distance > 0.0) || !std::isfinite(p->distance)) return fail(ctx, HB_ERR_ARG, "distance must be positive");
-    if (p->method != HB_METHOD_IN_SELECTION && p->method != HB_METHOD_WATER_AROUND) return fail(ctx, HB_ERR_ARG, "unknown method");
+    if (p->method != HB_METHOD_IN_SELECTION && p->method != HB_METHOD_WATER_AROUND && p->method != HB_METHOD_ION_CONTACTS)
+        return fail(ctx, HB_ERR_ARG, "unknown method");
+    if (p->method == HB_METHOD_ION_CONTACTS && p->structure_batch) return fail(ctx, HB_ERR_ARG, "ion contacts: trajectories only");
     if (p->method == HB_METHOD_WATER_AROUND && (!(p->around_radius >= 0.0) || !std::isfinite(p->around_radius)))
         return fail(ctx, HB_ERR_ARG, "around_radius must be >= 0");
     if (p->pbc_mode != HB_PBC_NONE && p->pbc_mode != HB_PBC_ORTHO && p->pbc_mode != HB_PBC_TRICLINIC)
@@ -563,7 +584,7 @@ int hb_set_params(hb_ctx* ctx, const hb_params* p) {
 // `grow` > 0 doubles the local-water / pair capacities that many times (used after a fused overflow).
 static bool plan_fused(hb_ctx* ctx, int grow = 0) {
     ctx->fused_active = false;
-    if (!ctx->opt_fused) return false;
+    if (!ctx->opt_fused || ctx->rp.method == HB_METHOD_ION_CONTACTS) return false;
     const bool wa = ctx->rp.method == HB_METHOD_WATER_AROUND;
     FusedCfg fc{};
     fc.sel_cap = std::max(ctx->max_sel, 1);
@@ -838,6 +859,16 @@ static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, 
         CK(cudaGetLastError());
         ctx->tm.fused_frames += nf;
         ctx->last_batch_fused = true;
+    } else if (ctx->rp.method == HB_METHOD_ION_CONTACTS) {
+        ctx->last_batch_fused = false;
+        const long long pts = (long long)ctx->max_sel + (ctx->ion_include_water ? ctx->max_wat : 0);
+        if (ctx->ions.n > 0 && pts > 0) {
+            dim3 grid((unsigned)((pts + 255) / 256), (unsigned)nf);
+            KTimer t(ctx, KC_PAIRS);
+            if (ctx->rp.pbc != HB_PBC_NONE) k_ion_contacts<true><<<grid, 256, 0, st>>>(bv, ctx->tp, ctx->rp, ctx->bt, ctx->ions, ctx->ion_include_water);
+            else k_ion_contacts<false><<<grid, 256, 0, st>>>(bv, ctx->tp, ctx->rp, ctx->bt, ctx->ions, ctx->ion_include_water);
+            CK(cudaGetLastError());
+        }
     } else {
         ctx->last_batch_fused = false;
         int rc = ensure_scratch(ctx);

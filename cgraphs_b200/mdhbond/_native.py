@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc"
 
 METHOD_IN_SELECTION = 0
 METHOD_WATER_AROUND = 1
+METHOD_ION_CONTACTS = 2
 PBC_NONE, PBC_ORTHO, PBC_TRICLINIC = 0, 1, 2
 
 
@@ -82,6 +83,7 @@ SYMBOLS = [
     ("hb_set_topology", C.c_int, [_P, C.POINTER(HbTopology)]),
     ("hb_set_entry_groups", C.c_int, [_P, C.POINTER(C.c_int32), C.c_int32]),
     ("hb_set_params", C.c_int, [_P, C.POINTER(HbParams)]),
+    ("hb_set_ions", C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int32]),
     ("hb_set_option", C.c_int, [_P, C.c_char_p, C.c_int64]),
     ("hb_begin", C.c_int, [_P, C.c_int64]),
     ("hb_submit_frames", C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
@@ -186,6 +188,11 @@ class Context:
         st.n_ent_h = len(keep["ent_h_atom"])
         assert len(keep["ent_h_off"]) == st.n_ent + 1
         self._ck(self.lib.hb_set_topology(self.h, C.byref(st)), "hb_set_topology")
+
+    def set_ions(self, ion_atom, ion_group, include_water=True):
+        a, g = _i32(ion_atom), _i32(ion_group)
+        self._ck(self.lib.hb_set_ions(self.h, _ptr(a, C.c_int32), _ptr(g, C.c_int32), len(a), int(bool(include_water))),
+                 "hb_set_ions")
 
     def set_entry_groups(self, groups):
         g = _i32(groups)

@@ -163,9 +163,13 @@ class HbondAnalysis(object):
                                        stop if isinstance(stop, int) else None, step)
         self._mda_selection = self._universe.select_atoms(selection)
         if not len(self._mda_selection): raise AssertionError('No atoms match the selection')
+        self._ions_list = ions                                        # basic.py:53-60
+        self._ions_atoms = _np.zeros(0, _np.int64)
+        self._ions_ids = []
+        self._ions_ids_atomwise = []
         if ions:
-            raise NotImplementedError('ion interactions (hbond.py:57-94) are outside the accelerated path')
-        self._ions_list = ions
+            ion_group = self._universe.select_atoms(' or '.join(['name {}'.format(ion) for ion in ions]))
+            self._ions_atoms = _np.asarray(ion_group.indices, dtype=_np.int64)
         self._water = self._universe.select_atoms(WATER_DEFINITION)
         self.initial_results = {}
         self.filtered_results = {}
@@ -190,6 +194,10 @@ class HbondAnalysis(object):
                                check_angle=check_angle, residuewise=residuewise,
                                add_donors_without_hydrogen=add_donors_without_hydrogen)
         self._topology = top
+        if len(self._ions_atoms):
+            from .topology import _ids
+            self._ions_ids = list(_ids(cols, self._ions_atoms, False))
+            self._ions_ids_atomwise = list(_ids(cols, self._ions_atoms, True))
         self.donor_names = top.donor_names
         self.acceptor_names = top.acceptor_names
         self._nb_donors = top.nD
@@ -234,11 +242,21 @@ class HbondAnalysis(object):
         if self._nb_donors == 0: raise AssertionError('No donors in the selection')
         result = self._run("in_selection", 0.0, exclude_backbone_backbone)
         self._set_results(result)
+        if self._ions_list: self.set_add_ion_interactions(False)          # hbond.py:135
 
     def set_hbonds_in_selection_and_water_around(self, around_radius, exclude_backbone_backbone=True):
         """hbond.py:232-289."""
         result = self._run("water_around", float(around_radius), exclude_backbone_backbone)
         self._set_results(result)
+        if self._ions_list: self.set_add_ion_interactions(True)           # hbond.py:289
+
+    def set_add_ion_interactions(self, include_water=True):
+        """hbond.py:57-94: contacts (no angle criterion) of the selection entries and, with include_water, of all
+        waters of the water group with the ions; keys ``id:ion_id``; merged into the current results."""
+        if not len(self._ions_atoms): raise AssertionError('No ions were specified during initialization.')
+        result = self._run("ions", 0.0, True, include_water=include_water)
+        if not self.initial_results: self._set_results(result)
+        else: self._add_overwrite_results(result)
 
     def _context(self):
         if self._ctx is None:
@@ -265,17 +283,24 @@ class HbondAnalysis(object):
                 raise IndexError('water hydrogens do not pair up as two per water; the reference indexes past '
                                  'heavy2hydrogen here (network.py:86, helpfunctions.py:144)')
 
-    def _run(self, method, around_radius, exclude_backbone_backbone):
+    def _run(self, method, around_radius, exclude_backbone_backbone, include_water=True):
         top = self._topology
         self._check_hydrogen_tables(method)
         ctx = self._context()
         cache = self.__dict__.setdefault("_packed", {})
         if method not in cache:          # packed device tables per method (the key id strings differ)
-            cache[method] = pack_systems([top], [top.key_ids(method)], [self._n_atoms])
-        tables, group_names = cache[method]
+            if method == "ions":         # hbond.py:61-66: _all_ids for the entries, water / ion ids by `residuewise`
+                ids = list(top.all_ids[:top.first_water]) + list(top.water_ids if self.residuewise else top.water_ids_atomwise)
+                cache[method] = pack_systems([top], [ids], [self._n_atoms],
+                                             extra_ids=self._ions_ids if self.residuewise else self._ions_ids_atomwise)
+            else:
+                cache[method] = pack_systems([top], [top.key_ids(method)], [self._n_atoms])
+        tables, group_names = cache[method][0], cache[method][1]
         if getattr(ctx, "_uploaded", None) is not tables:
             ctx.set_topology(tables)
             ctx._uploaded = tables
+        if method == "ions":
+            ctx.set_ions(self._ions_atoms, cache[method][2], include_water)
         cthr = self._cos_threshold_override
         if cthr is None:
             cthr = _cos_threshold(float(self.cut_angle)) if self.check_angle else -1.0
@@ -288,8 +313,9 @@ class HbondAnalysis(object):
             else:   # True: decide from the first frame's cell
                 b0 = _frame_boxes(self._universe, self._frame_indices[:1])[0]
                 pbc_mode = _native.PBC_ORTHO if not (b0[1, 0] or b0[2, 0] or b0[2, 1]) else _native.PBC_TRICLINIC
-        ctx.set_params(self.distance, around_radius, cthr, self.check_angle, exclude_backbone_backbone,
-                       _native.METHOD_WATER_AROUND if method == "water_around" else _native.METHOD_IN_SELECTION,
+        native_method = {"water_around": _native.METHOD_WATER_AROUND, "in_selection": _native.METHOD_IN_SELECTION,
+                         "ions": _native.METHOD_ION_CONTACTS}[method]
+        ctx.set_params(self.distance, around_radius, cthr, self.check_angle, exclude_backbone_backbone, native_method,
                        pbc_mode=pbc_mode)
         # frame block of this rank (block boundaries are multiples of 32 frames)
         fi = self._frame_indices

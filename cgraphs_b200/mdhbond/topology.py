@@ -205,15 +205,22 @@ class CompiledTopology:
         return out
 
 
-def pack_systems(tops, methods_ids, n_atoms_list):
+def pack_systems(tops, methods_ids, n_atoms_list, extra_ids=None):
     """Concatenate CompiledTopology objects of several systems into the hb_topology arrays.
 
     `methods_ids[i]` is the id list (one string per entry) that forms the keys of system i.  Key group
     ids index the sorted list of distinct id strings over all systems, returned as `group_names`.
+    `extra_ids` (e.g. ion ids) join the same id table; their group ids are returned as a third value.
     """
     all_ids = [s for ids in methods_ids for s in ids]
+    n_ent_ids = len(all_ids)
+    if extra_ids is not None:
+        all_ids = all_ids + list(extra_ids)
     group_names, ent_group = np.unique(np.asarray(all_ids, dtype=object).astype(str), return_inverse=True) \
         if all_ids else (np.zeros(0, dtype=str), np.zeros(0, np.int64))
+    extra_group = np.asarray(ent_group[n_ent_ids:], np.int32)
+    ent_group = ent_group[:n_ent_ids]
+    all_ids = all_ids[:n_ent_ids]
     res3 = ['-'.join(s.split('-')[:3]) for s in all_ids]
     _, ent_residue = np.unique(np.asarray(res3, dtype=object).astype(str), return_inverse=True) \
         if res3 else (None, np.zeros(0, np.int64))
@@ -252,4 +259,6 @@ def pack_systems(tops, methods_ids, n_atoms_list):
     t["ent_group"] = np.asarray(ent_group, np.int32)
     t["ent_residue"] = np.asarray(ent_residue, np.int32)
     t["ent_h_off"] = np.concatenate([[0], np.cumsum(cat("ent_h_cnt", np.int64))]).astype(np.int32)
+    if extra_ids is not None:
+        return t, [str(s) for s in group_names], extra_group
     return t, [str(s) for s in group_names]

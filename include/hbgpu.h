@@ -44,6 +44,7 @@ typedef enum {
 
 #define HB_METHOD_IN_SELECTION 0   /* HbondAnalysis.set_hbonds_in_selection, hbond.py:96 */
 #define HB_METHOD_WATER_AROUND 1   /* HbondAnalysis.set_hbonds_in_selection_and_water_around, hbond.py:232 */
+#define HB_METHOD_ION_CONTACTS 2   /* HbondAnalysis.set_add_ion_interactions, hbond.py:57-94 (needs hb_set_ions) */
 
 #define HB_PBC_NONE 0              /* reference semantics: no periodic images */
 #define HB_PBC_ORTHO 1             /* opt-in minimum image, orthorhombic cell */
@@ -126,6 +127,10 @@ const char* hb_kernel_name(int kernel_class);      /* names for hb_timers.ms_ker
 int hb_set_topology(hb_ctx* ctx, const hb_topology* topo);
 int hb_set_entry_groups(hb_ctx* ctx, const int32_t* ent_group, int32_t n_ent); /* swap key ids only */
 int hb_set_params(hb_ctx* ctx, const hb_params* params);
+/* Ions for HB_METHOD_ION_CONTACTS (basic.py:53-60): atom index inside the frame and key group id (an index into the
+ * same id-string table ent_group refers to) of every ion; include_water: also pair the waters of the water group
+ * with the ions (hbond.py:78-83). Call after hb_set_topology. */
+int hb_set_ions(hb_ctx* ctx, const int32_t* ion_atom, const int32_t* ion_group, int32_t n_ions, int32_t include_water);
 int hb_set_option(hb_ctx* ctx, const char* name, int64_t value);
         /* "batch_bytes": device budget per frame batch; "table_capacity": initial bond-table slots;
            "profile": 1 = time every kernel class with CUDA events; "max_batch_frames";

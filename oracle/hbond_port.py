@@ -441,3 +441,35 @@ def run(universe, selection, method='in_selection', around=3.5, exclude_backbone
         run_block(pt, [frames.frame(f)], method, around, exclude_backbone_backbone, backend, cos_threshold,
                   strict, results, col, box=box)
     return PortResult(pt, results)
+
+
+def run_ions(universe, selection, ions, include_water=True, box=None, **ctor):
+    """HbondAnalysis.set_add_ion_interactions (hbond.py:57-94; ion group basic.py:53-60): contacts within `distance`
+    of every selection entry (and every water of the water group) with the ions, no angle criterion.
+    Returns the result dict the reference merges into the H-bond results."""
+    pt = PortTopology(universe, selection, **ctor)
+    topo = universe.topology
+    ion_atoms = universe.select_atoms(' or '.join('name %s' % i for i in ions)).indices
+    detailed = not pt.residuewise
+    ion_ids = [_id(topo, i, detailed) for i in ion_atoms]
+    water_ids = pt.water_ids if pt.residuewise else pt.water_ids_atomwise
+    fw = pt.first_water
+    results = {}
+    frames = universe.trajectory.frames
+    bp = (lambda a, b, r: ball_pairs_pbc(a, b, r, np.asarray(box, dtype=np.float32))) if box is not None else \
+         (lambda a, b, r: ball_pairs(a, b, r))
+    for col, f in enumerate(pt.frame_indices):
+        pos = np.asarray(frames.frame(f), dtype=np.float32)
+        ion_pos = pos[ion_atoms]
+        keys = set()
+        i, j = bp(pos[pt.entry_atom[:fw]], ion_pos, pt.distance)
+        keys.update(pt.all_ids[a] + ':' + ion_ids[b] for a, b in zip(i.tolist(), j.tolist()))
+        if include_water and len(pt.water_atoms):
+            i, j = bp(pos[pt.water_atoms], ion_pos, pt.distance)
+            keys.update(water_ids[a] + ':' + ion_ids[b] for a, b in zip(i.tolist(), j.tolist()))
+        for key in keys:
+            row = results.get(key)
+            if row is None:
+                row = results[key] = np.zeros(pt.nb_frames, dtype=bool)
+            row[col] = True
+    return results

@@ -63,3 +63,33 @@ def golden_cases():
             n = len(json.load(f)["runs"])
         out += [(name, i) for i in range(n)]
     return out
+
+
+def ion_system(seed=3, n_frames=3):
+    """A synthetic system with 40 ions (SOD / CLA) placed next to protein and water atoms."""
+    from cgraphs_b200 import synth
+    from cgraphs_b200.universe import Topology, Universe
+    s = synth.make_system(3000, 25, seed, n_filler=60)
+    t = s.topology
+    names, resnames, resids, segids = list(t.names), list(t.resnames), list(t.resids), list(t.segids)
+    fill = [i for i, r in enumerate(resnames) if r == "POPC"]
+    for k, i in enumerate(fill[:40]):
+        nm = "SOD" if k % 2 == 0 else "CLA"
+        names[i] = nm
+        resnames[i] = nm
+        resids[i] = 5000 + k
+        segids[i] = "ION"
+    xyz = s.frames(0, n_frames)
+    rng = np.random.default_rng(seed)
+    targets = rng.choice(len(names) - len(fill), size=40, replace=False)
+    for k, i in enumerate(fill[:40]):
+        xyz[:, i, :] = xyz[:, targets[k], :] + rng.normal(0, 1.4, size=(n_frames, 3)).astype(np.float32)
+    return Universe(Topology(names, resnames, resids, segids), xyz, s.dimensions)
+
+
+def port_with_ions(u, selection, method, ions, around=3.5, **kw):
+    """Oracle result of a set_hbonds_* call on an analysis constructed with ions= (hbond.py:135,289)."""
+    from oracle import hbond_port
+    res = dict(hbond_port.run(u, selection, method, around=around, **kw).initial_results)
+    res.update(hbond_port.run_ions(u, selection, ions, include_water=(method == "water_around"), **kw))
+    return res

@@ -333,3 +333,23 @@ def test_gpu_batch_conserved_graph():
         assert {frozenset(e) for e in edges} == ce
         assert set(nodes) == cnodes
         assert len(ce) > 0
+
+
+@pytest.mark.parametrize("residuewise", [True, False])
+def test_gpu_ion_contacts(residuewise):
+    """ions=[...]: set_add_ion_interactions runs after both set_hbonds_* methods (hbond.py:57-94,135,289)."""
+    from cgraphs_b200.mdhbond import HbondAnalysis
+    from tests.helpers import ion_system, port_with_ions
+    u = ion_system(seed=4, n_frames=5)
+    for method, pbc in (("in_selection", False), ("water_around", False), ("water_around", True)):
+        ref = port_with_ions(u, "protein", method, ['SOD', 'CLA'], residuewise=residuewise)
+        hba = HbondAnalysis("protein", u, ions=['SOD', 'CLA'], residuewise=residuewise, pbc=pbc)
+        if method == "in_selection":
+            hba.set_hbonds_in_selection()
+        else:
+            hba.set_hbonds_in_selection_and_water_around(3.5)
+        assert_same_results(hba.initial_results, ref, "ions %s pbc=%s" % (method, pbc))
+        assert sum(1 for k in ref if k.split(':')[1].split('-')[1] in ('SOD', 'CLA')) > 5
+    bare = HbondAnalysis("protein", u)
+    with pytest.raises(AssertionError, match="No ions"):
+        bare.set_add_ion_interactions()

@@ -58,3 +58,15 @@ def test_second_call_replaces_first_result():
     port = hbond_port.run(u, "protein", "water_around", check_angle=False, add_donors_without_hydrogen=True)
     assert_same_results(port.initial_results, hba.initial_results)
     assert set(first) <= set(hba.initial_results)
+
+
+@pytest.mark.parametrize("residuewise", [True, False])
+def test_port_ion_contacts_equal_reference(residuewise):
+    """set_add_ion_interactions (hbond.py:57-94), called at the end of both set_hbonds_* methods when ions are given."""
+    from tests.helpers import ion_system, port_with_ions
+    u = ion_system()
+    for method in ("in_selection", "water_around"):
+        ref = ref_harness.run_reference(u, "protein", method, ions=['SOD', 'CLA'], residuewise=residuewise)
+        got = port_with_ions(u, "protein", method, ['SOD', 'CLA'], residuewise=residuewise)
+        assert {k: v.tobytes() for k, v in ref.initial_results.items()} == {k: v.tobytes() for k, v in got.items()}
+        assert any(k.split(':')[1].split('-')[1] in ('SOD', 'CLA') for k in got)
