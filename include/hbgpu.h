@@ -15,6 +15,15 @@
  *                        key building and result[key][frame] = True
  *   hb_finalize / hb_get_keys / hb_get_bits
  *                     <- the `result` dict handed to _set_results, hbond.py:134 / 288 (basic.py:94-98)
+ *   hb_submit_frames_planar
+ *                     <- the trajectory reader's frame decode, basic.py:46-47 (DCD X / Y / Z records)
+ *   hb_set_ions + HB_METHOD_ION_CONTACTS
+ *                     <- set_add_ion_interactions, hbond.py:57-94 (ion group: basic.py:53-60)
+ *   hb_get_counts / hb_joint_occupancy / hb_get_frame_column
+ *                     <- filter_occupancy, compute_joint_occupancy, _compute_graph_in_frame,
+ *                        network.py:99-107, 369-376, 1186-1198 (on the packed matrix)
+ *   hb_finalize_async / hb_pack_keys_device / hb_merge_keys_device
+ *                     <- no counterpart: the multi-GPU key exchange (frames sharded over ranks)
  *
  * Conventions: every function returns 0 on success or a negative hb_status; no C++ exception crosses the
  * ABI; the message of the last failure is available from hb_last_error().  The caller owns every host
@@ -135,7 +144,8 @@ int hb_set_option(hb_ctx* ctx, const char* name, int64_t value);
         /* "batch_bytes": device budget per frame batch; "table_capacity": initial bond-table slots;
            "profile": 1 = time every kernel class with CUDA events; "max_batch_frames";
            "fused": 0 = never use the one-CTA-per-frame kernel; "fused_lw_cap" / "fused_cell_cap": its
-           shared-memory capacities (0 = automatic); "fused_stages", "fused_prefetch", "fused_batch_frames";
+           shared-memory capacities (0 = automatic); "fused_pair_cap", "fused_stages", "fused_prefetch", "fused_wait_ns",
+           "fused_batch_frames"; "pair_buf_bytes": batch-wide pair buffer of the general kernels (0 = per-point kernel);
            "copy_ranges": 0 = always copy whole frames; "force_radix_sort" (test hook);
            "compute_stream": a cudaStream_t of the caller on which every kernel of the context is launched, so
            that the caller's own stream-ordered work (events, collectives) brackets the search (0 = library stream) */
