@@ -11,7 +11,7 @@ LIB = os.path.join(CSRC, "libhbgpu.so")
 SOURCES = [os.path.join(CSRC, "hbgpu.cu")]
 HEADERS = [os.path.join(HERE, "..", "include", "hbgpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared"]
 
 
 def needs_build():

@@ -29,6 +29,7 @@
 #include <cstring>
 #include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #define HB_VERSION "hbgpu 0.1 (sm_100a)"
@@ -156,6 +157,7 @@ struct hb_ctx {
     // (inert atoms) is never copied to the device. Empty = copy whole frames.
     std::vector<std::pair<long long, long long>> copy_ranges;
     int opt_copy_ranges = 1;
+    int opt_stage_threads = 8;        // host threads that copy pageable frames into the pinned staging buffer
     int trace = 0;
 
     // timers
@@ -248,6 +250,22 @@ struct KTimer {   // times one kernel class when profiling is on
     }
 };
 
+// Staging copy pageable -> pinned with several threads: one thread moves ~10 GB/s, PCIe takes 55 GB/s.
+// copy(f0, f1) copies the frames [f0, f1) of the batch.
+template <typename F>
+static void parallel_frames(int nf, size_t bytes_per_frame, int max_threads, F copy) {
+    int nt = (int)std::min<size_t>((size_t)std::max(max_threads, 1), (bytes_per_frame * (size_t)nf) >> 23);   // >= 8 MB per thread
+    nt = std::min(nt, nf);
+    if (nt <= 1) { copy(0, nf); return; }
+    std::vector<std::thread> th;
+    th.reserve(nt);
+    for (int t = 0; t < nt; ++t) {
+        const int a = (int)((long long)nf * t / nt), b = (int)((long long)nf * (t + 1) / nt);
+        th.emplace_back([=]() { copy(a, b); });
+    }
+    for (auto& x : th) x.join();
+}
+
 extern "C" {
 
 const char* hb_version(void) { return HB_VERSION; }
@@ -270,6 +288,7 @@ int hb_create(hb_ctx** out, int device) {
     if (!ctx) return HB_ERR_NOMEM;
     ctx->device = device;
     ctx->trace = getenv("HBGPU_TRACE") != nullptr;
+    ctx->opt_stage_threads = (int)std::min<unsigned>(16u, std::max<unsigned>(1u, std::thread::hardware_concurrency()));
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess) {
         g_create_error = cudaGetErrorString(e);
         delete ctx;
@@ -374,6 +393,7 @@ int hb_set_option(hb_ctx* ctx, const char* name, int64_t value) {
         ctx->s_compute = value ? (cudaStream_t)(uintptr_t)value : ctx->s_own;
     }
     else if (n == "copy_ranges") ctx->opt_copy_ranges = value != 0;
+    else if (n == "stage_threads") ctx->opt_stage_threads = (int)std::min<long long>(std::max<long long>(value, 1), 64);
     else if (n == "fused_lw_cap") ctx->opt_fused_lw_cap = std::max<long long>(value, 0);
     else if (n == "fused_cell_cap") ctx->opt_fused_cell_cap = std::max<long long>(value, 0);
     else if (n == "fused_pair_cap") ctx->opt_fused_pair_cap = std::max<long long>(value, 0);
@@ -1087,15 +1107,23 @@ int hb_submit_frames(hb_ctx* ctx, const float* xyz, int64_t n_atoms, int64_t n_f
         const float* h = src;
         const bool ranged = ctx->opt_copy_ranges && !ctx->prm.structure_batch && !ctx->copy_ranges.empty();
         if (!pinned) {
+            float* stg = ctx->h_stage[k];
             if (ranged) {
-                for (int f = 0; f < nf; ++f)
-                    for (auto& r : ctx->copy_ranges)
-                        memcpy(ctx->h_stage[k] + ((size_t)f * n_atoms + r.first) * 3, src + ((size_t)f * n_atoms + r.first) * 3,
-                               (size_t)(r.second - r.first) * 12);
+                const auto& ranges = ctx->copy_ranges;
+                parallel_frames(nf, (size_t)n_atoms * 12, ctx->opt_stage_threads, [=, &ranges](int fa, int fb2) {
+                    for (int f = fa; f < fb2; ++f)
+                        for (auto& r : ranges)
+                            memcpy(stg + ((size_t)f * n_atoms + r.first) * 3, src + ((size_t)f * n_atoms + r.first) * 3,
+                                   (size_t)(r.second - r.first) * 12);
+                });
+            } else if (ctx->prm.structure_batch) {
+                memcpy(stg, src, bytes);
             } else {
-                memcpy(ctx->h_stage[k], src, bytes);
+                parallel_frames(nf, (size_t)n_atoms * 12, ctx->opt_stage_threads, [=](int fa, int fb2) {
+                    memcpy(stg + (size_t)fa * n_atoms * 3, src + (size_t)fa * n_atoms * 3, (size_t)(fb2 - fa) * n_atoms * 12);
+                });
             }
-            h = ctx->h_stage[k];
+            h = stg;
         }
         if (pbc) {
             memcpy(ctx->h_box[k], box + 9 * done, (size_t)nf * 36);
@@ -1164,11 +1192,13 @@ int hb_submit_frames_planar(hb_ctx* ctx, const void* raw, int64_t frame_stride, 
         const unsigned char* h = src;
         if (!pinned) {                                   // only the plane pieces that are copied on are staged
             unsigned char* st = (unsigned char*)ctx->h_stage[k];
-            for (int f = 0; f < nf; ++f)
-                for (int p = 0; p < 3; ++p)
-                    for (auto& r : ranges)
-                        memcpy(st + (size_t)f * frame_stride + offs[p] + r.first * 4, src + (size_t)f * frame_stride + offs[p] + r.first * 4,
-                               (size_t)(r.second - r.first) * 4);
+            parallel_frames(nf, (size_t)frame_stride, ctx->opt_stage_threads, [=, &ranges](int fa, int fb2) {
+                for (int f = fa; f < fb2; ++f)
+                    for (int p = 0; p < 3; ++p)
+                        for (auto& r : ranges)
+                            memcpy(st + (size_t)f * frame_stride + offs[p] + r.first * 4,
+                                   src + (size_t)f * frame_stride + offs[p] + r.first * 4, (size_t)(r.second - r.first) * 4);
+            });
             h = st;
         }
         if (pbc) {

@@ -146,7 +146,8 @@ int hb_set_option(hb_ctx* ctx, const char* name, int64_t value);
            "fused": 0 = never use the one-CTA-per-frame kernel; "fused_lw_cap" / "fused_cell_cap": its
            shared-memory capacities (0 = automatic); "fused_pair_cap", "fused_stages", "fused_prefetch", "fused_wait_ns",
            "fused_batch_frames"; "pair_buf_bytes": batch-wide pair buffer of the general kernels (0 = per-point kernel);
-           "copy_ranges": 0 = always copy whole frames; "force_radix_sort" (test hook);
+           "copy_ranges": 0 = always copy whole frames; "stage_threads": host threads that move pageable frames
+           into the pinned staging buffers (default min(16, cores)); "force_radix_sort" (test hook);
            "compute_stream": a cudaStream_t of the caller on which every kernel of the context is launched, so
            that the caller's own stream-ordered work (events, collectives) brackets the search (0 = library stream) */
 
