@@ -20,12 +20,12 @@ from .topology import pack_systems
 class StructureResult(object):
     """What a per-structure ``HbondAnalysis`` exposes after a ``set_hbonds_*`` call."""
 
-    def __init__(self, results, residuewise):
+    def __init__(self, results, residuewise, graph=None):
         self.initial_results = results
         self.filtered_results = results
         self.nb_frames = 1
         self.residuewise = residuewise
-        self.initial_graph = dict2graph(results, residuewise)
+        self.initial_graph = dict2graph(results, residuewise) if graph is None else graph
         self.filtered_graph = self.initial_graph
 
 
@@ -95,8 +95,10 @@ class HbondBatch(object):
         for i, a in enumerate(self.analyses):
             rows = _np.nonzero(bits[:, i])[0]
             res = {self.bond_keys[r]: _np.ones(1, dtype=bool) for r in rows}
-            a._set_results(res)
-            self.results.append(StructureResult(res, self.residuewise))
+            graph = dict2graph(res, self.residuewise)      # one graph per structure, shared by the views below
+            a.initial_results = a.filtered_results = res   # (what _set_results does, basic.py:94-98)
+            a.initial_graph = a.filtered_graph = graph
+            self.results.append(StructureResult(res, self.residuewise, graph))
         return self.results
 
     # ---------------------------------------------------------------------------------------------
