@@ -189,6 +189,54 @@ __global__ void __launch_bounds__(1024) k_merge_keys(const unsigned long long* g
         if (mk[i] != EMPTY_KEY && (i == 0 || mk[i] != mk[i - 1])) out[pos++] = mk[i];
 }
 
+// Merge step for many ranks: the distinct keys are far fewer than the gathered ones (most bonds exist on every
+// rank), so they are first de-duplicated in a small hash set by all SMs (k_union_insert) and only the distinct
+// keys are sorted by one CTA (k_union_finish). Cost follows the number of distinct keys, not world * cap.
+#define UNION_SLOTS 32768
+__global__ void k_union_insert(const unsigned long long* gathered, int world, int cap, unsigned long long* table, long long* info) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= world * cap) return;
+    const int w = i / cap, j = i - w * cap;
+    const long long cnt = (long long)gathered[(size_t)w * (cap + 1)];
+    if (j == 0 && cnt > cap) info[1] = 1;
+    if (j >= cnt) return;
+    const unsigned long long key = gathered[(size_t)w * (cap + 1) + 1 + j];
+    unsigned h = hash64(key) & (UNION_SLOTS - 1);
+    for (int probe = 0; probe < UNION_SLOTS; ++probe) {
+        const unsigned long long cur = atomicCAS(&table[h], EMPTY_KEY, key);
+        if (cur == EMPTY_KEY || cur == key) return;
+        h = (h + 1) & (UNION_SLOTS - 1);
+    }
+}
+__global__ void __launch_bounds__(1024) k_union_finish(const unsigned long long* table, unsigned long long* out, long long* info) {
+    extern __shared__ __align__(16) unsigned long long mk[];      // up to 16384 keys
+    __shared__ int total;
+    if (threadIdx.x == 0) total = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < UNION_SLOTS; i += blockDim.x) {  // coalesced scan; order is irrelevant, a sort follows
+        const unsigned long long k = table[i];
+        if (k != EMPTY_KEY) mk[atomicAdd(&total, 1)] = k;
+    }
+    __syncthreads();
+    const int n = total;
+    int m = 2;
+    while (m < n) m <<= 1;
+    for (int i = n + threadIdx.x; i < m; i += blockDim.x) mk[i] = EMPTY_KEY;
+    __syncthreads();
+    for (int size = 2; size <= m; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = threadIdx.x; i < (m >> 1); i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                const bool up = (lo & size) == 0;
+                const unsigned long long a = mk[lo], b = mk[hi];
+                if ((a > b) == up) { mk[lo] = b; mk[hi] = a; }
+            }
+            __syncthreads();
+        }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = mk[i];
+    if (threadIdx.x == 0) info[0] = n;
+}
+
 __global__ void k_gather_rows(const unsigned* bits, const unsigned* slots, const int* n_ptr, int n_max, int wpr, unsigned* out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t total = (size_t)min(*n_ptr, n_max) * wpr;

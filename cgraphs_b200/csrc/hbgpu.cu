@@ -152,6 +152,7 @@ struct hb_ctx {
     bool fin_queued = false, fin_speculative = false;
     long long n_sel_total = 0, n_wat_total = 0;
     IonTable ions{nullptr, nullptr, 0};
+    unsigned long long* merge_table = nullptr;    // hash set of hb_merge_keys_device (many ranks)
     int ion_include_water = 1;
     // trajectory mode: atom ranges [begin, end) that hold every atom the kernels read; the rest of a frame
     // (inert atoms) is never copied to the device. Empty = copy whole frames.
@@ -368,6 +369,7 @@ int hb_destroy(hb_ctx* ctx) {
     for (int k = 0; k < 2; ++k) { cudaEventDestroy(ctx->ev_copied[k]); cudaEventDestroy(ctx->ev_done[k]); }
     cudaEventDestroy(ctx->ev_run0);
     cudaEventDestroy(ctx->ev_run1);
+    if (ctx->merge_table) cudaFree(ctx->merge_table);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->h_verify) cudaFreeHost(ctx->h_verify);
     if (ctx->h_hits) cudaFreeHost(ctx->h_hits);
@@ -1492,6 +1494,21 @@ int hb_merge_keys_device(hb_ctx* ctx, const uint64_t* d_gathered, int32_t world,
     const int pow2_cap = (cap & (cap - 1)) == 0 && cap >= 2;     // merge-only network needs power-of-two runs
     if (total > 16384) return fail(ctx, HB_ERR_ARG, "hb_merge_keys_device: more than 16384 gathered keys; merge on the host");
     CK(cudaSetDevice(ctx->device));
+    if (total > 8192) {      // many ranks: de-duplicate in a hash set first, sort only the distinct keys
+        cudaStream_t st = ctx->s_compute;
+        if (!ctx->merge_table) {
+            CK(cudaMalloc((void**)&ctx->merge_table, (size_t)UNION_SLOTS * 8));
+            CK(cudaFuncSetAttribute(k_union_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+        }
+        k_fill_u64<<<32, 256, 0, st>>>(ctx->merge_table, (size_t)UNION_SLOTS, EMPTY_KEY);
+        CK(cudaMemsetAsync(d_info, 0, 16, st));
+        k_union_insert<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const unsigned long long*)d_gathered, world, cap,
+                                                                        ctx->merge_table, (long long*)d_info);
+        k_union_finish<<<1, 1024, 16384 * 8, st>>>(ctx->merge_table, (unsigned long long*)d_out, (long long*)d_info);
+        CK(cudaGetLastError());
+        ctx->tm.n_launches += 3;
+        return HB_OK;
+    }
     size_t smem = (size_t)m * 8;
     CK(cudaFuncSetAttribute(k_merge_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_merge_keys<<<1, 1024, smem, ctx->s_compute>>>((const unsigned long long*)d_gathered, world, cap, m, pow2_cap,
