@@ -37,12 +37,13 @@
 #include "hb_general.cuh"
 #include "hb_fused.cuh"
 #include "hb_finalize.cuh"
+#include "hb_wires.cuh"
 
 namespace {
 
-enum KernelClass { KC_INIT = 0, KC_GATHER, KC_GRID, KC_COUNT, KC_SCAN, KC_SCATTER, KC_LOCAL, KC_PAIRS, KC_FUSED, KC_N };
+enum KernelClass { KC_INIT = 0, KC_GATHER, KC_GRID, KC_COUNT, KC_SCAN, KC_SCATTER, KC_LOCAL, KC_PAIRS, KC_FUSED, KC_WIRES, KC_N };
 const char* const kKernelNames[KC_N] = {"init_frames", "gather_sel", "grid_setup", "cell_count",
-                                        "cell_scan", "cell_scatter", "local_water", "pairs", "frame_fused"};
+                                        "cell_scan", "cell_scatter", "local_water", "pairs", "frame_fused", "wire_bfs"};
 
 }  // namespace
 
@@ -153,6 +154,22 @@ struct hb_ctx {
     long long n_sel_total = 0, n_wat_total = 0;
     IonTable ions{nullptr, nullptr, 0};
     unsigned long long* merge_table = nullptr;    // hash set of hb_merge_keys_device (many ranks)
+    // water wires (hb_wires.cuh)
+    struct Wire {
+        bool on = false;
+        const int* d_ent_node = nullptr;          // lives in topo_allocs
+        int n_res = 0, n_wat_nodes = 1, max_water = 0, allow_direct = 1;
+        int nb4 = 0;                              // row words holding the per-frame bytes
+        int2* d_edges = nullptr;
+        int* d_cnt = nullptr;
+        long long edge_cap = 0;
+        int frames = 0;                           // frames per search + BFS round
+        int n_cta = 0;
+        std::vector<void*> allocs;
+        WireCfg cfg{};
+    } wire;
+    long long opt_wire_edge_cap = 0;              // 0: automatic
+    BondTable bt_run{};                           // what the search kernels of the current launch get (wire mode: + edge lists)
     int ion_include_water = 1;
     // trajectory mode: atom ranges [begin, end) that hold every atom the kernels read; the rest of a frame
     // (inert atoms) is never copied to the device. Empty = copy whole frames.
@@ -310,7 +327,7 @@ int hb_create(hb_ctx** out, int device) {
     }
     cudaEventCreate(&ctx->ev_run0);
     cudaEventCreate(&ctx->ev_run1);
-    cudaHostAlloc((void**)&ctx->h_status, 8 * sizeof(int), cudaHostAllocDefault);
+    cudaHostAlloc((void**)&ctx->h_status, 16 * sizeof(int), cudaHostAllocDefault);
     cudaHostAlloc((void**)&ctx->h_verify, 8 * sizeof(int), cudaHostAllocDefault);
     cudaHostAlloc((void**)&ctx->h_hits, sizeof(unsigned long long), cudaHostAllocDefault);
     *out = ctx;
@@ -336,6 +353,9 @@ static void free_run(hb_ctx* ctx) {
         ctx->h_box[k] = nullptr;
     }
     ctx->box_cap = 0;
+    free_list(ctx->wire.allocs);
+    ctx->wire.d_edges = nullptr;
+    ctx->wire.d_cnt = nullptr;
     if (ctx->bt.keys) cudaFree(ctx->bt.keys);
     if (ctx->bt.bits) cudaFree(ctx->bt.bits);
     if (ctx->bt.n_keys) cudaFree(ctx->bt.n_keys);
@@ -380,6 +400,7 @@ int hb_destroy(hb_ctx* ctx) {
 }
 
 int hb_set_option(hb_ctx* ctx, const char* name, int64_t value) {
+    if (ctx && name && !strcmp(name, "wire_edge_cap")) { ctx->opt_wire_edge_cap = value; return HB_OK; }
     if (!ctx || !name) return HB_ERR_ARG;
     std::string n(name);
     if (n == "batch_bytes") ctx->opt_batch_bytes = std::max<long long>(value, 1 << 20);
@@ -417,6 +438,8 @@ int hb_set_topology(hb_ctx* ctx, const hb_topology* t) {
     CK(cudaSetDevice(ctx->device));
     free_list(ctx->topo_allocs);
     ctx->ions = IonTable{nullptr, nullptr, 0};
+    ctx->wire.on = false;
+    ctx->wire.d_ent_node = nullptr;
     ctx->have_topo = false;       // (run allocations are kept: hb_begin compares everything that sizes them)
     int ns = t->n_systems;
     ctx->h_sys_atom_off.assign(t->sys_atom_off, t->sys_atom_off + ns + 1);
@@ -558,6 +581,34 @@ int hb_set_ions(hb_ctx* ctx, const int32_t* ion_atom, const int32_t* ion_group, 
     return HB_OK;
 }
 
+int hb_set_wires(hb_ctx* ctx, const int32_t* ent_node, int32_t n_ent, int32_t n_res, int32_t max_water, int32_t allow_direct_bonds) {
+    if (!ctx) return HB_ERR_ARG;
+    if (!ctx->have_topo) return fail(ctx, HB_ERR_STATE, "hb_set_wires before hb_set_topology");
+    if (ctx->running) return fail(ctx, HB_ERR_STATE, "hb_set_wires during a run");
+    if (!ent_node) { ctx->wire.on = false; return HB_OK; }
+    if (n_ent != ctx->n_ent) return fail(ctx, HB_ERR_ARG, "hb_set_wires: size mismatch");
+    if (ctx->tp.n_systems != 1) return fail(ctx, HB_ERR_ARG, "hb_set_wires: trajectories of one system only");
+    if (n_res < 1 || max_water < 0 || max_water > 127) return fail(ctx, HB_ERR_ARG, "hb_set_wires: n_res >= 1 and 0 <= max_water <= 127");
+    int n_wat_nodes = 1;
+    for (int i = 0; i < n_ent; ++i) {
+        if (ent_node[i] < 0 || ent_node[i] - n_res >= n_ent) return fail(ctx, HB_ERR_ARG, "hb_set_wires: node out of range");
+        n_wat_nodes = std::max(n_wat_nodes, ent_node[i] - n_res + 1);
+    }
+    if (n_wat_nodes != ctx->wire.n_wat_nodes || n_res != ctx->wire.n_res) {   // the BFS scratch is sized by both
+        free_list(ctx->wire.allocs);
+        ctx->wire.d_edges = nullptr;
+    }
+    ctx->wire.n_wat_nodes = n_wat_nodes;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = upload(ctx, ent_node, (size_t)n_ent, &ctx->wire.d_ent_node, ctx->topo_allocs))) return rc;
+    ctx->wire.n_res = n_res;
+    ctx->wire.max_water = max_water;
+    ctx->wire.allow_direct = allow_direct_bonds != 0;
+    ctx->wire.on = true;
+    return HB_OK;
+}
+
 int hb_set_entry_groups(hb_ctx* ctx, const int32_t* g, int32_t n) {
     if (!ctx || !g) return HB_ERR_ARG;
     if (!ctx->have_topo || n != ctx->n_ent) return fail(ctx, HB_ERR_ARG, "hb_set_entry_groups: size mismatch");
@@ -595,9 +646,7 @@ int hb_set_params(hb_ctx* ctx, const hb_params* p) {
     r.check_angle = p->check_angle;
     r.excl_bb = p->exclude_backbone_backbone;
     r.method = p->method;
-    // a point paired with itself: with the angle criterion ANG(P, h, P) is 180 degrees (cos_arg = -1) and fails
-    // unless the threshold admits -1; without it both entries share one residue and are skipped (hbond.py:125-127)
-    r.self_pairs = (p->check_angle && !(p->cos_threshold > -1.0f)) ? 1 : 0;
+    r.self_pairs = 0;          // decided in hb_begin
     ctx->have_params = true;
     return HB_OK;
 }
@@ -684,6 +733,17 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     drain_events(ctx);
     tr.mark("sync");
     int wpr = (int)((n_frames_total + 31) / 32);
+    if (ctx->wire.on) {        // one byte per frame, then the two "first direct bond" words (hb_wires.cuh)
+        if (ctx->prm.structure_batch || ctx->rp.method != HB_METHOD_WATER_AROUND)
+            return fail(ctx, HB_ERR_ARG, "water wires: HB_METHOD_WATER_AROUND on a trajectory");
+        ctx->wire.nb4 = (int)((((n_frames_total + 3) / 4) + 1) & ~1ll);
+        wpr = ctx->wire.nb4 + 2;
+    }
+    // a point paired with itself: with the angle criterion ANG(P, h, P) is 180 degrees (cos_arg = -1) and fails
+    // unless the threshold admits -1; without it both entries share one residue and are skipped (hbond.py:125-127),
+    // except for wires, which have no same-residue rule
+    ctx->rp.self_pairs = ctx->wire.on ? ((!ctx->prm.check_angle || !(ctx->prm.cos_threshold > -1.0f)) ? 1 : 0)
+                                      : ((ctx->prm.check_angle && !(ctx->prm.cos_threshold > -1.0f)) ? 1 : 0);
     long long want = ctx->opt_table_capacity;
     if (!want) {   // a few slots per selection point (+ as many local waters); the table doubles on demand
         want = 4 * (ctx->n_sel_total + (ctx->rp.method == HB_METHOD_WATER_AROUND ? std::min(ctx->n_sel_total, ctx->n_wat_total) : 0));
@@ -706,7 +766,7 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     plan_fused(ctx);
     tr.mark("plan");
     // allocations of the previous run are reused when nothing that sizes them changed
-    long long sig[8] = {wpr, ctx->max_sel, ctx->max_wat, ctx->max_atoms, fb, cc, ctx->prm.structure_batch, hb};
+    long long sig[8] = {wpr, ctx->max_sel, ctx->max_wat, ctx->max_atoms, fb, cc, ctx->prm.structure_batch + 2 * (ctx->wire.on ? ctx->wire.n_res + 1 : 0), hb};
     bool reuse = ctx->bt.keys && ctx->table_cap >= cap && memcmp(sig, ctx->alloc_sig, sizeof(sig)) == 0;
     if (!reuse) free_run(ctx);
     ctx->tm = hb_timers{};
@@ -840,11 +900,11 @@ static int run_general_t(hb_ctx* ctx, BatchView bv) {
             PairBuf pb = ctx->pairbuf;
             pb.overflow = ctx->bt.n_keys + 3;
             CK(cudaMemsetAsync(pb.count, 0, 8, st));
-            { KTimer t(ctx, KC_PAIRS); k_collect_pairs<PBC><<<gp, 128, 0, st>>>(bv, tp, rp, ctx->bt, pb); }
-            { KTimer t(ctx, KC_PAIRS); k_expand_pairs<PBC><<<148 * 8, 128, 0, st>>>(bv, tp, rp, ctx->bt, pb); }
+            { KTimer t(ctx, KC_PAIRS); k_collect_pairs<PBC><<<gp, 128, 0, st>>>(bv, tp, rp, ctx->bt_run, pb); }
+            { KTimer t(ctx, KC_PAIRS); k_expand_pairs<PBC><<<148 * 8, 128, 0, st>>>(bv, tp, rp, ctx->bt_run, pb); }
         } else {
             KTimer t(ctx, KC_PAIRS);
-            k_pairs<PBC><<<gp, 128, 0, st>>>(bv, tp, rp, ctx->bt);
+            k_pairs<PBC><<<gp, 128, 0, st>>>(bv, tp, rp, ctx->bt_run);
         }
     }
     CK(cudaGetLastError());
@@ -857,8 +917,8 @@ static int run_general(hb_ctx* ctx, const BatchView& bv) {
 
 // launch the kernels for one batch resident at d_xyz: one fused launch, or the general pipeline over
 // sub-batches of at most `batch_frames` frames (the capacity of its scratch)
-static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, long long atoms_per_frame,
-                     size_t xyz_bytes, const float* d_box, bool allow_fused = true) {
+static int run_search(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, long long atoms_per_frame,
+                      const float* buf0, size_t buf_bytes, const float* d_box, bool allow_fused) {
     BatchView bv = ctx->bv;
     bv.xyz = d_xyz;
     bv.box = d_box;
@@ -867,16 +927,14 @@ static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, 
     bv.atoms_per_frame = atoms_per_frame;
     bv.atom_base = bv.structure_batch ? ctx->h_sys_atom_off[frame0] : 0;
     cudaStream_t st = ctx->s_compute;
-    cudaEvent_t t0 = get_event(ctx), t1 = get_event(ctx);
-    cudaEventRecord(t0, st);
     if (ctx->fused_active && allow_fused) {
         FusedCfg fc = ctx->fc;
-        fc.buf_begin = (unsigned long long)(uintptr_t)d_xyz;
-        fc.buf_end = fc.buf_begin + xyz_bytes;
+        fc.buf_begin = (unsigned long long)(uintptr_t)buf0;
+        fc.buf_end = fc.buf_begin + buf_bytes;
         {
             KTimer t(ctx, KC_FUSED);
-            if (ctx->rp.pbc != HB_PBC_NONE) k_frame_fused<true><<<nf, FUSED_THREADS, fc.smem_bytes, st>>>(bv, ctx->tp, ctx->rp, ctx->bt, fc);
-            else k_frame_fused<false><<<nf, FUSED_THREADS, fc.smem_bytes, st>>>(bv, ctx->tp, ctx->rp, ctx->bt, fc);
+            if (ctx->rp.pbc != HB_PBC_NONE) k_frame_fused<true><<<nf, FUSED_THREADS, fc.smem_bytes, st>>>(bv, ctx->tp, ctx->rp, ctx->bt_run, fc);
+            else k_frame_fused<false><<<nf, FUSED_THREADS, fc.smem_bytes, st>>>(bv, ctx->tp, ctx->rp, ctx->bt_run, fc);
         }
         CK(cudaGetLastError());
         ctx->tm.fused_frames += nf;
@@ -887,8 +945,8 @@ static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, 
         if (ctx->ions.n > 0 && pts > 0) {
             dim3 grid((unsigned)((pts + 255) / 256), (unsigned)nf);
             KTimer t(ctx, KC_PAIRS);
-            if (ctx->rp.pbc != HB_PBC_NONE) k_ion_contacts<true><<<grid, 256, 0, st>>>(bv, ctx->tp, ctx->rp, ctx->bt, ctx->ions, ctx->ion_include_water);
-            else k_ion_contacts<false><<<grid, 256, 0, st>>>(bv, ctx->tp, ctx->rp, ctx->bt, ctx->ions, ctx->ion_include_water);
+            if (ctx->rp.pbc != HB_PBC_NONE) k_ion_contacts<true><<<grid, 256, 0, st>>>(bv, ctx->tp, ctx->rp, ctx->bt_run, ctx->ions, ctx->ion_include_water);
+            else k_ion_contacts<false><<<grid, 256, 0, st>>>(bv, ctx->tp, ctx->rp, ctx->bt_run, ctx->ions, ctx->ion_include_water);
             CK(cudaGetLastError());
         }
     } else {
@@ -907,6 +965,90 @@ static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, 
             if ((rc = run_general(ctx, bv))) return rc;
         }
     }
+    return HB_OK;
+}
+
+// edge lists and the per-CTA scratch of k_wire_bfs (allocated the first time a wire run launches; the edge lists are
+// re-allocated with twice the capacity after a wire overflow)
+static int ensure_wire_buffers(hb_ctx* ctx) {
+    hb_ctx::Wire& w = ctx->wire;
+    if (w.d_edges) return HB_OK;
+    free_list(w.allocs);
+    auto dalloc = [&](void** p, size_t bytes) -> int {
+        CK(cudaMalloc(p, std::max<size_t>(bytes, 16)));
+        w.allocs.push_back(*p);
+        return HB_OK;
+    };
+    if (!w.edge_cap) {
+        long long guess = ctx->opt_wire_edge_cap ? ctx->opt_wire_edge_cap
+                                                 : 4ll * ctx->max_sel + std::min<long long>(4ll * ctx->max_wat, 16384);
+        w.edge_cap = std::max<long long>(guess, 256);
+    }
+    long long fr = (long long)((512ll << 20) / (w.edge_cap * 8));
+    w.frames = (int)std::min<long long>(std::max<long long>(fr, 1), 1024);
+    const int n_wat = w.n_wat_nodes, n_res = w.n_res;
+    const int cap_words = std::min((n_res + 31) / 32, WIRE_CHUNK_WORDS);
+    const size_t per_cta = (size_t)n_wat * 8 + (size_t)n_res * 8 + 3 * (size_t)n_wat * cap_words * 4 + 2 * (size_t)n_res * cap_words * 4;
+    long long ncta = std::min<long long>(2ll * ctx->prop.multiProcessorCount, (long long)((2ll << 30) / std::max<size_t>(per_cta, 1)));
+    w.n_cta = (int)std::max<long long>(1, std::min<long long>(ncta, w.frames));
+    int rc;
+    WireCfg c{};
+    if ((rc = dalloc((void**)&w.d_edges, (size_t)w.frames * w.edge_cap * 8))) return rc;
+    if ((rc = dalloc((void**)&w.d_cnt, (size_t)w.frames * 4))) return rc;
+    if ((rc = dalloc((void**)&c.wl_of, (size_t)w.n_cta * n_wat * 4))) return rc;
+    if ((rc = dalloc((void**)&c.lw_list, (size_t)w.n_cta * n_wat * 4))) return rc;
+    if ((rc = dalloc((void**)&c.ar_of, (size_t)w.n_cta * n_res * 4))) return rc;
+    if ((rc = dalloc((void**)&c.ar_list, (size_t)w.n_cta * n_res * 4))) return rc;
+    if ((rc = dalloc((void**)&c.wbits, (size_t)w.n_cta * 3 * n_wat * cap_words * 4))) return rc;
+    if ((rc = dalloc((void**)&c.tbits, (size_t)w.n_cta * 2 * n_res * cap_words * 4))) return rc;
+    CK(cudaMemsetAsync(c.wl_of, 0xFF, (size_t)w.n_cta * n_wat * 4, ctx->s_compute));
+    CK(cudaMemsetAsync(c.ar_of, 0xFF, (size_t)w.n_cta * n_res * 4, ctx->s_compute));
+    c.ent_node = w.d_ent_node;
+    c.n_res = n_res;
+    c.n_wat = n_wat;
+    c.cap_words = cap_words;
+    w.cfg = c;
+    return HB_OK;
+}
+
+// launch the kernels for one batch resident at d_xyz (wire mode: rounds of search + breadth-first search over as
+// many frames as the edge lists hold)
+static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, long long atoms_per_frame,
+                     size_t xyz_bytes, const float* d_box, bool allow_fused = true) {
+    cudaStream_t st = ctx->s_compute;
+    cudaEvent_t t0 = get_event(ctx), t1 = get_event(ctx);
+    cudaEventRecord(t0, st);
+    int rc;
+    ctx->bt_run = ctx->bt;
+    if (!ctx->wire.on) {
+        if ((rc = run_search(ctx, d_xyz, frame0, nf, atoms_per_frame, d_xyz, xyz_bytes, d_box, allow_fused))) return rc;
+    } else {
+        if ((rc = ensure_wire_buffers(ctx))) return rc;
+        hb_ctx::Wire& w = ctx->wire;
+        WireCfg c = w.cfg;
+        c.ent_node = w.d_ent_node;
+        c.max_water = w.max_water;
+        c.allow_direct = w.allow_direct;
+        c.nb4 = w.nb4;
+        c.status = ctx->bt.n_keys;
+        for (int done = 0; done < nf; done += w.frames) {
+            const int n = std::min(nf - done, w.frames);
+            CK(cudaMemsetAsync(w.d_cnt, 0, (size_t)n * 4, st));
+            ctx->bt_run = ctx->bt;
+            ctx->bt_run.edges = w.d_edges;
+            ctx->bt_run.edge_cnt = w.d_cnt;
+            ctx->bt_run.edge_cap = (int)w.edge_cap;
+            ctx->bt_run.edge_frame0 = frame0 + done;
+            ctx->bt_run.wire_overflow = ctx->bt.n_keys + 6;
+            if ((rc = run_search(ctx, d_xyz + (size_t)done * atoms_per_frame * 3, frame0 + done, n, atoms_per_frame, d_xyz,
+                                 xyz_bytes, d_box ? d_box + (size_t)done * 9 : nullptr, allow_fused))) return rc;
+            {
+                KTimer t(ctx, KC_WIRES);
+                k_wire_bfs<<<std::min(n, w.n_cta), WIRE_THREADS, 0, st>>>(ctx->bt, c, w.d_edges, w.d_cnt, (int)w.edge_cap, frame0 + done, n);
+            }
+            CK(cudaGetLastError());
+        }
+    }
     cudaEventRecord(t1, st);
     ctx->pending.push_back({t0, t1, -1});
     ctx->tm.frames += nf;
@@ -919,13 +1061,13 @@ static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, 
 // the table is grown and every in-flight batch is re-run (idempotent: bits are OR-ed, keys deduplicate).
 static int full_verify(hb_ctx* ctx) {
     for (int attempt = 0; attempt < 28; ++attempt) {
-        int st[6];        // n_keys, overflow, fused_overflow, pad, n_hits (64 bit): one stream-ordered read back
+        int st[8];        // n_keys, overflow, fused_overflow, pair_overflow, n_hits (64 bit), wire_overflow, pad
         CK(cudaMemcpyAsync(ctx->h_verify, ctx->bt.n_keys, sizeof(st), cudaMemcpyDeviceToHost, ctx->s_compute));
         CK(cudaStreamSynchronize(ctx->s_compute));
         memcpy(st, ctx->h_verify, sizeof(st));
-        memcpy(ctx->last_status, st, sizeof(st));
-        bool overflow = st[1] != 0, fused_overflow = st[2] != 0, pair_overflow = st[3] != 0;
-        if (!overflow && !fused_overflow && !pair_overflow && (long long)st[0] * 2 <= ctx->table_cap) {
+        memcpy(ctx->last_status, st, 6 * sizeof(int));
+        bool overflow = st[1] != 0, fused_overflow = st[2] != 0, pair_overflow = st[3] != 0, wire_overflow = st[6] != 0;
+        if (!overflow && !fused_overflow && !pair_overflow && !wire_overflow && (long long)st[0] * 2 <= ctx->table_cap) {
             for (auto& sl : ctx->slots) sl.busy = false;
             return HB_OK;
         }
@@ -944,7 +1086,14 @@ static int full_verify(hb_ctx* ctx) {
             if (ctx->batch_frames > 1) ctx->batch_frames = std::max(1, ctx->batch_frames / 2);
             else ctx->use_pairbuf = false;
         }
-        if (overflow || fused_overflow || pair_overflow) {
+        if (wire_overflow) {       // some frame has more H-bond pairs than its edge list holds: double the lists
+            CK(cudaStreamSynchronize(ctx->s_compute));
+            free_list(ctx->wire.allocs);
+            ctx->wire.d_edges = nullptr;
+            ctx->wire.edge_cap *= 2;
+            CK(cudaMemsetAsync(ctx->bt.n_keys + 6, 0, sizeof(int), ctx->s_compute));
+        }
+        if (overflow || fused_overflow || pair_overflow || wire_overflow) {
             CK(cudaMemsetAsync(ctx->bt.overflow, 0, 3 * sizeof(int), ctx->s_compute));
             for (auto& sl : ctx->slots)
                 if (sl.busy) {
@@ -964,7 +1113,7 @@ static int acquire_slot(hb_ctx* ctx, int k) {
     hb_ctx::Slot& sl = ctx->slots[k];
     if (!sl.busy) return HB_OK;
     CK(cudaEventSynchronize(ctx->ev_done[k]));
-    int nkeys = ctx->h_status[4 * k], overflow = ctx->h_status[4 * k + 1] | ctx->h_status[4 * k + 2] | ctx->h_status[4 * k + 3];
+    int nkeys = ctx->h_status[8 * k], overflow = ctx->h_status[8 * k + 1] | ctx->h_status[8 * k + 2] | ctx->h_status[8 * k + 3] | ctx->h_status[8 * k + 6];
     if (overflow || (long long)nkeys * 2 > ctx->table_cap) return full_verify(ctx);
     sl.busy = false;
     return HB_OK;
@@ -974,7 +1123,7 @@ static int launch_in_slot(hb_ctx* ctx, int k, const float* d_xyz, long long f0, 
                           const float* d_box) {
     int rc = run_batch(ctx, d_xyz, f0, nf, apf, bytes, d_box);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(ctx->h_status + 4 * k, ctx->bt.n_keys, 4 * sizeof(int), cudaMemcpyDeviceToHost, ctx->s_compute));
+    CK(cudaMemcpyAsync(ctx->h_status + 8 * k, ctx->bt.n_keys, 8 * sizeof(int), cudaMemcpyDeviceToHost, ctx->s_compute));
     CK(cudaEventRecord(ctx->ev_done[k], ctx->s_compute));
     ctx->slots[k] = hb_ctx::Slot{true, d_xyz, f0, nf, apf, bytes, d_box, ctx->last_batch_fused};
     return HB_OK;
@@ -1350,7 +1499,7 @@ static int queue_finalize(hb_ctx* ctx, bool speculative, int* n_known) {
     ctx->fin_sorted_k = k0;
     ctx->fin_n_max = n_max;
     if (speculative) {   // the read back that verifies the run, and the end-of-run time stamp
-        CK(cudaMemcpyAsync(ctx->h_verify, ctx->bt.n_keys, 6 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->h_verify, ctx->bt.n_keys, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaEventRecord(ctx->ev_run1, st));
     }
     ctx->fin_queued = true;
@@ -1406,7 +1555,8 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
         CK(cudaStreamSynchronize(st));
         memcpy(ctx->last_status, ctx->h_verify, 6 * sizeof(int));
         n = ctx->last_status[0];
-        const bool bad = ctx->last_status[1] || ctx->last_status[2] || ctx->last_status[3] || (long long)n * 2 > ctx->table_cap;
+        const bool bad = ctx->last_status[1] || ctx->last_status[2] || ctx->last_status[3] || ctx->h_verify[6] ||
+                         (long long)n * 2 > ctx->table_cap;
         if (!bad) {
             for (auto& sl : ctx->slots) sl.busy = false;
             drain_events(ctx);

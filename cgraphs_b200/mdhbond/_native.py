@@ -84,6 +84,7 @@ SYMBOLS = [
     ("hb_set_entry_groups", C.c_int, [_P, C.POINTER(C.c_int32), C.c_int32]),
     ("hb_set_params", C.c_int, [_P, C.POINTER(HbParams)]),
     ("hb_set_ions", C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int32]),
+    ("hb_set_wires", C.c_int, [_P, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     ("hb_set_option", C.c_int, [_P, C.c_char_p, C.c_int64]),
     ("hb_begin", C.c_int, [_P, C.c_int64]),
     ("hb_submit_frames", C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
@@ -193,6 +194,15 @@ class Context:
         a, g = _i32(ion_atom), _i32(ion_group)
         self._ck(self.lib.hb_set_ions(self.h, _ptr(a, C.c_int32), _ptr(g, C.c_int32), len(a), int(bool(include_water))),
                  "hb_set_ions")
+
+    def set_wires(self, ent_node, n_res, max_water, allow_direct_bonds=True):
+        """Water-wire mode (hb_set_wires); ent_node=None switches it off."""
+        if ent_node is None:
+            self._ck(self.lib.hb_set_wires(self.h, None, 0, 0, 0, 0), "hb_set_wires")
+            return
+        g = _i32(ent_node)
+        self._ck(self.lib.hb_set_wires(self.h, _ptr(g, C.c_int32), len(g), int(n_res), int(max_water),
+                                       int(bool(allow_direct_bonds))), "hb_set_wires")
 
     def set_entry_groups(self, groups):
         g = _i32(groups)

@@ -283,10 +283,14 @@ class HbondAnalysis(object):
                 raise IndexError('water hydrogens do not pair up as two per water; the reference indexes past '
                                  'heavy2hydrogen here (network.py:86, helpfunctions.py:144)')
 
-    def _run(self, method, around_radius, exclude_backbone_backbone, include_water=True):
+    def _run(self, method, around_radius, exclude_backbone_backbone, include_water=True, wires=None):
+        """wires = (ent_node, n_res, max_water, allow_direct_bonds): water-wire mode of the water_around search
+        (hb_set_wires); returns the raw (keys, rows) of that run instead of a result dict."""
         top = self._topology
         self._check_hydrogen_tables(method)
         ctx = self._context()
+        if wires is not None and self._shard is not None and self._shard[1] > 1:
+            raise NotImplementedError('water wires are not sharded over GPUs yet')
         cache = self.__dict__.setdefault("_packed", {})
         if method not in cache:          # packed device tables per method (the key id strings differ)
             if method == "ions":         # hbond.py:61-66: _all_ids for the entries, water / ion ids by `residuewise`
@@ -301,6 +305,12 @@ class HbondAnalysis(object):
             ctx._uploaded = tables
         if method == "ions":
             ctx.set_ions(self._ions_atoms, cache[method][2], include_water)
+        if wires is not None:
+            ctx.set_wires(*wires)
+            ctx._wires_on = True
+        elif getattr(ctx, "_wires_on", False):
+            ctx.set_wires(None, 0, 0)
+            ctx._wires_on = False
         cthr = self._cos_threshold_override
         if cthr is None:
             cthr = _cos_threshold(float(self.cut_angle)) if self.check_angle else -1.0
@@ -346,10 +356,15 @@ class HbondAnalysis(object):
                     done += len(xyz)
             keys, words = ctx.results()
             self.last_run_stats = ctx.timers()
+            if wires is not None:
+                self._rows = None
+                return keys, words
             if self._shard is None:      # the packed rows stay on the device for the occupancy post-processing below
                 self._rows = dict(run_id=ctx._run_id, wpr=words.shape[1], n=len(keys),
                                   row_of={group_names[int(k >> _np.uint64(32))] + ':' + group_names[int(k & _np.uint64(0xFFFFFFFF))]: i
                                           for i, k in enumerate(keys)})
+        if wires is not None:
+            return keys, words
         if self._shard is not None and self._shard[1] > 1:
             from .sharding import merge_shards
             keys, words = merge_shards(keys, words, lo, hi, self.nb_frames, self._shard, ctx)

@@ -1,0 +1,111 @@
+"""``WireAnalysis`` - water wires on the GPU (SURVEY 8f "next" #1; reference ``cgraphs/mdhbond/waterwire.py``).
+
+cgraphs' trajectory workflow (``cgraphs/proteingraphanalyser.py:472-485``) builds one ``WireAnalysis`` per
+trajectory, calls ``set_water_wires(max_water=...)``, ``compute_average_water_per_wire()`` and reads
+``filtered_graph``. This class mirrors that surface: same constructor keywords as the reference
+(``waterwire.py:42-45``), ``set_water_wires`` (``waterwire.py:191-317``) and the results it publishes -
+``initial_results`` / ``filtered_results`` (bool per frame), ``wire_lengths`` (float per frame: inf = no wire,
+0 = direct H-bond, k = waters in the shortest wire) and the graphs.
+
+The neighbour stage (``waterwire.py:200-248``) is the library's water-around search with the radius
+``(max_water + 1) * distance / 2``; the per-frame breadth-first search (``waterwire.py:250-309``) runs in
+``k_wire_bfs`` (``csrc/hb_wires.cuh``). No part of it runs on the CPU.
+
+Not covered (out of scope): ``water_in_convex_hull`` (scipy Delaunay), the explicit wire paths
+(``hashs`` / ``hash_table``: Python ``hash(str(path))`` values, salted per process), ``residuewise=False`` and the
+plotting methods.
+"""
+from __future__ import annotations
+
+import numpy as _np
+
+from .hbond import HbondAnalysis
+
+
+class WireAnalysis(HbondAnalysis):
+
+    def __init__(self, selection=None, structure=None, trajectories=None, distance=3.5, cut_angle=60.,
+                 start=None, stop=None, step=1, additional_donors=[], additional_acceptors=[], exclude_donors=[],
+                 exclude_acceptors=[], ions=[], check_angle=True, residuewise=True,
+                 add_donors_without_hydrogen=False, restore_filename=None, **kw):
+        super().__init__(selection=selection, structure=structure, trajectories=trajectories, distance=distance,
+                         cut_angle=cut_angle, start=start, stop=stop, step=step, additional_donors=additional_donors,
+                         additional_acceptors=additional_acceptors, exclude_donors=exclude_donors,
+                         exclude_acceptors=exclude_acceptors, ions=ions, check_angle=check_angle,
+                         residuewise=residuewise, add_donors_without_hydrogen=add_donors_without_hydrogen,
+                         restore_filename=restore_filename, **kw)
+        self.hashs = {}
+        self.hash_table = {}
+        self.wire_lengths = {}
+        if restore_filename is not None:
+            return
+        top = self._topology
+        # waterwire.py:60-65: `da_trans` - all entries with one residue-level id are the first of them
+        res_ids = ['-'.join(s.split('-')[:3]) for s in top.all_ids_atomwise[:top.first_water]]
+        first = {}
+        node_first_entry = []
+        ent_node = _np.empty(top.first_water + top.nW, dtype=_np.int32)
+        for e, rid in enumerate(res_ids):
+            n = first.get(rid)
+            if n is None:
+                n = first[rid] = len(node_first_entry)
+                node_first_entry.append(e)
+            ent_node[e] = n
+        self._n_wire_nodes = len(node_first_entry)
+        ent_node[top.first_water:] = self._n_wire_nodes + _np.arange(top.nW, dtype=_np.int32)
+        self._wire_ent_node = ent_node
+        self._wire_node_entry = _np.asarray(node_first_entry, dtype=_np.int64)
+        self.da_trans = self._wire_node_entry[ent_node[:top.first_water]]
+
+    def set_water_wires(self, max_water=5, allow_direct_bonds=True, water_in_convex_hull=False):
+        """waterwire.py:191-317."""
+        if water_in_convex_hull:
+            raise NotImplementedError('water_in_convex_hull (scipy Delaunay, waterwire.py:218-221) is not supported')
+        if not self.residuewise:
+            raise NotImplementedError('water wires: residuewise=False is not supported')
+        max_water = int(max_water)
+        self._allow_direct_bonds = allow_direct_bonds
+        around = float(max_water + 1) * self.distance / 2.
+        wires = (self._wire_ent_node, self._n_wire_nodes, max_water, bool(allow_direct_bonds))
+        keys, words = self._run("water_around", around, False, wires=wires)
+        n = self.nb_frames
+        results = {}
+        if len(keys):
+            nb4 = words.shape[1] - 2
+            cols = words[:, :nb4].view(_np.uint8)[:, :n]
+            tail = _np.ascontiguousarray(words[:, nb4:nb4 + 2]).view(_np.uint64)[:, 0]
+            wire_k = cols & 0x7f
+            direct = (cols & 0x80) != 0
+            lengths = _np.full(cols.shape, _np.inf)
+            has = wire_k > 0
+            lengths[has] = wire_k[has]
+            lengths[direct] = 0
+            # key orientation = first discovery (waterwire.py:277-279, 299-301): a wire names the residue with the
+            # smaller node first; a direct bond names the donor's residue first
+            has_wire = has.any(axis=1)
+            first_wire = _np.where(has_wire, has.argmax(axis=1), n)
+            has_direct = tail != 0
+            packed = ~tail
+            first_direct = _np.where(has_direct, (packed >> _np.uint64(32)).astype(_np.int64), n)
+            donor_hi = (packed & _np.uint64(1)).astype(bool) & has_direct
+            by_wire = has_wire & (first_wire <= first_direct)
+            lo = self._wire_node_entry[(keys >> _np.uint64(32)).astype(_np.int64)]
+            hi = self._wire_node_entry[(keys & _np.uint64(0xFFFFFFFF)).astype(_np.int64)]
+            swap = ~by_wire & donor_hi
+            a = _np.where(swap, hi, lo)
+            b = _np.where(swap, lo, hi)
+            ids = self._all_ids
+            order = _np.lexsort((_np.arange(len(keys)), _np.minimum(first_wire, first_direct)))
+            for i in order:
+                results[ids[a[i]] + ':' + ids[b[i]]] = lengths[i]
+        self._set_results({key: results[key] != _np.inf for key in results})
+        self.wire_lengths = results
+        self.hashs = {}
+        self.hash_table = {}
+        self.occupancy_dict = {}
+        self.first_frame_dict = {}
+
+    def compute_average_water_per_wire(self, use_filtered=True):
+        """waterwire.py:359-362."""
+        results = self.filtered_results if use_filtered else self.initial_results
+        return {key: self.wire_lengths[key][self.wire_lengths[key] < _np.inf].mean() for key in results}

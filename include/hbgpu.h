@@ -19,6 +19,9 @@
  *                     <- the trajectory reader's frame decode, basic.py:46-47 (DCD X / Y / Z records)
  *   hb_set_ions + HB_METHOD_ION_CONTACTS
  *                     <- set_add_ion_interactions, hbond.py:57-94 (ion group: basic.py:53-60)
+ *   hb_set_wires      <- WireAnalysis.set_water_wires, waterwire.py:191-317: the same neighbour search
+ *                        (waterwire.py:200-248) feeds a per-frame breadth-first search over the water
+ *                        network (waterwire.py:250-309); results are wire lengths per residue pair and frame
  *   hb_get_counts / hb_joint_occupancy / hb_get_frame_column
  *                     <- filter_occupancy, compute_joint_occupancy, _compute_graph_in_frame,
  *                        network.py:99-107, 369-376, 1186-1198 (on the packed matrix)
@@ -140,6 +143,19 @@ int hb_set_params(hb_ctx* ctx, const hb_params* params);
  * same id-string table ent_group refers to) of every ion; include_water: also pair the waters of the water group
  * with the ions (hbond.py:78-83). Call after hb_set_topology. */
 int hb_set_ions(hb_ctx* ctx, const int32_t* ion_atom, const int32_t* ion_group, int32_t n_ions, int32_t include_water);
+/* Water wires (WireAnalysis.set_water_wires, waterwire.py:191-317). ent_node[e]: graph node of entry e - for a
+ * selection entry the residue node (`da_trans`, waterwire.py:60-65: dense rank, in entry order, of the first entry
+ * with the same residue-level id; < n_res), for the entry of water w the value n_res + w. Use with
+ * HB_METHOD_WATER_AROUND, around_radius = (max_water + 1) * distance / 2, exclude_backbone_backbone = 0 on a
+ * trajectory. The run then yields one row per residue pair that is ever connected: key = (node_lo << 32) | node_hi,
+ * words_per_bond = nb4 + 2 with nb4 = (ceil(n_frames / 4) + 1) & ~1; byte f of a row (little endian inside the words)
+ * = waters of the shortest wire in frame f (1..max_water, 0 = none) | 0x80 if the residues are directly H-bonded;
+ * words nb4, nb4 + 1 = a 64-bit value v, 0 if there never is a direct bond, else ~v = (first frame with a direct
+ * bond << 32) | (its smallest acceptor entry << 1) | (1 if the donor is node_hi) - what a caller needs to orient the
+ * key string like the reference's first discovery (waterwire.py:277-279, 299-301). ent_node = NULL switches the
+ * mode off. The bit-matrix post-processing calls (hb_get_counts, ...) do not apply to such rows. */
+int hb_set_wires(hb_ctx* ctx, const int32_t* ent_node, int32_t n_ent, int32_t n_res, int32_t max_water,
+                 int32_t allow_direct_bonds);
 int hb_set_option(hb_ctx* ctx, const char* name, int64_t value);
         /* "batch_bytes": device budget per frame batch; "table_capacity": initial bond-table slots;
            "profile": 1 = time every kernel class with CUDA events; "max_batch_frames";

@@ -473,3 +473,132 @@ def run_ions(universe, selection, ions, include_water=True, box=None, **ctor):
                 row = results[key] = np.zeros(pt.nb_frames, dtype=bool)
             row[col] = True
     return results
+
+
+# ------------------------------------------------------------------------------------------------
+# WireAnalysis.set_water_wires (waterwire.py:191-317) - neighbour stage :200-248,
+# per-frame breadth-first search :250-295, direct bonds :297-309, publication :312-314.
+# ------------------------------------------------------------------------------------------------
+def wire_node_of_entry(pt):
+    """`da_trans` of waterwire.py:60-65: every selection entry is represented by the FIRST entry that carries the
+    same residue-level id (MDA_info_list without detailed_info, helpfunctions.py:107-117)."""
+    topo = pt.universe.topology
+    first = {}
+    out = np.empty(pt.first_water, dtype=np.int64)
+    for e in range(pt.first_water):
+        out[e] = first.setdefault(_id(topo, pt.entry_atom[e], False), e)
+    return out
+
+
+def wire_frame_edges(pt, pos, max_water, backend='kdtree', cos_threshold=None, box=None):
+    """Neighbour stage of one frame (waterwire.py:200-248): the three H-bond pair classes, local waters taken within
+    (max_water + 1) * distance / 2 of the selection, no backbone filter. Returns entry pairs
+    (direct [donor entry, acceptor entry], selection-water [entry, water entry], water-water)."""
+    around = float(max_water + 1) * pt.distance / 2.
+    e0, e1 = frame_pairs(pt, pos, 'water_around', around, False, backend, cos_threshold, False, box)
+    fw = pt.first_water
+    lo, hi = np.minimum(e0, e1), np.maximum(e0, e1)          # np.sort of every pair (waterwire.py:245-247)
+    da = hi < fw
+    ww = lo >= fw
+    sw = ~da & ~ww
+    return (lo[da], hi[da]), (lo[sw], hi[sw]), (lo[ww], hi[ww])
+
+
+def wires_of_frame(pt, node_of, edges, max_water, allow_direct_bonds=True):
+    """waterwire.py:250-309 for one frame. Returns (wires, directs): wires = {(source node, target node): waters in the
+    shortest wire}, source < target, in the order the reference first meets them; directs = [(donor entry,
+    acceptor entry)] in the reference's row order (acceptor-major, waterwire.py:230,245)."""
+    (d_lo, d_hi), (s_e, s_w), (w_a, w_b) = edges
+    adj = {}
+    for a, b in zip(w_a.tolist(), w_b.tolist()):
+        adj.setdefault(a, []).append(b)
+        adj.setdefault(b, []).append(a)
+    s_n = node_of[s_e]
+    by_source = {}
+    for n, w in zip(s_n.tolist(), s_w.tolist()):
+        by_source.setdefault(n, []).append(w)
+    wires = {}
+    for source in sorted(by_source):                          # residues = unique(local_hbonds[:, 0]), ascending
+        depth = {}
+        frontier = []
+        for w in by_source[source]:
+            if w not in depth and max_water >= 1:
+                depth[w] = 1
+                frontier.append(w)
+        d = 1
+        while frontier and d < max_water:                     # single_source_shortest_path(g, source, max_water)
+            d += 1
+            nxt = []
+            for u in frontier:
+                for v in adj.get(u, ()):
+                    if v not in depth:
+                        depth[v] = d
+                        nxt.append(v)
+            frontier = nxt
+        for target, w in zip(s_n.tolist(), s_w.tolist()):     # rows of local_hbonds whose water was reached
+            if target <= source or w not in depth:            # already_checked holds every smaller source
+                continue
+            k = depth[w]                                      # waters in this wire = len(wire) - 2
+            key = (source, target)
+            if key not in wires or k < wires[key]:
+                wires[key] = k
+    directs = []
+    if allow_direct_bonds:
+        order = np.argsort(d_hi, kind='stable')               # rows come acceptor by acceptor
+        directs = list(zip(d_lo[order].tolist(), d_hi[order].tolist()))
+    return wires, directs
+
+
+class WireResult:
+    def __init__(self, pt, wire_lengths):
+        self.topology = pt
+        self.wire_lengths = wire_lengths
+        self.initial_results = {k: v != np.inf for k, v in wire_lengths.items()}
+        self.filtered_results = self.initial_results
+        self.nb_frames = pt.nb_frames
+        self.initial_graph = dict2graph(self.initial_results, pt.residuewise)
+        self.filtered_graph = self.initial_graph
+
+    def compute_average_water_per_wire(self):                 # waterwire.py:359-362
+        return {k: v[v < np.inf].mean() for k, v in self.wire_lengths.items()}
+
+
+def run_wires(universe, selection, max_water=5, allow_direct_bonds=True, backend='kdtree', cos_threshold=None,
+              box=None, **ctor):
+    """WireAnalysis(...).set_water_wires(max_water, allow_direct_bonds) without the convex-hull option.
+    Returns a WireResult: `wire_lengths` = {key: float64[nb_frames]} (inf = no wire, 0 = direct H-bond, k = k waters)
+    with the reference's key orientation (first discovery decides, waterwire.py:277-279, 299-301) and key order.
+    The wire paths themselves (`hashs`, `hash_table`: Python `hash(str(path))`, salted per process) are not restated.
+
+    Divergence: frames in which one of the three pair classes is empty make the reference raise
+    (waterwire.py:228,231,248); here they are frames that contribute nothing from that class."""
+    pt = PortTopology(universe, selection, **ctor)
+    node_of = wire_node_of_entry(pt)
+    ids = pt.all_ids
+    results = {}
+    frames = universe.trajectory.frames
+    for col, f in enumerate(pt.frame_indices):
+        pos = np.asarray(frames.frame(f), dtype=np.float32)
+        bk = None if box is None else (np.asarray(box)[col] if np.asarray(box).ndim == 3 else np.asarray(box))
+        edges = wire_frame_edges(pt, pos, max_water, backend, cos_threshold, bk)
+        wires, directs = wires_of_frame(pt, node_of, edges, max_water, allow_direct_bonds)
+        for (s, t), k in wires.items():
+            key = ids[s] + ':' + ids[t]
+            rev = ids[t] + ':' + ids[s]
+            if rev in results:
+                key = rev
+            row = results.get(key)
+            if row is None:
+                row = results[key] = np.full(pt.nb_frames, np.inf)
+            if k < row[col]:
+                row[col] = k
+        for a, b in directs:
+            key = ids[a] + ':' + ids[b]
+            rev = ids[b] + ':' + ids[a]
+            if rev in results:
+                key = rev
+            row = results.get(key)
+            if row is None:
+                row = results[key] = np.full(pt.nb_frames, np.inf)
+            row[col] = 0
+    return WireResult(pt, results)

@@ -93,3 +93,31 @@ def port_with_ions(u, selection, method, ions, around=3.5, **kw):
     res = dict(hbond_port.run(u, selection, method, around=around, **kw).initial_results)
     res.update(hbond_port.run_ions(u, selection, ions, include_water=(method == "water_around"), **kw))
     return res
+
+
+def load_golden_wires(name="wires_traj"):
+    """(Universe, runs) of a golden water-wire fixture (tests/golden/make_golden_wires.py)."""
+    from cgraphs_b200.universe import Topology, Universe
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    topo = Topology([str(s) for s in z["names"]], [str(s) for s in z["resnames"]], z["resids"],
+                    [str(s) for s in z["segids"]])
+    with open(os.path.join(GOLDEN_DIR, name + ".json")) as f:
+        runs = json.load(f)["runs"]
+    return Universe(topo, z["xyz"]), runs
+
+
+def wire_lists(wire_lengths):
+    """key -> list over frames, -1 for inf (the golden form)."""
+    return {k: [(-1 if not np.isfinite(x) else int(x)) for x in v] for k, v in wire_lengths.items()}
+
+
+def assert_same_wires(got, want, what=""):
+    """Both: key -> per-frame list (-1 = none). Keys must agree in orientation."""
+    if got == want:
+        return
+    only_a = sorted(set(got) - set(want))
+    only_b = sorted(set(want) - set(got))
+    diff = sorted(k for k in set(got) & set(want) if list(got[k]) != list(want[k]))
+    detail = ["%s: got %s want %s" % (k, got[k], want[k]) for k in diff[:4]]
+    raise AssertionError("%s wires differ: %d keys only in first %s, %d only in second %s, %d with different lengths %s"
+                         % (what, len(only_a), only_a[:5], len(only_b), only_b[:5], len(diff), detail))
