@@ -15,8 +15,9 @@
 // All sources advance together: a water carries one bit per source residue (seen / frontier / next), a level is
 // one pass over the water-water edges OR-ing frontier words into the neighbours, and the pairs found at level k
 // are the new bits that reach the waters next to a target residue. Sources are taken in chunks of at most
-// 32 * WIRE_CHUNK_WORDS so that the bit sets stay small. One CTA works on one frame; its bit sets live in a
-// per-CTA scratch area in global memory (L2 resident).
+// 32 * WIRE_CHUNK_WORDS so that the bit sets stay small. One CTA (1024 threads, one per SM) works on one frame; the
+// bit sets live in its shared memory - the source chunk is narrowed until they fit - and only for frames with
+// more than ~17,000 local waters in a per-CTA scratch area in global memory.
 //
 // Results go into the bond table with byte-wide columns: row word (frame >> 2), byte (frame & 3) = k (waters of the
 // shortest wire, 1..127, 0 = none) | 0x80 if a direct bond exists; the last two words of a row hold
@@ -28,7 +29,9 @@
 namespace {
 
 #define WIRE_CHUNK_WORDS 32
-#define WIRE_THREADS 256
+#define WIRE_THREADS 1024
+#define WIRE_QUEUE 4096
+#define WIRE_SMEM_WORDS (50 * 1024)      // 200 kB of bit sets per CTA (one CTA per SM)
 
 struct WireCfg {
     const int* ent_node;     // [n_ent] residue node (< n_res) of a selection entry, n_res + water index of a water entry
@@ -36,6 +39,7 @@ struct WireCfg {
     int max_water, allow_direct;
     int nb4;                 // row words that hold the per-frame bytes (the "first direct" tail follows)
     int cap_words;           // min(ceil(n_res / 32), WIRE_CHUNK_WORDS): words per node the scratch is sized for
+    int smem_words;          // shared-memory budget of the bit sets (WIRE_SMEM_WORDS; smaller values are a test hook)
     // per-CTA scratch
     int* wl_of;              // [n_cta][n_wat]   water -> local index, -1 when idle
     int* lw_list;            // [n_cta][n_wat]
@@ -43,6 +47,7 @@ struct WireCfg {
     int* ar_list;            // [n_cta][n_res]
     unsigned* wbits;         // [n_cta][3][n_wat * cap_words]   seen / frontier / next
     unsigned* tbits;         // [n_cta][2][n_res * cap_words]   found / level accumulator
+    int2* rlist;             // [n_cta][edge_cap]               the frame's edges in local indices
     const int* status;       // status block: [2] fused_overflow, [3] pair_overflow, [6] wire_overflow
 };
 
@@ -77,21 +82,20 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
     int* lw = wc.lw_list + (size_t)blockIdx.x * wc.n_wat;
     int* ar_of = wc.ar_of + (size_t)blockIdx.x * n_res;
     int* ar = wc.ar_list + (size_t)blockIdx.x * n_res;
+    int2* R = wc.rlist + (size_t)blockIdx.x * edge_cap;
     const size_t wstride = (size_t)wc.n_wat * wc.cap_words, tstride = (size_t)n_res * wc.cap_words;
-    unsigned* seen = wc.wbits + (size_t)blockIdx.x * 3 * wstride;
-    unsigned* cur = seen + wstride;
-    unsigned* nxt = cur + wstride;
-    unsigned* found = wc.tbits + (size_t)blockIdx.x * 2 * tstride;
-    unsigned* acc = found + tstride;
-    __shared__ int s_nlw, s_nar, s_any;
+    extern __shared__ unsigned s_bits[];
+    __shared__ int s_nlw, s_nar, s_nsw, s_nww, s_any, s_nq;
+    __shared__ unsigned s_queue[WIRE_QUEUE];      // pairs found at the current level: (source node index << 16) | target index
 
     for (int b = blockIdx.x; b < n_frames; b += gridDim.x) {
         const int ne = min(edge_cnt[b], edge_cap);
         const int2* E = edges + (size_t)b * edge_cap;
         const long long frame = frame0 + b;
-        if (tid == 0) { s_nlw = 0; s_nar = 0; }
+        if (tid == 0) { s_nlw = 0; s_nar = 0; s_nsw = 0; s_nww = 0; }
         __syncthreads();
-        // local waters and active residues (those with a residue-water edge) get dense indices
+        // local waters and active residues (those with a residue-water edge) get dense indices; direct bonds
+        // (acceptor entry, donor entry) are recorded on the way
         for (int i = tid; i < ne; i += nt) {
             const int2 e = E[i];
             const int n0 = wc.ent_node[e.x], n1 = wc.ent_node[e.y];
@@ -100,6 +104,16 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
             if ((n0 >= n_res) != (n1 >= n_res)) {
                 const int r = n0 < n_res ? n0 : n1;
                 if (atomicCAS(&ar_of[r], -1, -2) == -1) ar[atomicAdd(&s_nar, 1)] = r;
+            } else if (n0 < n_res && wc.allow_direct) {
+                const int lo = min(n0, n1), hi = max(n0, n1);
+                const int h = table_slot(bt, ((unsigned long long)(unsigned)lo << 32) | (unsigned)hi);
+                if (h >= 0) {
+                    unsigned* row = bt.bits + (size_t)h * bt.wpr;
+                    atomicOr(&row[frame >> 2], 0x80u << (8 * (int)(frame & 3)));
+                    const unsigned long long packed = ((unsigned long long)frame << 32) | ((unsigned long long)(unsigned)e.x << 1) |
+                                                      (unsigned long long)(n1 == hi ? 1 : 0);
+                    atomicMax((unsigned long long*)(row + wc.nb4), ~packed);
+                }
             }
         }
         __syncthreads();
@@ -107,41 +121,54 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
         for (int i = tid; i < nlw; i += nt) wl_of[lw[i]] = i;
         for (int i = tid; i < nar; i += nt) ar_of[ar[i]] = i;
         __syncthreads();
+        // the edges in local indices: residue-water (active residue, local water) from the front of R,
+        // water-water (local water, local water) from its back
+        for (int i = tid; i < ne; i += nt) {
+            const int2 e = E[i];
+            const int n0 = wc.ent_node[e.x], n1 = wc.ent_node[e.y];
+            const bool w0 = n0 >= n_res, w1 = n1 >= n_res;
+            if (w0 && w1) R[edge_cap - 1 - atomicAdd(&s_nww, 1)] = make_int2(wl_of[n0 - n_res], wl_of[n1 - n_res]);
+            else if (w0 != w1) R[atomicAdd(&s_nsw, 1)] = make_int2(ar_of[w0 ? n1 : n0], wl_of[(w0 ? n0 : n1) - n_res]);
+        }
+        __syncthreads();
+        const int nsw = s_nsw, nww = s_nww;
+        const int2* SW = R;
+        const int2* WW = R + (edge_cap - nww);
 
         if (nar > 0 && wc.max_water >= 1) {
-            const int words = min((nar + 31) >> 5, wc.cap_words);
+            // bit sets: shared memory when one word per node fits, with the widest source chunk that does
+            const int per_word = 3 * nlw + 2 * nar;
+            const bool in_smem = per_word <= wc.smem_words;
+            const int words = min((nar + 31) >> 5, in_smem ? min(wc.smem_words / per_word, WIRE_CHUNK_WORDS) : wc.cap_words);
             const int chunk = words * 32;
+            const int nw = nlw * words, ntw = nar * words;
+            unsigned* seen = in_smem ? s_bits : wc.wbits + (size_t)blockIdx.x * 3 * wstride;
+            unsigned* cur = in_smem ? seen + nw : seen + wstride;
+            unsigned* nxt = in_smem ? cur + nw : cur + wstride;
+            unsigned* found = in_smem ? nxt + nw : wc.tbits + (size_t)blockIdx.x * 2 * tstride;
+            unsigned* acc = in_smem ? found + ntw : found + tstride;
             for (int base = 0; base < nar; base += chunk) {
-                const int nw = nlw * words, ntw = nar * words;
                 for (int i = tid; i < nw; i += nt) cur[i] = 0;
                 for (int i = tid; i < ntw; i += nt) found[i] = 0;
                 __syncthreads();
                 // depth 1: the waters bonded to each source of this chunk
-                for (int i = tid; i < ne; i += nt) {
-                    const int2 e = E[i];
-                    const int n0 = wc.ent_node[e.x], n1 = wc.ent_node[e.y];
-                    if ((n0 >= n_res) == (n1 >= n_res)) continue;
-                    const int s = ar_of[n0 < n_res ? n0 : n1] - base;
-                    if (s < 0 || s >= chunk) continue;
-                    const int w = wl_of[(n0 < n_res ? n1 : n0) - n_res];
-                    atomicOr(&cur[(size_t)w * words + (s >> 5)], 1u << (s & 31));
+                for (int i = tid; i < nsw; i += nt) {
+                    const int2 e = SW[i];
+                    const int s = e.x - base;
+                    if (s >= 0 && s < chunk) atomicOr(&cur[(size_t)e.y * words + (s >> 5)], 1u << (s & 31));
                 }
                 __syncthreads();
                 for (int i = tid; i < nw; i += nt) seen[i] = cur[i];
                 for (int k = 1; k <= wc.max_water; ++k) {
                     for (int i = tid; i < ntw; i += nt) acc[i] = 0;
+                    if (tid == 0) s_nq = 0;
                     __syncthreads();
                     // sources whose frontier (depth k) holds a water next to residue t
-                    for (int i = tid; i < ne; i += nt) {
-                        const int2 e = E[i];
-                        const int n0 = wc.ent_node[e.x], n1 = wc.ent_node[e.y];
-                        if ((n0 >= n_res) == (n1 >= n_res)) continue;
-                        const int t = ar_of[n0 < n_res ? n0 : n1];
-                        const int w = wl_of[(n0 < n_res ? n1 : n0) - n_res];
-                        for (int j = 0; j < words; ++j) {
-                            const unsigned v = cur[(size_t)w * words + j];
-                            if (v) atomicOr(&acc[(size_t)t * words + j], v);
-                        }
+                    for (int i = tid; i < nsw * words; i += nt) {
+                        const int q = i / words, j = i - q * words;
+                        const int2 e = SW[q];
+                        const unsigned v = cur[(size_t)e.y * words + j];
+                        if (v) atomicOr(&acc[(size_t)e.x * words + j], v);
                     }
                     __syncthreads();
                     for (int i = tid; i < ntw; i += nt) {
@@ -150,28 +177,33 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
                         found[i] |= nb;
                         const int t = i / words, j = i - t * words;
                         const int tn = ar[t];
-                        while (nb) {
+                        while (nb) {            // every pair is reported from its smaller node
                             const int bit = __ffs(nb) - 1;
                             nb &= nb - 1;
-                            const int sn = ar[base + j * 32 + bit];
-                            if (sn < tn) wire_record(bt, sn, tn, frame, (unsigned)k);   // every pair from its smaller node
+                            const int si = base + j * 32 + bit;
+                            if (ar[si] >= tn) continue;
+                            const int q = (nar <= 65536) ? atomicAdd(&s_nq, 1) : WIRE_QUEUE;
+                            if (q < WIRE_QUEUE) s_queue[q] = ((unsigned)si << 16) | (unsigned)t;
+                            else wire_record(bt, ar[si], tn, frame, (unsigned)k);
                         }
+                    }
+                    __syncthreads();
+                    // the table updates (hash probe + atomic in global memory) spread over all threads
+                    for (int i = tid; i < min(s_nq, WIRE_QUEUE); i += nt) {
+                        const unsigned q = s_queue[i];
+                        wire_record(bt, ar[q >> 16], ar[q & 0xffffu], frame, (unsigned)k);
                     }
                     if (k == wc.max_water) break;
                     // one step along the water-water edges
                     for (int i = tid; i < nw; i += nt) nxt[i] = 0;
                     if (tid == 0) s_any = 0;
                     __syncthreads();
-                    for (int i = tid; i < ne; i += nt) {
-                        const int2 e = E[i];
-                        const int n0 = wc.ent_node[e.x], n1 = wc.ent_node[e.y];
-                        if (n0 < n_res || n1 < n_res) continue;
-                        const int a = wl_of[n0 - n_res], c = wl_of[n1 - n_res];
-                        for (int j = 0; j < words; ++j) {
-                            const unsigned va = cur[(size_t)a * words + j], vc = cur[(size_t)c * words + j];
-                            if (va) atomicOr(&nxt[(size_t)c * words + j], va);
-                            if (vc) atomicOr(&nxt[(size_t)a * words + j], vc);
-                        }
+                    for (int i = tid; i < nww * words; i += nt) {
+                        const int q = i / words, j = i - q * words;
+                        const int2 e = WW[q];
+                        const unsigned va = cur[(size_t)e.x * words + j], vc = cur[(size_t)e.y * words + j];
+                        if (va) atomicOr(&nxt[(size_t)e.y * words + j], va);
+                        if (vc) atomicOr(&nxt[(size_t)e.x * words + j], vc);
                     }
                     __syncthreads();
                     int any = 0;
@@ -186,22 +218,6 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
                     if (!s_any) break;
                 }
                 __syncthreads();
-            }
-        }
-        // direct bonds: (acceptor entry, donor entry)
-        if (wc.allow_direct) {
-            for (int i = tid; i < ne; i += nt) {
-                const int2 e = E[i];
-                const int na = wc.ent_node[e.x], nd = wc.ent_node[e.y];
-                if (na >= n_res || nd >= n_res) continue;
-                const int lo = min(na, nd), hi = max(na, nd);
-                const int h = table_slot(bt, ((unsigned long long)(unsigned)lo << 32) | (unsigned)hi);
-                if (h < 0) continue;
-                unsigned* row = bt.bits + (size_t)h * bt.wpr;
-                atomicOr(&row[frame >> 2], 0x80u << (8 * (int)(frame & 3)));
-                const unsigned long long packed = ((unsigned long long)frame << 32) | ((unsigned long long)(unsigned)e.x << 1) |
-                                                  (unsigned long long)(nd == hi ? 1 : 0);
-                atomicMax((unsigned long long*)(row + wc.nb4), ~packed);
             }
         }
         __syncthreads();

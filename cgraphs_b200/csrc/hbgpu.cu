@@ -89,12 +89,15 @@ struct hb_ctx {
     long long opt_fused_wait_ns = 100;
     long long opt_fused_prefetch = 2; // tiles prefetched into L2 ahead of the ring (more evicts lines before use)
     int fused_grow = 0;
+    int fused_grow_hint = 0;          // capacities that an earlier run on this topology needed ...
+    double fused_hint_around = 0.0;   // ... with this around radius (narrower shells start from the defaults)
 
     // fused-path plan (valid for the current run)
     bool water_regular = false;       // water point i of every system is atom first + i * stride
     int water_stride = 0;
     bool fused_active = false;
-    FusedCfg fc{};
+    double fused_unfit_around = -1.0; // around radius of a run whose frames did not fit the fused kernel's shared memory
+    FusedCfg fc{};                    // (same topology): later runs with a shell at least as wide start on the general path
     long long fused_fallbacks = 0;
 
     // run state
@@ -169,6 +172,8 @@ struct hb_ctx {
         WireCfg cfg{};
     } wire;
     long long opt_wire_edge_cap = 0;              // 0: automatic
+    long long opt_wire_smem_words = WIRE_SMEM_WORDS;
+    long long opt_wire_ctas_per_sm = 1;           // the BFS kernel takes a whole SM's shared memory
     BondTable bt_run{};                           // what the search kernels of the current launch get (wire mode: + edge lists)
     int ion_include_water = 1;
     // trajectory mode: atom ranges [begin, end) that hold every atom the kernels read; the rest of a frame
@@ -401,6 +406,13 @@ int hb_destroy(hb_ctx* ctx) {
 
 int hb_set_option(hb_ctx* ctx, const char* name, int64_t value) {
     if (ctx && name && !strcmp(name, "wire_edge_cap")) { ctx->opt_wire_edge_cap = value; return HB_OK; }
+    if (ctx && name && !strcmp(name, "wire_smem_words")) { ctx->opt_wire_smem_words = value; return HB_OK; }
+    if (ctx && name && !strcmp(name, "wire_ctas_per_sm")) {
+        ctx->opt_wire_ctas_per_sm = 1;      // (kept for compatibility: the kernel is one CTA per SM)
+        free_list(ctx->wire.allocs);
+        ctx->wire.d_edges = nullptr;
+        return HB_OK;
+    }
     if (!ctx || !name) return HB_ERR_ARG;
     std::string n(name);
     if (n == "batch_bytes") ctx->opt_batch_bytes = std::max<long long>(value, 1 << 20);
@@ -440,6 +452,8 @@ int hb_set_topology(hb_ctx* ctx, const hb_topology* t) {
     ctx->ions = IonTable{nullptr, nullptr, 0};
     ctx->wire.on = false;
     ctx->wire.d_ent_node = nullptr;
+    ctx->fused_unfit_around = -1.0;
+    ctx->fused_grow_hint = 0;
     ctx->have_topo = false;       // (run allocations are kept: hb_begin compares everything that sizes them)
     int ns = t->n_systems;
     ctx->h_sys_atom_off.assign(t->sys_atom_off, t->sys_atom_off + ns + 1);
@@ -656,6 +670,8 @@ int hb_set_params(hb_ctx* ctx, const hb_params* p) {
 static bool plan_fused(hb_ctx* ctx, int grow = 0) {
     ctx->fused_active = false;
     if (!ctx->opt_fused || ctx->rp.method == HB_METHOD_ION_CONTACTS) return false;
+    if (ctx->fused_unfit_around >= 0.0 && ctx->rp.method == HB_METHOD_WATER_AROUND &&
+        ctx->prm.around_radius >= ctx->fused_unfit_around) return false;
     const bool wa = ctx->rp.method == HB_METHOD_WATER_AROUND;
     FusedCfg fc{};
     fc.sel_cap = std::max(ctx->max_sel, 1);
@@ -763,7 +779,10 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     fb = round32(std::min<long long>(std::max<long long>(1, std::min<long long>(fb, ctx->opt_max_batch_frames)), n_frames_total));
     long long hb = (long long)(ctx->opt_batch_bytes / 2 / std::max<size_t>((size_t)ctx->max_atoms * 24, 1));
     hb = round32(std::min<long long>(std::max<long long>(1, std::min<long long>(hb, ctx->opt_max_batch_frames)), n_frames_total));
-    plan_fused(ctx);
+    {
+        const int hint = (ctx->rp.method == HB_METHOD_WATER_AROUND && ctx->prm.around_radius >= ctx->fused_hint_around) ? ctx->fused_grow_hint : 0;
+        if (!plan_fused(ctx, hint) && hint) plan_fused(ctx, 0);
+    }
     tr.mark("plan");
     // allocations of the previous run are reused when nothing that sizes them changed
     long long sig[8] = {wpr, ctx->max_sel, ctx->max_wat, ctx->max_atoms, fb, cc, ctx->prm.structure_batch + 2 * (ctx->wire.on ? ctx->wire.n_res + 1 : 0), hb};
@@ -988,8 +1007,9 @@ static int ensure_wire_buffers(hb_ctx* ctx) {
     w.frames = (int)std::min<long long>(std::max<long long>(fr, 1), 1024);
     const int n_wat = w.n_wat_nodes, n_res = w.n_res;
     const int cap_words = std::min((n_res + 31) / 32, WIRE_CHUNK_WORDS);
-    const size_t per_cta = (size_t)n_wat * 8 + (size_t)n_res * 8 + 3 * (size_t)n_wat * cap_words * 4 + 2 * (size_t)n_res * cap_words * 4;
-    long long ncta = std::min<long long>(2ll * ctx->prop.multiProcessorCount, (long long)((2ll << 30) / std::max<size_t>(per_cta, 1)));
+    const size_t per_cta = (size_t)n_wat * 8 + (size_t)n_res * 8 + 3 * (size_t)n_wat * cap_words * 4 + 2 * (size_t)n_res * cap_words * 4 +
+                           (size_t)w.edge_cap * 8;
+    long long ncta = std::min<long long>((long long)ctx->opt_wire_ctas_per_sm * ctx->prop.multiProcessorCount, (long long)((2ll << 30) / std::max<size_t>(per_cta, 1)));
     w.n_cta = (int)std::max<long long>(1, std::min<long long>(ncta, w.frames));
     int rc;
     WireCfg c{};
@@ -1001,6 +1021,8 @@ static int ensure_wire_buffers(hb_ctx* ctx) {
     if ((rc = dalloc((void**)&c.ar_list, (size_t)w.n_cta * n_res * 4))) return rc;
     if ((rc = dalloc((void**)&c.wbits, (size_t)w.n_cta * 3 * n_wat * cap_words * 4))) return rc;
     if ((rc = dalloc((void**)&c.tbits, (size_t)w.n_cta * 2 * n_res * cap_words * 4))) return rc;
+    if ((rc = dalloc((void**)&c.rlist, (size_t)w.n_cta * w.edge_cap * 8))) return rc;
+    CK(cudaFuncSetAttribute(k_wire_bfs, cudaFuncAttributeMaxDynamicSharedMemorySize, WIRE_SMEM_WORDS * 4));
     CK(cudaMemsetAsync(c.wl_of, 0xFF, (size_t)w.n_cta * n_wat * 4, ctx->s_compute));
     CK(cudaMemsetAsync(c.ar_of, 0xFF, (size_t)w.n_cta * n_res * 4, ctx->s_compute));
     c.ent_node = w.d_ent_node;
@@ -1031,6 +1053,7 @@ static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, 
         c.allow_direct = w.allow_direct;
         c.nb4 = w.nb4;
         c.status = ctx->bt.n_keys;
+        c.smem_words = (int)std::max<long long>(0, std::min<long long>(ctx->opt_wire_smem_words, WIRE_SMEM_WORDS));
         for (int done = 0; done < nf; done += w.frames) {
             const int n = std::min(nf - done, w.frames);
             CK(cudaMemsetAsync(w.d_cnt, 0, (size_t)n * 4, st));
@@ -1044,7 +1067,7 @@ static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, 
                                  xyz_bytes, d_box ? d_box + (size_t)done * 9 : nullptr, allow_fused))) return rc;
             {
                 KTimer t(ctx, KC_WIRES);
-                k_wire_bfs<<<std::min(n, w.n_cta), WIRE_THREADS, 0, st>>>(ctx->bt, c, w.d_edges, w.d_cnt, (int)w.edge_cap, frame0 + done, n);
+                k_wire_bfs<<<std::min(n, w.n_cta), WIRE_THREADS, WIRE_SMEM_WORDS * 4, st>>>(ctx->bt, c, w.d_edges, w.d_cnt, (int)w.edge_cap, frame0 + done, n);
             }
             CK(cudaGetLastError());
         }
@@ -1079,8 +1102,16 @@ static int full_verify(hb_ctx* ctx) {
         }
         if (fused_overflow) {      // some frame did not fit in shared memory: retry with doubled capacities
             ctx->fused_fallbacks++;   // while they fit, else this run continues on the general path
-            if (ctx->opt_fused_lw_cap || ctx->opt_fused_pair_cap || ctx->fused_grow >= 6 || !plan_fused(ctx, ctx->fused_grow + 1))
+            if (ctx->opt_fused_lw_cap || ctx->opt_fused_pair_cap || ctx->fused_grow >= 6 || !plan_fused(ctx, ctx->fused_grow + 1)) {
                 ctx->fused_active = false;
+                if (!ctx->opt_fused_lw_cap && !ctx->opt_fused_pair_cap && ctx->rp.method == HB_METHOD_WATER_AROUND)
+                    ctx->fused_unfit_around = ctx->prm.around_radius;
+            } else {
+                if (ctx->rp.method == HB_METHOD_WATER_AROUND) {
+                    ctx->fused_grow_hint = ctx->fused_grow;
+                    ctx->fused_hint_around = ctx->prm.around_radius;
+                }
+            }
         }
         if (pair_overflow) {       // the sub-batch found more pairs than the pair buffer holds: halve it
             if (ctx->batch_frames > 1) ctx->batch_frames = std::max(1, ctx->batch_frames / 2);
