@@ -204,6 +204,58 @@ def run_reference_arm(args):
     return 0
 
 
+def wires_leg(args, system, d_xyz, local_rank, peak, bytes_frame):
+    """Secondary measurement: WireAnalysis.set_water_wires(max_water=5) on the first frames of the
+    same trajectory, resident in HBM; device time from hb_begin to the end of hb_finalize (CUDA events inside the
+    library). Reported next to the headline, never part of it."""
+    import torch
+    from cgraphs_b200.mdhbond import WireAnalysis, _native
+    from cgraphs_b200.mdhbond.calib import cos_threshold
+    from cgraphs_b200.mdhbond.topology import pack_systems
+    nf = min(args.wire_frames, d_xyz.shape[0])
+    na = system.n_atoms
+    max_water = 5
+    wa = WireAnalysis(SELECTION, system.universe(1), device=local_rank)
+    top = wa._topology
+    tables, _ = pack_systems([top], [top.key_ids("water_around")], [na])
+    ctx = wa._context()
+    ctx.set_topology(tables)
+    ctx.set_wires(wa._wire_ent_node, wa._n_wire_nodes, max_water, True)
+    ctx.set_params(3.5, (max_water + 1) * 3.5 / 2., cos_threshold(60.0), True, False, _native.METHOD_WATER_AROUND)
+    ctx.set_option("profile", 1)
+    ms, kernels, nb, tm = [], {}, 0, None
+    for it in range(3 + 5):
+        ctx.begin(nf)
+        ctx.submit_device(d_xyz.data_ptr(), na, nf)
+        nb, _ = ctx.finalize()
+        torch.cuda.synchronize()
+        tm = ctx.timers()
+        if it >= 3:
+            ms.append(tm["ms_run"])
+            for k, v in tm["ms_kernel"].items():
+                if v:
+                    kernels[k] = kernels.get(k, 0.0) + v / 5
+    ms_pass = float(np.mean(ms))
+    value = nf / (ms_pass * 1e-3)
+    out = {"metric": "water_wire_frames_per_s", "value": value, "unit": "frames/s", "ms_per_pass": ms_pass,
+           "workload": "first %d frames of the same trajectory resident in HBM, WireAnalysis.set_water_wires(max_water=%d): "
+                       "10.5 A water shell, 3.5 A + 60 deg, selection '%s'" % (nf, max_water, SELECTION),
+           "n_residue_pairs": int(nb), "edges_per_frame": tm["pairs_emitted"] / nf, "launches_per_pass": int(tm["n_launches"]),
+           "kernel_ms_per_pass": {k: round(v, 3) for k, v in kernels.items()},
+           "hbm_frac": bytes_frame * value / 1e9 / peak}
+    if not args.no_cpu:
+        from oracle import hbond_port                   # CPU baseline leg: the validated port on a bounded sample
+        n_cpu = 4
+        sample = d_xyz[:n_cpu].cpu().numpy()
+        from cgraphs_b200.universe import Universe
+        t0 = time.perf_counter()
+        hbond_port.run_wires(Universe(system.topology, sample, system.dimensions), SELECTION, max_water=max_water)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n_cpu / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+                               "sample": "first %d frames, oracle/hbond_port.py run_wires (%.1f s)" % (n_cpu, dt)}
+    return out
+
+
 def workload_config(system, cfg, args):
     return {"workload": "C3: %d-atom membrane-protein-like system x %d frames per GPU, triclinic box, "
                         "set_hbonds_in_selection_and_water_around(3.5), 3.5 A + 60 deg, selection 'protein'"
@@ -425,6 +477,11 @@ def run_ours(args):
             "atom_frames_per_s": value * na, "wall_ms_per_step": wall_ms_max / args.steps,
             "n_bonds": int(nb), "n_global_bonds": n_global_keys, "n_part_atoms": int(n_part),
             "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
+    if world == 1 and args.wire_frames > 0:
+        try:
+            line["wires"] = wires_leg(args, system, d_xyz, local_rank, peak, bytes_frame)
+        except Exception as e:                          # the secondary leg never takes the headline down
+            line["wires"] = {"error": repr(e)[:300]}
     if per_rank is not None:
         line["per_rank_ms_per_step"] = {"columns": ["pass", "frame_fused kernel"], "ranks": per_rank}
     print(json.dumps(line))
@@ -443,6 +500,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="atom-count scale of the workload (1.0 = BASELINE config)")
     ap.add_argument("--cpu-frames", type=int, default=1024)
     ap.add_argument("--batch-bytes", type=int, default=0)
+    ap.add_argument("--wire-frames", type=int, default=2048, help="frames of the secondary water-wire leg (0: skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

@@ -85,6 +85,15 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
     int2* R = wc.rlist + (size_t)blockIdx.x * edge_cap;
     const size_t wstride = (size_t)wc.n_wat * wc.cap_words, tstride = (size_t)n_res * wc.cap_words;
     extern __shared__ unsigned s_bits[];
+    // HBGPU_TRACE: cycles thread 0 spends per phase (slots 16.. of the status block's cycle counters)
+    long long t_last = bt.phase_cycles ? clock64() : 0;
+    auto phase = [&](int slot) {
+        if (bt.phase_cycles && threadIdx.x == 0) {
+            const long long t = clock64();
+            atomicAdd(&bt.phase_cycles[16 + slot], (unsigned long long)(t - t_last));
+            t_last = t;
+        }
+    };
     __shared__ int s_nlw, s_nar, s_nsw, s_nww, s_any, s_nq;
     __shared__ unsigned s_queue[WIRE_QUEUE];      // pairs found at the current level: (source node index << 16) | target index
 
@@ -117,6 +126,7 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
             }
         }
         __syncthreads();
+        phase(0);
         const int nlw = s_nlw, nar = s_nar;
         for (int i = tid; i < nlw; i += nt) wl_of[lw[i]] = i;
         for (int i = tid; i < nar; i += nt) ar_of[ar[i]] = i;
@@ -131,6 +141,7 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
             else if (w0 != w1) R[atomicAdd(&s_nsw, 1)] = make_int2(ar_of[w0 ? n1 : n0], wl_of[(w0 ? n0 : n1) - n_res]);
         }
         __syncthreads();
+        phase(1);
         const int nsw = s_nsw, nww = s_nww;
         const int2* SW = R;
         const int2* WW = R + (edge_cap - nww);
@@ -159,6 +170,7 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
                 }
                 __syncthreads();
                 for (int i = tid; i < nw; i += nt) seen[i] = cur[i];
+                phase(2);
                 for (int k = 1; k <= wc.max_water; ++k) {
                     for (int i = tid; i < ntw; i += nt) acc[i] = 0;
                     if (tid == 0) s_nq = 0;
@@ -171,6 +183,7 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
                         if (v) atomicOr(&acc[(size_t)e.x * words + j], v);
                     }
                     __syncthreads();
+                    phase(3);
                     for (int i = tid; i < ntw; i += nt) {
                         unsigned nb = acc[i] & ~found[i];
                         if (!nb) continue;
@@ -188,11 +201,13 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
                         }
                     }
                     __syncthreads();
+                    phase(4);
                     // the table updates (hash probe + atomic in global memory) spread over all threads
                     for (int i = tid; i < min(s_nq, WIRE_QUEUE); i += nt) {
                         const unsigned q = s_queue[i];
                         wire_record(bt, ar[q >> 16], ar[q & 0xffffu], frame, (unsigned)k);
                     }
+                    phase(5);
                     if (k == wc.max_water) break;
                     // one step along the water-water edges
                     for (int i = tid; i < nw; i += nt) nxt[i] = 0;
@@ -206,6 +221,7 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
                         if (vc) atomicOr(&nxt[(size_t)e.x * words + j], vc);
                     }
                     __syncthreads();
+                    phase(6);
                     int any = 0;
                     for (int i = tid; i < nw; i += nt) {
                         const unsigned n = nxt[i] & ~seen[i];
@@ -215,6 +231,7 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
                     }
                     if (any) s_any = 1;
                     __syncthreads();
+                    phase(7);
                     if (!s_any) break;
                 }
                 __syncthreads();
@@ -224,6 +241,7 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
         for (int i = tid; i < nlw; i += nt) wl_of[lw[i]] = -1;
         for (int i = tid; i < nar; i += nt) ar_of[ar[i]] = -1;
         __syncthreads();
+        phase(8);
     }
 }
 

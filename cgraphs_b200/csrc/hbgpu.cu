@@ -1615,6 +1615,15 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
     ctx->fin_queued = false;
     ctx->d_out_keys = k0;
     tr.mark("sort+gather");
+    if (ctx->trace && ctx->bt.phase_cycles && ctx->wire.on) {
+        unsigned long long pc[9];
+        if (cudaMemcpy(pc, ctx->bt.phase_cycles + 16, sizeof(pc), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            double f = (double)std::max<long long>(ctx->tm.frames, 1);
+            fprintf(stderr, "[hbgpu] wire BFS, cycles per frame (thread 0): index+direct %.0f | local ids+rewrite %.0f | zero+seed %.0f | "
+                            "acc (residue-water) %.0f | found %.0f | table updates %.0f | water-water step %.0f | frontier update %.0f | reset %.0f\n",
+                    pc[0] / f, pc[1] / f, pc[2] / f, pc[3] / f, pc[4] / f, pc[5] / f, pc[6] / f, pc[7] / f, pc[8] / f);
+        }
+    }
     if (ctx->trace && ctx->bt.phase_cycles && ctx->tm.fused_frames) {
         unsigned long long pc[16];
         if (cudaMemcpy(pc, ctx->bt.phase_cycles, sizeof(pc), cudaMemcpyDeviceToHost) == cudaSuccess) {

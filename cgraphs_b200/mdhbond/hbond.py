@@ -289,8 +289,6 @@ class HbondAnalysis(object):
         top = self._topology
         self._check_hydrogen_tables(method)
         ctx = self._context()
-        if wires is not None and self._shard is not None and self._shard[1] > 1:
-            raise NotImplementedError('water wires are not sharded over GPUs yet')
         cache = self.__dict__.setdefault("_packed", {})
         if method not in cache:          # packed device tables per method (the key id strings differ)
             if method == "ions":         # hbond.py:61-66: _all_ids for the entries, water / ion ids by `residuewise`

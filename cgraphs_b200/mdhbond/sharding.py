@@ -154,3 +154,26 @@ def merge_shards(keys, words, lo, hi, n_frames, shard, ctx=None, group=None):
         if w:
             out[:, a // 32:a // 32 + w] = part[:, :w].cpu().numpy().view(np.uint32)
     return gkeys, out
+
+
+def merge_wire_shards(keys, cols, first_direct, lo, hi, n_frames, group=None):
+    """Water-wire results of frame block [lo, hi) of this rank -> the complete result on every rank.
+
+    keys: sorted distinct uint64 residue-pair keys; cols: uint8 [n, hi - lo] per-frame bytes; first_direct: uint64 [n]
+    with GLOBAL frame numbers (waterwire.split_wire_rows). One object all-gather (the result of a finished run, not a
+    data-path collective); the global key list is the sorted union, columns are placed at their frame block and the
+    first-direct word is the minimum over ranks."""
+    dist = _dist()
+    world = dist.get_world_size(group)
+    parts = [None] * world
+    dist.all_gather_object(parts, (int(lo), int(hi), np.asarray(keys), np.asarray(cols), np.asarray(first_direct)), group=group)
+    all_keys = np.unique(np.concatenate([p[2] for p in parts])) if parts else np.zeros(0, np.uint64)
+    out_cols = np.zeros((len(all_keys), n_frames), dtype=np.uint8)
+    out_fd = np.full(len(all_keys), np.uint64(0xFFFFFFFFFFFFFFFF), dtype=np.uint64)
+    for p_lo, p_hi, p_keys, p_cols, p_fd in parts:
+        if len(p_keys) == 0:
+            continue
+        idx = np.searchsorted(all_keys, p_keys)
+        out_cols[idx, p_lo:p_hi] = p_cols
+        out_fd[idx] = np.minimum(out_fd[idx], p_fd)
+    return all_keys, out_cols, out_fd

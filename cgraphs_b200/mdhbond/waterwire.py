@@ -22,6 +22,52 @@ import numpy as _np
 from .hbond import HbondAnalysis
 
 
+def split_wire_rows(words, n_frames, frame0=0):
+    """Rows of a wire run (include/hbgpu.h, hb_set_wires) -> (uint8 [n, n_frames] per-frame bytes,
+    uint64 [n] `(first direct frame << 32) | (acceptor entry << 1) | donor_is_second_node`, all ones = never)."""
+    n = len(words)
+    if n == 0:
+        return _np.zeros((0, n_frames), _np.uint8), _np.zeros(0, _np.uint64)
+    nb4 = words.shape[1] - 2
+    cols = _np.ascontiguousarray(words[:, :nb4].view(_np.uint8)[:, :n_frames])
+    tail = _np.ascontiguousarray(words[:, nb4:nb4 + 2]).view(_np.uint64)[:, 0]
+    packed = ~tail                                   # the device keeps the complement (atomicMax on zeroed rows)
+    has = tail != 0
+    packed = _np.where(has, packed + (_np.uint64(frame0) << _np.uint64(32)), _np.uint64(0xFFFFFFFFFFFFFFFF))
+    return cols, packed
+
+
+def decode_wire_rows(keys, cols, first_direct, node_entry, ids, n_frames):
+    """(node_lo << 32 | node_hi) keys + per-frame bytes -> the reference's `wire_lengths` dict
+    (waterwire.py:286-293, 302-309): float64 per frame, inf = no wire, 0 = direct H-bond, k = waters in the wire.
+    Key orientation = first discovery (waterwire.py:277-279, 299-301): a wire names the residue with the smaller
+    node first; a direct bond names the donor's residue first; within a frame wires are met first."""
+    results = {}
+    if len(keys) == 0:
+        return results
+    wire_k = cols & 0x7f
+    direct = (cols & 0x80) != 0
+    lengths = _np.full(cols.shape, _np.inf)
+    has = wire_k > 0
+    lengths[has] = wire_k[has]
+    lengths[direct] = 0
+    has_wire = has.any(axis=1)
+    first_wire = _np.where(has_wire, has.argmax(axis=1), n_frames)
+    has_direct = first_direct != _np.uint64(0xFFFFFFFFFFFFFFFF)
+    fd_frame = _np.where(has_direct, (first_direct >> _np.uint64(32)).astype(_np.int64), n_frames)
+    donor_hi = (first_direct & _np.uint64(1)).astype(bool) & has_direct
+    by_wire = has_wire & (first_wire <= fd_frame)
+    lo = node_entry[(keys >> _np.uint64(32)).astype(_np.int64)]
+    hi = node_entry[(keys & _np.uint64(0xFFFFFFFF)).astype(_np.int64)]
+    swap = ~by_wire & donor_hi
+    a = _np.where(swap, hi, lo)
+    b = _np.where(swap, lo, hi)
+    order = _np.lexsort((_np.arange(len(keys)), _np.minimum(first_wire, fd_frame)))
+    for i in order:
+        results[ids[a[i]] + ':' + ids[b[i]]] = lengths[i]
+    return results
+
+
 class WireAnalysis(HbondAnalysis):
 
     def __init__(self, selection=None, structure=None, trajectories=None, distance=3.5, cut_angle=60.,
@@ -68,36 +114,15 @@ class WireAnalysis(HbondAnalysis):
         around = float(max_water + 1) * self.distance / 2.
         wires = (self._wire_ent_node, self._n_wire_nodes, max_water, bool(allow_direct_bonds))
         keys, words = self._run("water_around", around, False, wires=wires)
-        n = self.nb_frames
-        results = {}
-        if len(keys):
-            nb4 = words.shape[1] - 2
-            cols = words[:, :nb4].view(_np.uint8)[:, :n]
-            tail = _np.ascontiguousarray(words[:, nb4:nb4 + 2]).view(_np.uint64)[:, 0]
-            wire_k = cols & 0x7f
-            direct = (cols & 0x80) != 0
-            lengths = _np.full(cols.shape, _np.inf)
-            has = wire_k > 0
-            lengths[has] = wire_k[has]
-            lengths[direct] = 0
-            # key orientation = first discovery (waterwire.py:277-279, 299-301): a wire names the residue with the
-            # smaller node first; a direct bond names the donor's residue first
-            has_wire = has.any(axis=1)
-            first_wire = _np.where(has_wire, has.argmax(axis=1), n)
-            has_direct = tail != 0
-            packed = ~tail
-            first_direct = _np.where(has_direct, (packed >> _np.uint64(32)).astype(_np.int64), n)
-            donor_hi = (packed & _np.uint64(1)).astype(bool) & has_direct
-            by_wire = has_wire & (first_wire <= first_direct)
-            lo = self._wire_node_entry[(keys >> _np.uint64(32)).astype(_np.int64)]
-            hi = self._wire_node_entry[(keys & _np.uint64(0xFFFFFFFF)).astype(_np.int64)]
-            swap = ~by_wire & donor_hi
-            a = _np.where(swap, hi, lo)
-            b = _np.where(swap, lo, hi)
-            ids = self._all_ids
-            order = _np.lexsort((_np.arange(len(keys)), _np.minimum(first_wire, first_direct)))
-            for i in order:
-                results[ids[a[i]] + ':' + ids[b[i]]] = lengths[i]
+        lo, hi = 0, self.nb_frames
+        if self._shard is not None:
+            from .sharding import shard_range
+            lo, hi = shard_range(self.nb_frames, *self._shard)
+        cols, tail = split_wire_rows(words, hi - lo, lo)
+        if self._shard is not None and self._shard[1] > 1:
+            from .sharding import merge_wire_shards
+            keys, cols, tail = merge_wire_shards(keys, cols, tail, lo, hi, self.nb_frames)
+        results = decode_wire_rows(keys, cols, tail, self._wire_node_entry, self._all_ids, self.nb_frames)
         self._set_results({key: results[key] != _np.inf for key in results})
         self.wire_lengths = results
         self.hashs = {}
