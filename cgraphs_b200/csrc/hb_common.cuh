@@ -642,7 +642,10 @@ __device__ void process_self(const DevTopo& tp, const RunParams& rp, const BondT
 // point array (start = cells[c-1], 0 for c = 0); cells are ordered x-fastest, so the three x-neighbours
 // of a (y, z) row are one contiguous run of points.
 // ------------------------------------------------------------------------------------------------
-template <bool PBC, typename CellT>
+// OWN_FIRST (general path): scan the water's own row of cells first, then the eight around it - a water next to the
+// selection usually finds its hit at once. (The fused kernel keeps the plain order: its candidates are pre-filtered
+// by the near bitmap and the shorter loop control is worth more there.)
+template <bool PBC, typename CellT, bool OWN_FIRST = false>
 __device__ __forceinline__ bool water_is_local(const FrameGrid& g, const CellT* cells, const float4* pts, float x,
                                                float y, float z, const RunParams& rp) {
     int cx, cy, cz;
@@ -664,6 +667,24 @@ __device__ __forceinline__ bool water_is_local(const FrameGrid& g, const CellT* 
             }
         return false;
     } else {
+        if constexpr (OWN_FIRST) {
+            for (int kz = 0; kz < 3; ++kz)
+                for (int ky = 0; ky < 3; ++ky) {
+                    const int zz = cz + ((kz + 1) % 3) - 1, yy = cy + ((ky + 1) % 3) - 1;      // offsets 0, +1, -1
+                    if (zz < 0 || zz >= g.nz || yy < 0 || yy >= g.ny) continue;
+                    const int c_lo = (zz * g.ny + yy) * g.nx + max(cx - 1, 0);
+                    const int c_hi = (zz * g.ny + yy) * g.nx + min(cx + 1, g.nx - 1);
+                    const int s = c_lo ? (int)cells[c_lo - 1] : 0;
+                    const int e = (int)cells[c_hi];
+                    for (int q = s; q < e; ++q) {
+                        const float4 sp = pts[q];
+                        if (dist2f(x, y, z, sp.x, sp.y, sp.z) <= rp.around2f_hi &&
+                            dist_le(x, y, z, sp.x, sp.y, sp.z, rp.around2))
+                            return true;
+                    }
+                }
+            return false;
+        }
         for (int zz = max(cz - 1, 0); zz <= min(cz + 1, g.nz - 1); ++zz)
             for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.ny - 1); ++yy) {
                 int c_lo = (zz * g.ny + yy) * g.nx + max(cx - 1, 0);

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(256) k_local_water(BatchView bv, DevTopo tp, R
                      z >= f.lo[2] - a && z <= f.hi[2] + a;
         }
         if (inside)
-            local = water_is_local<PBC>(f.g1, bv.cells1 + (size_t)b * (bv.cell_cap + 1),
+            local = water_is_local<PBC, int, true>(f.g1, bv.cells1 + (size_t)b * (bv.cell_cap + 1),
                                         bv.sorted1 + (size_t)b * bv.max_sel, x, y, z, rp);
     }
     unsigned m = __ballot_sync(0xffffffffu, local);
@@ -267,6 +267,62 @@ __global__ void __launch_bounds__(256) k_local_water(BatchView bv, DevTopo tp, R
         if (local) {
             int pos = base + __popc(m & ((1u << lane) - 1u));
             bv.lw[(size_t)b * bv.max_wat + pos] = make_float4(x, y, z, __int_as_float(WATER_TAG | i));
+        }
+    }
+}
+
+// K6 with the selection grid in shared memory: when the cell-sorted selection points and the g1 cell offsets of a
+// frame fit (the host checks the points, the kernel the cells), a block stages them once and tests `per_block` waters
+// against them - the dependent cell-offset and point loads then cost shared-memory instead of L2 latency.
+#define LW_SMEM_CELLS 4096
+template <bool PBC>
+__global__ void __launch_bounds__(256) k_local_water_smem(BatchView bv, DevTopo tp, RunParams rp, int per_block) {
+    extern __shared__ float4 s_pts[];                    // [max_sel] points, then [LW_SMEM_CELLS + 1] cell offsets
+    int* s_cells = (int*)(s_pts + bv.max_sel);
+    const int b = blockIdx.y;
+    int sys;
+    const float* xyz = frame_xyz(bv, tp, b, sys);
+    const int w0 = tp.sys_wat_off[sys], w1 = tp.sys_wat_off[sys + 1];
+    const int n_sel = tp.sys_sel_off[sys + 1] - tp.sys_sel_off[sys];
+    const FrameState& f = bv.fs[b];
+    const int first = blockIdx.x * per_block;
+    if (w0 + first >= w1) return;
+    const int* g_cells = bv.cells1 + (size_t)b * (bv.cell_cap + 1);
+    const float4* g_pts = bv.sorted1 + (size_t)b * bv.max_sel;
+    const bool staged = f.g1.ncell <= LW_SMEM_CELLS;     // uniform per block
+    if (staged) {
+        for (int i = threadIdx.x; i < n_sel; i += blockDim.x) s_pts[i] = g_pts[i];
+        for (int i = threadIdx.x; i <= f.g1.ncell; i += blockDim.x) s_cells[i] = g_cells[i];
+    }
+    __syncthreads();
+    const int* cells = staged ? s_cells : g_cells;
+    const float4* pts = staged ? s_pts : g_pts;
+    for (int base = first; base < first + per_block; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        bool local = false;
+        float x = 0.f, y = 0.f, z = 0.f;
+        if (i < first + per_block && w0 + i < w1) {
+            const float* p = xyz + 3ll * tp.wat_atom[w0 + i];
+            x = p[0]; y = p[1]; z = p[2];
+            bool inside;
+            if constexpr (PBC) {
+                int cx, cy, cz;
+                inside = cell3_pbc(f.g1, x, y, z, cx, cy, cz);
+            } else {
+                const float a = rp.around_f;
+                inside = x >= f.lo[0] - a && x <= f.hi[0] + a && y >= f.lo[1] - a && y <= f.hi[1] + a &&
+                         z >= f.lo[2] - a && z <= f.hi[2] + a;
+            }
+            if (inside) local = water_is_local<PBC, int, true>(f.g1, cells, pts, x, y, z, rp);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, local);
+        if (m) {
+            const int lane = threadIdx.x & 31;
+            int pos0 = 0;
+            if (lane == 0) pos0 = atomicAdd(&bv.fs[b].n_local, __popc(m));
+            pos0 = __shfl_sync(0xffffffffu, pos0, 0);
+            if (local)
+                bv.lw[(size_t)b * bv.max_wat + pos0 + __popc(m & ((1u << lane) - 1u))] = make_float4(x, y, z, __int_as_float(WATER_TAG | i));
         }
     }
 }

@@ -171,6 +171,7 @@ struct hb_ctx {
         std::vector<void*> allocs;
         WireCfg cfg{};
     } wire;
+    int opt_lw_smem = 1;                          // general path: stage the selection grid in shared memory when it fits
     long long opt_wire_edge_cap = 0;              // 0: automatic
     long long opt_wire_smem_words = WIRE_SMEM_WORDS;
     long long opt_wire_ctas_per_sm = 1;           // the BFS kernel takes a whole SM's shared memory
@@ -405,6 +406,7 @@ int hb_destroy(hb_ctx* ctx) {
 }
 
 int hb_set_option(hb_ctx* ctx, const char* name, int64_t value) {
+    if (ctx && name && !strcmp(name, "lw_smem")) { ctx->opt_lw_smem = value != 0; return HB_OK; }
     if (ctx && name && !strcmp(name, "wire_edge_cap")) { ctx->opt_wire_edge_cap = value; return HB_OK; }
     if (ctx && name && !strcmp(name, "wire_smem_words")) { ctx->opt_wire_smem_words = value; return HB_OK; }
     if (ctx && name && !strcmp(name, "wire_ctas_per_sm")) {
@@ -905,7 +907,22 @@ static int run_general_t(hb_ctx* ctx, BatchView bv) {
         { KTimer t(ctx, KC_COUNT); k_count<PBC><<<gsel, 256, 0, st>>>(bv, tp, 1); }
         { KTimer t(ctx, KC_SCAN); k_scan<<<nf, 1024, 0, st>>>(bv, 1); }
         { KTimer t(ctx, KC_SCATTER); k_scatter<PBC><<<gsel, 256, 0, st>>>(bv, tp, 1); }
-        { KTimer t(ctx, KC_LOCAL); k_local_water<PBC><<<gwat, 256, 0, st>>>(bv, tp, rp); }
+        const size_t lw_smem = (size_t)bv.max_sel * 16 + (LW_SMEM_CELLS + 1) * 4;
+        if (ctx->opt_lw_smem && lw_smem <= 96 * 1024) {
+            // selection grid staged in shared memory, 2048 waters per block
+            const int per_block = 2048;
+            static bool attr_set[2] = {false, false};
+            if (!attr_set[PBC ? 1 : 0]) {
+                CK(cudaFuncSetAttribute(k_local_water_smem<PBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                attr_set[PBC ? 1 : 0] = true;
+            }
+            dim3 gw((bv.max_wat + per_block - 1) / per_block, nf);
+            KTimer t(ctx, KC_LOCAL);
+            k_local_water_smem<PBC><<<gw, 256, lw_smem, st>>>(bv, tp, rp, per_block);
+        } else {
+            KTimer t(ctx, KC_LOCAL);
+            k_local_water<PBC><<<gwat, 256, 0, st>>>(bv, tp, rp);
+        }
     }
     int maxp = bv.max_sel + (wa ? bv.max_wat : 0);
     if (maxp > 0) {

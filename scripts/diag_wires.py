@@ -47,12 +47,12 @@ def main():
     ctx = wa._context()
     ctx.set_topology(tables)
     ctx.set_wires(wa._wire_ent_node, wa._n_wire_nodes, args.max_water, True)
-    around = (args.max_water + 1) * 3.5 / 2.
-    ctx.set_params(3.5, around, cos_threshold(60.0) if ca else -1.0, ca, False, _native.METHOD_WATER_AROUND)
     ctx.set_option("profile", args.profile)
     for kv in filter(None, args.options.split(",")):
         k, v = kv.split("=")
         ctx.set_option(k, int(v))
+    around = (args.max_water + 1) * 3.5 / 2.
+    ctx.set_params(3.5, around, cos_threshold(60.0) if ca else -1.0, ca, False, _native.METHOD_WATER_AROUND)
     for rep in range(args.reps):
         torch.cuda.synchronize()
         t0 = time.perf_counter()

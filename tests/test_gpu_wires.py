@@ -107,3 +107,20 @@ def test_wires_unsupported_options_raise():
         WireAnalysis("protein", u).set_water_wires(water_in_convex_hull=True)
     with pytest.raises(NotImplementedError):
         WireAnalysis("protein", u, residuewise=False).set_water_wires()
+
+
+def test_wide_shells_general_path_local_water_kernels():
+    """Wide around radii on the general path: the local-water test with the selection grid staged in shared memory
+    (k_local_water_smem) and from global memory (k_local_water) against the oracle."""
+    from cgraphs_b200.mdhbond import HbondAnalysis
+    from oracle import hbond_port
+    s = synth.make_system(6000, 40, 611, n_chains=2)
+    u = s.universe(3)
+    kw = dict(additional_donors=['N'], additional_acceptors=['O'])
+    for around in (3.5, 8.75, 14.0):
+        ref = hbond_port.run(u, "protein", "water_around", around=around, **kw).initial_results
+        assert len(ref) > 30
+        for lw_smem in (1, 0):
+            hba = HbondAnalysis("protein", u, native_options={"fused": 0, "lw_smem": lw_smem}, **kw)
+            hba.set_hbonds_in_selection_and_water_around(around)
+            assert {k: v.tobytes() for k, v in hba.initial_results.items()} == {k: v.tobytes() for k, v in ref.items()}, around
