@@ -115,10 +115,16 @@ struct BondTable {
     unsigned long long* n_hits;
     unsigned long long* phase_cycles;   // optional (HBGPU_TRACE): SM cycles thread 0 of each fused CTA spent per phase
     // water-wire mode (hb_wires.cuh): the search appends the H-bond entry pairs of every frame to a per-frame edge
-    // list instead of setting table bits; k_wire_bfs consumes the lists and writes wire lengths into the table rows
-    int2* edges;                // [frames of the sub-batch][edge_cap], null outside wire mode
-    int* edge_cnt;              // [frames of the sub-batch]
+    // list instead of setting table bits; k_wire_bfs consumes the lists and writes wire lengths into the table rows.
+    // One pointer (null outside wire mode) so that the H-bond path's kernels carry nothing else for it.
+    const struct EdgeSink* sink;
+};
+
+struct EdgeSink {               // lives in device memory, rewritten by the host before every search round
+    int2* edges;                // [frames of the round][edge_cap]
+    int* edge_cnt;              // [frames of the round]
     int edge_cap;
+    int pad;
     long long edge_frame0;      // global frame of list 0
     int* wire_overflow;         // some list ran out of space: the host doubles edge_cap and re-runs the batch
 };
@@ -510,12 +516,13 @@ __device__ __noinline__ bool any_h4(const float* xyz, int hl, int atom, float ox
 
 __device__ __noinline__ void emit_bond(const int4* ent_pack, const int* ent_group, int check_angle, BondTable bt,
                                        long long frame, int e0, int e1, int* nhit) {
-    if (bt.edges) {                                    // wire mode: (acceptor, donor) / (selection, water) / (water, water)
+    if (bt.sink) {                                     // wire mode: (acceptor, donor) / (selection, water) / (water, water)
         ++*nhit;
-        const int b = (int)(frame - bt.edge_frame0);
-        const int i = atomicAdd(&bt.edge_cnt[b], 1);
-        if (i < bt.edge_cap) bt.edges[(size_t)b * bt.edge_cap + i] = make_int2(e0, e1);
-        else atomicExch(bt.wire_overflow, 1);
+        const EdgeSink sk = *bt.sink;
+        const int b = (int)(frame - sk.edge_frame0);
+        const int i = atomicAdd(&sk.edge_cnt[b], 1);
+        if (i < sk.edge_cap) sk.edges[(size_t)b * sk.edge_cap + i] = make_int2(e0, e1);
+        else atomicExch(sk.wire_overflow, 1);
         return;
     }
     int x = min(e0, e1), y = max(e0, e1);

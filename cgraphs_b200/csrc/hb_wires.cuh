@@ -51,6 +51,8 @@ struct WireCfg {
     const int* status;       // status block: [2] fused_overflow, [3] pair_overflow, [6] wire_overflow
 };
 
+__global__ void k_set_sink(EdgeSink* dst, EdgeSink v) { *dst = v; }
+
 __device__ __forceinline__ int table_slot(const BondTable& bt, unsigned long long key) {
     unsigned h = hash64(key) & bt.mask;
     for (unsigned probe = 0; probe <= bt.mask; ++probe) {

@@ -165,6 +165,7 @@ struct hb_ctx {
         int nb4 = 0;                              // row words holding the per-frame bytes
         int2* d_edges = nullptr;
         int* d_cnt = nullptr;
+        EdgeSink* d_sink = nullptr;
         long long edge_cap = 0;
         int frames = 0;                           // frames per search + BFS round
         int n_cta = 0;
@@ -1032,6 +1033,7 @@ static int ensure_wire_buffers(hb_ctx* ctx) {
     WireCfg c{};
     if ((rc = dalloc((void**)&w.d_edges, (size_t)w.frames * w.edge_cap * 8))) return rc;
     if ((rc = dalloc((void**)&w.d_cnt, (size_t)w.frames * 4))) return rc;
+    if ((rc = dalloc((void**)&w.d_sink, sizeof(EdgeSink)))) return rc;
     if ((rc = dalloc((void**)&c.wl_of, (size_t)w.n_cta * n_wat * 4))) return rc;
     if ((rc = dalloc((void**)&c.lw_list, (size_t)w.n_cta * n_wat * 4))) return rc;
     if ((rc = dalloc((void**)&c.ar_of, (size_t)w.n_cta * n_res * 4))) return rc;
@@ -1074,12 +1076,16 @@ static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, 
         for (int done = 0; done < nf; done += w.frames) {
             const int n = std::min(nf - done, w.frames);
             CK(cudaMemsetAsync(w.d_cnt, 0, (size_t)n * 4, st));
+            // the sink descriptor of this round (stream ordered: the previous round's kernels are done with theirs)
+            EdgeSink sk{};
+            sk.edges = w.d_edges;
+            sk.edge_cnt = w.d_cnt;
+            sk.edge_cap = (int)w.edge_cap;
+            sk.edge_frame0 = frame0 + done;
+            sk.wire_overflow = ctx->bt.n_keys + 6;
+            k_set_sink<<<1, 1, 0, st>>>(w.d_sink, sk);
             ctx->bt_run = ctx->bt;
-            ctx->bt_run.edges = w.d_edges;
-            ctx->bt_run.edge_cnt = w.d_cnt;
-            ctx->bt_run.edge_cap = (int)w.edge_cap;
-            ctx->bt_run.edge_frame0 = frame0 + done;
-            ctx->bt_run.wire_overflow = ctx->bt.n_keys + 6;
+            ctx->bt_run.sink = w.d_sink;
             if ((rc = run_search(ctx, d_xyz + (size_t)done * atoms_per_frame * 3, frame0 + done, n, atoms_per_frame, d_xyz,
                                  xyz_bytes, d_box ? d_box + (size_t)done * 9 : nullptr, allow_fused))) return rc;
             {
