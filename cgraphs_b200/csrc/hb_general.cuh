@@ -327,6 +327,19 @@ __global__ void __launch_bounds__(256) k_local_water_smem(BatchView bv, DevTopo 
     }
 }
 
+// HB_METHOD_WATER_PRESENCE (HydrationAnalysis.set_presence_around, hydration.py:71-107): every local water of a
+// frame sets its bit in the row of its water id.
+__global__ void __launch_bounds__(256) k_presence_emit(BatchView bv, DevTopo tp, BondTable bt) {
+    const int b = blockIdx.y;
+    const int sys = bv.structure_batch ? (int)(bv.frame0 + b) : 0;
+    const int n = bv.fs[b].n_local;
+    const int w0 = tp.sys_wat_off[sys];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int w = __float_as_int(bv.lw[(size_t)b * bv.max_wat + i].w) & POINT_ID_MASK;
+        record_bond(bt, (unsigned long long)(unsigned)tp.ent_group[tp.wat_ent[w0 + w]], bv.frame0 + b);
+    }
+}
+
 template <bool PBC>
 __global__ void __launch_bounds__(128) k_pairs(BatchView bv, DevTopo tp, RunParams rp, BondTable bt) {
     int b = blockIdx.y;

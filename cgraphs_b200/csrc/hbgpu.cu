@@ -95,6 +95,7 @@ struct hb_ctx {
     // fused-path plan (valid for the current run)
     bool water_regular = false;       // water point i of every system is atom first + i * stride
     int water_stride = 0;
+    bool presence = false;            // HB_METHOD_WATER_PRESENCE
     bool fused_active = false;
     double fused_unfit_around = -1.0; // around radius of a run whose frames did not fit the fused kernel's shared memory
     FusedCfg fc{};                    // (same topology): later runs with a shell at least as wide start on the general path
@@ -639,10 +640,12 @@ int hb_set_params(hb_ctx* ctx, const hb_params* p) {
     if (!ctx || !p) return HB_ERR_ARG;
     if (ctx->running) return fail(ctx, HB_ERR_STATE, "hb_set_params during a run");
     if (!(p->distance > 0.0) || !std::isfinite(p->distance)) return fail(ctx, HB_ERR_ARG, "distance must be positive");
-    if (p->method != HB_METHOD_IN_SELECTION && p->method != HB_METHOD_WATER_AROUND && p->method != HB_METHOD_ION_CONTACTS)
+    if (p->method != HB_METHOD_IN_SELECTION && p->method != HB_METHOD_WATER_AROUND && p->method != HB_METHOD_ION_CONTACTS &&
+        p->method != HB_METHOD_WATER_PRESENCE)
         return fail(ctx, HB_ERR_ARG, "unknown method");
     if (p->method == HB_METHOD_ION_CONTACTS && p->structure_batch) return fail(ctx, HB_ERR_ARG, "ion contacts: trajectories only");
-    if (p->method == HB_METHOD_WATER_AROUND && (!(p->around_radius >= 0.0) || !std::isfinite(p->around_radius)))
+    if ((p->method == HB_METHOD_WATER_AROUND || p->method == HB_METHOD_WATER_PRESENCE) &&
+        (!(p->around_radius >= 0.0) || !std::isfinite(p->around_radius)))
         return fail(ctx, HB_ERR_ARG, "around_radius must be >= 0");
     if (p->pbc_mode != HB_PBC_NONE && p->pbc_mode != HB_PBC_ORTHO && p->pbc_mode != HB_PBC_TRICLINIC)
         return fail(ctx, HB_ERR_ARG, "unknown pbc_mode");
@@ -662,7 +665,9 @@ int hb_set_params(hb_ctx* ctx, const hb_params* p) {
     r.cos_threshold = p->cos_threshold;
     r.check_angle = p->check_angle;
     r.excl_bb = p->exclude_backbone_backbone;
-    r.method = p->method;
+    // the presence method is the first half of the water-around pipeline (selection grid + local-water test)
+    ctx->presence = p->method == HB_METHOD_WATER_PRESENCE;
+    r.method = ctx->presence ? HB_METHOD_WATER_AROUND : p->method;
     r.self_pairs = 0;          // decided in hb_begin
     ctx->have_params = true;
     return HB_OK;
@@ -672,7 +677,7 @@ int hb_set_params(hb_ctx* ctx, const hb_params* p) {
 // `grow` > 0 doubles the local-water / pair capacities that many times (used after a fused overflow).
 static bool plan_fused(hb_ctx* ctx, int grow = 0) {
     ctx->fused_active = false;
-    if (!ctx->opt_fused || ctx->rp.method == HB_METHOD_ION_CONTACTS) return false;
+    if (!ctx->opt_fused || ctx->rp.method == HB_METHOD_ION_CONTACTS || ctx->presence) return false;
     if (ctx->fused_unfit_around >= 0.0 && ctx->rp.method == HB_METHOD_WATER_AROUND &&
         ctx->prm.around_radius >= ctx->fused_unfit_around) return false;
     const bool wa = ctx->rp.method == HB_METHOD_WATER_AROUND;
@@ -753,7 +758,7 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     tr.mark("sync");
     int wpr = (int)((n_frames_total + 31) / 32);
     if (ctx->wire.on) {        // one byte per frame, then the two "first direct bond" words (hb_wires.cuh)
-        if (ctx->prm.structure_batch || ctx->rp.method != HB_METHOD_WATER_AROUND)
+        if (ctx->prm.structure_batch || ctx->rp.method != HB_METHOD_WATER_AROUND || ctx->presence)
             return fail(ctx, HB_ERR_ARG, "water wires: HB_METHOD_WATER_AROUND on a trajectory");
         ctx->wire.nb4 = (int)((((n_frames_total + 3) / 4) + 1) & ~1ll);
         wpr = ctx->wire.nb4 + 2;
@@ -924,6 +929,14 @@ static int run_general_t(hb_ctx* ctx, BatchView bv) {
             KTimer t(ctx, KC_LOCAL);
             k_local_water<PBC><<<gwat, 256, 0, st>>>(bv, tp, rp);
         }
+    }
+    if (ctx->presence) {
+        if (bv.max_sel > 0 && bv.max_wat > 0) {
+            KTimer t(ctx, KC_PAIRS);
+            k_presence_emit<<<dim3(8, nf), 256, 0, st>>>(bv, tp, ctx->bt_run);
+        }
+        CK(cudaGetLastError());
+        return HB_OK;
     }
     int maxp = bv.max_sel + (wa ? bv.max_wat : 0);
     if (maxp > 0) {
@@ -1194,7 +1207,7 @@ static int check_submit(hb_ctx* ctx, int64_t n_atoms, int64_t n_frames) {
 // lattice vectors of host-supplied frames: lower-triangular rows a, b, c with a positive diagonal, and cut-offs
 // below half of every brick edge so that the sequential minimum-image reduction finds every pair
 static int check_boxes(hb_ctx* ctx, const float* box, long long n_frames) {
-    const double rmax = std::max(ctx->prm.distance, ctx->prm.method == HB_METHOD_WATER_AROUND ? ctx->prm.around_radius : 0.0);
+    const double rmax = std::max(ctx->prm.distance, (ctx->prm.method == HB_METHOD_WATER_AROUND || ctx->presence) ? ctx->prm.around_radius : 0.0);
     for (long long f = 0; f < n_frames; ++f) {
         const float* b = box + 9 * f;
         if (b[1] != 0.f || b[2] != 0.f || b[5] != 0.f)

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc"
 METHOD_IN_SELECTION = 0
 METHOD_WATER_AROUND = 1
 METHOD_ION_CONTACTS = 2
+METHOD_WATER_PRESENCE = 3
 PBC_NONE, PBC_ORTHO, PBC_TRICLINIC = 0, 1, 2
 
 

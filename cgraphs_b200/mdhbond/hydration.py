@@ -1,0 +1,124 @@
+"""``HydrationAnalysis.set_presence_around`` on the GPU (SURVEY 8f "next" #4; reference
+``cgraphs/mdhbond/hydration.py:71-107``).
+
+Per frame: the waters of the water group (``basic.py:62``) within ``around_distance`` of ANY atom of the selection
+(all selected atoms, not only donors / acceptors). That is the local-water test of the H-bond path
+(``hbond.py:249-252``) with the whole selection as the point set, so the library runs the first half of its
+water-around pipeline (``HB_METHOD_WATER_PRESENCE``: selection cell grid, ``k_local_water``) and sets one bit per
+present water and frame (``k_presence_emit``). Results: ``initial_results`` / ``filtered_results`` =
+``{water id: bool[nb_frames]}`` like the reference's, plus ``filter_occupancy`` (``hydration.py:109-115``).
+
+Not covered: ``per_residue=True`` (pair keys), the convex-hull variant ``set_presence_in_hull`` (scipy Delaunay) and
+the diffusion / residence-time statistics further down in the reference class.
+"""
+from __future__ import annotations
+
+import numpy as _np
+
+from . import _native
+from .hbond import WATER_DEFINITION, _as_universe, _frame_blocks
+from .topology import AtomColumns, _ids
+
+
+class HydrationAnalysis(object):
+
+    def __init__(self, selection=None, structure=None, trajectories=None, start=None, stop=None, step=1,
+                 restore_filename=None, device=None, native_options=None):
+        if restore_filename is not None:
+            raise NotImplementedError('restore_filename is not supported by the GPU HydrationAnalysis')
+        # basic.py:41-51
+        if selection is None: raise AssertionError('No selection string.')
+        if structure is None: raise AssertionError('No structure file path.')
+        self._selection = selection
+        self._universe = _as_universe(structure, trajectories)
+        self._trajectory_slice = slice(start if isinstance(start, int) else None,
+                                       stop if isinstance(stop, int) else None, step)
+        self._mda_selection = self._universe.select_atoms(selection)
+        if not len(self._mda_selection): raise AssertionError('No atoms match the selection')
+        self._water = self._universe.select_atoms(WATER_DEFINITION)
+        cols = AtomColumns(self._universe)
+        self._n_atoms = cols.n_atoms
+        self._water_ids = list(_ids(cols, _np.asarray(self._water.indices), False))
+        self._water_ids_atomwise = list(_ids(cols, _np.asarray(self._water.indices), True))
+        self.initial_results = {}
+        self.filtered_results = {}
+        n_traj = len(self._universe.trajectory)
+        self._frame_indices = range(*self._trajectory_slice.indices(n_traj))
+        self.nb_frames = len(self._frame_indices)
+        self.applied_filters = {'resnames': None, 'segnames': None, 'shortest_paths': None, 'single_path': None,
+                                'occupancy': None, 'connected_component': None, 'shells': None,
+                                'avg_least_bonds': None, 'backbone': None}
+        self._device = device
+        self._native_options = dict(native_options or {})
+        self._ctx = None
+        self._cols = cols
+        self.last_run_stats = None
+
+    def _tables(self):
+        """hb_topology arrays: every selected atom is a selection point without entries, every water one entry."""
+        sel = _np.asarray(self._mda_selection.indices, dtype=_np.int64)
+        wat = _np.asarray(self._water.indices, dtype=_np.int64)
+        group_names, ent_group = _np.unique(_np.asarray(self._water_ids, dtype=object).astype(str), return_inverse=True) \
+            if len(wat) else (_np.zeros(0, dtype=str), _np.zeros(0, _np.int64))
+        n_sel, n_wat = len(sel), len(wat)
+        minus = _np.full(n_sel, -1, _np.int32)
+        t = dict(n_systems=1,
+                 sys_atom_off=_np.asarray([0, self._n_atoms], _np.int64),
+                 sys_sel_off=_np.asarray([0, n_sel], _np.int32), sys_wat_off=_np.asarray([0, n_wat], _np.int32),
+                 sel_atom=sel.astype(_np.int32), sel_don=minus, sel_acc=minus.copy(), sel_wat=minus.copy(),
+                 sel_bb=_np.zeros(n_sel, _np.uint8), wat_atom=wat.astype(_np.int32),
+                 wat_ent=_np.arange(n_wat, dtype=_np.int32),
+                 ent_resid=_np.asarray(self._cols.resids[wat], dtype=_np.int64).astype(_np.int32),
+                 ent_group=_np.asarray(ent_group, _np.int32), ent_residue=_np.asarray(ent_group, _np.int32),
+                 ent_h_off=_np.zeros(n_wat + 1, _np.int32), ent_h_atom=_np.zeros(0, _np.int32))
+        return t, [str(s) for s in group_names]
+
+    def _context(self):
+        if self._ctx is None:
+            self._ctx = _native.Context(0 if self._device is None else self._device)
+            for name, value in self._native_options.items():
+                self._ctx.set_option(name, value)
+        return self._ctx
+
+    def set_presence_around(self, around_distance, per_residue=False):
+        """hydration.py:71-107 (per_residue=False)."""
+        if per_residue:
+            raise NotImplementedError('set_presence_around(per_residue=True) is not supported')
+        result = {}
+        if len(self._water) and self.nb_frames:
+            ctx = self._context()
+            cached = self.__dict__.get("_packed")
+            if cached is None:
+                cached = self._packed = self._tables()
+            tables, group_names = cached
+            if getattr(ctx, "_uploaded", None) is not tables:
+                ctx.set_topology(tables)
+                ctx._uploaded = tables
+            ctx.set_params(1.0, float(around_distance), -1.0, False, False, _native.METHOD_WATER_PRESENCE)
+            ctx.begin(self.nb_frames)
+            block = max(1, min(self.nb_frames, int((256 << 20) // max(1, self._n_atoms * 12))))
+            for xyz in _frame_blocks(self._universe, self._frame_indices, block):
+                ctx.submit(xyz)
+            keys, words = ctx.results()
+            self.last_run_stats = ctx.timers()
+            if len(keys):
+                bits = _np.unpackbits(words.view(_np.uint8), axis=1, bitorder="little")[:, :self.nb_frames].astype(bool)
+                rows = {group_names[int(k)]: bits[i] for i, k in enumerate(keys)}
+                # the reference's dict grows in order of first appearance: frame, then water index (hydration.py:99-104)
+                index_of = {}
+                for i, w in enumerate(self._water_ids):
+                    index_of.setdefault(w, i)
+                order = sorted(rows, key=lambda w: (int(rows[w].argmax()), index_of[w]))
+                result = {w: rows[w] for w in order}
+        self.initial_results = result
+        self.filtered_results = result
+
+    def filter_occupancy(self, min_occupancy, use_filtered=True):     # hydration.py:109-115
+        results = self.filtered_results if use_filtered else self.initial_results
+        if len(results) == 0: raise AssertionError('nothing to filter!')
+        filtered_result = {key: results[key] for key in results if _np.mean(results[key]) > min_occupancy}
+        if self.applied_filters['occupancy'] != None:
+            self.applied_filters['occupancy'] = max(self.applied_filters['occupancy'], min_occupancy)
+        else:
+            self.applied_filters['occupancy'] = min_occupancy
+        self.filtered_results = filtered_result

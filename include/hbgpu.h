@@ -22,6 +22,8 @@
  *   hb_set_wires      <- WireAnalysis.set_water_wires, waterwire.py:191-317: the same neighbour search
  *                        (waterwire.py:200-248) feeds a per-frame breadth-first search over the water
  *                        network (waterwire.py:250-309); results are wire lengths per residue pair and frame
+ *   HB_METHOD_WATER_PRESENCE
+ *                     <- HydrationAnalysis.set_presence_around, hydration.py:71-107 (the same local-water test)
  *   hb_get_counts / hb_joint_occupancy / hb_get_frame_column
  *                     <- filter_occupancy, compute_joint_occupancy, _compute_graph_in_frame,
  *                        network.py:99-107, 369-376, 1186-1198 (on the packed matrix)
@@ -57,6 +59,10 @@ typedef enum {
 #define HB_METHOD_IN_SELECTION 0   /* HbondAnalysis.set_hbonds_in_selection, hbond.py:96 */
 #define HB_METHOD_WATER_AROUND 1   /* HbondAnalysis.set_hbonds_in_selection_and_water_around, hbond.py:232 */
 #define HB_METHOD_ION_CONTACTS 2   /* HbondAnalysis.set_add_ion_interactions, hbond.py:57-94 (needs hb_set_ions) */
+#define HB_METHOD_WATER_PRESENCE 3 /* HydrationAnalysis.set_presence_around, hydration.py:71-107 (per_residue=False): the
+                                      waters within around_radius of any selection point; one row per water, key =
+                                      ent_group of the water's entry (upper 32 bits 0). Selection points need no
+                                      entries (sel_don = sel_acc = sel_wat = -1); distance / angle are not used */
 
 #define HB_PBC_NONE 0              /* reference semantics: no periodic images */
 #define HB_PBC_ORTHO 1             /* opt-in minimum image, orthorhombic cell */
