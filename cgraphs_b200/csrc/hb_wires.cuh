@@ -48,7 +48,7 @@ struct WireCfg {
     unsigned* wbits;         // [n_cta][3][n_wat * cap_words]   seen / frontier / next
     unsigned* tbits;         // [n_cta][2][n_res * cap_words]   found / level accumulator
     int2* rlist;             // [n_cta][edge_cap]               the frame's edges in local indices
-    const int* status;       // status block: [2] fused_overflow, [3] pair_overflow, [6] wire_overflow
+    const int* status;       // status block: [2] fused_overflow, [3] pair_overflow, [6] wire_overflow, [7] frame-pairs overflow
 };
 
 __global__ void k_set_sink(EdgeSink* dst, EdgeSink v) { *dst = v; }
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
                                                            int edge_cap, long long frame0, int n_frames) {
     // an incomplete edge list (a capacity overflow somewhere in the search) would give wires that are too long:
     // the host re-runs the batch after growing whatever overflowed, so this launch does nothing
-    if (wc.status[2] | wc.status[3] | wc.status[6]) return;
+    if (wc.status[2] | wc.status[3] | wc.status[6] | wc.status[7]) return;
     const int tid = threadIdx.x, nt = blockDim.x;
     const int n_res = wc.n_res;
     int* wl_of = wc.wl_of + (size_t)blockIdx.x * wc.n_wat;

@@ -36,6 +36,7 @@
 
 #include "hb_general.cuh"
 #include "hb_fused.cuh"
+#include "hb_framepairs.cuh"
 #include "hb_finalize.cuh"
 #include "hb_wires.cuh"
 
@@ -96,6 +97,10 @@ struct hb_ctx {
     bool water_regular = false;       // water point i of every system is atom first + i * stride
     int water_stride = 0;
     bool presence = false;            // HB_METHOD_WATER_PRESENCE
+    // general path: pair search as one CTA per frame (hb_framepairs.cuh) while the frames fit
+    int opt_frame_pairs = 1;
+    int fp_level = 0;                 // 0: two CTAs per SM, 1: one CTA per SM, 2: does not fit - multi-kernel pair search
+    FramePairsCfg fp{};
     bool fused_active = false;
     double fused_unfit_around = -1.0; // around radius of a run whose frames did not fit the fused kernel's shared memory
     FusedCfg fc{};                    // (same topology): later runs with a shell at least as wide start on the general path
@@ -408,6 +413,7 @@ int hb_destroy(hb_ctx* ctx) {
 }
 
 int hb_set_option(hb_ctx* ctx, const char* name, int64_t value) {
+    if (ctx && name && !strcmp(name, "frame_pairs")) { ctx->opt_frame_pairs = value != 0; return HB_OK; }
     if (ctx && name && !strcmp(name, "lw_smem")) { ctx->opt_lw_smem = value != 0; return HB_OK; }
     if (ctx && name && !strcmp(name, "wire_edge_cap")) { ctx->opt_wire_edge_cap = value; return HB_OK; }
     if (ctx && name && !strcmp(name, "wire_smem_words")) { ctx->opt_wire_smem_words = value; return HB_OK; }
@@ -458,6 +464,7 @@ int hb_set_topology(hb_ctx* ctx, const hb_topology* t) {
     ctx->wire.d_ent_node = nullptr;
     ctx->fused_unfit_around = -1.0;
     ctx->fused_grow_hint = 0;
+    ctx->fp_level = 0;
     ctx->have_topo = false;       // (run allocations are kept: hb_begin compares everything that sizes them)
     int ns = t->n_systems;
     ctx->h_sys_atom_off.assign(t->sys_atom_off, t->sys_atom_off + ns + 1);
@@ -649,6 +656,7 @@ int hb_set_params(hb_ctx* ctx, const hb_params* p) {
         return fail(ctx, HB_ERR_ARG, "around_radius must be >= 0");
     if (p->pbc_mode != HB_PBC_NONE && p->pbc_mode != HB_PBC_ORTHO && p->pbc_mode != HB_PBC_TRICLINIC)
         return fail(ctx, HB_ERR_ARG, "unknown pbc_mode");
+    if (ctx->have_params && (p->around_radius != ctx->prm.around_radius || p->method != ctx->prm.method)) ctx->fp_level = 0;
     ctx->prm = *p;
     RunParams& r = ctx->rp;
     r.r2 = p->distance * p->distance;
@@ -864,6 +872,36 @@ static int grow_table(hb_ctx* ctx) {
     return HB_OK;
 }
 
+// shared-memory layout of k_frame_pairs for the current level; false when the selection alone does not fit
+static bool plan_frame_pairs(hb_ctx* ctx) {
+    if (!ctx->opt_frame_pairs || ctx->fp_level > 1) return false;
+    FramePairsCfg c{};
+    c.cell_cap = 8192;
+    c.pair_cap = 4096;
+    c.task_cap = 1536;
+    size_t off = (sizeof(FusedShared) + 15) & ~(size_t)15;
+    c.off_pairs = (unsigned)off; off += (size_t)c.pair_cap * 4;
+    c.off_tasks = (unsigned)off; off += (size_t)c.task_cap * 8;
+    c.off_flags = (unsigned)off; off += (size_t)FUSED_CONSUMERS * 4;
+    c.off_cells = (unsigned)off; off += (((size_t)c.cell_cap + 2) * 2 + 15) & ~(size_t)15;
+    c.off_pts = (unsigned)off;
+    const size_t budget = ctx->fp_level == 0 ? 113 * 1024 : 226 * 1024;
+    if (off + 16 * 64 > budget) return false;
+    long long np = (long long)((budget - off) / 16);
+    np = std::min<long long>(np, std::min<long long>((long long)ctx->max_sel + ctx->max_wat, 65535));
+    if (np < ctx->max_sel || np < 1) return false;
+    c.np_cap = (int)np;
+    c.smem_bytes = (unsigned)(off + (size_t)np * 16);
+    c.overflow = ctx->bt.n_keys + 7;
+    if (cudaFuncSetAttribute(k_frame_pairs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem_bytes) != cudaSuccess ||
+        cudaFuncSetAttribute(k_frame_pairs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    ctx->fp = c;
+    return true;
+}
+
 // the general path's per-batch scratch is allocated the first time that path runs
 static int ensure_scratch(hb_ctx* ctx) {
     if (!ctx->scratch_allocs.empty()) return HB_OK;
@@ -907,8 +945,9 @@ static int run_general_t(hb_ctx* ctx, BatchView bv) {
     { KTimer t(ctx, KC_GRID); k_grid_setup<PBC><<<(nf + 127) / 128, 128, 0, st>>>(bv, tp, rp); }
     // only the cells each frame's grid really has are cleared (the capacity is sized for the worst case)
     dim3 gzero(16, nf);
+    const bool frame_pairs = !ctx->presence && plan_frame_pairs(ctx);
     if (wa) { KTimer t(ctx, KC_INIT); k_zero_cells<<<gzero, 256, 0, st>>>(bv, 1); }
-    { KTimer t(ctx, KC_INIT); k_zero_cells<<<gzero, 256, 0, st>>>(bv, 2); }
+    if (!frame_pairs) { KTimer t(ctx, KC_INIT); k_zero_cells<<<gzero, 256, 0, st>>>(bv, 2); }
     if (wa && bv.max_sel > 0 && bv.max_wat > 0) {
         { KTimer t(ctx, KC_COUNT); k_count<PBC><<<gsel, 256, 0, st>>>(bv, tp, 1); }
         { KTimer t(ctx, KC_SCAN); k_scan<<<nf, 1024, 0, st>>>(bv, 1); }
@@ -939,7 +978,10 @@ static int run_general_t(hb_ctx* ctx, BatchView bv) {
         return HB_OK;
     }
     int maxp = bv.max_sel + (wa ? bv.max_wat : 0);
-    if (maxp > 0) {
+    if (frame_pairs && maxp > 0) {
+        KTimer t(ctx, KC_PAIRS);
+        k_frame_pairs<PBC><<<nf, FUSED_CONSUMERS, ctx->fp.smem_bytes, st>>>(bv, tp, rp, ctx->bt_run, ctx->fp);
+    } else if (maxp > 0) {
         // selection + local waters: the kernels stride over the points a frame really has (far fewer than all waters)
         dim3 gall(std::min((maxp + 255) / 256, 48), nf);
         { KTimer t(ctx, KC_COUNT); k_count<PBC><<<gall, 256, 0, st>>>(bv, tp, 2); }
@@ -1126,7 +1168,8 @@ static int full_verify(hb_ctx* ctx) {
         memcpy(st, ctx->h_verify, sizeof(st));
         memcpy(ctx->last_status, st, 6 * sizeof(int));
         bool overflow = st[1] != 0, fused_overflow = st[2] != 0, pair_overflow = st[3] != 0, wire_overflow = st[6] != 0;
-        if (!overflow && !fused_overflow && !pair_overflow && !wire_overflow && (long long)st[0] * 2 <= ctx->table_cap) {
+        const bool fp_overflow = st[7] != 0;
+        if (!overflow && !fused_overflow && !pair_overflow && !wire_overflow && !fp_overflow && (long long)st[0] * 2 <= ctx->table_cap) {
             for (auto& sl : ctx->slots) sl.busy = false;
             return HB_OK;
         }
@@ -1160,7 +1203,11 @@ static int full_verify(hb_ctx* ctx) {
             ctx->wire.edge_cap *= 2;
             CK(cudaMemsetAsync(ctx->bt.n_keys + 6, 0, sizeof(int), ctx->s_compute));
         }
-        if (overflow || fused_overflow || pair_overflow || wire_overflow) {
+        if (fp_overflow) {         // a frame did not fit k_frame_pairs: one CTA per SM, then the multi-kernel pair search
+            ctx->fp_level++;
+            CK(cudaMemsetAsync(ctx->bt.n_keys + 7, 0, sizeof(int), ctx->s_compute));
+        }
+        if (overflow || fused_overflow || pair_overflow || wire_overflow || fp_overflow) {
             CK(cudaMemsetAsync(ctx->bt.overflow, 0, 3 * sizeof(int), ctx->s_compute));
             for (auto& sl : ctx->slots)
                 if (sl.busy) {
@@ -1180,7 +1227,7 @@ static int acquire_slot(hb_ctx* ctx, int k) {
     hb_ctx::Slot& sl = ctx->slots[k];
     if (!sl.busy) return HB_OK;
     CK(cudaEventSynchronize(ctx->ev_done[k]));
-    int nkeys = ctx->h_status[8 * k], overflow = ctx->h_status[8 * k + 1] | ctx->h_status[8 * k + 2] | ctx->h_status[8 * k + 3] | ctx->h_status[8 * k + 6];
+    int nkeys = ctx->h_status[8 * k], overflow = ctx->h_status[8 * k + 1] | ctx->h_status[8 * k + 2] | ctx->h_status[8 * k + 3] | ctx->h_status[8 * k + 6] | ctx->h_status[8 * k + 7];
     if (overflow || (long long)nkeys * 2 > ctx->table_cap) return full_verify(ctx);
     sl.busy = false;
     return HB_OK;
@@ -1622,7 +1669,7 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
         CK(cudaStreamSynchronize(st));
         memcpy(ctx->last_status, ctx->h_verify, 6 * sizeof(int));
         n = ctx->last_status[0];
-        const bool bad = ctx->last_status[1] || ctx->last_status[2] || ctx->last_status[3] || ctx->h_verify[6] ||
+        const bool bad = ctx->last_status[1] || ctx->last_status[2] || ctx->last_status[3] || ctx->h_verify[6] || ctx->h_verify[7] ||
                          (long long)n * 2 > ctx->table_cap;
         if (!bad) {
             for (auto& sl : ctx->slots) sl.busy = false;

@@ -18,7 +18,8 @@ def main():
     s = synth.make_system(2500, 20, 4, dimensions_kind="tric")
     u = s.universe(5)
     n = 0
-    for opts in ({"fused": 1}, {"fused": 0}, {"fused": 0, "pair_buf_bytes": 0}, {"fused": 1, "force_radix_sort": 1}):
+    for opts in ({"fused": 1}, {"fused": 0}, {"fused": 0, "frame_pairs": 0}, {"fused": 0, "frame_pairs": 0, "pair_buf_bytes": 0},
+                 {"fused": 1, "force_radix_sort": 1}):
         for sel, method, ca, pbc in [("protein", "water_around", True, False), ("protein or resname TIP3", "water_around", True, False),
                                      ("protein", "in_selection", False, False), ("protein", "water_around", True, True)]:
             h = HbondAnalysis(sel, u, check_angle=ca, native_options=opts, pbc=pbc,

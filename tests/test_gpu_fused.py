@@ -42,7 +42,8 @@ def test_fused_and_general_match_oracle(seed):
         assert_same_results(g.initial_results, ref, "general %s %s %s" % (sel, method, ca))
         assert g.last_run_stats["fused_frames"] == 0
         assert f.last_run_stats["fused_frames"] == 9, f.last_run_stats
-        assert f.last_run_stats["n_launches"] < g.last_run_stats["n_launches"]
+        if f.last_run_stats["fused_fallbacks"] == 0:      # (a capacity retry launches the fused kernel again)
+            assert f.last_run_stats["n_launches"] < g.last_run_stats["n_launches"]
 
 
 @pytest.mark.parametrize("cut", [180.0, 179.0, 120.0])
@@ -266,8 +267,8 @@ def test_general_path_pair_buffer_overflow_and_fallback():
     u = s.universe(24)
     sel = "protein or resname TIP3"
     ref = _port(u, sel, "water_around").initial_results
-    for opts in ({"fused": 0}, {"fused": 0, "pair_buf_bytes": 0}, {"fused": 0, "pair_buf_bytes": 1 << 16},
-                 {"fused": 0, "pair_buf_bytes": 4096}):
+    for opts in ({"fused": 0}, {"fused": 0, "frame_pairs": 0}, {"fused": 0, "frame_pairs": 0, "pair_buf_bytes": 0},
+                 {"fused": 0, "frame_pairs": 0, "pair_buf_bytes": 1 << 16}, {"fused": 0, "frame_pairs": 0, "pair_buf_bytes": 4096}):
         got = _run(u, sel, "water_around", opts)
         assert_same_results(got.initial_results, ref, str(opts))
         assert got.last_run_stats["fused_frames"] == 0
@@ -286,3 +287,17 @@ def test_other_cutoffs_and_angles(distance, around, cut):
         for fused in (1, 0):
             got = _run(u, sel, "water_around", {"fused": fused}, around=around, **kw)
             assert_same_results(got.initial_results, ref, "d=%s a=%s cut=%s %s fused=%d" % (distance, around, cut, sel, fused))
+
+
+@pytest.mark.parametrize("n_atoms", [16000, 60000])
+def test_frame_pairs_capacity_levels(n_atoms):
+    """General path, pair search as one CTA per frame (k_frame_pairs): frames with more points than two CTAs per SM
+    can hold move to one CTA per SM, larger ones to the multi-kernel pair search - same bits every way."""
+    s = synth.make_system(n_atoms, 50, 1234)
+    u = s.universe(3)
+    sel = "protein or resname TIP3"
+    ref = _port(u, sel, "water_around").initial_results
+    assert len(ref) > 1000
+    for opts in ({"fused": 0}, {"fused": 0, "frame_pairs": 0}):
+        got = _run(u, sel, "water_around", opts)
+        assert_same_results(got.initial_results, ref, str(opts))

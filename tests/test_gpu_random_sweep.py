@@ -20,7 +20,7 @@ def _case(rng):
         check_angle=bool(rng.integers(2)), residuewise=bool(rng.integers(2)),
         distance=float(np.round(rng.uniform(2.6, 4.4), 2)), around=float(np.round(rng.uniform(1.0, 7.5), 2)),
         cut_angle=float(np.round(rng.uniform(15.0, 110.0), 1)), excl_bb=bool(rng.integers(2)),
-        pbc=bool(rng.integers(2)), fused=int(rng.integers(2)), extra=bool(rng.integers(2)))
+        pbc=bool(rng.integers(2)), fused=int(rng.integers(2)), extra=bool(rng.integers(2)), frame_pairs=int(rng.integers(2)))
 
 
 @pytest.mark.parametrize("block", range(10))
@@ -48,7 +48,7 @@ def test_random_parameter_sweep(block):
         edge = min(hbond_port.box_rows(s.dimensions).diagonal())
         if 2.0 * max(c["distance"], c["around"]) >= 0.98 * edge:
             c["pbc"] = False                 # cut-off too close to half the cell for the minimum-image mode
-        h = HbondAnalysis(c["selection"], u, pbc=c["pbc"], native_options={"fused": c["fused"]}, **kw)
+        h = HbondAnalysis(c["selection"], u, pbc=c["pbc"], native_options={"fused": c["fused"], "frame_pairs": c["frame_pairs"]}, **kw)
         if c["method"] == "in_selection":
             h.set_hbonds_in_selection(c["excl_bb"])
         else:

@@ -79,7 +79,7 @@ def test_wires_capacity_overflows_are_retried():
     ref = wire_lists(_port(u, "protein", 4, **kw).wire_lengths)
     assert len(ref) > 50
     for options in ({"wire_edge_cap": 256}, {"table_capacity": 16}, {"wire_edge_cap": 300, "table_capacity": 32, "fused": 0},
-                    {"fused_lw_cap": 64}, {"wire_smem_words": 0}, {"wire_smem_words": 700}):
+                    {"fused_lw_cap": 64}, {"wire_smem_words": 0}, {"wire_smem_words": 700}, {"fused": 0, "frame_pairs": 0}):
         got = _gpu(u, "protein", 4, options=options, **kw)
         assert_same_wires(wire_lists(got.wire_lengths), ref, str(options))
 
