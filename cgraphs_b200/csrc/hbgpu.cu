@@ -99,7 +99,7 @@ struct hb_ctx {
     bool presence = false;            // HB_METHOD_WATER_PRESENCE
     // general path: pair search as one CTA per frame (hb_framepairs.cuh) while the frames fit
     int opt_frame_pairs = 1;
-    int fp_level = 0;                 // 0: two CTAs per SM, 1: one CTA per SM, 2: does not fit - multi-kernel pair search
+    int fp_level = 0;                 // 0: use it, 1: some frame did not fit - multi-kernel pair search
     FramePairsCfg fp{};
     bool fused_active = false;
     double fused_unfit_around = -1.0; // around radius of a run whose frames did not fit the fused kernel's shared memory
@@ -874,18 +874,18 @@ static int grow_table(hb_ctx* ctx) {
 
 // shared-memory layout of k_frame_pairs for the current level; false when the selection alone does not fit
 static bool plan_frame_pairs(hb_ctx* ctx) {
-    if (!ctx->opt_frame_pairs || ctx->fp_level > 1) return false;
+    if (!ctx->opt_frame_pairs || ctx->fp_level > 0) return false;
     FramePairsCfg c{};
-    c.cell_cap = 8192;
-    c.pair_cap = 4096;
-    c.task_cap = 1536;
-    size_t off = (sizeof(FusedShared) + 15) & ~(size_t)15;
+    c.cell_cap = 16384;
+    c.pair_cap = 8192;
+    c.task_cap = 4096;
+    size_t off = (sizeof(FpShared) + 15) & ~(size_t)15;
     c.off_pairs = (unsigned)off; off += (size_t)c.pair_cap * 4;
     c.off_tasks = (unsigned)off; off += (size_t)c.task_cap * 8;
-    c.off_flags = (unsigned)off; off += (size_t)FUSED_CONSUMERS * 4;
+    c.off_flags = (unsigned)off; off += (size_t)FP_THREADS * 4;
     c.off_cells = (unsigned)off; off += (((size_t)c.cell_cap + 2) * 2 + 15) & ~(size_t)15;
     c.off_pts = (unsigned)off;
-    const size_t budget = ctx->fp_level == 0 ? 113 * 1024 : 226 * 1024;
+    const size_t budget = 226 * 1024;
     if (off + 16 * 64 > budget) return false;
     long long np = (long long)((budget - off) / 16);
     np = std::min<long long>(np, std::min<long long>((long long)ctx->max_sel + ctx->max_wat, 65535));
@@ -980,7 +980,7 @@ static int run_general_t(hb_ctx* ctx, BatchView bv) {
     int maxp = bv.max_sel + (wa ? bv.max_wat : 0);
     if (frame_pairs && maxp > 0) {
         KTimer t(ctx, KC_PAIRS);
-        k_frame_pairs<PBC><<<nf, FUSED_CONSUMERS, ctx->fp.smem_bytes, st>>>(bv, tp, rp, ctx->bt_run, ctx->fp);
+        k_frame_pairs<PBC><<<nf, FP_THREADS, ctx->fp.smem_bytes, st>>>(bv, tp, rp, ctx->bt_run, ctx->fp);
     } else if (maxp > 0) {
         // selection + local waters: the kernels stride over the points a frame really has (far fewer than all waters)
         dim3 gall(std::min((maxp + 255) / 256, 48), nf);
@@ -1203,7 +1203,7 @@ static int full_verify(hb_ctx* ctx) {
             ctx->wire.edge_cap *= 2;
             CK(cudaMemsetAsync(ctx->bt.n_keys + 6, 0, sizeof(int), ctx->s_compute));
         }
-        if (fp_overflow) {         // a frame did not fit k_frame_pairs: one CTA per SM, then the multi-kernel pair search
+        if (fp_overflow) {         // a frame did not fit k_frame_pairs: back to the multi-kernel pair search
             ctx->fp_level++;
             CK(cudaMemsetAsync(ctx->bt.n_keys + 7, 0, sizeof(int), ctx->s_compute));
         }
