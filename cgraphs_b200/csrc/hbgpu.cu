@@ -178,6 +178,7 @@ struct hb_ctx {
         std::vector<void*> allocs;
         WireCfg cfg{};
     } wire;
+    bool lw_attr_set[2] = {false, false};
     int opt_lw_smem = 1;                          // general path: stage the selection grid in shared memory when it fits
     long long opt_wire_edge_cap = 0;              // 0: automatic
     long long opt_wire_smem_words = WIRE_SMEM_WORDS;
@@ -417,12 +418,6 @@ int hb_set_option(hb_ctx* ctx, const char* name, int64_t value) {
     if (ctx && name && !strcmp(name, "lw_smem")) { ctx->opt_lw_smem = value != 0; return HB_OK; }
     if (ctx && name && !strcmp(name, "wire_edge_cap")) { ctx->opt_wire_edge_cap = value; return HB_OK; }
     if (ctx && name && !strcmp(name, "wire_smem_words")) { ctx->opt_wire_smem_words = value; return HB_OK; }
-    if (ctx && name && !strcmp(name, "wire_ctas_per_sm")) {
-        ctx->opt_wire_ctas_per_sm = 1;      // (kept for compatibility: the kernel is one CTA per SM)
-        free_list(ctx->wire.allocs);
-        ctx->wire.d_edges = nullptr;
-        return HB_OK;
-    }
     if (!ctx || !name) return HB_ERR_ARG;
     std::string n(name);
     if (n == "batch_bytes") ctx->opt_batch_bytes = std::max<long long>(value, 1 << 20);
@@ -956,10 +951,9 @@ static int run_general_t(hb_ctx* ctx, BatchView bv) {
         if (ctx->opt_lw_smem && lw_smem <= 96 * 1024) {
             // selection grid staged in shared memory, 2048 waters per block
             const int per_block = 2048;
-            static bool attr_set[2] = {false, false};
-            if (!attr_set[PBC ? 1 : 0]) {
+            if (!ctx->lw_attr_set[PBC ? 1 : 0]) {      // per context: the attribute belongs to the context's device
                 CK(cudaFuncSetAttribute(k_local_water_smem<PBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-                attr_set[PBC ? 1 : 0] = true;
+                ctx->lw_attr_set[PBC ? 1 : 0] = true;
             }
             dim3 gw((bv.max_wat + per_block - 1) / per_block, nf);
             KTimer t(ctx, KC_LOCAL);

@@ -168,6 +168,10 @@ int hb_set_option(hb_ctx* ctx, const char* name, int64_t value);
            "fused": 0 = never use the one-CTA-per-frame kernel; "fused_lw_cap" / "fused_cell_cap": its
            shared-memory capacities (0 = automatic); "fused_pair_cap", "fused_stages", "fused_prefetch", "fused_wait_ns",
            "fused_batch_frames"; "pair_buf_bytes": batch-wide pair buffer of the general kernels (0 = per-point kernel);
+           "frame_pairs": 0 = never run the general path's pair search as one CTA per frame (hb_framepairs.cuh);
+           "lw_smem": 0 = keep the selection grid of the general path's local-water test in global memory;
+           "wire_edge_cap": H-bond pairs per frame the edge lists of the water-wire mode start with (doubles on
+           overflow), "wire_smem_words": shared-memory budget of its bit sets (test hook);
            "copy_ranges": 0 = always copy whole frames; "stage_threads": host threads that move pageable frames
            into the pinned staging buffers (default min(16, cores)); "force_radix_sort" (test hook);
            "compute_stream": a cudaStream_t of the caller on which every kernel of the context is launched, so
