@@ -107,9 +107,21 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
         __syncthreads();
         // local waters and active residues (those with a residue-water edge) get dense indices; direct bonds
         // (acceptor entry, donor entry) are recorded on the way
-        for (int i = tid; i < ne; i += nt) {
-            const int2 e = E[i];
-            const int n0 = wc.ent_node[e.x], n1 = wc.ent_node[e.y];
+        for (int i0 = tid; i0 < ne; i0 += 4 * nt) {           // four edges per thread in flight
+            int2 e4[4];
+            int n04[4], n14[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) e4[u] = (i0 + u * nt < ne) ? E[i0 + u * nt] : make_int2(-1, -1);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                n04[u] = e4[u].x >= 0 ? wc.ent_node[e4[u].x] : 0;
+                n14[u] = e4[u].x >= 0 ? wc.ent_node[e4[u].y] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+            if (e4[u].x < 0) continue;
+            const int2 e = e4[u];
+            const int n0 = n04[u], n1 = n14[u];
             if (n0 >= n_res && atomicCAS(&wl_of[n0 - n_res], -1, -2) == -1) lw[atomicAdd(&s_nlw, 1)] = n0 - n_res;
             if (n1 >= n_res && atomicCAS(&wl_of[n1 - n_res], -1, -2) == -1) lw[atomicAdd(&s_nlw, 1)] = n1 - n_res;
             if ((n0 >= n_res) != (n1 >= n_res)) {
@@ -126,6 +138,7 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
                     atomicMax((unsigned long long*)(row + wc.nb4), ~packed);
                 }
             }
+            }
         }
         __syncthreads();
         phase(0);
@@ -135,12 +148,32 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
         __syncthreads();
         // the edges in local indices: residue-water (active residue, local water) from the front of R,
         // water-water (local water, local water) from its back
-        for (int i = tid; i < ne; i += nt) {
-            const int2 e = E[i];
-            const int n0 = wc.ent_node[e.x], n1 = wc.ent_node[e.y];
-            const bool w0 = n0 >= n_res, w1 = n1 >= n_res;
-            if (w0 && w1) R[edge_cap - 1 - atomicAdd(&s_nww, 1)] = make_int2(wl_of[n0 - n_res], wl_of[n1 - n_res]);
-            else if (w0 != w1) R[atomicAdd(&s_nsw, 1)] = make_int2(ar_of[w0 ? n1 : n0], wl_of[(w0 ? n0 : n1) - n_res]);
+        for (int i0 = tid; i0 < ne; i0 += 4 * nt) {
+            int2 e4[4];
+            int n04[4], n14[4], a4[4], b4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) e4[u] = (i0 + u * nt < ne) ? E[i0 + u * nt] : make_int2(-1, -1);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                n04[u] = e4[u].x >= 0 ? wc.ent_node[e4[u].x] : 0;
+                n14[u] = e4[u].x >= 0 ? wc.ent_node[e4[u].y] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                     // local ids of both ends (water / active residue)
+                a4[u] = b4[u] = -1;
+                if (e4[u].x < 0) continue;
+                const bool w0 = n04[u] >= n_res, w1 = n14[u] >= n_res;
+                if (!w0 && !w1) continue;
+                a4[u] = w0 ? wl_of[n04[u] - n_res] : ar_of[n04[u]];
+                b4[u] = w1 ? wl_of[n14[u] - n_res] : ar_of[n14[u]];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (a4[u] < 0) continue;
+                const bool w0 = n04[u] >= n_res, w1 = n14[u] >= n_res;
+                if (w0 && w1) R[edge_cap - 1 - atomicAdd(&s_nww, 1)] = make_int2(a4[u], b4[u]);
+                else R[atomicAdd(&s_nsw, 1)] = w0 ? make_int2(b4[u], a4[u]) : make_int2(a4[u], b4[u]);
+            }
         }
         __syncthreads();
         phase(1);
@@ -215,12 +248,25 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
                     for (int i = tid; i < nw; i += nt) nxt[i] = 0;
                     if (tid == 0) s_any = 0;
                     __syncthreads();
-                    for (int i = tid; i < nww * words; i += nt) {
-                        const int q = i / words, j = i - q * words;
-                        const int2 e = WW[q];
-                        const unsigned va = cur[(size_t)e.x * words + j], vc = cur[(size_t)e.y * words + j];
-                        if (va) atomicOr(&nxt[(size_t)e.y * words + j], va);
-                        if (vc) atomicOr(&nxt[(size_t)e.x * words + j], vc);
+                    // (one edge per thread, its words in an inner loop: the edge list is read from L2 once per level and
+                    // the loads of a thread's edges are issued back to back)
+                    for (int q0 = tid; q0 < nww; q0 += 4 * nt) {
+                        int2 e[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) e[u] = (q0 + u * nt < nww) ? WW[q0 + u * nt] : make_int2(-1, -1);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            if (e[u].x < 0) continue;
+                            const unsigned* ca = cur + (size_t)e[u].x * words;
+                            const unsigned* cc = cur + (size_t)e[u].y * words;
+                            unsigned* na = nxt + (size_t)e[u].x * words;
+                            unsigned* nc = nxt + (size_t)e[u].y * words;
+                            for (int j = 0; j < words; ++j) {
+                                const unsigned va = ca[j], vc = cc[j];
+                                if (va) atomicOr(&nc[j], va);
+                                if (vc) atomicOr(&na[j], vc);
+                            }
+                        }
                     }
                     __syncthreads();
                     phase(6);
