@@ -51,3 +51,24 @@ def test_gpu_reads_dcd_records_directly(tmp_path, pbc):
     sl = HbondAnalysis("protein", pdb, dcd, start=2, stop=8, step=1)
     sl.set_hbonds_in_selection_and_water_around(3.5)
     assert {k: v.tobytes() for k, v in sl.initial_results.items()} == {k: v[2:8].tobytes() for k, v in ref.items() if v[2:8].any()}
+
+
+@pytest.mark.gpu
+def test_gpu_wires_and_presence_from_files(tmp_path):
+    """WireAnalysis / HydrationAnalysis constructed from a PDB + DCD pair like cgraphs does (file paths, frame records
+    decoded on the device for the wires)."""
+    from cgraphs_b200.mdhbond import HydrationAnalysis, WireAnalysis
+    from oracle import hbond_port
+    from tests.helpers import assert_same_wires, wire_lists
+    s, xyz, pdb, dcd = _files(tmp_path, n_frames=9)
+    u = s.universe(9)
+    kw = dict(additional_donors=['N'], additional_acceptors=['O'])
+    wa = WireAnalysis("protein", pdb, dcd, **kw)
+    wa.set_water_wires(max_water=3)
+    ref = hbond_port.run_wires(u, "protein", max_water=3, **kw)
+    assert len(ref.wire_lengths) > 5
+    assert_same_wires(wire_lists(wa.wire_lengths), wire_lists(ref.wire_lengths))
+    ha = HydrationAnalysis("protein", pdb, dcd)
+    ha.set_presence_around(4.0)
+    refp = hbond_port.run_presence_around(u, "protein", 4.0)
+    assert {k: v.tobytes() for k, v in ha.initial_results.items()} == {k: v.tobytes() for k, v in refp.items()}
