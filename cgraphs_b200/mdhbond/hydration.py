@@ -97,8 +97,17 @@ class HydrationAnalysis(object):
             ctx.set_params(1.0, float(around_distance), -1.0, False, False, _native.METHOD_WATER_PRESENCE)
             ctx.begin(self.nb_frames)
             block = max(1, min(self.nb_frames, int((256 << 20) // max(1, self._n_atoms * 12))))
-            for xyz in _frame_blocks(self._universe, self._frame_indices, block):
-                ctx.submit(xyz)
+            frames = getattr(self._universe.trajectory, "frames", None)
+            fi = self._frame_indices
+            if hasattr(frames, "planar_block") and fi.step == 1:
+                # trajectory file records go to the device as they are and are decoded (interleaved) there
+                for i in range(fi.start, fi.stop, block):
+                    j = min(fi.stop, i + block)
+                    raw, stride, xo, yo, zo = frames.planar_block(i, j)
+                    ctx.submit_planar(raw, stride, xo, yo, zo, self._n_atoms, j - i)
+            else:
+                for xyz in _frame_blocks(self._universe, fi, block):
+                    ctx.submit(xyz)
             keys, words = ctx.results()
             self.last_run_stats = ctx.timers()
             if len(keys):

@@ -124,3 +124,29 @@ def test_wide_shells_general_path_local_water_kernels():
             hba = HbondAnalysis("protein", u, native_options={"fused": 0, "lw_smem": lw_smem}, **kw)
             hba.set_hbonds_in_selection_and_water_around(around)
             assert {k: v.tobytes() for k, v in hba.initial_results.items()} == {k: v.tobytes() for k, v in ref.items()}, around
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_wires_random_sweep(block):
+    """Small random systems x random parameters (selection, max_water, criteria, direct bonds, kernel options)."""
+    rng = np.random.default_rng(7300 + block)
+    for case in range(6):
+        n_atoms, n_res = int(rng.integers(700, 3500)), int(rng.integers(4, 30))
+        s = synth.make_system(n_atoms, n_res, int(rng.integers(0, 10 ** 6)), n_chains=int(rng.integers(1, 3)),
+                              dimensions_kind=["ortho", "tric"][int(rng.integers(2))])
+        u = s.universe(int(rng.integers(1, 6)))
+        ca = bool(rng.integers(2))
+        kw = dict(check_angle=ca, add_donors_without_hydrogen=not ca, distance=float(np.round(rng.uniform(2.8, 4.0), 2)),
+                  cut_angle=float(np.round(rng.uniform(30.0, 100.0), 1)))
+        if rng.integers(2):
+            kw.update(additional_donors=['N'], additional_acceptors=['O'])
+        sel = ["protein", "protein or resname TIP3", "segid PA"][int(rng.integers(3))]
+        mw, direct = int(rng.integers(0, 7)), bool(rng.integers(2))
+        options = {"fused": int(rng.integers(2)), "frame_pairs": int(rng.integers(2)), "lw_smem": int(rng.integers(2))}
+        try:
+            ref = _port(u, sel, mw, direct, **kw)
+        except AssertionError:
+            continue                                    # (selection without donors / acceptors)
+        got = _gpu(u, sel, mw, direct, options, **kw)
+        assert_same_wires(wire_lists(got.wire_lengths), wire_lists(ref.wire_lengths),
+                          "block %d case %d: %s max_water=%d %s %s" % (block, case, sel, mw, kw, options))
