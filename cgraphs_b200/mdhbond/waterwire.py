@@ -74,15 +74,15 @@ class WireAnalysis(HbondAnalysis):
                  start=None, stop=None, step=1, additional_donors=[], additional_acceptors=[], exclude_donors=[],
                  exclude_acceptors=[], ions=[], check_angle=True, residuewise=True,
                  add_donors_without_hydrogen=False, restore_filename=None, **kw):
+        self.hashs = {}
+        self.hash_table = {}
+        self.wire_lengths = {}
         super().__init__(selection=selection, structure=structure, trajectories=trajectories, distance=distance,
                          cut_angle=cut_angle, start=start, stop=stop, step=step, additional_donors=additional_donors,
                          additional_acceptors=additional_acceptors, exclude_donors=exclude_donors,
                          exclude_acceptors=exclude_acceptors, ions=ions, check_angle=check_angle,
                          residuewise=residuewise, add_donors_without_hydrogen=add_donors_without_hydrogen,
                          restore_filename=restore_filename, **kw)
-        self.hashs = {}
-        self.hash_table = {}
-        self.wire_lengths = {}
         if restore_filename is not None:
             return
         top = self._topology

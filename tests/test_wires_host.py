@@ -110,3 +110,20 @@ def test_sharded_wires_equal_single_process(world, tmp_path):
     for r in range(world):
         with open(os.path.join(str(tmp_path), "rank%d.pkl" % r), "rb") as f:
             assert_same_wires(pickle.load(f), ref, "rank %d of %d" % (r, world))
+
+
+def test_wire_analysis_dump_and_restore(tmp_path):
+    """basic.py:71-86 as cgraphs uses it for wires (proteingraphanalyser.py:499-509): results survive a dump / restore
+    (no GPU needed: the results are planted)."""
+    from cgraphs_b200.mdhbond import WireAnalysis
+    u = _system().universe(3)
+    wa = WireAnalysis("protein", u)
+    wa.wire_lengths = {"PA-SER-1:PA-THR-2": np.array([1.0, np.inf, 0.0])}
+    wa._set_results({k: v != np.inf for k, v in wa.wire_lengths.items()})
+    f = str(tmp_path / "wires.pickle")
+    wa.dump_to_file(f)
+    wb = WireAnalysis(restore_filename=f)
+    assert wb.nb_frames == 3 and list(wb.wire_lengths) == list(wa.wire_lengths)
+    assert np.array_equal(wb.wire_lengths["PA-SER-1:PA-THR-2"], wa.wire_lengths["PA-SER-1:PA-THR-2"])
+    assert wb.compute_average_water_per_wire() == {"PA-SER-1:PA-THR-2": 0.5}
+    assert wb.filtered_graph.number_of_edges() == 1
