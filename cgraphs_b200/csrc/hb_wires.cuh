@@ -194,8 +194,8 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
             unsigned* found = in_smem ? nxt + nw : wc.tbits + (size_t)blockIdx.x * 2 * tstride;
             unsigned* acc = in_smem ? found + ntw : found + tstride;
             for (int base = 0; base < nar; base += chunk) {
-                for (int i = tid; i < nw; i += nt) cur[i] = 0;
-                for (int i = tid; i < ntw; i += nt) found[i] = 0;
+                for (int i = tid; i < nw; i += nt) { cur[i] = 0; nxt[i] = 0; }
+                for (int i = tid; i < ntw; i += nt) { found[i] = 0; acc[i] = 0; }
                 __syncthreads();
                 // depth 1: the waters bonded to each source of this chunk
                 for (int i = tid; i < nsw; i += nt) {
@@ -206,8 +206,7 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
                 __syncthreads();
                 for (int i = tid; i < nw; i += nt) seen[i] = cur[i];
                 phase(2);
-                for (int k = 1; k <= wc.max_water; ++k) {
-                    for (int i = tid; i < ntw; i += nt) acc[i] = 0;
+                for (int k = 1; k <= wc.max_water; ++k) {        // (acc and nxt are zero here: their readers clear them)
                     if (tid == 0) s_nq = 0;
                     __syncthreads();
                     // sources whose frontier (depth k) holds a water next to residue t
@@ -220,7 +219,10 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
                     __syncthreads();
                     phase(3);
                     for (int i = tid; i < ntw; i += nt) {
-                        unsigned nb = acc[i] & ~found[i];
+                        const unsigned av = acc[i];
+                        if (!av) continue;
+                        acc[i] = 0;
+                        unsigned nb = av & ~found[i];
                         if (!nb) continue;
                         found[i] |= nb;
                         const int t = i / words, j = i - t * words;
@@ -245,9 +247,7 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
                     phase(5);
                     if (k == wc.max_water) break;
                     // one step along the water-water edges
-                    for (int i = tid; i < nw; i += nt) nxt[i] = 0;
-                    if (tid == 0) s_any = 0;
-                    __syncthreads();
+                    if (tid == 0) s_any = 0;        // (read two barriers ago, written after the next one)
                     // (one edge per thread, its words in an inner loop: the edge list is read from L2 once per level and
                     // the loads of a thread's edges are issued back to back)
                     for (int q0 = tid; q0 < nww; q0 += 4 * nt) {
@@ -272,7 +272,9 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
                     phase(6);
                     int any = 0;
                     for (int i = tid; i < nw; i += nt) {
-                        const unsigned n = nxt[i] & ~seen[i];
+                        const unsigned nv = nxt[i];
+                        if (nv) nxt[i] = 0;
+                        const unsigned n = nv & ~seen[i];
                         seen[i] |= n;
                         cur[i] = n;
                         any |= n != 0;
