@@ -166,7 +166,7 @@ struct hb_ctx {
     // water wires (hb_wires.cuh)
     struct Wire {
         bool on = false;
-        const int* d_ent_node = nullptr;          // lives in topo_allocs
+        int* d_ent_node = nullptr;                // owned here (hb_set_wires may be called before every run)
         int n_res = 0, n_wat_nodes = 1, max_water = 0, allow_direct = 1;
         int nb4 = 0;                              // row words holding the per-frame bytes
         int2* d_edges = nullptr;
@@ -399,6 +399,7 @@ int hb_destroy(hb_ctx* ctx) {
     drain_events(ctx);
     free_run(ctx);
     free_list(ctx->topo_allocs);
+    if (ctx->wire.d_ent_node) cudaFree(ctx->wire.d_ent_node);
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     for (int k = 0; k < 2; ++k) { cudaEventDestroy(ctx->ev_copied[k]); cudaEventDestroy(ctx->ev_done[k]); }
     cudaEventDestroy(ctx->ev_run0);
@@ -456,6 +457,7 @@ int hb_set_topology(hb_ctx* ctx, const hb_topology* t) {
     free_list(ctx->topo_allocs);
     ctx->ions = IonTable{nullptr, nullptr, 0};
     ctx->wire.on = false;
+    if (ctx->wire.d_ent_node) cudaFree(ctx->wire.d_ent_node);
     ctx->wire.d_ent_node = nullptr;
     ctx->fused_unfit_around = -1.0;
     ctx->fused_grow_hint = 0;
@@ -620,8 +622,10 @@ int hb_set_wires(hb_ctx* ctx, const int32_t* ent_node, int32_t n_ent, int32_t n_
     }
     ctx->wire.n_wat_nodes = n_wat_nodes;
     CK(cudaSetDevice(ctx->device));
-    int rc;
-    if ((rc = upload(ctx, ent_node, (size_t)n_ent, &ctx->wire.d_ent_node, ctx->topo_allocs))) return rc;
+    if (ctx->wire.d_ent_node) cudaFree(ctx->wire.d_ent_node);
+    ctx->wire.d_ent_node = nullptr;
+    CK(cudaMalloc((void**)&ctx->wire.d_ent_node, std::max<size_t>((size_t)n_ent * sizeof(int), 16)));
+    if (n_ent) CK(cudaMemcpy(ctx->wire.d_ent_node, ent_node, (size_t)n_ent * sizeof(int), cudaMemcpyHostToDevice));
     ctx->wire.n_res = n_res;
     ctx->wire.max_water = max_water;
     ctx->wire.allow_direct = allow_direct_bonds != 0;
