@@ -243,6 +243,32 @@ def wires_leg(args, system, d_xyz, local_rank, peak, bytes_frame):
            "n_residue_pairs": int(nb), "edges_per_frame": tm["pairs_emitted"] / nf, "launches_per_pass": int(tm["n_launches"]),
            "kernel_ms_per_pass": {k: round(v, 3) for k, v in kernels.items()},
            "hbm_frac": bytes_frame * value / 1e9 / peak}
+    if not args.no_e2e:
+        # the same pass from pinned host memory (host -> device copies and the result read back inside the timed region)
+        pin = _native.PinnedBuffer((nf, na, 3))
+        try:
+            host = pin.array
+            chunk = max(1, (1 << 30) // (na * 12))
+            for s0 in range(0, nf, chunk):
+                host[s0:s0 + chunk] = d_xyz[s0:min(s0 + chunk, nf)].cpu().numpy()
+
+            def one_pass_host():
+                ctx.begin(nf)
+                ctx.submit_raw(host.ctypes.data, na, nf)
+                return ctx.results()
+
+            one_pass_host()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                keys, words = one_pass_host()
+            torch.cuda.synchronize()
+            e2e_ms = 1000.0 * (time.perf_counter() - t0) / 3
+            out["e2e"] = {"value": nf / (e2e_ms / 1000.0), "unit": "frames/s", "ms_per_pass": e2e_ms,
+                          "h2d_bytes_per_step": int(ctx.timers()["h2d_bytes"]),
+                          "d2h_bytes_per_step": int(keys.nbytes + words.nbytes), "host_memory": "pinned"}
+        finally:
+            pin.free()
     if not args.no_cpu:
         from oracle import hbond_port                   # CPU baseline leg: the validated port on a bounded sample
         n_cpu = 4
