@@ -608,24 +608,36 @@ def run_wires(universe, selection, max_water=5, allow_direct_bonds=True, backend
 # HydrationAnalysis.set_presence_around (hydration.py:71-107), per_residue=False:
 # the waters (water group, basic.py:62) within `around_distance` of ANY atom of the selection, per frame.
 # ------------------------------------------------------------------------------------------------
-def run_presence_around(universe, selection, around_distance, start=None, stop=None, step=1, backend='kdtree'):
-    """Returns {water id: bool[nb_frames]} like HydrationAnalysis.initial_results after set_presence_around."""
+def run_presence_around(universe, selection, around_distance, start=None, stop=None, step=1, backend='kdtree',
+                        per_residue=False):
+    """Returns {water id: bool[nb_frames]} like HydrationAnalysis.initial_results after set_presence_around;
+    per_residue=True (hydration.py:88-94): keys 'selection-atom residue id:water id' for every (selected atom, water)
+    pair within the distance, the reversed key when that one already exists."""
     topo = universe.topology
     sel = universe.select_atoms(selection).indices
     if len(sel) == 0:
         raise AssertionError('No atoms match the selection')
     waters = universe.select_atoms(WATER_DEFINITION).indices
     water_ids = [_id(topo, i, False) for i in waters]
+    sel_ids = [_id(topo, i, False) for i in sel]
     sl = slice(start if isinstance(start, int) else None, stop if isinstance(stop, int) else None, step)
     frame_indices = list(universe.trajectory.frame_indices(sl))
     frames = universe.trajectory.frames
     result = {}
     for col, f in enumerate(frame_indices):
         pos = np.asarray(frames.frame(f), dtype=np.float32)
-        _, wj = ball_pairs(pos[sel], pos[waters], float(around_distance), backend)
-        for w in np.unique(wj):
-            row = result.get(water_ids[w])
+        si, wj = ball_pairs(pos[sel], pos[waters], float(around_distance), backend)
+        if per_residue:
+            order = np.lexsort((wj, si))                       # rows come selection atom by selection atom
+            keys = []
+            for i, j in zip(si[order].tolist(), wj[order].tolist()):
+                a, b = sel_ids[i], water_ids[j]
+                keys.append(b + ':' + a if (b + ':' + a) in result else a + ':' + b)
+        else:
+            keys = [water_ids[w] for w in np.unique(wj)]
+        for key in keys:
+            row = result.get(key)
             if row is None:
-                row = result[water_ids[w]] = np.zeros(len(frame_indices), dtype=bool)
+                row = result[key] = np.zeros(len(frame_indices), dtype=bool)
             row[col] = True
     return result

@@ -60,5 +60,32 @@ def test_gpu_presence_membrane_like():
     ha.set_presence_around(5.0)
     assert len(ref) > 100
     _same(ha.initial_results, ref)
+
+
+@pytest.mark.reference
+def test_port_presence_per_residue_equals_reference():
+    from oracle import hbond_port, ref_harness
+    ref = ref_harness.load_reference()
+    u = _system().universe(4)
+    for sel, r in (("protein", 3.5), ("segid PA and name CA", 5.0), ("protein or resid 40", 4.0)):
+        ha = ref.HydrationAnalysis(sel, u)
+        ha.set_presence_around(r, per_residue=True)
+        got = hbond_port.run_presence_around(u, sel, r, per_residue=True)
+        assert {k: v.tobytes() for k, v in got.items()} == {k: v.tobytes() for k, v in ha.initial_results.items()}
+
+
+@pytest.mark.gpu
+def test_gpu_presence_per_residue_equals_oracle():
+    """per_residue=True: 'residue id:water id' keys from the distance-only pair search (selected atoms as entries)."""
+    from cgraphs_b200.mdhbond import HydrationAnalysis
+    from oracle import hbond_port
+    u = _system().universe(6)
+    for sel, r, kw in (("protein", 3.5, {}), ("segid PA and name CA", 5.0, {}), ("protein", 7.25, dict(start=1, stop=6, step=2))):
+        ref = hbond_port.run_presence_around(u, sel, r, per_residue=True, **kw)
+        assert len(ref) > 20
+        for options in ({}, {"fused": 0}, {"fused": 0, "frame_pairs": 0}):
+            ha = HydrationAnalysis(sel, u, native_options=options, **kw)
+            ha.set_presence_around(r, per_residue=True)
+            assert {k: v.tobytes() for k, v in ha.initial_results.items()} == {k: v.tobytes() for k, v in ref.items()}, (sel, r, options)
     with pytest.raises(NotImplementedError):
-        ha.set_presence_around(5.0, per_residue=True)
+        HydrationAnalysis("protein or resname TIP3", u).set_presence_around(3.5, per_residue=True)
