@@ -89,3 +89,36 @@ def test_gpu_presence_per_residue_equals_oracle():
             assert {k: v.tobytes() for k, v in ha.initial_results.items()} == {k: v.tobytes() for k, v in ref.items()}, (sel, r, options)
     with pytest.raises(NotImplementedError):
         HydrationAnalysis("protein or resname TIP3", u).set_presence_around(3.5, per_residue=True)
+
+
+def _golden_runs():
+    import json
+    import os
+    from tests.helpers import GOLDEN_DIR
+    with open(os.path.join(GOLDEN_DIR, "hydration_traj.json")) as f:
+        return json.load(f)["runs"]
+
+
+@pytest.mark.parametrize("i", range(6))
+def test_port_presence_equals_golden(i):
+    """Golden vectors of the live reference (tests/golden/make_golden_hydration.py) - travel to the GPU box."""
+    from oracle import hbond_port
+    from tests.helpers import lists_to_results, load_golden_wires
+    u, _ = load_golden_wires()
+    r = _golden_runs()[i]
+    got = hbond_port.run_presence_around(u, r["selection"], r["around"], per_residue=r["per_residue"], **r["kwargs"])
+    want = lists_to_results(r["results"], r["nb_frames"])
+    assert {k: v.tobytes() for k, v in got.items()} == {k: v.tobytes() for k, v in want.items()}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", range(6))
+def test_gpu_presence_equals_golden(i):
+    from cgraphs_b200.mdhbond import HydrationAnalysis
+    from tests.helpers import lists_to_results, load_golden_wires
+    u, _ = load_golden_wires()
+    r = _golden_runs()[i]
+    ha = HydrationAnalysis(r["selection"], u, **r["kwargs"])
+    ha.set_presence_around(r["around"], per_residue=r["per_residue"])
+    want = lists_to_results(r["results"], r["nb_frames"])
+    assert {k: v.tobytes() for k, v in ha.initial_results.items()} == {k: v.tobytes() for k, v in want.items()}
