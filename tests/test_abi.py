@@ -80,3 +80,28 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/hbgpu.h is the binding surface for any host language: it must compile as C99 on its own, and a C
+    translation unit that references every entry point must link against libhbgpu.so."""
+    import re
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    hb_build.build()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "hbgpu.h")).read()
+    names = sorted(set(re.findall(r"\b(hb_[a-z_0-9]+)\s*\(", header)))
+    assert "hb_set_wires" in names and "hb_submit_frames" in names
+    src = tmp_path / "use_abi.c"
+    src.write_text('#include "hbgpu.h"\n#include <stdio.h>\nint main(void) {\n  const void* f[] = {%s};\n'
+                   '  printf("%%d %%d\\n", (int)(sizeof f / sizeof f[0]), (int)sizeof(hb_timers));\n  return f[0] == 0;\n}\n'
+                   % ", ".join("(const void*)%s" % n for n in names))
+    exe = tmp_path / "use_abi"
+    lib_dir = os.path.join(root, "cgraphs_b200", "csrc")
+    res = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(src), "-o", str(exe),
+                          "-L", lib_dir, "-lhbgpu", "-Wl,-rpath," + lib_dir], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
