@@ -11,6 +11,8 @@ if ROOT not in sys.path:
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
     config.addinivalue_line("markers", "reference: needs the live reference under /root/reference")
+    # the unmodified reference calls numpy functions that are deprecated in numpy 2 (np.in1d in waterwire.py)
+    config.addinivalue_line("filterwarnings", "ignore:.*in1d.*:DeprecationWarning")
 
 
 def _has_gpu():
