@@ -44,7 +44,7 @@ def read_pdb(path):
 
     Residue numbers above 9999 wrap in the file; a new residue starts whenever (segid, resid, resname) changes,
     and wrapped numbers are unwrapped per segment so that residues stay distinct."""
-    names, resnames, resids, segids, xyz = [], [], [], [], []
+    names, resnames, resids, segids, xyz, types = [], [], [], [], [], []
     dims = None
     with open(path) as f:
         for line in f:
@@ -59,6 +59,14 @@ def read_pdb(path):
                 seg = line[72:76].strip() if len(line) >= 76 else ""
                 segids.append(seg if seg else (line[21].strip() or "SYSTEM"))
                 xyz.append((float(line[30:38]), float(line[38:46]), float(line[46:54])))
+                # atom type like MDAnalysis' PDB parser: the element columns 77-78 when present, else guessed from the
+                # name (leading digits dropped: '1HB' is a hydrogen) - the reference's donor rule looks at it
+                # (helpfunctions.py:57-66)
+                el = line[76:78].strip().upper() if len(line) >= 78 else ""
+                if not el:
+                    stripped = names[-1].lstrip("0123456789")
+                    el = stripped[:1].upper()
+                types.append(el)
             elif rec.startswith("ENDMDL"):
                 break
     resids = np.asarray(resids, dtype=np.int64)
@@ -72,7 +80,7 @@ def read_pdb(path):
             offset += 10000
         out[i] = r + offset
         prev_seg, prev_raw = seg, r
-    return Topology(names, resnames, out, segids), np.asarray(xyz, dtype=np.float32), dims
+    return Topology(names, resnames, out, segids, types=types), np.asarray(xyz, dtype=np.float32), dims
 
 
 # ------------------------------------------------------------------------------------------------

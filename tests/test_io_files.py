@@ -72,3 +72,17 @@ def test_gpu_wires_and_presence_from_files(tmp_path):
     ha.set_presence_around(4.0)
     refp = hbond_port.run_presence_around(u, "protein", 4.0)
     assert {k: v.tobytes() for k, v in ha.initial_results.items()} == {k: v.tobytes() for k, v in refp.items()}
+
+
+def test_pdb_atom_types(tmp_path):
+    """Element columns win, names with leading digits are hydrogens (the donor rule reads the type)."""
+    p = tmp_path / "t.pdb"
+    p.write_text(
+        "ATOM      1  N   SER A   1       0.000   0.000   0.000  1.00  0.00           N\n"
+        "ATOM      2 1HB  SER A   1       1.000   0.000   0.000  1.00  0.00\n"
+        "ATOM      3  HG  SER A   1       0.000   1.000   0.000  1.00  0.00           H\n"
+        "HETATM    4  O   HOH A   2       3.000   0.000   0.000  1.00  0.00           O\n"
+        "END\n")
+    topo, xyz, dims = read_pdb(str(p))
+    assert list(topo.types) == ["N", "H", "H", "O"] and list(topo.names) == ["N", "1HB", "HG", "O"]
+    assert dims is None and xyz.shape == (4, 3)
