@@ -8,6 +8,8 @@ interleaved on the device.
 
 * :func:`read_pdb` / :func:`write_pdb`  - topology columns (names, resnames, resids, segids), one coordinate set,
   ``CRYST1`` cell
+* :func:`read_psf` / :func:`write_psf`  - CHARMM / NAMD / X-PLOR PSF topologies (what cgraphs' trajectory workflow
+  passes as ``structure``, ``proteingraphanalyser.py:472-476``); coordinates then come from the trajectory
 * :class:`DCDFrames` / :func:`write_dcd` - frame source over a DCD file (memory mapped), with the planar view
   ``planar_block`` the native path uses, and the unit cell of every frame
 * :func:`universe_from_files` - ``Universe`` (cgraphs_b200.universe) from a PDB and an optional DCD
@@ -84,6 +86,52 @@ def read_pdb(path):
 
 
 # ------------------------------------------------------------------------------------------------
+# PSF (CHARMM / NAMD / X-PLOR; standard and EXT column widths - the atom records are read field by field)
+# ------------------------------------------------------------------------------------------------
+def read_psf(path):
+    """Topology of the !NATOM section: segid, resid, resname, atom name and the PSF atom type (MDAnalysis' PSF parser
+    exposes that type string as ``atom.type``; the reference's hydrogen rule reads it, helpfunctions.py:57-66)."""
+    names, resnames, resids, segids, types = [], [], [], [], []
+    with open(path) as f:
+        first = f.readline()
+        if not first.startswith("PSF"):
+            raise ValueError("%s: not a PSF file" % path)
+        n_atoms = None
+        for line in f:
+            if "!NATOM" in line:
+                n_atoms = int(line.split()[0])
+                break
+        if n_atoms is None:
+            raise ValueError("%s: no !NATOM section" % path)
+        for _ in range(n_atoms):
+            parts = f.readline().split()
+            if len(parts) < 6:
+                raise ValueError("%s: truncated atom record" % path)
+            segids.append(parts[1])
+            digits = parts[2].lstrip("-")
+            k = 0
+            while k < len(digits) and digits[k].isdigit():
+                k += 1
+            resids.append(int(parts[2][:len(parts[2]) - len(digits) + k]))      # '12A' (insertion code) -> 12
+            resnames.append(parts[3])
+            names.append(parts[4])
+            types.append(parts[5])
+    return Topology(names, resnames, np.asarray(resids, dtype=np.int64), segids, types=types)
+
+
+def write_psf(path, topology, types=None):
+    """Minimal EXT PSF with the !NATOM section only (tests, and conversion of generated systems)."""
+    types = topology.types if types is None else types
+    with open(path, "w") as f:
+        f.write("PSF EXT\n\n%10d !NTITLE\n REMARKS written by cgraphs_b200.io\n\n%10d !NATOM\n" % (1, topology.n_atoms))
+        for i in range(topology.n_atoms):
+            f.write("%10d %-8s %-8d %-8s %-8s %-6s %10.6f %13.4f %11d\n" % (
+                i + 1, str(topology.segids[i]), int(topology.resids[i]), str(topology.resnames[i]), str(topology.names[i]),
+                str(types[i]) or "X", 0.0, 1.0, 0))
+        f.write("\n%10d !NBOND: bonds\n\n" % 0)
+
+
+# ------------------------------------------------------------------------------------------------
 # DCD (CHARMM / NAMD, little endian, 32-bit record markers)
 # ------------------------------------------------------------------------------------------------
 def write_dcd(path, frames, dimensions=None):
@@ -157,6 +205,9 @@ class DCDFrames:
         raw = self._map[start * self.frame_stride:stop * self.frame_stride]
         return raw, self.frame_stride, self.x_off, self.y_off, self.z_off
 
+    def planar_count(self, start, stop):
+        return stop - start
+
     def block(self, start, stop):
         raw = np.asarray(self._map[start * self.frame_stride:stop * self.frame_stride]).reshape(stop - start, self.frame_stride)
         out = np.empty((stop - start, self.n_atoms, 3), dtype=np.float32)
@@ -179,12 +230,70 @@ class DCDFrames:
         return [float(a), float(b), float(c), ang[0], ang[1], ang[2]]
 
 
+class ConcatDCDFrames:
+    """Several DCD files of one system read as one trajectory (MDAnalysis' ChainReader for the list of trajectories
+    cgraphs passes, ``proteingraphanalyser.py:472-476``). ``planar_block`` hands out frame records of ONE file, so a
+    block that would cross a file boundary ends there (callers advance by the number of frames they got)."""
+
+    def __init__(self, paths):
+        self.parts = [DCDFrames(p) for p in paths]
+        if not self.parts:
+            raise ValueError("no trajectory files")
+        self.n_atoms = self.parts[0].n_atoms
+        for p, part in zip(paths, self.parts):
+            if part.n_atoms != self.n_atoms:
+                raise ValueError("%s has %d atoms, %s has %d" % (p, part.n_atoms, paths[0], self.n_atoms))
+        self.offsets = np.concatenate([[0], np.cumsum([len(p) for p in self.parts])]).astype(np.int64)
+        self.n_frames = int(self.offsets[-1])
+        self.has_cell = all(p.has_cell for p in self.parts)
+
+    def __len__(self):
+        return self.n_frames
+
+    def _locate(self, i):
+        k = int(np.searchsorted(self.offsets, i, side="right") - 1)
+        return k, int(i - self.offsets[k])
+
+    def planar_block(self, start, stop):
+        k, a = self._locate(start)
+        b = min(int(stop - self.offsets[k]), len(self.parts[k]))
+        return self.parts[k].planar_block(a, b)
+
+    def planar_count(self, start, stop):
+        """Frames `planar_block(start, stop)` returns (fewer than stop - start at a file boundary)."""
+        k, a = self._locate(start)
+        return min(int(stop - self.offsets[k]), len(self.parts[k])) - a
+
+    def block(self, start, stop):
+        out = np.empty((stop - start, self.n_atoms, 3), dtype=np.float32)
+        i = start
+        while i < stop:
+            n = self.planar_count(i, stop)
+            k, a = self._locate(i)
+            out[i - start:i - start + n] = self.parts[k].block(a, a + n)
+            i += n
+        return out
+
+    def frame(self, i):
+        k, a = self._locate(int(i))
+        return self.parts[k].frame(a)
+
+    def dimensions_of(self, i):
+        k, a = self._locate(int(i))
+        return self.parts[k].dimensions_of(a)
+
+
 def universe_from_files(structure, trajectory=None):
-    """``Universe`` from a PDB file and an optional DCD trajectory (without one, the PDB coordinates are the only frame)."""
-    topo, xyz, dims = read_pdb(structure)
+    """``Universe`` from a PDB or PSF file and a DCD trajectory (a PDB alone: its coordinates are the only frame)."""
+    if str(structure).lower().endswith(".psf"):
+        if trajectory is None:
+            raise ValueError("%s: a PSF topology holds no coordinates, a trajectory is needed" % structure)
+        topo, xyz, dims = read_psf(structure), None, None
+    else:
+        topo, xyz, dims = read_pdb(structure)
     if trajectory is None:
         return Universe(topo, xyz[None], dims)
-    frames = DCDFrames(trajectory)
+    frames = ConcatDCDFrames(list(trajectory)) if isinstance(trajectory, (list, tuple)) else DCDFrames(trajectory)
     if frames.n_atoms != topo.n_atoms:
         raise ValueError("%s has %d atoms, %s has %d" % (trajectory, frames.n_atoms, structure, topo.n_atoms))
     d0 = frames.dimensions_of(0) if frames.n_frames else None

@@ -56,14 +56,14 @@ def _as_universe(structure, trajectories):
         try:
             import MDAnalysis as _MDAnalysis
         except ImportError:
-            # no MDAnalysis: the built-in readers cover PDB structures and DCD trajectories (cgraphs_b200/io.py)
+            # no MDAnalysis: the built-in readers cover PDB / PSF structures and DCD trajectories (cgraphs_b200/io.py)
             import os as _os
             from ..io import universe_from_files
             traj = trajectories[0] if isinstance(trajectories, (list, tuple)) and len(trajectories) == 1 else trajectories
             ext = _os.path.splitext(str(structure))[1].lower()
-            if ext != ".pdb" or (traj is not None and (isinstance(traj, (list, tuple)) or
-                                                       _os.path.splitext(str(traj))[1].lower() != ".dcd")):
-                raise ImportError("without MDAnalysis only a .pdb structure with at most one .dcd trajectory can be "
+            trajs = [] if traj is None else (list(traj) if isinstance(traj, (list, tuple)) else [traj])
+            if ext not in (".pdb", ".psf") or any(_os.path.splitext(str(t))[1].lower() != ".dcd" for t in trajs):
+                raise ImportError("without MDAnalysis only .pdb / .psf structures with .dcd trajectories can be "
                                   "read; pass a Universe object instead")
             return universe_from_files(structure, traj)
         return _MDAnalysis.Universe(structure, trajectories) if trajectories is not None else _MDAnalysis.Universe(structure)
@@ -342,11 +342,13 @@ class HbondAnalysis(object):
             sub = fi[lo:hi]
             if hasattr(frames, "planar_block") and isinstance(sub, range) and sub.step == 1:
                 # trajectory file records go to the device as they are and are decoded (interleaved) there
-                for i in range(sub.start, sub.stop, block):
-                    j = min(sub.stop, i + block)
+                i = sub.start
+                while i < sub.stop:
+                    j = i + frames.planar_count(i, min(sub.stop, i + block))     # (a block ends at a file boundary)
                     raw, stride, xo, yo, zo = frames.planar_block(i, j)
                     box = _frame_boxes(self._universe, range(i, j)) if pbc_mode else None
                     ctx.submit_planar(raw, stride, xo, yo, zo, self._n_atoms, j - i, box=box)
+                    i = j
             else:
                 for xyz in _frame_blocks(self._universe, sub, block):
                     box = _frame_boxes(self._universe, fi[done:done + len(xyz)]) if pbc_mode else None

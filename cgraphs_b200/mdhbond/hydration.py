@@ -111,10 +111,12 @@ class HydrationAnalysis(object):
         fi = self._frame_indices
         if hasattr(frames, "planar_block") and fi.step == 1:
             # trajectory file records go to the device as they are and are decoded (interleaved) there
-            for i in range(fi.start, fi.stop, block):
-                j = min(fi.stop, i + block)
+            i = fi.start
+            while i < fi.stop:
+                j = i + frames.planar_count(i, min(fi.stop, i + block))          # (a block ends at a file boundary)
                 raw, stride, xo, yo, zo = frames.planar_block(i, j)
                 ctx.submit_planar(raw, stride, xo, yo, zo, self._n_atoms, j - i)
+                i = j
         else:
             for xyz in _frame_blocks(self._universe, fi, block):
                 ctx.submit(xyz)

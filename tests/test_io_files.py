@@ -86,3 +86,65 @@ def test_pdb_atom_types(tmp_path):
     topo, xyz, dims = read_pdb(str(p))
     assert list(topo.types) == ["N", "H", "H", "O"] and list(topo.names) == ["N", "1HB", "HG", "O"]
     assert dims is None and xyz.shape == (4, 3)
+
+
+def test_psf_and_several_dcd_files(tmp_path):
+    """What cgraphs' trajectory workflow passes: a PSF topology and a list of DCD files (proteingraphanalyser.py:472-476)."""
+    from cgraphs_b200.io import ConcatDCDFrames, read_psf, write_psf
+    s = synth.make_system(1800, 16, 7)
+    xyz = s.frames(0, 11)
+    psf = str(tmp_path / "sys.psf")
+    write_psf(psf, s.topology)
+    topo = read_psf(psf)
+    t = s.topology
+    assert list(topo.names) == list(t.names) and list(topo.resnames) == list(t.resnames)
+    assert list(topo.segids) == list(t.segids) and np.array_equal(topo.resids, t.resids) and list(topo.types) == list(t.types)
+    parts = [(0, 4), (4, 5), (5, 11)]
+    dcds = []
+    for k, (a, b) in enumerate(parts):
+        p = str(tmp_path / ("part%d.dcd" % k))
+        write_dcd(p, xyz[a:b], s.dimensions)
+        dcds.append(p)
+    fr = ConcatDCDFrames(dcds)
+    assert len(fr) == 11 and np.array_equal(fr.block(0, 11), xyz) and np.array_equal(fr.frame(4), xyz[4])
+    assert fr.planar_count(2, 9) == 2 and fr.planar_count(4, 9) == 1 and fr.planar_count(5, 9) == 4
+    raw, stride, xo, yo, zo = fr.planar_block(5, 9)
+    assert len(raw) == 4 * stride
+    assert np.array_equal(np.asarray(raw[xo:xo + 4 * fr.n_atoms]).view("<f4"), xyz[5][:, 0])
+    u = universe_from_files(psf, dcds)
+    assert len(u.trajectory) == 11
+    # the drop-in classes take the same arguments (constructor only: no GPU here) and see the same topology as the oracle
+    from cgraphs_b200.mdhbond import WireAnalysis
+    from oracle import hbond_port
+    wa = WireAnalysis("protein", psf, dcds)
+    assert wa.nb_frames == 11
+    pt = hbond_port.PortTopology(s.universe(11), "protein")
+    assert wa._nb_donors == pt.nD and wa._nb_acceptors == pt.nA and list(wa._all_ids) == list(pt.all_ids)
+    with pytest.raises(ValueError):
+        universe_from_files(psf)
+
+
+@pytest.mark.gpu
+def test_gpu_psf_and_several_dcd_files(tmp_path):
+    """PSF + a list of DCD files through the planar path: blocks end at file boundaries."""
+    from cgraphs_b200.io import write_psf
+    from cgraphs_b200.mdhbond import HbondAnalysis, WireAnalysis
+    from oracle import hbond_port
+    from tests.helpers import assert_same_wires, wire_lists
+    s = synth.make_system(3200, 25, 61, dimensions_kind="tric")
+    xyz = s.frames(0, 11)
+    psf = str(tmp_path / "sys.psf")
+    write_psf(psf, s.topology)
+    dcds = []
+    for k, (a, b) in enumerate([(0, 4), (4, 5), (5, 11)]):
+        p = str(tmp_path / ("part%d.dcd" % k))
+        write_dcd(p, xyz[a:b], s.dimensions)
+        dcds.append(p)
+    u = s.universe(11)
+    hba = HbondAnalysis("protein", psf, dcds)
+    hba.set_hbonds_in_selection_and_water_around(3.5)
+    assert_same_results(hba.initial_results, hbond_port.run(u, "protein", "water_around", around=3.5).initial_results)
+    kw = dict(additional_donors=['N'], additional_acceptors=['O'])
+    wa = WireAnalysis("protein", psf, dcds, **kw)
+    wa.set_water_wires(max_water=3)
+    assert_same_wires(wire_lists(wa.wire_lengths), wire_lists(hbond_port.run_wires(u, "protein", max_water=3, **kw).wire_lengths))
