@@ -329,7 +329,7 @@ class AtomGroup:
         return self._u.topology.resindices[self.indices]
 
     def select_atoms(self, sel):
-        mask = _Selector(self._u.topology).evaluate(sel)
+        mask = _Selector(self._u.topology, self._u).evaluate(sel)
         keep = np.unique(self.indices[mask[self.indices]])
         return AtomGroup(keep, self._u)
 
@@ -353,21 +353,29 @@ class Universe:
         self.dimensions = dimensions
 
     def select_atoms(self, sel):
-        mask = _Selector(self.topology).evaluate(sel)
+        mask = _Selector(self.topology, self).evaluate(sel)
         return AtomGroup(np.nonzero(mask)[0], self)
 
 
 # ------------------------------------------------------------------------------------------------
-# selection mini-language: protein / all / resname / name / segid / type / resid / and / or / not / ()
+# selection mini-language: protein / backbone / nucleic / water / all / resname / name / segid / type / resid (a:b, a-b,
+# a to b) / index / bynum / byres / around R <sel> (first frame) / and / or / not / ()
 # precedence not > and > or, several values after a keyword are OR-ed (as MDAnalysis does)
 # ------------------------------------------------------------------------------------------------
 _TOKEN = re.compile(r"\(|\)|[^\s()]+")
-_KEYWORDS = {"and", "or", "not", "protein", "all", "resname", "name", "segid", "type", "resid", "resnum", "(", ")"}
+_KEYWORDS = {"and", "or", "not", "protein", "all", "resname", "name", "segid", "type", "resid", "resnum", "(", ")",
+             "backbone", "nucleic", "water", "index", "bynum", "byres", "around", "chainID", "chainid"}
+# MDAnalysis' residue-name tables (core/selection.py): water and nucleic acids
+WATER_RESNAMES = {"H2O", "HOH", "OH2", "HHO", "OHH", "TIP", "T3P", "T4P", "T5P", "SOL", "WAT", "TIP2", "TIP3", "TIP4"}
+NUCLEIC_RESNAMES = {"ADE", "URA", "CYT", "GUA", "THY", "DA", "DC", "DG", "DT", "RA", "RU", "RG", "RC", "A", "T", "U", "C", "G",
+                    "DA5", "DC5", "DG5", "DT5", "DA3", "DC3", "DG3", "DT3", "RA5", "RU5", "RG5", "RC5", "RA3", "RU3", "RG3", "RC3"}
+BACKBONE_NAMES = {"N", "CA", "C", "O"}
 
 
 class _Selector:
-    def __init__(self, topology):
+    def __init__(self, topology, universe=None):
         self.t = topology
+        self.u = universe
 
     def evaluate(self, sel):
         self.tokens = _TOKEN.findall(sel)
@@ -405,6 +413,25 @@ class _Selector:
         if self._peek() == "not":
             self._next()
             return ~self._not()
+        if self._peek() == "byres":             # every atom of the residues touched by the following selection
+            self._next()
+            inner = self._not()
+            hit = np.zeros(self.t.n_residues, dtype=bool)
+            hit[self.t.resindices[inner]] = True
+            return hit[self.t.resindices]
+        if self._peek() == "around":            # atoms within R of the following selection (first frame), not the selection itself
+            self._next()
+            radius = float(self._next())
+            inner = self._not()
+            if self.u is None:
+                raise ValueError("'around' needs coordinates")
+            from scipy.spatial import cKDTree
+            pos = np.asarray(self.u.trajectory.frames.frame(0), dtype=np.float32)
+            m = np.zeros(self.t.n_atoms, dtype=bool)
+            if inner.any():
+                near = cKDTree(pos).query_ball_tree(cKDTree(pos[inner]), radius)
+                m = np.fromiter((len(x) > 0 for x in near), dtype=bool, count=self.t.n_atoms)
+            return m & ~inner
         return self._atom()
 
     def _values(self):
@@ -440,6 +467,26 @@ class _Selector:
             return np.ones(t.n_atoms, dtype=bool)
         if tok == "protein":
             return np.fromiter((r in PROTEIN_RESNAMES for r in t.resnames), dtype=bool, count=t.n_atoms)
+        if tok == "backbone":
+            prot = np.fromiter((r in PROTEIN_RESNAMES for r in t.resnames), dtype=bool, count=t.n_atoms)
+            return prot & np.fromiter((n in BACKBONE_NAMES for n in t.names), dtype=bool, count=t.n_atoms)
+        if tok == "nucleic":
+            return np.fromiter((r in NUCLEIC_RESNAMES for r in t.resnames), dtype=bool, count=t.n_atoms)
+        if tok == "water":
+            return np.fromiter((r in WATER_RESNAMES for r in t.resnames), dtype=bool, count=t.n_atoms)
+        if tok in ("index", "bynum"):
+            m = np.zeros(t.n_atoms, dtype=bool)
+            shift = 1 if tok == "bynum" else 0          # bynum is 1-based, both ranges are inclusive
+            for v in self._values():
+                mm = re.match(r"^(\d+)(?:[:\-](\d+))?$", v)
+                if not mm:
+                    raise ValueError("bad %s range %r" % (tok, v))
+                lo = int(mm.group(1)) - shift
+                hi = (int(mm.group(2)) if mm.group(2) is not None else int(mm.group(1))) - shift
+                m[max(lo, 0):hi + 1] = True
+            return m
+        if tok in ("chainID", "chainid"):               # (the built-in readers keep the chain id in segids)
+            return self._match(t.segids, self._values())
         if tok == "resname":
             return self._match(t.resnames, self._values())
         if tok == "name":
@@ -450,7 +497,14 @@ class _Selector:
             return self._match(t.types, self._values())
         if tok in ("resid", "resnum"):
             m = np.zeros(t.n_atoms, dtype=bool)
-            for v in self._values():
+            vals = self._values()
+            k = 0
+            while k < len(vals):
+                v = vals[k]
+                if k + 2 < len(vals) and vals[k + 1] == "to":      # 'resid 1 to 5'
+                    v = v + ":" + vals[k + 2]
+                    k += 2
+                k += 1
                 mm = re.match(r"^(-?\d+)(?:[:\-](-?\d+))?$", v)
                 if not mm:
                     raise ValueError("bad resid range %r" % v)
