@@ -7,6 +7,14 @@ from cgraphs_b200.io import DCDFrames, read_pdb, universe_from_files, write_dcd,
 from tests.helpers import assert_same_results
 
 
+@pytest.fixture(autouse=True)
+def _no_mdanalysis(monkeypatch):
+    """These tests exercise the built-in readers: hide MDAnalysis (absent in this image; the live-reference harness of
+    other tests installs a stub module under that name)."""
+    import sys
+    monkeypatch.setitem(sys.modules, "MDAnalysis", None)
+
+
 def _files(tmp_path, n_frames=7, kind="tric"):
     s = synth.make_system(3200, 25, 61, dimensions_kind=kind)
     xyz = s.frames(0, n_frames)
