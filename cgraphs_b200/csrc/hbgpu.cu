@@ -188,6 +188,7 @@ struct hb_ctx {
     // trajectory mode: atom ranges [begin, end) that hold every atom the kernels read; the rest of a frame
     // (inert atoms) is never copied to the device. Empty = copy whole frames.
     std::vector<std::pair<long long, long long>> copy_ranges;
+    std::vector<unsigned char> atom_used;     // single-system topologies: 1 = some kernel reads this atom's coordinates
     int opt_copy_ranges = 1;
     int opt_stage_threads = 8;        // host threads that copy pageable frames into the pinned staging buffer
     int trace = 0;
@@ -296,6 +297,25 @@ static void parallel_frames(int nf, size_t bytes_per_frame, int max_threads, F c
         th.emplace_back([=]() { copy(a, b); });
     }
     for (auto& x : th) x.join();
+}
+
+// Trajectory mode: atom ranges [begin, end) that cover every atom marked in ctx->atom_used; holes shorter than 4096
+// atoms (48 kB) are copied along. Left empty (= copy whole frames) when the ranges would not save at least 10 %.
+static void build_copy_ranges(hb_ctx* ctx) {
+    ctx->copy_ranges.clear();
+    const std::vector<unsigned char>& used = ctx->atom_used;
+    const long long n = (long long)used.size(), gap = 4096;
+    long long covered = 0, a = 0;
+    while (a < n) {
+        while (a < n && !used[a]) ++a;
+        if (a >= n) break;
+        long long b = a, last = a;
+        while (b < n && b - last <= gap) { if (used[b]) last = b; ++b; }
+        ctx->copy_ranges.push_back({a, last + 1});
+        covered += last + 1 - a;
+        a = last + 1;
+    }
+    if (ctx->copy_ranges.size() > 8 || covered * 10 > n * 9) ctx->copy_ranges.clear();   // not worth it
 }
 
 extern "C" {
@@ -501,25 +521,15 @@ int hb_set_topology(hb_ctx* ctx, const hb_topology* t) {
     for (int k = 0; k < t->n_ent_h; ++k)
         if (t->ent_h_atom[k] < 0 || t->ent_h_atom[k] >= ctx->max_atoms) return fail(ctx, HB_ERR_ARG, "topology: hydrogen atom out of range");
     // atoms the kernels can touch (single system): selection points, water points, every listed hydrogen
-    ctx->copy_ranges.clear();
+    // (hb_set_ions adds the ions and rebuilds the ranges)
+    ctx->atom_used.clear();
     if (ns == 1 && ctx->max_atoms > 0) {
-        std::vector<unsigned char> used((size_t)ctx->max_atoms, 0);
-        for (int i = 0; i < t->n_sel; ++i) used[t->sel_atom[i]] = 1;
-        for (int i = 0; i < t->n_wat; ++i) used[t->wat_atom[i]] = 1;
-        for (int i = 0; i < t->n_ent_h; ++i) used[t->ent_h_atom[i]] = 1;
-        const long long gap = 4096;                    // holes shorter than this (48 kB) are copied along
-        long long covered = 0, a = 0, n = ctx->max_atoms;
-        while (a < n) {
-            while (a < n && !used[a]) ++a;
-            if (a >= n) break;
-            long long b = a, last = a;
-            while (b < n && b - last <= gap) { if (used[b]) last = b; ++b; }
-            ctx->copy_ranges.push_back({a, last + 1});
-            covered += last + 1 - a;
-            a = last + 1;
-        }
-        if (ctx->copy_ranges.size() > 8 || covered * 10 > n * 9) ctx->copy_ranges.clear();   // not worth it
+        ctx->atom_used.assign((size_t)ctx->max_atoms, 0);
+        for (int i = 0; i < t->n_sel; ++i) ctx->atom_used[t->sel_atom[i]] = 1;
+        for (int i = 0; i < t->n_wat; ++i) ctx->atom_used[t->wat_atom[i]] = 1;
+        for (int i = 0; i < t->n_ent_h; ++i) ctx->atom_used[t->ent_h_atom[i]] = 1;
     }
+    build_copy_ranges(ctx);
     // water points at a constant atom stride (O, H, H, O, H, H ...) can be streamed as contiguous slabs
     ctx->water_regular = t->n_wat > 0;
     ctx->water_stride = 0;
@@ -600,6 +610,11 @@ int hb_set_ions(hb_ctx* ctx, const int32_t* ion_atom, const int32_t* ion_group, 
     if ((rc = upload(ctx, ion_group, (size_t)n_ions, &ctx->ions.group, ctx->topo_allocs))) return rc;
     ctx->ions.n = n_ions;
     ctx->ion_include_water = include_water != 0;
+    // k_ion_contacts reads the ions' coordinates: they must be inside the atom ranges that reach the device
+    if (!ctx->atom_used.empty()) {
+        for (int i = 0; i < n_ions; ++i) ctx->atom_used[ion_atom[i]] = 1;
+        build_copy_ranges(ctx);
+    }
     return HB_OK;
 }
 

@@ -287,6 +287,9 @@ class HbondAnalysis(object):
         """wires = (ent_node, n_res, max_water, allow_direct_bonds): water-wire mode of the water_around search
         (hb_set_wires); returns the raw (keys, rows) of that run instead of a result dict."""
         top = self._topology
+        if top is None or getattr(self, "_universe", None) is None:
+            raise AssertionError('this analysis was restored from a file without its Universe; construct it with the '
+                                 'structure again or call load_from_file(fname, reload_universe=True) before running')
         self._check_hydrogen_tables(method)
         ctx = self._context()
         cache = self.__dict__.setdefault("_packed", {})
@@ -473,17 +476,32 @@ class HbondAnalysis(object):
         return {key: float(_np.mean(results[key])) for key in results}
 
     def dump_to_file(self, fname):                                    # basic.py:71-81
+        """Like the reference, everything but the MDAnalysis objects is pickled: the derived tables (`_topology`:
+        plain numpy arrays, the source of `heavy2hydrogen`, `_all_ids`, ...) stay in the file."""
         tmp = _cp.copy(self)
-        for name in ('_universe', '_water', '_mda_selection', '_ctx', '_topology', '_packed', '_rows'):
+        for name in ('_universe', '_water', '_mda_selection', '_ctx', '_rows'):
             tmp.__dict__[name] = None
+        tmp.__dict__.pop('_packed', None)          # device tables: rebuilt from `_topology` on the next run
         with open(fname, 'wb') as af:
             af.write(_pickle.dumps(tmp.__dict__))
+
+    _RUNTIME_KWARGS = ('_device', '_pbc', '_native_options', '_shard', '_cos_threshold_override', '_batch_bytes')
 
     def load_from_file(self, fname, reload_universe=False):           # basic.py:83-86
         with open(fname, 'rb') as af:
             state = _pickle.loads(af.read())
+        # where / how to run is a property of this process, not of the dumped analysis: keyword arguments given to
+        # the constructor win over the dumped values
+        mine = {k: self.__dict__[k] for k in self._RUNTIME_KWARGS if k in self.__dict__}
+        defaults = {'_device': None, '_pbc': False, '_native_options': {}, '_shard': None,
+                    '_cos_threshold_override': None, '_batch_bytes': None}
         self.__dict__.update(state)
+        for k, v in mine.items():
+            if v != defaults[k] or k not in state:
+                self.__dict__[k] = v
         self._ctx = None
+        self.__dict__.pop('_packed', None)
+        self._rows = None
         if reload_universe: self._reload_universe()
 
     def _reload_universe(self):                                       # basic.py:88-92

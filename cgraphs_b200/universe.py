@@ -360,7 +360,7 @@ class Universe:
 # ------------------------------------------------------------------------------------------------
 # selection mini-language: protein / backbone / nucleic / water / all / resname / name / segid / type / resid (a:b, a-b,
 # a to b) / index / bynum / byres / around R <sel> (first frame) / and / or / not / ()
-# precedence not > and > or, several values after a keyword are OR-ed (as MDAnalysis does)
+# precedence as in MDAnalysis: not > (and = or, left to right) > byres = around; several values after a keyword are OR-ed
 # ------------------------------------------------------------------------------------------------
 _TOKEN = re.compile(r"\(|\)|[^\s()]+")
 _KEYWORDS = {"and", "or", "not", "protein", "all", "resname", "name", "segid", "type", "resid", "resnum", "(", ")",
@@ -382,7 +382,7 @@ class _Selector:
         self.pos = 0
         if not self.tokens:
             raise ValueError("empty selection")
-        mask = self._or()
+        mask = self._expr(0)
         if self.pos != len(self.tokens):
             raise ValueError("unexpected token %r in selection %r" % (self.tokens[self.pos], sel))
         return mask
@@ -395,34 +395,34 @@ class _Selector:
         self.pos += 1
         return tok
 
-    def _or(self):
-        m = self._and()
-        while self._peek() == "or":
-            self._next()
-            m = m | self._and()
+    # MDAnalysis' SelectionParser (core/selection.py) is a precedence-climbing parser: `and` and `or` share one
+    # precedence (3) and associate to the left, `not` (5) binds tighter, `byres` and `around` (1) take the whole
+    # expression that follows them:  A or B and C = (A or B) and C;  around 3.5 protein and name CA =
+    # around 3.5 (protein and name CA);  not A and B = (not A) and B.
+    _PREC = {"and": 3, "or": 3}
+
+    def _expr(self, p=0):
+        m = self._subexp()
+        while self._peek() in self._PREC and self._PREC[self._peek()] >= p:
+            op = self._next()
+            rhs = self._expr(self._PREC[op] + 1)
+            m = (m & rhs) if op == "and" else (m | rhs)
         return m
 
-    def _and(self):
-        m = self._not()
-        while self._peek() == "and":
-            self._next()
-            m = m & self._not()
-        return m
-
-    def _not(self):
+    def _subexp(self):
         if self._peek() == "not":
             self._next()
-            return ~self._not()
-        if self._peek() == "byres":             # every atom of the residues touched by the following selection
+            return ~self._expr(5)
+        if self._peek() == "byres":             # every atom of the residues touched by the following expression
             self._next()
-            inner = self._not()
+            inner = self._expr(1)
             hit = np.zeros(self.t.n_residues, dtype=bool)
             hit[self.t.resindices[inner]] = True
             return hit[self.t.resindices]
-        if self._peek() == "around":            # atoms within R of the following selection (first frame), not the selection itself
+        if self._peek() == "around":            # atoms within R of the following expression (first frame), not the expression itself
             self._next()
             radius = float(self._next())
-            inner = self._not()
+            inner = self._expr(1)
             if self.u is None:
                 raise ValueError("'around' needs coordinates")
             from scipy.spatial import cKDTree
@@ -459,7 +459,7 @@ class _Selector:
         if tok is None:
             raise ValueError("unexpected end of selection")
         if tok == "(":
-            m = self._or()
+            m = self._expr(0)
             if self._next() != ")":
                 raise ValueError("missing ) in selection")
             return m

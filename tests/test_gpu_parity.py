@@ -353,3 +353,61 @@ def test_gpu_ion_contacts(residuewise):
     bare = HbondAnalysis("protein", u)
     with pytest.raises(AssertionError, match="No ions"):
         bare.set_add_ion_interactions()
+
+
+@pytest.mark.gpu
+def test_gpu_ions_behind_an_inert_atom_range():
+    """Ions that lie after a long run of atoms no kernel reads (CHARMM order: ... waters, lipids, SOD / CLA): the host
+    frames reach the device as atom ranges, and hb_set_ions has to add the ions to them (both submit paths)."""
+    from cgraphs_b200.mdhbond import HbondAnalysis
+    from cgraphs_b200.universe import Topology
+    from tests.helpers import port_with_ions
+    s, cfg = synth.config("C3", scale=0.3)
+    t = s.topology
+    resn = np.asarray(t.resnames)
+    fill = np.nonzero(resn == "POPC")[0]
+    rest = np.nonzero(resn != "POPC")[0]
+    n_ions = 24
+    order = np.concatenate([rest, fill])                    # protein, waters, membrane (inert), ions = last filler atoms
+    names = [t.names[i] for i in order]
+    resnames = [t.resnames[i] for i in order]
+    resids = [int(t.resids[i]) for i in order]
+    segids = [t.segids[i] for i in order]
+    n = len(order)
+    for k in range(n_ions):
+        i = n - n_ions + k
+        names[i] = resnames[i] = "SOD" if k % 2 == 0 else "CLA"
+        resids[i] = 7000 + k
+        segids[i] = "ION"
+    nf = 6
+    xyz = s.frames(0, nf)[:, order, :]
+    rng = np.random.default_rng(11)
+    targets = rng.choice(len(rest), size=n_ions, replace=False)
+    for k in range(n_ions):
+        xyz[:, n - n_ions + k, :] = xyz[:, targets[k], :] + rng.normal(0, 1.4, size=(nf, 3)).astype(np.float32)
+    assert len(fill) - n_ions > 4096 and len(rest) < 0.9 * n
+    u = Universe(Topology(names, resnames, resids, segids), np.ascontiguousarray(xyz), s.dimensions)
+    ref = port_with_ions(u, "protein", "water_around", ['SOD', 'CLA'])
+    assert sum(1 for k in ref if k.split(':')[1].split('-')[1] in ('SOD', 'CLA')) > 5
+    for opts in ({}, {"copy_ranges": 0}):
+        hba = HbondAnalysis("protein", u, ions=['SOD', 'CLA'], native_options=opts)
+        hba.set_hbonds_in_selection_and_water_around(3.5)
+        assert_same_results(hba.initial_results, ref, "ions behind a hole %s" % opts)
+        if not opts:
+            assert hba.last_run_stats["h2d_bytes"] < 0.9 * xyz.nbytes       # ranges were in use
+    # planar (DCD record) submission of the same frames
+    from cgraphs_b200.mdhbond import _native
+    from cgraphs_b200.mdhbond.topology import pack_systems
+    hba = HbondAnalysis("protein", u, ions=['SOD', 'CLA'])
+    hba.set_hbonds_in_selection_and_water_around(3.5)
+    want = dict(hba.initial_results)
+    planar = np.ascontiguousarray(xyz.transpose(0, 2, 1))   # [frame][x|y|z][atom]
+    ctx = hba._context()
+    ctx.begin(nf)
+    ctx.submit_planar(planar, n * 12, 0, n * 4, n * 8, n, nf)
+    keys, words = ctx.results()
+    ctx.begin(nf)
+    ctx.submit(np.ascontiguousarray(xyz))
+    keys2, words2 = ctx.results()
+    assert np.array_equal(keys, keys2) and np.array_equal(words, words2) and len(keys) > 0
+    assert want

@@ -53,3 +53,26 @@ def test_errors(u):
     for bad in ("", "resid x", "index a", "frobnicate 3", "protein and", "(protein"):
         with pytest.raises(ValueError):
             u.select_atoms(bad)
+
+
+def test_precedence_follows_mdanalysis(u):
+    """MDAnalysis' SelectionParser: `and` / `or` share one precedence and associate to the left, `not` binds
+    tighter, `byres` / `around` take the whole following expression (core/selection.py, precedence table)."""
+    same = [
+        ("name CA or name N and resid 3", "(name CA or name N) and resid 3"),
+        ("resid 3 and name CA or name N", "(resid 3 and name CA) or name N"),
+        ("name CA or name N and resid 3 or name OH2", "((name CA or name N) and resid 3) or name OH2"),
+        ("not name CA and resid 3", "(not name CA) and resid 3"),
+        ("not name CA or resid 3", "(not name CA) or resid 3"),
+        ("byres name CA and resid 3", "byres (name CA and resid 3)"),
+        ("byres name CA and resid 3 or resid 4 and name N", "byres (((name CA and resid 3) or resid 4) and name N)"),
+        ("around 3.5 protein and name CA", "around 3.5 (protein and name CA)"),
+        ("name OH2 and around 3.5 protein or name CA", "name OH2 and (around 3.5 (protein or name CA))"),
+        ("name OH2 and not around 3.5 protein and resid 1 to 40", "name OH2 and (not (around 3.5 (protein and resid 1:40)))"),
+        ("not byres name CA and resid 3", "not (byres (name CA and resid 3))"),
+    ]
+    for a, b in same:
+        assert np.array_equal(_idx(u, a), _idx(u, b)), a
+    # and the two readings really differ on this system (the test would be vacuous otherwise)
+    assert not np.array_equal(_idx(u, "name CA or name N and resid 3"), _idx(u, "name CA or (name N and resid 3)"))
+    assert not np.array_equal(_idx(u, "around 3.5 protein and name CA"), _idx(u, "(around 3.5 protein) and name CA"))

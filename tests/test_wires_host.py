@@ -127,3 +127,22 @@ def test_wire_analysis_dump_and_restore(tmp_path):
     assert np.array_equal(wb.wire_lengths["PA-SER-1:PA-THR-2"], wa.wire_lengths["PA-SER-1:PA-THR-2"])
     assert wb.compute_average_water_per_wire() == {"PA-SER-1:PA-THR-2": 0.5}
     assert wb.filtered_graph.number_of_edges() == 1
+
+
+def test_hbond_analysis_restore_keeps_derived_tables(tmp_path):
+    """The reference pickles heavy2hydrogen / _all_ids / ... (basic.py:71-81); a restored object keeps them, keeps the
+    constructor's runtime keyword arguments, and says clearly why it cannot run without its Universe."""
+    from cgraphs_b200.mdhbond import HbondAnalysis
+    u = _system().universe(3)
+    a = HbondAnalysis("protein", u, device=0)
+    a.initial_results = {"PA-SER-1:PA-THR-2": np.array([True, False, True])}
+    f = str(tmp_path / "hba.pickle")
+    a.dump_to_file(f)
+    b = HbondAnalysis(restore_filename=f, device=3, pbc="ortho")
+    assert b.heavy2hydrogen == a.heavy2hydrogen and b._all_ids == a._all_ids
+    assert b._device == 3 and b._pbc == "ortho" and b._universe is None
+    c = HbondAnalysis(restore_filename=f)
+    assert c._device == 0 and c._pbc is False
+    with pytest.raises(AssertionError, match="restored from a file"):
+        b.set_hbonds_in_selection()
+    assert a._topology is not None and a._universe is u            # dumping does not strip the live object
