@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libhbgpu.so")
 SOURCES = [os.path.join(CSRC, "hbgpu.cu")]
 HEADERS = [os.path.join(HERE, "..", "include", "hbgpu.h")] + \
-          [os.path.join(CSRC, f) for f in ("hb_common.cuh", "hb_fused.cuh", "hb_general.cuh", "hb_finalize.cuh", "hb_wires.cuh", "hb_framepairs.cuh")]
+          [os.path.join(CSRC, f) for f in ("hb_common.cuh", "hb_fused.cuh", "hb_general.cuh", "hb_finalize.cuh", "hb_wires.cuh", "hb_framepairs.cuh", "hb_xtc.cuh", "hb_xtc_host.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-shared"]
 

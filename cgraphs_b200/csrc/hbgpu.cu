@@ -39,6 +39,8 @@
 #include "hb_framepairs.cuh"
 #include "hb_finalize.cuh"
 #include "hb_wires.cuh"
+#include "hb_xtc.cuh"
+#include "hb_xtc_host.h"
 
 namespace {
 
@@ -135,6 +137,11 @@ struct hb_ctx {
     size_t stage_alloc = 0;           // bytes per pinned staging buffer
     unsigned char* d_raw[2] = {nullptr, nullptr};   // planar sources (DCD): raw frame records before the interleave
     size_t raw_alloc = 0;
+    long long* d_xoff[2] = {nullptr, nullptr};      // XTC sources: record offsets of the frames in d_raw[k]
+    long long* h_xoff[2] = {nullptr, nullptr};      // (pinned)
+    size_t xoff_cap = 0;                            // frames
+    int* d_xtc_status = nullptr;                    // set by k_xtc_decode when a record is malformed
+    int* h_xtc_status = nullptr;                    // pinned copy, read back behind every decode
     cudaEvent_t ev_copied[2]{}, ev_done[2]{};
     cudaEvent_t ev_run0{}, ev_run1{};
     long long batch_counter = 0;
@@ -425,6 +432,9 @@ int hb_destroy(hb_ctx* ctx) {
     cudaEventDestroy(ctx->ev_run0);
     cudaEventDestroy(ctx->ev_run1);
     if (ctx->merge_table) cudaFree(ctx->merge_table);
+    for (int k = 0; k < 2; ++k) { if (ctx->d_xoff[k]) cudaFree(ctx->d_xoff[k]); if (ctx->h_xoff[k]) cudaFreeHost(ctx->h_xoff[k]); }
+    if (ctx->d_xtc_status) cudaFree(ctx->d_xtc_status);
+    if (ctx->h_xtc_status) cudaFreeHost(ctx->h_xtc_status);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
     if (ctx->h_verify) cudaFreeHost(ctx->h_verify);
     if (ctx->h_hits) cudaFreeHost(ctx->h_hits);
@@ -1513,6 +1523,231 @@ int hb_submit_frames_planar(hb_ctx* ctx, const void* raw, int64_t frame_stride, 
     return HB_OK;
 }
 
+// ---- XTC sources -----------------------------------------------------------------------------------------
+static int check_xtc_status(hb_ctx* ctx) {        // after the copy stream has drained
+    if (ctx->h_xtc_status && *ctx->h_xtc_status) {
+        *ctx->h_xtc_status = 0;
+        if (ctx->d_xtc_status) cudaMemsetAsync(ctx->d_xtc_status, 0, sizeof(int), ctx->s_copy);
+        return fail(ctx, HB_ERR_ARG, "hb_submit_frames_xtc: malformed XTC frame record (magic, atom count or bit stream)");
+    }
+    return HB_OK;
+}
+
+int hb_xtc_index(const void* buf, int64_t nbytes, int64_t* frame_off, int64_t max_frames, int64_t* n_frames, int64_t* n_atoms) {
+    if (!buf || nbytes < 0 || !n_frames) return HB_ERR_ARG;
+    const unsigned char* p = (const unsigned char*)buf;
+    int64_t off = 0, n = 0;
+    int atoms0 = -1;
+    while (off < nbytes) {
+        int na = 0;
+        const size_t len = xtc::frame_bytes(p + off, (size_t)(nbytes - off), &na);
+        if (!len) break;                               // truncated tail or foreign bytes: the index ends here
+        if (atoms0 < 0) atoms0 = na;
+        if (na != atoms0) return HB_ERR_ARG;
+        if (frame_off && n < max_frames) frame_off[n] = off;
+        ++n;
+        off += (int64_t)len;
+    }
+    if (frame_off && n <= max_frames) frame_off[n] = off;
+    *n_frames = n;
+    if (n_atoms) *n_atoms = atoms0 < 0 ? 0 : atoms0;
+    return HB_OK;
+}
+
+int hb_xtc_encode(const float* xyz, int64_t n_atoms, int64_t n_frames, float in_scale, float precision, const float* box9,
+                  int64_t first_step, float dt, void* out, int64_t out_cap, int64_t* frame_off, int64_t* bytes_written,
+                  int32_t n_threads) {
+    if (!xyz || n_atoms < 1 || n_atoms > INT32_MAX / 3 || n_frames < 0 || !bytes_written) return HB_ERR_ARG;
+    const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n_threads > 0 ? n_threads : 1, 64), n_frames));
+    std::vector<std::vector<unsigned char>> parts((size_t)nt);
+    std::vector<std::vector<int64_t>> lens((size_t)nt);
+    std::vector<int> ok((size_t)nt, 1);
+    auto work = [&](int t) {
+        const int64_t a = n_frames * t / nt, b = n_frames * (t + 1) / nt;
+        for (int64_t f = a; f < b; ++f) {
+            const size_t before = parts[t].size();
+            if (!xtc::encode_frame(xyz + (size_t)f * n_atoms * 3, (int)n_atoms, in_scale, precision, (int)(first_step + f),
+                                   dt * (float)(first_step + f), box9 ? box9 + 9 * f : nullptr, parts[t])) { ok[t] = 0; return; }
+            lens[t].push_back((int64_t)(parts[t].size() - before));
+        }
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    int64_t total = 0, f = 0;
+    for (int t = 0; t < nt; ++t) { if (!ok[t]) return HB_ERR_ARG; total += (int64_t)parts[t].size(); }
+    *bytes_written = total;
+    if (!out || total > out_cap) return out ? HB_ERR_NOMEM : HB_OK;     // out == NULL: size query
+    int64_t off = 0;
+    for (int t = 0; t < nt; ++t) {
+        memcpy((unsigned char*)out + off, parts[t].data(), parts[t].size());
+        if (frame_off) for (int64_t l : lens[t]) { frame_off[f++] = off; off += l; }
+        else off += (int64_t)parts[t].size();
+    }
+    if (frame_off) frame_off[n_frames] = total;
+    return HB_OK;
+}
+
+int hb_xtc_decode_host(const void* rec, int64_t avail, int64_t n_atoms, float scale, float* xyz, float* box9, int64_t* rec_bytes) {
+    if (!rec || !xyz || avail < 0 || n_atoms < 0 || n_atoms > INT32_MAX / 3) return HB_ERR_ARG;
+    const size_t len = xtc::decode_frame((const unsigned char*)rec, (size_t)avail, (int)n_atoms, scale, xyz, box9, nullptr, nullptr);
+    if (!len) return HB_ERR_ARG;
+    if (rec_bytes) *rec_bytes = (int64_t)len;
+    return HB_OK;
+}
+
+int hb_xtc_decode_to_device(hb_ctx* ctx, const void* raw, const int64_t* frame_off, int64_t n_atoms, int64_t n_frames,
+                            float scale, float* d_out) {
+    if (!ctx || !raw || !frame_off || !d_out || n_frames < 0 || n_atoms < 1 || n_atoms > INT32_MAX / 3) return HB_ERR_ARG;
+    if (n_frames == 0) return HB_OK;
+    for (int64_t f = 0; f < n_frames; ++f)
+        if (frame_off[f + 1] <= frame_off[f] || (frame_off[f] & 3)) return fail(ctx, HB_ERR_ARG, "hb_xtc_decode_to_device: frame offsets must ascend in multiples of 4");
+    CK(cudaSetDevice(ctx->device));
+    const int64_t b0 = frame_off[0];
+    const size_t bytes = (size_t)(frame_off[n_frames] - b0);
+    unsigned char* d_raw = nullptr;
+    long long* d_off = nullptr;
+    int* d_status = nullptr;
+    std::vector<long long> rel((size_t)n_frames + 1);
+    for (int64_t f = 0; f <= n_frames; ++f) rel[f] = frame_off[f] - b0;
+    int status = 0;
+    cudaError_t e = cudaMalloc((void**)&d_raw, bytes + 64);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_off, rel.size() * 8);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&d_status, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_status, 0, sizeof(int), ctx->s_copy);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_raw + bytes, 0, 64, ctx->s_copy);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_raw, (const unsigned char*)raw + b0, bytes, cudaMemcpyHostToDevice, ctx->s_copy);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice, ctx->s_copy);
+    if (e == cudaSuccess) {
+        XtcArgs xa{};
+        xa.raw = d_raw; xa.frame_off = d_off; xa.n_frames = (int)n_frames; xa.n_atoms = (int)n_atoms; xa.scale = scale;
+        xa.out = d_out; xa.status = d_status;
+        k_xtc_decode<<<(unsigned)((n_frames + XTC_WARPS - 1) / XTC_WARPS), XTC_WARPS * 32, 0, ctx->s_copy>>>(xa);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_copy);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->s_copy);
+    if (d_raw) cudaFree(d_raw);
+    if (d_off) cudaFree(d_off);
+    if (d_status) cudaFree(d_status);
+    if (e != cudaSuccess) return fail(ctx, HB_ERR_CUDA, cudaGetErrorString(e));
+    if (status) return fail(ctx, HB_ERR_ARG, "hb_xtc_decode_to_device: malformed XTC frame record (magic, atom count or bit stream)");
+    return HB_OK;
+}
+
+int hb_submit_frames_xtc(hb_ctx* ctx, const void* raw, const int64_t* frame_off, int64_t n_atoms, int64_t n_frames, float scale,
+                         const float* box) {
+    if (!ctx || ((!raw || !frame_off) && n_frames > 0)) return HB_ERR_ARG;
+    int rc = check_submit(ctx, n_atoms, n_frames);
+    if (rc) return rc;
+    if (ctx->prm.structure_batch) return fail(ctx, HB_ERR_ARG, "hb_submit_frames_xtc: trajectories only");
+    if (n_atoms > INT32_MAX / 3) return fail(ctx, HB_ERR_ARG, "hb_submit_frames_xtc: too many atoms");
+    size_t max_rec = 0;
+    for (int64_t f = 0; f < n_frames; ++f) {
+        if (frame_off[f + 1] <= frame_off[f] || (frame_off[f] & 3)) return fail(ctx, HB_ERR_ARG, "hb_submit_frames_xtc: frame offsets must ascend in multiples of 4");
+        max_rec = std::max(max_rec, (size_t)(frame_off[f + 1] - frame_off[f]));
+    }
+    const bool pbc = ctx->prm.pbc_mode != HB_PBC_NONE;
+    if (pbc) {
+        if (!box) return fail(ctx, HB_ERR_ARG, "hb_submit_frames_xtc: pbc_mode needs the lattice vectors of every frame");
+        if ((rc = check_boxes(ctx, box, n_frames))) return rc;
+    }
+    CK(cudaSetDevice(ctx->device));
+    if (pbc && (rc = ensure_box_buffers(ctx))) return rc;
+    cudaPointerAttributes attr{};
+    bool pinned = cudaPointerGetAttributes(&attr, raw) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    // raw buffers: half the bytes of the decoded frames (a record takes 3 - 5 bytes per atom), at least one record
+    if ((rc = ensure_input_buffers(ctx, std::max((size_t)n_atoms * 12 * (size_t)n_frames, 2 * max_rec + 1024), pinned, 1, 2))) return rc;
+    if (max_rec + 64 > ctx->raw_alloc) return fail(ctx, HB_ERR_NOMEM, "hb_submit_frames_xtc: a frame record does not fit the input buffer (raise batch_bytes)");
+    if (!ctx->d_xtc_status) {
+        CK(cudaMalloc((void**)&ctx->d_xtc_status, sizeof(int)));
+        CK(cudaMemset(ctx->d_xtc_status, 0, sizeof(int)));
+        CK(cudaHostAlloc((void**)&ctx->h_xtc_status, sizeof(int), cudaHostAllocDefault));
+        *ctx->h_xtc_status = 0;
+    }
+    const size_t want_off = (size_t)std::max(ctx->host_batch_frames, 1) + 1;
+    if (ctx->xoff_cap < want_off) {
+        CK(cudaStreamSynchronize(ctx->s_copy));
+        for (int k = 0; k < 2; ++k) {
+            if (ctx->d_xoff[k]) cudaFree(ctx->d_xoff[k]);
+            if (ctx->h_xoff[k]) cudaFreeHost(ctx->h_xoff[k]);
+            ctx->d_xoff[k] = nullptr; ctx->h_xoff[k] = nullptr;
+        }
+        ctx->xoff_cap = 0;
+        for (int k = 0; k < 2; ++k) {
+            CK(cudaMalloc((void**)&ctx->d_xoff[k], want_off * 8));
+            CK(cudaHostAlloc((void**)&ctx->h_xoff[k], want_off * 8, cudaHostAllocDefault));
+        }
+        ctx->xoff_cap = want_off;
+    }
+    XtcRanges xr{};
+    if (ctx->opt_copy_ranges && !ctx->copy_ranges.empty() && ctx->copy_ranges.size() <= 8) {
+        xr.n = (int)ctx->copy_ranges.size();
+        for (int k = 0; k < xr.n; ++k) { xr.b[k] = (int)ctx->copy_ranges[k].first; xr.e[k] = (int)ctx->copy_ranges[k].second; }
+    }
+    const unsigned char* src = (const unsigned char*)raw;
+    long long done = 0;
+    while (done < n_frames) {
+        long long f0 = ctx->next_frame;
+        int nf = next_batch_frames(ctx, f0, n_frames - done, true);
+        nf = (int)std::min<long long>(nf, (long long)ctx->xoff_cap - 1);
+        while (nf > 1 && (size_t)(frame_off[done + nf] - frame_off[done]) + 64 > ctx->raw_alloc) --nf;
+        const int64_t b0 = frame_off[done];
+        const size_t bytes = (size_t)(frame_off[done + nf] - b0);
+        int k = (int)(ctx->batch_counter & 1);
+        if ((rc = acquire_slot(ctx, k))) return rc;
+        if ((rc = check_xtc_status(ctx))) return rc;
+        const unsigned char* h = src + b0;
+        if (!pinned) {
+            unsigned char* st = (unsigned char*)ctx->h_stage[k];
+            const int pieces = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->opt_stage_threads, bytes >> 23));
+            parallel_frames(pieces, bytes / (size_t)pieces + 1, ctx->opt_stage_threads, [=](int a, int b2) {
+                const size_t lo = bytes * (size_t)a / (size_t)pieces, hi = bytes * (size_t)b2 / (size_t)pieces;
+                memcpy(st + lo, h + lo, hi - lo);
+            });
+            h = st;
+        }
+        for (int f = 0; f <= nf; ++f) ctx->h_xoff[k][f] = frame_off[done + f] - b0;
+        if (pbc) {
+            memcpy(ctx->h_box[k], box + 9 * done, (size_t)nf * 36);
+            CK(cudaMemcpyAsync(ctx->d_box[k], ctx->h_box[k], (size_t)nf * 36, cudaMemcpyHostToDevice, ctx->s_copy));
+        }
+        cudaEvent_t c0 = get_event(ctx), c1 = get_event(ctx);
+        cudaEventRecord(c0, ctx->s_copy);
+        CK(cudaMemcpyAsync(ctx->d_xoff[k], ctx->h_xoff[k], (size_t)(nf + 1) * 8, cudaMemcpyHostToDevice, ctx->s_copy));
+        CK(cudaMemcpyAsync(ctx->d_raw[k], h, bytes, cudaMemcpyHostToDevice, ctx->s_copy));
+        ctx->tm.h2d_bytes += (long long)bytes;
+        XtcArgs xa{};
+        xa.raw = ctx->d_raw[k];
+        xa.frame_off = ctx->d_xoff[k];
+        xa.n_frames = nf;
+        xa.n_atoms = (int)n_atoms;
+        xa.scale = scale;
+        xa.out = ctx->d_in[k];
+        xa.status = ctx->d_xtc_status;
+        xa.ranges = xr;
+        k_xtc_decode<<<(nf + XTC_WARPS - 1) / XTC_WARPS, XTC_WARPS * 32, 0, ctx->s_copy>>>(xa);
+        CK(cudaGetLastError());
+        ctx->tm.n_launches += 1;
+        CK(cudaMemcpyAsync(ctx->h_xtc_status, ctx->d_xtc_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_copy));
+        cudaEventRecord(c1, ctx->s_copy);
+        ctx->pending.push_back({c0, c1, -2});
+        CK(cudaEventRecord(ctx->ev_copied[k], ctx->s_copy));
+        CK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_copied[k], 0));
+        if ((rc = launch_in_slot(ctx, k, ctx->d_in[k], f0, nf, n_atoms, (size_t)nf * n_atoms * 12, pbc ? ctx->d_box[k] : nullptr))) return rc;
+        ctx->batch_counter++;
+        ctx->next_frame += nf;
+        done += nf;
+        if (ctx->pending.size() > 8192) drain_events(ctx);
+    }
+    if (pinned) CK(cudaStreamSynchronize(ctx->s_copy));
+    return HB_OK;
+}
+
 int hb_submit_frames_device(hb_ctx* ctx, const float* d_xyz, int64_t n_atoms, int64_t n_frames, const float* d_box) {
     if (!ctx || (!d_xyz && n_frames > 0)) return HB_ERR_ARG;
     int rc = check_submit(ctx, n_atoms, n_frames);
@@ -1543,6 +1778,7 @@ int hb_sync(hb_ctx* ctx) {
     if (!ctx) return HB_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->s_copy));
+    { int rcx = check_xtc_status(ctx); if (rcx) return rcx; }
     if (ctx->running) {
         int rc = full_verify(ctx);
         if (rc) return rc;
@@ -1673,6 +1909,7 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
     int n = 0;
     bool settled = false;             // ev_run1 recorded and the stream drained
     CK(cudaStreamSynchronize(ctx->s_copy));
+    if ((rc = check_xtc_status(ctx))) return rc;
     for (int attempt = 0;; ++attempt) {
         if (attempt > 40) return fail(ctx, HB_ERR_NOMEM, "hb_finalize: the bond table kept overflowing");
         if (!ctx->fin_queued && (rc = queue_finalize(ctx, finalize_can_speculate(ctx), &n))) return rc;

@@ -12,7 +12,10 @@ interleaved on the device.
   passes as ``structure``, ``proteingraphanalyser.py:472-476``); coordinates then come from the trajectory
 * :class:`DCDFrames` / :func:`write_dcd` - frame source over a DCD file (memory mapped), with the planar view
   ``planar_block`` the native path uses, and the unit cell of every frame
-* :func:`universe_from_files` - ``Universe`` (cgraphs_b200.universe) from a PDB and an optional DCD
+* :class:`XTCFrames` / :func:`write_xtc` - frame source over a GROMACS XTC file: the compressed frame records are
+  handed to ``hb_submit_frames_xtc`` as they lie in the file and decoded on the device; coordinates come out in
+  Angstrom with the float32 arithmetic of MDAnalysis' reader (xdrfile decode, then ``x *= 10``)
+* :func:`universe_from_files` - ``Universe`` (cgraphs_b200.universe) from a PDB / PSF and optional DCD / XTC files
 """
 from __future__ import annotations
 
@@ -283,8 +286,101 @@ class ConcatDCDFrames:
         return self.parts[k].dimensions_of(a)
 
 
+# ------------------------------------------------------------------------------------------------
+# XTC (GROMACS; XDR big endian, lossy integer compression, nm)
+# ------------------------------------------------------------------------------------------------
+def write_xtc(path, frames, dimensions=None, precision=1000.0, dt=1.0, append=False):
+    """frames: float32 [F, N, 3] in Angstrom (stored in nm at 1 / precision nm resolution, like `gmx trjconv`);
+    dimensions: [a, b, c, alpha, beta, gamma] in Angstrom / degrees or None (a zero box is written)."""
+    from .mdhbond import _native
+    from .mdhbond.hbond import box_rows
+    frames = np.asarray(frames, dtype=np.float32)
+    box_nm = None if dimensions is None else (box_rows(dimensions).astype(np.float64) * 0.1).astype(np.float32)
+    buf, _ = _native.xtc_encode(frames, in_scale=0.1, precision=precision, box_nm=box_nm, dt=dt)
+    with open(path, "ab" if append else "wb") as f:
+        f.write(buf.tobytes())
+
+
+class XTCFrames:
+    """Frame source over an XTC file (memory mapped): ``len``, ``frame(i)``, ``block(a, b)`` decode on the host (the
+    constructor needs frame 0; everything else is a convenience), ``xtc_block(a, b)`` hands out the compressed
+    records for ``hb_submit_frames_xtc`` and ``dimensions_of(i)`` the unit cell in Angstrom / degrees."""
+
+    LENGTH_SCALE = 10.0                 # nm -> Angstrom (MDAnalysis convert_units=True)
+
+    def __init__(self, path):
+        from .mdhbond import _native
+        self.path = path
+        self._native = _native
+        self._map = np.memmap(path, dtype=np.uint8, mode="r")
+        self.offsets, self.n_atoms = _native.xtc_index(self._map)
+        self.n_frames = len(self.offsets) - 1
+        if self.n_frames == 0:
+            raise ValueError("%s: no XTC frame records" % path)
+
+    def __len__(self):
+        return self.n_frames
+
+    def xtc_block(self, start, stop):
+        """(uint8 view of the records of frames [start, stop), int64 offsets [stop - start + 1] relative to it)."""
+        a, b = int(self.offsets[start]), int(self.offsets[stop])
+        return self._map[a:b], self.offsets[start:stop + 1] - a
+
+    def xtc_count(self, start, stop):
+        return stop - start
+
+    def frame(self, i):
+        return self._native.xtc_decode_host(self._map, int(self.offsets[int(i)]), self.n_atoms, self.LENGTH_SCALE)[0]
+
+    def block(self, start, stop):
+        out = np.empty((stop - start, self.n_atoms, 3), dtype=np.float32)
+        for k, i in enumerate(range(start, stop)):
+            out[k] = self.frame(i)
+        return out
+
+    def box_nm(self, i):
+        o = int(self.offsets[int(i)])
+        return np.asarray(self._map[o + 16:o + 52]).view(">f4").astype(np.float32).reshape(3, 3)
+
+    def dimensions_of(self, i):
+        """[a, b, c, alpha, beta, gamma] (Angstrom, degrees) of frame i, or None for a zero box."""
+        h = self.box_nm(i).astype(np.float64) * self.LENGTH_SCALE
+        la, lb, lc = (float(np.linalg.norm(h[k])) for k in range(3))
+        if la == 0.0 or lb == 0.0 or lc == 0.0:
+            return None
+        ang = lambda u, v, lu, lv: float(np.rad2deg(np.arccos(np.clip(np.dot(u, v) / (lu * lv), -1.0, 1.0))))
+        return [la, lb, lc, ang(h[1], h[2], lb, lc), ang(h[0], h[2], la, lc), ang(h[0], h[1], la, lb)]
+
+
+class ConcatXTCFrames(ConcatDCDFrames):
+    """Several XTC files of one system read as one trajectory; ``xtc_block`` stays inside one file."""
+
+    def __init__(self, paths):
+        self.parts = [XTCFrames(p) for p in paths]
+        if not self.parts:
+            raise ValueError("no trajectory files")
+        self.n_atoms = self.parts[0].n_atoms
+        for p, part in zip(paths, self.parts):
+            if part.n_atoms != self.n_atoms:
+                raise ValueError("%s has %d atoms, %s has %d" % (p, part.n_atoms, paths[0], self.n_atoms))
+        self.offsets = np.concatenate([[0], np.cumsum([len(p) for p in self.parts])]).astype(np.int64)
+        self.n_frames = int(self.offsets[-1])
+        self.has_cell = True
+
+    planar_block = None                  # (not a planar source; hbond.py looks for xtc_block first)
+
+    def xtc_block(self, start, stop):
+        k, a = self._locate(start)
+        b = min(int(stop - self.offsets[k]), len(self.parts[k]))
+        return self.parts[k].xtc_block(a, b)
+
+    def xtc_count(self, start, stop):
+        return self.planar_count(start, stop)
+
+
 def universe_from_files(structure, trajectory=None):
-    """``Universe`` from a PDB or PSF file and a DCD trajectory (a PDB alone: its coordinates are the only frame)."""
+    """``Universe`` from a PDB or PSF file and DCD or XTC trajectories (a PDB alone: its coordinates are the only frame)."""
+    import os
     if str(structure).lower().endswith(".psf"):
         if trajectory is None:
             raise ValueError("%s: a PSF topology holds no coordinates, a trajectory is needed" % structure)
@@ -293,7 +389,14 @@ def universe_from_files(structure, trajectory=None):
         topo, xyz, dims = read_pdb(structure)
     if trajectory is None:
         return Universe(topo, xyz[None], dims)
-    frames = ConcatDCDFrames(list(trajectory)) if isinstance(trajectory, (list, tuple)) else DCDFrames(trajectory)
+    paths = list(trajectory) if isinstance(trajectory, (list, tuple)) else [trajectory]
+    exts = {os.path.splitext(str(p))[1].lower() for p in paths}
+    if exts == {".xtc"}:
+        frames = ConcatXTCFrames(paths) if len(paths) > 1 else XTCFrames(paths[0])
+    elif exts == {".dcd"}:
+        frames = ConcatDCDFrames(paths) if len(paths) > 1 else DCDFrames(paths[0])
+    else:
+        raise ValueError("trajectories must be all .dcd or all .xtc files, got %s" % sorted(exts))
     if frames.n_atoms != topo.n_atoms:
         raise ValueError("%s has %d atoms, %s has %d" % (trajectory, frames.n_atoms, structure, topo.n_atoms))
     d0 = frames.dimensions_of(0) if frames.n_frames else None

@@ -91,6 +91,12 @@ SYMBOLS = [
     ("hb_submit_frames", C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
     ("hb_submit_frames_planar", C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P]),
     ("hb_submit_frames_device", C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
+    ("hb_submit_frames_xtc", C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_float, _P]),
+    ("hb_xtc_decode_to_device", C.c_int, [_P, _P, _P, C.c_int64, C.c_int64, C.c_float, _P]),
+    ("hb_xtc_index", C.c_int, [_P, C.c_int64, _P, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    ("hb_xtc_decode_host", C.c_int, [_P, C.c_int64, C.c_int64, C.c_float, _P, _P, C.POINTER(C.c_int64)]),
+    ("hb_xtc_encode", C.c_int, [_P, C.c_int64, C.c_int64, C.c_float, C.c_float, _P, C.c_int64, C.c_float, _P, C.c_int64, _P,
+                                C.POINTER(C.c_int64), C.c_int32]),
     ("hb_finalize_async", C.c_int, [_P]),
     ("hb_pack_keys_device", C.c_int, [_P, _P, C.c_int32]),
     ("hb_finalize", C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
@@ -249,6 +255,24 @@ class Context:
                                                   int(n_atoms), int(n_frames), b.ctypes.data if b is not None else None),
                  "hb_submit_frames_planar")
 
+    def submit_xtc(self, raw, frame_off, n_atoms, n_frames, scale=10.0, box=None):
+        """raw: contiguous uint8 array (or address) holding the XTC records; frame_off: int64 [n_frames + 1] offsets."""
+        b = None
+        if box is not None:
+            b = np.ascontiguousarray(box, dtype=np.float32).reshape(int(n_frames), 9)
+        off = np.ascontiguousarray(frame_off, dtype=np.int64)
+        if len(off) != int(n_frames) + 1:
+            raise ValueError("frame_off must hold n_frames + 1 offsets")
+        ptr = raw if isinstance(raw, int) else raw.ctypes.data
+        self._ck(self.lib.hb_submit_frames_xtc(self.h, ptr, off.ctypes.data, int(n_atoms), int(n_frames), float(scale),
+                                               b.ctypes.data if b is not None else None), "hb_submit_frames_xtc")
+
+    def xtc_decode_to_device(self, raw, frame_off, n_atoms, n_frames, dev_ptr, scale=10.0):
+        off = np.ascontiguousarray(frame_off, dtype=np.int64)
+        ptr = raw if isinstance(raw, int) else raw.ctypes.data
+        self._ck(self.lib.hb_xtc_decode_to_device(self.h, ptr, off.ctypes.data, int(n_atoms), int(n_frames), float(scale),
+                                                  int(dev_ptr)), "hb_xtc_decode_to_device")
+
     def submit_device(self, dev_ptr, n_atoms, n_frames, box_dev_ptr=None):
         self._ck(self.lib.hb_submit_frames_device(self.h, int(dev_ptr), int(n_atoms), int(n_frames),
                                                   int(box_dev_ptr) if box_dev_ptr else None),
@@ -355,3 +379,66 @@ class PinnedBuffer:
             self.array = None
             self.lib.hb_host_free(self.ptr)
             self.ptr = None
+
+
+# ------------------------------------------------------------------------------------------------
+# XTC host helpers (no context, no GPU): index, single-frame decode, writer
+# ------------------------------------------------------------------------------------------------
+def xtc_index(buf):
+    """(int64 offsets [n_frames + 1], n_atoms) of the XTC frame records in the uint8 array `buf`."""
+    lib = load_library()
+    buf = np.asarray(buf)
+    n, na = C.c_int64(), C.c_int64()
+    ptr = buf.ctypes.data if buf.size else None
+    if lib.hb_xtc_index(ptr, buf.size, None, 0, C.byref(n), C.byref(na)) != 0:
+        raise HbError("hb_xtc_index: not an XTC file (or the atom count changes between frames)")
+    off = np.zeros(n.value + 1, dtype=np.int64)
+    if n.value:
+        lib.hb_xtc_index(ptr, buf.size, off.ctypes.data, n.value, C.byref(n), C.byref(na))
+    return off, int(na.value)
+
+
+def xtc_decode_host(buf, offset, n_atoms, scale=10.0):
+    """(float32 [n_atoms, 3], float32 box rows [3, 3] in nm) of the record at buf[offset:], decoded on the CPU."""
+    lib = load_library()
+    buf = np.asarray(buf)
+    xyz = np.empty((int(n_atoms), 3), dtype=np.float32)
+    box = np.empty(9, dtype=np.float32)
+    if lib.hb_xtc_decode_host(buf.ctypes.data + int(offset), buf.size - int(offset), int(n_atoms), float(scale),
+                              xyz.ctypes.data, box.ctypes.data, None) != 0:
+        raise HbError("hb_xtc_decode_host: malformed XTC record")
+    return xyz, box.reshape(3, 3)
+
+
+def xtc_encode(xyz, in_scale=0.1, precision=1000.0, box_nm=None, first_step=0, dt=1.0, n_threads=0):
+    """XTC records of the frames xyz [F, N, 3] (times in_scale = nm): (uint8 array, int64 offsets [F + 1])."""
+    lib = load_library()
+    xyz = np.ascontiguousarray(xyz, dtype=np.float32)
+    nf, na = xyz.shape[0], xyz.shape[1]
+    b = None
+    if box_nm is not None:
+        b = np.ascontiguousarray(np.broadcast_to(np.asarray(box_nm, dtype=np.float32).reshape(-1, 9), (nf, 9)))
+    if n_threads <= 0:
+        n_threads = min(64, os.cpu_count() or 1)
+    cap = nf * (96 + 15 * na + 64)
+    out = np.empty(cap, dtype=np.uint8)
+    off = np.zeros(nf + 1, dtype=np.int64)
+    written = C.c_int64()
+    rc = lib.hb_xtc_encode(xyz.ctypes.data, na, nf, float(in_scale), float(precision), b.ctypes.data if b is not None else None,
+                           int(first_step), float(dt), out.ctypes.data, cap, off.ctypes.data, C.byref(written), int(n_threads))
+    if rc != 0:
+        raise HbError("hb_xtc_encode failed (%d): coordinate out of range?" % rc)
+    return out[:written.value].copy() if written.value < cap // 2 else out[:written.value], off
+
+
+def xtc_decode_device(buf, offsets, n_atoms, scale=10.0, device=0):
+    """Decode XTC records on the GPU and return the frames as a numpy array (tests, spot checks); needs torch."""
+    import torch
+    nf = len(offsets) - 1
+    out = torch.empty((nf, int(n_atoms), 3), dtype=torch.float32, device="cuda:%d" % device)
+    ctx = Context(device)
+    try:
+        ctx.xtc_decode_to_device(np.ascontiguousarray(buf, dtype=np.uint8), offsets, n_atoms, nf, out.data_ptr(), scale)
+    finally:
+        ctx.close()
+    return out.cpu().numpy()

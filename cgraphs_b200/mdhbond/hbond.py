@@ -62,8 +62,8 @@ def _as_universe(structure, trajectories):
             traj = trajectories[0] if isinstance(trajectories, (list, tuple)) and len(trajectories) == 1 else trajectories
             ext = _os.path.splitext(str(structure))[1].lower()
             trajs = [] if traj is None else (list(traj) if isinstance(traj, (list, tuple)) else [traj])
-            if ext not in (".pdb", ".psf") or any(_os.path.splitext(str(t))[1].lower() != ".dcd" for t in trajs):
-                raise ImportError("without MDAnalysis only .pdb / .psf structures with .dcd trajectories can be "
+            if ext not in (".pdb", ".psf") or any(_os.path.splitext(str(t))[1].lower() not in (".dcd", ".xtc") for t in trajs):
+                raise ImportError("without MDAnalysis only .pdb / .psf structures with .dcd / .xtc trajectories can be "
                                   "read; pass a Universe object instead")
             return universe_from_files(structure, traj)
         return _MDAnalysis.Universe(structure, trajectories) if trajectories is not None else _MDAnalysis.Universe(structure)
@@ -343,7 +343,16 @@ class HbondAnalysis(object):
             done = lo
             frames = getattr(self._universe.trajectory, "frames", None)
             sub = fi[lo:hi]
-            if hasattr(frames, "planar_block") and isinstance(sub, range) and sub.step == 1:
+            if hasattr(frames, "xtc_block") and isinstance(sub, range) and sub.step == 1:
+                # XTC: the compressed frame records go to the device as they are and are decoded there
+                i = sub.start
+                while i < sub.stop:
+                    j = i + frames.xtc_count(i, min(sub.stop, i + block))        # (a block ends at a file boundary)
+                    raw, off = frames.xtc_block(i, j)
+                    box = _frame_boxes(self._universe, range(i, j)) if pbc_mode else None
+                    ctx.submit_xtc(raw, off, self._n_atoms, j - i, scale=getattr(frames, "LENGTH_SCALE", 10.0), box=box)
+                    i = j
+            elif getattr(frames, "planar_block", None) is not None and isinstance(sub, range) and sub.step == 1:
                 # trajectory file records go to the device as they are and are decoded (interleaved) there
                 i = sub.start
                 while i < sub.stop:

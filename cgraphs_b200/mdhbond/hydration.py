@@ -109,7 +109,15 @@ class HydrationAnalysis(object):
         block = max(1, min(self.nb_frames, int((256 << 20) // max(1, self._n_atoms * 12))))
         frames = getattr(self._universe.trajectory, "frames", None)
         fi = self._frame_indices
-        if hasattr(frames, "planar_block") and fi.step == 1:
+        if hasattr(frames, "xtc_block") and fi.step == 1:
+            # XTC: compressed frame records, decoded on the device
+            i = fi.start
+            while i < fi.stop:
+                j = i + frames.xtc_count(i, min(fi.stop, i + block))
+                raw, off = frames.xtc_block(i, j)
+                ctx.submit_xtc(raw, off, self._n_atoms, j - i, scale=getattr(frames, "LENGTH_SCALE", 10.0))
+                i = j
+        elif getattr(frames, "planar_block", None) is not None and fi.step == 1:
             # trajectory file records go to the device as they are and are decoded (interleaved) there
             i = fi.start
             while i < fi.stop:

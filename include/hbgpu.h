@@ -17,6 +17,9 @@
  *                     <- the `result` dict handed to _set_results, hbond.py:134 / 288 (basic.py:94-98)
  *   hb_submit_frames_planar
  *                     <- the trajectory reader's frame decode, basic.py:46-47 (DCD X / Y / Z records)
+ *   hb_submit_frames_xtc / hb_xtc_index / hb_xtc_decode_host / hb_xtc_encode
+ *                     <- the same decode for GROMACS .xtc files (MDAnalysis' XTC reader = xdrfile's
+ *                        xdrfile_decompress_coord_float + the float32 nm -> Angstrom conversion), basic.py:46-47
  *   hb_set_ions + HB_METHOD_ION_CONTACTS
  *                     <- set_add_ion_interactions, hbond.py:57-94 (ion group: basic.py:53-60)
  *   hb_set_wires      <- WireAnalysis.set_water_wires, waterwire.py:191-317: the same neighbour search
@@ -193,6 +196,34 @@ int hb_submit_frames(hb_ctx* ctx, const float* xyz, int64_t n_atoms, int64_t n_f
  * skipped) and interleaved there - the decode MDAnalysis' reader does for the reference (basic.py:46-47). */
 int hb_submit_frames_planar(hb_ctx* ctx, const void* raw, int64_t frame_stride, int64_t x_off, int64_t y_off,
                             int64_t z_off, int64_t n_atoms, int64_t n_frames, const float* box);
+
+/* Same, for GROMACS XTC frame records (compressed, about 3.5 bytes per atom): raw + frame_off[f] is the first byte of
+ * frame f's record (magic 1995), frame_off[n_frames] the end of the last one; offsets are multiples of 4 (XDR). The
+ * records are copied to the device as they are and decoded there, one warp per frame, with the arithmetic of the
+ * reader the reference uses through MDAnalysis: x = fl32(fl32(float(int) * fl32(1 / precision)) * scale); scale = 10
+ * gives Angstrom (MDAnalysis' convert_units), 1 leaves nm. box as in hb_submit_frames (the caller reads the cell of a
+ * frame from its record header, see hb_xtc_decode_host). A malformed record makes this or a later call (at the latest
+ * hb_finalize) fail with HB_ERR_ARG. */
+int hb_submit_frames_xtc(hb_ctx* ctx, const void* raw, const int64_t* frame_off, int64_t n_atoms, int64_t n_frames,
+                         float scale, const float* box);
+/* Decode XTC records (host memory) straight into a caller-provided DEVICE buffer float32 [n_frames][n_atoms][3], e.g.
+ * to keep a decoded trajectory resident for hb_submit_frames_device. Synchronous. */
+int hb_xtc_decode_to_device(hb_ctx* ctx, const void* raw, const int64_t* frame_off, int64_t n_atoms, int64_t n_frames,
+                            float scale, float* d_out);
+/* Host helpers for XTC files (no context, no GPU needed).
+ * hb_xtc_index: walk the frame records in buf[0, nbytes): frame_off[0 .. min(n, max_frames)] (may be NULL to count),
+ * *n_frames = n complete records found, *n_atoms their atom count (HB_ERR_ARG if it changes between frames).
+ * hb_xtc_decode_host: decode ONE record on the CPU (frame 0 for the constructor's bonded-hydrogen detection,
+ * network.py:54-86; spot checks): xyz [n_atoms][3] with the arithmetic above, box9 = lattice rows in nm (unscaled).
+ * hb_xtc_encode: write records (test and benchmark inputs): xyz [n_frames][n_atoms][3] times in_scale are nm (0.1 for
+ * Angstrom input), precision 1000 is GROMACS' default, box9 NULL or 9 floats per frame (nm), frame f gets step
+ * first_step + f and time dt * step. out = NULL asks for the size only; frame_off (n_frames + 1, may be NULL) receives
+ * the record offsets; n_threads host threads encode frame blocks in parallel. */
+int hb_xtc_index(const void* buf, int64_t nbytes, int64_t* frame_off, int64_t max_frames, int64_t* n_frames, int64_t* n_atoms);
+int hb_xtc_decode_host(const void* rec, int64_t avail, int64_t n_atoms, float scale, float* xyz, float* box9, int64_t* rec_bytes);
+int hb_xtc_encode(const float* xyz, int64_t n_atoms, int64_t n_frames, float in_scale, float precision, const float* box9,
+                  int64_t first_step, float dt, void* out, int64_t out_cap, int64_t* frame_off, int64_t* bytes_written,
+                  int32_t n_threads);
 
 /* Same, for coordinates already resident in device memory (the caller guarantees they are complete, and keeps
  * d_xyz / d_box valid and unchanged until hb_sync or hb_finalize returns: a batch may be re-run on overflow). */
