@@ -5,15 +5,20 @@
 // decodes one frame into the float32 [atom][3] layout the search kernels read:
 //
 //   The bit stream is a sequence of groups {large atom: `bitsize` bits, flag bit, [5 bits: run + smallidx change],
-//   run / 3 small atoms of `smallidx` bits each}. Where a group starts depends on all groups before it, but as long
-//   as the flag bit is 0 nothing changes, so the warp speculates: lane k assumes the next k groups have no flag
-//   and looks at "its" flag bit; the lanes up to and including the first one that finds a flag are right, all
-//   decode their group in parallel, and the flagged lane's new run / smallidx become the warp's state. In water
-//   (O, H, H: run = 6 for tens of thousands of groups) one step decodes 32 molecules.
-//   A triple (a, b, c) with ranges (sa, sb, sc) is v = (a * sb + b) * sc + c, stored as the bytes of v least
-//   significant first (the last chunk holds the remaining 1..8 bits), bits most significant first: read as a
-//   64-bit big-endian window, byte-swapped, and divided as one integer (128-bit only when nbits > 64).
-//   Decoded atoms are staged in shared memory and stored as full warp-wide float rows.
+//   run / 3 small atoms of `smallidx` bits each}. Where a group starts depends on all groups before it. Per window
+//   of 4 kB of the stream (staged in shared memory with 16-byte loads) the warp works in two phases:
+//   SCAN   finds the groups: as long as the flag bit is 0 nothing changes, so lane k assumes the next k groups have
+//          no flag and looks at "its" flag bit; the lanes up to and including the first one that finds a flag are
+//          right and queue one descriptor each (bit offset, atom index, run, smallidx), the flagged lane's new run /
+//          smallidx become the warp's state. In water (O, H, H: run = 6 for tens of thousands of groups) one step
+//          finds 32 molecules; the dependent chain of a step is two shared-memory reads and a few shuffles.
+//   DECODE takes 32 queued groups at a time, one per lane, whatever their flags were. A triple (a, b, c) with ranges
+//          (sa, sb, sc) is v = (a * sb + b) * sc + c, stored as the bytes of v least significant first (the last
+//          chunk holds the remaining 1..8 bits), bits most significant first: read as a 64-bit big-endian window,
+//          byte-swapped and divided by multiplication with precomputed reciprocals (Granlund-Montgomery; the 73
+//          possible small ranges come from constant memory, the frame's own ranges are derived once per frame;
+//          128-bit arithmetic only when nbits > 64). Decoded atoms are staged in shared memory and stored as full
+//          warp-wide float rows.
 //
 // Arithmetic of the published decoder (xdrfile_decompress_coord_float) and of MDAnalysis' unit conversion:
 //   x = fl32(fl32(float(int) * fl32(1 / precision)) * scale), scale = 10 (nm -> Angstrom), every step rounded.
@@ -25,12 +30,18 @@ namespace {
 
 #define XTC_WARPS 4
 #define XTC_STAGE_ATOMS (32 * 9)
+#define XTC_WIN_BYTES 4096                 // bit-stream window per warp (16 more bytes are loaded behind it)
+#define XTC_QCAP 512                       // group descriptors per window
+#define XTC_GROUP_MAX_BITS 704             // 96 + 1 + 5 + 8 * 72, rounded up
 
 __constant__ int c_xtc_magic[73] = {
     0, 0, 0, 0, 0, 0, 0, 0, 0, 8, 10, 12, 16, 20, 25, 32, 40, 50, 64, 80, 101, 128, 161, 203, 256, 322, 406, 512, 645, 812,
     1024, 1290, 1625, 2048, 2580, 3250, 4096, 5060, 6501, 8192, 10321, 13003, 16384, 20642, 26007, 32768, 41285, 52015,
     65536, 82570, 104031, 131072, 165140, 208063, 262144, 330280, 416127, 524287, 660561, 832255, 1048576, 1321122, 1664510,
     2097152, 2642245, 3329021, 4194304, 5284491, 6658042, 8388607, 10568983, 13316085, 16777216};
+// reciprocals of c_xtc_magic[9..72] for xtc_fastdiv (filled by hb_create through xtc_upload_tables)
+__constant__ unsigned long long c_xtc_mul[73];
+__constant__ int c_xtc_shift[73];
 
 struct XtcRanges {            // atom ranges [b, e) whose coordinates are written (n = 0: all atoms)
     int n;
@@ -38,7 +49,7 @@ struct XtcRanges {            // atom ranges [b, e) whose coordinates are writte
 };
 
 struct XtcArgs {
-    const unsigned char* raw;       // records of the batch, 4-byte aligned, 16 readable bytes past the end
+    const unsigned char* raw;       // records of the batch, 4-byte aligned, 64 readable bytes past the end
     const long long* frame_off;     // [n_frames + 1] byte offsets of the records inside raw
     int n_frames;
     int n_atoms;
@@ -48,13 +59,29 @@ struct XtcArgs {
     XtcRanges ranges;
 };
 
+// n / d for every 64-bit n by one multiplication: d >= 2, l = ceil(log2 d), mul = floor(2^64 (2^l - d) / d) + 1,
+// shift = l - 1:  t = mulhi(mul, n);  q = (t + ((n - t) >> 1)) >> shift      (Granlund & Montgomery 1994, fig. 4.1)
+__host__ __device__ inline void xtc_make_div(unsigned d, unsigned long long& mul, int& shift) {
+    int fl = 0;
+    while ((d >> fl) > 1u) ++fl;                                   // floor(log2 d)
+    const int l = (d & (d - 1u)) ? fl + 1 : fl;
+    const unsigned __int128 num = ((unsigned __int128)1 << 64) * ((((unsigned __int128)1) << l) - d);
+    mul = (unsigned long long)(num / d) + 1ull;
+    shift = l - 1;
+}
+__device__ __forceinline__ unsigned long long xtc_fastdiv(unsigned long long n, unsigned long long mul, int shift) {
+    const unsigned long long t = __umul64hi(mul, n);
+    return (t + ((n - t) >> 1)) >> shift;
+}
+
 __device__ __forceinline__ unsigned xtc_be32(const unsigned char* p) {       // p is 4-byte aligned
     return __byte_perm(*reinterpret_cast<const unsigned*>(p), 0, 0x0123);
 }
-// `n` (1..64) bits of the big-endian bit stream starting at bit `pos` of `data` (4-byte aligned)
-__device__ __forceinline__ unsigned long long xtc_bits(const unsigned char* data, unsigned long long pos, int n) {
-    const unsigned* w = reinterpret_cast<const unsigned*>(data) + (pos >> 5);
-    const unsigned a = __byte_perm(__ldg(w), 0, 0x0123), b = __byte_perm(__ldg(w + 1), 0, 0x0123), c = __byte_perm(__ldg(w + 2), 0, 0x0123);
+// `n` (1..64) bits of the big-endian bit stream starting at bit `pos` of the 4-byte aligned shared-memory window
+// (the window holds the stream as native 32-bit words: byte-swapped when it was staged)
+__device__ __forceinline__ unsigned long long xtc_bits(const unsigned* win, unsigned pos, int n) {
+    const unsigned* w = win + (pos >> 5);
+    const unsigned a = w[0], b = w[1], c = w[2];
     const int s = (int)(pos & 31);
     unsigned long long hi = ((unsigned long long)a << 32) | b;
     if (s) hi = (hi << s) | (c >> (32 - s));
@@ -65,73 +92,72 @@ __device__ __forceinline__ unsigned long long xtc_bswap64(unsigned long long v) 
     return ((unsigned long long)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
 }
 // the integer v of a triple stored in `nbits` (<= 64) bits at `pos`
-__device__ __forceinline__ unsigned long long xtc_triple64(const unsigned char* data, unsigned long long pos, int nbits) {
+__device__ __forceinline__ unsigned long long xtc_triple64(const unsigned* win, unsigned pos, int nbits) {
     const int k = (nbits - 1) >> 3, r = nbits - 8 * k;              // k full bytes, then r = 1..8 bits
-    const unsigned long long w = xtc_bits(data, pos, nbits);
+    const unsigned long long w = xtc_bits(win, pos, nbits);
     const unsigned long long last = w & ((1ull << r) - 1ull);
     unsigned long long v = 0;
     if (k) v = xtc_bswap64((w >> r) << (64 - 8 * k));             // chunk 0 (first in the stream) is the lowest byte
     return v | (last << (8 * k));                                   // k <= 7 here
 }
-
-__device__ __forceinline__ void xtc_split(unsigned long long v, unsigned sb, unsigned sc, int nbits, int& a, int& b, int& c) {
-    if (nbits <= 32) {
-        const unsigned u = (unsigned)v, q = u / sc;
-        c = (int)(u - q * sc);
-        const unsigned q2 = q / sb;
-        b = (int)(q - q2 * sb);
-        a = (int)q2;
-    } else {
-        const unsigned long long q = v / sc;
-        c = (int)(v - q * sc);
-        const unsigned long long q2 = q / sb;
-        b = (int)(q - q2 * sb);
-        a = (int)q2;
-    }
+struct XtcDiv { unsigned d; unsigned long long mul; int shift; };
+// v = (a * sb + b) * sc + c  ->  a, b, c
+__device__ __forceinline__ void xtc_split(unsigned long long v, const XtcDiv& sb, const XtcDiv& sc, int& a, int& b, int& c) {
+    const unsigned long long q = sc.d > 1u ? xtc_fastdiv(v, sc.mul, sc.shift) : v;
+    c = (int)(unsigned)(v - q * sc.d);
+    const unsigned long long q2 = sb.d > 1u ? xtc_fastdiv(q, sb.mul, sb.shift) : q;
+    b = (int)(unsigned)(q - q2 * sb.d);
+    a = (int)(unsigned)q2;
 }
 // general triple (nbits up to 72)
-__device__ __noinline__ void xtc_triple_wide(const unsigned char* data, unsigned long long pos, int nbits, unsigned sb, unsigned sc,
-                                             int& a, int& b, int& c) {
+__device__ __noinline__ void xtc_triple_wide(const unsigned* win, unsigned pos, int nbits, unsigned sb, unsigned sc, int* abc) {
     unsigned __int128 v = 0;
     int shift = 0, left = nbits;
-    while (left > 8) { v |= (unsigned __int128)xtc_bits(data, pos, 8) << shift; pos += 8; shift += 8; left -= 8; }
-    v |= (unsigned __int128)xtc_bits(data, pos, left) << shift;
-    c = (int)(unsigned)(v % sc); v /= sc;
-    b = (int)(unsigned)(v % sb); v /= sb;
-    a = (int)(unsigned)v;
+    while (left > 8) { v |= (unsigned __int128)xtc_bits(win, pos, 8) << shift; pos += 8; shift += 8; left -= 8; }
+    v |= (unsigned __int128)xtc_bits(win, pos, left) << shift;
+    abc[2] = (int)(unsigned)(v % sc); v /= sc;
+    abc[1] = (int)(unsigned)(v % sb); v /= sb;
+    abc[0] = (int)(unsigned)v;
 }
-__device__ __forceinline__ void xtc_triple(const unsigned char* data, unsigned long long pos, int nbits, unsigned sb, unsigned sc,
-                                           int& a, int& b, int& c) {
-    if (nbits <= 64) xtc_split(xtc_triple64(data, pos, nbits), sb, sc, nbits, a, b, c);
-    else xtc_triple_wide(data, pos, nbits, sb, sc, a, b, c);
+__device__ __forceinline__ void xtc_triple(const unsigned* win, unsigned pos, int nbits, const XtcDiv& sb, const XtcDiv& sc, int* abc) {
+    if (nbits <= 64) xtc_split(xtc_triple64(win, pos, nbits), sb, sc, abc[0], abc[1], abc[2]);
+    else xtc_triple_wide(win, pos, nbits, sb.d, sc.d, abc);
 }
 __device__ __forceinline__ int xtc_bit_length(unsigned __int128 v) {
     const unsigned long long hi = (unsigned long long)(v >> 64), lo = (unsigned long long)v;
     return hi ? 128 - __clzll((long long)hi) : (lo ? 64 - __clzll((long long)lo) : 0);
 }
 
-__global__ void __launch_bounds__(XTC_WARPS * 32) k_xtc_decode(XtcArgs A) {
-    __shared__ float stage[XTC_WARPS][XTC_STAGE_ATOMS * 3];
+struct XtcShared {
+    unsigned win[XTC_WIN_BYTES / 4 + 8];          // window of the bit stream (+ 16 bytes read-ahead, + padding)
+    uint2 queue[XTC_QCAP];                        // x: bit offset inside the window, y: atom | nsmall << 20 | flag << 24 | smallidx << 25
+    float stage[XTC_WARPS][XTC_STAGE_ATOMS * 3];
+    unsigned long long pos;                       // stream state, owned by warp 0, published at the end of every scan
+    int i, nq, i_first, bad;
+};
+
+// One CTA (XTC_WARPS warps) per frame: all warps stage the window and decode, warp 0 scans.
+__global__ void __launch_bounds__(XTC_WARPS * 32, 5) k_xtc_decode(XtcArgs A) {
+    __shared__ __align__(16) XtcShared S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int f = blockIdx.x * XTC_WARPS + warp;
-    if (f >= A.n_frames) return;
+    const int f = blockIdx.x;
     const unsigned char* rec = A.raw + A.frame_off[f];
     const long long rec_len = A.frame_off[f + 1] - A.frame_off[f];
     float* out = A.out + (size_t)f * A.n_atoms * 3;
-    float* st = stage[warp];
     const int natoms = A.n_atoms;
-    auto fail = [&]() { if (lane == 0) atomicExch(A.status, 1); };
+    auto fail = [&]() { if (threadIdx.x == 0) atomicExch(A.status, 1); };
+    // (every exit below is taken by the whole CTA: the conditions only depend on the record header)
     if (rec_len < 56 || xtc_be32(rec) != 1995u || (int)xtc_be32(rec + 4) != natoms || (int)xtc_be32(rec + 52) != natoms) { fail(); return; }
+    const int n_ranges = A.ranges.n;
     auto wanted = [&](int atom) {
-        if (A.ranges.n == 0) return true;
+        if (n_ranges == 0) return true;
         bool w = false;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) w = w || (k < A.ranges.n && atom >= A.ranges.b[k] && atom < A.ranges.e[k]);
+        for (int k = 0; k < n_ranges; ++k) w = w || (atom >= A.ranges.b[k] && atom < A.ranges.e[k]);
         return w;
     };
     if (natoms <= 9) {                                   // stored as plain floats
         if (rec_len < 56 + 12ll * natoms) { fail(); return; }
-        for (int k = lane; k < 3 * natoms; k += 32) out[k] = __fmul_rn(__uint_as_float(xtc_be32(rec + 56 + 4 * k)), A.scale);
+        for (int k = threadIdx.x; k < 3 * natoms; k += XTC_WARPS * 32) out[k] = __fmul_rn(__uint_as_float(xtc_be32(rec + 56 + 4 * k)), A.scale);
         return;
     }
     if (rec_len < 92) { fail(); return; }
@@ -143,65 +169,131 @@ __global__ void __launch_bounds__(XTC_WARPS * 32) k_xtc_decode(XtcArgs A) {
         lo[k] = (int)xtc_be32(rec + 60 + 4 * k);
         size[k] = (unsigned)((int)xtc_be32(rec + 72 + 4 * k) - lo[k] + 1);
     }
-    int smallidx = (int)xtc_be32(rec + 84);
+    int smallidx = (int)xtc_be32(rec + 84);          // (kept up to date by warp 0 only)
     const unsigned long long nbits_total = 8ull * xtc_be32(rec + 88);
-    if (smallidx < 9 || smallidx > 72 || 92ull + nbits_total / 8 > (unsigned long long)rec_len) { fail(); return; }
+    if (smallidx < 9 || smallidx > 72 || size[0] == 0 || size[1] == 0 || size[2] == 0 ||
+        92ull + nbits_total / 8 > (unsigned long long)rec_len) { fail(); return; }
     const unsigned char* data = rec + 92;
     const bool wide = (size[0] | size[1] | size[2]) > 0xffffffu;
     int wb[3] = {0, 0, 0}, bitsize;
+    XtcDiv dy{size[1], 0, 0}, dz{size[2], 0, 0};
     if (wide) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) wb[k] = size[k] ? 32 - __clz(size[k]) : 0;      // bits of an int of this range
+        for (int k = 0; k < 3; ++k) wb[k] = 32 - __clz(size[k]);      // bits of an int of this range
         bitsize = wb[0] + wb[1] + wb[2];
     } else {
         bitsize = xtc_bit_length((unsigned __int128)size[0] * size[1] * size[2]);
+        if (size[1] > 1u) xtc_make_div(size[1], dy.mul, dy.shift);
+        if (size[2] > 1u) xtc_make_div(size[2], dz.mul, dz.shift);
     }
     const float inv = (float)(1.0 / (double)precision);
     const float scale = A.scale;
-    int smaller = c_xtc_magic[max(smallidx - 1, 9)] / 2;
-    int smallnum = c_xtc_magic[smallidx] / 2;
-    unsigned ssize = (unsigned)c_xtc_magic[smallidx];
-
-    unsigned long long pos = 0;          // warp-uniform state
-    int i = 0, run = 0;
-    while (i < natoms) {
-        const int per = 1 + run / 3;                                 // atoms of a group without a flag
-        const unsigned long long glen = (unsigned long long)bitsize + 1ull + (unsigned long long)(run / 3) * smallidx;
-        const unsigned long long p = pos + (unsigned long long)lane * glen;
-        const int i0 = i + lane * per;
-        const bool active = i0 < natoms && p + bitsize + 1 <= nbits_total;          // my flag bit lies inside the stream
-        int flag = 0;
-        if (active) flag = (int)xtc_bits(data, p + bitsize, 1);
-        const unsigned am = __ballot_sync(0xffffffffu, active), fm = __ballot_sync(0xffffffffu, active && flag);
-        if (!(am & 1u)) { fail(); return; }                          // lane 0 ran past the end of the stream
-        const int first = fm ? __ffs(fm) - 1 : 32;
-        const int ngroups = min(first + 1, __popc(am));             // active lanes are a prefix
-        const bool mine = lane < ngroups;
-        int myrun = run, change = 0;
-        unsigned long long q = p + bitsize + 1;                      // first small atom of my group
-        if (mine && flag) {
-            const int r5 = p + bitsize + 6 <= nbits_total ? (int)xtc_bits(data, p + bitsize + 1, 5) : 31;   // 31: rejected below
-            change = r5 % 3;
-            myrun = r5 - change;
-            change -= 1;
-            q += 5;
+    if (threadIdx.x == 0) { S.pos = 0; S.i = 0; S.bad = 0; }
+    int run = 0;                                         // warp 0: current run (3 * small atoms per group)
+    __syncthreads();
+    for (;;) {
+        const unsigned long long pos0 = S.pos;           // bit position of the next group
+        const int i_first = S.i;                         // atoms decoded so far
+        if (i_first >= natoms || S.bad) break;
+        // ---- window: 16-byte aligned global address at or before the byte of pos0 -----------------------------------
+        const unsigned long long a0 = ((unsigned long long)(uintptr_t)data + (pos0 >> 3)) & ~15ull;
+        const long long wbase_bits = 8ll * ((long long)a0 - (long long)(uintptr_t)data);      // may be negative (header bytes)
+        {
+            const uint4* g = reinterpret_cast<const uint4*>(a0);
+            uint4* w = reinterpret_cast<uint4*>(S.win);
+            for (int k = threadIdx.x; k < XTC_WIN_BYTES / 16 + 1; k += XTC_WARPS * 32) {
+                uint4 v = __ldg(g + k);
+                v.x = __byte_perm(v.x, 0, 0x0123); v.y = __byte_perm(v.y, 0, 0x0123);
+                v.z = __byte_perm(v.z, 0, 0x0123); v.w = __byte_perm(v.w, 0, 0x0123);
+                w[k] = v;
+            }
+            // the window after this one: into L2 while this one is decoded
+            if (warp == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(a0 + XTC_WIN_BYTES + 128ull * lane));
         }
-        const int nsmall = myrun / 3;
-        if (mine) {
-            if (nsmall > 8 || i0 + 1 + nsmall > natoms || q + (unsigned long long)nsmall * smallidx > nbits_total) {
-                atomicExch(A.status, 1);
-            } else {
+        __syncthreads();
+        // ---- scan (warp 0): queue the groups that lie completely inside the window -----------------------------------
+        if (warp == 0) {
+            const long long wend_bits = wbase_bits + 8ll * XTC_WIN_BYTES;
+            const bool last_window = wend_bits >= (long long)nbits_total;
+            const unsigned end_rel = (unsigned)min((long long)nbits_total - wbase_bits, 1ll << 30);   // stream end, window relative
+            const unsigned lim_rel = last_window ? end_rel : 8u * XTC_WIN_BYTES - XTC_GROUP_MAX_BITS;  // a group may start up to here
+            unsigned prel0 = (unsigned)((long long)pos0 - wbase_bits);
+            int i = i_first, nq = 0;
+            bool bad = false, lane_bad = false;
+            while (i < natoms && nq <= XTC_QCAP - 32) {
+                const int nsm = run / 3;                                    // small atoms of a group without a flag
+                const unsigned glen = (unsigned)bitsize + 1u + (unsigned)nsm * (unsigned)smallidx;
+                const unsigned prel = prel0 + (unsigned)lane * glen;
+                const int i0 = i + lane * (1 + nsm);
+                const bool active = i0 < natoms && prel + bitsize + 1 <= end_rel && (last_window || prel <= lim_rel);
+                // flag bit and the five bits behind it in one read (bits past the end of the stream are never used)
+                unsigned six = 0;
+                if (active) six = (unsigned)xtc_bits(S.win, prel + bitsize, 6);
+                const unsigned am = __ballot_sync(0xffffffffu, active), fm = __ballot_sync(0xffffffffu, six >> 5);
+                if (!(am & 1u)) {
+                    // lane 0 cannot go on: the window is used up (slide it), or the stream ended before the last atom
+                    bad = last_window || nq == 0;
+                    break;
+                }
+                const int first = fm ? __ffs(fm) - 1 : 32;
+                const int ngroups = min(first + 1, __popc(am));             // active lanes are a prefix
+                const bool mine = lane < ngroups;
+                const int flag = (int)(six >> 5);
+                int myrun = run, change = 0;
+                if (flag) {
+                    const int r5 = prel + bitsize + 6 <= end_rel ? (int)(six & 31u) : 31;   // 31: rejected below
+                    change = r5 % 3;
+                    myrun = r5 - change;
+                    change -= 1;
+                }
+                const int nsmall = myrun / 3;
+                const unsigned pnext = prel + (unsigned)bitsize + 1u + (flag ? 5u : 0u) + (unsigned)nsmall * (unsigned)smallidx;
+                lane_bad = lane_bad || (mine && (nsmall > 8 || i0 + 1 + nsmall > natoms || pnext > end_rel));
+                if (mine) S.queue[nq + lane] = make_uint2(prel, (unsigned)(i0 - i_first) | ((unsigned)nsmall << 20) | ((unsigned)flag << 24) |
+                                                                   ((unsigned)smallidx << 25));
+                const int src = ngroups - 1;
+                i = __shfl_sync(0xffffffffu, i0 + 1 + nsmall, src);
+                prel0 = __shfl_sync(0xffffffffu, pnext, src);
+                const int rc = __shfl_sync(0xffffffffu, myrun | ((change + 1) << 8), src);
+                run = rc & 0xff;
+                smallidx += (rc >> 8) - 1;
+                nq += ngroups;
+                if (smallidx < 9 || smallidx > 72 || run > 24) { bad = true; break; }
+            }
+            bad = bad || __any_sync(0xffffffffu, lane_bad);
+            if (lane == 0) {
+                S.pos = (unsigned long long)(wbase_bits + (long long)prel0);
+                S.i = i;
+                S.nq = nq;
+                S.i_first = i_first;
+                if (bad || i > natoms) S.bad = 1;
+            }
+        }
+        __syncthreads();
+        if (S.bad) break;
+        // ---- decode: 32 queued groups per warp and pass ---------------------------------------------------------------
+        const int nq = S.nq, i_end = S.i;
+        float* stage = S.stage[warp];
+        for (int g0 = 32 * warp; g0 < nq; g0 += 32 * XTC_WARPS) {
+            const int g = g0 + lane;
+            const int a_first = (int)(S.queue[g0].y & 0xfffffu);                                  // first atom of this pass
+            const int a_end = g0 + 32 < nq ? (int)(S.queue[g0 + 32].y & 0xfffffu) : i_end - i_first;   // first atom of the next
+            if (g < nq) {
+                const uint2 d = S.queue[g];
+                const unsigned prel = d.x;
+                const int arel = (int)(d.y & 0xfffffu), nsmall = (int)((d.y >> 20) & 15u), flag = (int)((d.y >> 24) & 1u);
+                const int sidx = (int)(d.y >> 25);
                 int big[3];
                 if (wide) {
-                    unsigned long long pp = p;
+                    unsigned pp = prel;
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) { big[k] = wb[k] ? (int)xtc_bits(data, pp, wb[k]) : 0; pp += wb[k]; }
+                    for (int k = 0; k < 3; ++k) { big[k] = (int)xtc_bits(S.win, pp, wb[k]); pp += wb[k]; }
                 } else {
-                    xtc_triple(data, p, bitsize, size[1], size[2], big[0], big[1], big[2]);
+                    xtc_triple(S.win, prel, bitsize, dy, dz, big);
                 }
 #pragma unroll
                 for (int k = 0; k < 3; ++k) big[k] += lo[k];
-                float* o = st + (size_t)(i0 - i) * 3;
+                float* o = stage + (size_t)(arel - a_first) * 3;
                 auto emit = [&](float* dst, const int* v) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) dst[k] = __fmul_rn(__fmul_rn(__int2float_rn(v[k]), inv), scale);
@@ -209,41 +301,45 @@ __global__ void __launch_bounds__(XTC_WARPS * 32) k_xtc_decode(XtcArgs A) {
                 if (nsmall == 0) {
                     emit(o, big);
                 } else {
+                    const XtcDiv ds{(unsigned)c_xtc_magic[sidx], c_xtc_mul[sidx], c_xtc_shift[sidx]};
+                    const int smallnum = c_xtc_magic[sidx] / 2;
+                    const unsigned q = prel + bitsize + 1 + (flag ? 5 : 0);
                     int prev[3] = {big[0], big[1], big[2]};
                     for (int t = 0; t < nsmall; ++t) {
-                        int s[3];
-                        xtc_triple(data, q + (unsigned long long)t * smallidx, smallidx, ssize, ssize, s[0], s[1], s[2]);
+                        int sm[3];
+                        xtc_triple(S.win, q + (unsigned)(t * sidx), sidx, ds, ds, sm);
 #pragma unroll
-                        for (int k = 0; k < 3; ++k) { s[k] += prev[k] - smallnum; prev[k] = s[k]; }
+                        for (int k = 0; k < 3; ++k) { sm[k] += prev[k] - smallnum; prev[k] = sm[k]; }
                         // stream order L, S1, S2, ... is atom order S1, L, S2, ... (the first two were swapped)
-                        emit(o + 3 * (t == 0 ? 0 : t + 1), s);
+                        emit(o + 3 * (t == 0 ? 0 : t + 1), sm);
                     }
                     emit(o + 3, big);
                 }
             }
+            __syncwarp();
+            const int nout = (a_end - a_first) * 3, abase = i_first + a_first;
+            for (int k = lane; k < nout; k += 32)
+                if (wanted(abase + k / 3)) out[(size_t)abase * 3 + k] = stage[k];
+            __syncwarp();
         }
-        // new warp state: from the flagged lane if there was one, else after the last group
-        const int src = ngroups - 1;
-        const int n_i = __shfl_sync(0xffffffffu, i0 + 1 + nsmall, src);
-        const unsigned long long n_pos = __shfl_sync(0xffffffffu, q + (unsigned long long)nsmall * smallidx, src);
-        const int n_run = __shfl_sync(0xffffffffu, myrun, src), n_change = __shfl_sync(0xffffffffu, change, src);
-        __syncwarp();
-        const int nout = min(n_i, natoms) - i;                      // atoms staged in this step
-        for (int k = lane; k < nout * 3; k += 32)
-            if (wanted(i + k / 3)) out[(size_t)i * 3 + k] = st[k];
-        __syncwarp();
-        if (n_i <= i || n_i > natoms || n_run > 24) { fail(); return; }
-        i = n_i;
-        pos = n_pos;
-        run = n_run;
-        if (n_change) {
-            smallidx += n_change;
-            if (smallidx < 9 || smallidx > 72) { fail(); return; }
-            if (n_change < 0) { smallnum = smaller; smaller = smallidx > 9 ? c_xtc_magic[smallidx - 1] / 2 : 0; }
-            else { smaller = smallnum; smallnum = c_xtc_magic[smallidx] / 2; }
-            ssize = (unsigned)c_xtc_magic[smallidx];
-        }
+        __syncthreads();                                 // the window and the queue are rewritten next
     }
+    if (S.bad) fail();
+}
+
+// reciprocal tables of the 64 small ranges (host; once per device)
+inline cudaError_t xtc_upload_tables() {
+    static const int magic[73] = {
+        0, 0, 0, 0, 0, 0, 0, 0, 0, 8, 10, 12, 16, 20, 25, 32, 40, 50, 64, 80, 101, 128, 161, 203, 256, 322, 406, 512, 645, 812,
+        1024, 1290, 1625, 2048, 2580, 3250, 4096, 5060, 6501, 8192, 10321, 13003, 16384, 20642, 26007, 32768, 41285, 52015,
+        65536, 82570, 104031, 131072, 165140, 208063, 262144, 330280, 416127, 524287, 660561, 832255, 1048576, 1321122, 1664510,
+        2097152, 2642245, 3329021, 4194304, 5284491, 6658042, 8388607, 10568983, 13316085, 16777216};
+    unsigned long long mul[73] = {0};
+    int shift[73] = {0};
+    for (int k = 9; k < 73; ++k) xtc_make_div((unsigned)magic[k], mul[k], shift[k]);
+    cudaError_t e = cudaMemcpyToSymbol(c_xtc_mul, mul, sizeof(mul));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_xtc_shift, shift, sizeof(shift));
+    return e;
 }
 
 }  // namespace

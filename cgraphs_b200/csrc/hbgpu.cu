@@ -44,9 +44,9 @@
 
 namespace {
 
-enum KernelClass { KC_INIT = 0, KC_GATHER, KC_GRID, KC_COUNT, KC_SCAN, KC_SCATTER, KC_LOCAL, KC_PAIRS, KC_FUSED, KC_WIRES, KC_N };
+enum KernelClass { KC_INIT = 0, KC_GATHER, KC_GRID, KC_COUNT, KC_SCAN, KC_SCATTER, KC_LOCAL, KC_PAIRS, KC_FUSED, KC_WIRES, KC_XTC, KC_N };
 const char* const kKernelNames[KC_N] = {"init_frames", "gather_sel", "grid_setup", "cell_count",
-                                        "cell_scan", "cell_scatter", "local_water", "pairs", "frame_fused", "wire_bfs"};
+                                        "cell_scan", "cell_scatter", "local_water", "pairs", "frame_fused", "wire_bfs", "xtc_decode"};
 
 }  // namespace
 
@@ -358,6 +358,11 @@ int hb_create(hb_ctx** out, int device) {
                          std::to_string(ctx->prop.minor);
         delete ctx;
         return HB_ERR_NODEVICE;
+    }
+    if ((e = xtc_upload_tables()) != cudaSuccess) {
+        g_create_error = std::string("constant tables: ") + cudaGetErrorString(e);
+        delete ctx;
+        return HB_ERR_CUDA;
     }
     cudaStreamCreateWithFlags(&ctx->s_own, cudaStreamNonBlocking);
     ctx->s_compute = ctx->s_own;
@@ -1527,7 +1532,7 @@ int hb_submit_frames_planar(hb_ctx* ctx, const void* raw, int64_t frame_stride, 
 static int check_xtc_status(hb_ctx* ctx) {        // after the copy stream has drained
     if (ctx->h_xtc_status && *ctx->h_xtc_status) {
         *ctx->h_xtc_status = 0;
-        if (ctx->d_xtc_status) cudaMemsetAsync(ctx->d_xtc_status, 0, sizeof(int), ctx->s_copy);
+        if (ctx->d_xtc_status) cudaMemsetAsync(ctx->d_xtc_status, 0, sizeof(int), ctx->s_compute);
         return fail(ctx, HB_ERR_ARG, "hb_submit_frames_xtc: malformed XTC frame record (magic, atom count or bit stream)");
     }
     return HB_OK;
@@ -1614,18 +1619,18 @@ int hb_xtc_decode_to_device(hb_ctx* ctx, const void* raw, const int64_t* frame_o
     std::vector<long long> rel((size_t)n_frames + 1);
     for (int64_t f = 0; f <= n_frames; ++f) rel[f] = frame_off[f] - b0;
     int status = 0;
-    cudaError_t e = cudaMalloc((void**)&d_raw, bytes + 64);
+    cudaError_t e = cudaMalloc((void**)&d_raw, bytes + 16384);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_off, rel.size() * 8);
     if (e == cudaSuccess) e = cudaMalloc((void**)&d_status, sizeof(int));
     if (e == cudaSuccess) e = cudaMemsetAsync(d_status, 0, sizeof(int), ctx->s_copy);
-    if (e == cudaSuccess) e = cudaMemsetAsync(d_raw + bytes, 0, 64, ctx->s_copy);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_raw + bytes, 0, 16384, ctx->s_copy);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_raw, (const unsigned char*)raw + b0, bytes, cudaMemcpyHostToDevice, ctx->s_copy);
     if (e == cudaSuccess) e = cudaMemcpyAsync(d_off, rel.data(), rel.size() * 8, cudaMemcpyHostToDevice, ctx->s_copy);
     if (e == cudaSuccess) {
         XtcArgs xa{};
         xa.raw = d_raw; xa.frame_off = d_off; xa.n_frames = (int)n_frames; xa.n_atoms = (int)n_atoms; xa.scale = scale;
         xa.out = d_out; xa.status = d_status;
-        k_xtc_decode<<<(unsigned)((n_frames + XTC_WARPS - 1) / XTC_WARPS), XTC_WARPS * 32, 0, ctx->s_copy>>>(xa);
+        k_xtc_decode<<<(unsigned)n_frames, XTC_WARPS * 32, 0, ctx->s_copy>>>(xa);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(&status, d_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_copy);
@@ -1661,8 +1666,8 @@ int hb_submit_frames_xtc(hb_ctx* ctx, const void* raw, const int64_t* frame_off,
     bool pinned = cudaPointerGetAttributes(&attr, raw) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
     // raw buffers: half the bytes of the decoded frames (a record takes 3 - 5 bytes per atom), at least one record
-    if ((rc = ensure_input_buffers(ctx, std::max((size_t)n_atoms * 12 * (size_t)n_frames, 2 * max_rec + 1024), pinned, 1, 2))) return rc;
-    if (max_rec + 64 > ctx->raw_alloc) return fail(ctx, HB_ERR_NOMEM, "hb_submit_frames_xtc: a frame record does not fit the input buffer (raise batch_bytes)");
+    if ((rc = ensure_input_buffers(ctx, std::max((size_t)n_atoms * 12 * (size_t)n_frames, 2 * max_rec + 65536), pinned, 1, 2))) return rc;
+    if (max_rec + 16384 > ctx->raw_alloc) return fail(ctx, HB_ERR_NOMEM, "hb_submit_frames_xtc: a frame record does not fit the input buffer (raise batch_bytes)");
     if (!ctx->d_xtc_status) {
         CK(cudaMalloc((void**)&ctx->d_xtc_status, sizeof(int)));
         CK(cudaMemset(ctx->d_xtc_status, 0, sizeof(int)));
@@ -1695,7 +1700,7 @@ int hb_submit_frames_xtc(hb_ctx* ctx, const void* raw, const int64_t* frame_off,
         long long f0 = ctx->next_frame;
         int nf = next_batch_frames(ctx, f0, n_frames - done, true);
         nf = (int)std::min<long long>(nf, (long long)ctx->xoff_cap - 1);
-        while (nf > 1 && (size_t)(frame_off[done + nf] - frame_off[done]) + 64 > ctx->raw_alloc) --nf;
+        while (nf > 1 && (size_t)(frame_off[done + nf] - frame_off[done]) + 16384 > ctx->raw_alloc) --nf;   // (the decoder reads windows ahead)
         const int64_t b0 = frame_off[done];
         const size_t bytes = (size_t)(frame_off[done + nf] - b0);
         int k = (int)(ctx->batch_counter & 1);
@@ -1730,14 +1735,18 @@ int hb_submit_frames_xtc(hb_ctx* ctx, const void* raw, const int64_t* frame_off,
         xa.out = ctx->d_in[k];
         xa.status = ctx->d_xtc_status;
         xa.ranges = xr;
-        k_xtc_decode<<<(nf + XTC_WARPS - 1) / XTC_WARPS, XTC_WARPS * 32, 0, ctx->s_copy>>>(xa);
-        CK(cudaGetLastError());
-        ctx->tm.n_launches += 1;
-        CK(cudaMemcpyAsync(ctx->h_xtc_status, ctx->d_xtc_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_copy));
         cudaEventRecord(c1, ctx->s_copy);
         ctx->pending.push_back({c0, c1, -2});
         CK(cudaEventRecord(ctx->ev_copied[k], ctx->s_copy));
         CK(cudaStreamWaitEvent(ctx->s_compute, ctx->ev_copied[k], 0));
+        // the decode runs on the compute stream, in front of the search of its batch: the copy stream goes straight on
+        // with the records of the next batch
+        {
+            KTimer t(ctx, KC_XTC);
+            k_xtc_decode<<<nf, XTC_WARPS * 32, 0, ctx->s_compute>>>(xa);
+        }
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->h_xtc_status, ctx->d_xtc_status, sizeof(int), cudaMemcpyDeviceToHost, ctx->s_compute));
         if ((rc = launch_in_slot(ctx, k, ctx->d_in[k], f0, nf, n_atoms, (size_t)nf * n_atoms * 12, pbc ? ctx->d_box[k] : nullptr))) return rc;
         ctx->batch_counter++;
         ctx->next_frame += nf;
@@ -1778,14 +1787,13 @@ int hb_sync(hb_ctx* ctx) {
     if (!ctx) return HB_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->s_copy));
-    { int rcx = check_xtc_status(ctx); if (rcx) return rcx; }
     if (ctx->running) {
         int rc = full_verify(ctx);
         if (rc) return rc;
     }
     CK(cudaStreamSynchronize(ctx->s_compute));
     drain_events(ctx);
-    return HB_OK;
+    return check_xtc_status(ctx);
 }
 
 // Queue compaction, key sort and row gather behind the search. Small tables (the common case) are handled
@@ -1909,7 +1917,6 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
     int n = 0;
     bool settled = false;             // ev_run1 recorded and the stream drained
     CK(cudaStreamSynchronize(ctx->s_copy));
-    if ((rc = check_xtc_status(ctx))) return rc;
     for (int attempt = 0;; ++attempt) {
         if (attempt > 40) return fail(ctx, HB_ERR_NOMEM, "hb_finalize: the bond table kept overflowing");
         if (!ctx->fin_queued && (rc = queue_finalize(ctx, finalize_can_speculate(ctx), &n))) return rc;
@@ -1939,6 +1946,11 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
     if (!settled) {
         CK(cudaEventRecord(ctx->ev_run1, st));
         CK(cudaStreamSynchronize(st));
+    }
+    if ((rc = check_xtc_status(ctx))) {      // a frame record was malformed: the run is void
+        ctx->running = false;
+        ctx->fin_queued = false;
+        return rc;
     }
     {
         float ms = 0.f;

@@ -360,19 +360,20 @@ class Context:
 
 
 class PinnedBuffer:
-    """float32 numpy array over cudaHostAlloc memory."""
+    """numpy array (float32 unless `dtype` says otherwise) over cudaHostAlloc memory."""
 
-    def __init__(self, shape):
+    def __init__(self, shape, dtype=np.float32):
         lib = load_library()
         self.lib = lib
+        dt = np.dtype(dtype)
         n = int(np.prod(shape))
         p = _P()
-        rc = lib.hb_host_alloc(C.byref(p), n * 4)
+        rc = lib.hb_host_alloc(C.byref(p), max(n * dt.itemsize, 16))
         if rc != 0:
-            raise HbError("hb_host_alloc(%d bytes) failed" % (n * 4))
+            raise HbError("hb_host_alloc(%d bytes) failed" % (n * dt.itemsize))
         self.ptr = p.value
-        buf = (C.c_float * n).from_address(self.ptr)
-        self.array = np.frombuffer(buf, dtype=np.float32).reshape(shape)
+        buf = (C.c_uint8 * (n * dt.itemsize)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dt).reshape(shape)
 
     def free(self):
         if self.ptr:

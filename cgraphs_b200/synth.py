@@ -69,6 +69,8 @@ _K_HEAVY = 4
 _K_H = 2
 SIGMA_HEAVY = 0.35
 SIGMA_H = 0.05
+FILLER_AMPLITUDE = 0.3  # fraction of the heavy-atom displacement the inert filler atoms get
+SIGMA_INTRA = 0.03     # internal jitter of the heavy atoms of a (rigidly moving) protein residue
 
 
 def _random_unit(rng, n):
@@ -173,6 +175,20 @@ class SynthSystem:
         self._nu_h = rng.uniform(0.01, 0.2, size=(n, 3, _K_H)).astype(np.float32)
         self._phi_h = rng.uniform(0.0, 1.0, size=(n, 3, _K_H)).astype(np.float32)
         self._is_h = self.parent != np.arange(n)
+        # protein residues move as rigid bodies (all heavy atoms follow the residue's first atom) plus a small internal
+        # jitter, like bonded atoms in a real trajectory: independent 0.35 A displacements of bonded neighbours put
+        # atoms 0.1 A apart now and then, which no force field allows (and which the XTC compression of real
+        # trajectories, coded relative to the previous atom, never sees). Waters and filler atoms move as before.
+        prot = np.isin(np.asarray(topology.resnames, dtype=object), list(TEMPLATES))
+        first_of_res = np.zeros(n, dtype=np.int64)
+        ri = np.asarray(topology.resindices)
+        starts = np.nonzero(np.concatenate([[True], ri[1:] != ri[:-1]]))[0] if n else np.zeros(0, np.int64)
+        first_of_res = starts[np.searchsorted(starts, np.arange(n), side="right") - 1] if n else first_of_res
+        self.anchor = np.where(prot, first_of_res, np.arange(n)).astype(np.int64)
+        self._w = np.where(self._is_h, 1.0, np.where(prot, SIGMA_INTRA / SIGMA_H, 0.0)).astype(np.float32)
+        # inert filler atoms (a 2.15 A lattice standing in for a membrane) keep their distance: smaller amplitude
+        filler = np.asarray(topology.resnames, dtype=object) == "POPC"
+        self._amp = np.where(filler, np.float32(FILLER_AMPLITUDE), np.float32(1.0)).astype(np.float32)
         self._torch = {}
 
     @property
@@ -195,9 +211,9 @@ class SynthSystem:
         for i, f in enumerate(range(f0, f1)):
             ff = np.float32(f)
             dh = (np.cos(two_pi * (self._nu * ff + self._phi))).sum(axis=2, dtype=np.float32) * a_heavy
-            d = dh[self.parent]
+            d = (dh * self._amp[:, None])[self.anchor[self.parent]]
             dw = (np.cos(two_pi * (self._nu_h * ff + self._phi_h))).sum(axis=2, dtype=np.float32) * a_h
-            d = d + dw * self._is_h[:, None].astype(np.float32)
+            d = d + dw * self._w[:, None]
             out[i] = self.ref + d
         return out
 
@@ -208,9 +224,8 @@ class SynthSystem:
         key = str(device)
         if key not in self._torch:
             t = lambda a: torch.as_tensor(a, device=device)
-            self._torch[key] = dict(ref=t(self.ref), parent=t(self.parent), nu=t(self._nu), phi=t(self._phi),
-                                    nu_h=t(self._nu_h), phi_h=t(self._phi_h),
-                                    is_h=t(self._is_h.astype(np.float32)))
+            self._torch[key] = dict(ref=t(self.ref), parent=t(self.anchor[self.parent]), nu=t(self._nu), phi=t(self._phi),
+                                    nu_h=t(self._nu_h), phi_h=t(self._phi_h), is_h=t(self._w), amp=t(self._amp))
         p = self._torch[key]
         nf = f1 - f0
         if out is None:
@@ -222,7 +237,7 @@ class SynthSystem:
             e = min(nf, s + chunk)
             ff = torch.arange(f0 + s, f0 + e, device=device, dtype=torch.float32).view(-1, 1, 1, 1)
             dh = torch.cos(2.0 * np.pi * (p["nu"][None] * ff + p["phi"][None])).sum(dim=3) * a_heavy
-            d = dh[:, p["parent"], :]
+            d = (dh * p["amp"][None, :, None])[:, p["parent"], :]
             dw = torch.cos(2.0 * np.pi * (p["nu_h"][None] * ff + p["phi_h"][None])).sum(dim=3) * a_h
             out[s:e] = p["ref"][None] + d + dw * p["is_h"][None, :, None]
         return out
