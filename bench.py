@@ -1,21 +1,28 @@
 #!/usr/bin/env python
 """Benchmark of the H-bond hot path on BASELINE.json's headline workload.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling weak|strong]
 
 Workload (config C3): 100,000-atom membrane-protein-like synthetic system x 10,000 frames, triclinic
 box, `set_hbonds_in_selection_and_water_around(3.5)`, 3.5 A + 60 deg angle criterion, selection `protein`.
-One "step" = one full pass of the hot path over all 10,000 frames.
+One "step" = one full pass of the hot path over all frames of the rank.
 
-* `value`  : frames/s with the frames already resident in HBM (hb_submit_frames_device), device-timed.
-* `e2e`    : frames/s through the C ABI with HOST (pinned) frames: H2D streaming of all frames and the D2H
-             read of bond keys + occupancy matrix inside the timed region.
+* `value`   : frames/s with the frames already resident in HBM (hb_submit_frames_device), device-timed.
+* `parity`  : the CPU oracle port runs on the first frames of the very trajectory the GPU searched; the GPU's
+              occupancy columns of those frames must equal the port's result dict, else the run exits non-zero.
+* `e2e`     : frames/s through the C ABI with HOST (pinned) buffers inside the timed region: the XTC records of
+              the trajectory (compressed, ~4 bytes per atom; decoded on the device) when that is the faster
+              source, else the float32 frames; both legs are reported (`e2e_f32`, `e2e_xtc`), and `e2e_class`
+              is the call a cgraphs user makes (HbondAnalysis.set_hbonds_in_selection_and_water_around on a
+              numpy-backed Universe, result dict built).
 * `roofline`: algorithmic bytes of the dominant kernel / its CUDA-event time, against the measured HBM peak.
 * `cpu_baseline`: the CPU oracle port (1 core) on a bounded sample of the same frames.
-* `--impl reference`: the CPU path with all host cores on a bounded sample per step.
+* `--impl reference`: the reference's own CPU code (oracle/_ref, byte-compiled from /root/reference by
+              oracle/make_ref.py) when present, else the validated port; all host cores, bounded sample per step.
 
-Multi-GPU (torchrun, one rank per GPU): weak scaling - every rank processes its own 10,000-frame block of
-one long trajectory; the only exchange is the all-gather of distinct bond keys at the end of each pass.
+Multi-GPU (torchrun, one rank per GPU): frames are sharded, the only exchange is the all-gather of distinct
+bond keys at the end of each pass. `--scaling weak` (default): every rank processes its own `--frames` block
+of one long trajectory; `--scaling strong`: `--frames` is the total, split over the ranks.
 """
 from __future__ import annotations
 
@@ -170,38 +177,141 @@ def cpu_port_rate(system, cfg, frames_xyz, n_procs, pool=None):
     return len(frames_xyz) / dt, dt
 
 
+def _ref_available():
+    return os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "cgraphs", "mdhbond", "hbond.pyc"))
+
+
+def _ref_process(conn, topology, dims, xyz):
+    """A worker that owns ONE reference HbondAnalysis (built once, like ours) over its frame block and runs the
+    reference's own frame loop (hbond.py:232-289) every time it is told to."""
+    os.environ["CGRAPHS_REF"] = os.path.join(ROOT, "oracle", "_ref", "cgraphs")
+    from oracle import ref_harness
+    from cgraphs_b200.universe import Universe
+    ref = ref_harness.load_reference()
+    hba = ref.HbondAnalysis(SELECTION, Universe(topology, xyz, dims), check_angle=True)
+    conn.send("ready")
+    while True:
+        cmd = conn.recv()
+        if cmd == "stop":
+            break
+        t = time.perf_counter()
+        hba.set_hbonds_in_selection_and_water_around(AROUND)
+        conn.send((time.perf_counter() - t, len(hba.initial_results)))
+
+
 def run_reference_arm(args):
-    """The CPU path on all host cores: the validated port (the reference itself needs /root/reference and
-    MDAnalysis stubs, which do not travel to the GPU box), frame-sharded over one process per core."""
+    """The reference's CPU implementation on all host cores, frame-sharded over one process per core: the reference
+    itself (oracle/_ref: the reference's mdhbond package byte-compiled by oracle/make_ref.py, run through MDAnalysis
+    stubs) when it travelled to this box, else the validated port."""
     rank = env_int("RANK", 0)
     if rank != 0:
         return 0
     import multiprocessing as mp
-    scale = args.scale
-    system, cfg = build_case(scale, args.frames)
+    system, cfg = build_case(args.scale, args.frames)
     cores = os.cpu_count() or 1
-    per_step = int(min(512, max(cores * 16, 64)))
+    use_ref = _ref_available() and not args.port_baseline
+    per_step = int(min(512, max(cores * (4 if use_ref else 16), 64)))
     xyz = system.frames(0, per_step)
-    _CPU_SHARED.update(pt=cpu_port_topology(system, cfg, xyz), xyz=xyz, method="water_around", around=AROUND)
     ctx = mp.get_context("fork")
     times = []
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(0, 1)] * cores, chunksize=1)          # spin-up, untimed
+    if use_ref:
+        bounds = np.linspace(0, per_step, cores + 1).astype(int)
+        blocks = [xyz[a:b] for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+        procs = []
+        for blk in blocks:
+            parent, child = ctx.Pipe()
+            pr = ctx.Process(target=_ref_process, args=(child, system.topology, system.dimensions, blk), daemon=True)
+            pr.start()
+            procs.append((pr, parent))
+        for _, c in procs:
+            c.recv()                                                     # constructors done (untimed, like ours)
+
+        def step():
+            t = time.perf_counter()
+            for _, c in procs:
+                c.send("run")
+            for _, c in procs:
+                c.recv()
+            return time.perf_counter() - t
+
+        step()                                                           # first run, untimed
         for i in range(args.warmup + args.steps):
-            rate, dt = cpu_port_rate(system, cfg, xyz, cores, pool)
+            dt = step()
             if i >= args.warmup:
                 times.append(dt)
+        for pr, c in procs:
+            c.send("stop")
+        for pr, c in procs:
+            pr.join(timeout=10)
+        kind, what = "reference", "cgraphs.mdhbond.HbondAnalysis (oracle/_ref, unmodified, MDAnalysis stubbed)"
+    else:
+        _CPU_SHARED.update(pt=cpu_port_topology(system, cfg, xyz), xyz=xyz, method="water_around", around=AROUND)
+        with ctx.Pool(cores) as pool:
+            pool.map(_cpu_worker, [(0, 1)] * cores, chunksize=1)          # spin-up, untimed
+            for i in range(args.warmup + args.steps):
+                rate, dt = cpu_port_rate(system, cfg, xyz, cores, pool)
+                if i >= args.warmup:
+                    times.append(dt)
+        kind, what = "port", "oracle/hbond_port.py"
     ms = 1000.0 * float(np.mean(times))
     value = per_step / (ms / 1000.0)
-    sample = "%d frames of the %d-atom workload per step, frame-sharded over %d processes" % (per_step, system.n_atoms, cores)
+    sample = "%d frames of the %d-atom workload per step, frame-sharded over %d processes, %s" % (
+        per_step, system.n_atoms, cores, what)
     line = {"impl": "reference", "metric": "hbond_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64 distance / f32 angle", "data": "synthetic",
-            "config": workload_config(system, cfg, args),
-            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": workload_config(system, cfg, args, env_int("WORLD_SIZE", 1)),
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
+
+
+def results_of(keys, words, group_names, n_cols):
+    """{key string: bool[n_cols]} of the rows that have a bond in the first n_cols frames."""
+    from cgraphs_b200.mdhbond import HbondAnalysis
+    full = HbondAnalysis._results_dict(keys, words, group_names, words.shape[1] * 32)
+    out = {}
+    for k, v in full.items():
+        if v[:n_cols].any():
+            out[k] = v[:n_cols].copy()
+    return out
+
+
+def parity_object(gpu, cpu, n_frames, what):
+    a = {k: v.tobytes() for k, v in gpu.items()}
+    b = {k: np.asarray(v, dtype=bool)[:n_frames].tobytes() for k, v in cpu.items() if np.asarray(v)[:n_frames].any()}
+    equal = a == b
+    out = {"checked_against": what, "frames": int(n_frames), "keys": len(b), "equal": bool(equal)}
+    if not equal:
+        out["only_gpu"] = sorted(set(a) - set(b))[:5]
+        out["only_cpu"] = sorted(set(b) - set(a))[:5]
+        out["different_rows"] = sorted(k for k in set(a) & set(b) if a[k] != b[k])[:5]
+    return out
+
+
+def bind_near_gpu(local_rank):
+    """Pin this process to the CPUs next to its GPU (NVML's ideal affinity) so that the pinned host buffers it
+    allocates afterwards land on that NUMA node (first touch) and its copy threads run there."""
+    info = {"bound": False}
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        info = {"bound": True, "cpus": "%d-%d (%d of %d)" % (cpus[0], cpus[-1], len(cpus), before)}
+        try:
+            bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+            node = open("/sys/bus/pci/devices/%s/numa_node" % bus.lower()[-12:]).read().strip()
+            info["numa_node"] = int(node)
+        except Exception:
+            pass
+    except Exception as e:
+        info["error"] = repr(e)[:120]
+    return info
 
 
 def wires_leg(args, system, d_xyz, local_rank, peak, bytes_frame):
@@ -270,25 +380,38 @@ def wires_leg(args, system, d_xyz, local_rank, peak, bytes_frame):
         finally:
             pin.free()
     if not args.no_cpu:
-        from oracle import hbond_port                   # CPU baseline leg: the validated port on a bounded sample
+        # CPU baseline leg + parity gate: the validated port on the first frames; the GPU's wire lengths of those frames
+        # (a fresh run over exactly these frames through the drop-in class) must be the same dict
+        from oracle import hbond_port
+        from cgraphs_b200.universe import Universe
         n_cpu = 4
         sample = d_xyz[:n_cpu].cpu().numpy()
-        from cgraphs_b200.universe import Universe
+        u = Universe(system.topology, sample, system.dimensions)
         t0 = time.perf_counter()
-        hbond_port.run_wires(Universe(system.topology, sample, system.dimensions), SELECTION, max_water=max_water)
+        ref = hbond_port.run_wires(u, SELECTION, max_water=max_water)
         dt = time.perf_counter() - t0
         out["cpu_baseline"] = {"value": n_cpu / dt, "unit": "frames/s", "cores": 1, "kind": "port",
                                "sample": "first %d frames, oracle/hbond_port.py run_wires (%.1f s)" % (n_cpu, dt)}
+        wg = WireAnalysis(SELECTION, u, device=local_rank)
+        wg.set_water_wires(max_water=max_water)
+        lists = lambda d: {k: [(-1 if not np.isfinite(x) else int(x)) for x in v] for k, v in d.items()}
+        got, want = lists(wg.wire_lengths), lists(ref.wire_lengths)
+        out["parity"] = {"checked_against": "oracle/hbond_port.py run_wires", "frames": n_cpu, "keys": len(want),
+                         "equal": bool(got == want)}
     return out
 
 
-def workload_config(system, cfg, args):
-    return {"workload": "C3: %d-atom membrane-protein-like system x %d frames per GPU, triclinic box, "
+def workload_config(system, cfg, args, world):
+    nf_total = args.frames if args.scaling == "strong" else args.frames * world
+    return {"workload": "C3: %d-atom membrane-protein-like system x %d frames %s, triclinic box, "
                         "set_hbonds_in_selection_and_water_around(3.5), 3.5 A + 60 deg, selection 'protein'"
-                        % (system.n_atoms, args.frames),
-            "n_atoms": system.n_atoms, "n_frames_per_gpu": args.frames, "selection": SELECTION, "method": "water_around",
+                        % (system.n_atoms, args.frames, "in total, sharded over the GPUs" if args.scaling == "strong" else "per GPU"),
+            "n_atoms": system.n_atoms, "n_frames_per_gpu": args.frames if args.scaling == "weak" else None,
+            "n_frames_total": nf_total, "scaling": args.scaling,
+            "selection": SELECTION, "method": "water_around",
             "check_angle": True, "pbc": "none (reference semantics; skin system)",
-            "cache": "inputs (%.1f GB of frames per GPU) are far larger than the 126 MB L2" % (system.n_atoms * 12 * args.frames / 1e9)}
+            "cache": "inputs (%.1f GB of frames per GPU) are far larger than the 126 MB L2"
+                     % (system.n_atoms * 12 * (nf_total / world) / 1e9)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -301,13 +424,14 @@ def run_ours(args):
     from cgraphs_b200.mdhbond import HbondAnalysis, _native
     from cgraphs_b200.mdhbond.calib import cos_threshold
     from cgraphs_b200.mdhbond.topology import pack_systems
-    from cgraphs_b200.mdhbond.sharding import exchange_keys_queued, merge_keys, merge_keys_device
+    from cgraphs_b200.mdhbond.sharding import exchange_keys_queued, merge_keys, merge_keys_device, shard_range
 
     world = env_int("WORLD_SIZE", 1)
     rank = env_int("RANK", 0)
     local_rank = env_int("LOCAL_RANK", 0)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: no CUDA device is visible (there is no CPU fallback)")
+    numa = bind_near_gpu(local_rank) if not args.no_numa else {"bound": False}
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dist = None
@@ -316,8 +440,17 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     system, cfg = build_case(args.scale, args.frames)
-    nf, na = args.frames, system.n_atoms
-    f0 = rank * nf                                      # weak scaling: each rank owns its own frame block
+    na = system.n_atoms
+    if args.scaling == "strong":                        # args.frames frames in total, contiguous blocks of multiples of 32
+        f0, f1 = shard_range(args.frames, rank, world)
+        nf = f1 - f0
+        nf_total = args.frames
+    else:                                               # weak: each rank owns its own block of args.frames frames
+        nf = args.frames
+        f0 = rank * nf
+        nf_total = nf * world
+    if nf < 1:
+        raise SystemExit("bench: rank %d has no frames (%d frames over %d ranks)" % (rank, args.frames, world))
     # frames generated on the device (synthetic data), then one copy to pinned host memory for the e2e arm
     d_xyz = torch.empty((nf, na, 3), dtype=torch.float32, device=dev)
     system.frames_torch(f0, f0 + nf, dev, out=d_xyz)
@@ -403,62 +536,148 @@ def run_ours(args):
             raise SystemExit("bench: the key gather overflowed its learnt capacity inside the timed loop")
         n_global_keys = n_out
     clocks = sampler.stop()
+    # the device-resident result of this rank (same state every pass), kept for the parity gate below
+    ctx.begin(nf)
+    ctx.submit_device(d_xyz.data_ptr(), na, nf)
+    dev_keys, dev_words = ctx.results()
     # max over ranks of the device-timed pass (CUDA events begin -> finalize), cross-checked by wall clock
     t = torch.tensor([dev_ms, wall_ms], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max, wall_ms_max = float(t[0]), float(t[1])
-    per_rank = None
-    if dist is not None:      # per-rank view: device ms per step and the fused kernel's ms per step
-        mine = torch.tensor([dev_ms / args.steps, kernel_ms.get("frame_fused", 0.0) / args.steps], dtype=torch.float64, device=dev)
-        allr = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(allr, mine)
-        per_rank = [[round(float(x[0]), 4), round(float(x[1]), 4)] for x in allr]
     ms_per_step = dev_ms_max / args.steps
-    value = world * nf / (ms_per_step / 1000.0)
+    value = nf_total / (ms_per_step / 1000.0)
 
-    # ---- e2e: host frames through the C ABI (H2D inside the timed region, results read back) ----
-    e2e = None
-    if not args.no_e2e:
-        # host memory: all frames of the pass at N=1; with several ranks on one host the pinned budget is shared,
-        # so each rank streams a bounded number of distinct frames per pass (same metric, shorter pass)
-        ef = nf if world == 1 else int(min(nf, max(2048, nf // world)))
-        try:
-            pin = _native.PinnedBuffer((ef, na, 3))
-            host = pin.array
-            pinned = True
-        except Exception:
-            pin, host, pinned = None, np.empty((ef, na, 3), dtype=np.float32), False
-        chunk = max(1, (1 << 30) // (na * 12))
-        for s in range(0, ef, chunk):
-            host[s:s + chunk] = d_xyz[s:min(s + chunk, ef)].cpu().numpy()
-
-        def one_pass_host():
-            ctx.begin(ef)
-            ctx.submit_raw(host.ctypes.data, na, ef)
-            keys, words = ctx.results()
-            if world > 1:
-                merge_keys(keys, device=local_rank)
-            return keys, words
-
-        one_pass_host()
+    # ---- e2e legs: host buffers through the C ABI (H2D inside the timed region, results read back) ----
+    def timed_passes(one_pass, steps):
+        one_pass()
         sync_all()
         t0 = time.perf_counter()
-        e2e_steps = max(1, min(args.steps, 3))
-        for _ in range(e2e_steps):
-            keys, words = one_pass_host()
+        for _ in range(steps):
+            res = one_pass()
         sync_all()
-        e2e_ms = 1000.0 * (time.perf_counter() - t0)
-        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        ms = 1000.0 * (time.perf_counter() - t0)
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
         if dist is not None:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t[0]) / e2e_steps
-        e2e = {"value": world * ef / (e2e_ms / 1000.0), "unit": "frames/s", "h2d_bytes_per_step": int(ctx.timers()["h2d_bytes"]),
-               "frames_per_step_per_gpu": ef, "frame_bytes_per_step": int(ef) * na * 12,
-               "d2h_bytes_per_step": int(keys.nbytes + words.nbytes), "ms_per_step": e2e_ms,
-               "host_memory": "pinned" if pinned else "pageable", "timer": "wall clock between device synchronisations"}
-        if pin is not None:
-            pin.free()
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt[0]) / steps, res
+
+    e2e_f32 = e2e_xtc = e2e_class = None
+    parity_xtc = None
+    merged_e2e = []
+    e2e_steps = max(1, min(args.steps, 3))
+    if not args.no_e2e:
+        # host memory: all frames of the pass at N = 1; with several ranks on one host the pinned budget is shared, so
+        # each rank keeps a ring of distinct frames and streams it as often as it takes to submit ALL its frames
+        # (same frame count per pass as the device-resident leg, same bytes over PCIe)
+        ring = nf if world == 1 else int(min(nf, args.ring_frames))
+        pin = _native.PinnedBuffer((ring, na, 3))
+        host = pin.array
+        chunk = max(1, (1 << 30) // (na * 12))
+        for s in range(0, ring, chunk):
+            host[s:s + chunk] = d_xyz[s:min(s + chunk, ring)].cpu().numpy()
+
+        def one_pass_f32():
+            ctx.begin(nf)
+            for s in range(0, nf, ring):
+                ctx.submit_raw(host.ctypes.data, na, min(ring, nf - s))
+            ctx.finalize_async()
+            if world > 1:       # the queued device-side exchange of the device-resident loop (no host merge)
+                merged_e2e.append(exchange_keys_queued(ctx)[1])
+            return ctx.results()
+
+        ms, (keys, words) = timed_passes(one_pass_f32, e2e_steps)
+        tm = ctx.timers()
+        e2e_f32 = {"value": nf_total / (ms / 1000.0), "unit": "frames/s", "source": "float32 frames [F][N][3] in pinned host memory",
+                   "h2d_bytes_per_step": int(tm["h2d_bytes"]), "frames_per_step_per_gpu": nf, "distinct_frames_in_host_ring": ring,
+                   "frame_bytes_per_step": int(nf) * na * 12, "d2h_bytes_per_step": int(keys.nbytes + words.nbytes),
+                   "ms_per_step": ms, "h2d_gbs_per_gpu": tm["h2d_bytes"] / 1e9 / (ms / 1e3), "ms_h2d": tm["ms_h2d"],
+                   "host_memory": "pinned", "timer": "wall clock between device synchronisations, max over ranks"}
+        if world == 1 and ring == nf and not (np.array_equal(keys, dev_keys) and np.array_equal(words, dev_words)):
+            raise SystemExit("bench: the host-frame pass and the device-resident pass disagree")
+
+        # ---- XTC: the compressed records of the same frames (written once, outside the timed region) ----
+        if not args.no_xtc:
+            xring = ring if world == 1 else int(min(ring, args.ring_frames))
+            t_enc = time.perf_counter()
+            xbuf, xoff = _native.xtc_encode(host[:xring], in_scale=0.1, precision=1000.0)
+            t_enc = time.perf_counter() - t_enc
+            xpin = _native.PinnedBuffer((len(xbuf),), dtype=np.uint8)
+            xpin.array[:] = xbuf
+            if args.xtc_batch_bytes:
+                ctx.set_option("batch_bytes", args.xtc_batch_bytes)
+
+            def one_pass_xtc():
+                ctx.begin(nf)
+                for s in range(0, nf, xring):
+                    k = min(xring, nf - s)
+                    ctx.submit_xtc(xpin.array, xoff[:k + 1], na, k, scale=10.0)
+                ctx.finalize_async()
+                if world > 1:
+                    merged_e2e.append(exchange_keys_queued(ctx)[1])
+                return ctx.results()
+
+            ms, (xkeys, xwords) = timed_passes(one_pass_xtc, e2e_steps)
+            tm = ctx.timers()
+            e2e_xtc = {"value": nf_total / (ms / 1000.0), "unit": "frames/s",
+                       "source": "GROMACS XTC records (precision 1000) in pinned host memory, decoded on the device",
+                       "h2d_bytes_per_step": int(tm["h2d_bytes"]), "frames_per_step_per_gpu": nf, "distinct_frames_in_host_ring": xring,
+                       "xtc_bytes_per_atom": len(xbuf) / xring / na, "d2h_bytes_per_step": int(xkeys.nbytes + xwords.nbytes),
+                       "ms_per_step": ms, "h2d_gbs_per_gpu": tm["h2d_bytes"] / 1e9 / (ms / 1e3), "ms_h2d": tm["ms_h2d"],
+                       "ms_decode_kernel": tm["ms_kernel"].get("xtc_decode"), "encode_s_untimed": t_enc, "host_memory": "pinned",
+                       "timer": "wall clock between device synchronisations, max over ranks"}
+            if rank == 0 and not args.no_cpu:
+                # parity gate of the XTC leg: oracle decode + oracle H-bond port on the first frames
+                from oracle import xtc_port                  # (CPU-baseline leg: the only place bench.py runs the oracle)
+                n_x = int(min(args.cpu_frames_xtc, xring))
+                dec, _ = xtc_port.decode(xbuf, xoff[:n_x + 1], na, scale=10.0)
+                pt = cpu_port_topology(system, cfg, dec)
+                from oracle import hbond_port
+                cpu_res = hbond_port.run_block(pt, dec, "water_around", AROUND, nb_frames=n_x)
+                parity_xtc = parity_object(results_of(xkeys, xwords, group_names, n_x), cpu_res, n_x,
+                                           "oracle/xtc_codec.c decode + oracle/hbond_port.py on the first frames of the XTC stream")
+            if args.xtc_batch_bytes:
+                ctx.set_option("batch_bytes", args.batch_bytes or (4 << 30))
+            xpin.free()
+
+        # ---- the call a cgraphs user makes: drop-in class on a numpy-backed Universe, result dict built ----
+        if world == 1 and not args.no_class:
+            from cgraphs_b200.universe import Universe
+            try:
+                import psutil
+                room = psutil.virtual_memory().available
+            except Exception:
+                room = 0
+            ncls = nf if room > 3 * host.nbytes else int(min(nf, 2048))
+            pageable = np.array(host[:ncls])                           # an ordinary (pageable) numpy array
+            hb2 = HbondAnalysis(SELECTION, Universe(system.topology, pageable, system.dimensions), check_angle=True,
+                                device=local_rank)
+            hb2.set_hbonds_in_selection_and_water_around(AROUND)
+            torch.cuda.synchronize()
+            tc = time.perf_counter()
+            for _ in range(2):
+                hb2.set_hbonds_in_selection_and_water_around(AROUND)
+            torch.cuda.synchronize()
+            ms = 1000.0 * (time.perf_counter() - tc) / 2
+            e2e_class = {"value": ncls / (ms / 1000.0), "unit": "frames/s", "frames": ncls, "ms_per_call": ms,
+                         "call": "HbondAnalysis.set_hbonds_in_selection_and_water_around(3.5) on a Universe over a pageable "
+                                 "numpy array [F][N][3]; returns with initial_results (dict[str, bool[F]]) and the graph built",
+                         "n_bonds": len(hb2.initial_results), "host_memory": "pageable (staged through pinned buffers by the library)"}
+            hb2.close()
+            del pageable
+        pin.free()
+
+    for info in merged_e2e:
+        if int(info.tolist()[1]):
+            raise SystemExit("bench: the key gather overflowed its learnt capacity inside an e2e pass")
+    per_rank = None
+    if dist is not None:      # per-rank view: device ms per step, the fused kernel's ms per step, e2e H2D GB/s
+        mine = torch.tensor([dev_ms / args.steps, kernel_ms.get("frame_fused", 0.0) / args.steps,
+                             e2e_f32["h2d_gbs_per_gpu"] if e2e_f32 else 0.0, e2e_xtc["h2d_gbs_per_gpu"] if e2e_xtc else 0.0],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [[round(float(v), 4) for v in x] for x in allr]
 
     if rank != 0:
         if dist is not None:
@@ -486,33 +705,52 @@ def run_ours(args):
                     "whole_path_frac": bytes_frame * (nf / (ms_per_step / 1e3)) / 1e9 / peak,
                     "kernel_ms_per_step": {k: v / args.steps for k, v in kernel_ms.items()}}
 
-    # ---- CPU baseline: oracle port, 1 core, bounded sample of the same frames -----------------------
+    # ---- CPU baseline + parity gate: oracle port, 1 core, the first frames of the very trajectory searched above ----
     cpu = None
+    parity = None
     if not args.no_cpu:
-        sample_n = args.cpu_frames
+        sample_n = int(min(args.cpu_frames, nf))
         sample = d_xyz[:sample_n].cpu().numpy()
-        rate, dt = cpu_port_rate(system, cfg, sample, 1)
-        cpu = {"value": rate, "unit": "frames/s", "cores": 1, "kind": "port",
+        from oracle import hbond_port
+        pt = cpu_port_topology(system, cfg, sample)
+        tcpu = time.perf_counter()
+        cpu_res = hbond_port.run_block(pt, sample, "water_around", AROUND, nb_frames=sample_n)
+        dt = time.perf_counter() - tcpu
+        cpu = {"value": sample_n / dt, "unit": "frames/s", "cores": 1, "kind": "port",
                "sample": "first %d frames of the same %d-atom trajectory (%.1f s of CPU work), oracle/hbond_port.py"
                          % (sample_n, na, dt)}
+        parity = parity_object(results_of(dev_keys, dev_words, group_names, sample_n), cpu_res, sample_n,
+                               "oracle/hbond_port.py on the first frames of the device-resident trajectory (rank 0)")
 
+    # the headline end-to-end figure: the faster host source (both legs are in the line)
+    e2e = None
+    if e2e_f32 or e2e_xtc:
+        best = e2e_xtc if (e2e_xtc and (not e2e_f32 or e2e_xtc["value"] > e2e_f32["value"])) else e2e_f32
+        e2e = dict(best)
     line = {"metric": "hbond_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64 distance / f32 angle", "data": "synthetic",
-            "config": workload_config(system, cfg, args),
+            "config": workload_config(system, cfg, args, world),
             "atom_frames_per_s": value * na, "wall_ms_per_step": wall_ms_max / args.steps,
             "n_bonds": int(nb), "n_global_bonds": n_global_keys, "n_part_atoms": int(n_part),
-            "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu}
+            "clocks": clocks, "gpu_launches": int(launches), "parity": parity, "e2e": e2e, "e2e_f32": e2e_f32,
+            "e2e_xtc": e2e_xtc, "parity_xtc": parity_xtc, "e2e_class": e2e_class, "roofline": roofline,
+            "cpu_baseline": cpu, "host_numa": numa}
     if world == 1 and args.wire_frames > 0:
         try:
             line["wires"] = wires_leg(args, system, d_xyz, local_rank, peak, bytes_frame)
         except Exception as e:                          # the secondary leg never takes the headline down
             line["wires"] = {"error": repr(e)[:300]}
     if per_rank is not None:
-        line["per_rank_ms_per_step"] = {"columns": ["pass", "frame_fused kernel"], "ranks": per_rank}
+        line["per_rank"] = {"columns": ["pass ms", "frame_fused kernel ms", "e2e_f32 H2D GB/s", "e2e_xtc H2D GB/s"], "ranks": per_rank}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+    bad = [n for n, p_ in (("parity", parity), ("parity_xtc", parity_xtc), ("wires.parity", (line.get("wires") or {}).get("parity")))
+           if p_ is not None and not p_["equal"]]
+    if bad:
+        sys.stderr.write("bench: PARITY GATE FAILED: %s\n" % ", ".join(bad))
+        return 3
     return 0
 
 
@@ -522,13 +760,22 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=10000, help="frames per GPU (BASELINE config: 10000)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --frames per GPU; strong: --frames in total, sharded over the GPUs")
+    ap.add_argument("--frames", type=int, default=10000, help="frames per GPU (weak) or in total (strong); BASELINE config: 10000")
     ap.add_argument("--scale", type=float, default=1.0, help="atom-count scale of the workload (1.0 = BASELINE config)")
-    ap.add_argument("--cpu-frames", type=int, default=1024)
+    ap.add_argument("--cpu-frames", type=int, default=1024, help="frames of the CPU baseline / parity gate")
+    ap.add_argument("--cpu-frames-xtc", type=int, default=128, help="frames of the XTC leg's parity gate")
     ap.add_argument("--batch-bytes", type=int, default=0)
+    ap.add_argument("--xtc-batch-bytes", type=int, default=0, help="batch_bytes of the XTC leg (0: the library default)")
+    ap.add_argument("--ring-frames", type=int, default=2048, help="distinct frames per rank in pinned host memory when N > 1")
     ap.add_argument("--wire-frames", type=int, default=2048, help="frames of the secondary water-wire leg (0: skip)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-xtc", action="store_true")
+    ap.add_argument("--no-class", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the process to the CPUs next to its GPU")
+    ap.add_argument("--port-baseline", action="store_true", help="--impl reference: time the port even if oracle/_ref exists")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not os.environ.get("HB_BENCH_ALLOW_SHORT_WARMUP"):
         args.warmup = max(args.warmup, 1)

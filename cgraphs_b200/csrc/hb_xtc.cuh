@@ -87,6 +87,11 @@ __device__ __forceinline__ unsigned long long xtc_bits(const unsigned* win, unsi
     if (s) hi = (hi << s) | (c >> (32 - s));
     return hi >> (64 - n);
 }
+// same for n <= 32: two words and one funnel shift
+__device__ __forceinline__ unsigned xtc_bits32(const unsigned* win, unsigned pos, int n) {
+    const unsigned* w = win + (pos >> 5);
+    return __funnelshift_l(w[1], w[0], pos & 31u) >> (32 - n);
+}
 __device__ __forceinline__ unsigned long long xtc_bswap64(unsigned long long v) {
     const unsigned lo = (unsigned)v, hi = (unsigned)(v >> 32);
     return ((unsigned long long)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123);
@@ -130,14 +135,15 @@ __device__ __forceinline__ int xtc_bit_length(unsigned __int128 v) {
 
 struct XtcShared {
     unsigned win[XTC_WIN_BYTES / 4 + 8];          // window of the bit stream (+ 16 bytes read-ahead, + padding)
-    uint2 queue[XTC_QCAP];                        // x: bit offset inside the window, y: atom | nsmall << 20 | flag << 24 | smallidx << 25
+    uint2 queue[XTC_QCAP];                        // x: bit offset inside the window | nsmall << 16 | flag << 20 | smallidx << 21, y: atom
     float stage[XTC_WARPS][XTC_STAGE_ATOMS * 3];
     unsigned long long pos;                       // stream state, owned by warp 0, published at the end of every scan
     int i, nq, i_first, bad;
+    int rb[8], re[8];                             // atom ranges to write
 };
 
 // One CTA (XTC_WARPS warps) per frame: all warps stage the window and decode, warp 0 scans.
-__global__ void __launch_bounds__(XTC_WARPS * 32, 5) k_xtc_decode(XtcArgs A) {
+__global__ void __launch_bounds__(XTC_WARPS * 32, 6) k_xtc_decode(XtcArgs A) {
     __shared__ __align__(16) XtcShared S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = blockIdx.x;
@@ -149,12 +155,7 @@ __global__ void __launch_bounds__(XTC_WARPS * 32, 5) k_xtc_decode(XtcArgs A) {
     // (every exit below is taken by the whole CTA: the conditions only depend on the record header)
     if (rec_len < 56 || xtc_be32(rec) != 1995u || (int)xtc_be32(rec + 4) != natoms || (int)xtc_be32(rec + 52) != natoms) { fail(); return; }
     const int n_ranges = A.ranges.n;
-    auto wanted = [&](int atom) {
-        if (n_ranges == 0) return true;
-        bool w = false;
-        for (int k = 0; k < n_ranges; ++k) w = w || (atom >= A.ranges.b[k] && atom < A.ranges.e[k]);
-        return w;
-    };
+    if (threadIdx.x < 8) { S.rb[threadIdx.x] = A.ranges.b[threadIdx.x]; S.re[threadIdx.x] = A.ranges.e[threadIdx.x]; }
     if (natoms <= 9) {                                   // stored as plain floats
         if (rec_len < 56 + 12ll * natoms) { fail(); return; }
         for (int k = threadIdx.x; k < 3 * natoms; k += XTC_WARPS * 32) out[k] = __fmul_rn(__uint_as_float(xtc_be32(rec + 56 + 4 * k)), A.scale);
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(XTC_WARPS * 32, 5) k_xtc_decode(XtcArgs A) {
     const float inv = (float)(1.0 / (double)precision);
     const float scale = A.scale;
     if (threadIdx.x == 0) { S.pos = 0; S.i = 0; S.bad = 0; }
-    int run = 0;                                         // warp 0: current run (3 * small atoms per group)
+    int nsm = 0;                                         // warp 0: small atoms per group (run / 3) until a flag changes it
     __syncthreads();
     for (;;) {
         const unsigned long long pos0 = S.pos;           // bit position of the next group
@@ -213,60 +214,56 @@ __global__ void __launch_bounds__(XTC_WARPS * 32, 5) k_xtc_decode(XtcArgs A) {
         __syncthreads();
         // ---- scan (warp 0): queue the groups that lie completely inside the window -----------------------------------
         if (warp == 0) {
+            // The scan only finds where groups start; it reads nothing but flag bits inside [0, lim] of the window and
+            // always advances, so it needs no validation of its own: the decoders check every descriptor they use.
             const long long wend_bits = wbase_bits + 8ll * XTC_WIN_BYTES;
             const bool last_window = wend_bits >= (long long)nbits_total;
-            const unsigned end_rel = (unsigned)min((long long)nbits_total - wbase_bits, 1ll << 30);   // stream end, window relative
-            const unsigned lim_rel = last_window ? end_rel : 8u * XTC_WIN_BYTES - XTC_GROUP_MAX_BITS;  // a group may start up to here
-            unsigned prel0 = (unsigned)((long long)pos0 - wbase_bits);
+            const long long end_rel = (long long)nbits_total - wbase_bits;                      // stream end, window relative
+            // a group may start up to `lim` (its flag bit lies inside the stream and, unless this is the last window,
+            // the whole group inside the window)
+            const int lim = (int)min(end_rel - bitsize - 1, last_window ? (1ll << 30) : (long long)(8 * XTC_WIN_BYTES - XTC_GROUP_MAX_BITS));
+            int prel0 = (int)((long long)pos0 - wbase_bits);
             int i = i_first, nq = 0;
-            bool bad = false, lane_bad = false;
+            bool bad = false;
             while (i < natoms && nq <= XTC_QCAP - 32) {
-                const int nsm = run / 3;                                    // small atoms of a group without a flag
-                const unsigned glen = (unsigned)bitsize + 1u + (unsigned)nsm * (unsigned)smallidx;
-                const unsigned prel = prel0 + (unsigned)lane * glen;
+                const int glen = bitsize + 1 + nsm * smallidx;
+                const unsigned sidx_bits = (unsigned)smallidx << 21;
+                const int prel = prel0 + lane * glen;
                 const int i0 = i + lane * (1 + nsm);
-                const bool active = i0 < natoms && prel + bitsize + 1 <= end_rel && (last_window || prel <= lim_rel);
-                // flag bit and the five bits behind it in one read (bits past the end of the stream are never used)
+                const bool active = i0 < natoms && prel <= lim;
+                // flag bit and the five bits behind it in one read
                 unsigned six = 0;
-                if (active) six = (unsigned)xtc_bits(S.win, prel + bitsize, 6);
+                if (active) six = xtc_bits32(S.win, (unsigned)(prel + bitsize), 6);
                 const unsigned am = __ballot_sync(0xffffffffu, active), fm = __ballot_sync(0xffffffffu, six >> 5);
                 if (!(am & 1u)) {
                     // lane 0 cannot go on: the window is used up (slide it), or the stream ended before the last atom
                     bad = last_window || nq == 0;
                     break;
                 }
-                const int first = fm ? __ffs(fm) - 1 : 32;
-                const int ngroups = min(first + 1, __popc(am));             // active lanes are a prefix
-                const bool mine = lane < ngroups;
+                const int f1 = __ffs(fm);                                    // flagged lanes are active lanes, active lanes a prefix
+                const int ngroups = f1 ? f1 : __popc(am);                    // up to and including the first flag
                 const int flag = (int)(six >> 5);
-                int myrun = run, change = 0;
-                if (flag) {
-                    const int r5 = prel + bitsize + 6 <= end_rel ? (int)(six & 31u) : 31;   // 31: rejected below
-                    change = r5 % 3;
-                    myrun = r5 - change;
-                    change -= 1;
-                }
-                const int nsmall = myrun / 3;
-                const unsigned pnext = prel + (unsigned)bitsize + 1u + (flag ? 5u : 0u) + (unsigned)nsmall * (unsigned)smallidx;
-                lane_bad = lane_bad || (mine && (nsmall > 8 || i0 + 1 + nsmall > natoms || pnext > end_rel));
-                if (mine) S.queue[nq + lane] = make_uint2(prel, (unsigned)(i0 - i_first) | ((unsigned)nsmall << 20) | ((unsigned)flag << 24) |
-                                                                   ((unsigned)smallidx << 25));
+                const int r5 = (int)(six & 31u);
+                const int fs = (r5 * 11) >> 5;                               // r5 / 3: small atoms of a flagged group
+                const int nsmall = flag ? fs : nsm;
+                const int change = flag ? r5 - 3 * fs : 1;                   // smallidx change + 1
+                const int pnext = prel + bitsize + 1 + 5 * flag + nsmall * smallidx;
+                if (lane < ngroups) S.queue[nq + lane] = make_uint2((unsigned)prel | ((unsigned)nsmall << 16) | (six >> 5 << 20) | sidx_bits,
+                                                                    (unsigned)(i0 - i_first));
                 const int src = ngroups - 1;
                 i = __shfl_sync(0xffffffffu, i0 + 1 + nsmall, src);
                 prel0 = __shfl_sync(0xffffffffu, pnext, src);
-                const int rc = __shfl_sync(0xffffffffu, myrun | ((change + 1) << 8), src);
-                run = rc & 0xff;
-                smallidx += (rc >> 8) - 1;
+                const int st = __shfl_sync(0xffffffffu, nsmall | (change << 8), src);
+                nsm = st & 0xff;
+                smallidx = min(max(smallidx + (st >> 8) - 1, 0), 127);     // (kept sane for the arithmetic; decoders reject < 9 or > 72)
                 nq += ngroups;
-                if (smallidx < 9 || smallidx > 72 || run > 24) { bad = true; break; }
             }
-            bad = bad || __any_sync(0xffffffffu, lane_bad);
             if (lane == 0) {
                 S.pos = (unsigned long long)(wbase_bits + (long long)prel0);
                 S.i = i;
                 S.nq = nq;
                 S.i_first = i_first;
-                if (bad || i > natoms) S.bad = 1;
+                if (bad) S.bad = 1;
             }
         }
         __syncthreads();
@@ -276,50 +273,71 @@ __global__ void __launch_bounds__(XTC_WARPS * 32, 5) k_xtc_decode(XtcArgs A) {
         float* stage = S.stage[warp];
         for (int g0 = 32 * warp; g0 < nq; g0 += 32 * XTC_WARPS) {
             const int g = g0 + lane;
-            const int a_first = (int)(S.queue[g0].y & 0xfffffu);                                  // first atom of this pass
-            const int a_end = g0 + 32 < nq ? (int)(S.queue[g0 + 32].y & 0xfffffu) : i_end - i_first;   // first atom of the next
+            const int a_first = (int)S.queue[g0].y;                                               // first atom of this pass
+            const int a_end = g0 + 32 < nq ? (int)S.queue[g0 + 32].y : i_end - i_first;          // first atom of the next
+            const int a_lim = min(a_end, a_first + XTC_STAGE_ATOMS);    // (a_end - a_first > 288 only for malformed streams)
             if (g < nq) {
                 const uint2 d = S.queue[g];
-                const unsigned prel = d.x;
-                const int arel = (int)(d.y & 0xfffffu), nsmall = (int)((d.y >> 20) & 15u), flag = (int)((d.y >> 24) & 1u);
-                const int sidx = (int)(d.y >> 25);
-                int big[3];
-                if (wide) {
-                    unsigned pp = prel;
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) { big[k] = (int)xtc_bits(S.win, pp, wb[k]); pp += wb[k]; }
+                const unsigned prel = d.x & 0xffffu;
+                const int arel = (int)d.y, nsmall = (int)((d.x >> 16) & 15u), flag = (int)((d.x >> 20) & 1u);
+                const int sidx = (int)(d.x >> 21);
+                const long long gend = wbase_bits + (long long)prel + bitsize + 1 + 5 * flag + (long long)nsmall * sidx;
+                if (nsmall > 8 || sidx < 9 || sidx > 72 || arel + 1 + nsmall > a_lim || i_first + arel + 1 + nsmall > natoms ||
+                    gend > (long long)nbits_total) {
+                    S.bad = 1;                                            // malformed stream (benign race: every writer writes 1)
                 } else {
-                    xtc_triple(S.win, prel, bitsize, dy, dz, big);
-                }
+                    int big[3];
+                    if (wide) {
+                        unsigned pp = prel;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) big[k] += lo[k];
-                float* o = stage + (size_t)(arel - a_first) * 3;
-                auto emit = [&](float* dst, const int* v) {
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) dst[k] = __fmul_rn(__fmul_rn(__int2float_rn(v[k]), inv), scale);
-                };
-                if (nsmall == 0) {
-                    emit(o, big);
-                } else {
-                    const XtcDiv ds{(unsigned)c_xtc_magic[sidx], c_xtc_mul[sidx], c_xtc_shift[sidx]};
-                    const int smallnum = c_xtc_magic[sidx] / 2;
-                    const unsigned q = prel + bitsize + 1 + (flag ? 5 : 0);
-                    int prev[3] = {big[0], big[1], big[2]};
-                    for (int t = 0; t < nsmall; ++t) {
-                        int sm[3];
-                        xtc_triple(S.win, q + (unsigned)(t * sidx), sidx, ds, ds, sm);
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) { sm[k] += prev[k] - smallnum; prev[k] = sm[k]; }
-                        // stream order L, S1, S2, ... is atom order S1, L, S2, ... (the first two were swapped)
-                        emit(o + 3 * (t == 0 ? 0 : t + 1), sm);
+                        for (int k = 0; k < 3; ++k) { big[k] = (int)xtc_bits(S.win, pp, wb[k]); pp += wb[k]; }
+                    } else {
+                        xtc_triple(S.win, prel, bitsize, dy, dz, big);
                     }
-                    emit(o + 3, big);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) big[k] += lo[k];
+                    float* o = stage + (size_t)(arel - a_first) * 3;
+                    auto emit = [&](float* dst, const int* v) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) dst[k] = __fmul_rn(__fmul_rn(__int2float_rn(v[k]), inv), scale);
+                    };
+                    if (nsmall == 0) {
+                        emit(o, big);
+                    } else {
+                        const XtcDiv ds{(unsigned)c_xtc_magic[sidx], c_xtc_mul[sidx], c_xtc_shift[sidx]};
+                        const int smallnum = c_xtc_magic[sidx] / 2;
+                        const unsigned q = prel + bitsize + 1 + (flag ? 5 : 0);
+                        int prev[3] = {big[0], big[1], big[2]};
+                        for (int t = 0; t < nsmall; ++t) {
+                            int sm[3];
+                            xtc_triple(S.win, q + (unsigned)(t * sidx), sidx, ds, ds, sm);
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) { sm[k] += prev[k] - smallnum; prev[k] = sm[k]; }
+                            // stream order L, S1, S2, ... is atom order S1, L, S2, ... (the first two were swapped)
+                            emit(o + 3 * (t == 0 ? 0 : t + 1), sm);
+                        }
+                        emit(o + 3, big);
+                    }
                 }
             }
             __syncwarp();
-            const int nout = (a_end - a_first) * 3, abase = i_first + a_first;
-            for (int k = lane; k < nout; k += 32)
-                if (wanted(abase + k / 3)) out[(size_t)abase * 3 + k] = stage[k];
+            // write the atoms of this pass: whole pass inside one wanted range (or no ranges) -> plain row copy
+            const int abase = i_first + a_first, npass = a_lim - a_first;
+            int mode = n_ranges == 0 ? 1 : 0;                           // 1: all, 0: none, 2: mixed
+            for (int k = 0; k < n_ranges; ++k) {
+                if (abase >= S.rb[k] && abase + npass <= S.re[k]) mode = 1;
+                else if (abase < S.re[k] && abase + npass > S.rb[k] && mode == 0) mode = 2;
+            }
+            if (mode == 1) {
+                for (int k = lane; k < npass * 3; k += 32) out[(size_t)abase * 3 + k] = stage[k];
+            } else if (mode == 2) {
+                for (int k = lane; k < npass * 3; k += 32) {
+                    const int atom = abase + k / 3;
+                    bool w = false;
+                    for (int r = 0; r < n_ranges; ++r) w = w || (atom >= S.rb[r] && atom < S.re[r]);
+                    if (w) out[(size_t)abase * 3 + k] = stage[k];
+                }
+            }
             __syncwarp();
         }
         __syncthreads();                                 // the window and the queue are rewritten next

@@ -11,8 +11,10 @@ replaced in ``sys.modules`` by thin stubs: ``MDAnalysis.Universe(structure)`` re
 ``cgraphs_b200.universe.Universe`` it is given, ``MDAnalysis.core.groups.AtomGroup`` is the array
 backed AtomGroup of that module, and the matplotlib names only need to exist.
 
-``/root/reference`` does not exist on the GPU box: nothing that runs there may import this module.
-Only ``tests/`` (CPU side) and ``tests/golden/make_golden.py`` do.
+``/root/reference`` does not exist on the GPU box; there ``CGRAPHS_REF`` points at ``oracle/_ref/cgraphs``, the
+reference's own modules byte-compiled by ``oracle/make_ref.py`` (compiler output, git-ignored, travels with the
+snapshot). Only ``tests/`` (CPU side), ``tests/golden/make_golden.py`` and ``bench.py --impl reference`` import this
+module.
 """
 from __future__ import annotations
 
@@ -26,7 +28,7 @@ REF_DEFAULT = "/root/reference/cgraphs"
 
 def reference_available(path=None):
     path = path or os.environ.get("CGRAPHS_REF", REF_DEFAULT)
-    return os.path.isfile(os.path.join(path, "mdhbond", "hbond.py"))
+    return os.path.isfile(os.path.join(path, "mdhbond", "hbond.py")) or os.path.isfile(os.path.join(path, "mdhbond", "hbond.pyc"))
 
 
 def _install_stubs():
@@ -82,9 +84,11 @@ def load_reference(path=None):
         raise ImportError("reference mdhbond not found under %s" % path)
     _install_stubs()
     # import `mdhbond` as a top-level package, skipping cgraphs/__init__.py (tkinter, Bio, sklearn GUI imports)
+    init = os.path.join(path, "mdhbond", "__init__.py")
+    if not os.path.isfile(init):          # oracle/_ref: the reference byte-compiled by oracle/make_ref.py
+        init += "c"
     spec = importlib.util.spec_from_file_location(
-        "_cgraphs_ref_mdhbond", os.path.join(path, "mdhbond", "__init__.py"),
-        submodule_search_locations=[os.path.join(path, "mdhbond")])
+        "_cgraphs_ref_mdhbond", init, submodule_search_locations=[os.path.join(path, "mdhbond")])
     mod = importlib.util.module_from_spec(spec)
     sys.modules["_cgraphs_ref_mdhbond"] = mod
     spec.loader.exec_module(mod)
