@@ -178,7 +178,7 @@ def cpu_port_rate(system, cfg, frames_xyz, n_procs, pool=None):
 
 
 def _ref_available():
-    return os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "cgraphs", "mdhbond", "hbond.pyc"))
+    return os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "cgraphs", "mdhbond", "hbond.pyc.bin"))
 
 
 def _ref_process(conn, topology, dims, xyz):
@@ -467,6 +467,8 @@ def run_ours(args):
     ctx.set_option("profile", 1)
     if args.batch_bytes:
         ctx.set_option("batch_bytes", args.batch_bytes)
+    for kv in args.native_opt:
+        ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     # every kernel of the library and the NCCL exchange run on one torch stream, so a pair of CUDA events on that
     # stream brackets whole passes (search + finalize + key merge)
     stream = torch.cuda.Stream(device=dev)
@@ -770,6 +772,7 @@ def main():
     ap.add_argument("--xtc-batch-bytes", type=int, default=0, help="batch_bytes of the XTC leg (0: the library default)")
     ap.add_argument("--ring-frames", type=int, default=2048, help="distinct frames per rank in pinned host memory when N > 1")
     ap.add_argument("--wire-frames", type=int, default=2048, help="frames of the secondary water-wire leg (0: skip)")
+    ap.add_argument("--native-opt", action="append", default=[], help="name=value passed to hb_set_option (experiments)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-xtc", action="store_true")
     ap.add_argument("--no-class", action="store_true")

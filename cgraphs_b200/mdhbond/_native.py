@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _LIB = None
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc", "libhbgpu.so")
+LIB_PATH = os.environ.get("HBGPU_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc", "libhbgpu.so")
 
 METHOD_IN_SELECTION = 0
 METHOD_WATER_AROUND = 1

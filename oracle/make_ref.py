@@ -33,7 +33,7 @@ def build():
         return None
     for rel in FILES:
         src = os.path.join(REF, rel)
-        dst = os.path.join(OUT, rel + "c")
+        dst = os.path.join(OUT, rel + "c.bin")       # (.pyc files are filtered out of the snapshot that goes to the GPU box)
         if not os.path.isfile(src):
             continue
         os.makedirs(os.path.dirname(dst), exist_ok=True)

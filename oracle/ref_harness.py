@@ -28,7 +28,7 @@ REF_DEFAULT = "/root/reference/cgraphs"
 
 def reference_available(path=None):
     path = path or os.environ.get("CGRAPHS_REF", REF_DEFAULT)
-    return os.path.isfile(os.path.join(path, "mdhbond", "hbond.py")) or os.path.isfile(os.path.join(path, "mdhbond", "hbond.pyc"))
+    return os.path.isfile(os.path.join(path, "mdhbond", "hbond.py")) or os.path.isfile(os.path.join(path, "mdhbond", "hbond.pyc.bin"))
 
 
 def _install_stubs():
@@ -85,8 +85,18 @@ def load_reference(path=None):
     _install_stubs()
     # import `mdhbond` as a top-level package, skipping cgraphs/__init__.py (tkinter, Bio, sklearn GUI imports)
     init = os.path.join(path, "mdhbond", "__init__.py")
-    if not os.path.isfile(init):          # oracle/_ref: the reference byte-compiled by oracle/make_ref.py
-        init += "c"
+    if not os.path.isfile(init):          # oracle/_ref: the reference byte-compiled by oracle/make_ref.py (*.pyc.bin)
+        import shutil
+        import tempfile
+        tmp = tempfile.mkdtemp(prefix="cgraphs_ref_")
+        for root, _, files in os.walk(path):
+            for fn in files:
+                if fn.endswith(".pyc.bin"):
+                    dst = os.path.join(tmp, os.path.relpath(root, path), fn[:-4])
+                    os.makedirs(os.path.dirname(dst), exist_ok=True)
+                    shutil.copyfile(os.path.join(root, fn), dst)
+        path = tmp
+        init = os.path.join(path, "mdhbond", "__init__.pyc")
     spec = importlib.util.spec_from_file_location(
         "_cgraphs_ref_mdhbond", init, submodule_search_locations=[os.path.join(path, "mdhbond")])
     mod = importlib.util.module_from_spec(spec)

@@ -301,3 +301,4 @@ def test_frame_pairs_capacity_levels(n_atoms):
     for opts in ({"fused": 0}, {"fused": 0, "frame_pairs": 0}):
         got = _run(u, sel, "water_around", opts)
         assert_same_results(got.initial_results, ref, str(opts))
+
