@@ -31,13 +31,13 @@ namespace {
 #define FUSED_THREADS (FUSED_CONSUMERS + 32)
 #define FUSED_TILE 256          // waters per tile: one per consumer thread
 #define FUSED_MAX_STAGES 8
-#define FUSED_CAND 64           // per-warp candidate buffer entries
 
 struct FusedCfg {
     int sel_cap;              // selection points per frame that fit
     int lw_cap;               // local waters per frame that fit
     int cell_cap;             // cells per grid (packed 16-bit counters)
     int pair_cap;             // point pairs per frame
+    int cand_cap;             // candidate waters per frame (indices, collected while the tiles stream)
     int task_cap;             // hydrogens to test per chunk of 256 pairs
     int regular;              // 1: water point i is atom w_first + i * w_stride in every system -> TMA tiles
     int w_stride;             // atoms between consecutive water oxygens
@@ -48,6 +48,7 @@ struct FusedCfg {
     unsigned off_union, off_lw, off_cells, off_near, off_cand, off_bar;   // byte offsets in dynamic smem
     unsigned smem_bytes;
     unsigned long long buf_begin, buf_end;   // address range of the coordinate batch (bounds for bulk copies)
+    int debug;                // measurement only: bit 0 = no water becomes a candidate, bit 1 = skip phase C
 };
 
 struct FusedShared {          // small fixed part at the start of dynamic shared memory
@@ -55,6 +56,7 @@ struct FusedShared {          // small fixed part at the start of dynamic shared
     float lo[3], hi[3];
     float red[FUSED_CWARPS][6];
     int n_lw;
+    int n_cand;
     int n_pairs;
     int n_tasks;
     int overflow;
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
     }
     if (tid == 0) {
         sh->n_lw = 0;
+        sh->n_cand = 0;
         sh->n_pairs = 0;
         sh->overflow = 0;
         for (int k = 0; k < fc.stages; ++k) { mbar_init(&full[k], 1); mbar_init(&empty[k], FUSED_CWARPS); }
@@ -377,28 +380,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
         const float a = rp.around_f;
         const float lox = sh->lo[0] - a, loy = sh->lo[1] - a, loz = sh->lo[2] - a;
         const float hix = sh->hi[0] + a, hiy = sh->hi[1] + a, hiz = sh->hi[2] + a;
-        float4* wc = cand + warp * FUSED_CAND;
-        int ncand = 0;                                  // warp-uniform
-        // exact local-water test of (up to) 32 buffered candidates, one per lane
-        auto test_candidates = [&](int first, int count) {
-            bool local = false;
-            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (lane < count) {
-                c = wc[first + lane];
-                local = water_is_local<PBC>(g1, cells, sorted1, c.x, c.y, c.z, rp);
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, local);
-            if (m) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&sh->n_lw, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (local) {
-                    const int pos = base + __popc(m & ((1u << lane) - 1u));
-                    if (pos < fc.lw_cap) lw[pos] = c;
-                    else sh->overflow = 1;
-                }
-            }
-        };
+        // Candidates (waters inside the dilated bounding box whose cell has a selection point in its neighbourhood) are
+        // only COLLECTED while the tiles stream - their indices go to one CTA-wide list - and tested afterwards, densely,
+        // by all consumers (phase B2). A warp that stopped to test 32 candidates in the middle of the stream held its
+        // arrival on the next tiles back and, with a ring of three stages, everybody else's too.
+        unsigned* clist = reinterpret_cast<unsigned*>(cand);
         int st = 0;
         unsigned parity = 0;
         // a tile advances by 256 * stride * 12 bytes, a multiple of 16: the offset of its first water inside the
@@ -440,19 +426,45 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
                     is_cand = (near[c >> 5] >> (c & 31)) & 1u;
                 }
             }
+            if (fc.debug & 1) is_cand = false;
             const unsigned m = __ballot_sync(0xffffffffu, is_cand);
             if (m) {
-                if (is_cand) wc[ncand + __popc(m & ((1u << lane) - 1u))] = make_float4(x, y, z, __int_as_float(WATER_TAG | i));
-                ncand += __popc(m);
-                __syncwarp();
-                if (ncand >= 32) {
-                    ncand -= 32;
-                    test_candidates(ncand, 32);
-                    __syncwarp();
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&sh->n_cand, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (is_cand) {
+                    const int pos = base + __popc(m & ((1u << lane) - 1u));
+                    if (pos < fc.cand_cap) clist[pos] = (unsigned)i;
+                    else sh->overflow = 1;
                 }
             }
         }
-        if (ncand) test_candidates(0, ncand);
+        phase_done(2);
+        consumer_sync();
+        // ---- phase B2: exact local-water test of the collected candidates, one per thread --------------------------------
+        const int ncand = min(sh->n_cand, fc.cand_cap);
+        for (int j0 = 0; j0 < ncand; j0 += FUSED_CONSUMERS) {
+            const int j = j0 + tid;
+            bool local = false;
+            float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j < ncand) {
+                const int i = (int)clist[j];
+                const float* f = xyz + 3ll * tp.wat_atom[w0 + i];     // (just streamed: an L2 hit)
+                c = make_float4(f[0], f[1], f[2], __int_as_float(WATER_TAG | i));
+                local = water_is_local<PBC>(g1, cells, sorted1, c.x, c.y, c.z, rp);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, local);
+            if (m) {
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&sh->n_lw, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (local) {
+                    const int pos = base + __popc(m & ((1u << lane) - 1u));
+                    if (pos < fc.lw_cap) lw[pos] = c;
+                    else sh->overflow = 1;
+                }
+            }
+        }
         phase_done(2);
     }
     consumer_sync();
@@ -462,6 +474,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
         return;
     }
 
+    if (fc.debug & 2) return;
     // ---- phase C: pair search over selection + local waters --------------------------------------------
     const int nlw = sh->n_lw;
     const int np = nsel + nlw;

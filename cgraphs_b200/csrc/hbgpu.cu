@@ -91,6 +91,7 @@ struct hb_ctx {
     long long opt_fused_stages = 3;   // depth of the water-tile ring
     long long opt_fused_wait_ns = 100;
     long long opt_fused_prefetch = 2; // tiles prefetched into L2 ahead of the ring (more evicts lines before use)
+    int opt_fused_debug = 0;          // measurement hook (results are wrong when set): see FusedCfg::debug
     int fused_grow = 0;
     int fused_grow_hint = 0;          // capacities that an earlier run on this topology needed ...
     double fused_hint_around = 0.0;   // ... with this around radius (narrower shells start from the defaults)
@@ -476,6 +477,7 @@ int hb_set_option(hb_ctx* ctx, const char* name, int64_t value) {
     else if (n == "fused_stages") ctx->opt_fused_stages = std::max<long long>(value, 2);
     else if (n == "fused_batch_frames") ctx->opt_fused_batch_frames = std::max<long long>(value, 1);
     else if (n == "fused_prefetch") ctx->opt_fused_prefetch = std::max<long long>(value, 0);
+    else if (n == "fused_debug") ctx->opt_fused_debug = (int)value;
     else if (n == "fused_wait_ns") ctx->opt_fused_wait_ns = std::max<long long>(value, 0);
     else return fail(ctx, HB_ERR_ARG, "unknown option " + n);
     return HB_OK;
@@ -735,6 +737,7 @@ static bool plan_fused(hb_ctx* ctx, int grow = 0) {
     fc.w_stride = ctx->water_stride;
     fc.stages = fc.regular ? (int)std::min<long long>(std::max<long long>(ctx->opt_fused_stages, 2), FUSED_MAX_STAGES) : 0;
     fc.prefetch = (int)ctx->opt_fused_prefetch;
+    fc.debug = ctx->opt_fused_debug;
     fc.wait_ns = (unsigned)ctx->opt_fused_wait_ns;
     fc.stage_bytes = fc.regular ? (unsigned)(((FUSED_TILE - 1) * fc.w_stride * 12 + 12 + 15 + 15) & ~15) : 0u;
     size_t off = (sizeof(FusedShared) + 15) & ~(size_t)15;
@@ -742,7 +745,11 @@ static bool plan_fused(hb_ctx* ctx, int grow = 0) {
     // phases A/B: [sorted1][tile ring][candidate buffers (before the g1 sort: selection points in gather order)]
     size_t un_b = (size_t)fc.sel_cap * 16 + (size_t)fc.stages * fc.stage_bytes;
     fc.off_cand = (unsigned)(off + un_b);
-    un_b += wa ? std::max((size_t)FUSED_CWARPS * FUSED_CAND * 16, (size_t)fc.sel_cap * 16) : 0;
+    {   // candidate index list (4 bytes each; before the g1 sort the region holds the selection points in gather order)
+        const size_t cand_bytes = wa ? std::max((size_t)8192 << std::min(grow, 3), (size_t)fc.sel_cap * 16) : 0;
+        fc.cand_cap = (int)(cand_bytes / 4);
+        un_b += cand_bytes;
+    }
     // phase C: [sorted1][psorted][pairs][tasks][flags]
     fc.task_cap = 1536 << grow;
     size_t un_c = (size_t)fc.sel_cap * 16 + ((size_t)fc.sel_cap + fc.lw_cap) * 16 + (size_t)fc.pair_cap * 4 +
