@@ -53,6 +53,61 @@ struct WireCfg {
 
 __global__ void k_set_sink(EdgeSink* dst, EdgeSink v) { *dst = v; }
 
+// ---- convex-hull option of the water wires (waterwire.py:218-228) -------------------------------------------------------
+// The reference keeps only the local waters inside the Delaunay triangulation of the selection (scipy / Qhull, done on
+// the host exactly as the reference does it) but goes on naming them by the UNFILTERED list: the j-th in-hull water
+// (`true_w[j]`: its position enters the distance searches) is called `label_w[j]`, the j-th local water, and the angle
+// criterion is evaluated with the labelled water's coordinates and hydrogens. The host hands over both index lists
+// per frame; this kernel does the selection-water and water-water searches over them (a few hundred waters per frame:
+// all pairs, no grid) and feeds the same pair expansion / edge lists as the ordinary search.
+struct VirtualWaters {
+    const long long* off;     // [n_frames + 1] offsets into true_w / label_w, indexed by the global frame number
+    const int* true_w;        // water point whose position is searched
+    const int* label_w;       // water point the pair is attributed to
+    long long n_frames;
+};
+
+__global__ void __launch_bounds__(256) k_virtual_pairs(BatchView bv, DevTopo tp, RunParams rp, BondTable bt, VirtualWaters vw) {
+    const int b = blockIdx.x;
+    int sys;
+    const float* xyz = frame_xyz(bv, tp, b, sys);
+    const long long frame = bv.frame0 + b;
+    if (frame >= vw.n_frames) return;
+    const long long o0 = vw.off[frame];
+    const int n = (int)(vw.off[frame + 1] - o0);
+    const int* tw = vw.true_w + o0;
+    const int* lw = vw.label_w + o0;
+    const int s0 = tp.sys_sel_off[sys], nsel = tp.sys_sel_off[sys + 1] - s0, w0 = tp.sys_wat_off[sys];
+    int nhit = 0;
+    const Box6 nobox{};
+    auto water_info = [&](int w, PointInfo& q) {
+        const float* p = xyz + 3ll * tp.wat_atom[w0 + w];
+        load_info(tp, rp, sys, make_float4(p[0], p[1], p[2], __int_as_float(WATER_TAG | w)), q);
+    };
+    for (long long k = threadIdx.x; k < (long long)nsel * n; k += blockDim.x) {          // selection - water
+        const int s = (int)(k / n), j = (int)(k - (long long)s * n);
+        const float* ps = xyz + 3ll * tp.sel_atom[s0 + s];
+        const float* pt = xyz + 3ll * tp.wat_atom[w0 + tw[j]];
+        if (dist2f(ps[0], ps[1], ps[2], pt[0], pt[1], pt[2]) > rp.r2f_hi || !dist_le(ps[0], ps[1], ps[2], pt[0], pt[1], pt[2], rp.r2)) continue;
+        PointInfo P, Q;
+        load_info(tp, rp, sys, make_float4(ps[0], ps[1], ps[2], __int_as_float(s)), P);
+        water_info(lw[j], Q);
+        process_pair<false>(tp, rp, bt, xyz, frame, P, Q, nhit, nobox);
+    }
+    for (long long k = threadIdx.x; k < (long long)n * n; k += blockDim.x) {             // water - water
+        const int i = (int)(k / n), j = (int)(k - (long long)i * n);
+        if (i >= j) continue;
+        const float* pa = xyz + 3ll * tp.wat_atom[w0 + tw[i]];
+        const float* pb = xyz + 3ll * tp.wat_atom[w0 + tw[j]];
+        if (dist2f(pa[0], pa[1], pa[2], pb[0], pb[1], pb[2]) > rp.r2f_hi || !dist_le(pa[0], pa[1], pa[2], pb[0], pb[1], pb[2], rp.r2)) continue;
+        PointInfo P, Q;
+        water_info(lw[i], P);
+        water_info(lw[j], Q);
+        process_pair<false>(tp, rp, bt, xyz, frame, P, Q, nhit, nobox);
+    }
+    flush_hits(bt, nhit);
+}
+
 __device__ __forceinline__ int table_slot(const BondTable& bt, unsigned long long key) {
     unsigned h = hash64(key) & bt.mask;
     for (unsigned probe = 0; probe <= bt.mask; ++probe) {

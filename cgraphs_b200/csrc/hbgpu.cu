@@ -185,6 +185,10 @@ struct hb_ctx {
         int n_cta = 0;
         std::vector<void*> allocs;
         WireCfg cfg{};
+        // convex-hull option: per-frame (position water, name water) lists from the host (hb_set_wire_virtual_waters)
+        bool virt_on = false;
+        VirtualWaters virt{nullptr, nullptr, nullptr, 0};
+        std::vector<void*> virt_allocs;
     } wire;
     bool lw_attr_set[2] = {false, false};
     int opt_lw_smem = 1;                          // general path: stage the selection grid in shared memory when it fits
@@ -433,6 +437,7 @@ int hb_destroy(hb_ctx* ctx) {
     free_run(ctx);
     free_list(ctx->topo_allocs);
     if (ctx->wire.d_ent_node) cudaFree(ctx->wire.d_ent_node);
+    free_list(ctx->wire.virt_allocs);
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     for (int k = 0; k < 2; ++k) { cudaEventDestroy(ctx->ev_copied[k]); cudaEventDestroy(ctx->ev_done[k]); }
     cudaEventDestroy(ctx->ev_run0);
@@ -496,6 +501,8 @@ int hb_set_topology(hb_ctx* ctx, const hb_topology* t) {
     ctx->wire.on = false;
     if (ctx->wire.d_ent_node) cudaFree(ctx->wire.d_ent_node);
     ctx->wire.d_ent_node = nullptr;
+    free_list(ctx->wire.virt_allocs);
+    ctx->wire.virt_on = false;
     ctx->fused_unfit_around = -1.0;
     ctx->fused_grow_hint = 0;
     ctx->fp_level = 0;
@@ -665,6 +672,34 @@ int hb_set_wires(hb_ctx* ctx, const int32_t* ent_node, int32_t n_ent, int32_t n_
     return HB_OK;
 }
 
+int hb_set_wire_virtual_waters(hb_ctx* ctx, const int64_t* frame_off, const int32_t* true_wat, const int32_t* label_wat, int64_t n_frames) {
+    if (!ctx) return HB_ERR_ARG;
+    if (!ctx->have_topo) return fail(ctx, HB_ERR_STATE, "hb_set_wire_virtual_waters before hb_set_topology");
+    if (ctx->running) return fail(ctx, HB_ERR_STATE, "hb_set_wire_virtual_waters during a run");
+    CK(cudaSetDevice(ctx->device));
+    free_list(ctx->wire.virt_allocs);
+    ctx->wire.virt_on = false;
+    ctx->wire.virt = VirtualWaters{nullptr, nullptr, nullptr, 0};
+    if (!frame_off || n_frames <= 0) return HB_OK;
+    if (ctx->tp.n_systems != 1) return fail(ctx, HB_ERR_ARG, "hb_set_wire_virtual_waters: trajectories of one system only");
+    const int64_t total = frame_off[n_frames];
+    if (frame_off[0] != 0 || total < 0 || (total > 0 && (!true_wat || !label_wat))) return fail(ctx, HB_ERR_ARG, "hb_set_wire_virtual_waters: bad offsets");
+    for (int64_t f = 0; f < n_frames; ++f)
+        if (frame_off[f + 1] < frame_off[f]) return fail(ctx, HB_ERR_ARG, "hb_set_wire_virtual_waters: offsets must not decrease");
+    for (int64_t k = 0; k < total; ++k)
+        if (true_wat[k] < 0 || true_wat[k] >= ctx->n_wat_total || label_wat[k] < 0 || label_wat[k] >= ctx->n_wat_total)
+            return fail(ctx, HB_ERR_ARG, "hb_set_wire_virtual_waters: water point out of range");
+    int rc;
+    const long long* d_off = nullptr;
+    const int *d_t = nullptr, *d_l = nullptr;
+    if ((rc = upload(ctx, (const long long*)frame_off, (size_t)n_frames + 1, &d_off, ctx->wire.virt_allocs))) return rc;
+    if ((rc = upload(ctx, true_wat, (size_t)total, &d_t, ctx->wire.virt_allocs))) return rc;
+    if ((rc = upload(ctx, label_wat, (size_t)total, &d_l, ctx->wire.virt_allocs))) return rc;
+    ctx->wire.virt = VirtualWaters{d_off, d_t, d_l, n_frames};
+    ctx->wire.virt_on = true;
+    return HB_OK;
+}
+
 int hb_set_entry_groups(hb_ctx* ctx, const int32_t* g, int32_t n) {
     if (!ctx || !g) return HB_ERR_ARG;
     if (!ctx->have_topo || n != ctx->n_ent) return fail(ctx, HB_ERR_ARG, "hb_set_entry_groups: size mismatch");
@@ -802,8 +837,11 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     tr.mark("sync");
     int wpr = (int)((n_frames_total + 31) / 32);
     if (ctx->wire.on) {        // one byte per frame, then the two "first direct bond" words (hb_wires.cuh)
-        if (ctx->prm.structure_batch || ctx->rp.method != HB_METHOD_WATER_AROUND || ctx->presence)
-            return fail(ctx, HB_ERR_ARG, "water wires: HB_METHOD_WATER_AROUND on a trajectory");
+        const bool method_ok = ctx->wire.virt_on ? ctx->rp.method == HB_METHOD_IN_SELECTION : ctx->rp.method == HB_METHOD_WATER_AROUND;
+        if (ctx->prm.structure_batch || !method_ok || ctx->presence)
+            return fail(ctx, HB_ERR_ARG, "water wires: HB_METHOD_WATER_AROUND on a trajectory (HB_METHOD_IN_SELECTION with hb_set_wire_virtual_waters)");
+        if (ctx->wire.virt_on && (ctx->prm.pbc_mode != HB_PBC_NONE || n_frames_total > ctx->wire.virt.n_frames))
+            return fail(ctx, HB_ERR_ARG, "water wires with virtual waters: no pbc_mode, and a water list for every frame");
         ctx->wire.nb4 = (int)((((n_frames_total + 3) / 4) + 1) & ~1ll);
         wpr = ctx->wire.nb4 + 2;
     }
@@ -1178,6 +1216,17 @@ static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, 
             ctx->bt_run.sink = w.d_sink;
             if ((rc = run_search(ctx, d_xyz + (size_t)done * atoms_per_frame * 3, frame0 + done, n, atoms_per_frame, d_xyz,
                                  xyz_bytes, d_box ? d_box + (size_t)done * 9 : nullptr, allow_fused))) return rc;
+            if (w.virt_on) {       // convex-hull option: the selection-water and water-water pairs over the host's water lists
+                BatchView bv = ctx->bv;
+                bv.xyz = d_xyz + (size_t)done * atoms_per_frame * 3;
+                bv.box = nullptr;
+                bv.frame0 = frame0 + done;
+                bv.n_frames = n;
+                bv.atoms_per_frame = atoms_per_frame;
+                bv.atom_base = 0;
+                KTimer t(ctx, KC_PAIRS);
+                k_virtual_pairs<<<n, 256, 0, st>>>(bv, ctx->tp, ctx->rp, ctx->bt_run, w.virt);
+            }
             {
                 KTimer t(ctx, KC_WIRES);
                 k_wire_bfs<<<std::min(n, w.n_cta), WIRE_THREADS, WIRE_SMEM_WORDS * 4, st>>>(ctx->bt, c, w.d_edges, w.d_cnt, (int)w.edge_cap, frame0 + done, n);

@@ -86,6 +86,7 @@ SYMBOLS = [
     ("hb_set_params", C.c_int, [_P, C.POINTER(HbParams)]),
     ("hb_set_ions", C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int32]),
     ("hb_set_wires", C.c_int, [_P, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    ("hb_set_wire_virtual_waters", C.c_int, [_P, _P, _P, _P, C.c_int64]),
     ("hb_set_option", C.c_int, [_P, C.c_char_p, C.c_int64]),
     ("hb_begin", C.c_int, [_P, C.c_int64]),
     ("hb_submit_frames", C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
@@ -210,6 +211,18 @@ class Context:
         g = _i32(ent_node)
         self._ck(self.lib.hb_set_wires(self.h, _ptr(g, C.c_int32), len(g), int(n_res), int(max_water),
                                        int(bool(allow_direct_bonds))), "hb_set_wires")
+
+    def set_wire_virtual_waters(self, frame_off=None, true_wat=None, label_wat=None):
+        """Per-frame (position water, name water) lists of the convex-hull wire option; None switches it off."""
+        if frame_off is None:
+            self._ck(self.lib.hb_set_wire_virtual_waters(self.h, None, None, None, 0), "hb_set_wire_virtual_waters")
+            return
+        off = np.ascontiguousarray(frame_off, dtype=np.int64)
+        t = np.ascontiguousarray(true_wat, dtype=np.int32)
+        l = np.ascontiguousarray(label_wat, dtype=np.int32)
+        self._ck(self.lib.hb_set_wire_virtual_waters(self.h, off.ctypes.data, t.ctypes.data if len(t) else None,
+                                                     l.ctypes.data if len(l) else None, len(off) - 1),
+                 "hb_set_wire_virtual_waters")
 
     def set_entry_groups(self, groups):
         g = _i32(groups)

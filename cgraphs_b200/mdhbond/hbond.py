@@ -283,9 +283,44 @@ class HbondAnalysis(object):
                 raise IndexError('water hydrogens do not pair up as two per water; the reference indexes past '
                                  'heavy2hydrogen here (network.py:86, helpfunctions.py:144)')
 
+    def _submit_frames(self, ctx, lo, hi, pbc_mode):
+        """Feed the frames [lo, hi) of this analysis to a context that has begun a run: trajectory-file records go to the
+        device as they are (XTC: compressed; DCD: planar) and are decoded there, everything else as float32 blocks."""
+        fi = self._frame_indices
+        n_local = hi - lo
+        block = max(1, min(n_local, int((256 << 20) // max(1, self._n_atoms * 12))))
+        done = lo
+        frames = getattr(self._universe.trajectory, "frames", None)
+        sub = fi[lo:hi]
+        if hasattr(frames, "xtc_block") and isinstance(sub, range) and sub.step == 1:
+            # XTC: the compressed frame records go to the device as they are and are decoded there
+            i = sub.start
+            while i < sub.stop:
+                j = i + frames.xtc_count(i, min(sub.stop, i + block))        # (a block ends at a file boundary)
+                raw, off = frames.xtc_block(i, j)
+                box = _frame_boxes(self._universe, range(i, j)) if pbc_mode else None
+                ctx.submit_xtc(raw, off, self._n_atoms, j - i, scale=getattr(frames, "LENGTH_SCALE", 10.0), box=box)
+                i = j
+        elif getattr(frames, "planar_block", None) is not None and isinstance(sub, range) and sub.step == 1:
+            # trajectory file records go to the device as they are and are decoded (interleaved) there
+            i = sub.start
+            while i < sub.stop:
+                j = i + frames.planar_count(i, min(sub.stop, i + block))     # (a block ends at a file boundary)
+                raw, stride, xo, yo, zo = frames.planar_block(i, j)
+                box = _frame_boxes(self._universe, range(i, j)) if pbc_mode else None
+                ctx.submit_planar(raw, stride, xo, yo, zo, self._n_atoms, j - i, box=box)
+                i = j
+        else:
+            for xyz in _frame_blocks(self._universe, sub, block):
+                box = _frame_boxes(self._universe, fi[done:done + len(xyz)]) if pbc_mode else None
+                ctx.submit(xyz, box=box)
+                done += len(xyz)
+
     def _run(self, method, around_radius, exclude_backbone_backbone, include_water=True, wires=None):
-        """wires = (ent_node, n_res, max_water, allow_direct_bonds): water-wire mode of the water_around search
-        (hb_set_wires); returns the raw (keys, rows) of that run instead of a result dict."""
+        """wires = (ent_node, n_res, max_water, allow_direct_bonds[, virtual waters]): water-wire mode of the search
+        (hb_set_wires; with the convex-hull option the per-frame water lists of hb_set_wire_virtual_waters); returns
+        the raw (keys, rows) of that run instead of a result dict. method "presence": the local-water test alone
+        (HB_METHOD_WATER_PRESENCE), raw (keys = water entry, rows = one bit per frame)."""
         top = self._topology
         if top is None or getattr(self, "_universe", None) is None:
             raise AssertionError('this analysis was restored from a file without its Universe; construct it with the '
@@ -299,18 +334,26 @@ class HbondAnalysis(object):
                 cache[method] = pack_systems([top], [ids], [self._n_atoms],
                                              extra_ids=self._ions_ids if self.residuewise else self._ions_ids_atomwise)
             else:
-                cache[method] = pack_systems([top], [top.key_ids(method)], [self._n_atoms])
+                cache[method] = pack_systems([top], [top.key_ids("water_around" if method == "presence" else method)], [self._n_atoms])
         tables, group_names = cache[method][0], cache[method][1]
         if getattr(ctx, "_uploaded", None) is not tables:
             ctx.set_topology(tables)
             ctx._uploaded = tables
+        if method == "presence":         # rows keyed by the water's entry index (the id strings of waters may repeat)
+            ctx.set_entry_groups(_np.arange(len(tables["ent_group"]), dtype=_np.int32))
+            ctx._uploaded = None         # (the next run uploads its own key groups again)
         if method == "ions":
             ctx.set_ions(self._ions_atoms, cache[method][2], include_water)
         if wires is not None:
-            ctx.set_wires(*wires)
+            ctx.set_wires(*wires[:4])
             ctx._wires_on = True
+            if len(wires) > 4:
+                ctx.set_wire_virtual_waters(*wires[4])
+            else:
+                ctx.set_wire_virtual_waters(None)
         elif getattr(ctx, "_wires_on", False):
             ctx.set_wires(None, 0, 0)
+            ctx.set_wire_virtual_waters(None)
             ctx._wires_on = False
         cthr = self._cos_threshold_override
         if cthr is None:
@@ -325,7 +368,7 @@ class HbondAnalysis(object):
                 b0 = _frame_boxes(self._universe, self._frame_indices[:1])[0]
                 pbc_mode = _native.PBC_ORTHO if not (b0[1, 0] or b0[2, 0] or b0[2, 1]) else _native.PBC_TRICLINIC
         native_method = {"water_around": _native.METHOD_WATER_AROUND, "in_selection": _native.METHOD_IN_SELECTION,
-                         "ions": _native.METHOD_ION_CONTACTS}[method]
+                         "ions": _native.METHOD_ION_CONTACTS, "presence": _native.METHOD_WATER_PRESENCE}[method]
         ctx.set_params(self.distance, around_radius, cthr, self.check_angle, exclude_backbone_backbone, native_method,
                        pbc_mode=pbc_mode)
         # frame block of this rank (block boundaries are multiples of 32 frames)
@@ -339,43 +382,17 @@ class HbondAnalysis(object):
         words = _np.zeros((0, (max(n_local, 1) + 31) // 32), _np.uint32)
         if n_local > 0:
             ctx.begin(n_local)
-            block = max(1, min(n_local, int((256 << 20) // max(1, self._n_atoms * 12))))
-            done = lo
-            frames = getattr(self._universe.trajectory, "frames", None)
-            sub = fi[lo:hi]
-            if hasattr(frames, "xtc_block") and isinstance(sub, range) and sub.step == 1:
-                # XTC: the compressed frame records go to the device as they are and are decoded there
-                i = sub.start
-                while i < sub.stop:
-                    j = i + frames.xtc_count(i, min(sub.stop, i + block))        # (a block ends at a file boundary)
-                    raw, off = frames.xtc_block(i, j)
-                    box = _frame_boxes(self._universe, range(i, j)) if pbc_mode else None
-                    ctx.submit_xtc(raw, off, self._n_atoms, j - i, scale=getattr(frames, "LENGTH_SCALE", 10.0), box=box)
-                    i = j
-            elif getattr(frames, "planar_block", None) is not None and isinstance(sub, range) and sub.step == 1:
-                # trajectory file records go to the device as they are and are decoded (interleaved) there
-                i = sub.start
-                while i < sub.stop:
-                    j = i + frames.planar_count(i, min(sub.stop, i + block))     # (a block ends at a file boundary)
-                    raw, stride, xo, yo, zo = frames.planar_block(i, j)
-                    box = _frame_boxes(self._universe, range(i, j)) if pbc_mode else None
-                    ctx.submit_planar(raw, stride, xo, yo, zo, self._n_atoms, j - i, box=box)
-                    i = j
-            else:
-                for xyz in _frame_blocks(self._universe, sub, block):
-                    box = _frame_boxes(self._universe, fi[done:done + len(xyz)]) if pbc_mode else None
-                    ctx.submit(xyz, box=box)
-                    done += len(xyz)
+            self._submit_frames(ctx, lo, hi, pbc_mode)
             keys, words = ctx.results()
             self.last_run_stats = ctx.timers()
-            if wires is not None:
+            if wires is not None or method == "presence":
                 self._rows = None
                 return keys, words
             if self._shard is None:      # the packed rows stay on the device for the occupancy post-processing below
                 self._rows = dict(run_id=ctx._run_id, wpr=words.shape[1], n=len(keys),
                                   row_of={group_names[int(k >> _np.uint64(32))] + ':' + group_names[int(k & _np.uint64(0xFFFFFFFF))]: i
                                           for i, k in enumerate(keys)})
-        if wires is not None:
+        if wires is not None or method == "presence":
             return keys, words
         if self._shard is not None and self._shard[1] > 1:
             from .sharding import merge_shards

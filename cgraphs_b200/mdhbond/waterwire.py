@@ -9,11 +9,18 @@ trajectory, calls ``set_water_wires(max_water=...)``, ``compute_average_water_pe
 
 The neighbour stage (``waterwire.py:200-248``) is the library's water-around search with the radius
 ``(max_water + 1) * distance / 2``; the per-frame breadth-first search (``waterwire.py:250-309``) runs in
-``k_wire_bfs`` (``csrc/hb_wires.cuh``). No part of it runs on the CPU.
+``k_wire_bfs`` (``csrc/hb_wires.cuh``).
 
-Not covered (out of scope): ``water_in_convex_hull`` (scipy Delaunay), the explicit wire paths
-(``hashs`` / ``hash_table``: Python ``hash(str(path))`` values, salted per process), ``residuewise=False`` and the
-plotting methods.
+``water_in_convex_hull`` (what cgraphs itself always passes, ``proteingraphanalyser.py:484``): the local waters of every
+frame come from the GPU (the water-presence search), the Delaunay test of the reference (``waterwire.py:218-221``,
+scipy / Qhull - a library call the reference makes too, not restated in CUDA) runs on the host frame by frame, and the
+per-frame lists "position of the j-th in-hull water, named like the j-th local water" - the reference does not filter
+its index list along with the coordinates, ``waterwire.py:221-228`` - go back to the device, where ``k_virtual_pairs``
+searches them and the same breadth-first search follows. Slow (a Delaunay triangulation per frame, as in the
+reference) but drop-in: the results are the reference's, labelling included.
+
+Not covered (out of scope): the explicit wire paths (``hashs`` / ``hash_table``: Python ``hash(str(path))``
+values, salted per process), ``residuewise=False`` and the plotting methods.
 """
 from __future__ import annotations
 
@@ -103,17 +110,61 @@ class WireAnalysis(HbondAnalysis):
         self._wire_node_entry = _np.asarray(node_first_entry, dtype=_np.int64)
         self.da_trans = self._wire_node_entry[ent_node[:top.first_water]]
 
+    def _hull_water_lists(self, max_water, lo, hi):
+        """Per frame of [lo, hi): (offsets, water points whose positions are searched, water points they are named as) -
+        waterwire.py:212-228 with `water_in_convex_hull` set, see the module docstring."""
+        from scipy.spatial import Delaunay
+        from .hbond import _frame_blocks
+        top = self._topology
+        if (top.sel_wat >= 0).any():
+            raise NotImplementedError('water_in_convex_hull with waters of the water group inside the selection')
+        radius = float(max_water + 1) * self.distance / 2.
+        keys, words = self._run("presence", radius, False)              # GPU: local waters of every frame
+        n_local = hi - lo
+        present = _np.zeros((top.nW, n_local), dtype=bool)
+        if len(keys):
+            bits = _np.unpackbits(words.view(_np.uint8), axis=1, bitorder="little")[:, :n_local].astype(bool)
+            present[(keys & _np.uint64(0xFFFFFFFF)).astype(_np.int64) - top.first_water] = bits
+        sel_atoms = top.entry_atom[:top.first_water]                     # donors ++ acceptors, like _da_selection
+        water_atoms = top.water_atoms
+        off, true, label = [0], [], []
+        block = max(1, int((256 << 20) // max(1, self._n_atoms * 12)))
+        col = 0
+        for xyz in _frame_blocks(self._universe, self._frame_indices[lo:hi], block):
+            for pos in xyz:
+                local = _np.nonzero(present[:, col])[0]
+                if len(local):
+                    hull = Delaunay(pos[sel_atoms])                      # waterwire.py:219
+                    inside = hull.find_simplex(pos[water_atoms[local]]) != -1
+                    t = local[inside]
+                    true.append(t)
+                    label.append(local[:len(t)])                         # (the unfiltered list keeps naming them)
+                    off.append(off[-1] + len(t))
+                else:
+                    off.append(off[-1])
+                col += 1
+        cat = lambda parts: _np.concatenate(parts).astype(_np.int32) if parts else _np.zeros(0, _np.int32)
+        return _np.asarray(off, dtype=_np.int64), cat(true), cat(label)
+
     def set_water_wires(self, max_water=5, allow_direct_bonds=True, water_in_convex_hull=False):
         """waterwire.py:191-317."""
-        if water_in_convex_hull:
-            raise NotImplementedError('water_in_convex_hull (scipy Delaunay, waterwire.py:218-221) is not supported')
         if not self.residuewise:
             raise NotImplementedError('water wires: residuewise=False is not supported')
         max_water = int(max_water)
         self._allow_direct_bonds = allow_direct_bonds
         around = float(max_water + 1) * self.distance / 2.
         wires = (self._wire_ent_node, self._n_wire_nodes, max_water, bool(allow_direct_bonds))
-        keys, words = self._run("water_around", around, False, wires=wires)
+        if water_in_convex_hull:
+            if self._pbc:
+                raise NotImplementedError('water_in_convex_hull has no minimum-image form')
+            lo, hi = 0, self.nb_frames
+            if self._shard is not None:
+                from .sharding import shard_range
+                lo, hi = shard_range(self.nb_frames, *self._shard)
+            lists = self._hull_water_lists(max_water, lo, hi)
+            keys, words = self._run("in_selection", 0.0, False, wires=wires + (lists,))
+        else:
+            keys, words = self._run("water_around", around, False, wires=wires)
         lo, hi = 0, self.nb_frames
         if self._shard is not None:
             from .sharding import shard_range

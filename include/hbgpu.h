@@ -165,6 +165,17 @@ int hb_set_ions(hb_ctx* ctx, const int32_t* ion_atom, const int32_t* ion_group, 
  * mode off. The bit-matrix post-processing calls (hb_get_counts, ...) do not apply to such rows. */
 int hb_set_wires(hb_ctx* ctx, const int32_t* ent_node, int32_t n_ent, int32_t n_res, int32_t max_water,
                  int32_t allow_direct_bonds);
+/* Convex-hull option of the water wires (set_water_wires(water_in_convex_hull=...), waterwire.py:218-228; the only form
+ * cgraphs itself calls, proteingraphanalyser.py:484). The Delaunay test stays on the host (scipy / Qhull, as in the
+ * reference); the host then hands over, per frame, the waters whose POSITIONS enter the distance searches (true_wat:
+ * the local waters inside the hull) and the waters the pairs are ATTRIBUTED to (label_wat: the reference keeps naming
+ * them by the unfiltered local-water list, so the j-th in-hull water is called like the j-th local water; the angle
+ * criterion is evaluated with the labelled water's coordinates and hydrogens). Indices are water points;
+ * frame_off[n_frames + 1] indexes both lists by frame. Use with hb_set_wires and HB_METHOD_IN_SELECTION (the
+ * acceptor-donor pairs come from the ordinary search, the selection-water and water-water pairs from these lists),
+ * exclude_backbone_backbone = 0, no pbc_mode. frame_off = NULL switches the mode off. */
+int hb_set_wire_virtual_waters(hb_ctx* ctx, const int64_t* frame_off, const int32_t* true_wat, const int32_t* label_wat,
+                               int64_t n_frames);
 int hb_set_option(hb_ctx* ctx, const char* name, int64_t value);
         /* "batch_bytes": device budget per frame batch; "table_capacity": initial bond-table slots;
            "profile": 1 = time every kernel class with CUDA events; "max_batch_frames";

@@ -490,13 +490,55 @@ def wire_node_of_entry(pt):
     return out
 
 
-def wire_frame_edges(pt, pos, max_water, backend='kdtree', cos_threshold=None, box=None):
+def hull_water_labels(pt, pos, max_water, backend='kdtree'):
+    """waterwire.py:212-221 with `water_in_convex_hull` set. Returns (true, label): index arrays into the water group.
+    `true[j]` is the j-th local water that lies inside the Delaunay triangulation of the selection coordinates - its
+    POSITION enters the distance searches (waterwire.py:221,223,226,228). The reference does not filter
+    `local_water_index` along with the coordinates, so the j-th point of those searches is NAMED
+    `local_water_index[j]` = `label[j]`, the j-th local water of the unfiltered list (waterwire.py:226,228): every pair
+    the searches find carries the labels, and the angle criterion is evaluated with the labelled waters' coordinates
+    and hydrogens (waterwire.py:236-239). Restated as it is - bit-exact results need the same labelling."""
+    from scipy.spatial import Delaunay
+    fw = pt.first_water
+    sel = pos[pt.entry_atom[:fw]]
+    wpos = pos[pt.water_atoms]
+    around = float(max_water + 1) * pt.distance / 2.
+    _, wj = ball_pairs(sel, wpos, around, backend)
+    local = np.unique(wj)
+    if len(local) == 0:
+        return local, local
+    inside = Delaunay(sel).find_simplex(wpos[local]) != -1
+    true = local[inside]
+    return true, local[:len(true)]
+
+
+def wire_frame_edges(pt, pos, max_water, backend='kdtree', cos_threshold=None, box=None, water_in_convex_hull=False):
     """Neighbour stage of one frame (waterwire.py:200-248): the three H-bond pair classes, local waters taken within
     (max_water + 1) * distance / 2 of the selection, no backbone filter. Returns entry pairs
     (direct [donor entry, acceptor entry], selection-water [entry, water entry], water-water)."""
     around = float(max_water + 1) * pt.distance / 2.
-    e0, e1 = frame_pairs(pt, pos, 'water_around', around, False, backend, cos_threshold, False, box)
     fw = pt.first_water
+    if water_in_convex_hull:
+        if box is not None:
+            raise ValueError("the convex-hull option has no minimum-image form")
+        nD = pt.nD
+        sel = pos[pt.entry_atom[:fw]]
+        wpos = pos[pt.water_atoms]
+        e0 = np.zeros(0, np.int64)
+        e1 = np.zeros(0, np.int64)
+        if nD > 0 and pt.nA > 0:
+            ia, jd = ball_pairs(pos[pt.acceptors], pos[pt.donors], pt.distance, backend)
+            e0, e1 = ia + nD, jd
+        true, label = hull_water_labels(pt, pos, max_water, backend)
+        tpos = wpos[true]
+        si, lj = ball_pairs(sel, tpos, pt.distance, backend)           # positions of the in-hull waters ...
+        wi, wj2 = self_pairs(tpos, pt.distance, backend)
+        e0 = np.concatenate([e0, label[wi] + fw, si])                  # ... names of the unfiltered list
+        e1 = np.concatenate([e1, label[wj2] + fw, label[lj] + fw])
+        if pt.check_angle:
+            e0, e1 = _angle_filter(pt, e0, e1, np.vstack([sel, wpos]), pos[pt.h_atom], pt.cut_angle, cos_threshold, None)
+    else:
+        e0, e1 = frame_pairs(pt, pos, 'water_around', around, False, backend, cos_threshold, False, box)
     lo, hi = np.minimum(e0, e1), np.maximum(e0, e1)          # np.sort of every pair (waterwire.py:245-247)
     da = hi < fw
     ww = lo >= fw
@@ -564,8 +606,8 @@ class WireResult:
 
 
 def run_wires(universe, selection, max_water=5, allow_direct_bonds=True, backend='kdtree', cos_threshold=None,
-              box=None, **ctor):
-    """WireAnalysis(...).set_water_wires(max_water, allow_direct_bonds) without the convex-hull option.
+              box=None, water_in_convex_hull=False, **ctor):
+    """WireAnalysis(...).set_water_wires(max_water, allow_direct_bonds, water_in_convex_hull).
     Returns a WireResult: `wire_lengths` = {key: float64[nb_frames]} (inf = no wire, 0 = direct H-bond, k = k waters)
     with the reference's key orientation (first discovery decides, waterwire.py:277-279, 299-301) and key order.
     The wire paths themselves (`hashs`, `hash_table`: Python `hash(str(path))`, salted per process) are not restated.
@@ -580,7 +622,7 @@ def run_wires(universe, selection, max_water=5, allow_direct_bonds=True, backend
     for col, f in enumerate(pt.frame_indices):
         pos = np.asarray(frames.frame(f), dtype=np.float32)
         bk = None if box is None else (np.asarray(box)[col] if np.asarray(box).ndim == 3 else np.asarray(box))
-        edges = wire_frame_edges(pt, pos, max_water, backend, cos_threshold, bk)
+        edges = wire_frame_edges(pt, pos, max_water, backend, cos_threshold, bk, water_in_convex_hull)
         wires, directs = wires_of_frame(pt, node_of, edges, max_water, allow_direct_bonds)
         for (s, t), k in wires.items():
             key = ids[s] + ':' + ids[t]

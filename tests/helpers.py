@@ -98,11 +98,12 @@ def port_with_ions(u, selection, method, ions, around=3.5, **kw):
 def load_golden_wires(name="wires_traj"):
     """(Universe, runs) of a golden water-wire fixture (tests/golden/make_golden_wires.py)."""
     from cgraphs_b200.universe import Topology, Universe
-    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    with open(os.path.join(GOLDEN_DIR, name + ".json")) as f:
+        doc = json.load(f)
+    runs = doc["runs"]
+    z = np.load(os.path.join(GOLDEN_DIR, doc.get("coordinates", name + ".npz")))     # (wires_hull shares wires_traj.npz)
     topo = Topology([str(s) for s in z["names"]], [str(s) for s in z["resnames"]], z["resids"],
                     [str(s) for s in z["segids"]])
-    with open(os.path.join(GOLDEN_DIR, name + ".json")) as f:
-        runs = json.load(f)["runs"]
     return Universe(topo, z["xyz"]), runs
 
 

@@ -104,9 +104,9 @@ def test_wires_unsupported_options_raise():
     s = synth.make_system(1500, 12, 5, hydrogens=True, water="TIP3")
     u = s.universe(1)
     with pytest.raises(NotImplementedError):
-        WireAnalysis("protein", u).set_water_wires(water_in_convex_hull=True)
-    with pytest.raises(NotImplementedError):
         WireAnalysis("protein", u, residuewise=False).set_water_wires()
+    with pytest.raises(NotImplementedError):
+        WireAnalysis("protein or resname TIP3", u).set_water_wires(water_in_convex_hull=True)
 
 
 def test_wide_shells_general_path_local_water_kernels():
@@ -150,3 +150,34 @@ def test_wires_random_sweep(block):
         got = _gpu(u, sel, mw, direct, options, **kw)
         assert_same_wires(wire_lists(got.wire_lengths), wire_lists(ref.wire_lengths),
                           "block %d case %d: %s max_water=%d %s %s" % (block, case, sel, mw, kw, options))
+
+
+# ---- convex-hull option: the call cgraphs itself makes (proteingraphanalyser.py:484, water_in_convex_hull=max_water) ------
+@pytest.mark.parametrize("i", range(len(load_golden_wires("wires_hull")[1])))
+def test_hull_wires_equal_golden(i):
+    from cgraphs_b200.mdhbond import WireAnalysis
+    u, runs = load_golden_wires("wires_hull")
+    r = runs[i]
+    for fused in (1, 0):
+        wa = WireAnalysis(r["selection"], u, native_options={"fused": fused}, **r["kwargs"])
+        wa.set_water_wires(max_water=r["max_water"], allow_direct_bonds=r["allow_direct_bonds"], water_in_convex_hull=r["max_water"])
+        assert_same_wires(wire_lists(wa.wire_lengths), r["wire_lengths"], "hull run %d fused=%d" % (i, fused))
+        assert sorted(sorted(e) for e in wa.filtered_graph.edges()) == r["graph_edges"]
+
+
+def test_hull_wires_equal_oracle_membrane_like():
+    """C3-like system, several batches, then the plain option on the same object (the virtual water lists are dropped)."""
+    from cgraphs_b200.mdhbond import WireAnalysis
+    from oracle import hbond_port
+    s, cfg = synth.config("C3", scale=0.1)
+    u = s.universe(12)
+    kw = dict(additional_donors=['N'], additional_acceptors=['O'])
+    wa = WireAnalysis("protein", u, native_options={"max_batch_frames": 5}, **kw)
+    for mw in (5, 2):
+        ref = hbond_port.run_wires(u, "protein", max_water=mw, water_in_convex_hull=True, **kw)
+        wa.set_water_wires(max_water=mw, water_in_convex_hull=mw)
+        assert_same_wires(wire_lists(wa.wire_lengths), wire_lists(ref.wire_lengths), "hull C3-like max_water=%d" % mw)
+        assert len(ref.wire_lengths) > 10
+    plain = hbond_port.run_wires(u, "protein", max_water=5, **kw)
+    wa.set_water_wires(max_water=5)
+    assert_same_wires(wire_lists(wa.wire_lengths), wire_lists(plain.wire_lengths), "plain after hull")

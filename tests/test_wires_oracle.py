@@ -60,3 +60,35 @@ def test_port_wires_membrane_like():
         p = hbond_port.run_wires(u, "protein", max_water=5, **kw)
         assert len(wa.wire_lengths) > 3
         assert_same_wires(wire_lists(p.wire_lengths), wire_lists(wa.wire_lengths))
+
+
+# ---- convex-hull option (waterwire.py:218-228; what cgraphs itself always sets, proteingraphanalyser.py:484) ----------
+@pytest.mark.parametrize("i", range(len(load_golden_wires("wires_hull")[1])))
+def test_port_hull_wires_equal_golden(i):
+    u, runs = load_golden_wires("wires_hull")
+    r = runs[i]
+    p = hbond_port.run_wires(u, r["selection"], max_water=r["max_water"], allow_direct_bonds=r["allow_direct_bonds"],
+                             water_in_convex_hull=True, **r["kwargs"])
+    assert_same_wires(wire_lists(p.wire_lengths), r["wire_lengths"], "hull %d" % i)
+    assert list(p.wire_lengths) == list(r["wire_lengths"])
+    assert sorted(sorted(e) for e in p.filtered_graph.edges()) == r["graph_edges"]
+
+
+@pytest.mark.reference
+def test_port_hull_wires_equal_reference_random():
+    import warnings
+    warnings.filterwarnings("ignore")
+    ref = ref_harness.load_reference()
+    s = synth.make_system(3000, 40, 5, hydrogens=True, water="TIP3", n_chains=2)
+    u = s.universe(4)
+    differs = 0
+    for mw, ca in itertools.product([1, 3, 5], [True, False]):
+        kw = dict(check_angle=ca, additional_donors=['N'], additional_acceptors=['O'], add_donors_without_hydrogen=not ca)
+        wa = ref.WireAnalysis("protein", u, **kw)
+        wa.set_water_wires(max_water=mw, water_in_convex_hull=mw)
+        p = hbond_port.run_wires(u, "protein", max_water=mw, water_in_convex_hull=True, **kw)
+        assert_same_wires(wire_lists(p.wire_lengths), wire_lists(wa.wire_lengths), "hull %d %s" % (mw, ca))
+        assert list(p.wire_lengths) == list(wa.wire_lengths)
+        plain = hbond_port.run_wires(u, "protein", max_water=mw, **kw)
+        differs += wire_lists(plain.wire_lengths) != wire_lists(p.wire_lengths)
+    assert differs > 0            # the option changes the result on this system (else the test would prove nothing)
