@@ -35,6 +35,8 @@ namespace {
 
 struct WireCfg {
     const int* ent_node;     // [n_ent] residue node (< n_res) of a selection entry, n_res + water index of a water entry
+    const int* direct_node;  // [n_ent] node a DIRECT bond of a selection entry is booked on (residuewise=False: the atom's
+                             // own node, while wires are still booked on the node of the residue's first entry); may equal ent_node
     int n_res, n_wat;
     int max_water, allow_direct;
     int nb4;                 // row words that hold the per-frame bytes (the "first direct" tail follows)
@@ -183,13 +185,14 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
                 const int r = n0 < n_res ? n0 : n1;
                 if (atomicCAS(&ar_of[r], -1, -2) == -1) ar[atomicAdd(&s_nar, 1)] = r;
             } else if (n0 < n_res && wc.allow_direct) {
-                const int lo = min(n0, n1), hi = max(n0, n1);
+                const int d0 = wc.direct_node[e.x], d1 = wc.direct_node[e.y];
+                const int lo = min(d0, d1), hi = max(d0, d1);
                 const int h = table_slot(bt, ((unsigned long long)(unsigned)lo << 32) | (unsigned)hi);
                 if (h >= 0) {
                     unsigned* row = bt.bits + (size_t)h * bt.wpr;
                     atomicOr(&row[frame >> 2], 0x80u << (8 * (int)(frame & 3)));
                     const unsigned long long packed = ((unsigned long long)frame << 32) | ((unsigned long long)(unsigned)e.x << 1) |
-                                                      (unsigned long long)(n1 == hi ? 1 : 0);
+                                                      (unsigned long long)(d1 == hi ? 1 : 0);
                     atomicMax((unsigned long long*)(row + wc.nb4), ~packed);
                 }
             }

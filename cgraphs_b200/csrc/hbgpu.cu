@@ -175,6 +175,7 @@ struct hb_ctx {
     struct Wire {
         bool on = false;
         int* d_ent_node = nullptr;                // owned here (hb_set_wires may be called before every run)
+        int* d_direct_node = nullptr;             // hb_set_wire_direct_nodes (null: direct bonds are booked on ent_node)
         int n_res = 0, n_wat_nodes = 1, max_water = 0, allow_direct = 1;
         int nb4 = 0;                              // row words holding the per-frame bytes
         int2* d_edges = nullptr;
@@ -437,6 +438,7 @@ int hb_destroy(hb_ctx* ctx) {
     free_run(ctx);
     free_list(ctx->topo_allocs);
     if (ctx->wire.d_ent_node) cudaFree(ctx->wire.d_ent_node);
+    if (ctx->wire.d_direct_node) cudaFree(ctx->wire.d_direct_node);
     free_list(ctx->wire.virt_allocs);
     for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
     for (int k = 0; k < 2; ++k) { cudaEventDestroy(ctx->ev_copied[k]); cudaEventDestroy(ctx->ev_done[k]); }
@@ -501,6 +503,8 @@ int hb_set_topology(hb_ctx* ctx, const hb_topology* t) {
     ctx->wire.on = false;
     if (ctx->wire.d_ent_node) cudaFree(ctx->wire.d_ent_node);
     ctx->wire.d_ent_node = nullptr;
+    if (ctx->wire.d_direct_node) cudaFree(ctx->wire.d_direct_node);
+    ctx->wire.d_direct_node = nullptr;
     free_list(ctx->wire.virt_allocs);
     ctx->wire.virt_on = false;
     ctx->fused_unfit_around = -1.0;
@@ -665,10 +669,28 @@ int hb_set_wires(hb_ctx* ctx, const int32_t* ent_node, int32_t n_ent, int32_t n_
     ctx->wire.d_ent_node = nullptr;
     CK(cudaMalloc((void**)&ctx->wire.d_ent_node, std::max<size_t>((size_t)n_ent * sizeof(int), 16)));
     if (n_ent) CK(cudaMemcpy(ctx->wire.d_ent_node, ent_node, (size_t)n_ent * sizeof(int), cudaMemcpyHostToDevice));
+    if (ctx->wire.d_direct_node) cudaFree(ctx->wire.d_direct_node);     // (set again after every hb_set_wires)
+    ctx->wire.d_direct_node = nullptr;
     ctx->wire.n_res = n_res;
     ctx->wire.max_water = max_water;
     ctx->wire.allow_direct = allow_direct_bonds != 0;
     ctx->wire.on = true;
+    return HB_OK;
+}
+
+int hb_set_wire_direct_nodes(hb_ctx* ctx, const int32_t* direct_node, int32_t n_ent) {
+    if (!ctx) return HB_ERR_ARG;
+    if (!ctx->wire.on) return fail(ctx, HB_ERR_STATE, "hb_set_wire_direct_nodes before hb_set_wires");
+    if (ctx->running) return fail(ctx, HB_ERR_STATE, "hb_set_wire_direct_nodes during a run");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->wire.d_direct_node) cudaFree(ctx->wire.d_direct_node);
+    ctx->wire.d_direct_node = nullptr;
+    if (!direct_node) return HB_OK;
+    if (n_ent != ctx->n_ent) return fail(ctx, HB_ERR_ARG, "hb_set_wire_direct_nodes: size mismatch");
+    for (int i = 0; i < n_ent; ++i)
+        if (direct_node[i] < 0 || direct_node[i] >= ctx->wire.n_res + ctx->wire.n_wat_nodes) return fail(ctx, HB_ERR_ARG, "hb_set_wire_direct_nodes: node out of range");
+    CK(cudaMalloc((void**)&ctx->wire.d_direct_node, std::max<size_t>((size_t)n_ent * sizeof(int), 16)));
+    if (n_ent) CK(cudaMemcpy(ctx->wire.d_direct_node, direct_node, (size_t)n_ent * sizeof(int), cudaMemcpyHostToDevice));
     return HB_OK;
 }
 
@@ -1196,6 +1218,7 @@ static int run_batch(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf, 
         hb_ctx::Wire& w = ctx->wire;
         WireCfg c = w.cfg;
         c.ent_node = w.d_ent_node;
+        c.direct_node = w.d_direct_node ? w.d_direct_node : w.d_ent_node;
         c.max_water = w.max_water;
         c.allow_direct = w.allow_direct;
         c.nb4 = w.nb4;

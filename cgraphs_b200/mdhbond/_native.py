@@ -87,6 +87,7 @@ SYMBOLS = [
     ("hb_set_ions", C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32, C.c_int32]),
     ("hb_set_wires", C.c_int, [_P, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     ("hb_set_wire_virtual_waters", C.c_int, [_P, _P, _P, _P, C.c_int64]),
+    ("hb_set_wire_direct_nodes", C.c_int, [_P, _P, C.c_int32]),
     ("hb_set_option", C.c_int, [_P, C.c_char_p, C.c_int64]),
     ("hb_begin", C.c_int, [_P, C.c_int64]),
     ("hb_submit_frames", C.c_int, [_P, _P, C.c_int64, C.c_int64, _P]),
@@ -211,6 +212,13 @@ class Context:
         g = _i32(ent_node)
         self._ck(self.lib.hb_set_wires(self.h, _ptr(g, C.c_int32), len(g), int(n_res), int(max_water),
                                        int(bool(allow_direct_bonds))), "hb_set_wires")
+
+    def set_wire_direct_nodes(self, direct_node=None):
+        if direct_node is None:
+            self._ck(self.lib.hb_set_wire_direct_nodes(self.h, None, 0), "hb_set_wire_direct_nodes")
+            return
+        d = np.ascontiguousarray(direct_node, dtype=np.int32)
+        self._ck(self.lib.hb_set_wire_direct_nodes(self.h, d.ctypes.data, len(d)), "hb_set_wire_direct_nodes")
 
     def set_wire_virtual_waters(self, frame_off=None, true_wat=None, label_wat=None):
         """Per-frame (position water, name water) lists of the convex-hull wire option; None switches it off."""

@@ -102,24 +102,17 @@ class HbondBatch(object):
         return self.results
 
     # ---------------------------------------------------------------------------------------------
-    # conserved network over the batch (SURVEY 8f "next" #3): the counting rule of
-    # ConservedGraph.get_conserved_graph for graph_type "hbond" (cgraphs/conservedgraph.py:114-170, without the
-    # water-cluster relabelling of :139-149, which needs the workflow's superimposed reference coordinates),
-    # evaluated on the bond x structure occupancy matrix instead of one networkx graph per structure
+    # conserved network over the batch (SURVEY 8f "next" #3): ConservedGraph.get_conserved_graph for graph_type "hbond"
+    # (cgraphs/conservedgraph.py:114-170) evaluated on the bond x structure occupancy matrix instead of one networkx
+    # graph per structure, including the relabelling of waters that sit on a conserved-water cluster centre
+    # (conservedgraph.py:118-149).
     # ---------------------------------------------------------------------------------------------
-    def get_conserved_graph(self, conservation_threshold=0.9):
-        """Returns (conserved_nodes, conserved_edges): nodes / edges present in at least
-        round(n_structures * conservation_threshold) of the per-structure graphs. Edges are (node, node) tuples with
-        the smaller resid first (the orientation dict2graph gives them, helpfunctions.py:120-134); water nodes are
-        kept only when they take part in a conserved edge (conservedgraph.py:160-168)."""
-        if self.results is None:
-            raise AssertionError('run set_hbonds_in_selection / set_hbonds_in_selection_and_water_around first')
-        n = len(self.analyses)
-        th = _np.round(n * conservation_threshold)
+    def _graph_edges_of_rows(self):
+        """Graph edge (a, b) of every bond key like dict2graph forms it (helpfunctions.py:120-134); -1: self loop."""
         cut = 3 if self.residuewise else 4
         edge_of_row = _np.full(len(self.bond_keys), -1, dtype=_np.int64)
         edges, index = [], {}
-        for r, key in enumerate(self.bond_keys):                 # graph edge of every bond key (once per key)
+        for r, key in enumerate(self.bond_keys):
             a, b = key.split(':')
             a = '-'.join(a.split('-')[:cut])
             b = '-'.join(b.split('-')[:cut])
@@ -132,28 +125,109 @@ class HbondBatch(object):
                 index[e] = len(edges)
                 edges.append((a, b))
             edge_of_row[r] = index[e]
+        return edges, edge_of_row
+
+    def _water_positions(self, i):
+        """conservedgraph.py:118-124: resid -> position of the waters of structure i (a later water with the same resid
+        replaces an earlier one, as in the reference's dict)."""
+        a = self.analyses[i]
+        top = a._topology
+        pos = a._first_frame_positions()
+        cols_resid = _np.asarray(a._universe.atoms.resids)
+        out = {}
+        for atom in top.water_atoms:
+            out[int(cols_resid[atom])] = pos[atom]
+        return out
+
+    def get_conserved_graph(self, conservation_threshold=0.9, eps=1.5, reference_coordinates=None):
+        """Returns (conserved_nodes, conserved_edges): nodes / edges present in at least
+        round(n_structures * conservation_threshold) of the per-structure graphs (conservedgraph.py:151-169).
+
+        reference_coordinates: the workflow's ``{'X-w-<k>': (x, y, z), ...}`` table of conserved-water cluster centres
+        (conservedgraph.py:41-45); a water end of an edge that lies within ``eps`` of a centre is renamed to that
+        centre's node before the edges are counted (conservedgraph.py:131-149; the last matching centre wins, nodes are
+        counted under their own names). Edges are (node, node) tuples, unordered: the reference orients a conserved edge
+        like its first occurrence in networkx's iteration order, which is not a property of the H-bond data.
+        Water nodes are kept only when they take part in a conserved edge (conservedgraph.py:160-168).
+
+        Without water clusters the edge counts are the per-row popcounts of the packed occupancy matrix that is still
+        on the device (hb_get_counts); rows whose edge may be renamed are counted structure by structure."""
+        if self.results is None:
+            raise AssertionError('run set_hbonds_in_selection / set_hbonds_in_selection_and_water_around first')
+        n = len(self.analyses)
+        th = _np.round(n * conservation_threshold)
+        edges, edge_of_row = self._graph_edges_of_rows()
         occ = self.occupancy                                     # bool [n_bonds, n_structures]
         keep = edge_of_row >= 0
+        is_water = lambda name: name.split('-')[1] in WATER_TYPES
+        centres = [(k, _np.asarray(c, dtype=_np.float64)) for k, c in (reference_coordinates or {}).items() if k.startswith("X-w")]
+        rows_per_edge = _np.bincount(edge_of_row[keep], minlength=len(edges))
+        counts = {}                                              # unordered edge -> instances over the structures
+        # edges that cannot be renamed and come from exactly one row: device popcount of that row
+        simple = _np.array([rows_per_edge[i] == 1 and not (centres and (is_water(a) or is_water(b)))
+                            for i, (a, b) in enumerate(edges)], dtype=bool) if edges else _np.zeros(0, bool)
+        row_counts = None
+        if simple.any() and self._ctx is not None and getattr(self._ctx, "_run_id", None) is not None:
+            try:
+                row_counts = self._ctx.counts(len(self.bond_keys))
+            except Exception:
+                row_counts = None
+        if row_counts is None:
+            row_counts = occ.sum(axis=1)
+        for r in _np.nonzero(keep)[0]:
+            e = edge_of_row[r]
+            if simple[e]:
+                counts[frozenset(edges[e])] = counts.get(frozenset(edges[e]), 0) + int(row_counts[r])
+        # the rest: per structure, the distinct graph edges present, water ends renamed by that structure's coordinates
+        hard = _np.nonzero(~simple)[0] if len(edges) else []
+        if len(hard):
+            hard_rows = _np.nonzero(keep & ~simple[_np.where(keep, edge_of_row, 0)])[0]
+            present = _np.zeros((len(edges), n), dtype=bool)
+            _np.logical_or.at(present, edge_of_row[hard_rows], occ[hard_rows])
+            eps2 = float(eps) ** 2
+            for i in range(n):
+                idx = _np.nonzero(present[:, i])[0]
+                if not len(idx):
+                    continue
+                waters = self._water_positions(i) if centres else {}
+                for e in idx:
+                    ends = list(edges[e])
+                    for j in (0, 1):
+                        if centres and is_water(ends[j]):
+                            w = waters.get(int(ends[j].split('-')[2]))
+                            if w is not None:
+                                for key, cc in centres:
+                                    d = _np.asarray(w, dtype=_np.float64) - cc
+                                    if d[0] ** 2 + d[1] ** 2 + d[2] ** 2 <= eps2:
+                                        ends[j] = "X-w-" + key.split("-")[-1]
+                    k = frozenset(ends) if ends[0] != ends[1] else (ends[0],)
+                    counts[k] = counts.get(k, 0) + 1
+        # nodes under their own names: a node is in a structure's graph iff one of its edges is
         edge_present = _np.zeros((len(edges), n), dtype=bool)
-        _np.logical_or.at(edge_present, edge_of_row[keep], occ[keep])
-        edge_counts = edge_present.sum(axis=1)
+        if keep.any():
+            _np.logical_or.at(edge_present, edge_of_row[keep], occ[keep])
         node_index, node_names = {}, []
-        ends = _np.empty((len(edges), 2), dtype=_np.int64)
+        ends_ix = _np.empty((len(edges), 2), dtype=_np.int64)
         for i, (a, b) in enumerate(edges):
             for j, name in enumerate((a, b)):
                 if name not in node_index:
                     node_index[name] = len(node_names)
                     node_names.append(name)
-                ends[i, j] = node_index[name]
+                ends_ix[i, j] = node_index[name]
         node_present = _np.zeros((len(node_names), n), dtype=bool)
         if len(edges):
-            _np.logical_or.at(node_present, ends[:, 0], edge_present)
-            _np.logical_or.at(node_present, ends[:, 1], edge_present)
+            _np.logical_or.at(node_present, ends_ix[:, 0], edge_present)
+            _np.logical_or.at(node_present, ends_ix[:, 1], edge_present)
         node_counts = node_present.sum(axis=1)
-        conserved_edges = [edges[i] for i in _np.nonzero(edge_counts >= th)[0]]
+        conserved_edges = []
+        for k, c in counts.items():
+            if c >= th:
+                t = tuple(sorted(k)) if isinstance(k, frozenset) else (k[0], k[0])
+                conserved_edges.append(t)
         in_edge = {x for e in conserved_edges for x in e}
         conserved_nodes = [node_names[i] for i in _np.nonzero(node_counts >= th)[0]
-                           if node_names[i].split('-')[1] not in WATER_TYPES or node_names[i] in in_edge]
+                           if not is_water(node_names[i]) or node_names[i] in in_edge]
         self.conserved_edges = sorted(conserved_edges)
         self.conserved_nodes = sorted(conserved_nodes)
+        self.conserved_edge_counts = {tuple(sorted(k)) if isinstance(k, frozenset) else (k[0], k[0]): c for k, c in counts.items()}
         return self.conserved_nodes, self.conserved_edges

@@ -347,6 +347,9 @@ class HbondAnalysis(object):
         if wires is not None:
             ctx.set_wires(*wires[:4])
             ctx._wires_on = True
+            direct = getattr(self, "_wire_direct_node", None)
+            if direct is not None:
+                ctx.set_wire_direct_nodes(direct)
             if len(wires) > 4:
                 ctx.set_wire_virtual_waters(*wires[4])
             else:

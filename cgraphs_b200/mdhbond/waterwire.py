@@ -20,7 +20,7 @@ searches them and the same breadth-first search follows. Slow (a Delaunay triang
 reference) but drop-in: the results are the reference's, labelling included.
 
 Not covered (out of scope): the explicit wire paths (``hashs`` / ``hash_table``: Python ``hash(str(path))``
-values, salted per process), ``residuewise=False`` and the plotting methods.
+values, salted per process) and the plotting methods.
 """
 from __future__ import annotations
 
@@ -93,22 +93,37 @@ class WireAnalysis(HbondAnalysis):
         if restore_filename is not None:
             return
         top = self._topology
-        # waterwire.py:60-65: `da_trans` - all entries with one residue-level id are the first of them
+        # waterwire.py:60-65: `da_trans` - all entries with one residue-level id are the first of them; wires are booked
+        # on that first entry whatever `residuewise` says, direct bonds on the entries themselves (waterwire.py:296-301).
+        # Nodes: residuewise - one per residue; else one per atom-level id (the donor and the acceptor entry of one atom
+        # share their id string, so they share a node).
         res_ids = ['-'.join(s.split('-')[:3]) for s in top.all_ids_atomwise[:top.first_water]]
         first = {}
-        node_first_entry = []
-        ent_node = _np.empty(top.first_water + top.nW, dtype=_np.int32)
+        da_trans = _np.empty(top.first_water, dtype=_np.int64)
         for e, rid in enumerate(res_ids):
-            n = first.get(rid)
+            da_trans[e] = first.setdefault(rid, e)
+        node_ids = res_ids if self.residuewise else list(top.all_ids_atomwise[:top.first_water])
+        node_of_id = {}
+        node_first_entry = []
+        own_node = _np.empty(top.first_water, dtype=_np.int32)
+        for e, nid in enumerate(node_ids):
+            n = node_of_id.get(nid)
             if n is None:
-                n = first[rid] = len(node_first_entry)
+                n = node_of_id[nid] = len(node_first_entry)
                 node_first_entry.append(e)
-            ent_node[e] = n
+            own_node[e] = n
         self._n_wire_nodes = len(node_first_entry)
+        ent_node = _np.empty(top.first_water + top.nW, dtype=_np.int32)
+        ent_node[:top.first_water] = own_node[da_trans]
         ent_node[top.first_water:] = self._n_wire_nodes + _np.arange(top.nW, dtype=_np.int32)
         self._wire_ent_node = ent_node
+        self._wire_direct_node = None
+        if not self.residuewise:
+            direct = ent_node.copy()
+            direct[:top.first_water] = own_node
+            self._wire_direct_node = direct
         self._wire_node_entry = _np.asarray(node_first_entry, dtype=_np.int64)
-        self.da_trans = self._wire_node_entry[ent_node[:top.first_water]]
+        self.da_trans = da_trans
 
     def _hull_water_lists(self, max_water, lo, hi):
         """Per frame of [lo, hi): (offsets, water points whose positions are searched, water points they are named as) -
@@ -148,8 +163,6 @@ class WireAnalysis(HbondAnalysis):
 
     def set_water_wires(self, max_water=5, allow_direct_bonds=True, water_in_convex_hull=False):
         """waterwire.py:191-317."""
-        if not self.residuewise:
-            raise NotImplementedError('water wires: residuewise=False is not supported')
         max_water = int(max_water)
         self._allow_direct_bonds = allow_direct_bonds
         around = float(max_water + 1) * self.distance / 2.

@@ -165,6 +165,10 @@ int hb_set_ions(hb_ctx* ctx, const int32_t* ion_atom, const int32_t* ion_group, 
  * mode off. The bit-matrix post-processing calls (hb_get_counts, ...) do not apply to such rows. */
 int hb_set_wires(hb_ctx* ctx, const int32_t* ent_node, int32_t n_ent, int32_t n_res, int32_t max_water,
                  int32_t allow_direct_bonds);
+/* residuewise = False (waterwire.py:60-65, 277-301): wires stay booked on the node of the residue's first entry
+ * (ent_node of hb_set_wires, which then holds ATOM nodes: the dense rank of the entry's atom-level id), direct H-bonds
+ * on the node of the entry's own atom: direct_node[e]. Call after hb_set_wires; NULL = direct bonds use ent_node. */
+int hb_set_wire_direct_nodes(hb_ctx* ctx, const int32_t* direct_node, int32_t n_ent);
 /* Convex-hull option of the water wires (set_water_wires(water_in_convex_hull=...), waterwire.py:218-228; the only form
  * cgraphs itself calls, proteingraphanalyser.py:484). The Delaunay test stays on the host (scipy / Qhull, as in the
  * reference); the host then hands over, per frame, the waters whose POSITIONS enter the distance searches (true_wat:

@@ -683,3 +683,40 @@ def run_presence_around(universe, selection, around_distance, start=None, stop=N
                 row = result[key] = np.zeros(len(frame_indices), dtype=bool)
             row[col] = True
     return result
+
+
+# ------------------------------------------------------------------------------------------------
+# ConservedGraph.get_conserved_graph, graph_type "hbond" (cgraphs/conservedgraph.py:114-170)
+# ------------------------------------------------------------------------------------------------
+WATER_TYPES = ("HOH", "TIP3", "TIP4")                          # cgraphs/helperfunctions.py:47
+
+
+def conserved_graph(graphs, water_positions, reference_coordinates, conservation_threshold=0.9, eps=1.5):
+    """graphs: one networkx graph per structure; water_positions: per structure {resid: position} of its waters
+    (conservedgraph.py:118-124). Water ends of an edge that lie within eps of a cluster centre 'X-w-<k>' are renamed
+    to it (the last matching centre wins, conservedgraph.py:131-149); nodes are counted under their own names. Returns
+    (conserved node names, conserved edges as frozensets / 1-tuples for renamed self pairs): present in at least
+    round(n * conservation_threshold) structures; water nodes only when some conserved edge names them."""
+    nodes, edges = [], []
+    centres = [(k, c) for k, c in (reference_coordinates or {}).items() if k.startswith("X-w")]
+    for g, waters in zip(graphs, water_positions):
+        nodes += list(g.nodes)
+        for edge in g.edges:
+            edge = [edge[0], edge[1]]
+            for i in (0, 1):
+                if edge[i].split("-")[1] in WATER_TYPES:
+                    n = edge[i].split("-")[2]
+                    for key, cc in centres:
+                        w = waters.get(int(n))
+                        if w is not None and ((w[0] - cc[0]) ** 2 + (w[1] - cc[1]) ** 2 + (w[2] - cc[2]) ** 2 <= float(eps) ** 2):
+                            edge[i] = "X-w-" + key.split("-")[-1]
+            edges.append(frozenset(edge) if edge[0] != edge[1] else (edge[0],))
+    th = np.round(len(graphs) * conservation_threshold)
+    un, cn = np.unique(nodes, return_counts=True) if nodes else (np.zeros(0, str), np.zeros(0, int))
+    count = {}
+    for e in edges:
+        count[e] = count.get(e, 0) + 1
+    c_edges = {e for e, c in count.items() if c >= th}
+    named = {x for e in c_edges for x in e}
+    c_nodes = {str(x) for x, c in zip(un, cn) if c >= th and (x.split("-")[1] not in WATER_TYPES or x in named)}
+    return c_nodes, c_edges

@@ -123,3 +123,67 @@ def run_reference(universe, selection, method="in_selection", around=3.5, exclud
 def results_bytes(results):
     """Canonical comparable form of a result dict (SURVEY 8c parity definition)."""
     return {k: bytes(memoryview(v.astype(bool))) for k, v in results.items()}
+
+
+_REF_WORKFLOW = None
+
+
+def load_reference_workflow(path=None):
+    """The reference's ``conservedgraph`` module (``ConservedGraph.get_conserved_graph``, conservedgraph.py:56-170),
+    imported under a throw-away package so that ``cgraphs/__init__.py`` (GUI imports) is never executed. Needs the
+    sources (this container): ``Bio``, ``MDAnalysis.analysis`` and ``matplotlib.cm`` are stubbed - the function under
+    test uses none of them."""
+    global _REF_WORKFLOW
+    if _REF_WORKFLOW is not None:
+        return _REF_WORKFLOW
+    path = path or os.environ.get("CGRAPHS_REF", REF_DEFAULT)
+    if not os.path.isfile(os.path.join(path, "conservedgraph.py")):
+        raise ImportError("reference conservedgraph.py not found under %s" % path)
+    _install_stubs()
+    mda = sys.modules["MDAnalysis"]
+    if "MDAnalysis.analysis" not in sys.modules:
+        ana = types.ModuleType("MDAnalysis.analysis")
+        dist = types.ModuleType("MDAnalysis.analysis.distances")
+        ana.distances = dist
+        mda.analysis = ana
+        sys.modules["MDAnalysis.analysis"] = ana
+        sys.modules["MDAnalysis.analysis.distances"] = dist
+    if "Bio" not in sys.modules:
+        bio = types.ModuleType("Bio")
+        svd = types.ModuleType("Bio.SVDSuperimposer")
+        svd.SVDSuperimposer = type("SVDSuperimposer", (), {})
+        align = types.ModuleType("Bio.Align")
+        bio.SVDSuperimposer = svd
+        bio.Align = align
+        sys.modules["Bio"] = bio
+        sys.modules["Bio.SVDSuperimposer"] = svd
+        sys.modules["Bio.Align"] = align
+    mpl = sys.modules["matplotlib"]
+    if getattr(mpl, "_hbgpu_stub", False) and "matplotlib.cm" not in sys.modules:
+        cm = types.ModuleType("matplotlib.cm")
+        mpl.cm = cm
+        sys.modules["matplotlib.cm"] = cm
+        for name in ("lines", "patches", "colors"):
+            m = types.ModuleType("matplotlib." + name)
+            setattr(mpl, name, m)
+            sys.modules["matplotlib." + name] = m
+    pkg = types.ModuleType("_cgraphs_ref_pkg")
+    pkg.__path__ = [path]
+    sys.modules["_cgraphs_ref_pkg"] = pkg
+    mod = importlib.import_module("_cgraphs_ref_pkg.conservedgraph")
+    _REF_WORKFLOW = mod
+    return mod
+
+
+def reference_conserved_graph(graph_coord_objects, reference_coordinates, conservation_threshold=0.9, eps=1.5):
+    """Run the reference's ConservedGraph.get_conserved_graph (graph_type "hbond") on prepared per-structure objects
+    ({name: {"graph": networkx graph, "structure": Universe}}) without its file-based constructor."""
+    import logging
+    mod = load_reference_workflow()
+    obj = mod.ConservedGraph.__new__(mod.ConservedGraph)
+    obj.logger = logging.getLogger("cgraphs_ref_stub")
+    obj.graph_type = "hbond"
+    obj.graph_coord_objects = graph_coord_objects
+    obj.reference_coordinates = reference_coordinates
+    obj.get_conserved_graph(conservation_threshold=conservation_threshold, eps=eps)
+    return obj.conserved_nodes, obj.conserved_edges

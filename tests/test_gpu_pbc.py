@@ -118,3 +118,66 @@ def test_pbc_argument_errors():
     ctx.begin(1)
     with pytest.raises(_native.HbError, match="lower-triangular"):
         ctx.submit(s.frames(0, 1), box=bad)
+
+
+def _ckdtree_periodic_keys(pt, pos, L, method, around):
+    """One frame's bond keys with scipy's own periodic cKDTree (boxsize=...) doing every distance query - an independent
+    check of the orthorhombic minimum-image search: wrapped float32 coordinates, no angle criterion."""
+    from scipy.spatial import cKDTree
+    from oracle import hbond_port
+    Ld = np.asarray(L, dtype=np.float64)
+    wrap = lambda p: np.mod(p.astype(np.float64), Ld)              # cKDTree wants [0, L)
+    nD, fw = pt.nD, pt.first_water
+    sel = wrap(pos[pt.entry_atom[:fw]])
+    ta, td = cKDTree(wrap(pos[pt.acceptors]), boxsize=Ld), cKDTree(wrap(pos[pt.donors]), boxsize=Ld)
+    e0, e1 = [], []
+    for i, js in enumerate(ta.query_ball_tree(td, pt.distance)):
+        for j in js:
+            e0.append(i + nD)
+            e1.append(j)
+    e0, e1 = np.asarray(e0, np.int64), np.asarray(e1, np.int64)
+    bb = hbond_port._backbone_flags(pt)
+    keep = ~(bb[e0] & bb[e1])
+    e0, e1 = e0[keep], e1[keep]
+    if method == "water_around":
+        wpos = wrap(pos[pt.water_atoms])
+        tw, ts = cKDTree(wpos, boxsize=Ld), cKDTree(sel, boxsize=Ld)
+        local = np.unique([j for js in ts.query_ball_tree(tw, around) for j in js]).astype(np.int64)
+        tl = cKDTree(wpos[local], boxsize=Ld)
+        s0, s1 = [], []
+        for i, js in enumerate(ts.query_ball_tree(tl, pt.distance)):
+            for j in js:
+                s0.append(i)
+                s1.append(local[j] + fw)
+        ww = np.array(sorted(tl.query_pairs(pt.distance)), dtype=np.int64).reshape(-1, 2)
+        e0 = np.concatenate([e0, local[ww[:, 0]] + fw, np.asarray(s0, np.int64)])
+        e1 = np.concatenate([e1, local[ww[:, 1]] + fw, np.asarray(s1, np.int64)])
+    return hbond_port._frame_keys(pt, e0, e1, hbond_port.key_ids(pt, method))
+
+
+@pytest.mark.parametrize("method", ["in_selection", "water_around"])
+def test_ortho_pbc_equals_scipy_periodic_ckdtree(method):
+    """Every atom wrapped into the cell on its own (molecules cut by the faces), the protein straddling three faces:
+    the per-frame bond sets of the minimum-image kernels equal what scipy's cKDTree(boxsize=...) finds."""
+    from oracle import hbond_port
+    s, cfg = synth.config("C2", scale=0.3)
+    box = hbond_port.box_rows(s.dimensions)
+    L = np.array([box[0, 0], box[1, 1], box[2, 2]], dtype=np.float32)
+    nf = 4
+    xyz = s.frames(0, nf).astype(np.float64) + np.array([0.48, 0.51, 0.5]) * L.astype(np.float64)
+    xyz = np.mod(xyz, L.astype(np.float64)).astype(np.float32)
+    xyz = np.where(xyz >= L, xyz - L, xyz)                            # (float32 rounding can land exactly on L)
+    u = Universe(s.topology, xyz, s.dimensions)
+    kw = dict(check_angle=False, add_donors_without_hydrogen=True, additional_donors=['N'], additional_acceptors=['O'])
+    pt = hbond_port.PortTopology(u, "protein", **kw)
+    want = {}
+    for f in range(nf):
+        for key in _ckdtree_periodic_keys(pt, xyz[f], L, method, 4.0):
+            want.setdefault(key, np.zeros(nf, dtype=bool))[f] = True
+    assert len(want) > 8
+    for opts in ({"fused": 1}, {"fused": 0}):
+        got = _run(u, "protein", method, opts, around=4.0, pbc="ortho", **kw)
+        assert_same_results(got.initial_results, want, "scipy periodic cKDTree, %s %s" % (method, opts))
+    # and the pairs really cross the faces: without images the result is a different one
+    plain = _run(u, "protein", method, around=4.0, **kw)
+    assert {k: v.tobytes() for k, v in plain.initial_results.items()} != {k: v.tobytes() for k, v in want.items()}

@@ -104,8 +104,6 @@ def test_wires_unsupported_options_raise():
     s = synth.make_system(1500, 12, 5, hydrogens=True, water="TIP3")
     u = s.universe(1)
     with pytest.raises(NotImplementedError):
-        WireAnalysis("protein", u, residuewise=False).set_water_wires()
-    with pytest.raises(NotImplementedError):
         WireAnalysis("protein or resname TIP3", u).set_water_wires(water_in_convex_hull=True)
 
 
@@ -181,3 +179,22 @@ def test_hull_wires_equal_oracle_membrane_like():
     plain = hbond_port.run_wires(u, "protein", max_water=5, **kw)
     wa.set_water_wires(max_water=5)
     assert_same_wires(wire_lists(wa.wire_lengths), wire_lists(plain.wire_lengths), "plain after hull")
+
+
+def test_wires_atomwise_keys():
+    """residuewise=False (waterwire.py:60-65, 277-301): wires named by the first entry of each residue, direct bonds by
+    the atoms themselves; plain and convex-hull option, against the oracle (pinned to the live reference on CPU)."""
+    from cgraphs_b200.mdhbond import WireAnalysis
+    from oracle import hbond_port
+    s = synth.make_system(3000, 40, 5, hydrogens=True, water="TIP3", n_chains=2)
+    u = s.universe(5)
+    for mw, ca, hull in itertools.product([1, 3], [True, False], [False, True]):
+        kw = dict(check_angle=ca, add_donors_without_hydrogen=not ca, residuewise=False,
+                  additional_donors=['N'], additional_acceptors=['O'])
+        ref = hbond_port.run_wires(u, "protein", max_water=mw, water_in_convex_hull=hull, **kw)
+        wa = WireAnalysis("protein", u, **kw)
+        wa.set_water_wires(max_water=mw, water_in_convex_hull=hull)
+        what = "atomwise max_water=%d angle=%s hull=%s" % (mw, ca, hull)
+        assert_same_wires(wire_lists(wa.wire_lengths), wire_lists(ref.wire_lengths), what)
+        assert graph_edges(wa.filtered_graph) == graph_edges(ref.filtered_graph), what
+        assert any(len(k.split(':')[0].split('-')) == 4 for k in ref.wire_lengths)

@@ -92,3 +92,21 @@ def test_port_hull_wires_equal_reference_random():
         plain = hbond_port.run_wires(u, "protein", max_water=mw, **kw)
         differs += wire_lists(plain.wire_lengths) != wire_lists(p.wire_lengths)
     assert differs > 0            # the option changes the result on this system (else the test would prove nothing)
+
+
+@pytest.mark.reference
+def test_port_wires_atomwise_equal_reference():
+    """residuewise=False: the port follows the reference (wire keys by the residue's first entry, direct bonds by atom)."""
+    import warnings
+    warnings.filterwarnings("ignore")
+    ref = ref_harness.load_reference()
+    s = synth.make_system(3000, 40, 5, hydrogens=True, water="TIP3", n_chains=2)
+    u = s.universe(4)
+    for mw, ca, hull in itertools.product([1, 3], [True, False], [False, True]):
+        kw = dict(check_angle=ca, additional_donors=['N'], additional_acceptors=['O'], add_donors_without_hydrogen=not ca,
+                  residuewise=False)
+        wa = ref.WireAnalysis("protein", u, **kw)
+        wa.set_water_wires(max_water=mw, water_in_convex_hull=hull)
+        p = hbond_port.run_wires(u, "protein", max_water=mw, water_in_convex_hull=hull, **kw)
+        assert_same_wires(wire_lists(p.wire_lengths), wire_lists(wa.wire_lengths), "atomwise %d %s %s" % (mw, ca, hull))
+        assert list(p.wire_lengths) == list(wa.wire_lengths)
