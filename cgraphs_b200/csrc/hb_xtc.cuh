@@ -6,7 +6,8 @@
 //
 //   The bit stream is a sequence of groups {large atom: `bitsize` bits, flag bit, [5 bits: run + smallidx change],
 //   run / 3 small atoms of `smallidx` bits each}. Where a group starts depends on all groups before it. Per window
-//   of 4 kB of the stream (staged in shared memory with 16-byte loads) the warp works in two phases:
+//   of 4 kB of the stream (staged in shared memory with 16-byte loads) there are two phases, done by different warps of
+//   the frame's CTA (the scanner warp runs one window ahead of the decoder warps; named barriers hand the buffers over):
 //   SCAN   finds the groups: as long as the flag bit is 0 nothing changes, so lane k assumes the next k groups have
 //          no flag and looks at "its" flag bit; the lanes up to and including the first one that finds a flag are
 //          right and queue one descriptor each (bit offset, atom index, run, smallidx), the flagged lane's new run /
@@ -133,16 +134,41 @@ __device__ __forceinline__ int xtc_bit_length(unsigned __int128 v) {
     return hi ? 128 - __clzll((long long)hi) : (lo ? 64 - __clzll((long long)lo) : 0);
 }
 
-struct XtcShared {
-    unsigned win[XTC_WIN_BYTES / 4 + 8];          // window of the bit stream (+ 16 bytes read-ahead, + padding)
+struct __align__(16) XtcWindow {                  // one window of the bit stream and what the scan found in it
+    unsigned win[XTC_WIN_BYTES / 4 + 8];          // the stream as native words (+ 16 bytes read-ahead, + padding)
     uint2 queue[XTC_QCAP];                        // x: bit offset inside the window | nsmall << 16 | flag << 20 | smallidx << 21, y: atom
-    float stage[XTC_WARPS][XTC_STAGE_ATOMS * 3];
-    unsigned long long pos;                       // stream state, owned by warp 0, published at the end of every scan
-    int i, nq, i_first, bad;
+    long long wbase_bits;                         // stream position of the window
+    int nq, i_first, i_end;                       // groups queued (-1: no more windows), atoms before / behind them
+};
+
+struct XtcShared {
+    XtcWindow w[2];
+    float stage[XTC_WARPS - 1][XTC_STAGE_ATOMS * 3];
+    int bad;
     int rb[8], re[8];                             // atom ranges to write
 };
 
-// One CTA (XTC_WARPS warps) per frame: all warps stage the window and decode, warp 0 scans.
+#define XTC_BAR_FULL 1                             // named barriers 1, 2: window b scanned (scanner arrives, decoders wait)
+#define XTC_BAR_EMPTY 3                            // named barriers 3, 4: window b decoded (decoders arrive, scanner waits)
+// (barrier numbers as immediates: with a register operand ptxas reserves all 16 barriers for the CTA, which costs occupancy)
+template <int ID>
+__device__ __forceinline__ void xtc_bar_sync_id() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(XTC_WARPS * 32) : "memory"); }
+template <int ID>
+__device__ __forceinline__ void xtc_bar_arrive_id() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(XTC_WARPS * 32) : "memory"); }
+__device__ __forceinline__ void xtc_bar_sync(int base, int b) {
+    __syncwarp();
+    if (base == XTC_BAR_FULL) { if (b) xtc_bar_sync_id<XTC_BAR_FULL + 1>(); else xtc_bar_sync_id<XTC_BAR_FULL>(); }
+    else { if (b) xtc_bar_sync_id<XTC_BAR_EMPTY + 1>(); else xtc_bar_sync_id<XTC_BAR_EMPTY>(); }
+}
+__device__ __forceinline__ void xtc_bar_arrive(int base, int b) {
+    __syncwarp();
+    __threadfence_block();                         // what this warp wrote to shared memory is visible to the waiting side
+    if (base == XTC_BAR_FULL) { if (b) xtc_bar_arrive_id<XTC_BAR_FULL + 1>(); else xtc_bar_arrive_id<XTC_BAR_FULL>(); }
+    else { if (b) xtc_bar_arrive_id<XTC_BAR_EMPTY + 1>(); else xtc_bar_arrive_id<XTC_BAR_EMPTY>(); }
+}
+
+// One CTA (XTC_WARPS warps) per frame, warp specialised: warp 0 stages windows and scans them, running one window ahead;
+// the other warps decode the groups it queued.
 __global__ void __launch_bounds__(XTC_WARPS * 32, 6) k_xtc_decode(XtcArgs A) {
     __shared__ __align__(16) XtcShared S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -170,52 +196,55 @@ __global__ void __launch_bounds__(XTC_WARPS * 32, 6) k_xtc_decode(XtcArgs A) {
         lo[k] = (int)xtc_be32(rec + 60 + 4 * k);
         size[k] = (unsigned)((int)xtc_be32(rec + 72 + 4 * k) - lo[k] + 1);
     }
-    int smallidx = (int)xtc_be32(rec + 84);          // (kept up to date by warp 0 only)
+    const int smallidx0 = (int)xtc_be32(rec + 84);
     const unsigned long long nbits_total = 8ull * xtc_be32(rec + 88);
-    if (smallidx < 9 || smallidx > 72 || size[0] == 0 || size[1] == 0 || size[2] == 0 ||
+    if (smallidx0 < 9 || smallidx0 > 72 || size[0] == 0 || size[1] == 0 || size[2] == 0 ||
         92ull + nbits_total / 8 > (unsigned long long)rec_len) { fail(); return; }
     const unsigned char* data = rec + 92;
     const bool wide = (size[0] | size[1] | size[2]) > 0xffffffu;
     int wb[3] = {0, 0, 0}, bitsize;
-    XtcDiv dy{size[1], 0, 0}, dz{size[2], 0, 0};
     if (wide) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) wb[k] = 32 - __clz(size[k]);      // bits of an int of this range
         bitsize = wb[0] + wb[1] + wb[2];
     } else {
         bitsize = xtc_bit_length((unsigned __int128)size[0] * size[1] * size[2]);
-        if (size[1] > 1u) xtc_make_div(size[1], dy.mul, dy.shift);
-        if (size[2] > 1u) xtc_make_div(size[2], dz.mul, dz.shift);
     }
-    const float inv = (float)(1.0 / (double)precision);
-    const float scale = A.scale;
-    if (threadIdx.x == 0) { S.pos = 0; S.i = 0; S.bad = 0; }
-    int nsm = 0;                                         // warp 0: small atoms per group (run / 3) until a flag changes it
+    if (threadIdx.x == 0) S.bad = 0;
     __syncthreads();
-    for (;;) {
-        const unsigned long long pos0 = S.pos;           // bit position of the next group
-        const int i_first = S.i;                         // atoms decoded so far
-        if (i_first >= natoms || S.bad) break;
-        // ---- window: 16-byte aligned global address at or before the byte of pos0 -----------------------------------
-        const unsigned long long a0 = ((unsigned long long)(uintptr_t)data + (pos0 >> 3)) & ~15ull;
-        const long long wbase_bits = 8ll * ((long long)a0 - (long long)(uintptr_t)data);      // may be negative (header bytes)
-        {
-            const uint4* g = reinterpret_cast<const uint4*>(a0);
-            uint4* w = reinterpret_cast<uint4*>(S.win);
-            for (int k = threadIdx.x; k < XTC_WIN_BYTES / 16 + 1; k += XTC_WARPS * 32) {
-                uint4 v = __ldg(g + k);
-                v.x = __byte_perm(v.x, 0, 0x0123); v.y = __byte_perm(v.y, 0, 0x0123);
-                v.z = __byte_perm(v.z, 0, 0x0123); v.w = __byte_perm(v.w, 0, 0x0123);
-                w[k] = v;
+
+    if (warp == 0) {
+        // ---- scanner: stage a window, find the groups that lie completely inside it, hand it over ----------------------
+        // The scan only finds where groups start; it reads nothing but flag bits inside [0, lim] of the window and
+        // always advances, so it needs no validation of its own: the decoders check every descriptor they use.
+        unsigned long long pos0 = 0;         // bit position of the next group
+        int i = 0, nsm = 0, smallidx = smallidx0;        // atoms found so far, small atoms per group until a flag changes it
+        bool bad = false;
+        for (int wi = 0;; ++wi) {
+            XtcWindow& W = S.w[wi & 1];
+            if (wi >= 2) xtc_bar_sync(XTC_BAR_EMPTY, wi & 1);     // the decoders are done with this buffer
+            if (i >= natoms || bad || *reinterpret_cast<volatile int*>(&S.bad)) {
+                if (lane == 0) { W.nq = -1; if (bad) S.bad = 1; }
+                xtc_bar_arrive(XTC_BAR_FULL, wi & 1);
+                break;
             }
-            // the window after this one: into L2 while this one is decoded
-            if (warp == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(a0 + XTC_WIN_BYTES + 128ull * lane));
-        }
-        __syncthreads();
-        // ---- scan (warp 0): queue the groups that lie completely inside the window -----------------------------------
-        if (warp == 0) {
-            // The scan only finds where groups start; it reads nothing but flag bits inside [0, lim] of the window and
-            // always advances, so it needs no validation of its own: the decoders check every descriptor they use.
+            // window: 16-byte aligned global address at or before the byte of pos0
+            const unsigned long long a0 = ((unsigned long long)(uintptr_t)data + (pos0 >> 3)) & ~15ull;
+            const long long wbase_bits = 8ll * ((long long)a0 - (long long)(uintptr_t)data);      // may be negative (header bytes)
+            {
+                const uint4* g = reinterpret_cast<const uint4*>(a0);
+                uint4* w = reinterpret_cast<uint4*>(W.win);
+                for (int k = lane; k < XTC_WIN_BYTES / 16 + 1; k += 32) {
+                    uint4 v = __ldg(g + k);
+                    v.x = __byte_perm(v.x, 0, 0x0123); v.y = __byte_perm(v.y, 0, 0x0123);
+                    v.z = __byte_perm(v.z, 0, 0x0123); v.w = __byte_perm(v.w, 0, 0x0123);
+                    w[k] = v;
+                }
+                // the two windows after this one: into L2 while this one is scanned and decoded
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a0 + XTC_WIN_BYTES + 256ull * lane));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a0 + XTC_WIN_BYTES + 256ull * lane + 128ull));
+            }
+            __syncwarp();
             const long long wend_bits = wbase_bits + 8ll * XTC_WIN_BYTES;
             const bool last_window = wend_bits >= (long long)nbits_total;
             const long long end_rel = (long long)nbits_total - wbase_bits;                      // stream end, window relative
@@ -223,8 +252,8 @@ __global__ void __launch_bounds__(XTC_WARPS * 32, 6) k_xtc_decode(XtcArgs A) {
             // the whole group inside the window)
             const int lim = (int)min(end_rel - bitsize - 1, last_window ? (1ll << 30) : (long long)(8 * XTC_WIN_BYTES - XTC_GROUP_MAX_BITS));
             int prel0 = (int)((long long)pos0 - wbase_bits);
-            int i = i_first, nq = 0;
-            bool bad = false;
+            const int i_first = i;
+            int nq = 0;
             while (i < natoms && nq <= XTC_QCAP - 32) {
                 const int glen = bitsize + 1 + nsm * smallidx;
                 const unsigned sidx_bits = (unsigned)smallidx << 21;
@@ -233,7 +262,7 @@ __global__ void __launch_bounds__(XTC_WARPS * 32, 6) k_xtc_decode(XtcArgs A) {
                 const bool active = i0 < natoms && prel <= lim;
                 // flag bit and the five bits behind it in one read
                 unsigned six = 0;
-                if (active) six = xtc_bits32(S.win, (unsigned)(prel + bitsize), 6);
+                if (active) six = xtc_bits32(W.win, (unsigned)(prel + bitsize), 6);
                 const unsigned am = __ballot_sync(0xffffffffu, active), fm = __ballot_sync(0xffffffffu, six >> 5);
                 if (!(am & 1u)) {
                     // lane 0 cannot go on: the window is used up (slide it), or the stream ended before the last atom
@@ -248,7 +277,7 @@ __global__ void __launch_bounds__(XTC_WARPS * 32, 6) k_xtc_decode(XtcArgs A) {
                 const int nsmall = flag ? fs : nsm;
                 const int change = flag ? r5 - 3 * fs : 1;                   // smallidx change + 1
                 const int pnext = prel + bitsize + 1 + 5 * flag + nsmall * smallidx;
-                if (lane < ngroups) S.queue[nq + lane] = make_uint2((unsigned)prel | ((unsigned)nsmall << 16) | (six >> 5 << 20) | sidx_bits,
+                if (lane < ngroups) W.queue[nq + lane] = make_uint2((unsigned)prel | ((unsigned)nsmall << 16) | (six >> 5 << 20) | sidx_bits,
                                                                     (unsigned)(i0 - i_first));
                 const int src = ngroups - 1;
                 i = __shfl_sync(0xffffffffu, i0 + 1 + nsmall, src);
@@ -258,90 +287,100 @@ __global__ void __launch_bounds__(XTC_WARPS * 32, 6) k_xtc_decode(XtcArgs A) {
                 smallidx = min(max(smallidx + (st >> 8) - 1, 0), 127);     // (kept sane for the arithmetic; decoders reject < 9 or > 72)
                 nq += ngroups;
             }
-            if (lane == 0) {
-                S.pos = (unsigned long long)(wbase_bits + (long long)prel0);
-                S.i = i;
-                S.nq = nq;
-                S.i_first = i_first;
-                if (bad) S.bad = 1;
-            }
+            pos0 = (unsigned long long)(wbase_bits + (long long)prel0);
+            if (lane == 0) { W.wbase_bits = wbase_bits; W.nq = nq; W.i_first = i_first; W.i_end = i; }
+            xtc_bar_arrive(XTC_BAR_FULL, wi & 1);
         }
-        __syncthreads();
-        if (S.bad) break;
-        // ---- decode: 32 queued groups per warp and pass ---------------------------------------------------------------
-        const int nq = S.nq, i_end = S.i;
-        float* stage = S.stage[warp];
-        for (int g0 = 32 * warp; g0 < nq; g0 += 32 * XTC_WARPS) {
-            const int g = g0 + lane;
-            const int a_first = (int)S.queue[g0].y;                                               // first atom of this pass
-            const int a_end = g0 + 32 < nq ? (int)S.queue[g0 + 32].y : i_end - i_first;          // first atom of the next
-            const int a_lim = min(a_end, a_first + XTC_STAGE_ATOMS);    // (a_end - a_first > 288 only for malformed streams)
-            if (g < nq) {
-                const uint2 d = S.queue[g];
-                const unsigned prel = d.x & 0xffffu;
-                const int arel = (int)d.y, nsmall = (int)((d.x >> 16) & 15u), flag = (int)((d.x >> 20) & 1u);
-                const int sidx = (int)(d.x >> 21);
-                const long long gend = wbase_bits + (long long)prel + bitsize + 1 + 5 * flag + (long long)nsmall * sidx;
-                if (nsmall > 8 || sidx < 9 || sidx > 72 || arel + 1 + nsmall > a_lim || i_first + arel + 1 + nsmall > natoms ||
-                    gend > (long long)nbits_total) {
-                    S.bad = 1;                                            // malformed stream (benign race: every writer writes 1)
-                } else {
-                    int big[3];
-                    if (wide) {
-                        unsigned pp = prel;
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) { big[k] = (int)xtc_bits(S.win, pp, wb[k]); pp += wb[k]; }
+    } else {
+        // ---- decoders: 32 queued groups per warp and pass -------------------------------------------------------------------
+        XtcDiv dy{size[1], 0, 0}, dz{size[2], 0, 0};
+        if (!wide) {
+            if (size[1] > 1u) xtc_make_div(size[1], dy.mul, dy.shift);
+            if (size[2] > 1u) xtc_make_div(size[2], dz.mul, dz.shift);
+        }
+        const float inv = (float)(1.0 / (double)precision);
+        const float scale = A.scale;
+        float* stage = S.stage[warp - 1];
+        for (int wi = 0;; ++wi) {
+            XtcWindow& W = S.w[wi & 1];
+            xtc_bar_sync(XTC_BAR_FULL, wi & 1);
+            const int nq = W.nq;
+            if (nq < 0) break;
+            const int i_first = W.i_first, i_end = W.i_end;
+            const long long wbase_bits = W.wbase_bits;
+            for (int g0 = 32 * (warp - 1); g0 < nq; g0 += 32 * (XTC_WARPS - 1)) {
+                const int g = g0 + lane;
+                const int a_first = (int)W.queue[g0].y;                                               // first atom of this pass
+                const int a_end = g0 + 32 < nq ? (int)W.queue[g0 + 32].y : i_end - i_first;          // first atom of the next
+                const int a_lim = min(a_end, a_first + XTC_STAGE_ATOMS);    // (a_end - a_first > 288 only for malformed streams)
+                if (g < nq) {
+                    const uint2 d = W.queue[g];
+                    const unsigned prel = d.x & 0xffffu;
+                    const int arel = (int)d.y, nsmall = (int)((d.x >> 16) & 15u), flag = (int)((d.x >> 20) & 1u);
+                    const int sidx = (int)(d.x >> 21);
+                    const long long gend = wbase_bits + (long long)prel + bitsize + 1 + 5 * flag + (long long)nsmall * sidx;
+                    if (nsmall > 8 || sidx < 9 || sidx > 72 || arel < a_first || arel + 1 + nsmall > a_lim ||
+                        i_first + arel + 1 + nsmall > natoms || gend > (long long)nbits_total) {
+                        S.bad = 1;                                            // malformed stream (benign race: every writer writes 1)
                     } else {
-                        xtc_triple(S.win, prel, bitsize, dy, dz, big);
-                    }
+                        int big[3];
+                        if (wide) {
+                            unsigned pp = prel;
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) big[k] += lo[k];
-                    float* o = stage + (size_t)(arel - a_first) * 3;
-                    auto emit = [&](float* dst, const int* v) {
-#pragma unroll
-                        for (int k = 0; k < 3; ++k) dst[k] = __fmul_rn(__fmul_rn(__int2float_rn(v[k]), inv), scale);
-                    };
-                    if (nsmall == 0) {
-                        emit(o, big);
-                    } else {
-                        const XtcDiv ds{(unsigned)c_xtc_magic[sidx], c_xtc_mul[sidx], c_xtc_shift[sidx]};
-                        const int smallnum = c_xtc_magic[sidx] / 2;
-                        const unsigned q = prel + bitsize + 1 + (flag ? 5 : 0);
-                        int prev[3] = {big[0], big[1], big[2]};
-                        for (int t = 0; t < nsmall; ++t) {
-                            int sm[3];
-                            xtc_triple(S.win, q + (unsigned)(t * sidx), sidx, ds, ds, sm);
-#pragma unroll
-                            for (int k = 0; k < 3; ++k) { sm[k] += prev[k] - smallnum; prev[k] = sm[k]; }
-                            // stream order L, S1, S2, ... is atom order S1, L, S2, ... (the first two were swapped)
-                            emit(o + 3 * (t == 0 ? 0 : t + 1), sm);
+                            for (int k = 0; k < 3; ++k) { big[k] = (int)xtc_bits(W.win, pp, wb[k]); pp += wb[k]; }
+                        } else {
+                            xtc_triple(W.win, prel, bitsize, dy, dz, big);
                         }
-                        emit(o + 3, big);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) big[k] += lo[k];
+                        float* o = stage + (size_t)(arel - a_first) * 3;
+                        auto emit = [&](float* dst, const int* v) {
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) dst[k] = __fmul_rn(__fmul_rn(__int2float_rn(v[k]), inv), scale);
+                        };
+                        if (nsmall == 0) {
+                            emit(o, big);
+                        } else {
+                            const XtcDiv ds{(unsigned)c_xtc_magic[sidx], c_xtc_mul[sidx], c_xtc_shift[sidx]};
+                            const int smallnum = c_xtc_magic[sidx] / 2;
+                            const unsigned q = prel + bitsize + 1 + (flag ? 5 : 0);
+                            int prev[3] = {big[0], big[1], big[2]};
+                            for (int t = 0; t < nsmall; ++t) {
+                                int sm[3];
+                                xtc_triple(W.win, q + (unsigned)(t * sidx), sidx, ds, ds, sm);
+#pragma unroll
+                                for (int k = 0; k < 3; ++k) { sm[k] += prev[k] - smallnum; prev[k] = sm[k]; }
+                                // stream order L, S1, S2, ... is atom order S1, L, S2, ... (the first two were swapped)
+                                emit(o + 3 * (t == 0 ? 0 : t + 1), sm);
+                            }
+                            emit(o + 3, big);
+                        }
                     }
                 }
-            }
-            __syncwarp();
-            // write the atoms of this pass: whole pass inside one wanted range (or no ranges) -> plain row copy
-            const int abase = i_first + a_first, npass = a_lim - a_first;
-            int mode = n_ranges == 0 ? 1 : 0;                           // 1: all, 0: none, 2: mixed
-            for (int k = 0; k < n_ranges; ++k) {
-                if (abase >= S.rb[k] && abase + npass <= S.re[k]) mode = 1;
-                else if (abase < S.re[k] && abase + npass > S.rb[k] && mode == 0) mode = 2;
-            }
-            if (mode == 1) {
-                for (int k = lane; k < npass * 3; k += 32) out[(size_t)abase * 3 + k] = stage[k];
-            } else if (mode == 2) {
-                for (int k = lane; k < npass * 3; k += 32) {
-                    const int atom = abase + k / 3;
-                    bool w = false;
-                    for (int r = 0; r < n_ranges; ++r) w = w || (atom >= S.rb[r] && atom < S.re[r]);
-                    if (w) out[(size_t)abase * 3 + k] = stage[k];
+                __syncwarp();
+                // write the atoms of this pass: whole pass inside one wanted range (or no ranges) -> plain row copy
+                const int abase = i_first + a_first, npass = max(a_lim - a_first, 0);
+                int mode = n_ranges == 0 ? 1 : 0;                           // 1: all, 0: none, 2: mixed
+                for (int k = 0; k < n_ranges; ++k) {
+                    if (abase >= S.rb[k] && abase + npass <= S.re[k]) mode = 1;
+                    else if (abase < S.re[k] && abase + npass > S.rb[k] && mode == 0) mode = 2;
                 }
+                if (mode == 1) {
+                    for (int k = lane; k < npass * 3; k += 32) out[(size_t)abase * 3 + k] = stage[k];
+                } else if (mode == 2) {
+                    for (int k = lane; k < npass * 3; k += 32) {
+                        const int atom = abase + k / 3;
+                        bool w = false;
+                        for (int r = 0; r < n_ranges; ++r) w = w || (atom >= S.rb[r] && atom < S.re[r]);
+                        if (w) out[(size_t)abase * 3 + k] = stage[k];
+                    }
+                }
+                __syncwarp();
             }
-            __syncwarp();
+            xtc_bar_arrive(XTC_BAR_EMPTY, wi & 1);
         }
-        __syncthreads();                                 // the window and the queue are rewritten next
     }
+    __syncthreads();
     if (S.bad) fail();
 }
 
