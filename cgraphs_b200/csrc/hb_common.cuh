@@ -5,6 +5,22 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+// Debug build (-DHB_DEBUG, cgraphs_b200/build.py --debug -> libhbgpu_debug.so): bounds checks on the indices that go into
+// shared-memory and global scratch arrays. A violated check prints where it happened and traps the kernel (the host
+// then fails with the CUDA error) - the stand-in for compute-sanitizer, which is closed on this GPU pool.
+#ifdef HB_DEBUG
+#include <cstdio>
+#define HB_DASSERT(cond)                                                                                              \
+    do {                                                                                                                 \
+        if (!(cond)) {                                                                                                   \
+            printf("HB_DASSERT failed: %s  (%s:%d, block %d thread %d)\n", #cond, __FILE__, __LINE__, (int)blockIdx.x, (int)threadIdx.x); \
+            __trap();                                                                                                    \
+        }                                                                                                                \
+    } while (0)
+#else
+#define HB_DASSERT(cond) do { } while (0)
+#endif
+
 namespace {
 
 
@@ -433,6 +449,7 @@ __device__ __forceinline__ void record_bond(const BondTable& bt, unsigned long l
             if (cur == EMPTY_KEY) { atomicAdd(bt.n_keys, 1); cur = key; }
         }
         if (cur == key) {
+            HB_DASSERT(frame >= 0 && (frame >> 5) < bt.wpr && h <= bt.mask);
             atomicOr(&bt.bits[(size_t)h * bt.wpr + (frame >> 5)], 1u << (frame & 31));
             return;
         }
@@ -520,6 +537,7 @@ __device__ __noinline__ void emit_bond(const int4* ent_pack, const int* ent_grou
         ++*nhit;
         const EdgeSink sk = *bt.sink;
         const int b = (int)(frame - sk.edge_frame0);
+        HB_DASSERT(b >= 0);
         const int i = atomicAdd(&sk.edge_cnt[b], 1);
         if (i < sk.edge_cap) sk.edges[(size_t)b * sk.edge_cap + i] = make_int2(e0, e1);
         else atomicExch(sk.wire_overflow, 1);

@@ -156,7 +156,11 @@ __device__ void block_cell_sort(const FrameGrid& g, unsigned short* cells, float
     block_scan_cells(cells, g.ncell, sh);
     for (int i = threadIdx.x; i < n; i += FUSED_CONSUMERS) {
         float4 p = src(i);
-        dst[cell_add(words, cell_of<PBC>(g, p.x, p.y, p.z))] = p;
+        const int c = cell_of<PBC>(g, p.x, p.y, p.z);
+        HB_DASSERT(c >= 0 && c < g.ncell);
+        const unsigned at = cell_add(words, c);
+        HB_DASSERT((int)at < n);
+        dst[at] = p;
     }
     consumer_sync();
 }
@@ -170,6 +174,7 @@ __device__ __forceinline__ void collect_pairs(const RunParams& rp, const FrameGr
         const float4 q4 = pts[q];
         if (!within<PBC>(p.x, p.y, p.z, q4.x, q4.y, q4.z, rp.r2f_hi, rp.r2, g.p)) return;
         const int k = atomicAdd(n_pairs, 1);
+        HB_DASSERT(i >= 0 && i < 65536 && q > i && q < 65536);
         if (k < pair_cap) pairs[k] = (unsigned)i | ((unsigned)q << 16);
     });
 }
@@ -397,6 +402,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
             float x = 0.f, y = 0.f, z = 0.f;
             if (stream) {
                 if (!mbar_wait(&full[st], parity, fc.wait_ns)) { sh->overflow = 2; break; }
+                HB_DASSERT(st >= 0 && st < fc.stages && my_off + 12u <= fc.stage_bytes);
                 const float* f = reinterpret_cast<const float*>(ring + (size_t)st * fc.stage_bytes + my_off);
                 x = f[0]; y = f[1]; z = f[2];             // (always inside the stage; meaningful if the bytes were copied)
                 const unsigned partial = sh->stage_head[st];
@@ -434,6 +440,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
                 base = __shfl_sync(0xffffffffu, base, 0);
                 if (is_cand) {
                     const int pos = base + __popc(m & ((1u << lane) - 1u));
+                    HB_DASSERT(pos >= 0 && i >= 0 && i < nwp);
                     if (pos < fc.cand_cap) clist[pos] = (unsigned)i;
                     else sh->overflow = 1;
                 }
@@ -449,6 +456,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
             float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
             if (j < ncand) {
                 const int i = (int)clist[j];
+                HB_DASSERT(i >= 0 && i < nwp);
                 const float* f = xyz + 3ll * tp.wat_atom[w0 + i];     // (just streamed: an L2 hit)
                 c = make_float4(f[0], f[1], f[2], __int_as_float(WATER_TAG | i));
                 local = water_is_local<PBC>(g1, cells, sorted1, c.x, c.y, c.z, rp);
@@ -543,6 +551,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
                                     const int d = (int)(signed char)((unsigned)lists[f] >> (8 * j));
+                                    HB_DASSERT(d == -128 || slot < fc.task_cap);
                                     if (d != -128) tasks[slot++] = make_uint2((unsigned)tid | ((unsigned)f << 16), (unsigned)(atoms[f] + d));
                                 }
                             }
@@ -564,6 +573,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
         for (int t = tid; t < ntasks; t += FUSED_CONSUMERS) {
             const uint2 tk = tasks[t];
             const unsigned kk = tk.x & 0xffffu, f = tk.x >> 16;
+            HB_DASSERT(kk < FUSED_CONSUMERS && f < 4u && (int)(base + kk) < npairs);
             const unsigned pq = pairs[base + kk];
             const float4 a4 = psorted[pq & 0xffffu], b4 = psorted[pq >> 16];
             const float4 own = (f & 1u) ? b4 : a4, oth = (f & 1u) ? a4 : b4;

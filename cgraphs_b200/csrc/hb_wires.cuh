@@ -179,6 +179,7 @@ __global__ void __launch_bounds__(WIRE_THREADS) k_wire_bfs(BondTable bt, WireCfg
             if (e4[u].x < 0) continue;
             const int2 e = e4[u];
             const int n0 = n04[u], n1 = n14[u];
+            HB_DASSERT(n0 >= 0 && n1 >= 0 && n0 < n_res + wc.n_wat && n1 < n_res + wc.n_wat);
             if (n0 >= n_res && atomicCAS(&wl_of[n0 - n_res], -1, -2) == -1) lw[atomicAdd(&s_nlw, 1)] = n0 - n_res;
             if (n1 >= n_res && atomicCAS(&wl_of[n1 - n_res], -1, -2) == -1) lw[atomicAdd(&s_nlw, 1)] = n1 - n_res;
             if ((n0 >= n_res) != (n1 >= n_res)) {

@@ -26,6 +26,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include "hb_common.cuh"
 
 namespace {
 
@@ -277,6 +278,7 @@ __global__ void __launch_bounds__(XTC_WARPS * 32, 6) k_xtc_decode(XtcArgs A) {
                 const int nsmall = flag ? fs : nsm;
                 const int change = flag ? r5 - 3 * fs : 1;                   // smallidx change + 1
                 const int pnext = prel + bitsize + 1 + 5 * flag + nsmall * smallidx;
+                HB_DASSERT(nq + ngroups <= XTC_QCAP && prel >= 0 && (lane >= ngroups || prel + bitsize + 6 <= 8 * XTC_WIN_BYTES + 128));
                 if (lane < ngroups) W.queue[nq + lane] = make_uint2((unsigned)prel | ((unsigned)nsmall << 16) | (six >> 5 << 20) | sidx_bits,
                                                                     (unsigned)(i0 - i_first));
                 const int src = ngroups - 1;
@@ -333,6 +335,7 @@ __global__ void __launch_bounds__(XTC_WARPS * 32, 6) k_xtc_decode(XtcArgs A) {
                         }
 #pragma unroll
                         for (int k = 0; k < 3; ++k) big[k] += lo[k];
+                        HB_DASSERT(arel - a_first >= 0 && arel - a_first + 1 + nsmall <= XTC_STAGE_ATOMS && prel + bitsize <= 8u * XTC_WIN_BYTES + 128u);
                         float* o = stage + (size_t)(arel - a_first) * 3;
                         auto emit = [&](float* dst, const int* v) {
 #pragma unroll

@@ -22,6 +22,7 @@
 #include "../../include/hbgpu.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -171,6 +172,11 @@ struct hb_ctx {
     long long n_sel_total = 0, n_wat_total = 0;
     IonTable ions{nullptr, nullptr, 0};
     unsigned long long* merge_table = nullptr;    // hash set of hb_merge_keys_device (many ranks)
+    void* nccl_comm = nullptr;                    // hb_comm_init: communicator of the key exchange (ncclComm_t)
+    int comm_world = 0, comm_rank = 0;
+    unsigned long long* comm_send = nullptr;      // [cap + 1] this rank's block
+    unsigned long long* comm_recv = nullptr;      // [world][cap + 1]
+    int comm_cap = 0;
     // water wires (hb_wires.cuh)
     struct Wire {
         bool on = false;
@@ -312,6 +318,40 @@ static void parallel_frames(int nf, size_t bytes_per_frame, int max_threads, F c
     for (auto& x : th) x.join();
 }
 
+// ---- NCCL, loaded at run time (the library links against nothing but the CUDA runtime) ---------------------------
+struct HbNcclId { char internal[128]; };
+struct HbNccl {
+    void* handle = nullptr;
+    int (*GetUniqueId)(HbNcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, HbNcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+static HbNccl& hb_nccl() {
+    static HbNccl n;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = {getenv("HBGPU_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) {
+            if (!nm || !*nm) continue;
+            n.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+            if (n.handle) break;
+        }
+        if (n.handle) {
+            n.GetUniqueId = (int (*)(HbNcclId*))dlsym(n.handle, "ncclGetUniqueId");
+            n.CommInitRank = (int (*)(void**, int, HbNcclId, int))dlsym(n.handle, "ncclCommInitRank");
+            n.CommDestroy = (int (*)(void*))dlsym(n.handle, "ncclCommDestroy");
+            n.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(n.handle, "ncclAllGather");
+            n.GetErrorString = (const char* (*)(int))dlsym(n.handle, "ncclGetErrorString");
+            n.ok = n.GetUniqueId && n.CommInitRank && n.CommDestroy && n.AllGather;
+        }
+    }
+    return n;
+}
+
 // Trajectory mode: atom ranges [begin, end) that cover every atom marked in ctx->atom_used; holes shorter than 4096
 // atoms (48 kB) are copied along. Left empty (= copy whole frames) when the ranges would not save at least 10 %.
 static void build_copy_ranges(hb_ctx* ctx) {
@@ -445,6 +485,9 @@ int hb_destroy(hb_ctx* ctx) {
     cudaEventDestroy(ctx->ev_run0);
     cudaEventDestroy(ctx->ev_run1);
     if (ctx->merge_table) cudaFree(ctx->merge_table);
+    if (ctx->nccl_comm) { hb_nccl().CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+    if (ctx->comm_send) cudaFree(ctx->comm_send);
+    if (ctx->comm_recv) cudaFree(ctx->comm_recv);
     for (int k = 0; k < 2; ++k) { if (ctx->d_xoff[k]) cudaFree(ctx->d_xoff[k]); if (ctx->h_xoff[k]) cudaFreeHost(ctx->h_xoff[k]); }
     if (ctx->d_xtc_status) cudaFree(ctx->d_xtc_status);
     if (ctx->h_xtc_status) cudaFreeHost(ctx->h_xtc_status);
@@ -2130,6 +2173,69 @@ int hb_merge_keys_device(hb_ctx* ctx, const uint64_t* d_gathered, int32_t world,
     CK(cudaGetLastError());
     ctx->tm.n_launches += 1;
     return HB_OK;
+}
+
+// ---- multi-GPU key exchange inside the C ABI: one NCCL all-gather of the distinct bond keys ------------------
+int hb_comm_unique_id(void* id128) {
+    if (!id128) return HB_ERR_ARG;
+    HbNccl& n = hb_nccl();
+    if (!n.ok) { g_create_error = "libnccl.so.2 not found (set HBGPU_NCCL_LIB)"; return HB_ERR_STATE; }
+    HbNcclId id;
+    if (n.GetUniqueId(&id) != 0) { g_create_error = "ncclGetUniqueId failed"; return HB_ERR_CUDA; }
+    memcpy(id128, &id, sizeof(id));
+    return HB_OK;
+}
+
+int hb_comm_destroy(hb_ctx* ctx) {
+    if (!ctx) return HB_ERR_ARG;
+    cudaSetDevice(ctx->device);
+    if (ctx->nccl_comm) { cudaStreamSynchronize(ctx->s_compute); hb_nccl().CommDestroy(ctx->nccl_comm); ctx->nccl_comm = nullptr; }
+    if (ctx->comm_send) cudaFree(ctx->comm_send);
+    if (ctx->comm_recv) cudaFree(ctx->comm_recv);
+    ctx->comm_send = ctx->comm_recv = nullptr;
+    ctx->comm_cap = ctx->comm_world = 0;
+    return HB_OK;
+}
+
+int hb_comm_init(hb_ctx* ctx, const void* id128, int32_t world, int32_t rank) {
+    if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return HB_ERR_ARG;
+    HbNccl& n = hb_nccl();
+    if (!n.ok) return fail(ctx, HB_ERR_STATE, "hb_comm_init: libnccl.so.2 not found (set HBGPU_NCCL_LIB)");
+    hb_comm_destroy(ctx);
+    CK(cudaSetDevice(ctx->device));
+    HbNcclId id;
+    memcpy(&id, id128, sizeof(id));
+    const int rc = n.CommInitRank(&ctx->nccl_comm, world, id, rank);
+    if (rc != 0) {
+        ctx->nccl_comm = nullptr;
+        return fail(ctx, HB_ERR_CUDA, std::string("ncclCommInitRank: ") + (n.GetErrorString ? n.GetErrorString(rc) : "failed"));
+    }
+    ctx->comm_world = world;
+    ctx->comm_rank = rank;
+    return HB_OK;
+}
+
+int hb_exchange_keys(hb_ctx* ctx, int32_t cap, uint64_t* d_out, int64_t* d_info) {
+    if (!ctx || cap < 1 || !d_out || !d_info) return HB_ERR_ARG;
+    if (!ctx->nccl_comm) return fail(ctx, HB_ERR_STATE, "hb_exchange_keys before hb_comm_init");
+    if (!ctx->fin_queued && !ctx->finalized) return fail(ctx, HB_ERR_STATE, "hb_exchange_keys before hb_finalize_async / hb_finalize");
+    if ((long long)ctx->comm_world * cap > 16384) return fail(ctx, HB_ERR_ARG, "hb_exchange_keys: world * cap must not exceed 16384");
+    CK(cudaSetDevice(ctx->device));
+    if (cap != ctx->comm_cap) {
+        CK(cudaStreamSynchronize(ctx->s_compute));
+        if (ctx->comm_send) cudaFree(ctx->comm_send);
+        if (ctx->comm_recv) cudaFree(ctx->comm_recv);
+        ctx->comm_send = ctx->comm_recv = nullptr;
+        ctx->comm_cap = 0;
+        CK(cudaMalloc((void**)&ctx->comm_send, ((size_t)cap + 1) * 8));
+        CK(cudaMalloc((void**)&ctx->comm_recv, (size_t)ctx->comm_world * ((size_t)cap + 1) * 8));
+        ctx->comm_cap = cap;
+    }
+    int rc = hb_pack_keys_device(ctx, (uint64_t*)ctx->comm_send, cap);
+    if (rc) return rc;
+    const int nrc = hb_nccl().AllGather(ctx->comm_send, ctx->comm_recv, (size_t)cap + 1, 4 /* ncclInt64 */, ctx->nccl_comm, ctx->s_compute);
+    if (nrc != 0) return fail(ctx, HB_ERR_CUDA, std::string("ncclAllGather: ") + (hb_nccl().GetErrorString ? hb_nccl().GetErrorString(nrc) : "failed"));
+    return hb_merge_keys_device(ctx, (const uint64_t*)ctx->comm_recv, ctx->comm_world, cap, d_out, d_info);
 }
 
 int hb_get_counts(hb_ctx* ctx, int64_t* counts) {

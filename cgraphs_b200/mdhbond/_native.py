@@ -107,6 +107,10 @@ SYMBOLS = [
     ("hb_get_keys_device", C.c_int, [_P, _P]),
     ("hb_get_bits_device", C.c_int, [_P, _P]),
     ("hb_merge_keys_device", C.c_int, [_P, _P, C.c_int32, C.c_int32, _P, _P]),
+    ("hb_comm_unique_id", C.c_int, [_P]),
+    ("hb_comm_init", C.c_int, [_P, _P, C.c_int32, C.c_int32]),
+    ("hb_exchange_keys", C.c_int, [_P, C.c_int32, _P, _P]),
+    ("hb_comm_destroy", C.c_int, [_P]),
     ("hb_get_counts", C.c_int, [_P, _P]),
     ("hb_joint_occupancy", C.c_int, [_P, _P, _P, C.POINTER(C.c_int64)]),
     ("hb_get_frame_column", C.c_int, [_P, C.c_int64, _P]),
@@ -338,6 +342,14 @@ class Context:
         self._ck(self.lib.hb_merge_keys_device(self.h, int(gathered_ptr), int(world), int(cap), int(out_ptr), int(info_ptr)),
                  "hb_merge_keys_device")
 
+    def comm_init(self, unique_id, world, rank):
+        """hb_comm_init: join the NCCL communicator of the key exchange (unique_id: the 128 bytes of comm_unique_id())."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._ck(self.lib.hb_comm_init(self.h, buf, int(world), int(rank)), "hb_comm_init")
+
+    def exchange_keys(self, cap, out_ptr, info_ptr):
+        self._ck(self.lib.hb_exchange_keys(self.h, int(cap), int(out_ptr), int(info_ptr)), "hb_exchange_keys")
+
     def counts(self, n_bonds):
         c = np.zeros(n_bonds, dtype=np.int64)
         if n_bonds:
@@ -464,3 +476,12 @@ def xtc_decode_device(buf, offsets, n_atoms, scale=10.0, device=0):
     finally:
         ctx.close()
     return out.cpu().numpy()
+
+
+def comm_unique_id():
+    """128-byte NCCL id (hb_comm_unique_id) that rank 0 creates and every rank passes to Context.comm_init."""
+    lib = load_library()
+    buf = (C.c_char * 128)()
+    if lib.hb_comm_unique_id(buf) != 0:
+        raise HbError("hb_comm_unique_id failed: " + (lib.hb_last_error(None) or b"").decode())
+    return bytes(buf)

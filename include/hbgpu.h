@@ -30,8 +30,9 @@
  *   hb_get_counts / hb_joint_occupancy / hb_get_frame_column
  *                     <- filter_occupancy, compute_joint_occupancy, _compute_graph_in_frame,
  *                        network.py:99-107, 369-376, 1186-1198 (on the packed matrix)
- *   hb_finalize_async / hb_pack_keys_device / hb_merge_keys_device
- *                     <- no counterpart: the multi-GPU key exchange (frames sharded over ranks)
+ *   hb_finalize_async / hb_pack_keys_device / hb_merge_keys_device, hb_comm_init / hb_exchange_keys
+ *                     <- no counterpart: the multi-GPU key exchange (frames sharded over ranks), with the caller's
+ *                        collective or with the library's own NCCL all-gather
  *
  * Conventions: every function returns 0 on success or a negative hb_status; no C++ exception crosses the
  * ABI; the message of the last failure is available from hb_last_error().  The caller owns every host
@@ -268,6 +269,21 @@ int hb_pack_keys_device(hb_ctx* ctx, uint64_t* d_block, int32_t cap);
  * and {n_out, overflow flag} to d_info. world*cap <= 16384. Queued on the compute stream, no host round trip. */
 int hb_merge_keys_device(hb_ctx* ctx, const uint64_t* d_gathered, int32_t world, int32_t cap, uint64_t* d_out,
                          int64_t* d_info);
+/* The same exchange without Python: the library loads NCCL at run time (libnccl.so.2, or $HBGPU_NCCL_LIB) and runs the
+ * one collective of the path itself, so that any host language can drive several GPUs (one process or thread per GPU,
+ * one context each).
+ *   hb_comm_unique_id : rank 0 creates the 128-byte NCCL id; the caller hands it to every rank (file, socket, MPI ...)
+ *   hb_comm_init      : ncclCommInitRank on the context's device; collective over all ranks
+ *   hb_exchange_keys  : after hb_finalize_async (or hb_finalize): pack this rank's distinct keys, ONE ncclAllGather of
+ *                       (cap + 1) 64-bit words per rank, merge - all queued on the compute stream, nothing waits on the
+ *                       host. d_out (device, world * cap words) receives the global sorted distinct keys, d_info
+ *                       (device, 2 words) {n_keys, overflow}: overflow != 0 means some rank had more than cap keys -
+ *                       repeat with a larger cap. world * cap <= 16384. Global bond id = rank of a key in d_out.
+ *   hb_comm_destroy   : frees the communicator (hb_destroy does it too). */
+int hb_comm_unique_id(void* id128);
+int hb_comm_init(hb_ctx* ctx, const void* id128, int32_t world, int32_t rank);
+int hb_exchange_keys(hb_ctx* ctx, int32_t cap, uint64_t* d_out, int64_t* d_info);
+int hb_comm_destroy(hb_ctx* ctx);
 /* Per-bond popcount over frames (occupancy numerator; network.py:99-107 filter_occupancy). */
 int hb_get_counts(hb_ctx* ctx, int64_t* counts);
 /* AND of the occupancy rows with select[i] != 0 (NULL: all rows): words = uint32 [words_per_bond] (host),
