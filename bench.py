@@ -401,6 +401,75 @@ def wires_leg(args, system, d_xyz, local_rank, peak, bytes_frame):
     return out
 
 
+def c4_leg(args, local_rank, peak):
+    """BASELINE config C4 (1M atoms; the selection is too large for the one-CTA-per-frame kernel, so the general kernels
+    run): a block of frames resident in HBM, device-timed like the headline; parity gate on its first frames."""
+    import torch
+    from cgraphs_b200 import synth
+    from cgraphs_b200.mdhbond import HbondAnalysis, _native
+    from cgraphs_b200.mdhbond.calib import cos_threshold
+    from cgraphs_b200.mdhbond.topology import pack_systems
+    system, cfg = synth.config("C4", scale=args.scale)
+    nf, na = args.c4_frames, system.n_atoms
+    dev = torch.device("cuda", local_rank)
+    d_xyz = torch.empty((nf, na, 3), dtype=torch.float32, device=dev)
+    system.frames_torch(0, nf, dev, out=d_xyz)
+    torch.cuda.synchronize()
+    hba = HbondAnalysis(SELECTION, system.universe(1), check_angle=True, device=local_rank)
+    top = hba._topology
+    tables, group_names = pack_systems([top], [top.key_ids("water_around")], [na])
+    ctx = hba._context()
+    ctx.set_topology(tables)
+    ctx.set_params(3.5, AROUND, cos_threshold(60.0), True, True, _native.METHOD_WATER_AROUND)
+    ctx.set_option("profile", 1)
+    ctx.set_option("max_batch_frames", nf)
+    ms, search, kernels, launches, nb = [], [], {}, 0, 0
+    for it in range(3 + 5):
+        ctx.begin(nf)
+        ctx.submit_device(d_xyz.data_ptr(), na, nf)
+        nb, _ = ctx.finalize()
+        torch.cuda.synchronize()
+        tm = ctx.timers()
+        if it >= 3:
+            ms.append(tm["ms_run"])
+            search.append(tm["ms_total"])
+            launches = int(tm["n_launches"])
+            for k, v in tm["ms_kernel"].items():
+                if v:
+                    kernels[k] = kernels.get(k, 0.0) + v / 5
+    ctx.begin(nf)
+    ctx.submit_device(d_xyz.data_ptr(), na, nf)
+    keys, words = ctx.results()
+    bytes_frame, n_part = algorithmic_bytes(top, nb)
+    ms_pass, ms_search = float(np.mean(ms)), float(np.mean(search))
+    out = {"workload": "C4: %d-atom system, %d frames resident in HBM, selection 'protein' (%d selection points), "
+                       "set_hbonds_in_selection_and_water_around(3.5), 3.5 A + 60 deg" % (na, nf, len(top.sel_atom)),
+           "metric": "hbond_frames_per_s", "value": nf / (ms_pass * 1e-3), "unit": "frames/s", "ms_per_pass": ms_pass,
+           "atom_frames_per_s": nf * na / (ms_pass * 1e-3), "n_bonds": int(nb), "launches_per_pass": launches,
+           "kernel_ms_per_pass": {k: round(v, 3) for k, v in kernels.items()},
+           "roofline": {"bound": "hbm", "algorithmic_bytes_per_frame": bytes_frame, "peak": peak, "unit": "GB/s",
+                        "achieved_search_kernels": bytes_frame * nf / (ms_search * 1e-3) / 1e9,
+                        "frac_search_kernels": bytes_frame * nf / (ms_search * 1e-3) / 1e9 / peak,
+                        "achieved_whole_pass": bytes_frame * nf / (ms_pass * 1e-3) / 1e9,
+                        "frac_whole_pass": bytes_frame * nf / (ms_pass * 1e-3) / 1e9 / peak}}
+    if not args.no_cpu:
+        n_cpu = 2
+        sample = d_xyz[:n_cpu].cpu().numpy()
+        from oracle import hbond_port
+        pt = cpu_port_topology(system, cfg, sample)
+        t0 = time.perf_counter()
+        cpu_res = hbond_port.run_block(pt, sample, "water_around", AROUND, nb_frames=n_cpu)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n_cpu / dt, "unit": "frames/s", "cores": 1, "kind": "port",
+                               "sample": "first %d frames (%.1f s), oracle/hbond_port.py" % (n_cpu, dt)}
+        out["parity"] = parity_object(results_of(keys, words, group_names, n_cpu), cpu_res, n_cpu,
+                                      "oracle/hbond_port.py on the first frames of the C4 block")
+    hba.close()
+    del d_xyz
+    torch.cuda.empty_cache()
+    return out
+
+
 def workload_config(system, cfg, args, world):
     nf_total = args.frames if args.scaling == "strong" else args.frames * world
     return {"workload": "C3: %d-atom membrane-protein-like system x %d frames %s, triclinic box, "
@@ -743,12 +812,18 @@ def run_ours(args):
             line["wires"] = wires_leg(args, system, d_xyz, local_rank, peak, bytes_frame)
         except Exception as e:                          # the secondary leg never takes the headline down
             line["wires"] = {"error": repr(e)[:300]}
+    if world == 1 and args.c4_frames > 0:
+        try:
+            line["c4"] = c4_leg(args, local_rank, peak)
+        except Exception as e:
+            line["c4"] = {"error": repr(e)[:300]}
     if per_rank is not None:
         line["per_rank"] = {"columns": ["pass ms", "frame_fused kernel ms", "e2e_f32 H2D GB/s", "e2e_xtc H2D GB/s"], "ranks": per_rank}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
-    bad = [n for n, p_ in (("parity", parity), ("parity_xtc", parity_xtc), ("wires.parity", (line.get("wires") or {}).get("parity")))
+    bad = [n for n, p_ in (("parity", parity), ("parity_xtc", parity_xtc), ("wires.parity", (line.get("wires") or {}).get("parity")),
+                           ("c4.parity", (line.get("c4") or {}).get("parity")))
            if p_ is not None and not p_["equal"]]
     if bad:
         sys.stderr.write("bench: PARITY GATE FAILED: %s\n" % ", ".join(bad))
@@ -772,6 +847,7 @@ def main():
     ap.add_argument("--xtc-batch-bytes", type=int, default=0, help="batch_bytes of the XTC leg (0: the library default)")
     ap.add_argument("--ring-frames", type=int, default=2048, help="distinct frames per rank in pinned host memory when N > 1")
     ap.add_argument("--wire-frames", type=int, default=2048, help="frames of the secondary water-wire leg (0: skip)")
+    ap.add_argument("--c4-frames", type=int, default=592, help="frames of the secondary C4 (1M atoms) leg, N = 1 only (0: skip)")
     ap.add_argument("--native-opt", action="append", default=[], help="name=value passed to hb_set_option (experiments)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-xtc", action="store_true")
