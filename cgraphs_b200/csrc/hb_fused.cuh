@@ -253,9 +253,44 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
                 if (e > a)
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((unsigned)(e - a)) : "memory");
             };
-            for (int t = 0; t < min(fc.prefetch, ntiles); ++t) prefetch_tile(t);
             int st = 0;
             unsigned parity = 1;                        // parity of the "previous round" of the empty barriers
+            // A tile advances by 256 * stride * 12 bytes, a multiple of 16, so every tile of the frame starts at the same
+            // offset `head` inside its 16-byte aligned copy. Frames whose water block lies inside the batch buffer with
+            // its alignment slack (all but the first and last frame of a batch) take the short loop: one thread issues
+            // every tile of the CTA and shares its issue slots with 36 resident warps, so each instruction here delays
+            // the whole ring.
+            const unsigned tile_step = (unsigned)(FUSED_TILE * stride12);
+            const unsigned long long start0 = gbase & ~15ull;
+            const unsigned head = (unsigned)(gbase - start0);
+            const int nw_last = nwp - (ntiles - 1) * FUSED_TILE;
+            const unsigned full_bytes = (head + (unsigned)((FUSED_TILE - 1) * stride12 + 12) + 15u) & ~15u;
+            const unsigned last_bytes = (head + (unsigned)((nw_last - 1) * stride12 + 12) + 15u) & ~15u;
+            const unsigned long long frame_end = start0 + (unsigned long long)(ntiles - 1) * tile_step + last_bytes;
+            if (start0 >= lim_lo && frame_end <= lim_hi) {
+                for (int k = 0; k < fc.stages; ++k) { sh->stage_head[k] = 0u; sh->stage_lo[k] = 0u; sh->stage_hi[k] = fc.stage_bytes; }
+                const int npre = min(fc.prefetch, ntiles);
+                for (int t = 0; t < npre; ++t)
+                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(start0 + (unsigned long long)t * tile_step),
+                                 "r"(t == ntiles - 1 ? last_bytes : tile_step) : "memory");
+                unsigned long long src = start0;
+                unsigned long long pre = start0 + (unsigned long long)npre * tile_step;
+                unsigned char* dst = ring;
+                for (int t = 0; t < ntiles; ++t) {
+                    if (t + npre < ntiles)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pre), "r"(t + npre == ntiles - 1 ? last_bytes : tile_step) : "memory");
+                    pre += tile_step;
+                    if (t >= fc.stages && !mbar_wait(&empty[st], parity, fc.wait_ns)) { sh->overflow = 2; break; }
+                    const unsigned bytes = t == ntiles - 1 ? last_bytes : full_bytes;
+                    mbar_expect_tx(&full[st], bytes);
+                    bulk_g2s(dst, reinterpret_cast<const void*>(src), bytes, &full[st]);
+                    src += tile_step;
+                    dst += fc.stage_bytes;
+                    if (++st == fc.stages) { st = 0; parity ^= 1u; dst = ring; }
+                }
+                return;
+            }
+            for (int t = 0; t < min(fc.prefetch, ntiles); ++t) prefetch_tile(t);
             for (int t = 0; t < ntiles; ++t) {
                 if (t + fc.prefetch < ntiles) prefetch_tile(t + fc.prefetch);
                 if (t >= fc.stages && !mbar_wait(&empty[st], parity, fc.wait_ns)) { sh->overflow = 2; break; }
