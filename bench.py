@@ -40,6 +40,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOAD = "C3"
+_WORKLOAD = [WORKLOAD]       # --workload C4 switches the device-resident legs to BASELINE config C4 (1M atoms; general kernels)
 SELECTION = "protein"
 AROUND = 3.5
 
@@ -125,7 +126,7 @@ def ncu_traffic(kernel):
 
 def build_case(scale, n_frames):
     from cgraphs_b200 import synth
-    system, cfg = synth.config(WORKLOAD, scale=scale)
+    system, cfg = synth.config(_WORKLOAD[0], scale=scale)
     cfg["n_frames"] = n_frames
     return system, cfg
 
@@ -472,9 +473,9 @@ def c4_leg(args, local_rank, peak):
 
 def workload_config(system, cfg, args, world):
     nf_total = args.frames if args.scaling == "strong" else args.frames * world
-    return {"workload": "C3: %d-atom membrane-protein-like system x %d frames %s, triclinic box, "
+    return {"workload": "%s: %d-atom membrane-protein-like system x %d frames %s, triclinic box, "
                         "set_hbonds_in_selection_and_water_around(3.5), 3.5 A + 60 deg, selection 'protein'"
-                        % (system.n_atoms, args.frames, "in total, sharded over the GPUs" if args.scaling == "strong" else "per GPU"),
+                        % (_WORKLOAD[0], system.n_atoms, args.frames, "in total, sharded over the GPUs" if args.scaling == "strong" else "per GPU"),
             "n_atoms": system.n_atoms, "n_frames_per_gpu": args.frames if args.scaling == "weak" else None,
             "n_frames_total": nf_total, "scaling": args.scaling,
             "selection": SELECTION, "method": "water_around",
@@ -538,6 +539,8 @@ def run_ours(args):
         ctx.set_option("batch_bytes", args.batch_bytes)
     for kv in args.native_opt:
         ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
+    if args.workload == "C4":
+        ctx.set_option("max_batch_frames", nf)
     # every kernel of the library and the NCCL exchange run on one torch stream, so a pair of CUDA events on that
     # stream brackets whole passes (search + finalize + key merge)
     stream = torch.cuda.Stream(device=dev)
@@ -582,7 +585,9 @@ def run_ours(args):
     kernel_launches = {}
     ev0.record(stream)
     for _ in range(args.steps):
-        nb, wpr = one_pass_device(sync_merge=False)     # gather capacity learnt during warm-up; no host wait here
+        # gather capacity learnt during warm-up; no host wait here (large bond tables - C4 - finalise synchronously:
+        # their radix sort is sized from the bond count, so the exchange follows the finalisation)
+        nb, wpr = one_pass_device(sync_merge=args.workload == "C4")
         tm = ctx.timers()
         launches += tm["n_launches"]
         retries += tm["finalize_retries"]
@@ -841,6 +846,8 @@ def main():
                     help="weak: --frames per GPU; strong: --frames in total, sharded over the GPUs")
     ap.add_argument("--frames", type=int, default=10000, help="frames per GPU (weak) or in total (strong); BASELINE config: 10000")
     ap.add_argument("--scale", type=float, default=1.0, help="atom-count scale of the workload (1.0 = BASELINE config)")
+    ap.add_argument("--workload", default="C3", choices=["C3", "C4"],
+                    help="C3 = the headline (default); C4 = the 1M-atom config (use with --frames 592 --no-e2e --cpu-frames 2 --c4-frames 0)")
     ap.add_argument("--cpu-frames", type=int, default=1024, help="frames of the CPU baseline / parity gate")
     ap.add_argument("--cpu-frames-xtc", type=int, default=128, help="frames of the XTC leg's parity gate")
     ap.add_argument("--batch-bytes", type=int, default=0)
@@ -858,6 +865,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not os.environ.get("HB_BENCH_ALLOW_SHORT_WARMUP"):
         args.warmup = max(args.warmup, 1)
+    _WORKLOAD[0] = args.workload
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_ours(args)
