@@ -98,12 +98,14 @@ __global__ void __launch_bounds__(32) k_rs_scatter(const unsigned long long* key
 
 // Small results (the common case: a few thousand distinct bonds): one CTA sorts (key, slot) pairs in shared
 // memory with a bitonic network; n <= SORT_SMALL_MAX, padded with the largest key to a power of two.
-#define SORT_SMALL_MAX 4096
+#define SORT_SMALL_MAX 16384                 // 12 bytes of dynamic shared memory per element: 192 kB
+#define SORT_SPECULATE_MAX 4096              // bond tables up to twice this size are finalised without knowing the count
 __global__ void __launch_bounds__(1024) k_sort_small(const unsigned long long* keys_in, const unsigned* vals_in,
-                                                     const int* n_ptr, unsigned long long* keys_out, unsigned* vals_out) {
-    __shared__ unsigned long long k[SORT_SMALL_MAX];
-    __shared__ unsigned v[SORT_SMALL_MAX];
-    const int n = min(*n_ptr, SORT_SMALL_MAX);     // (a larger count is caught by the host and redone with radix passes)
+                                                     const int* n_ptr, unsigned long long* keys_out, unsigned* vals_out, int cap) {
+    extern __shared__ __align__(16) unsigned long long sort_smem[];
+    unsigned long long* k = sort_smem;                                       // [cap]
+    unsigned* v = reinterpret_cast<unsigned*>(sort_smem + cap);            // [cap]
+    const int n = min(*n_ptr, cap);                // (a larger count is caught by the host and redone with radix passes)
     int m = 1;
     while (m < n) m <<= 1;
     for (int i = threadIdx.x; i < m; i += blockDim.x) {

@@ -94,6 +94,7 @@ struct hb_ctx {
     long long opt_fused_prefetch = 2; // tiles prefetched into L2 ahead of the ring (more evicts lines before use)
     int opt_fused_debug = 0;          // measurement hook (results are wrong when set): see FusedCfg::debug
     int fused_grow = 0;
+    int sort_smem_cap = 0;            // dynamic shared memory k_sort_small may use was raised (per context / device)
     int fused_grow_hint = 0;          // capacities that an earlier run on this topology needed ...
     double fused_hint_around = 0.0;   // ... with this around radius (narrower shells start from the defaults)
 
@@ -1970,7 +1971,13 @@ static int queue_finalize(hb_ctx* ctx, bool speculative, int* n_known) {
     unsigned cap = ctx->bt.mask + 1u;
     k_compact<<<(cap + 255) / 256, 256, 0, st>>>(ctx->bt, k0, v0, counter);
     if (speculative || (n > 1 && n <= SORT_SMALL_MAX && !ctx->opt_force_radix)) {
-        k_sort_small<<<1, 1024, 0, st>>>(k0, v0, counter, k1, v1);
+        int cap = SORT_SPECULATE_MAX;                     // power of two >= the number of keys the sort can meet
+        while (cap < (speculative ? (int)std::min<long long>(n_max, SORT_SMALL_MAX) : n)) cap <<= 1;
+        if (cap > ctx->sort_smem_cap) {
+            CK(cudaFuncSetAttribute(k_sort_small, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_SMALL_MAX * 12));
+            ctx->sort_smem_cap = SORT_SMALL_MAX;
+        }
+        k_sort_small<<<1, 1024, (size_t)cap * 12, st>>>(k0, v0, counter, k1, v1, cap);
         std::swap(k0, k1);
         std::swap(v0, v1);
         ctx->tm.n_launches += 3;
@@ -2001,7 +2008,7 @@ static int queue_finalize(hb_ctx* ctx, bool speculative, int* n_known) {
     return HB_OK;
 }
 
-static bool finalize_can_speculate(hb_ctx* ctx) { return ctx->table_cap <= 2ll * SORT_SMALL_MAX && !ctx->opt_force_radix; }
+static bool finalize_can_speculate(hb_ctx* ctx) { return ctx->table_cap <= 2ll * SORT_SPECULATE_MAX && !ctx->opt_force_radix; }
 
 int hb_finalize_async(hb_ctx* ctx) {
     if (!ctx) return HB_ERR_ARG;
