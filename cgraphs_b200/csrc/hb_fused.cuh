@@ -45,10 +45,15 @@ struct FusedCfg {
     int prefetch;             // tiles pulled into L2 ahead of the ring
     unsigned wait_ns;         // sleep between two polls of a barrier
     unsigned stage_bytes;     // bytes of one stage (multiple of 16)
-    unsigned off_union, off_lw, off_cells, off_near, off_cand, off_bar;   // byte offsets in dynamic smem
+    int cand16;               // candidate indices are 16-bit (every system has < 65536 waters)
+    unsigned off_sorted, off_ring, off_lw, off_cells, off_near, off_cand, off_bar;   // byte offsets in dynamic smem
     unsigned smem_bytes;
     unsigned long long buf_begin, buf_end;   // address range of the coordinate batch (bounds for bulk copies)
     int debug;                // measurement only: bit 0 = no water becomes a candidate, bit 1 = skip phase C
+    unsigned stagger;         // cycles over which the CTAs of the first wave spread their start (0 = all start together)
+    unsigned wave_ctas;       // CTAs of the first wave (SMs x resident CTAs per SM)
+    unsigned n_sm;
+    unsigned long long* cta_trace;   // diagnostic (HBGPU_CTA_TRACE): [frame][8] = globaltimer at start / after the stagger / B begin / B end / B2 end / end, SM id
 };
 
 struct FusedShared {          // small fixed part at the start of dynamic shared memory
@@ -106,6 +111,35 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned pari
         }
         if (clock64() - t0 > 2000000000ll) return false;
     }
+}
+// the same on 32-bit shared-window addresses computed once outside a loop (the generic-pointer forms above make the
+// compiler rebuild the shared-window base - S2R SR_CgaCtaId, LEA - at every use)
+__device__ __forceinline__ bool mbar_try_wait_a(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(1000u)
+        : "memory");
+    return ok != 0;
+}
+__device__ __noinline__ bool mbar_wait_slow_a(unsigned bar, unsigned parity, unsigned ns) {
+    const long long t0 = clock64();
+    for (;;) {
+        for (int k = 0; k < 64; ++k) {
+            if (ns) __nanosleep(ns);
+            if (mbar_try_wait_a(bar, parity)) return true;
+        }
+        if (clock64() - t0 > 2000000000ll) return false;
+    }
+}
+__device__ __forceinline__ void mbar_arrive_a(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
 }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(FUSED_CONSUMERS) : "memory"); }
 
@@ -183,12 +217,12 @@ template <bool PBC>
 __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(BatchView bv, DevTopo tp, RunParams rp, BondTable bt, FusedCfg fc) {
     extern __shared__ __align__(16) unsigned char smem[];
     FusedShared* sh = reinterpret_cast<FusedShared*>(smem);
-    // union region, phases A/B: [sorted1][tile ring][candidate buffers];  phase C: [sorted1][psorted][pairs][tasks][flags]
-    float4* sorted1 = reinterpret_cast<float4*>(smem + fc.off_union);      // selection points (g1 cell order with waters)
-    unsigned char* ring = smem + fc.off_union + (size_t)fc.sel_cap * 16;   // phase B: tile stages
+    // regions by lifetime (plan_fused): [sorted1 | pairs] [ring | candidate coordinates | psorted, tasks, flags] [cand][lw]
+    float4* sorted1 = reinterpret_cast<float4*>(smem + fc.off_sorted);     // selection points in g1 cell order (until the phase C sort)
+    unsigned* pairs = reinterpret_cast<unsigned*>(smem + fc.off_sorted);   // phase C1 onwards: the pair list
+    unsigned char* ring = smem + fc.off_ring;                              // phase B: tile stages
     float4* psorted = reinterpret_cast<float4*>(ring);                     // phase C: selection + local waters, g2 order
-    unsigned* pairs = reinterpret_cast<unsigned*>(psorted + fc.sel_cap + fc.lw_cap);
-    uint2* tasks = reinterpret_cast<uint2*>(pairs + fc.pair_cap);          // phase C: (pair | flag, hydrogen atom)
+    uint2* tasks = reinterpret_cast<uint2*>(psorted + fc.sel_cap + fc.lw_cap);   // phase C: (pair | flag, hydrogen atom)
     unsigned* pflags = reinterpret_cast<unsigned*>(tasks + fc.task_cap);   // phase C: angle flags of the chunk's pairs
     float4* lw = reinterpret_cast<float4*>(smem + fc.off_lw);
     unsigned short* cells = reinterpret_cast<unsigned short*>(smem + fc.off_cells);
@@ -221,6 +255,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
             tick = now;
         }
     };
+    auto cta_mark = [&](int k) {       // diagnostic only: wall-clock marks of consumer thread 0
+        if (fc.cta_trace && tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            fc.cta_trace[(size_t)b * 8 + k] = t;
+            if (k == 0) {
+                unsigned sm;
+                asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+                fc.cta_trace[(size_t)b * 8 + 6] = sm;
+            }
+        }
+    };
+    cta_mark(0);
     if (nsel > fc.sel_cap) {           // uniform over the CTA: this frame does not fit
         if (tid == 0) atomicExch(bt.fused_overflow, 1);
         return;
@@ -233,8 +280,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
         for (int k = 0; k < fc.stages; ++k) { mbar_init(&full[k], 1); mbar_init(&empty[k], FUSED_CWARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // All frames cost the same and the CTAs of a wave share HBM fairly, so a launch whose CTAs start together stays in
+        // lock step: every resident frame streams at the same time (HBM saturated) and then every frame computes at the
+        // same time (HBM idle). The first wave therefore starts spread over one frame time; the order persists.
+        if (fc.stagger && (unsigned)b < fc.wave_ctas) {
+            const unsigned per_sm = fc.wave_ctas / fc.n_sm;
+            const unsigned long long rank = (unsigned long long)(((unsigned)b / fc.n_sm) % per_sm) * fc.n_sm + (unsigned)b % fc.n_sm;
+            const long long delay = (long long)((unsigned long long)fc.stagger * rank / fc.wave_ctas);
+            const long long t0 = clock64();
+            while (clock64() - t0 < delay) __nanosleep(500);
+        }
     }
     __syncthreads();
+    cta_mark(1);
 
     // ---- producer warp: stream the water block of this frame ------------------------------------------
     if (warp == FUSED_CWARPS) {
@@ -276,17 +334,26 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
                 unsigned long long src = start0;
                 unsigned long long pre = start0 + (unsigned long long)npre * tile_step;
                 unsigned char* dst = ring;
+                const bool trb = (fc.debug & 4) && bt.phase_cycles;      // measurement: where the producer's time goes
+                unsigned c_pwait = 0, c_pissue = 0, tk = trb ? (unsigned)clock() : 0u;
                 for (int t = 0; t < ntiles; ++t) {
                     if (t + npre < ntiles)
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pre), "r"(t + npre == ntiles - 1 ? last_bytes : tile_step) : "memory");
                     pre += tile_step;
+                    if (trb) { const unsigned now = (unsigned)clock(); c_pissue += now - tk; tk = now; }
                     if (t >= fc.stages && !mbar_wait(&empty[st], parity, fc.wait_ns)) { sh->overflow = 2; break; }
+                    if (trb) { const unsigned now = (unsigned)clock(); c_pwait += now - tk; tk = now; }
                     const unsigned bytes = t == ntiles - 1 ? last_bytes : full_bytes;
                     mbar_expect_tx(&full[st], bytes);
                     bulk_g2s(dst, reinterpret_cast<const void*>(src), bytes, &full[st]);
                     src += tile_step;
                     dst += fc.stage_bytes;
                     if (++st == fc.stages) { st = 0; parity ^= 1u; dst = ring; }
+                }
+                if (trb) {
+                    c_pissue += (unsigned)clock() - tk;
+                    atomicAdd(&bt.phase_cycles[25], (unsigned long long)c_pwait);
+                    atomicAdd(&bt.phase_cycles[26], (unsigned long long)c_pissue);
                 }
                 return;
             }
@@ -352,13 +419,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
     if (lane == 0)
         for (int k = 0; k < 3; ++k) { sh->red[warp][k] = mn[k]; sh->red[warp][3 + k] = mx[k]; }
     consumer_sync();
-    if (tid == 0) {
+    // thread 0 builds the selection grid g1, thread 32 (another warp) the pair grid g2 at the same time: the grid sizing is a
+    // serial loop of divisions
+    const bool split_grids = !PBC && wa;
+    if (tid == 0 || (tid == 32 && split_grids)) {
         // same values the general path obtains through its ordered-int atomics: min / max over the points
+        float lo3[3], hi3[3];
         for (int k = 0; k < 3; ++k) {
             float a = sh->red[0][k], c = sh->red[0][3 + k];
             for (int w = 1; w < FUSED_CWARPS; ++w) { a = fminf(a, sh->red[w][k]); c = fmaxf(c, sh->red[w][3 + k]); }
-            sh->lo[k] = a; sh->hi[k] = c;
+            lo3[k] = a; hi3[k] = c;
         }
+        if (tid == 0)
+            for (int k = 0; k < 3; ++k) { sh->lo[k] = lo3[k]; sh->hi[k] = hi3[k]; }
         if constexpr (PBC) {
             PbcGrid pg;
             pg.box = load_box(bv.box + 9ll * b);
@@ -369,17 +442,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
                 frac_coords(pg, r[0], r[1], r[2], sR[0], sR[1], sR[2]);
             }
             if (wa) {
-                make_grid_pbc(sh->g1, pg.box, sR, sh->lo, sh->hi, rp.cell1, rp.cell1, fc.cell_cap);
-                make_grid_pbc(sh->g2, pg.box, sR, sh->lo, sh->hi, rp.around_f, rp.cell2, fc.cell_cap);
+                make_grid_pbc(sh->g1, pg.box, sR, lo3, hi3, rp.cell1, rp.cell1, fc.cell_cap);
+                make_grid_pbc(sh->g2, pg.box, sR, lo3, hi3, rp.around_f, rp.cell2, fc.cell_cap);
             } else {
-                make_grid_pbc(sh->g2, pg.box, sR, sh->lo, sh->hi, 0.f, rp.cell2, fc.cell_cap);
+                make_grid_pbc(sh->g2, pg.box, sR, lo3, hi3, 0.f, rp.cell2, fc.cell_cap);
                 sh->g1 = sh->g2;
             }
         } else if (wa) {
-            make_grid(sh->g1, sh->lo, sh->hi, rp.cell1, rp.cell1, fc.cell_cap);
-            make_grid(sh->g2, sh->lo, sh->hi, rp.around_f, rp.cell2, fc.cell_cap);
+            if (tid == 0) make_grid(sh->g1, lo3, hi3, rp.cell1, rp.cell1, fc.cell_cap);
+            else make_grid(sh->g2, lo3, hi3, rp.around_f, rp.cell2, fc.cell_cap);
         } else {
-            make_grid(sh->g2, sh->lo, sh->hi, 0.f, rp.cell2, fc.cell_cap);
+            make_grid(sh->g2, lo3, hi3, 0.f, rp.cell2, fc.cell_cap);
             sh->g1 = sh->g2;
         }
     }
@@ -406,16 +479,21 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
                             atomicOr(&near[c >> 5], 1u << (c & 31));
                         }
             } else {
+                // the (up to) three cells of a row are consecutive bits: one atomic per row, two where they straddle a word
+                const int xl = max(cx - 1, 0), nb = min(cx + 1, g1.nx - 1) - xl + 1;
                 for (int zz = max(cz - 1, 0); zz <= min(cz + 1, g1.nz - 1); ++zz)
-                    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g1.ny - 1); ++yy)
-                        for (int xx = max(cx - 1, 0); xx <= min(cx + 1, g1.nx - 1); ++xx) {
-                            const int c = (zz * g1.ny + yy) * g1.nx + xx;
-                            atomicOr(&near[c >> 5], 1u << (c & 31));
-                        }
+                    for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g1.ny - 1); ++yy) {
+                        const int r = (zz * g1.ny + yy) * g1.nx + xl;
+                        const int sh5 = r & 31;
+                        const unsigned m = (1u << nb) - 1u;
+                        atomicOr(&near[r >> 5], m << sh5);
+                        if (sh5 + nb > 32) atomicOr(&near[(r >> 5) + 1], m >> (32 - sh5));
+                    }
             }
         }
         consumer_sync();
         phase_done(1);
+        cta_mark(2);
 
         const float a = rp.around_f;
         const float lox = sh->lo[0] - a, loy = sh->lo[1] - a, loz = sh->lo[2] - a;
@@ -424,19 +502,123 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
         // only COLLECTED while the tiles stream - their indices go to one CTA-wide list - and tested afterwards, densely,
         // by all consumers (phase B2). A warp that stopped to test 32 candidates in the middle of the stream held its
         // arrival on the next tiles back and, with a ring of three stages, everybody else's too.
-        unsigned* clist = reinterpret_cast<unsigned*>(cand);
+        // candidate indices, 16-bit where every water index fits
+        auto cand_put = [&](int pos, int i) {
+            if (fc.cand16) reinterpret_cast<unsigned short*>(cand)[pos] = (unsigned short)i;
+            else reinterpret_cast<unsigned*>(cand)[pos] = (unsigned)i;
+        };
+        auto cand_get = [&](int j) -> int {
+            return fc.cand16 ? (int)reinterpret_cast<const unsigned short*>(cand)[j] : (int)reinterpret_cast<const unsigned*>(cand)[j];
+        };
         int st = 0;
         unsigned parity = 0;
         // a tile advances by 256 * stride * 12 bytes, a multiple of 16: the offset of its first water inside the
         // 16-byte aligned stage is the same for every tile of the frame
-        const unsigned my_off = stream ? (unsigned)(((unsigned long long)(uintptr_t)(xyz + 3ll * tp.wat_atom[w0]) & 15ull) +
-                                                    (unsigned long long)(tid * stride12)) : 0u;
+        const unsigned long long gbase_c = stream ? (unsigned long long)(uintptr_t)(xyz + 3ll * tp.wat_atom[w0]) : 0ull;
+        const unsigned my_off = stream ? (unsigned)((gbase_c & 15ull) + (unsigned long long)(tid * stride12)) : 0u;
+        const bool trb = (fc.debug & 4) && bt.phase_cycles && warp == 0;      // measurement: where warp 0's time goes
+        unsigned c_wait = 0, c_load = 0, c_test = 0, tk = trb ? (unsigned)clock() : 0u;
+        const unsigned lt_mask = (1u << lane) - 1u;
+        // two tiles' candidates, one ballot each and one shared-memory atomic for both
+        auto append2 = [&](bool c0, int i0, bool c1, int i1) {
+            const unsigned m0 = __ballot_sync(0xffffffffu, c0), m1 = __ballot_sync(0xffffffffu, c1);
+            if (m0 | m1) {
+                const int n0 = __popc(m0);
+                int base = 0;
+                if (lane == 0) base = atomicAdd(&sh->n_cand, n0 + __popc(m1));
+                base = __shfl_sync(0xffffffffu, base, 0);
+                if (c0) {
+                    const int pos = base + __popc(m0 & lt_mask);
+                    HB_DASSERT(pos >= 0 && i0 >= 0 && i0 < nwp);
+                    if (pos < fc.cand_cap) cand_put(pos, i0);
+                    else sh->overflow = 1;
+                }
+                if (c1) {
+                    const int pos = base + n0 + __popc(m1 & lt_mask);
+                    HB_DASSERT(pos >= 0 && i1 >= 0 && i1 < nwp);
+                    if (pos < fc.cand_cap) cand_put(pos, i1);
+                    else sh->overflow = 1;
+                }
+            }
+        };
+        // cheap test first (non-periodic: dilated bounding box), then the near bitmap
+        auto in_box = [&](float x, float y, float z) -> bool {
+            if constexpr (PBC) return true;
+            else return x >= lox && x <= hix && y >= loy && y <= hiy && z >= loz && z <= hiz;
+        };
+        auto near_hit = [&](float x, float y, float z) -> bool {
+            int c;
+            if constexpr (PBC) {
+                int cx, cy, cz;
+                if (!cell3_pbc(g1, x, y, z, cx, cy, cz)) return false;
+                c = (cz * g1.ny + cy) * g1.nx + cx;
+            } else {
+                c = cell_of<false>(g1, x, y, z);
+            }
+            return (near[c >> 5] >> (c & 31)) & 1u;
+        };
+        bool inside = false;       // every tile of the frame was copied completely (the frame does not touch the edges of the batch buffer)
+        if (stream) {
+            const unsigned long long lim_lo = (fc.buf_begin + 15ull) & ~15ull, lim_hi = fc.buf_end & ~15ull;
+            const unsigned long long start0 = gbase_c & ~15ull;
+            const int nw_last = nwp - (ntiles - 1) * FUSED_TILE;
+            const unsigned last_bytes = ((unsigned)(gbase_c - start0) + (unsigned)((nw_last - 1) * stride12 + 12) + 15u) & ~15u;
+            const unsigned long long frame_end = start0 + (unsigned long long)(ntiles - 1) * (unsigned long long)(FUSED_TILE * stride12) + last_bytes;
+            inside = start0 >= lim_lo && frame_end <= lim_hi;      // (the producer takes its short loop under the same condition)
+        }
+        if (inside && !trb) {
+            // Short loop. A consumer warp's own instruction stream is what bounds the streaming rate of a CTA (the producer
+            // waits for free stages most of the time), so: barrier and ring addresses are computed once, two tiles are taken
+            // per trip and tested together (two independent dependency chains), and a trip whose 64 waters all lie outside
+            // the dilated bounding box ends after one vote.
+            const unsigned full_a = smem_u32(full), empty_a = smem_u32(empty);
+            const unsigned ring_a = smem_u32(ring) + my_off;
+            unsigned st_a = ring_a;
+            bool ok = true;
+            auto take = [&](float& x, float& y, float& z) -> bool {     // next tile: wait, read this thread's water, release the stage
+                const unsigned bar = full_a + 8u * (unsigned)st;
+                if (!mbar_try_wait_a(bar, parity) && !mbar_wait_slow_a(bar, parity, fc.wait_ns)) return false;
+                x = lds_f32(st_a); y = lds_f32(st_a + 4u); z = lds_f32(st_a + 8u);
+                __syncwarp();                                   // every lane has read its water before the stage is released
+                if (lane == 0) mbar_arrive_a(empty_a + 8u * (unsigned)st);
+                st_a += fc.stage_bytes;
+                if (++st == fc.stages) { st = 0; parity ^= 1u; st_a = ring_a; }
+                return true;
+            };
+            const int nfull = nwp / FUSED_TILE;                 // tiles whose 256 waters all exist
+            int t = 0;
+            for (; t + 2 <= nfull; t += 2) {
+                float x0, y0, z0, x1, y1, z1;
+                if (!take(x0, y0, z0) || !take(x1, y1, z1)) { ok = false; break; }
+                bool c0 = in_box(x0, y0, z0), c1 = in_box(x1, y1, z1);
+                if (__any_sync(0xffffffffu, c0 || c1)) {
+                    c0 = c0 && near_hit(x0, y0, z0);
+                    c1 = c1 && near_hit(x1, y1, z1);
+                    if (fc.debug & 1) c0 = c1 = false;
+                    append2(c0, t * FUSED_TILE + tid, c1, (t + 1) * FUSED_TILE + tid);
+                }
+            }
+            for (; ok && t < ntiles; ++t) {
+                float x0, y0, z0;
+                if (!take(x0, y0, z0)) { ok = false; break; }
+                const int i = t * FUSED_TILE + tid;
+                bool c0 = i < nwp && in_box(x0, y0, z0);
+                if (__any_sync(0xffffffffu, c0)) {
+                    c0 = c0 && near_hit(x0, y0, z0);
+                    if (fc.debug & 1) c0 = false;
+                    append2(c0, i, false, 0);
+                }
+            }
+            if (!ok) sh->overflow = 2;
+        } else
         for (int t = 0; t < ntiles; ++t) {
             const int i = t * FUSED_TILE + tid;
             const bool live = i < nwp;
             float x = 0.f, y = 0.f, z = 0.f;
+            if (trb) { const unsigned now = (unsigned)clock(); c_test += now - tk; tk = now; }
             if (stream) {
                 if (!mbar_wait(&full[st], parity, fc.wait_ns)) { sh->overflow = 2; break; }
+                if (trb) { const unsigned now = (unsigned)clock(); c_wait += now - tk; tk = now; }
                 HB_DASSERT(st >= 0 && st < fc.stages && my_off + 12u <= fc.stage_bytes);
                 const float* f = reinterpret_cast<const float*>(ring + (size_t)st * fc.stage_bytes + my_off);
                 x = f[0]; y = f[1]; z = f[2];             // (always inside the stage; meaningful if the bytes were copied)
@@ -448,54 +630,68 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
                 __syncwarp();                           // every lane has read its water before the stage is released
                 if (lane == 0) mbar_arrive(&empty[st]);
                 if (++st == fc.stages) { st = 0; parity ^= 1u; }
+                if (trb) { const unsigned now = (unsigned)clock(); c_load += now - tk; tk = now; }
             } else if (live) {
                 const float* f = xyz + 3ll * tp.wat_atom[w0 + i];
                 x = f[0]; y = f[1]; z = f[2];
             }
-            bool is_cand;
-            if constexpr (PBC) {
-                int cx, cy, cz;
-                is_cand = cell3_pbc(g1, x, y, z, cx, cy, cz) && live;
-                if (is_cand) {
-                    const int c = (cz * g1.ny + cy) * g1.nx + cx;
-                    is_cand = (near[c >> 5] >> (c & 31)) & 1u;
-                }
-            } else {
-                is_cand = live && x >= lox && x <= hix && y >= loy && y <= hiy && z >= loz && z <= hiz;
-                if (is_cand) {
-                    const int c = cell_of<false>(g1, x, y, z);
-                    is_cand = (near[c >> 5] >> (c & 31)) & 1u;
-                }
-            }
+            bool is_cand = live && in_box(x, y, z);
+            if (is_cand) is_cand = near_hit(x, y, z);
             if (fc.debug & 1) is_cand = false;
-            const unsigned m = __ballot_sync(0xffffffffu, is_cand);
-            if (m) {
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&sh->n_cand, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (is_cand) {
-                    const int pos = base + __popc(m & ((1u << lane) - 1u));
-                    HB_DASSERT(pos >= 0 && i >= 0 && i < nwp);
-                    if (pos < fc.cand_cap) clist[pos] = (unsigned)i;
-                    else sh->overflow = 1;
-                }
-            }
+            append2(is_cand, i, false, 0);
+        }
+        if (trb && tid == 0) {
+            atomicAdd(&bt.phase_cycles[27], (unsigned long long)c_wait);
+            atomicAdd(&bt.phase_cycles[28], (unsigned long long)c_load);
+            atomicAdd(&bt.phase_cycles[29], (unsigned long long)c_test);
         }
         phase_done(2);
+        cta_mark(3);
+        unsigned b2_t[5] = {0u, 0u, 0u, 0u, 0u}, b2_tk = 0u;                 // measurement (fused_debug & 4), warp 0
+        const bool trb2 = (fc.debug & 4) && bt.phase_cycles && warp == 0;
+        auto b2_lap = [&](int k) { if (trb2) { const unsigned now = (unsigned)clock(); b2_t[k] += now - b2_tk; b2_tk = now; } };
+        if (trb2) b2_tk = (unsigned)clock();
         consumer_sync();
+        b2_lap(0);
         // ---- phase B2: exact local-water test of the collected candidates, one per thread --------------------------------
         const int ncand = min(sh->n_cand, fc.cand_cap);
+        // The candidates' coordinates were just streamed (L2 hits), but a round trip per round of 256 candidates was half
+        // of this phase: all of them are gathered at once with asynchronous 4-byte copies into the drained tile ring.
+        float* cxyz = reinterpret_cast<float*>(ring);
+        const bool staged = stream && !sh->overflow && (size_t)ncand * 12 <= (size_t)fc.stages * fc.stage_bytes;
+        if (staged) {
+            for (int j = tid; j < ncand; j += FUSED_CONSUMERS) {
+                const unsigned long long src = gbase_c + (unsigned long long)cand_get(j) * (unsigned long long)stride12;
+                const unsigned dst = smem_u32(cxyz + 3 * j);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u), "l"(src + 4ull) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 8u), "l"(src + 8ull) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            consumer_sync();
+        }
+        b2_lap(1);
         for (int j0 = 0; j0 < ncand; j0 += FUSED_CONSUMERS) {
             const int j = j0 + tid;
             bool local = false;
             float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
             if (j < ncand) {
-                const int i = (int)clist[j];
+                const int i = cand_get(j);
                 HB_DASSERT(i >= 0 && i < nwp);
-                const float* f = xyz + 3ll * tp.wat_atom[w0 + i];     // (just streamed: an L2 hit)
-                c = make_float4(f[0], f[1], f[2], __int_as_float(WATER_TAG | i));
+                if (staged) {
+                    c = make_float4(cxyz[3 * j], cxyz[3 * j + 1], cxyz[3 * j + 2], __int_as_float(WATER_TAG | i));
+                } else {
+                    // (just streamed: an L2 hit; a regular water block needs no index load in front of it)
+                    const float* f = stream ? reinterpret_cast<const float*>(gbase_c) + (long long)i * (3 * fc.w_stride)
+                                            : xyz + 3ll * tp.wat_atom[w0 + i];
+                    c = make_float4(f[0], f[1], f[2], __int_as_float(WATER_TAG | i));
+                }
+                b2_lap(2);
                 local = water_is_local<PBC>(g1, cells, sorted1, c.x, c.y, c.z, rp);
             }
+            __syncwarp();
+            b2_lap(3);
             const unsigned m = __ballot_sync(0xffffffffu, local);
             if (m) {
                 int base = 0;
@@ -507,11 +703,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
                     else sh->overflow = 1;
                 }
             }
+            b2_lap(4);
         }
-        phase_done(2);
+        if (trb2 && lane == 0) {
+            for (int k = 0; k < 5; ++k) atomicAdd(&bt.phase_cycles[30 + k], (unsigned long long)b2_t[k]);
+            atomicAdd(&bt.phase_cycles[35], (unsigned long long)ncand);
+        }
+        phase_done(9);
     }
     consumer_sync();
     phase_done(3);
+    cta_mark(4);
     if (sh->overflow || sh->n_lw > fc.lw_cap) {
         if (tid == 0) atomicExch(bt.fused_overflow, 1);
         return;
@@ -636,6 +838,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
     phase_done(7);
     flush_hits(bt, nhit);
     phase_done(8);
+    cta_mark(5);
 }
 
 }  // namespace

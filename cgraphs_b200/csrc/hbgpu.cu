@@ -92,6 +92,7 @@ struct hb_ctx {
     long long opt_fused_stages = 3;   // depth of the water-tile ring
     long long opt_fused_wait_ns = 100;
     long long opt_fused_prefetch = 2; // tiles prefetched into L2 ahead of the ring (more evicts lines before use)
+    long long opt_fused_stagger = 125000; // cycles over which the first wave of fused CTAs spreads its start
     int opt_fused_debug = 0;          // measurement hook (results are wrong when set): see FusedCfg::debug
     int fused_grow = 0;
     int sort_smem_cap = 0;            // dynamic shared memory k_sort_small may use was raised (per context / device)
@@ -529,6 +530,7 @@ int hb_set_option(hb_ctx* ctx, const char* name, int64_t value) {
     else if (n == "fused_batch_frames") ctx->opt_fused_batch_frames = std::max<long long>(value, 1);
     else if (n == "fused_prefetch") ctx->opt_fused_prefetch = std::max<long long>(value, 0);
     else if (n == "fused_debug") ctx->opt_fused_debug = (int)value;
+    else if (n == "fused_stagger") ctx->opt_fused_stagger = std::min<long long>(std::max<long long>(value, 0), 4000000);
     else if (n == "fused_wait_ns") ctx->opt_fused_wait_ns = std::max<long long>(value, 0);
     else return fail(ctx, HB_ERR_ARG, "unknown option " + n);
     return HB_OK;
@@ -831,8 +833,6 @@ static bool plan_fused(hb_ctx* ctx, int grow = 0) {
     }
     fc.lw_cap = (int)lw;
     if ((long long)fc.sel_cap + fc.lw_cap > 65535) return false;      // 16-bit cell cursors / pair indices
-    long long cc = ctx->opt_fused_cell_cap ? ctx->opt_fused_cell_cap : 3712;   // 16-bit counters: 7.3 kB
-    fc.cell_cap = (int)std::min<long long>(cc, 32768);
     fc.pair_cap = (int)((ctx->opt_fused_pair_cap ? ctx->opt_fused_pair_cap : 2048) << grow);
     fc.regular = (wa && ctx->water_regular && ctx->water_stride <= 8) ? 1 : 0;
     fc.w_stride = ctx->water_stride;
@@ -841,29 +841,43 @@ static bool plan_fused(hb_ctx* ctx, int grow = 0) {
     fc.debug = ctx->opt_fused_debug;
     fc.wait_ns = (unsigned)ctx->opt_fused_wait_ns;
     fc.stage_bytes = fc.regular ? (unsigned)(((FUSED_TILE - 1) * fc.w_stride * 12 + 12 + 15 + 15) & ~15) : 0u;
-    size_t off = (sizeof(FusedShared) + 15) & ~(size_t)15;
-    fc.off_union = (unsigned)off;
-    // phases A/B: [sorted1][tile ring][candidate buffers (before the g1 sort: selection points in gather order)]
-    size_t un_b = (size_t)fc.sel_cap * 16 + (size_t)fc.stages * fc.stage_bytes;
-    fc.off_cand = (unsigned)(off + un_b);
-    {   // candidate index list (4 bytes each; before the g1 sort the region holds the selection points in gather order)
-        const size_t cand_bytes = wa ? std::max((size_t)8192 << std::min(grow, 3), (size_t)fc.sel_cap * 16) : 0;
-        fc.cand_cap = (int)(cand_bytes / 4);
-        un_b += cand_bytes;
-    }
-    // phase C: [sorted1][psorted][pairs][tasks][flags]
     fc.task_cap = 1536 << grow;
-    size_t un_c = (size_t)fc.sel_cap * 16 + ((size_t)fc.sel_cap + fc.lw_cap) * 16 + (size_t)fc.pair_cap * 4 +
-                  (size_t)fc.task_cap * 8 + FUSED_CONSUMERS * 4;
-    off += (std::max(un_b, un_c) + 15) & ~(size_t)15;
-    fc.off_lw = (unsigned)off;
-    off += (size_t)fc.lw_cap * 16;
-    fc.off_cells = (unsigned)off;
-    off += (((size_t)fc.cell_cap + 2) * 2 + 15) & ~(size_t)15;
-    fc.off_near = (unsigned)off;
-    off += (((size_t)fc.cell_cap + 31) / 32 * 4 + 15) & ~(size_t)15;
-    fc.off_bar = (unsigned)off;
-    off += (size_t)2 * FUSED_MAX_STAGES * 8;
+    // Regions by lifetime (every region 16-byte aligned):
+    //   sorted1 | pairs   selection points in g1 order (g1 sort .. phase C sort), then the pair list (phase C1 ..)
+    //   ring              tile stages (phase B), gathered candidate coordinates (B2), then psorted + tasks + flags (phase C)
+    //   cand, lw          candidate indices (B .. B2) and local waters (B2 .. C sort); before the g1 sort the two together
+    //                     hold the selection points in gather order
+    //   cells, near       cell counters of the current grid, near bitmap of g1
+    auto al16 = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    fc.cand16 = ctx->max_wat <= 65535 ? 1 : 0;
+    const size_t sorted_b = al16(std::max((size_t)fc.sel_cap * 16, (size_t)fc.pair_cap * 4));
+    const size_t ring_b = al16(std::max((size_t)fc.stages * fc.stage_bytes,
+                                        ((size_t)fc.sel_cap + fc.lw_cap) * 16 + (size_t)fc.task_cap * 8 + FUSED_CONSUMERS * 4));
+    const size_t lw_b = (size_t)fc.lw_cap * 16;
+    size_t cand_b = 0;
+    if (wa) {
+        fc.cand_cap = 2048 << std::min(grow, 3);
+        cand_b = al16((size_t)fc.cand_cap * (fc.cand16 ? 2 : 4));
+        if (cand_b + lw_b < (size_t)fc.sel_cap * 16) cand_b = al16((size_t)fc.sel_cap * 16 - lw_b);
+        fc.cand_cap = (int)(cand_b / (fc.cand16 ? 2 : 4));
+    }
+    size_t off = al16(sizeof(FusedShared));
+    fc.off_sorted = (unsigned)off;  off += sorted_b;
+    fc.off_ring = (unsigned)off;    off += ring_b;
+    fc.off_cand = (unsigned)off;    off += cand_b;
+    fc.off_lw = (unsigned)off;      off += lw_b;
+    fc.off_bar = (unsigned)off;     off += (size_t)2 * FUSED_MAX_STAGES * 8;
+    // the cell counters take what is left of the shared memory that still lets four frames share an SM (finer cells =
+    // fewer distance tests in phases B2 and C1): 2 bytes per cell + 1 bit for the near bitmap
+    long long cc = ctx->opt_fused_cell_cap;
+    if (!cc) {
+        const long long budget = (long long)(ctx->prop.sharedMemPerMultiprocessor / 4) - (long long)ctx->prop.reservedSharedMemPerBlock - 64;
+        cc = ((budget - (long long)off - 64) * 8 / 17) & ~31ll;
+        cc = std::min<long long>(std::max<long long>(cc, 3712), 8192);
+    }
+    fc.cell_cap = (int)std::min<long long>(cc, 32768);
+    fc.off_cells = (unsigned)off;   off += al16(((size_t)fc.cell_cap + 2) * 2);
+    fc.off_near = (unsigned)off;    off += al16(((size_t)fc.cell_cap + 31) / 32 * 4);
     fc.smem_bytes = (unsigned)off;
     if (fc.smem_bytes > 112 * 1024) return false;                     // keep at least two frames resident per SM
     if (cudaFuncSetAttribute(k_frame_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fc.smem_bytes) != cudaSuccess ||
@@ -959,7 +973,7 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
         k_fill_u64<<<1184, 256, 0, ctx->s_compute>>>(ctx->bt.keys, tc, EMPTY_KEY);
         ctx->tm.n_launches += 1;
         CK(cudaMemsetAsync(ctx->bt.bits, 0, tc * wpr * sizeof(unsigned), ctx->s_compute));
-        CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 32 * sizeof(unsigned long long), ctx->s_compute));
+        CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 64 * sizeof(unsigned long long), ctx->s_compute));
         if (ctx->trace) { cudaStreamSynchronize(ctx->s_compute); tr.mark("clear(reuse)"); }
         ctx->running = true;
         ctx->finalized = false;
@@ -968,8 +982,8 @@ int hb_begin(hb_ctx* ctx, int64_t n_frames_total) {
     // bond table
     if ((rc = alloc_table(ctx, ctx->bt, cap, wpr))) return rc;
     ctx->table_cap = cap;
-    CK(cudaMalloc((void**)&ctx->bt.n_keys, 32 * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 32 * sizeof(unsigned long long), ctx->s_compute));
+    CK(cudaMalloc((void**)&ctx->bt.n_keys, 64 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->bt.n_keys, 0, 64 * sizeof(unsigned long long), ctx->s_compute));
     ctx->bt.overflow = ctx->bt.n_keys + 1;
     ctx->bt.fused_overflow = ctx->bt.n_keys + 2;
     ctx->bt.n_hits = (unsigned long long*)(ctx->bt.n_keys + 4);
@@ -1162,12 +1176,32 @@ static int run_search(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf,
         FusedCfg fc = ctx->fc;
         fc.buf_begin = (unsigned long long)(uintptr_t)buf0;
         fc.buf_end = fc.buf_begin + buf_bytes;
+        fc.stagger = 0;
+        if (ctx->opt_fused_stagger > 0) {
+            int per_sm = 0;
+            if (ctx->rp.pbc != HB_PBC_NONE) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame_fused<true>, FUSED_THREADS, fc.smem_bytes);
+            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame_fused<false>, FUSED_THREADS, fc.smem_bytes);
+            fc.n_sm = (unsigned)ctx->prop.multiProcessorCount;
+            fc.wave_ctas = (unsigned)std::max(per_sm, 1) * fc.n_sm;
+            if ((long long)nf >= 2ll * fc.wave_ctas) fc.stagger = (unsigned)ctx->opt_fused_stagger;   // short launches: the delay would not pay
+        }
+        const char* trace_path = getenv("HBGPU_CTA_TRACE");      // diagnostic: per-CTA wall-clock marks appended to this file
+        fc.cta_trace = nullptr;
+        if (trace_path && cudaMalloc((void**)&fc.cta_trace, (size_t)nf * 64) == cudaSuccess) cudaMemsetAsync(fc.cta_trace, 0, (size_t)nf * 64, st);
         {
             KTimer t(ctx, KC_FUSED);
             if (ctx->rp.pbc != HB_PBC_NONE) k_frame_fused<true><<<nf, FUSED_THREADS, fc.smem_bytes, st>>>(bv, ctx->tp, ctx->rp, ctx->bt_run, fc);
             else k_frame_fused<false><<<nf, FUSED_THREADS, fc.smem_bytes, st>>>(bv, ctx->tp, ctx->rp, ctx->bt_run, fc);
         }
         CK(cudaGetLastError());
+        if (fc.cta_trace) {
+            std::vector<unsigned long long> h((size_t)nf * 8);
+            cudaStreamSynchronize(st);
+            if (cudaMemcpy(h.data(), fc.cta_trace, h.size() * 8, cudaMemcpyDeviceToHost) == cudaSuccess) {
+                if (FILE* f = fopen(trace_path, "ab")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+            }
+            cudaFree(fc.cta_trace);
+        }
         ctx->tm.fused_frames += nf;
         ctx->last_batch_fused = true;
     } else if (ctx->rp.method == HB_METHOD_ION_CONTACTS) {
@@ -2099,9 +2133,16 @@ int hb_finalize(hb_ctx* ctx, int64_t* n_bonds, int64_t* words_per_bond) {
         }
     }
     if (ctx->trace && ctx->bt.phase_cycles && ctx->tm.fused_frames) {
-        unsigned long long pc[16];
+        unsigned long long pc[40];
         if (cudaMemcpy(pc, ctx->bt.phase_cycles, sizeof(pc), cudaMemcpyDeviceToHost) == cudaSuccess) {
             double f = (double)ctx->tm.fused_frames;
+            fprintf(stderr, "[hbgpu]   B2 (candidate tests) %.0f\n", pc[9] / f);
+            if (ctx->opt_fused_debug & 4)
+                fprintf(stderr, "[hbgpu]   stream loop, cycles per frame: producer waits for a free stage %.0f, issues %.0f | consumer warp 0 waits for a tile %.0f, "
+                                "loads + releases %.0f, tests %.0f\n", pc[25] / f, pc[26] / f, pc[27] / f, pc[28] / f, pc[29] / f);
+            if (ctx->opt_fused_debug & 4)
+                fprintf(stderr, "[hbgpu]   B2 (warp 0), cycles per frame: sync after the stream %.0f | gather %.0f | fetch %.0f | 27-cell walk %.0f | append %.0f | "
+                                "candidates per frame %.0f\n", pc[30] / f, pc[31] / f, pc[32] / f, pc[33] / f, pc[34] / f, pc[35] / f);
             fprintf(stderr, "[hbgpu] fused phases, cycles per frame (thread 0): A gather+grid %.0f | g1 sort+near %.0f | B stream %.0f | "
                             "B tail sync %.0f | C sort %.0f | C collect %.0f | C sync %.0f | C expand %.0f | flush %.0f\n",
                     pc[0] / f, pc[1] / f, pc[2] / f, pc[3] / f, pc[4] / f, pc[5] / f, pc[6] / f, pc[7] / f, pc[8] / f);
