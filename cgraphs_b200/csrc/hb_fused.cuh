@@ -1,18 +1,17 @@
 // hb_fused.cuh - fused fast path: ONE CTA processes ONE frame end to end; everything but the frame's
 // coordinates and the bond table stays in shared memory.
 //
-// The CTA has 8 consumer warps and 1 producer warp.
+// The CTA has 8 warps.
 //
-//   phase A  (consumers) gather the selection points (<= sel_cap) into smem, bounding box, cell grid g1
-//            (edge >= around_radius), counting sort, "near" bitmap: bit c is set iff some selection point
-//            lies in the 27-cell neighbourhood of cell c.
-//   phase B  the producer warp streams the frame's water block through a ring of shared-memory stages
-//            with 1-D bulk async copies (TMA engine: cp.async.bulk + mbarrier complete_tx); a tile is
-//            256 consecutive waters (O,H,H,O,H,H ... as they lie in the coordinate array), so HBM is read
-//            in large aligned bursts exactly once.  Consumer thread j takes water j of the tile:
-//            dilated-bounding-box test, near-bitmap test, then the survivors ("candidates") go to a
-//            per-warp buffer and are tested 32 at a time, densely, against the 27 neighbouring g1 cells
-//            with the exact DIST predicate; local waters (hbond.py:249-252) are appended to a shared list.
+//   phase A  gather the selection points (<= sel_cap) into smem, bounding box, cell grid g1 (edge >= around_radius),
+//            counting sort, "near" bitmap: bit c is set iff some selection point lies in the 27-cell neighbourhood of cell c.
+//   phase B  the frame's water block streams through a ring of shared-memory stages with 1-D bulk async copies (TMA engine:
+//            cp.async.bulk + mbarrier complete_tx); a tile is 256 consecutive waters (O,H,H,O,H,H ... as they lie in the
+//            coordinate array), so HBM is read in large aligned bursts exactly once. Warp w < stages owns stage w and every
+//            stages-th tile: eight waters per lane, dilated-bounding-box test -> near-bitmap test -> the survivors'
+//            ("candidates") indices go to a CTA-wide list; the owner refills its stage as soon as it has read it.
+//   phase B2 candidates are tested densely against the 27 neighbouring g1 cells with the exact DIST predicate; local
+//            waters (hbond.py:249-252) are appended to a shared list.
 //   phase C  (consumers) cell grid g2 (edge >= distance) over selection + local waters; per block of 256
 //            points: half-shell walk collecting the point pairs that pass the exact DIST test into a pair
 //            list, then one thread per pair expands it into the reference's entry pairs, applies the
@@ -28,8 +27,11 @@ namespace {
 
 #define FUSED_CWARPS 8
 #define FUSED_CONSUMERS (FUSED_CWARPS * 32)
-#define FUSED_THREADS (FUSED_CONSUMERS + 32)
-#define FUSED_TILE 256          // waters per tile: one per consumer thread
+#define FUSED_THREADS FUSED_CONSUMERS
+#ifndef FUSED_WPL
+#define FUSED_WPL 3             // waters per lane and tile
+#endif
+#define FUSED_TILE (32 * FUSED_WPL)   // waters per tile: one warp takes a whole tile
 #define FUSED_MAX_STAGES 8
 
 struct FusedCfg {
@@ -229,7 +231,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
     unsigned* near = reinterpret_cast<unsigned*>(smem + fc.off_near);
     float4* cand = reinterpret_cast<float4*>(smem + fc.off_cand);
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + fc.off_bar);
-    unsigned long long* empty = full + FUSED_MAX_STAGES;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.x;
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
         sh->n_cand = 0;
         sh->n_pairs = 0;
         sh->overflow = 0;
-        for (int k = 0; k < fc.stages; ++k) { mbar_init(&full[k], 1); mbar_init(&empty[k], FUSED_CWARPS); }
+        for (int k = 0; k < fc.stages; ++k) mbar_init(&full[k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         // All frames cost the same and the CTAs of a wave share HBM fairly, so a launch whose CTAs start together stays in
@@ -294,98 +295,56 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
     __syncthreads();
     cta_mark(1);
 
-    // ---- producer warp: stream the water block of this frame ------------------------------------------
-    if (warp == FUSED_CWARPS) {
-        if (stream && lane == 0) {
-            const unsigned long long gbase = (unsigned long long)(uintptr_t)(xyz + 3ll * tp.wat_atom[w0]);
-            const unsigned long long lim_lo = (fc.buf_begin + 15ull) & ~15ull, lim_hi = fc.buf_end & ~15ull;
-            // tiles further ahead are pulled into L2 while the ring holds the next few: the ring then only
-            // has to cover the L2 -> shared-memory latency
-            const unsigned long long wat_end = gbase + (unsigned long long)(nwp - 1) * (unsigned long long)stride12 + 12ull;
-            auto prefetch_tile = [&](int t) {
-                unsigned long long a = (gbase + (unsigned long long)t * (unsigned long long)(FUSED_TILE * stride12)) & ~15ull;
-                unsigned long long e = a + (unsigned long long)(FUSED_TILE * stride12);
-                if (e > wat_end) e = wat_end & ~15ull;
-                if (a < lim_lo) a = lim_lo;
-                if (e > lim_hi) e = lim_hi;
-                if (e > a)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((unsigned)(e - a)) : "memory");
-            };
-            int st = 0;
-            unsigned parity = 1;                        // parity of the "previous round" of the empty barriers
-            // A tile advances by 256 * stride * 12 bytes, a multiple of 16, so every tile of the frame starts at the same
-            // offset `head` inside its 16-byte aligned copy. Frames whose water block lies inside the batch buffer with
-            // its alignment slack (all but the first and last frame of a batch) take the short loop: one thread issues
-            // every tile of the CTA and shares its issue slots with 36 resident warps, so each instruction here delays
-            // the whole ring.
-            const unsigned tile_step = (unsigned)(FUSED_TILE * stride12);
-            const unsigned long long start0 = gbase & ~15ull;
-            const unsigned head = (unsigned)(gbase - start0);
-            const int nw_last = nwp - (ntiles - 1) * FUSED_TILE;
-            const unsigned full_bytes = (head + (unsigned)((FUSED_TILE - 1) * stride12 + 12) + 15u) & ~15u;
-            const unsigned last_bytes = (head + (unsigned)((nw_last - 1) * stride12 + 12) + 15u) & ~15u;
-            const unsigned long long frame_end = start0 + (unsigned long long)(ntiles - 1) * tile_step + last_bytes;
-            if (start0 >= lim_lo && frame_end <= lim_hi) {
-                for (int k = 0; k < fc.stages; ++k) { sh->stage_head[k] = 0u; sh->stage_lo[k] = 0u; sh->stage_hi[k] = fc.stage_bytes; }
-                const int npre = min(fc.prefetch, ntiles);
-                for (int t = 0; t < npre; ++t)
-                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(start0 + (unsigned long long)t * tile_step),
-                                 "r"(t == ntiles - 1 ? last_bytes : tile_step) : "memory");
-                unsigned long long src = start0;
-                unsigned long long pre = start0 + (unsigned long long)npre * tile_step;
-                unsigned char* dst = ring;
-                const bool trb = (fc.debug & 4) && bt.phase_cycles;      // measurement: where the producer's time goes
-                unsigned c_pwait = 0, c_pissue = 0, tk = trb ? (unsigned)clock() : 0u;
-                for (int t = 0; t < ntiles; ++t) {
-                    if (t + npre < ntiles)
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pre), "r"(t + npre == ntiles - 1 ? last_bytes : tile_step) : "memory");
-                    pre += tile_step;
-                    if (trb) { const unsigned now = (unsigned)clock(); c_pissue += now - tk; tk = now; }
-                    if (t >= fc.stages && !mbar_wait(&empty[st], parity, fc.wait_ns)) { sh->overflow = 2; break; }
-                    if (trb) { const unsigned now = (unsigned)clock(); c_pwait += now - tk; tk = now; }
-                    const unsigned bytes = t == ntiles - 1 ? last_bytes : full_bytes;
-                    mbar_expect_tx(&full[st], bytes);
-                    bulk_g2s(dst, reinterpret_cast<const void*>(src), bytes, &full[st]);
-                    src += tile_step;
-                    dst += fc.stage_bytes;
-                    if (++st == fc.stages) { st = 0; parity ^= 1u; dst = ring; }
-                }
-                if (trb) {
-                    c_pissue += (unsigned)clock() - tk;
-                    atomicAdd(&bt.phase_cycles[25], (unsigned long long)c_pwait);
-                    atomicAdd(&bt.phase_cycles[26], (unsigned long long)c_pissue);
-                }
-                return;
-            }
-            for (int t = 0; t < min(fc.prefetch, ntiles); ++t) prefetch_tile(t);
-            for (int t = 0; t < ntiles; ++t) {
-                if (t + fc.prefetch < ntiles) prefetch_tile(t + fc.prefetch);
-                if (t >= fc.stages && !mbar_wait(&empty[st], parity, fc.wait_ns)) { sh->overflow = 2; break; }
-                const int nw = min(FUSED_TILE, nwp - t * FUSED_TILE);
-                const unsigned long long ga = gbase + (unsigned long long)t * (unsigned long long)(FUSED_TILE * stride12);
-                const unsigned long long start = ga & ~15ull;
-                const unsigned head = (unsigned)(ga - start);
-                const unsigned long long end = (ga + (unsigned long long)((nw - 1) * stride12 + 12) + 15ull) & ~15ull;
-                const unsigned long long c0 = start > lim_lo ? start : lim_lo, c1 = end < lim_hi ? end : lim_hi;
-                const bool partial = c0 != start || c1 != end;     // tile touches the edge of the batch buffer
-                sh->stage_head[st] = partial ? 1u : 0u;
-                unsigned char* dst = ring + (size_t)st * fc.stage_bytes;
-                if (c1 > c0) {
-                    const unsigned lo = (unsigned)(c0 - start), bytes = (unsigned)(c1 - c0);
-                    sh->stage_lo[st] = lo;
-                    sh->stage_hi[st] = lo + bytes;
-                    mbar_expect_tx(&full[st], bytes);
-                    bulk_g2s(dst + lo, reinterpret_cast<const void*>(c0), bytes, &full[st]);
-                } else {
-                    sh->stage_lo[st] = 0;
-                    sh->stage_hi[st] = 0;
-                    mbar_arrive(&full[st]);
-                }
-                if (++st == fc.stages) { st = 0; parity ^= 1u; }
+    // ---- the water block of this frame is streamed through the tile ring ------------------------------------------
+    // A tile is 32 x FUSED_WPL consecutive waters. Warp w < stages owns stage w of the ring and the tiles w, w + stages, ...: it waits
+    // for its tile, reads FUSED_WPL waters per lane, and - the stage being free again - one of its lanes issues the copy of its
+    // next tile into it before the warp tests what it read. There is no producer warp and no "empty" barrier; the per-tile
+    // costs (wait, refill, loop) are paid once per 256 waters, and the copies of the other stages are in flight meanwhile.
+    // A tile advances by 256 * stride * 12 bytes, a multiple of 16, so every tile of the frame starts at the same offset
+    // `head` inside its 16-byte aligned copy. Frames whose water block touches the edge of the batch buffer (the first and
+    // last frame of a batch) copy the part of a tile that lies inside and read the few waters outside with plain loads.
+    const unsigned long long gbase = stream ? (unsigned long long)(uintptr_t)(xyz + 3ll * tp.wat_atom[w0]) : 0ull;
+    const unsigned tile_step = (unsigned)(FUSED_TILE * stride12);
+    const unsigned long long start0 = gbase & ~15ull;
+    const unsigned head = (unsigned)(gbase - start0);
+    const unsigned long long lim_lo = (fc.buf_begin + 15ull) & ~15ull, lim_hi = fc.buf_end & ~15ull;
+    const int nw_last = nwp - (ntiles - 1) * FUSED_TILE;
+    const unsigned full_bytes = (head + (unsigned)((FUSED_TILE - 1) * stride12 + 12) + 15u) & ~15u;
+    const unsigned last_bytes = (head + (unsigned)((nw_last - 1) * stride12 + 12) + 15u) & ~15u;
+    const bool inside = stream && start0 >= lim_lo &&
+                        start0 + (unsigned long long)(ntiles - 1) * tile_step + last_bytes <= lim_hi;
+    auto issue_tile = [&](int t) {      // one thread: copy tile t into its stage, pull a tile further ahead into L2
+        const int st = t % fc.stages;
+        unsigned char* dst = ring + (size_t)st * fc.stage_bytes;
+        const unsigned long long src = start0 + (unsigned long long)t * tile_step;
+        const unsigned bytes = t == ntiles - 1 ? last_bytes : full_bytes;
+        if (inside) {
+            mbar_expect_tx(&full[st], bytes);
+            bulk_g2s(dst, reinterpret_cast<const void*>(src), bytes, &full[st]);
+        } else {
+            const unsigned long long end = src + bytes;
+            const unsigned long long c0 = src > lim_lo ? src : lim_lo, c1 = end < lim_hi ? end : lim_hi;
+            if (c1 > c0) {
+                sh->stage_lo[st] = (unsigned)(c0 - src);
+                sh->stage_hi[st] = (unsigned)(c1 - src);
+                mbar_expect_tx(&full[st], (unsigned)(c1 - c0));
+                bulk_g2s(dst + (c0 - src), reinterpret_cast<const void*>(c0), (unsigned)(c1 - c0), &full[st]);
+            } else {
+                sh->stage_lo[st] = 0;
+                sh->stage_hi[st] = 0;
+                mbar_arrive(&full[st]);
             }
         }
-        return;
-    }
+        const int tp2 = t + fc.prefetch;
+        if (fc.prefetch > 0 && tp2 < ntiles) {
+            unsigned long long a = start0 + (unsigned long long)tp2 * tile_step;
+            unsigned long long e = a + (tp2 == ntiles - 1 ? last_bytes : tile_step);
+            if (a < lim_lo) a = lim_lo;
+            if (e > lim_hi) e = lim_hi;
+            if (e > a) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((unsigned)(e - a)) : "memory");
+        }
+    };
+    if (stream && lane == 0 && warp < fc.stages && warp < ntiles) issue_tile(warp);
 
     // ---- phase A: selection points, bounding box, grids ------------------------------------------
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -510,37 +469,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
         auto cand_get = [&](int j) -> int {
             return fc.cand16 ? (int)reinterpret_cast<const unsigned short*>(cand)[j] : (int)reinterpret_cast<const unsigned*>(cand)[j];
         };
-        int st = 0;
-        unsigned parity = 0;
-        // a tile advances by 256 * stride * 12 bytes, a multiple of 16: the offset of its first water inside the
-        // 16-byte aligned stage is the same for every tile of the frame
-        const unsigned long long gbase_c = stream ? (unsigned long long)(uintptr_t)(xyz + 3ll * tp.wat_atom[w0]) : 0ull;
-        const unsigned my_off = stream ? (unsigned)((gbase_c & 15ull) + (unsigned long long)(tid * stride12)) : 0u;
-        const bool trb = (fc.debug & 4) && bt.phase_cycles && warp == 0;      // measurement: where warp 0's time goes
-        unsigned c_wait = 0, c_load = 0, c_test = 0, tk = trb ? (unsigned)clock() : 0u;
         const unsigned lt_mask = (1u << lane) - 1u;
-        // two tiles' candidates, one ballot each and one shared-memory atomic for both
-        auto append2 = [&](bool c0, int i0, bool c1, int i1) {
-            const unsigned m0 = __ballot_sync(0xffffffffu, c0), m1 = __ballot_sync(0xffffffffu, c1);
-            if (m0 | m1) {
-                const int n0 = __popc(m0);
-                int base = 0;
-                if (lane == 0) base = atomicAdd(&sh->n_cand, n0 + __popc(m1));
-                base = __shfl_sync(0xffffffffu, base, 0);
-                if (c0) {
-                    const int pos = base + __popc(m0 & lt_mask);
-                    HB_DASSERT(pos >= 0 && i0 >= 0 && i0 < nwp);
-                    if (pos < fc.cand_cap) cand_put(pos, i0);
-                    else sh->overflow = 1;
-                }
-                if (c1) {
-                    const int pos = base + n0 + __popc(m1 & lt_mask);
-                    HB_DASSERT(pos >= 0 && i1 >= 0 && i1 < nwp);
-                    if (pos < fc.cand_cap) cand_put(pos, i1);
-                    else sh->overflow = 1;
-                }
-            }
-        };
         // cheap test first (non-periodic: dilated bounding box), then the near bitmap
         auto in_box = [&](float x, float y, float z) -> bool {
             if constexpr (PBC) return true;
@@ -557,93 +486,101 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
             }
             return (near[c >> 5] >> (c & 31)) & 1u;
         };
-        bool inside = false;       // every tile of the frame was copied completely (the frame does not touch the edges of the batch buffer)
         if (stream) {
-            const unsigned long long lim_lo = (fc.buf_begin + 15ull) & ~15ull, lim_hi = fc.buf_end & ~15ull;
-            const unsigned long long start0 = gbase_c & ~15ull;
-            const int nw_last = nwp - (ntiles - 1) * FUSED_TILE;
-            const unsigned last_bytes = ((unsigned)(gbase_c - start0) + (unsigned)((nw_last - 1) * stride12 + 12) + 15u) & ~15u;
-            const unsigned long long frame_end = start0 + (unsigned long long)(ntiles - 1) * (unsigned long long)(FUSED_TILE * stride12) + last_bytes;
-            inside = start0 >= lim_lo && frame_end <= lim_hi;      // (the producer takes its short loop under the same condition)
-        }
-        if (inside && !trb) {
-            // Short loop. A consumer warp's own instruction stream is what bounds the streaming rate of a CTA (the producer
-            // waits for free stages most of the time), so: barrier and ring addresses are computed once, two tiles are taken
-            // per trip and tested together (two independent dependency chains), and a trip whose 64 waters all lie outside
-            // the dilated bounding box ends after one vote.
-            const unsigned full_a = smem_u32(full), empty_a = smem_u32(empty);
-            const unsigned ring_a = smem_u32(ring) + my_off;
-            unsigned st_a = ring_a;
+            const unsigned full_a = smem_u32(full);
+            const unsigned lane_a = smem_u32(ring) + head + (unsigned)(lane * stride12);    // this lane's first water of stage 0
+            const unsigned step32 = (unsigned)(32 * stride12);
             bool ok = true;
-            auto take = [&](float& x, float& y, float& z) -> bool {     // next tile: wait, read this thread's water, release the stage
-                const unsigned bar = full_a + 8u * (unsigned)st;
-                if (!mbar_try_wait_a(bar, parity) && !mbar_wait_slow_a(bar, parity, fc.wait_ns)) return false;
-                x = lds_f32(st_a); y = lds_f32(st_a + 4u); z = lds_f32(st_a + 8u);
-                __syncwarp();                                   // every lane has read its water before the stage is released
-                if (lane == 0) mbar_arrive_a(empty_a + 8u * (unsigned)st);
-                st_a += fc.stage_bytes;
-                if (++st == fc.stages) { st = 0; parity ^= 1u; st_a = ring_a; }
-                return true;
-            };
-            const int nfull = nwp / FUSED_TILE;                 // tiles whose 256 waters all exist
-            int t = 0;
-            for (; t + 2 <= nfull; t += 2) {
-                float x0, y0, z0, x1, y1, z1;
-                if (!take(x0, y0, z0) || !take(x1, y1, z1)) { ok = false; break; }
-                bool c0 = in_box(x0, y0, z0), c1 = in_box(x1, y1, z1);
-                if (__any_sync(0xffffffffu, c0 || c1)) {
-                    c0 = c0 && near_hit(x0, y0, z0);
-                    c1 = c1 && near_hit(x1, y1, z1);
-                    if (fc.debug & 1) c0 = c1 = false;
-                    append2(c0, t * FUSED_TILE + tid, c1, (t + 1) * FUSED_TILE + tid);
+            // warp w < stages owns stage w: tiles w, w + stages, ... (the other warps wait at the barrier after the loop)
+            const int st = warp;
+            const unsigned bar = full_a + 8u * (unsigned)st;
+            const unsigned a = lane_a + (unsigned)st * fc.stage_bytes;
+            unsigned par = 0u;
+            for (int t = warp; warp < fc.stages && t < ntiles; t += fc.stages, par ^= 1u) {
+                if (!mbar_try_wait_a(bar, par) && !mbar_wait_slow_a(bar, par, fc.wait_ns)) { ok = false; break; }
+                const int i0 = t * FUSED_TILE + lane;
+                float x[FUSED_WPL], y[FUSED_WPL], z[FUSED_WPL];
+#pragma unroll
+                for (int k = 0; k < FUSED_WPL; ++k) {          // (always inside the stage; meaningful if the bytes were copied)
+                    x[k] = lds_f32(a + k * step32); y[k] = lds_f32(a + k * step32 + 4u); z[k] = lds_f32(a + k * step32 + 8u);
                 }
-            }
-            for (; ok && t < ntiles; ++t) {
-                float x0, y0, z0;
-                if (!take(x0, y0, z0)) { ok = false; break; }
-                const int i = t * FUSED_TILE + tid;
-                bool c0 = i < nwp && in_box(x0, y0, z0);
-                if (__any_sync(0xffffffffu, c0)) {
-                    c0 = c0 && near_hit(x0, y0, z0);
-                    if (fc.debug & 1) c0 = false;
-                    append2(c0, i, false, 0);
+                if (!inside) {                          // bytes outside the batch buffer were not copied
+                    const unsigned lo = sh->stage_lo[st], hi = sh->stage_hi[st];
+#pragma unroll
+                    for (int k = 0; k < FUSED_WPL; ++k) {
+                        const unsigned off = head + (unsigned)((lane + 32 * k) * stride12);
+                        if (i0 + 32 * k < nwp && !(off >= lo && off + 12u <= hi)) {
+                            const float* g = xyz + 3ll * tp.wat_atom[w0 + i0 + 32 * k];
+                            x[k] = g[0]; y[k] = g[1]; z[k] = g[2];
+                        }
+                    }
+                }
+                // The last load of every lane has returned when this vote completes (shared-memory loads of a warp return in
+                // order, and the vote needs the value): the stage is free, and one lane refills it before the tests.
+                asm volatile("{\n .reg .pred p, q;\n setp.eq.u32 p, %0, 0xffffffff;\n vote.sync.any.pred q, p, 0xffffffff;\n}" ::"r"(__float_as_uint(z[FUSED_WPL - 1])) : "memory");
+                if (lane == 0 && t + fc.stages < ntiles) issue_tile(t + fc.stages);
+                unsigned inb = 0u;
+                if (t == ntiles - 1) {
+#pragma unroll
+                    for (int k = 0; k < FUSED_WPL; ++k)
+                        if (i0 + 32 * k < nwp && in_box(x[k], y[k], z[k])) inb |= 1u << k;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < FUSED_WPL; ++k)
+                        if (in_box(x[k], y[k], z[k])) inb |= 1u << k;
+                }
+                if (!__any_sync(0xffffffffu, inb != 0u)) continue;
+                unsigned cm = 0u;
+#pragma unroll
+                for (int k = 0; k < FUSED_WPL; ++k)
+                    if (((inb >> k) & 1u) && near_hit(x[k], y[k], z[k])) cm |= 1u << k;
+                if (fc.debug & 1) cm = 0u;
+                if (!__any_sync(0xffffffffu, cm != 0u)) continue;
+                // append: warp scan of the per-lane counts, one shared-memory atomic per tile
+                const int n = __popc(cm);
+                int incl = n;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                int base = 0;
+                if (lane == 31) base = atomicAdd(&sh->n_cand, incl);
+                base = __shfl_sync(0xffffffffu, base, 31);
+                int pos = base + incl - n;
+                while (cm) {
+                    const int k = __ffs(cm) - 1;
+                    cm &= cm - 1u;
+                    HB_DASSERT(pos >= 0 && i0 + 32 * k < nwp);
+                    if (pos < fc.cand_cap) cand_put(pos, i0 + 32 * k);
+                    else sh->overflow = 1;
+                    ++pos;
                 }
             }
             if (!ok) sh->overflow = 2;
-        } else
-        for (int t = 0; t < ntiles; ++t) {
-            const int i = t * FUSED_TILE + tid;
-            const bool live = i < nwp;
-            float x = 0.f, y = 0.f, z = 0.f;
-            if (trb) { const unsigned now = (unsigned)clock(); c_test += now - tk; tk = now; }
-            if (stream) {
-                if (!mbar_wait(&full[st], parity, fc.wait_ns)) { sh->overflow = 2; break; }
-                if (trb) { const unsigned now = (unsigned)clock(); c_wait += now - tk; tk = now; }
-                HB_DASSERT(st >= 0 && st < fc.stages && my_off + 12u <= fc.stage_bytes);
-                const float* f = reinterpret_cast<const float*>(ring + (size_t)st * fc.stage_bytes + my_off);
-                x = f[0]; y = f[1]; z = f[2];             // (always inside the stage; meaningful if the bytes were copied)
-                const unsigned partial = sh->stage_head[st];
-                if (partial && live && !(my_off >= sh->stage_lo[st] && my_off + 12u <= sh->stage_hi[st])) {
-                    const float* g = xyz + 3ll * tp.wat_atom[w0 + i];   // bytes outside the batch buffer were not copied
-                    x = g[0]; y = g[1]; z = g[2];
+        } else {
+            // waters without a regular stride: index loads, one water per thread and trip
+            for (int i0 = 0; i0 < nwp; i0 += FUSED_CONSUMERS) {
+                const int i = i0 + tid;
+                bool is_cand = false;
+                if (i < nwp) {
+                    const float* f = xyz + 3ll * tp.wat_atom[w0 + i];
+                    const float x = f[0], y = f[1], z = f[2];
+                    is_cand = in_box(x, y, z) && near_hit(x, y, z);
                 }
-                __syncwarp();                           // every lane has read its water before the stage is released
-                if (lane == 0) mbar_arrive(&empty[st]);
-                if (++st == fc.stages) { st = 0; parity ^= 1u; }
-                if (trb) { const unsigned now = (unsigned)clock(); c_load += now - tk; tk = now; }
-            } else if (live) {
-                const float* f = xyz + 3ll * tp.wat_atom[w0 + i];
-                x = f[0]; y = f[1]; z = f[2];
+                if (fc.debug & 1) is_cand = false;
+                const unsigned m = __ballot_sync(0xffffffffu, is_cand);
+                if (m) {
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&sh->n_cand, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (is_cand) {
+                        const int pos = base + __popc(m & lt_mask);
+                        if (pos < fc.cand_cap) cand_put(pos, i);
+                        else sh->overflow = 1;
+                    }
+                }
             }
-            bool is_cand = live && in_box(x, y, z);
-            if (is_cand) is_cand = near_hit(x, y, z);
-            if (fc.debug & 1) is_cand = false;
-            append2(is_cand, i, false, 0);
-        }
-        if (trb && tid == 0) {
-            atomicAdd(&bt.phase_cycles[27], (unsigned long long)c_wait);
-            atomicAdd(&bt.phase_cycles[28], (unsigned long long)c_load);
-            atomicAdd(&bt.phase_cycles[29], (unsigned long long)c_test);
         }
         phase_done(2);
         cta_mark(3);
@@ -661,7 +598,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
         const bool staged = stream && !sh->overflow && (size_t)ncand * 12 <= (size_t)fc.stages * fc.stage_bytes;
         if (staged) {
             for (int j = tid; j < ncand; j += FUSED_CONSUMERS) {
-                const unsigned long long src = gbase_c + (unsigned long long)cand_get(j) * (unsigned long long)stride12;
+                const unsigned long long src = gbase + (unsigned long long)cand_get(j) * (unsigned long long)stride12;
                 const unsigned dst = smem_u32(cxyz + 3 * j);
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u), "l"(src + 4ull) : "memory");
@@ -683,7 +620,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
                     c = make_float4(cxyz[3 * j], cxyz[3 * j + 1], cxyz[3 * j + 2], __int_as_float(WATER_TAG | i));
                 } else {
                     // (just streamed: an L2 hit; a regular water block needs no index load in front of it)
-                    const float* f = stream ? reinterpret_cast<const float*>(gbase_c) + (long long)i * (3 * fc.w_stride)
+                    const float* f = stream ? reinterpret_cast<const float*>(gbase) + (long long)i * (3 * fc.w_stride)
                                             : xyz + 3ll * tp.wat_atom[w0 + i];
                     c = make_float4(f[0], f[1], f[2], __int_as_float(WATER_TAG | i));
                 }

@@ -89,7 +89,7 @@ struct hb_ctx {
     long long opt_fused_lw_cap = 0;   // 0: automatic
     long long opt_fused_cell_cap = 0; // 0: automatic
     long long opt_fused_pair_cap = 0; // 0: automatic
-    long long opt_fused_stages = 3;   // depth of the water-tile ring
+    long long opt_fused_stages = 8;   // stages of the water-tile ring = warps that stream (one stage each)
     long long opt_fused_wait_ns = 100;
     long long opt_fused_prefetch = 2; // tiles prefetched into L2 ahead of the ring (more evicts lines before use)
     long long opt_fused_stagger = 125000; // cycles over which the first wave of fused CTAs spreads its start
