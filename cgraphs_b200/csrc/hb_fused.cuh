@@ -55,6 +55,9 @@ struct FusedCfg {
     unsigned stagger;         // cycles over which the CTAs of the first wave spread their start (0 = all start together)
     unsigned wave_ctas;       // CTAs of the first wave (SMs x resident CTAs per SM)
     unsigned n_sm;
+    unsigned pf_off, pf_bytes; // byte range of a frame that holds the selection points and their hydrogens (0 = none)
+    int* sm_streams;          // [n_sm] frames streaming on each SM right now (admission: at most max_streams per SM)
+    int max_streams;          // 0 = no limit
     unsigned long long* cta_trace;   // diagnostic (HBGPU_CTA_TRACE): [frame][8] = globaltimer at start / after the stagger / B begin / B end / B2 end / end, SM id
 };
 
@@ -281,6 +284,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
         for (int k = 0; k < fc.stages; ++k) mbar_init(&full[k], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (fc.pf_bytes) {                 // the selection's atom block -> L2 (phases A and C gather from it)
+            unsigned long long a = ((unsigned long long)(uintptr_t)xyz + fc.pf_off) & ~15ull;
+            unsigned long long e = ((unsigned long long)(uintptr_t)xyz + fc.pf_off + fc.pf_bytes + 15ull) & ~15ull;
+            const unsigned long long l0 = (fc.buf_begin + 15ull) & ~15ull, l1 = fc.buf_end & ~15ull;
+            if (a < l0) a = l0;
+            if (e > l1) e = l1;
+            if (e > a) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((unsigned)(e - a)) : "memory");
+        }
         // All frames cost the same and the CTAs of a wave share HBM fairly, so a launch whose CTAs start together stays in
         // lock step: every resident frame streams at the same time (HBM saturated) and then every frame computes at the
         // same time (HBM idle). The first wave therefore starts spread over one frame time; the order persists.
@@ -344,7 +355,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
             if (e > a) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"((unsigned)(e - a)) : "memory");
         }
     };
-    if (stream && lane == 0 && warp < fc.stages && warp < ntiles) issue_tile(warp);
 
     // ---- phase A: selection points, bounding box, grids ------------------------------------------
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -450,9 +460,27 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
                     }
             }
         }
+        // Admission: at most max_streams frames of an SM stream at the same time. Frames that all cost the same drift into
+        // lock step (every resident frame streams - HBM saturated - and then every frame computes - HBM idle); a frame that
+        // finds its SM's share taken starts a little later and stays out of step from then on.
+        unsigned my_sm = 0u;
+        bool admitted = false;
+        if (stream && fc.max_streams > 0 && tid == 0) {
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(my_sm));
+            if (my_sm < fc.n_sm) {
+                const long long t0 = clock64();
+                for (;;) {
+                    if (atomicAdd(&fc.sm_streams[my_sm], 1) < fc.max_streams) { admitted = true; break; }
+                    atomicSub(&fc.sm_streams[my_sm], 1);
+                    if (clock64() - t0 > 400000ll) break;             // (~0.2 ms: never wait for long)
+                    __nanosleep(2000);
+                }
+            }
+        }
         consumer_sync();
         phase_done(1);
         cta_mark(2);
+        if (stream && lane == 0 && warp < fc.stages && warp < ntiles) issue_tile(warp);
 
         const float a = rp.around_f;
         const float lox = sh->lo[0] - a, loy = sh->lo[1] - a, loz = sh->lo[2] - a;
@@ -589,6 +617,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
         auto b2_lap = [&](int k) { if (trb2) { const unsigned now = (unsigned)clock(); b2_t[k] += now - b2_tk; b2_tk = now; } };
         if (trb2) b2_tk = (unsigned)clock();
         consumer_sync();
+        if (admitted) atomicSub(&fc.sm_streams[my_sm], 1);      // (thread 0 only)
         b2_lap(0);
         // ---- phase B2: exact local-water test of the collected candidates, one per thread --------------------------------
         const int ncand = min(sh->n_cand, fc.cand_cap);

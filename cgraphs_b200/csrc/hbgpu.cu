@@ -92,6 +92,9 @@ struct hb_ctx {
     long long opt_fused_stages = 8;   // stages of the water-tile ring = warps that stream (one stage each)
     long long opt_fused_wait_ns = 100;
     long long opt_fused_prefetch = 2; // tiles prefetched into L2 ahead of the ring (more evicts lines before use)
+    int opt_fused_sel_prefetch = 1;   // bulk L2 prefetch of the selection's atom block at the start of a frame
+    long long opt_fused_max_streams = 2; // frames of one SM that may stream at the same time (0 = no limit)
+    int* d_sm_streams = nullptr;
     long long opt_fused_stagger = 125000; // cycles over which the first wave of fused CTAs spreads its start
     int opt_fused_debug = 0;          // measurement hook (results are wrong when set): see FusedCfg::debug
     int fused_grow = 0;
@@ -209,6 +212,7 @@ struct hb_ctx {
     // trajectory mode: atom ranges [begin, end) that hold every atom the kernels read; the rest of a frame
     // (inert atoms) is never copied to the device. Empty = copy whole frames.
     std::vector<std::pair<long long, long long>> copy_ranges;
+    long long sel_block_lo = 0, sel_block_n = 0;   // atoms [lo, lo + n) hold the selection points and their hydrogens (0 = unknown)
     std::vector<unsigned char> atom_used;     // single-system topologies: 1 = some kernel reads this atom's coordinates
     int opt_copy_ranges = 1;
     int opt_stage_threads = 8;        // host threads that copy pageable frames into the pinned staging buffer
@@ -450,6 +454,7 @@ static void free_run(hb_ctx* ctx) {
     free_list(ctx->wire.allocs);
     ctx->wire.d_edges = nullptr;
     ctx->wire.d_cnt = nullptr;
+    if (ctx->d_sm_streams) cudaFree(ctx->d_sm_streams);
     if (ctx->bt.keys) cudaFree(ctx->bt.keys);
     if (ctx->bt.bits) cudaFree(ctx->bt.bits);
     if (ctx->bt.n_keys) cudaFree(ctx->bt.n_keys);
@@ -530,6 +535,8 @@ int hb_set_option(hb_ctx* ctx, const char* name, int64_t value) {
     else if (n == "fused_batch_frames") ctx->opt_fused_batch_frames = std::max<long long>(value, 1);
     else if (n == "fused_prefetch") ctx->opt_fused_prefetch = std::max<long long>(value, 0);
     else if (n == "fused_debug") ctx->opt_fused_debug = (int)value;
+    else if (n == "fused_sel_prefetch") ctx->opt_fused_sel_prefetch = value != 0;
+    else if (n == "fused_max_streams") ctx->opt_fused_max_streams = std::min<long long>(std::max<long long>(value, 0), 64);
     else if (n == "fused_stagger") ctx->opt_fused_stagger = std::min<long long>(std::max<long long>(value, 0), 4000000);
     else if (n == "fused_wait_ns") ctx->opt_fused_wait_ns = std::max<long long>(value, 0);
     else return fail(ctx, HB_ERR_ARG, "unknown option " + n);
@@ -604,6 +611,24 @@ int hb_set_topology(hb_ctx* ctx, const hb_topology* t) {
         for (int i = 0; i < t->n_ent_h; ++i) ctx->atom_used[t->ent_h_atom[i]] = 1;
     }
     build_copy_ranges(ctx);
+    // the block of atoms that holds the selection points and their hydrogens (single system, waters excluded): the fused
+    // kernel pulls it into L2 with one bulk prefetch when a frame starts, so its gathers do not wait for DRAM
+    ctx->sel_block_lo = ctx->sel_block_n = 0;
+    if (ns == 1 && t->n_sel > 0) {
+        long long lo = t->sel_atom[0], hi = t->sel_atom[0], wlo = -1, whi = -2;
+        for (int i = 0; i < t->n_sel; ++i) { lo = std::min<long long>(lo, t->sel_atom[i]); hi = std::max<long long>(hi, t->sel_atom[i]); }
+        if (t->n_wat > 0) {
+            wlo = whi = t->wat_atom[0];
+            for (int i = 0; i < t->n_wat; ++i) { wlo = std::min<long long>(wlo, t->wat_atom[i]); whi = std::max<long long>(whi, t->wat_atom[i]); }
+            whi += 8;      // (the hydrogens of the last water)
+        }
+        for (int i = 0; i < t->n_ent_h; ++i) {
+            const long long h = t->ent_h_atom[i];
+            if (h >= wlo && h <= whi) continue;
+            lo = std::min(lo, h); hi = std::max(hi, h);
+        }
+        if ((hi - lo + 1) * 12 <= 512 * 1024) { ctx->sel_block_lo = lo; ctx->sel_block_n = hi - lo + 1; }
+    }
     // water points at a constant atom stride (O, H, H, O, H, H ...) can be streamed as contiguous slabs
     ctx->water_regular = t->n_wat > 0;
     ctx->water_stride = 0;
@@ -1176,6 +1201,23 @@ static int run_search(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf,
         FusedCfg fc = ctx->fc;
         fc.buf_begin = (unsigned long long)(uintptr_t)buf0;
         fc.buf_end = fc.buf_begin + buf_bytes;
+        fc.n_sm = (unsigned)ctx->prop.multiProcessorCount;
+        fc.pf_off = fc.pf_bytes = 0;
+        if (ctx->opt_fused_sel_prefetch && !bv.structure_batch && ctx->sel_block_n > 0) {
+            fc.pf_off = (unsigned)(ctx->sel_block_lo * 12);
+            fc.pf_bytes = (unsigned)(ctx->sel_block_n * 12);
+        }
+        fc.max_streams = 0;
+        fc.sm_streams = nullptr;
+        if (ctx->opt_fused_max_streams > 0) {
+            if (!ctx->d_sm_streams && cudaMalloc((void**)&ctx->d_sm_streams, 1024 * sizeof(int)) == cudaSuccess)
+                cudaMemsetAsync(ctx->d_sm_streams, 0, 1024 * sizeof(int), st);
+            if (ctx->d_sm_streams && fc.n_sm <= 1024 && (long long)nf >= 8ll * fc.n_sm) {   // (short launches: nothing to keep apart)
+                cudaMemsetAsync(ctx->d_sm_streams, 0, fc.n_sm * sizeof(int), st);          // a failed launch must not leave counts behind
+                fc.sm_streams = ctx->d_sm_streams;
+                fc.max_streams = (int)ctx->opt_fused_max_streams;
+            }
+        }
         fc.stagger = 0;
         if (ctx->opt_fused_stagger > 0) {
             int per_sm = 0;
