@@ -455,6 +455,7 @@ static void free_run(hb_ctx* ctx) {
     ctx->wire.d_edges = nullptr;
     ctx->wire.d_cnt = nullptr;
     if (ctx->d_sm_streams) cudaFree(ctx->d_sm_streams);
+    ctx->d_sm_streams = nullptr;
     if (ctx->bt.keys) cudaFree(ctx->bt.keys);
     if (ctx->bt.bits) cudaFree(ctx->bt.bits);
     if (ctx->bt.n_keys) cudaFree(ctx->bt.n_keys);
