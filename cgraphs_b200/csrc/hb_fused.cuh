@@ -146,6 +146,16 @@ __device__ __forceinline__ float lds_f32(unsigned addr) {
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ unsigned lds_u16(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(FUSED_CONSUMERS) : "memory"); }
 
 // counting-sort helpers on packed 16-bit cell counters ---------------------------------------------
@@ -216,6 +226,58 @@ __device__ __forceinline__ void collect_pairs(const RunParams& rp, const FrameGr
         HB_DASSERT(i >= 0 && i < 65536 && q > i && q < 65536);
         if (k < pair_cap) pairs[k] = (unsigned)i | ((unsigned)q << 16);
     });
+}
+
+// The two neighbour walks of the non-periodic fused path on 32-bit shared-window addresses (`cells_a`: 16-bit end offsets
+// per cell, `pts_a`: float4 points in cell order): the same walks as water_is_local / for_each_partner in hb_common.cuh,
+// but the generic-pointer forms make the compiler rebuild the shared-window base at every access of these short loops.
+__device__ __forceinline__ bool water_is_local_a(const FrameGrid& g, unsigned cells_a, unsigned pts_a, float x, float y, float z,
+                                                 const RunParams& rp) {
+    int cx, cy, cz;
+    cell3<false>(g, x, y, z, cx, cy, cz);
+    const int xl = max(cx - 1, 0), xh = min(cx + 1, g.nx - 1);
+    for (int zz = max(cz - 1, 0); zz <= min(cz + 1, g.nz - 1); ++zz)
+        for (int yy = max(cy - 1, 0); yy <= min(cy + 1, g.ny - 1); ++yy) {
+            const int row = (zz * g.ny + yy) * g.nx;
+            const int c_lo = row + xl;
+            const int s = c_lo ? (int)lds_u16(cells_a + 2u * (unsigned)(c_lo - 1)) : 0;
+            const int e = (int)lds_u16(cells_a + 2u * (unsigned)(row + xh));
+            for (int q = s; q < e; ++q) {
+                const float4 sp = lds_f4(pts_a + 16u * (unsigned)q);
+                if (dist2f(x, y, z, sp.x, sp.y, sp.z) <= rp.around2f_hi && dist_le(x, y, z, sp.x, sp.y, sp.z, rp.around2)) return true;
+            }
+        }
+    return false;
+}
+__device__ __forceinline__ void collect_pairs_a(const RunParams& rp, const FrameGrid& g, unsigned cells_a, unsigned pts_a, int i,
+                                                unsigned* pairs, int pair_cap, int* n_pairs) {
+    const float4 p = lds_f4(pts_a + 16u * (unsigned)i);
+    int cx, cy, cz;
+    cell3<false>(g, p.x, p.y, p.z, cx, cy, cz);
+    const int nx = g.nx, ny = g.ny, nz = g.nz;
+    const int xl = max(cx - 1, 0), xh = min(cx + 1, nx - 1);
+#pragma unroll 1
+    for (int run = 0; run < 5; ++run) {         // own cell + 13 forward cells as five contiguous runs
+        int s, e;
+        if (run == 0) {
+            s = i + 1;
+            e = (int)lds_u16(cells_a + 2u * (unsigned)((cz * ny + cy) * nx + xh));
+        } else {
+            const int yy = run == 1 ? cy + 1 : cy + (run - 3);
+            const int zz = run == 1 ? cz : cz + 1;
+            if (yy < 0 || yy >= ny || zz >= nz) continue;
+            const int row = (zz * ny + yy) * nx;
+            s = (row + xl) ? (int)lds_u16(cells_a + 2u * (unsigned)(row + xl - 1)) : 0;
+            e = (int)lds_u16(cells_a + 2u * (unsigned)(row + xh));
+        }
+        for (int q = s; q < e; ++q) {
+            const float4 q4 = lds_f4(pts_a + 16u * (unsigned)q);
+            if (dist2f(p.x, p.y, p.z, q4.x, q4.y, q4.z) > rp.r2f_hi || !dist_le(p.x, p.y, p.z, q4.x, q4.y, q4.z, rp.r2)) continue;
+            const int k = atomicAdd(n_pairs, 1);
+            HB_DASSERT(i >= 0 && i < 65536 && q > i && q < 65536);
+            if (k < pair_cap) pairs[k] = (unsigned)i | ((unsigned)q << 16);
+        }
+    }
 }
 
 template <bool PBC>
@@ -324,8 +386,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
     const unsigned last_bytes = (head + (unsigned)((nw_last - 1) * stride12 + 12) + 15u) & ~15u;
     const bool inside = stream && start0 >= lim_lo &&
                         start0 + (unsigned long long)(ntiles - 1) * tile_step + last_bytes <= lim_hi;
-    auto issue_tile = [&](int t) {      // one thread: copy tile t into its stage, pull a tile further ahead into L2
-        const int st = t % fc.stages;
+    auto issue_tile = [&](int t, int st) {      // one thread: copy tile t into stage st, pull a tile further ahead into L2 (any frame)
         unsigned char* dst = ring + (size_t)st * fc.stage_bytes;
         const unsigned long long src = start0 + (unsigned long long)t * tile_step;
         const unsigned bytes = t == ntiles - 1 ? last_bytes : full_bytes;
@@ -480,7 +541,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
         consumer_sync();
         phase_done(1);
         cta_mark(2);
-        if (stream && lane == 0 && warp < fc.stages && warp < ntiles) issue_tile(warp);
+        if (stream && lane == 0 && warp < fc.stages && warp < ntiles) issue_tile(warp, warp);
 
         const float a = rp.around_f;
         const float lox = sh->lo[0] - a, loy = sh->lo[1] - a, loz = sh->lo[2] - a;
@@ -524,6 +585,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
             const unsigned bar = full_a + 8u * (unsigned)st;
             const unsigned a = lane_a + (unsigned)st * fc.stage_bytes;
             unsigned par = 0u;
+            // refill of this warp's stage, frames inside the batch buffer: everything but the source address is loop invariant
+            const unsigned stage_a = smem_u32(ring) + (unsigned)st * fc.stage_bytes;
+            const unsigned long long src_step = (unsigned long long)fc.stages * tile_step;
+            const unsigned long long pf_dist = (unsigned long long)fc.prefetch * tile_step;
+            unsigned long long next_src = start0 + (unsigned long long)(warp + fc.stages) * tile_step;
             for (int t = warp; warp < fc.stages && t < ntiles; t += fc.stages, par ^= 1u) {
                 if (!mbar_try_wait_a(bar, par) && !mbar_wait_slow_a(bar, par, fc.wait_ns)) { ok = false; break; }
                 const int i0 = t * FUSED_TILE + lane;
@@ -546,7 +612,21 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
                 // The last load of every lane has returned when this vote completes (shared-memory loads of a warp return in
                 // order, and the vote needs the value): the stage is free, and one lane refills it before the tests.
                 asm volatile("{\n .reg .pred p, q;\n setp.eq.u32 p, %0, 0xffffffff;\n vote.sync.any.pred q, p, 0xffffffff;\n}" ::"r"(__float_as_uint(z[FUSED_WPL - 1])) : "memory");
-                if (lane == 0 && t + fc.stages < ntiles) issue_tile(t + fc.stages);
+                if (lane == 0 && t + fc.stages < ntiles) {
+                    const int u = t + fc.stages;
+                    if (inside) {
+                        const unsigned bytes = u == ntiles - 1 ? last_bytes : full_bytes;
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(stage_a),
+                                     "l"(next_src), "r"(bytes), "r"(bar) : "memory");
+                        if (fc.prefetch > 0 && u + fc.prefetch < ntiles)
+                            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(next_src + pf_dist),
+                                         "r"(u + fc.prefetch == ntiles - 1 ? last_bytes : tile_step) : "memory");
+                        next_src += src_step;
+                    } else {
+                        issue_tile(u, st);
+                    }
+                }
                 unsigned inb = 0u;
                 if (t == ntiles - 1) {
 #pragma unroll
@@ -638,6 +718,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
             consumer_sync();
         }
         b2_lap(1);
+        const unsigned cells_a = smem_u32(cells), sorted1_a = smem_u32(sorted1);
         for (int j0 = 0; j0 < ncand; j0 += FUSED_CONSUMERS) {
             const int j = j0 + tid;
             bool local = false;
@@ -654,7 +735,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
                     c = make_float4(f[0], f[1], f[2], __int_as_float(WATER_TAG | i));
                 }
                 b2_lap(2);
-                local = water_is_local<PBC>(g1, cells, sorted1, c.x, c.y, c.z, rp);
+                if constexpr (PBC) local = water_is_local<true>(g1, cells, sorted1, c.x, c.y, c.z, rp);
+                else local = water_is_local_a(g1, cells_a, sorted1_a, c.x, c.y, c.z, rp);
             }
             __syncwarp();
             b2_lap(3);
@@ -697,7 +779,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
     const float ct = rp.cos_threshold;
     // C1: every point walks its half shell and appends the point pairs within `distance` to one list
     for (int i = tid; i < np; i += FUSED_CONSUMERS) {
-        collect_pairs<PBC>(rp, g2, cells, psorted, i, pairs, fc.pair_cap, &sh->n_pairs);
+        if constexpr (PBC) collect_pairs<true>(rp, g2, cells, psorted, i, pairs, fc.pair_cap, &sh->n_pairs);
+        else collect_pairs_a(rp, g2, smem_u32(cells), smem_u32(psorted), i, pairs, fc.pair_cap, &sh->n_pairs);
         if (rp.self_pairs) {
             const float4 p4 = psorted[i];
             if (__float_as_int(p4.w) & SELF_TAG) {

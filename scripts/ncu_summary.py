@@ -43,6 +43,14 @@ def main():
             if w in d:
                 lines.append("| %s | %s | %s |" % (w, d[w], u[w]))
         lines.append("")
+        # warps per issued instruction waiting for each reason (the raw page's ratios; the per-line stall columns of the
+        # source page are not aligned between its cuda and sass rows)
+        pre, suf = "smsp__average_warps_issue_stalled_", "_per_issue_active.ratio"
+        st = sorted(((float(v), k[len(pre):-len(suf)]) for k, v in d.items() if k.startswith(pre) and k.endswith(suf) and v), reverse=True)
+        tot = sum(v for v, _ in st) or 1.0
+        lines += ["| stall reason | warps per issue | share |", "|---|---|---|"]
+        lines += ["| %s | %.2f | %.1f%% |" % (k, v, 100 * v / tot) for v, k in st[:10]]
+        lines.append("")
     src = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]))))
     cur, h, recs, stall = None, None, [], {}
     num = lambda x: int(x) if x.strip().lstrip("-").isdigit() else 0
@@ -62,9 +70,6 @@ def main():
     ti = max(1, sum(x[0] for x in recs))
     ts = max(1, sum(x[1] for x in recs))
     st = max(1, sum(stall.values()))
-    lines += ["## warp stall samples", "", "| reason | share |", "|---|---|"]
-    for name, v in sorted(stall.items(), key=lambda kv: -kv[1])[:8]:
-        lines.append("| %s | %.1f%% |" % (name, 100.0 * v / st))
     lines += ["", "## source lines by warp instructions executed (total %d)" % ti, "",
               "| inst | samples | file:line | source |", "|---|---|---|---|"]
     for x in sorted(recs, key=lambda x: -x[0])[:30]:
