@@ -93,7 +93,7 @@ struct hb_ctx {
     long long opt_fused_wait_ns = 100;
     long long opt_fused_prefetch = 2; // tiles prefetched into L2 ahead of the ring (more evicts lines before use)
     int opt_fused_sel_prefetch = 1;   // bulk L2 prefetch of the selection's atom block at the start of a frame
-    long long opt_fused_max_streams = 2; // frames of one SM that may stream at the same time (0 = no limit)
+    long long opt_fused_max_streams = 0; // frames of one SM that may stream at the same time (0 = no limit)
     int* d_sm_streams = nullptr;
     long long opt_fused_stagger = 125000; // cycles over which the first wave of fused CTAs spreads its start
     int opt_fused_debug = 0;          // measurement hook (results are wrong when set): see FusedCfg::debug
