@@ -143,7 +143,7 @@ __device__ __forceinline__ void mbar_arrive_a(unsigned bar) {
 }
 __device__ __forceinline__ float lds_f32(unsigned addr) {
     float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned lds_u16(unsigned addr) {
@@ -609,11 +609,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
                         }
                     }
                 }
-                // The last load of every lane has returned when this vote completes (shared-memory loads of a warp return in
-                // order, and the vote needs the value): the stage is free, and one lane refills it before the tests.
-                asm volatile("{\n .reg .pred p, q;\n setp.eq.u32 p, %0, 0xffffffff;\n vote.sync.any.pred q, p, 0xffffffff;\n}" ::"r"(__float_as_uint(z[FUSED_WPL - 1])) : "memory");
+                // Every lane's reads of the stage are ordered before the refill: the warp barrier orders the lanes' shared-memory
+                // accesses, and the proxy fence orders them before the bulk copy's writes (async proxy).
+                __syncwarp();
                 if (lane == 0 && t + fc.stages < ntiles) {
                     const int u = t + fc.stages;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     if (inside) {
                         const unsigned bytes = u == ntiles - 1 ? last_bytes : full_bytes;
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
