@@ -185,8 +185,11 @@ int hb_set_option(hb_ctx* ctx, const char* name, int64_t value);
         /* "batch_bytes": device budget per frame batch; "table_capacity": initial bond-table slots;
            "profile": 1 = time every kernel class with CUDA events; "max_batch_frames";
            "fused": 0 = never use the one-CTA-per-frame kernel; "fused_lw_cap" / "fused_cell_cap": its
-           shared-memory capacities (0 = automatic); "fused_pair_cap", "fused_stages", "fused_prefetch", "fused_wait_ns",
-           "fused_batch_frames"; "pair_buf_bytes": batch-wide pair buffer of the general kernels (0 = per-point kernel);
+           shared-memory capacities (0 = automatic); "fused_pair_cap", "fused_stages" (stages of its water-tile ring =
+           warps that stream, 2..8), "fused_prefetch" (tiles pulled into L2 ahead of the ring), "fused_wait_ns",
+           "fused_batch_frames", "fused_stagger" (cycles over which the first wave of its CTAs spreads its start, 0 = off),
+           "fused_sel_prefetch" (0 = no bulk L2 prefetch of the selection's atom block), "fused_max_streams" (frames
+           of one SM that may stream at the same time, 0 = no limit); "pair_buf_bytes": batch-wide pair buffer of the general kernels (0 = per-point kernel);
            "frame_pairs": 0 = never run the general path's pair search as one CTA per frame (hb_framepairs.cuh);
            "lw_smem": 0 = keep the selection grid of the general path's local-water test in global memory;
            "wire_edge_cap": H-bond pairs per frame the edge lists of the water-wire mode start with (doubles on
