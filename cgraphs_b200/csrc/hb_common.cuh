@@ -458,6 +458,26 @@ __device__ __forceinline__ void record_bond(const BondTable& bt, unsigned long l
     atomicExch(bt.overflow, 1);
 }
 
+// record_bond with the first probe already loaded (`cur` = bt.keys[h]): the fused kernel requests the probes of several
+// bonds together before it handles them
+__device__ __forceinline__ void record_bond_probed(const BondTable& bt, unsigned long long key, long long frame, unsigned h,
+                                                   unsigned long long cur) {
+    for (unsigned probe = 0; probe <= bt.mask; ++probe) {
+        if (probe) cur = bt.keys[h];
+        if (cur == EMPTY_KEY) {
+            cur = atomicCAS(&bt.keys[h], EMPTY_KEY, key);
+            if (cur == EMPTY_KEY) { atomicAdd(bt.n_keys, 1); cur = key; }
+        }
+        if (cur == key) {
+            HB_DASSERT(frame >= 0 && (frame >> 5) < bt.wpr && h <= bt.mask);
+            atomicOr(&bt.bits[(size_t)h * bt.wpr + (frame >> 5)], 1u << (frame & 31));
+            return;
+        }
+        h = (h + 1) & bt.mask;
+    }
+    atomicExch(bt.overflow, 1);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K7: pair search
 // ------------------------------------------------------------------------------------------------

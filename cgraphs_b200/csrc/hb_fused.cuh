@@ -417,12 +417,35 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
         }
     };
 
+    // the first tile of every stage is requested now, so that it lands while phase A runs (with the admission control on, it has
+    // to wait until the frame is admitted)
+    const bool early_issue = stream && fc.max_streams <= 0;
+    if (early_issue && lane == 0 && warp < fc.stages && warp < ntiles) issue_tile(warp, warp);
+
     // ---- phase A: selection points, bounding box, grids ------------------------------------------
     float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
-    for (int i = tid; i < nsel; i += FUSED_CONSUMERS) {
-        const float* p = xyz + 3ll * tp.sel_atom[s0 + i];
-        const int4 k = tp.sel_pack[s0 + i];
-        float x = p[0], y = p[1], z = p[2];
+    // two points per thread and trip: the atom indices are requested together, then the coordinates (two dependent round
+    // trips per trip instead of two per point)
+    for (int i0 = tid; i0 < nsel; i0 += 2 * FUSED_CONSUMERS) {
+        int at[2];
+        int4 kk4[2];
+        float cx4[2], cy4[2], cz4[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int i = i0 + j * FUSED_CONSUMERS;
+            if (i < nsel) { at[j] = tp.sel_atom[s0 + i]; kk4[j] = tp.sel_pack[s0 + i]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int i = i0 + j * FUSED_CONSUMERS;
+            if (i < nsel) { const float* p = xyz + 3ll * at[j]; cx4[j] = p[0]; cy4[j] = p[1]; cz4[j] = p[2]; }
+        }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int i = i0 + j * FUSED_CONSUMERS;
+        if (i >= nsel) break;
+        const int4 k = kk4[j];
+        float x = cx4[j], y = cy4[j], z = cz4[j];
         const int multi = (k.x >= 0) + (k.y >= 0) + ((wa && k.z >= 0) ? 1 : 0);
         spos[i] = make_float4(x, y, z, __int_as_float(i | (multi > 1 ? SELF_TAG : 0)));
         if constexpr (PBC) {   // fractional coordinates relative to the first selection point, wrapped
@@ -438,6 +461,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
         }
         mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
         mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
+    }
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k)
@@ -541,7 +565,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
         consumer_sync();
         phase_done(1);
         cta_mark(2);
-        if (stream && lane == 0 && warp < fc.stages && warp < ntiles) issue_tile(warp, warp);
+        if (stream && !early_issue && lane == 0 && warp < fc.stages && warp < ntiles) issue_tile(warp, warp);
 
         const float a = rp.around_f;
         const float lox = sh->lo[0] - a, loy = sh->lo[1] - a, loz = sh->lo[2] - a;
@@ -857,15 +881,30 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
             if (tid == 0) atomicExch(bt.fused_overflow, 1);
             return;
         }
-        for (int t = tid; t < ntasks; t += FUSED_CONSUMERS) {
-            const uint2 tk = tasks[t];
-            const unsigned kk = tk.x & 0xffffu, f = tk.x >> 16;
-            HB_DASSERT(kk < FUSED_CONSUMERS && f < 4u && (int)(base + kk) < npairs);
-            const unsigned pq = pairs[base + kk];
-            const float4 a4 = psorted[pq & 0xffffu], b4 = psorted[pq >> 16];
-            const float4 own = (f & 1u) ? b4 : a4, oth = (f & 1u) ? a4 : b4;
-            const float* h = xyz + 3ll * (long long)tk.y;
-            if (ang_ok<PBC>(oth.x, oth.y, oth.z, h[0], h[1], h[2], own.x, own.y, own.z, ct, g2.p.box)) atomicOr(&pflags[kk], 1u << f);
+        // three tasks per thread and trip: their hydrogen coordinates (L2 / DRAM) are requested together, so a chunk pays one
+        // round trip here instead of one per 256 tasks
+        for (int t0 = tid; t0 < ntasks; t0 += 3 * FUSED_CONSUMERS) {
+            uint2 tk[3];
+            float hx[3], hy[3], hz[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int t = t0 + j * FUSED_CONSUMERS;
+                if (t < ntasks) {
+                    tk[j] = tasks[t];
+                    const float* h = xyz + 3ll * (long long)tk[j].y;
+                    hx[j] = h[0]; hy[j] = h[1]; hz[j] = h[2];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                if (t0 + j * FUSED_CONSUMERS >= ntasks) break;
+                const unsigned kk = tk[j].x & 0xffffu, f = tk[j].x >> 16;
+                HB_DASSERT(kk < FUSED_CONSUMERS && f < 4u && (int)(base + kk) < npairs);
+                const unsigned pq = pairs[base + kk];
+                const float4 a4 = psorted[pq & 0xffffu], b4 = psorted[pq >> 16];
+                const float4 own = (f & 1u) ? b4 : a4, oth = (f & 1u) ? a4 : b4;
+                if (ang_ok<PBC>(oth.x, oth.y, oth.z, hx[j], hy[j], hz[j], own.x, own.y, own.z, ct, g2.p.box)) atomicOr(&pflags[kk], 1u << f);
+            }
         }
         phase_done(12);
         consumer_sync();
@@ -873,12 +912,58 @@ __global__ void __launch_bounds__(FUSED_THREADS, PBC ? 3 : 4) k_frame_fused(Batc
         // (c) entry pairs whose hydrogens passed
         if (have) {
             unsigned m = rules & rules_pass(pflags[tid]);
-            while (m) {
-                const int r = __ffs(m) - 1;
-                m &= m - 1;
-                int e0, e1;
-                rule_entries(P, Q, r, e0, e1);
-                emit(tp, rp, bt, frame, e0, e1, nhit);
+            if (bt.sink) {                              // water-wire mode: edges go to the per-frame lists
+                while (m) {
+                    const int r = __ffs(m) - 1;
+                    m &= m - 1;
+                    int e0, e1;
+                    rule_entries(P, Q, r, e0, e1);
+                    emit(tp, rp, bt, frame, e0, e1, nhit);
+                }
+            }
+            // Two entry pairs at a time (emit_bond of hb_common.cuh, hbond.py:119-127, in two steps): the entry tables of
+            // both are requested together, then the first probes of the bond table - two dependent round trips per trip
+            // instead of two per bond.
+            while (m && !bt.sink) {
+                unsigned long long key[2];
+                unsigned hs[2];
+                int ex[2], ey[2];
+                int nk = 0;
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    if (m) {
+                        const int r = __ffs(m) - 1;
+                        m &= m - 1;
+                        int e0, e1;
+                        rule_entries(P, Q, r, e0, e1);
+                        ex[j] = min(e0, e1); ey[j] = max(e0, e1);
+                        nk = j + 1;
+                    }
+                int pxx[2], pxy[2], pyx[2], pyy[2], gx[2], gy[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    if (j < nk) {
+                        const int4 px = tp.ent_pack[ex[j]], py = tp.ent_pack[ey[j]];
+                        pxx[j] = px.x; pxy[j] = px.y; pyx[j] = py.x; pyy[j] = py.y;
+                        gx[j] = tp.ent_group[ex[j]]; gy[j] = tp.ent_group[ey[j]];
+                    }
+                unsigned long long cur[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    key[j] = EMPTY_KEY;
+                    if (j < nk && (rp.check_angle || pxy[j] != pyy[j])) {          // hbond.py:125-127
+                        const bool chk = pxx[j] < pyx[j];                          // hbond.py:120-122
+                        key[j] = ((unsigned long long)(unsigned)(chk ? gx[j] : gy[j]) << 32) | (unsigned long long)(unsigned)(chk ? gy[j] : gx[j]);
+                        hs[j] = hash64(key[j]) & bt.mask;
+                        cur[j] = bt.keys[hs[j]];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+                    if (key[j] != EMPTY_KEY) {
+                        ++nhit;
+                        record_bond_probed(bt, key[j], frame, hs[j], cur[j]);
+                    }
             }
         }
         phase_done(14);
