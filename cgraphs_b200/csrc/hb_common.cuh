@@ -364,6 +364,7 @@ __device__ void make_grid(FrameGrid& g, const float* lo, const float* hi, float 
     }
     g.ox = lo[0] - pad; g.oy = lo[1] - pad; g.oz = lo[2] - pad;
     if (!finite) { g.inv = 0.f; g.nx = g.ny = g.nz = 1; g.ncell = 1; g.ox = g.oy = g.oz = 0.f; return; }
+#pragma unroll 1
     for (int it = 0; it < 64; ++it) {
         int n[3];
         double tot = 1.0;
@@ -413,6 +414,7 @@ __device__ void make_grid_pbc(FrameGrid& g, const Box6& B, const float* sR, cons
         }
     }
     int n[3] = {1, 1, 1};
+#pragma unroll 1
     for (int it = 0; it < 64; ++it) {
         double tot = 1.0;
         bool ok = true;

@@ -110,6 +110,7 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned pari
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
     for (;;) {
+#pragma unroll 1
         for (int k = 0; k < 64; ++k) {
             if (ns) __nanosleep(ns);
             if (mbar_try_wait(bar, parity)) return true;
@@ -131,6 +132,7 @@ __device__ __forceinline__ bool mbar_try_wait_a(unsigned bar, unsigned parity) {
 __device__ __noinline__ bool mbar_wait_slow_a(unsigned bar, unsigned parity, unsigned ns) {
     const long long t0 = clock64();
     for (;;) {
+#pragma unroll 1
         for (int k = 0; k < 64; ++k) {
             if (ns) __nanosleep(ns);
             if (mbar_try_wait_a(bar, parity)) return true;
