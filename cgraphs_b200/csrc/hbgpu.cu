@@ -29,6 +29,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <chrono>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -95,6 +96,8 @@ struct hb_ctx {
     int opt_fused_sel_prefetch = 1;   // bulk L2 prefetch of the selection's atom block at the start of a frame
     long long opt_fused_max_streams = 0; // frames of one SM that may stream at the same time (0 = no limit)
     int* d_sm_streams = nullptr;
+    long long occ_key = -1;           // resident fused CTAs per SM, cached per shared-memory plan
+    int occ_per_sm = 0;
     long long opt_fused_stagger = 125000; // cycles over which the first wave of fused CTAs spreads its start
     int opt_fused_debug = 0;          // measurement hook (results are wrong when set): see FusedCfg::debug
     int fused_grow = 0;
@@ -906,10 +909,19 @@ static bool plan_fused(hb_ctx* ctx, int grow = 0) {
     fc.off_near = (unsigned)off;    off += al16(((size_t)fc.cell_cap + 31) / 32 * 4);
     fc.smem_bytes = (unsigned)off;
     if (fc.smem_bytes > 112 * 1024) return false;                     // keep at least two frames resident per SM
-    if (cudaFuncSetAttribute(k_frame_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fc.smem_bytes) != cudaSuccess ||
-        cudaFuncSetAttribute(k_frame_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fc.smem_bytes) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
+    {   // the attribute belongs to the function (all contexts of the device share it): it is only ever raised
+        static std::mutex mu;
+        static long long attr_smem[64];
+        std::lock_guard<std::mutex> lock(mu);
+        const int d = ctx->device & 63;
+        if ((long long)fc.smem_bytes > attr_smem[d]) {
+            if (cudaFuncSetAttribute(k_frame_fused<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fc.smem_bytes) != cudaSuccess ||
+                cudaFuncSetAttribute(k_frame_fused<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fc.smem_bytes) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+            }
+            attr_smem[d] = (long long)fc.smem_bytes;
+        }
     }
     ctx->fc = fc;
     ctx->fused_grow = grow;
@@ -1221,9 +1233,15 @@ static int run_search(hb_ctx* ctx, const float* d_xyz, long long frame0, int nf,
         }
         fc.stagger = 0;
         if (ctx->opt_fused_stagger > 0) {
-            int per_sm = 0;
-            if (ctx->rp.pbc != HB_PBC_NONE) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame_fused<true>, FUSED_THREADS, fc.smem_bytes);
-            else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_frame_fused<false>, FUSED_THREADS, fc.smem_bytes);
+            const long long occ_key = (long long)fc.smem_bytes * 2 + (ctx->rp.pbc != HB_PBC_NONE ? 1 : 0);
+            if (ctx->occ_key != occ_key) {            // (asked once per shared-memory plan, not per launch)
+                int q = 0;
+                if (ctx->rp.pbc != HB_PBC_NONE) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k_frame_fused<true>, FUSED_THREADS, fc.smem_bytes);
+                else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, k_frame_fused<false>, FUSED_THREADS, fc.smem_bytes);
+                ctx->occ_per_sm = q;
+                ctx->occ_key = occ_key;
+            }
+            const int per_sm = ctx->occ_per_sm;
             fc.n_sm = (unsigned)ctx->prop.multiProcessorCount;
             fc.wave_ctas = (unsigned)std::max(per_sm, 1) * fc.n_sm;
             if ((long long)nf >= 2ll * fc.wave_ctas) fc.stagger = (unsigned)ctx->opt_fused_stagger;   // short launches: the delay would not pay
