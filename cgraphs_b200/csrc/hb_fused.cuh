@@ -6,20 +6,23 @@
 //   phase A  gather the selection points (<= sel_cap) into smem, bounding box, cell grid g1 (edge >= around_radius),
 //            counting sort, "near" bitmap: bit c is set iff some selection point lies in the 27-cell neighbourhood of cell c.
 //   phase B  the frame's water block streams through a ring of shared-memory stages with 1-D bulk async copies (TMA engine:
-//            cp.async.bulk + mbarrier complete_tx); a tile is 256 consecutive waters (O,H,H,O,H,H ... as they lie in the
-//            coordinate array), so HBM is read in large aligned bursts exactly once. Warp w < stages owns stage w and every
-//            stages-th tile: eight waters per lane, dilated-bounding-box test -> near-bitmap test -> the survivors'
+//            cp.async.bulk + mbarrier complete_tx); a tile is 32 x FUSED_WPL consecutive waters (O,H,H,O,H,H ... as they lie
+//            in the coordinate array), so HBM is read in large aligned bursts exactly once. Warp w < stages owns stage w and
+//            every stages-th tile: FUSED_WPL waters per lane, dilated-bounding-box test -> near-bitmap test -> the survivors'
 //            ("candidates") indices go to a CTA-wide list; the owner refills its stage as soon as it has read it.
 //   phase B2 candidates are tested densely against the 27 neighbouring g1 cells with the exact DIST predicate; local
 //            waters (hbond.py:249-252) are appended to a shared list.
-//   phase C  (consumers) cell grid g2 (edge >= distance) over selection + local waters; per block of 256
-//            points: half-shell walk collecting the point pairs that pass the exact DIST test into a pair
-//            list, then one thread per pair expands it into the reference's entry pairs, applies the
-//            exact ANG test over the hydrogen lists and records the bond (hash-table insert + frame bit).
+//   phase C  cell grid g2 (edge >= distance) over selection + local waters; half-shell walk collecting the point pairs
+//            that pass the exact DIST test into a pair list (C1), then per chunk of 256 pairs (C2): one thread per pair
+//            expands it into the reference's entry pairs and writes one task per hydrogen, one thread per task applies the
+//            exact ANG test, one thread per pair records the bonds (hash-table insert + frame bit). Loads that depend on
+//            each other through L2 / DRAM are requested several at a time (three tasks, two bonds, two points per trip):
+//            the number of dependent round trips per frame, times the loaded memory latency, is what a frame's life is made of.
 //
-// Several CTAs are resident per SM, so the gathers of phases A / C of one frame overlap the streaming
-// of others.  Frames that exceed the shared capacities (sel_cap / lw_cap / pair_cap) raise
-// `fused_overflow`; the host then re-runs the batch on the general path (hb_general.cuh).
+// Four CTAs are resident per SM, so the gathers of phases A / C of one frame overlap the streaming of others; the first
+// wave of a launch starts staggered (FusedCfg::stagger), otherwise frames that all cost the same stream and compute in
+// lock step.  Frames that exceed the shared capacities (sel_cap / lw_cap / pair_cap) raise `fused_overflow`; the host
+// then re-runs the batch with doubled capacities or on the general path (hb_general.cuh).
 #pragma once
 #include "hb_common.cuh"
 
@@ -43,7 +46,7 @@ struct FusedCfg {
     int task_cap;             // hydrogens to test per chunk of 256 pairs
     int regular;              // 1: water point i is atom w_first + i * w_stride in every system -> TMA tiles
     int w_stride;             // atoms between consecutive water oxygens
-    int stages;               // ring depth
+    int stages;               // stages of the ring = warps that stream (one stage each)
     int prefetch;             // tiles pulled into L2 ahead of the ring
     unsigned wait_ns;         // sleep between two polls of a barrier
     unsigned stage_bytes;     // bytes of one stage (multiple of 16)
@@ -71,7 +74,6 @@ struct FusedShared {          // small fixed part at the start of dynamic shared
     int n_tasks;
     int overflow;
     int warp_sum[FUSED_CWARPS];
-    unsigned stage_head[FUSED_MAX_STAGES];   // 1: the tile touches the edge of the batch buffer (only [lo, hi) was copied)
     unsigned stage_lo[FUSED_MAX_STAGES];     // [lo, hi): bytes of the stage the bulk copy filled
     unsigned stage_hi[FUSED_MAX_STAGES];
 };
@@ -92,34 +94,10 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes or ~1 us passed,
-// instead of burning issue slots in a polling loop
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
-    unsigned ok;
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(1000u)
-        : "memory");
-    return ok != 0;
-}
-// bounded wait (about a second): a lost copy must never hang the GPU; the caller flags the frame instead.
-// Between polls the warp sleeps `ns` nanoseconds: a polling warp would otherwise take issue slots from the
-// warps of the other resident frames that have work to do.
-__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, unsigned parity, unsigned ns) {
-    if (mbar_try_wait(bar, parity)) return true;
-    const long long t0 = clock64();
-    for (;;) {
-#pragma unroll 1
-        for (int k = 0; k < 64; ++k) {
-            if (ns) __nanosleep(ns);
-            if (mbar_try_wait(bar, parity)) return true;
-        }
-        if (clock64() - t0 > 2000000000ll) return false;
-    }
-}
-// the same on 32-bit shared-window addresses computed once outside a loop (the generic-pointer forms above make the
-// compiler rebuild the shared-window base - S2R SR_CgaCtaId, LEA - at every use)
+// Waits take 32-bit shared-window addresses computed once outside the loop (the generic-pointer forms make the compiler
+// rebuild the shared-window base - S2R SR_CgaCtaId, LEA - at every use). try_wait carries a suspend-time hint: the warp
+// sleeps in hardware until the phase completes or ~1 us passed. The slow path is bounded (about a second): a lost copy
+// must never hang the GPU, the caller flags the frame instead; between its polls the warp sleeps `ns` nanoseconds.
 __device__ __forceinline__ bool mbar_try_wait_a(unsigned bar, unsigned parity) {
     unsigned ok;
     asm volatile(
